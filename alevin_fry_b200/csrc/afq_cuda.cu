@@ -1,0 +1,577 @@
+// afq_cuda.cu — C-ABI implementation (include/afq.h) over the sm_100a kernels.
+//
+// One afq_ctx per GPU. The device API (afq_quant_device) enqueues the whole per-batch
+// pipeline on the caller's stream without host synchronisation:
+//   memset(ctl) -> k_bin_cells -> k_resolve_smem<0..5> (persistent, one launch per arena
+//   size) -> k_resolve_large -> row scan (3 launches) -> k_gather_rows
+// The host API (afq_submit / afq_wait) wraps it with pinned-buffer H2D / D2H copies on a
+// separate copy stream so that batch k+1 uploads while batch k computes.
+// There is NO CPU fallback: without a usable CUDA device afq_create fails.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/afq.h"
+#include "afq_kernels.cuh"
+#include "afq_pug.cuh"
+
+using namespace afq;
+
+namespace {
+
+thread_local std::string g_create_err;
+
+#define CUDA_TRY(ctx, expr)                                                              \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                   \
+      return AFQ_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+
+template <class T>
+struct DBuf {  // grow-only device buffer
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    size_t want = n + n / 8 + 64;
+    cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+    cap = (e == cudaSuccess) ? want : 0;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+template <class T>
+struct HBuf {  // grow-only pinned host buffer
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    size_t want = n + n / 8 + 64;
+    cudaError_t e = cudaHostAlloc((void**)&p, want * sizeof(T), cudaHostAllocDefault);
+    cap = (e == cudaSuccess) ? want : 0;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct Work {  // per-pipeline scratch (ordered on one stream)
+  DBuf<Ctl> ctl;
+  DBuf<u32> bin_list;
+  DBuf<u32> stage_col;
+  DBuf<float> stage_val;
+  DBuf<u64> tile_sums;
+  PugWork pug;
+  cudaError_t ensure(u64 n_cells, u64 n_refs) {
+    cudaError_t e;
+    if ((e = ctl.ensure(1)) != cudaSuccess) return e;
+    if ((e = bin_list.ensure((size_t)NUM_BINS * n_cells)) != cudaSuccess) return e;
+    if ((e = stage_col.ensure(n_refs + 1)) != cudaSuccess) return e;
+    if ((e = stage_val.ensure(n_refs + 1)) != cudaSuccess) return e;
+    if ((e = tile_sums.ensure(n_cells / SCAN_TILE + 2)) != cudaSuccess) return e;
+    return cudaSuccess;
+  }
+  void release() {
+    ctl.release(); bin_list.release(); stage_col.release(); stage_val.release();
+    tile_sums.release(); pug.release();
+  }
+};
+
+struct Slot {  // one in-flight host batch
+  DBuf<u64> cell_rec_off;
+  DBuf<u32> umi, ref_off, refs;
+  DBuf<u64> row_ptr;
+  DBuf<u32> col;
+  DBuf<float> val, sum_umi, max_umi;
+  DBuf<u32> num_expr, num_over_mean;
+  DBuf<u8> flags;
+  HBuf<u64> h_row_ptr;
+  HBuf<u32> h_col, h_num_expr, h_num_over_mean;
+  HBuf<float> h_val, h_sum, h_max;
+  HBuf<u8> h_flags;
+  HBuf<Ctl> h_ctl;
+  cudaEvent_t ev_h2d = nullptr, ev_done = nullptr;
+  u64 n_cells = 0, n_refs = 0, ticket = 0;
+  bool busy = false;
+  void release() {
+    cell_rec_off.release(); umi.release(); ref_off.release(); refs.release();
+    row_ptr.release(); col.release(); val.release(); sum_umi.release(); max_umi.release();
+    num_expr.release(); num_over_mean.release(); flags.release();
+    h_row_ptr.release(); h_col.release(); h_num_expr.release(); h_num_over_mean.release();
+    h_val.release(); h_sum.release(); h_max.release(); h_flags.release(); h_ctl.release();
+    if (ev_h2d) cudaEventDestroy(ev_h2d);
+    if (ev_done) cudaEventDestroy(ev_done);
+  }
+};
+
+struct ProfRec { int kid; cudaEvent_t a, b; };
+constexpr int NUM_KID = 16;
+const char* const KID_NAMES[NUM_KID] = {
+    "k_bin_cells", "k_resolve_smem<0>", "k_resolve_smem<1>", "k_resolve_smem<2>",
+    "k_resolve_smem<3>", "k_resolve_smem<4>", "k_resolve_smem<5>", "k_resolve_large",
+    "k_scan_tile_sums", "k_scan_tiles", "k_scan_rows", "k_gather_rows",
+    "k_pug_cell", "k_em_cell", "k_geq_finish", "other"};
+
+}  // namespace
+
+struct afq_ctx {
+  afq_config cfg{};
+  int device = 0;
+  int num_sms = 0;
+  u32* d_t2g = nullptr;
+  u64 n_refs = 0;
+  std::string err;
+  u64 launches = 0;
+  // giant-cell scratch
+  u64* large_keys = nullptr;
+  u32* large_cnts = nullptr;
+  u32 large_cap_log2 = 22;
+  u32 large_blocks = 32;
+  int force_bin = -1;
+  int grid_smem[NUM_SMEM_BINS] = {0};
+  // pipelines
+  Work work_dev, work_host;
+  static constexpr int NSLOT = 3;
+  Slot slots[NSLOT];
+  cudaStream_t s_copy = nullptr, s_compute = nullptr, s_d2h = nullptr;
+  u64 next_ticket = 1;
+  std::mutex mu;
+  // profiling
+  bool profiling = false;
+  std::vector<ProfRec> prof;
+  double kid_ms[NUM_KID] = {0};
+  u64 kid_launches[NUM_KID] = {0};
+  Ctl* h_ctl_dev = nullptr;  // pinned, for afq_device_finish
+};
+
+namespace {
+
+struct ProfScope {
+  afq_ctx* c; int kid; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
+  ProfScope(afq_ctx* c_, int kid_, cudaStream_t st_) : c(c_), kid(kid_), st(st_) {
+    c->launches++;
+    c->kid_launches[kid]++;
+    if (c->profiling) {
+      cudaEventCreate(&a); cudaEventCreate(&b);
+      cudaEventRecord(a, st);
+    }
+  }
+  ~ProfScope() {
+    if (c->profiling) { cudaEventRecord(b, st); c->prof.push_back({kid, a, b}); }
+  }
+};
+
+template <int BIN>
+int setup_bin(afq_ctx* c) {
+  const size_t smem = (size_t)12 << bin_cap_log2(BIN);
+  CUDA_TRY(c, cudaFuncSetAttribute(k_resolve_smem<BIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+  int occ = 0;
+  CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_resolve_smem<BIN>,
+                                                            (int)bin_threads(BIN), smem));
+  if (occ < 1) occ = 1;
+  c->grid_smem[BIN] = occ * c->num_sms;
+  return AFQ_OK;
+}
+
+template <int BIN>
+void launch_bin(afq_ctx* c, const KArgs& a, cudaStream_t st) {
+  ProfScope ps(c, 1 + BIN, st);
+  const size_t smem = (size_t)12 << bin_cap_log2(BIN);
+  k_resolve_smem<BIN><<<c->grid_smem[BIN], bin_threads(BIN), smem, st>>>(a);
+}
+
+bool is_pug_resolution(int r) {
+  return r == AFQ_RES_PARSIMONY || r == AFQ_RES_PARSIMONY_EM || r == AFQ_RES_PARSIMONY_GENE ||
+         r == AFQ_RES_PARSIMONY_GENE_EM;
+}
+bool is_em_resolution(int r) {
+  return r == AFQ_RES_CR_LIKE_EM || r == AFQ_RES_PARSIMONY_EM || r == AFQ_RES_PARSIMONY_GENE_EM;
+}
+
+// Enqueue the full device pipeline for one batch. All pointers are device pointers.
+int run_pipeline(afq_ctx* c, Work& w, const afq_batch& b, const afq_device_out& o, cudaStream_t st) {
+  if (b.n_cells == 0) {
+    CUDA_TRY(c, cudaMemsetAsync(o.row_ptr, 0, sizeof(u64), st));
+    return AFQ_OK;
+  }
+  if (b.n_cells >= 0xFFFFFFF0ull || b.n_refs_total >= 0xFFFFFFF0ull || b.n_records >= 0xFFFFFFF0ull) {
+    c->err = "batch too large: n_cells, n_records and n_refs_total must be < 2^32 (split the batch)";
+    return AFQ_ERR_INVALID;
+  }
+  if (o.cap_cells < b.n_cells + 1 || o.cap_nnz < b.n_refs_total) {
+    c->err = "afq_device_out capacities too small (need n_cells+1 rows and n_refs_total nnz)";
+    return AFQ_ERR_INVALID;
+  }
+  CUDA_TRY(c, w.ensure(b.n_cells, b.n_refs_total));
+  KArgs a{};
+  a.n_cells = b.n_cells;
+  a.cell_rec_off = b.cell_rec_offsets;
+  a.umi = b.rec_umi32;
+  a.ref_off = b.rec_ref_offsets;
+  a.refs = b.refs;
+  a.t2g = c->d_t2g;
+  a.mode = (c->cfg.resolution == AFQ_RES_TRIVIAL) ? MODE_TRIVIAL : MODE_CRLIKE;
+  a.usa_mode = c->cfg.usa_mode ? 1u : 0u;
+  a.num_rows = c->cfg.num_rows;
+  a.uo = c->cfg.usa_mode ? c->cfg.num_rows / 3 : 0;
+  a.ao = 2 * a.uo;
+  a.small_thresh = c->cfg.small_thresh;
+  a.tiny_eligible = c->cfg.sa_model == AFQ_SA_WINNER_TAKE_ALL ? 1u : 0u;
+  a.ctl = w.ctl.p;
+  a.bin_list = w.bin_list.p;
+  a.stage_col = w.stage_col.p;
+  a.stage_val = w.stage_val.p;
+  a.sum_umi = o.sum_umi;
+  a.max_umi = o.max_umi;
+  a.num_expr = o.num_expr;
+  a.num_over_mean = o.num_over_mean;
+  a.flags = o.flags;
+  a.large_keys = c->large_keys;
+  a.large_cnts = c->large_cnts;
+  a.large_cap_log2 = c->large_cap_log2;
+
+  CUDA_TRY(c, cudaMemsetAsync(w.ctl.p, 0, sizeof(Ctl), st));
+  const int res = c->cfg.resolution;
+  if (res == AFQ_RES_CR_LIKE || res == AFQ_RES_TRIVIAL) {
+    {
+      ProfScope ps(c, 0, st);
+      k_bin_cells<<<(unsigned)((b.n_cells + 255) / 256), 256, 0, st>>>(a, c->force_bin);
+    }
+    launch_bin<0>(c, a, st);
+    launch_bin<1>(c, a, st);
+    launch_bin<2>(c, a, st);
+    launch_bin<3>(c, a, st);
+    launch_bin<4>(c, a, st);
+    launch_bin<5>(c, a, st);
+    {
+      ProfScope ps(c, 7, st);
+      k_resolve_large<<<c->large_blocks, 1024, 0, st>>>(a);
+    }
+  } else {
+    // cr-like-em and the parsimony family: tiny cells keep the cr-like fast path
+    // (src/quant.rs:794-846); every other cell goes through the PUG / EM kernels.
+    int rc = run_pug_em_pipeline(c->cfg, c->num_sms, c->force_bin, a, w.pug, b, st,
+                                 [&](int kid) { c->launches++; c->kid_launches[kid]++; }, c->err);
+    if (rc != AFQ_OK) return rc;
+  }
+  CUDA_TRY(c, cudaGetLastError());
+
+  const u32 n_tiles = (u32)((b.n_cells + SCAN_TILE - 1) / SCAN_TILE);
+  {
+    ProfScope ps(c, 8, st);
+    k_scan_tile_sums<<<n_tiles, 1024, 0, st>>>(o.num_expr, b.n_cells, w.tile_sums.p);
+  }
+  {
+    ProfScope ps(c, 9, st);
+    k_scan_tiles<<<1, 1024, 0, st>>>(w.tile_sums.p, n_tiles, o.row_ptr, b.n_cells);
+  }
+  {
+    ProfScope ps(c, 10, st);
+    k_scan_rows<<<n_tiles, 1024, 0, st>>>(o.num_expr, b.n_cells, w.tile_sums.p, o.row_ptr);
+  }
+  {
+    ProfScope ps(c, 11, st);
+    k_gather_rows<<<(unsigned)((b.n_cells * 32 + 255) / 256), 256, 0, st>>>(a, o.row_ptr, o.col, o.val);
+  }
+  CUDA_TRY(c, cudaGetLastError());
+  return AFQ_OK;
+}
+
+int check_device_error(afq_ctx* c, const Ctl& h) {
+  if (h.error & DEV_ERR_CELL_TOO_LARGE) {
+    c->err = "a cell has " + std::to_string(h.max_cell_refs) +
+             " alignments, more than the giant-cell arena holds (raise AFQ_LARGE_CAP_LOG2)";
+    return AFQ_ERR_UNSUPPORTED;
+  }
+  if (h.error) {
+    c->err = "device-side error flags " + std::to_string(h.error);
+    return AFQ_ERR_INTERNAL;
+  }
+  return AFQ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int afq_abi_version(void) { return AFQ_ABI_VERSION; }
+
+const char* afq_last_error(const afq_ctx* ctx) {
+  return ctx ? ctx->err.c_str() : g_create_err.c_str();
+}
+
+int afq_create(const afq_config* cfg, const uint32_t* tid_to_gid, uint64_t n_refs, afq_ctx** out) {
+  if (!cfg || !tid_to_gid || !out || n_refs == 0) { g_create_err = "afq_create: null argument"; return AFQ_ERR_INVALID; }
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_err = std::string("no CUDA device available (") +
+                   (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+                   "); the afq product path has no CPU fallback";
+    return AFQ_ERR_NO_DEVICE;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) { g_create_err = "afq_create: bad device ordinal"; return AFQ_ERR_INVALID; }
+  if (cfg->umi_len > 16) { g_create_err = "umi_len > 16 is not supported on the CUDA path (UMI packed in 32 bits)"; return AFQ_ERR_UNSUPPORTED; }
+  if (cfg->sa_model != AFQ_SA_WINNER_TAKE_ALL) { g_create_err = "--sa-model prefer-ambig is not implemented on the CUDA path"; return AFQ_ERR_UNSUPPORTED; }
+  if (cfg->resolution < AFQ_RES_TRIVIAL || cfg->resolution > AFQ_RES_PARSIMONY_GENE) { g_create_err = "bad resolution"; return AFQ_ERR_INVALID; }
+  if (cfg->usa_mode && (cfg->num_rows % 3 != 0)) { g_create_err = "USA mode needs num_rows = 3G"; return AFQ_ERR_INVALID; }
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, cfg->device)) != cudaSuccess) { g_create_err = cudaGetErrorString(e); return AFQ_ERR_CUDA; }
+  if (prop.major < 10) {
+    g_create_err = std::string("device ") + prop.name + " is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                   "; this library is built for sm_100a only";
+    return AFQ_ERR_NO_DEVICE;
+  }
+  auto* c = new afq_ctx();
+  c->cfg = *cfg;
+  c->device = cfg->device;
+  c->num_sms = prop.multiProcessorCount;
+  c->n_refs = n_refs;
+  if (const char* s = getenv("AFQ_LARGE_CAP_LOG2")) c->large_cap_log2 = (u32)atoi(s);
+  if (const char* s = getenv("AFQ_LARGE_BLOCKS")) c->large_blocks = (u32)atoi(s);
+  if (const char* s = getenv("AFQ_FORCE_BIN")) c->force_bin = atoi(s);
+  if (c->large_cap_log2 < 10) c->large_cap_log2 = 10;
+  if (c->large_cap_log2 > 30) c->large_cap_log2 = 30;
+  if (c->large_blocks < 1) c->large_blocks = 1;
+  auto fail = [&](int code) { g_create_err = c->err; afq_destroy(c); return code; };
+#define CREATE_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { c->err = std::string(#expr) + ": " + cudaGetErrorString(_e); return fail(AFQ_ERR_CUDA); } } while (0)
+  CREATE_TRY(cudaSetDevice(c->device));
+  CREATE_TRY(cudaMalloc((void**)&c->d_t2g, n_refs * sizeof(u32)));
+  CREATE_TRY(cudaMemcpy(c->d_t2g, tid_to_gid, n_refs * sizeof(u32), cudaMemcpyHostToDevice));
+  const size_t large_entries = (size_t)c->large_blocks << c->large_cap_log2;
+  CREATE_TRY(cudaMalloc((void**)&c->large_keys, large_entries * sizeof(u64)));
+  CREATE_TRY(cudaMalloc((void**)&c->large_cnts, large_entries * sizeof(u32)));
+  CREATE_TRY(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
+  CREATE_TRY(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
+  CREATE_TRY(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+  CREATE_TRY(cudaHostAlloc((void**)&c->h_ctl_dev, sizeof(Ctl), cudaHostAllocDefault));
+  for (auto& s : c->slots) {
+    CREATE_TRY(cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
+    CREATE_TRY(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+  }
+#undef CREATE_TRY
+  int rc;
+  if ((rc = setup_bin<0>(c)) || (rc = setup_bin<1>(c)) || (rc = setup_bin<2>(c)) ||
+      (rc = setup_bin<3>(c)) || (rc = setup_bin<4>(c)) || (rc = setup_bin<5>(c)))
+    return fail(rc);
+  std::string perr;
+  if ((rc = pug_em_setup(c->num_sms, perr)) != AFQ_OK) { c->err = perr; return fail(rc); }
+  *out = c;
+  return AFQ_OK;
+}
+
+void afq_destroy(afq_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (auto& p : c->prof) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+  c->work_dev.release();
+  c->work_host.release();
+  for (auto& s : c->slots) s.release();
+  if (c->d_t2g) cudaFree(c->d_t2g);
+  if (c->large_keys) cudaFree(c->large_keys);
+  if (c->large_cnts) cudaFree(c->large_cnts);
+  if (c->h_ctl_dev) cudaFreeHost(c->h_ctl_dev);
+  if (c->s_copy) cudaStreamDestroy(c->s_copy);
+  if (c->s_compute) cudaStreamDestroy(c->s_compute);
+  if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
+  delete c;
+}
+
+int afq_quant_device(afq_ctx* c, const afq_batch* b, const afq_device_out* o, void* stream) {
+  if (!c || !b || !o) return AFQ_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  return run_pipeline(c, c->work_dev, *b, *o, (cudaStream_t)stream);
+}
+
+int afq_device_finish(afq_ctx* c, void* stream, uint64_t* nnz, const uint64_t* dev_row_ptr,
+                      uint64_t n_cells) {
+  if (!c) return AFQ_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (c->work_dev.ctl.p)
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_ctl_dev, c->work_dev.ctl.p, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
+  else
+    memset(c->h_ctl_dev, 0, sizeof(Ctl));
+  u64 h_nnz = 0;
+  if (nnz && dev_row_ptr)
+    CUDA_TRY(c, cudaMemcpyAsync(&h_nnz, dev_row_ptr + n_cells, sizeof(u64), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(c, cudaStreamSynchronize(st));
+  if (nnz) *nnz = h_nnz;
+  return check_device_error(c, *c->h_ctl_dev);
+}
+
+int afq_submit(afq_ctx* c, const afq_batch* hb, uint64_t* ticket) {
+  if (!c || !hb || !ticket) return AFQ_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  if (hb->n_cells >= 0xFFFFFFF0ull || hb->n_refs_total >= 0xFFFFFFF0ull || hb->n_records >= 0xFFFFFFF0ull) {
+    c->err = "batch too large: n_cells, n_records and n_refs_total must be < 2^32 (split the batch)";
+    return AFQ_ERR_INVALID;
+  }
+  const u64 t = c->next_ticket;
+  Slot& s = c->slots[t % afq_ctx::NSLOT];
+  if (s.busy) {
+    c->err = "too many batches in flight (at most " + std::to_string(afq_ctx::NSLOT) + "): call afq_wait first";
+    return AFQ_ERR_INVALID;
+  }
+  const u64 nc = hb->n_cells, nr = hb->n_records, nf = hb->n_refs_total;
+  CUDA_TRY(c, s.cell_rec_off.ensure(nc + 1));
+  CUDA_TRY(c, s.umi.ensure(nr + 1));
+  CUDA_TRY(c, s.ref_off.ensure(nr + 1));
+  CUDA_TRY(c, s.refs.ensure(nf + 1));
+  CUDA_TRY(c, s.row_ptr.ensure(nc + 1));
+  CUDA_TRY(c, s.col.ensure(nf + 1));
+  CUDA_TRY(c, s.val.ensure(nf + 1));
+  CUDA_TRY(c, s.sum_umi.ensure(nc + 1));
+  CUDA_TRY(c, s.max_umi.ensure(nc + 1));
+  CUDA_TRY(c, s.num_expr.ensure(nc + 1));
+  CUDA_TRY(c, s.num_over_mean.ensure(nc + 1));
+  CUDA_TRY(c, s.flags.ensure(nc + 1));
+  CUDA_TRY(c, s.h_row_ptr.ensure(nc + 1));
+  CUDA_TRY(c, s.h_sum.ensure(nc + 1));
+  CUDA_TRY(c, s.h_max.ensure(nc + 1));
+  CUDA_TRY(c, s.h_num_expr.ensure(nc + 1));
+  CUDA_TRY(c, s.h_num_over_mean.ensure(nc + 1));
+  CUDA_TRY(c, s.h_flags.ensure(nc + 1));
+  CUDA_TRY(c, s.h_ctl.ensure(1));
+  // H2D on the copy stream (overlaps the previous batch's kernels)
+  CUDA_TRY(c, cudaMemcpyAsync(s.cell_rec_off.p, hb->cell_rec_offsets, (nc + 1) * sizeof(u64), cudaMemcpyHostToDevice, c->s_copy));
+  if (nr) CUDA_TRY(c, cudaMemcpyAsync(s.umi.p, hb->rec_umi32, nr * sizeof(u32), cudaMemcpyHostToDevice, c->s_copy));
+  CUDA_TRY(c, cudaMemcpyAsync(s.ref_off.p, hb->rec_ref_offsets, (nr + 1) * sizeof(u32), cudaMemcpyHostToDevice, c->s_copy));
+  if (nf) CUDA_TRY(c, cudaMemcpyAsync(s.refs.p, hb->refs, nf * sizeof(u32), cudaMemcpyHostToDevice, c->s_copy));
+  CUDA_TRY(c, cudaEventRecord(s.ev_h2d, c->s_copy));
+  CUDA_TRY(c, cudaStreamWaitEvent(c->s_compute, s.ev_h2d, 0));
+  afq_batch db = *hb;
+  db.cell_rec_offsets = s.cell_rec_off.p;
+  db.rec_umi32 = s.umi.p;
+  db.rec_ref_offsets = s.ref_off.p;
+  db.refs = s.refs.p;
+  afq_device_out o{};
+  o.row_ptr = s.row_ptr.p; o.cap_cells = nc + 1;
+  o.col = s.col.p; o.val = s.val.p; o.cap_nnz = nf + 1;
+  o.sum_umi = s.sum_umi.p; o.max_umi = s.max_umi.p;
+  o.num_expr = s.num_expr.p; o.num_over_mean = s.num_over_mean.p; o.flags = s.flags.p;
+  int rc = run_pipeline(c, c->work_host, db, o, c->s_compute);
+  if (rc != AFQ_OK) return rc;
+  // small per-cell results come back on the compute stream right behind the kernels
+  CUDA_TRY(c, cudaMemcpyAsync(s.h_row_ptr.p, s.row_ptr.p, (nc + 1) * sizeof(u64), cudaMemcpyDeviceToHost, c->s_compute));
+  if (nc) {
+    CUDA_TRY(c, cudaMemcpyAsync(s.h_sum.p, s.sum_umi.p, nc * sizeof(float), cudaMemcpyDeviceToHost, c->s_compute));
+    CUDA_TRY(c, cudaMemcpyAsync(s.h_max.p, s.max_umi.p, nc * sizeof(float), cudaMemcpyDeviceToHost, c->s_compute));
+    CUDA_TRY(c, cudaMemcpyAsync(s.h_num_expr.p, s.num_expr.p, nc * sizeof(u32), cudaMemcpyDeviceToHost, c->s_compute));
+    CUDA_TRY(c, cudaMemcpyAsync(s.h_num_over_mean.p, s.num_over_mean.p, nc * sizeof(u32), cudaMemcpyDeviceToHost, c->s_compute));
+    CUDA_TRY(c, cudaMemcpyAsync(s.h_flags.p, s.flags.p, nc * sizeof(u8), cudaMemcpyDeviceToHost, c->s_compute));
+    CUDA_TRY(c, cudaMemcpyAsync(s.h_ctl.p, c->work_host.ctl.p, sizeof(Ctl), cudaMemcpyDeviceToHost, c->s_compute));
+  } else {
+    memset(s.h_ctl.p, 0, sizeof(Ctl));
+  }
+  CUDA_TRY(c, cudaEventRecord(s.ev_done, c->s_compute));
+  s.n_cells = nc; s.n_refs = nf; s.ticket = t; s.busy = true;
+  c->next_ticket++;
+  *ticket = t;
+  return AFQ_OK;
+}
+
+int afq_wait(afq_ctx* c, uint64_t ticket, afq_result* out) {
+  if (!c || !out) return AFQ_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  Slot& s = c->slots[ticket % afq_ctx::NSLOT];
+  if (!s.busy || s.ticket != ticket) { c->err = "afq_wait: unknown or already-collected ticket"; return AFQ_ERR_INVALID; }
+  CUDA_TRY(c, cudaEventSynchronize(s.ev_done));
+  int rc = check_device_error(c, *s.h_ctl.p);
+  if (rc != AFQ_OK) { s.busy = false; return rc; }
+  const u64 nnz = s.h_row_ptr.p[s.n_cells];
+  CUDA_TRY(c, s.h_col.ensure(nnz + 1));
+  CUDA_TRY(c, s.h_val.ensure(nnz + 1));
+  if (nnz) {
+    CUDA_TRY(c, cudaMemcpyAsync(s.h_col.p, s.col.p, nnz * sizeof(u32), cudaMemcpyDeviceToHost, c->s_d2h));
+    CUDA_TRY(c, cudaMemcpyAsync(s.h_val.p, s.val.p, nnz * sizeof(float), cudaMemcpyDeviceToHost, c->s_d2h));
+    CUDA_TRY(c, cudaStreamSynchronize(c->s_d2h));
+  }
+  out->n_cells = s.n_cells;
+  out->nnz = nnz;
+  out->row_ptr = s.h_row_ptr.p;
+  out->col = s.h_col.p;
+  out->val = s.h_val.p;
+  out->sum_umi = s.h_sum.p;
+  out->max_umi = s.h_max.p;
+  out->num_expr = s.h_num_expr.p;
+  out->num_over_mean = s.h_num_over_mean.p;
+  out->flags = s.h_flags.p;
+  return AFQ_OK;
+}
+
+void afq_result_release(afq_ctx* c, afq_result* res) {
+  if (!c || !res) return;
+  std::lock_guard<std::mutex> lk(c->mu);
+  for (auto& s : c->slots)
+    if (s.busy && s.h_row_ptr.p == res->row_ptr) s.busy = false;
+  memset(res, 0, sizeof(*res));
+}
+
+int afq_host_alloc(void** ptr, size_t bytes) {
+  if (!ptr) return AFQ_ERR_INVALID;
+  cudaError_t e = cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault);
+  return e == cudaSuccess ? AFQ_OK : AFQ_ERR_CUDA;
+}
+void afq_host_free(void* ptr) { if (ptr) cudaFreeHost(ptr); }
+
+uint64_t afq_launch_count(const afq_ctx* c) { return c ? c->launches : 0; }
+
+int afq_set_profiling(afq_ctx* c, int enable) {
+  if (!c) return AFQ_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  c->profiling = enable != 0;
+  return AFQ_OK;
+}
+
+// Drain the recorded CUDA-event pairs into per-kernel totals (synchronises the device).
+int afq_profile_collect(afq_ctx* c) {
+  if (!c) return AFQ_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  CUDA_TRY(c, cudaDeviceSynchronize());
+  for (auto& p : c->prof) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) c->kid_ms[p.kid] += ms;
+    cudaEventDestroy(p.a); cudaEventDestroy(p.b);
+  }
+  c->prof.clear();
+  return AFQ_OK;
+}
+
+int afq_profile_reset(afq_ctx* c) {
+  if (!c) return AFQ_ERR_INVALID;
+  int rc = afq_profile_collect(c);
+  std::lock_guard<std::mutex> lk(c->mu);
+  for (int i = 0; i < NUM_KID; ++i) { c->kid_ms[i] = 0; c->kid_launches[i] = 0; }
+  return rc;
+}
+
+// idx-th kernel's accumulated device time; returns nonzero past the end.
+int afq_profile_get(afq_ctx* c, int idx, const char** name, double* ms, uint64_t* launches) {
+  if (!c || idx < 0 || idx >= NUM_KID) return AFQ_ERR_INVALID;
+  if (name) *name = KID_NAMES[idx];
+  if (ms) *ms = c->kid_ms[idx];
+  if (launches) *launches = c->kid_launches[idx];
+  return AFQ_OK;
+}
+
+}  // extern "C"

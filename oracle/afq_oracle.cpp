@@ -1,0 +1,1013 @@
+// afq_oracle.cpp — CPU restatement of alevin-fry 0.18.0's `quant` per-cell hot path.
+//
+// *** TEST INFRASTRUCTURE, NOT PRODUCT. *** Only tests/, __graft_entry__.smoke() and
+// bench.py's cpu_baseline / `--impl reference` legs may load this library. The product
+// (alevin_fry_b200/libafq.so) never links, loads or calls it, and has no CPU fallback.
+//
+// PARITY STATUS: the reference is Rust and cannot be built in this environment (no
+// cargo/rustc, no vendored crates), so this restatement is pinned only against the
+// known-answer tests the reference's own test-suite holds for this path (src/em.rs
+// 1175-1215; tests/multi_barcode_integration.rs 1404-1556, 721-863 — re-expressed in
+// tests/test_oracle_kat.py). For cr-like / parsimony on non-trivial input the reference
+// holds no golden matrix => "parity unpinned" for those against a real reference run.
+//
+// Where the reference's result depends on ahash/hashbrown iteration order (which cannot
+// be reproduced without the crates) a canonical, record-order-invariant order is used
+// instead and documented at the site (DESIGN.md §"determinism contract"):
+//   * gene-level eq-classes are visited in lexicographic label order (EM f32 sums);
+//   * the parsimony cover loop visits start vertices in ascending (class label
+//     lexicographic, UMI) order.
+//
+// Every function cites the reference file:line it follows (paths relative to
+// /root/reference).
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "../include/afq.h"
+
+namespace {
+
+using u32 = uint32_t;
+using u64 = uint64_t;
+using Label = std::vector<u32>;
+
+struct LabelHash {
+  size_t operator()(const Label& v) const {
+    u64 h = 0x9E3779B97F4A7C15ull ^ (v.size() * 0xD6E8FEB86659FD93ull);
+    for (u32 x : v) {
+      h ^= x + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+      h *= 0xFF51AFD7ED558CCDull;
+      h ^= h >> 32;
+    }
+    return (size_t)h;
+  }
+};
+// gene_eqc: sorted gene-label vector -> de-duplicated molecule count (src/quant.rs:719-720)
+using GeneEqc = std::unordered_map<Label, u32, LabelHash>;
+
+struct CellView {
+  u64 nrec;
+  const u32* umi;       // [nrec]
+  const u32* ref_off;   // [nrec+1] absolute offsets into refs
+  const u32* refs;
+  u32 na(u64 i) const { return ref_off[i + 1] - ref_off[i]; }
+  const u32* r(u64 i) const { return refs + ref_off[i]; }
+};
+
+struct Cfg {
+  int resolution, usa_mode, em_init_uniform, pug_exact_umi, sa_model;
+  u32 num_gene_ids, num_rows;
+  u64 small_thresh, large_graph_thresh;
+};
+
+// src/utils.rs:409-422
+inline bool same_gene(u32 g1, u32 g2) { return (g1 == g2) || ((g1 & ~1u) == (g2 & ~1u)); }
+inline bool is_spliced(u32 g) { return (g & 1u) == 0; }
+
+// src/utils.rs:389-393
+inline u32 count_diff_2_bit_packed(u64 a, u64 b) {
+  u64 d = a ^ b;
+  u64 t = (d | (d >> 1)) & 0x5555555555555555ull;
+  return (u32)__builtin_popcountll(t);
+}
+
+struct Triplet {
+  u64 umi;
+  u32 gene, ct;
+  bool operator<(const Triplet& o) const {
+    if (umi != o.umi) return umi < o.umi;
+    if (gene != o.gene) return gene < o.gene;
+    return ct < o.ct;
+  }
+};
+
+// ---------------------------------------------------------------------------------
+// USA tie rules shared by the tiny path (src/quant.rs:557-605) and extract_counts
+// (src/utils.rs:688-753). Returns the output slot or -1 to drop. `best` is an
+// ascending gene-id list; uo = num_rows/3, ao = 2*uo.
+// ---------------------------------------------------------------------------------
+inline int64_t usa_slot_for_label(const u32* best, size_t n, u32 uo, u32 ao) {
+  if (n == 0) return -1;
+  if (n == 1) return is_spliced(best[0]) ? (best[0] >> 1) : (uo + (best[0] >> 1));
+  if (n == 2) {
+    u32 g1 = best[0], g2 = best[1];
+    if (same_gene(g1, g2)) return ao + (g1 >> 1);
+    bool s1 = is_spliced(g1), s2 = is_spliced(g2);
+    if (s1 && !s2) return g1 >> 1;
+    if (!s1 && s2) return g2 >> 1;
+    return -1;
+  }
+  if (n <= 10) {
+    // exactly one spliced id -> its A slot if its U partner follows, else its S slot
+    int64_t sidx = -1;
+    for (size_t i = 0; i < n; ++i) {
+      if (is_spliced(best[i])) {
+        if (sidx >= 0) return -1;  // 2+ spliced genes: gene-ambiguous
+        sidx = (int64_t)i;
+      }
+    }
+    if (sidx < 0) return -1;
+    u32 sg = best[sidx];
+    if ((size_t)sidx + 1 < n && same_gene(sg, best[sidx + 1])) return ao + (sg >> 1);
+    return sg >> 1;
+  }
+  return -1;
+}
+
+// ---------------------------------------------------------------------------------
+// resolve_num_molecules_crlike_from_vec (src/pugutils.rs:644-749): sort triplets by
+// (umi, gene, count); per UMI the set of genes attaining the max aggregated count gets
+// +1 in gene_eqc. The streaming state machine of the reference is kept as is.
+// ---------------------------------------------------------------------------------
+void resolve_crlike_from_vec(std::vector<Triplet>& v, GeneEqc& gene_eqc) {
+  if (v.empty()) return;  // the reference would panic ("cell with no UMIs"); unreachable
+  std::sort(v.begin(), v.end());
+  u64 curr_umi = v[0].umi;
+  u32 curr_gn = v[0].gene;
+  u32 max_count = 0, count_aggr = 0;
+  Label best_genes;
+  best_genes.reserve(16);
+  for (size_t cidx = 0; cidx < v.size(); ++cidx) {
+    const Triplet& t = v[cidx];
+    if (t.umi != curr_umi) {
+      gene_eqc[best_genes] += 1;
+      curr_umi = t.umi;
+      curr_gn = t.gene;
+      best_genes.clear();
+      best_genes.push_back(t.gene);
+      count_aggr = t.ct;
+      max_count = t.ct;
+    } else {
+      if (t.gene == curr_gn) {
+        count_aggr += t.ct;
+      } else {
+        count_aggr = t.ct;
+        curr_gn = t.gene;
+      }
+      if (count_aggr > max_count) {
+        max_count = count_aggr;
+        if (!(best_genes.size() == 1 && best_genes[0] == t.gene)) {
+          best_genes.clear();
+          best_genes.push_back(t.gene);
+        }
+      } else if (count_aggr == max_count) {
+        best_genes.push_back(t.gene);
+      }
+    }
+    if (cidx == v.size() - 1) gene_eqc[best_genes] += 1;
+  }
+}
+
+// resolve_num_molecules_crlike_from_vec_prefer_ambig (src/pugutils.rs:505-641)
+void resolve_crlike_from_vec_prefer_ambig(std::vector<Triplet>& v, GeneEqc& gene_eqc) {
+  if (v.empty()) return;
+  std::sort(v.begin(), v.end());
+  u64 curr_umi = v[0].umi;
+  u32 curr_gn[2];
+  int ncg = 0;
+  curr_gn[ncg++] = v[0].gene;
+  u32 max_count = 0, count_aggr = 0;
+  Label best_genes;
+  for (size_t cidx = 0; cidx < v.size(); ++cidx) {
+    const Triplet& t = v[cidx];
+    if (t.umi != curr_umi) {
+      gene_eqc[best_genes] += 1;
+      curr_umi = t.umi;
+      ncg = 0;
+      curr_gn[ncg++] = t.gene;
+      best_genes.clear();
+      best_genes.push_back(t.gene);
+      count_aggr = t.ct;
+      max_count = t.ct;
+    } else {
+      u32 prev_gid = curr_gn[ncg - 1];
+      if (same_gene(t.gene, prev_gid)) {
+        if (prev_gid != t.gene && ncg < 2) curr_gn[ncg++] = t.gene;
+        count_aggr += t.ct;
+      } else {
+        count_aggr = t.ct;
+        ncg = 0;
+        curr_gn[ncg++] = t.gene;
+      }
+      if (count_aggr > max_count) {
+        max_count = count_aggr;
+        best_genes.clear();
+        for (int i = 0; i < ncg; ++i) best_genes.push_back(curr_gn[i]);
+      } else if (count_aggr == max_count) {
+        for (int i = 0; i < ncg; ++i) best_genes.push_back(curr_gn[i]);
+      }
+    }
+    if (cidx == v.size() - 1) gene_eqc[best_genes] += 1;
+  }
+}
+
+void resolve_dispatch(std::vector<Triplet>& v, GeneEqc& g, int sa_model) {
+  if (sa_model == AFQ_SA_PREFER_AMBIG) resolve_crlike_from_vec_prefer_ambig(v, g);
+  else resolve_crlike_from_vec(v, g);
+}
+
+// sorted-dedup gene projection of a transcript list
+inline void project_genes(const u32* refs, u32 na, const u32* t2g, Label& out) {
+  out.clear();
+  for (u32 i = 0; i < na; ++i) out.push_back(t2g[refs[i]]);
+  std::sort(out.begin(), out.end());
+  out.erase(std::unique(out.begin(), out.end()), out.end());
+}
+
+// ---------------------------------------------------------------------------------
+// Tiny-cell fast path: quantify_small_cell_sparse (src/quant.rs:469-657) followed by the
+// run-length count of src/quant.rs:806-843. Output: sparse (slot, count) ascending slot.
+// ---------------------------------------------------------------------------------
+void quantify_small_cell_sparse(const CellView& c, const u32* t2g, const Cfg& cfg,
+                                std::vector<u32>& out_ind, std::vector<float>& out_val) {
+  out_ind.clear();
+  out_val.clear();
+  std::vector<Triplet> trip;
+  Label gset;
+  for (u64 i = 0; i < c.nrec; ++i) {
+    u32 na = c.na(i);
+    if (na == 0) continue;
+    const u32* refs = c.r(i);
+    u32 first_gid = t2g[refs[0]];
+    bool single = true;
+    for (u32 k = 1; k < na; ++k)
+      if (t2g[refs[k]] != first_gid) { single = false; break; }
+    if (single) {
+      trip.push_back({c.umi[i], first_gid, 1});
+    } else {
+      project_genes(refs, na, t2g, gset);
+      for (u32 g : gset) trip.push_back({c.umi[i], g, 1});
+    }
+  }
+  if (trip.empty()) return;
+  const bool usa = cfg.usa_mode != 0;
+  const u32 uo = usa ? cfg.num_rows / 3 : 0, ao = 2 * uo;
+  std::vector<std::pair<u32, u64>> gene_umi;  // (slot, umi)
+  std::sort(trip.begin(), trip.end());
+  auto commit = [&](const Label& best, u64 umi) {
+    if (best.empty()) return;
+    if (!usa) {
+      if (best.size() == 1) gene_umi.push_back({best[0], umi});
+      return;
+    }
+    int64_t s = usa_slot_for_label(best.data(), best.size(), uo, ao);
+    if (s >= 0) gene_umi.push_back({(u32)s, umi});
+  };
+  u64 curr_umi = trip[0].umi;
+  u32 curr_gn = trip[0].gene, max_count = 0, count_aggr = 0;
+  Label best{curr_gn};
+  for (size_t idx = 0; idx < trip.size(); ++idx) {
+    const Triplet& t = trip[idx];
+    if (t.umi != curr_umi) {
+      commit(best, curr_umi);
+      curr_umi = t.umi;
+      curr_gn = t.gene;
+      count_aggr = t.ct;
+      max_count = t.ct;
+      best.clear();
+      best.push_back(t.gene);
+    } else {
+      if (t.gene == curr_gn) count_aggr += t.ct;
+      else { count_aggr = t.ct; curr_gn = t.gene; }
+      if (count_aggr > max_count) {
+        max_count = count_aggr;
+        if (!(best.size() == 1 && best[0] == t.gene)) { best.clear(); best.push_back(t.gene); }
+      } else if (count_aggr == max_count) {
+        best.push_back(t.gene);
+      }
+    }
+    if (idx == trip.size() - 1) commit(best, curr_umi);
+  }
+  std::sort(gene_umi.begin(), gene_umi.end());
+  // run-length count by slot (src/quant.rs:812-839)
+  if (!gene_umi.empty()) {
+    u32 cur = gene_umi[0].first, cnt = 0;
+    for (auto& p : gene_umi) {
+      if (p.first == cur) ++cnt;
+      else { out_ind.push_back(cur); out_val.push_back((float)cnt); cur = p.first; cnt = 1; }
+    }
+    out_ind.push_back(cur);
+    out_val.push_back((float)cnt);
+  }
+}
+
+// get_num_molecules_cell_ranger_like_small (src/pugutils.rs:751-797)
+void crlike_small(const CellView& c, const u32* t2g, const Cfg& cfg, GeneEqc& gene_eqc) {
+  std::vector<Triplet> v;
+  v.reserve(c.nrec);
+  Label gset;
+  for (u64 i = 0; i < c.nrec; ++i) {
+    project_genes(c.r(i), c.na(i), t2g, gset);
+    for (u32 g : gset) v.push_back({c.umi[i], g, 1});
+  }
+  resolve_dispatch(v, gene_eqc, cfg.sa_model);
+}
+
+// ---------------------------------------------------------------------------------
+// EqMap (src/eq_class.rs:592-650, 723-1036, 1061-1069)
+// ---------------------------------------------------------------------------------
+struct EqMap {
+  struct Entry { std::vector<std::pair<u64, u32>> umis; };  // (umi, count) ascending
+  std::vector<Entry> eqc;
+  std::vector<u32> eq_labels, eq_label_starts;
+  // inverted index ref -> classes (descending class id per ref, as the reference's
+  // decrementing fill produces, src/eq_class.rs:956-959). Built sparsely here (a hash map
+  // instead of the reference's dense u32[nref] per worker) — same content.
+  std::unordered_map<u32, std::vector<u32>> ref_to_eq;
+  bool gene_level = false;
+
+  size_t num() const { return eqc.size(); }
+  const u32* label(u32 e) const { return eq_labels.data() + eq_label_starts[e]; }
+  u32 label_len(u32 e) const { return eq_label_starts[e + 1] - eq_label_starts[e]; }
+
+  void finish() {
+    eq_label_starts.push_back((u32)eq_labels.size());
+    for (u32 e = 0; e < eqc.size(); ++e) {
+      const u32* l = label(e);
+      for (u32 k = 0; k < label_len(e); ++k) ref_to_eq[l[k]].push_back(e);
+      auto& um = eqc[e].umis;
+      std::stable_sort(um.begin(), um.end(),
+                       [](auto& a, auto& b) { return a.first < b.first; });
+      std::vector<std::pair<u64, u32>> cv;
+      cv.swap(um);
+      u64 cur = cv[0].first;
+      u32 count = 1;
+      for (size_t i = 1; i < cv.size(); ++i) {
+        if (cv[i].first == cur) ++count;
+        else { um.push_back({cur, count}); cur = cv[i].first; count = 1; }
+      }
+      um.push_back({cur, count});
+    }
+    for (auto& kv : ref_to_eq) std::reverse(kv.second.begin(), kv.second.end());
+  }
+
+  // init_from_chunk (src/eq_class.rs:823-1036): key = refs as given, ids in
+  // first-appearance order.
+  void init_from_chunk(const CellView& c) {
+    std::unordered_map<Label, u32, LabelHash> eqid;
+    Label key;
+    for (u64 i = 0; i < c.nrec; ++i) {
+      key.assign(c.r(i), c.r(i) + c.na(i));
+      auto it = eqid.find(key);
+      if (it != eqid.end()) {
+        eqc[it->second].umis.push_back({c.umi[i], 1});
+      } else {
+        u32 id = (u32)eqc.size();
+        eq_label_starts.push_back((u32)eq_labels.size());
+        eq_labels.insert(eq_labels.end(), key.begin(), key.end());
+        eqc.push_back({});
+        eqc.back().umis.push_back({c.umi[i], 1});
+        eqid.emplace(key, id);
+      }
+    }
+    finish();
+  }
+  // init_from_chunk_gene_level (src/eq_class.rs:723-821): key = sorted-dedup gene set
+  void init_from_chunk_gene_level(const CellView& c, const u32* t2g) {
+    gene_level = true;
+    std::unordered_map<Label, u32, LabelHash> eqid;
+    Label key;
+    for (u64 i = 0; i < c.nrec; ++i) {
+      project_genes(c.r(i), c.na(i), t2g, key);
+      auto it = eqid.find(key);
+      if (it != eqid.end()) {
+        eqc[it->second].umis.push_back({c.umi[i], 1});
+      } else {
+        u32 id = (u32)eqc.size();
+        eq_label_starts.push_back((u32)eq_labels.size());
+        eq_labels.insert(eq_labels.end(), key.begin(), key.end());
+        eqc.push_back({});
+        eqc.back().umis.push_back({c.umi[i], 1});
+        eqid.emplace(key, id);
+      }
+    }
+    finish();
+  }
+};
+
+// get_num_molecules_cell_ranger_like (src/pugutils.rs:799-850)
+void crlike_from_eqmap(const EqMap& m, const u32* t2g, const Cfg& cfg, GeneEqc& gene_eqc) {
+  std::vector<Triplet> v;
+  Label gset;
+  for (u32 e = 0; e < m.num(); ++e) {
+    project_genes(m.label(e), m.label_len(e), t2g, gset);
+    for (auto& uc : m.eqc[e].umis)
+      for (u32 g : gset) v.push_back({uc.first, g, uc.second});
+  }
+  resolve_dispatch(v, gene_eqc, cfg.sa_model);
+}
+
+// get_num_molecules_trivial_discard_all_ambig (src/pugutils.rs:852-911)
+void trivial_counts(const EqMap& m, const u32* t2g, u32 num_genes, std::vector<float>& counts) {
+  counts.assign(num_genes, 0.0f);
+  std::unordered_map<u32, std::vector<u64>> gene_map;
+  for (u32 e = 0; e < m.num(); ++e) {
+    u32 prev = UINT32_MAX;
+    bool multi = false;
+    for (u32 k = 0; k < m.label_len(e); ++k) {
+      u32 gid = t2g[m.label(e)[k]];
+      if (gid != prev && prev < UINT32_MAX) { multi = true; break; }
+      prev = gid;
+    }
+    if (!multi) {
+      auto& v = gene_map[prev];
+      for (auto& uc : m.eqc[e].umis) v.push_back(uc.first);
+    }
+  }
+  for (auto& kv : gene_map) {
+    auto& v = kv.second;
+    std::sort(v.begin(), v.end());
+    v.erase(std::unique(v.begin(), v.end()), v.end());
+    counts[kv.first] += (float)v.size();
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// PUG: extract_graph (src/pugutils.rs:65-267). Node id = prefix(|umis|) + rank
+// (src/pugutils.rs:110-117). Out-adjacency only is materialised (BFS follows Outgoing,
+// src/pugutils.rs:352); an undirected edge list feeds the union-find.
+// ---------------------------------------------------------------------------------
+struct Pug {
+  std::vector<u32> node_eq, node_rank;            // node -> (class, umi rank)
+  std::vector<u32> eq_first;                      // class -> first node id
+  std::vector<std::vector<u32>> out;              // outgoing neighbours
+  std::vector<std::pair<u32, u32>> undirected;    // every edge once
+};
+
+void extract_graph(const EqMap& m, bool exact, Pug& g) {
+  const u32 neq = (u32)m.num();
+  g.eq_first.assign(neq + 1, 0);
+  for (u32 e = 0; e < neq; ++e) g.eq_first[e + 1] = g.eq_first[e] + (u32)m.eqc[e].umis.size();
+  const u32 nv = g.eq_first[neq];
+  g.node_eq.resize(nv);
+  g.node_rank.resize(nv);
+  g.out.assign(nv, {});
+  for (u32 e = 0; e < neq; ++e)
+    for (u32 r = 0; r < m.eqc[e].umis.size(); ++r) {
+      g.node_eq[g.eq_first[e] + r] = e;
+      g.node_rank[g.eq_first[e] + r] = r;
+    }
+  // has_edge (src/pugutils.rs:76-99): 0 none, 1 bidirected, 2 x->y, 3 y->x
+  auto has_edge = [&](const std::pair<u64, u32>& x, const std::pair<u64, u32>& y) -> int {
+    u32 hd = exact ? (x.first == y.first ? 0u : 99u) : count_diff_2_bit_packed(x.first, y.first);
+    if (hd == 0) return 1;
+    if (hd < 2) {
+      // u32 arithmetic `x.1 > 2*y.1 - 1` (counts >= 1 so no wrap)
+      if (x.second > 2 * y.second - 1) return 2;
+      if (y.second > 2 * x.second - 1) return 3;
+      return 1;
+    }
+    return 0;
+  };
+  auto add = [&](u32 a, u32 b, int et) {
+    if (et == 0) return;
+    if (et == 1) { g.out[a].push_back(b); g.out[b].push_back(a); }
+    else if (et == 2) g.out[a].push_back(b);
+    else g.out[b].push_back(a);
+    g.undirected.push_back({a, b});
+  };
+  std::vector<uint8_t> hset(neq, 0);
+  std::vector<u32> idxvec;
+  for (u32 e = 0; e < neq; ++e) {
+    const auto& u1 = m.eqc[e].umis;
+    for (u32 xi = 0; xi < u1.size(); ++xi)
+      for (u32 xj = xi + 1; xj < u1.size(); ++xj)
+        add(g.eq_first[e] + xi, g.eq_first[e] + xj, has_edge(u1[xi], u1[xj]));
+    for (u32 i : idxvec) hset[i] = 0;
+    idxvec.clear();
+    for (u32 k = 0; k < m.label_len(e); ++k) {
+      auto it = m.ref_to_eq.find(m.label(e)[k]);
+      if (it == m.ref_to_eq.end()) continue;
+      for (u32 e2 : it->second) {
+        if (e2 <= e) continue;
+        if (hset[e2]) continue;
+        hset[e2] = 1;
+        idxvec.push_back(e2);
+        const auto& u2 = m.eqc[e2].umis;
+        for (u32 xi = 0; xi < u1.size(); ++xi)
+          for (u32 yi = 0; yi < u2.size(); ++yi)
+            add(g.eq_first[e] + xi, g.eq_first[e2] + yi, has_edge(u1[xi], u2[yi]));
+      }
+    }
+  }
+}
+
+struct UnionFind {
+  std::vector<u32> p;
+  explicit UnionFind(u32 n) : p(n) { for (u32 i = 0; i < n; ++i) p[i] = i; }
+  u32 find(u32 x) { while (p[x] != x) { p[x] = p[p[x]]; x = p[x]; } return x; }
+  void unite(u32 a, u32 b) { a = find(a); b = find(b); if (a != b) p[std::max(a, b)] = std::min(a, b); }
+};
+
+// collapse_vertices (src/pugutils.rs:308-391). `uncovered`/`visited` are byte maps over
+// node ids (the reference uses hash sets; membership semantics are identical).
+void collapse_vertices(u32 v, const std::vector<uint8_t>& uncovered, const Pug& g, const EqMap& m,
+                       std::vector<u32>& visited_stamp, u32& stamp,
+                       std::vector<u32>& largest, u32& chosen_txp) {
+  largest.clear();
+  chosen_txp = 0;
+  const u32 ve = g.node_eq[v];
+  std::vector<u32> cur;
+  std::deque<u32> q;
+  for (u32 k = 0; k < m.label_len(ve); ++k) {
+    const u32 txp = m.label(ve)[k];
+    ++stamp;
+    q.clear();
+    q.push_back(v);
+    visited_stamp[v] = stamp;
+    cur.clear();
+    while (!q.empty()) {
+      u32 cv = q.front();
+      q.pop_front();
+      cur.push_back(cv);
+      for (u32 n : g.out[cv]) {
+        if (!uncovered[n] || visited_stamp[n] == stamp) continue;
+        visited_stamp[n] = stamp;
+        const u32 ne = g.node_eq[n];
+        const u32* lb = m.label(ne);
+        if (std::binary_search(lb, lb + m.label_len(ne), txp)) q.push_back(n);
+      }
+    }
+    if (largest.size() < cur.size()) { largest = cur; chosen_txp = txp; }
+  }
+}
+
+// get_num_molecules_large_component (src/pugutils.rs:916-982)
+void large_component(const Pug& g, const EqMap& m, const std::vector<u32>& verts, const u32* t2g,
+                     GeneEqc& gene_eqc) {
+  std::map<u32, std::vector<std::pair<u64, u32>>> tmp;
+  for (u32 v : verts) tmp[g.node_eq[v]].push_back(m.eqc[g.node_eq[v]].umis[g.node_rank[v]]);
+  std::vector<Triplet> tv;
+  Label gset;
+  for (auto& kv : tmp) {
+    if (m.gene_level) gset.assign(m.label(kv.first), m.label(kv.first) + m.label_len(kv.first));
+    else project_genes(m.label(kv.first), m.label_len(kv.first), t2g, gset);
+    for (auto& uc : kv.second)
+      for (u32 gg : gset) tv.push_back({uc.first, gg, uc.second});
+  }
+  resolve_crlike_from_vec(tv, gene_eqc);
+}
+
+// get_num_molecules (src/pugutils.rs:989-1330). Returns used_alternative_strategy.
+// CANONICAL TIE-BREAK (deviation): the reference iterates `uncovered_vertices`
+// in ahash/hashbrown order (src/pugutils.rs:1090-1093, 1110); here start vertices are
+// visited in ascending (class label lexicographic, UMI) order. Everything else — strict
+// `<` update, early break, label intersection — follows the reference.
+bool get_num_molecules(const Pug& g, const EqMap& m, const u32* t2g, GeneEqc& gene_eqc,
+                       u64 large_graph_thresh) {
+  const u32 nv = (u32)g.node_eq.size();
+  UnionFind uf(nv);
+  for (auto& e : g.undirected) uf.unite(e.first, e.second);
+  // canonical class rank: lexicographic by label
+  const u32 neq = (u32)m.num();
+  std::vector<u32> order(neq), rank(neq);
+  for (u32 e = 0; e < neq; ++e) order[e] = e;
+  std::sort(order.begin(), order.end(), [&](u32 a, u32 b) {
+    return std::lexicographical_compare(m.label(a), m.label(a) + m.label_len(a), m.label(b),
+                                        m.label(b) + m.label_len(b));
+  });
+  for (u32 i = 0; i < neq; ++i) rank[order[i]] = i;
+  auto canon_less = [&](u32 a, u32 b) {
+    u32 ra = rank[g.node_eq[a]], rb = rank[g.node_eq[b]];
+    if (ra != rb) return ra < rb;
+    return g.node_rank[a] < g.node_rank[b];  // UMIs ascending within a class
+  };
+  std::unordered_map<u32, std::vector<u32>> comps;
+  for (u32 v = 0; v < nv; ++v) comps[uf.find(v)].push_back(v);
+
+  bool alt = false;
+  std::vector<uint8_t> uncovered(nv, 0);
+  std::vector<u32> visited_stamp(nv, 0);
+  u32 stamp = 0;
+  Label global_genes;
+  std::vector<u32> global_txps, best_mcc, cand;
+  for (auto& kv : comps) {
+    auto& comp = kv.second;
+    if (comp.size() > 1) {
+      if (comp.size() > large_graph_thresh) {
+        large_component(g, m, comp, t2g, gene_eqc);
+        alt = true;
+        continue;
+      }
+      std::sort(comp.begin(), comp.end(), canon_less);
+      for (u32 v : comp) uncovered[v] = 1;
+      size_t remaining = comp.size();
+      while (remaining > 0) {
+        best_mcc.clear();
+        u32 best_txp = UINT32_MAX;
+        for (u32 v : comp) {
+          if (!uncovered[v]) continue;
+          u32 txp;
+          collapse_vertices(v, uncovered, g, m, visited_stamp, stamp, cand, txp);
+          if (best_mcc.size() < cand.size()) { best_mcc = cand; best_txp = txp; }
+          if (cand.size() == remaining) break;
+        }
+        if (best_txp == UINT32_MAX) abort();  // src/pugutils.rs:1148-1151
+        // intersect labels over the MCC (src/pugutils.rs:1161-1188)
+        global_txps.clear();
+        for (size_t i = 0; i < best_mcc.size(); ++i) {
+          u32 e = g.node_eq[best_mcc[i]];
+          const u32* lb = m.label(e);
+          u32 ln = m.label_len(e);
+          if (i == 0) global_txps.assign(lb, lb + ln);
+          else {
+            std::vector<u32> keep;
+            for (u32 t : global_txps)
+              if (std::binary_search(lb, lb + ln, t)) keep.push_back(t);
+            global_txps.swap(keep);
+          }
+        }
+        global_genes.clear();
+        for (u32 t : global_txps) global_genes.push_back(m.gene_level ? t : t2g[t]);
+        std::sort(global_genes.begin(), global_genes.end());
+        global_genes.erase(std::unique(global_genes.begin(), global_genes.end()), global_genes.end());
+        gene_eqc[global_genes] += 1;
+        for (u32 rv : best_mcc) { uncovered[rv] = 0; }
+        remaining -= best_mcc.size();
+      }
+    } else {
+      u32 e = g.node_eq[comp[0]];
+      if (m.gene_level) global_genes.assign(m.label(e), m.label(e) + m.label_len(e));
+      else project_genes(m.label(e), m.label_len(e), t2g, global_genes);
+      gene_eqc[global_genes] += 1;
+    }
+  }
+  return alt;
+}
+
+// ---------------------------------------------------------------------------------
+// EM. Thresholds src/em.rs:28-34.
+// ---------------------------------------------------------------------------------
+constexpr float MIN_OUTPUT_ALPHA = 0.01f;
+constexpr float ALPHA_CHECK_CUTOFF = 1e-2f;
+constexpr float REL_DIFF_TOLERANCE = 1e-2f;
+constexpr u32 MIN_ITER = 2, MAX_ITER = 100;
+
+// canonical (lexicographic) class order — replaces HashMap iteration (src/em.rs:464, 499)
+std::vector<std::pair<const Label*, u32>> canonical_classes(const GeneEqc& g) {
+  std::vector<std::pair<const Label*, u32>> v;
+  v.reserve(g.size());
+  for (auto& kv : g) v.push_back({&kv.first, kv.second});
+  std::sort(v.begin(), v.end(), [](auto& a, auto& b) { return *a.first < *b.first; });
+  return v;
+}
+
+// em_optimize + em_update (src/em.rs:458-582) — gene mode, HashMap form (M1).
+void em_optimize(const GeneEqc& gene_eqc, bool init_uniform, u32 num_alphas, bool only_unique,
+                 std::vector<float>& alphas_in) {
+  alphas_in.assign(num_alphas, 0.0f);
+  if (only_unique) {  // integer adds: order-free
+    for (auto& kv : gene_eqc)
+      if (kv.first.size() == 1) alphas_in[kv.first[0]] += (float)kv.second;
+    return;
+  }
+  auto classes = canonical_classes(gene_eqc);
+  for (auto& c : classes)
+    if (c.first->size() == 1) alphas_in[(*c.first)[0]] += (float)c.second;
+  std::vector<float> alphas_out(num_alphas, 0.0f);
+  const float uni_prior = 1.0f / (float)num_alphas;
+  for (auto& a : alphas_in) a = init_uniform ? uni_prior : (a + 0.5f) * 1e-3f;
+  u32 it = 0;
+  bool converged = true;
+  while (it < MIN_ITER || (it < MAX_ITER && !converged)) {
+    for (auto& c : classes) {
+      const Label& lab = *c.first;
+      if (lab.size() > 1) {
+        float denom = 0.0f;
+        for (u32 l : lab) denom += alphas_in[l];
+        if (denom > 0.0f) {
+          float inv = (float)c.second / denom;
+          for (u32 l : lab) alphas_out[l] += alphas_in[l] * inv;
+        }
+      } else {
+        alphas_out[lab[0]] += (float)c.second;
+      }
+    }
+    converged = true;
+    for (u32 i = 0; i < num_alphas; ++i) {
+      if (alphas_out[i] > ALPHA_CHECK_CUTOFF) {
+        float d = std::fabs(alphas_in[i] - alphas_out[i]);
+        if (d > REL_DIFF_TOLERANCE) converged = false;
+      }
+      alphas_in[i] = alphas_out[i];
+      alphas_out[i] = 0.0f;
+    }
+    ++it;
+  }
+  for (auto& a : alphas_in) if (a < MIN_OUTPUT_ALPHA) a = 0.0f;
+}
+
+// get_abundance_for (src/em.rs:167-187)
+inline float abundance_for(u32 idx, const float* a, u32 uo, u32 ao) {
+  if (idx >= ao) return a[idx - uo] + a[idx - ao] + a[idx];
+  if (idx >= uo) return a[idx + uo] + a[idx];
+  return a[idx + ao] + a[idx];
+}
+
+// em_optimize_subset_impl (src/em.rs:306-456) over an indexed class list (M2).
+// `labels`/`starts` = IndexedEqList CSR, cell_data = (eq id, count). usa: offsets (uo, ao).
+void em_optimize_subset(const std::vector<u32>& labels, const std::vector<u32>& starts,
+                        const std::vector<std::pair<u32, u32>>& cell_data, bool init_uniform,
+                        u32 num_alphas, bool only_unique, bool usa, u32 uo, u32 ao,
+                        std::vector<float>& alphas_in) {
+  alphas_in.assign(num_alphas, 0.0f);
+  bool needs_em = false;
+  for (auto& cd : cell_data) {
+    u32 b = starts[cd.first], e = starts[cd.first + 1];
+    if (e - b == 1) alphas_in[labels[b]] += (float)cd.second;
+    else needs_em = true;
+  }
+  if (only_unique || !needs_em) return;
+  // support (src/em.rs:87-113)
+  std::vector<u32> support;
+  std::vector<uint8_t> member(num_alphas, 0);
+  auto mark = [&](u32 i) { if (!member[i]) { member[i] = 1; support.push_back(i); } };
+  for (auto& cd : cell_data)
+    for (u32 k = starts[cd.first]; k < starts[cd.first + 1]; ++k) {
+      u32 idx = labels[k];
+      mark(idx);
+      if (usa) {
+        if (idx >= ao) { mark(idx - uo); mark(idx - ao); }
+        else if (idx >= uo) mark(idx + uo);
+        else mark(idx + ao);
+      }
+    }
+  std::vector<float> alphas_out(num_alphas, 0.0f);
+  const float uni_prior = 1.0f / (float)num_alphas;
+  for (u32 i : support) alphas_in[i] = init_uniform ? uni_prior : (alphas_in[i] + 0.5f) * 1e-3f;
+  u32 it = 0;
+  bool converged = true, last_round = false;
+  while (it < MIN_ITER || (it < MAX_ITER && !converged) || last_round) {
+    for (auto& cd : cell_data) {
+      u32 b = starts[cd.first], e = starts[cd.first + 1];
+      if (e - b > 1) {
+        float denom = 0.0f;
+        for (u32 k = b; k < e; ++k)
+          denom += usa ? abundance_for(labels[k], alphas_in.data(), uo, ao) : alphas_in[labels[k]];
+        if (denom > 0.0f) {
+          float inv = (float)cd.second / denom;
+          for (u32 k = b; k < e; ++k) {
+            float a = usa ? abundance_for(labels[k], alphas_in.data(), uo, ao) : alphas_in[labels[k]];
+            alphas_out[labels[k]] += a * inv;
+          }
+        }
+      } else {
+        alphas_out[labels[b]] += (float)cd.second;
+      }
+    }
+    converged = true;
+    for (u32 i : support) {
+      if (alphas_out[i] > ALPHA_CHECK_CUTOFF) {
+        float d = std::fabs(alphas_in[i] - alphas_out[i]);
+        if (d > REL_DIFF_TOLERANCE) converged = false;
+      }
+      alphas_in[i] = alphas_out[i];
+      alphas_out[i] = 0.0f;
+    }
+    ++it;
+    if (last_round) break;
+    if (it >= MIN_ITER && converged) {
+      for (u32 i : support) if (alphas_in[i] < MIN_OUTPUT_ALPHA) alphas_in[i] = 0.0f;
+      last_round = true;
+    }
+  }
+  for (u32 i : support) if (alphas_in[i] < MIN_OUTPUT_ALPHA) alphas_in[i] = 0.0f;
+}
+
+// utils::extract_counts (src/utils.rs:673-756) — USA, unique-only
+void extract_counts(const GeneEqc& gene_eqc, u32 num_counts, std::vector<float>& counts) {
+  const u32 uo = num_counts / 3, ao = 2 * uo;
+  counts.assign(num_counts, 0.0f);
+  for (auto& kv : gene_eqc) {
+    int64_t s = usa_slot_for_label(kv.first.data(), kv.first.size(), uo, ao);
+    if (s >= 0) counts[s] += (float)kv.second;
+  }
+}
+
+// utils::extract_usa_eqmap (src/utils.rs:842-926), classes visited in canonical order
+void extract_usa_eqmap(const GeneEqc& gene_eqc, u32 num_counts, std::vector<u32>& labels,
+                       std::vector<u32>& starts, std::vector<std::pair<u32, u32>>& cell_data) {
+  labels.clear();
+  starts.assign(1, 0);
+  cell_data.clear();
+  const u32 uo = num_counts / 3, ao = 2 * uo;
+  auto classes = canonical_classes(gene_eqc);
+  u32 ctr = 0;
+  for (auto& c : classes) {
+    const Label& lab = *c.first;
+    if (lab.size() == 1) {
+      u32 g = lab[0];
+      labels.push_back(is_spliced(g) ? (g >> 1) : uo + (g >> 1));
+    } else {
+      for (size_t i = 0; i < lab.size(); ++i) {
+        u32 gn = lab[i];
+        u32 idx = gn >> 1;
+        if (is_spliced(gn)) {
+          if (i + 1 < lab.size() && same_gene(gn, lab[i + 1])) { idx += ao; ++i; }
+        } else {
+          idx += uo;
+        }
+        labels.push_back(idx);
+      }
+    }
+    starts.push_back((u32)labels.size());
+    cell_data.push_back({ctr, c.second});
+    ++ctr;
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// One cell: the body of the hot loop (src/quant.rs:735-1196).
+// ---------------------------------------------------------------------------------
+struct CellOut {
+  std::vector<u32> ind;
+  std::vector<float> val;
+  float sum_umi = 0, max_umi = 0;
+  u32 num_expr = 0, num_over_mean = 0;
+  uint8_t flags = 0;
+};
+
+void quant_cell(const CellView& c, const u32* t2g, const Cfg& cfg, CellOut& o) {
+  o = CellOut();
+  const bool tiny_eligible = cfg.sa_model == AFQ_SA_WINNER_TAKE_ALL;
+  if (tiny_eligible && c.nrec < cfg.small_thresh) {
+    o.flags |= AFQ_FLAG_TINY;
+    quantify_small_cell_sparse(c, t2g, cfg, o.ind, o.val);
+    for (float v : o.val) { o.sum_umi += v; if (v > o.max_umi) o.max_umi = v; }
+    o.num_expr = (u32)o.val.size();
+  } else {
+    std::vector<float> counts;
+    GeneEqc gene_eqc;
+    const int res = cfg.resolution;
+    bool alt = false;
+    if (res == AFQ_RES_TRIVIAL) {
+      EqMap m;
+      m.init_from_chunk(c);
+      trivial_counts(m, t2g, cfg.num_gene_ids, counts);
+      // NB: the reference sizes this vector num_genes (src/pugutils.rs:858); in USA mode
+      // `trivial` is not a supported combination (src/quant.rs:1076-1081).
+      counts.resize(cfg.num_rows, 0.0f);
+    } else {
+      bool only_unique;
+      if (res == AFQ_RES_CR_LIKE || res == AFQ_RES_CR_LIKE_EM) {
+        if (c.nrec <= 250) {  // src/quant.rs:853, 861-869
+          crlike_small(c, t2g, cfg, gene_eqc);
+        } else {
+          EqMap m;
+          m.init_from_chunk(c);
+          crlike_from_eqmap(m, t2g, cfg, gene_eqc);
+        }
+        only_unique = (res == AFQ_RES_CR_LIKE);
+      } else {
+        EqMap m;
+        if (res == AFQ_RES_PARSIMONY_GENE || res == AFQ_RES_PARSIMONY_GENE_EM)
+          m.init_from_chunk_gene_level(c, t2g);
+        else
+          m.init_from_chunk(c);
+        Pug g;
+        extract_graph(m, cfg.pug_exact_umi != 0, g);
+        alt = get_num_molecules(g, m, t2g, gene_eqc, cfg.large_graph_thresh);
+        only_unique = (res == AFQ_RES_PARSIMONY || res == AFQ_RES_PARSIMONY_GENE);
+      }
+      if (cfg.usa_mode) {
+        if (only_unique) {
+          extract_counts(gene_eqc, cfg.num_rows, counts);
+        } else {
+          std::vector<u32> labels, starts;
+          std::vector<std::pair<u32, u32>> cell_data;
+          extract_usa_eqmap(gene_eqc, cfg.num_rows, labels, starts, cell_data);
+          em_optimize_subset(labels, starts, cell_data, cfg.em_init_uniform != 0, cfg.num_rows,
+                             false, true, cfg.num_rows / 3, 2 * cfg.num_rows / 3, counts);
+        }
+      } else {
+        em_optimize(gene_eqc, cfg.em_init_uniform != 0, cfg.num_gene_ids, only_unique, counts);
+      }
+    }
+    if (alt) o.flags |= AFQ_FLAG_ALT;
+    // dense -> sparse scan (src/quant.rs:1150-1171)
+    for (u32 gn = 0; gn < counts.size(); ++gn) {
+      float v = counts[gn];
+      if (v > o.max_umi) o.max_umi = v;
+      o.sum_umi += v;
+      if (v > 0.0f) { ++o.num_expr; o.val.push_back(v); o.ind.push_back(gn); }
+    }
+  }
+  if (o.num_expr == 0) o.flags |= AFQ_FLAG_EMPTY;
+  const float mean_expr = o.sum_umi / (float)o.num_expr;  // NaN when empty, as the reference
+  for (float v : o.val) if (v > mean_expr) ++o.num_over_mean;
+}
+
+struct OracleResult {
+  std::vector<u64> row_ptr;
+  std::vector<u32> col;
+  std::vector<float> val, sum_umi, max_umi;
+  std::vector<u32> num_expr, num_over_mean;
+  std::vector<uint8_t> flags;
+};
+
+thread_local std::string g_err;
+
+}  // namespace
+
+extern "C" {
+
+// Quantify a host batch on `n_threads` CPU threads (cells are independent work items,
+// the reference's only parallelism — src/quant.rs:1389, 733-735). Result arrays are
+// owned by the returned handle; free with afq_oracle_release.
+int afq_oracle_quant(const afq_config* cfg_in, const uint32_t* tid_to_gid, uint64_t n_refs,
+                     const afq_batch* b, int n_threads, afq_result* out, void** handle) {
+  (void)n_refs;
+  if (!cfg_in || !b || !out || !handle) return AFQ_ERR_INVALID;
+  Cfg cfg{cfg_in->resolution, cfg_in->usa_mode, cfg_in->em_init_uniform, cfg_in->pug_exact_umi,
+          cfg_in->sa_model, cfg_in->num_gene_ids, cfg_in->num_rows, cfg_in->small_thresh,
+          cfg_in->large_graph_thresh};
+  const u64 nc = b->n_cells;
+  std::vector<CellOut> outs(nc);
+  if (n_threads < 1) n_threads = 1;
+  std::atomic<u64> next{0};
+  auto work = [&]() {
+    for (;;) {
+      u64 c0 = next.fetch_add(16);
+      if (c0 >= nc) break;
+      u64 c1 = std::min(nc, c0 + 16);
+      for (u64 c = c0; c < c1; ++c) {
+        u64 r0 = b->cell_rec_offsets[c], r1 = b->cell_rec_offsets[c + 1];
+        CellView cv{r1 - r0, b->rec_umi32 + r0, b->rec_ref_offsets + r0, b->refs};
+        quant_cell(cv, tid_to_gid, cfg, outs[c]);
+      }
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < n_threads; ++t) th.emplace_back(work);
+  work();
+  for (auto& t : th) t.join();
+
+  auto* r = new OracleResult();
+  r->row_ptr.resize(nc + 1, 0);
+  for (u64 c = 0; c < nc; ++c) r->row_ptr[c + 1] = r->row_ptr[c] + outs[c].ind.size();
+  r->col.resize(r->row_ptr[nc]);
+  r->val.resize(r->row_ptr[nc]);
+  r->sum_umi.resize(nc); r->max_umi.resize(nc); r->num_expr.resize(nc);
+  r->num_over_mean.resize(nc); r->flags.resize(nc);
+  for (u64 c = 0; c < nc; ++c) {
+    std::copy(outs[c].ind.begin(), outs[c].ind.end(), r->col.begin() + r->row_ptr[c]);
+    std::copy(outs[c].val.begin(), outs[c].val.end(), r->val.begin() + r->row_ptr[c]);
+    r->sum_umi[c] = outs[c].sum_umi; r->max_umi[c] = outs[c].max_umi;
+    r->num_expr[c] = outs[c].num_expr; r->num_over_mean[c] = outs[c].num_over_mean;
+    r->flags[c] = outs[c].flags;
+  }
+  out->n_cells = nc; out->nnz = r->row_ptr[nc];
+  out->row_ptr = r->row_ptr.data(); out->col = r->col.data(); out->val = r->val.data();
+  out->sum_umi = r->sum_umi.data(); out->max_umi = r->max_umi.data();
+  out->num_expr = r->num_expr.data(); out->num_over_mean = r->num_over_mean.data();
+  out->flags = r->flags.data();
+  *handle = r;
+  return AFQ_OK;
+}
+
+void afq_oracle_release(void* handle) { delete static_cast<OracleResult*>(handle); }
+
+// Known-answer hooks for the EM tests of src/em.rs:1175-1215: run the subset EM (M2) on a
+// caller-supplied indexed class list. usa_uo/usa_ao = 0 => gene mode.
+int afq_oracle_em_subset(const uint32_t* labels, const uint32_t* starts, uint32_t n_classes,
+                         const uint32_t* cell_eq, const uint32_t* cell_ct, uint32_t n_cell,
+                         int init_uniform, uint32_t num_alphas, int only_unique,
+                         uint32_t usa_uo, uint32_t usa_ao, float* out_alphas) {
+  std::vector<u32> l(labels, labels + starts[n_classes]), s(starts, starts + n_classes + 1);
+  std::vector<std::pair<u32, u32>> cd;
+  for (u32 i = 0; i < n_cell; ++i) cd.push_back({cell_eq[i], cell_ct[i]});
+  std::vector<float> a;
+  em_optimize_subset(l, s, cd, init_uniform != 0, num_alphas, only_unique != 0,
+                     usa_ao != 0, usa_uo, usa_ao, a);
+  std::copy(a.begin(), a.end(), out_alphas);
+  return AFQ_OK;
+}
+
+// Dense EM over explicit classes (M1, src/em.rs:487-582), classes given as CSR + counts.
+int afq_oracle_em_dense(const uint32_t* labels, const uint32_t* starts, uint32_t n_classes,
+                        const uint32_t* counts, int init_uniform, uint32_t num_alphas,
+                        int only_unique, float* out_alphas) {
+  GeneEqc g;
+  for (u32 i = 0; i < n_classes; ++i) {
+    Label lab(labels + starts[i], labels + starts[i + 1]);
+    g[lab] += counts[i];
+  }
+  std::vector<float> a;
+  em_optimize(g, init_uniform != 0, num_alphas, only_unique != 0, a);
+  std::copy(a.begin(), a.end(), out_alphas);
+  return AFQ_OK;
+}
+
+int afq_oracle_hamming(uint64_t a, uint64_t b) { return (int)count_diff_2_bit_packed(a, b); }
+
+}  // extern "C"

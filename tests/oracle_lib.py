@@ -1,0 +1,79 @@
+"""ctypes access to the CPU oracle (oracle/libafq_oracle.so). TEST INFRASTRUCTURE ONLY:
+nothing under alevin_fry_b200/ imports this module."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from alevin_fry_b200._abi import AfqBatch, AfqConfig, AfqResult, REPO_ROOT
+from alevin_fry_b200.quant import CellBatch, QuantOpts, QuantResult
+
+ORACLE_LIB_PATH = os.path.join(REPO_ROOT, "oracle", "libafq_oracle.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        l = C.CDLL(ORACLE_LIB_PATH)
+        l.afq_oracle_quant.restype = C.c_int
+        l.afq_oracle_quant.argtypes = [C.POINTER(AfqConfig), C.c_void_p, C.c_uint64, C.POINTER(AfqBatch), C.c_int,
+                                       C.POINTER(AfqResult), C.POINTER(C.c_void_p)]
+        l.afq_oracle_release.restype = None
+        l.afq_oracle_release.argtypes = [C.c_void_p]
+        l.afq_oracle_em_subset.restype = C.c_int
+        l.afq_oracle_em_subset.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
+                                           C.c_int, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p]
+        l.afq_oracle_em_dense.restype = C.c_int
+        l.afq_oracle_em_dense.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.c_uint32,
+                                          C.c_int, C.c_void_p]
+        l.afq_oracle_hamming.restype = C.c_int
+        l.afq_oracle_hamming.argtypes = [C.c_uint64, C.c_uint64]
+        _lib = l
+    return _lib
+
+
+def oracle_quant(opts: QuantOpts, tid_to_gid: np.ndarray, batch: CellBatch, n_threads: int = 0) -> QuantResult:
+    if n_threads <= 0:
+        n_threads = os.cpu_count() or 1
+    t2g = np.ascontiguousarray(tid_to_gid, dtype=np.uint32)
+    cfg = opts.to_c()
+    cb = batch.to_c()
+    r = AfqResult()
+    h = C.c_void_p()
+    rc = lib().afq_oracle_quant(C.byref(cfg), t2g.ctypes.data_as(C.c_void_p), len(t2g), C.byref(cb), n_threads,
+                                C.byref(r), C.byref(h))
+    assert rc == 0, rc
+    out = QuantResult.from_c(r)
+    lib().afq_oracle_release(h)
+    return out
+
+
+def _csr(classes):
+    labels, starts = [], [0]
+    for c in classes:
+        labels.extend(c)
+        starts.append(len(labels))
+    return np.array(labels, dtype=np.uint32), np.array(starts, dtype=np.uint32)
+
+
+def em_subset(classes, cell_data, init_uniform, num_alphas, only_unique=False, usa_offsets=None):
+    """em_optimize_subset (src/em.rs:251-456) on explicit classes; cell_data = [(eq_id, count)]."""
+    labels, starts = _csr(classes)
+    eq = np.array([c[0] for c in cell_data], dtype=np.uint32)
+    ct = np.array([c[1] for c in cell_data], dtype=np.uint32)
+    out = np.zeros(num_alphas, dtype=np.float32)
+    uo, ao = usa_offsets if usa_offsets else (0, 0)
+    lib().afq_oracle_em_subset(labels.ctypes.data, starts.ctypes.data, len(classes), eq.ctypes.data, ct.ctypes.data,
+                               len(cell_data), int(init_uniform), num_alphas, int(only_unique), uo, ao, out.ctypes.data)
+    return out
+
+
+def em_dense(classes, counts, init_uniform, num_alphas, only_unique=False):
+    """em_optimize (src/em.rs:487-582) on explicit classes."""
+    labels, starts = _csr(classes)
+    ct = np.array(counts, dtype=np.uint32)
+    out = np.zeros(num_alphas, dtype=np.float32)
+    lib().afq_oracle_em_dense(labels.ctypes.data, starts.ctypes.data, len(classes), ct.ctypes.data, int(init_uniform),
+                              num_alphas, int(only_unique), out.ctypes.data)
+    return out

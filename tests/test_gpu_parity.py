@@ -1,0 +1,161 @@
+"""GPU parity tests: the CUDA path through the C-ABI vs the CPU oracle on identical seeded
+inputs. Integer resolutions must be bit-exact; EM within 1e-5 relative (north_star)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib
+from alevin_fry_b200 import CellBatch, QuantOpts, Quantifier, synth, FLAG_TINY
+
+pytestmark = pytest.mark.gpu
+
+EM_RTOL = 1e-5  # BASELINE.json north_star: "within 1e-5 relative for EM gene counts"
+
+
+def assert_same(got, want, exact=True, ctx=""):
+    assert np.array_equal(got.row_ptr, want.row_ptr), f"{ctx}: row_ptr differs"
+    assert np.array_equal(got.col, want.col), f"{ctx}: col differs"
+    if exact:
+        assert np.array_equal(got.val, want.val), f"{ctx}: val differs"
+        assert np.array_equal(got.sum_umi, want.sum_umi), f"{ctx}: sum_umi"
+        assert np.array_equal(got.max_umi, want.max_umi), f"{ctx}: max_umi"
+    else:
+        np.testing.assert_allclose(got.val, want.val, rtol=EM_RTOL, atol=0, err_msg=ctx)
+        np.testing.assert_allclose(got.sum_umi, want.sum_umi, rtol=1e-4, err_msg=ctx)
+        np.testing.assert_allclose(got.max_umi, want.max_umi, rtol=EM_RTOL, err_msg=ctx)
+    assert np.array_equal(got.num_expr, want.num_expr), f"{ctx}: num_expr"
+    assert np.array_equal(got.flags, want.flags), f"{ctx}: flags"
+    if exact:
+        assert np.array_equal(got.num_over_mean, want.num_over_mean), f"{ctx}: num_over_mean"
+
+
+def gpu_quant(opts, t2g, batch):
+    with Quantifier(opts, t2g) as q:
+        r = q.quantify_batch(batch)
+        assert q.launch_count > 0
+    return r
+
+
+def opts_for(spec, res, **kw):
+    return QuantOpts(resolution=res, usa_mode=spec.usa_mode, num_gene_ids=spec.num_gene_ids,
+                     num_rows=spec.num_rows, **kw)
+
+
+INT_RES = ["cr-like", "trivial", "parsimony", "parsimony-gene"]
+EM_RES = ["cr-like-em", "parsimony-em", "parsimony-gene-em"]
+
+
+@pytest.mark.parametrize("res", INT_RES + EM_RES)
+def test_mini_c2_all_resolutions(res):
+    spec = synth.config_spec("C2")
+    b = synth.generate(spec, 0, 300)
+    t2g = synth.tid_to_gid(spec)
+    o = opts_for(spec, res)
+    assert_same(gpu_quant(o, t2g, b), oracle_lib.oracle_quant(o, t2g, b), exact=res in INT_RES, ctx=res)
+
+
+@pytest.mark.parametrize("res", ["cr-like", "parsimony", "cr-like-em"])
+def test_c1_tiny_cells(res):
+    spec = synth.config_spec("C1")  # 50 reads/cell: every cell takes the tiny path
+    b = synth.generate(spec, 0, 1000)
+    t2g = synth.tid_to_gid(spec)
+    o = opts_for(spec, res)
+    got = gpu_quant(o, t2g, b)
+    assert int((got.flags & FLAG_TINY != 0).sum()) == 1000
+    assert_same(got, oracle_lib.oracle_quant(o, t2g, b), exact=True, ctx=res)
+    o0 = opts_for(spec, res, small_thresh=0)  # tiny path disabled: requested resolution runs
+    assert_same(gpu_quant(o0, t2g, b), oracle_lib.oracle_quant(o0, t2g, b), exact=not res.endswith("-em"), ctx=res + "/st0")
+
+
+@pytest.mark.parametrize("res", ["cr-like", "cr-like-em", "parsimony", "parsimony-em"])
+def test_mini_c4_usa(res):
+    spec = synth.config_spec("C4")
+    b = synth.generate(spec, 0, 200)
+    t2g = synth.tid_to_gid(spec)
+    o = opts_for(spec, res)
+    assert_same(gpu_quant(o, t2g, b), oracle_lib.oracle_quant(o, t2g, b), exact=not res.endswith("-em"), ctx=res)
+
+
+@pytest.mark.parametrize("res", ["parsimony-em", "parsimony", "cr-like"])
+def test_mini_c5_high_duplication(res):
+    spec = synth.config_spec("C5")
+    b = synth.generate(spec, 0, 200)
+    t2g = synth.tid_to_gid(spec)
+    o = opts_for(spec, res)
+    assert_same(gpu_quant(o, t2g, b), oracle_lib.oracle_quant(o, t2g, b), exact=not res.endswith("-em"), ctx=res)
+
+
+def test_edge_cases_empty_ragged():
+    t2g = np.arange(10, dtype=np.uint32)
+    cells = [[], [(5, [1])], [(5, [1, 2])], [(7, [])], [(1, [0])] * 300 + [(2, [0, 3])] * 2, []]
+    b = CellBatch.from_cells(cells)
+    for res in ("cr-like", "trivial", "parsimony", "cr-like-em"):
+        for st in (100, 0):
+            o = QuantOpts(resolution=res, num_gene_ids=10, num_rows=10, small_thresh=st)
+            assert_same(gpu_quant(o, t2g, b), oracle_lib.oracle_quant(o, t2g, b), exact=not res.endswith("-em"), ctx=f"{res}/{st}")
+    # a batch with zero cells
+    e = CellBatch.from_cells([])
+    r = gpu_quant(QuantOpts(num_gene_ids=10, num_rows=10), t2g, e)
+    assert r.n_cells == 0 and r.nnz == 0
+
+
+def test_skewed_cells_hit_every_arena_bin(monkeypatch):
+    # lognormal sigma 1.6 spreads cells from a few records to > 16k: exercises all shared-memory
+    # arenas, the overflow re-queue and the giant-cell global arena
+    spec = synth.SynthSpec(reads_mean=3000.0, lognorm_sigma=1.6, reads_per_umi=1.3)
+    b = synth.generate(spec, 0, 400)
+    t2g = synth.tid_to_gid(spec)
+    n = np.diff(b.cell_rec_offsets.astype(np.int64))
+    assert n.max() > 16384 and n.min() < 256
+    for res in ("cr-like", "parsimony"):
+        o = opts_for(spec, res)
+        assert_same(gpu_quant(o, t2g, b), oracle_lib.oracle_quant(o, t2g, b), ctx=res)
+
+
+@pytest.mark.parametrize("force_bin", [3, 6])
+def test_forced_large_arena_matches(monkeypatch, force_bin):
+    monkeypatch.setenv("AFQ_FORCE_BIN", str(force_bin))
+    monkeypatch.setenv("AFQ_LARGE_CAP_LOG2", "18")
+    spec = synth.config_spec("C2")
+    b = synth.generate(spec, 1000, 64)
+    t2g = synth.tid_to_gid(spec)
+    for res in ("cr-like", "parsimony"):
+        o = opts_for(spec, res)
+        assert_same(gpu_quant(o, t2g, b), oracle_lib.oracle_quant(o, t2g, b), ctx=f"{res}/bin{force_bin}")
+
+
+def test_pipelined_submits_and_full_size_properties():
+    # several batches in flight; results identical to one-shot; size-independent invariants
+    spec = synth.config_spec("C2")
+    t2g = synth.tid_to_gid(spec)
+    o = opts_for(spec, "cr-like")
+    b = synth.generate(spec, 5000, 1500)
+    with Quantifier(o, t2g) as q:
+        whole = q.quantify_batch(b)
+        parts = [b.slice_cells(i, min(i + 500, 1500)) for i in range(0, 1500, 500)]
+        tickets = [q.submit(p) for p in parts]
+        rs = [q.wait(t) for t in tickets]
+    assert sum(r.nnz for r in rs) == whole.nnz
+    assert np.array_equal(np.concatenate([r.col for r in rs]), whole.col)
+    assert np.array_equal(np.concatenate([r.val for r in rs]), whole.val)
+    # invariants: columns strictly ascending inside a row, counts integral and >= 1,
+    # sum_umi == sum of the row, molecules <= records
+    for c in range(whole.n_cells):
+        col, val = whole.row(c)
+        assert np.all(np.diff(col.astype(np.int64)) > 0)
+        assert np.all(val >= 1) and np.all(val == np.floor(val))
+        assert val.sum() == whole.sum_umi[c]
+        assert whole.sum_umi[c] <= b.cell_rec_offsets[c + 1] - b.cell_rec_offsets[c]
+    # permuting records inside a cell must not change anything (order is not part of the contract)
+    rng = np.random.default_rng(1)
+    cells = []
+    for c in range(200):
+        r0, r1 = int(b.cell_rec_offsets[c]), int(b.cell_rec_offsets[c + 1])
+        recs = [(int(b.rec_umi32[r]), b.refs[b.rec_ref_offsets[r]:b.rec_ref_offsets[r + 1]].tolist()) for r in range(r0, r1)]
+        rng.shuffle(recs)
+        cells.append(recs)
+    shuf = CellBatch.from_cells(cells)
+    for res in ("cr-like", "parsimony"):
+        oo = opts_for(spec, res)
+        assert_same(gpu_quant(oo, t2g, shuf), gpu_quant(oo, t2g, b.slice_cells(0, 200)), ctx="shuffle/" + res)
