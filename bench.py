@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the quant hot path (BASELINE.json metric).
+
+A "step" is one pass of the hot path (per-cell UMI resolution -> sparse cell x gene rows)
+over the whole per-GPU synthetic workload. Workload at N=1 = BASELINE.json configs[1] (C2):
+100k cells x ~200M reads, 10x-v3 (16 bp BC / 12 bp UMI), `--resolution cr-like`. Under
+torchrun every rank generates and processes its own C2-sized shard of cells (weak scaling,
+cells are independent: no data-path collective; the only exchange is the per-rank row-count
+all-gather that assembles the global matrix index).
+
+  value : cells/s, inputs resident in HBM when the timed region starts (CUDA events on the
+          launching stream, max over ranks)
+  e2e   : cells/s through the reference-facing C-ABI call (afq_submit/afq_wait) with pinned
+          HOST buffers: H2D of the batch and D2H of the sparse result inside the timed region
+  roofline / cpu_baseline / clocks / gpu_launches : see DESIGN.md §Measurement
+
+`--impl reference` times the reference's CPU algorithm (the oracle port, oracle/) on the host
+cores of the box, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "cells/sec quant (collated RAD→matrix) at 1/2/4/8 B200 vs CPU ref"
+HBM_FALLBACK_GBS = 6650.0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="afq", choices=["afq", "reference"])
+    ap.add_argument("--config", default="C2")
+    ap.add_argument("--cells", type=int, default=0, help="cells per GPU (default: the config's)")
+    ap.add_argument("--resolution", default="")
+    ap.add_argument("--e2e-batches", type=int, default=8, help="host batches per e2e step (pipelined)")
+    ap.add_argument("--cpu-sample-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+CONFIGS = {  # name -> (cells per GPU, resolution, description)
+    "C1": (1000, "cr-like", "C1: 1k cells x 50k reads, 10x-v3, cr-like"),
+    "C2": (100_000, "cr-like", "C2: 100k cells x ~200M reads per GPU, 10x-v3 16bp BC/12bp UMI, --resolution cr-like"),
+    "C3": (125_000, "parsimony", "C3: 1M cells x 2B reads over 8 GPUs (125k cells/GPU), --resolution parsimony"),
+    "C4": (125_000, "cr-like-em", "C4: 500k cells USA-mode over 4 GPUs (125k cells/GPU), --resolution cr-like-em"),
+    "C5": (100_000, "parsimony-em", "C5: 100k cells, 40 reads/UMI, 5k genes, --resolution parsimony-em"),
+}
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        v = float(json.load(open(p))["hbm_gbs"])
+        return v, "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.p = index, [], None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.p:
+            self.p.terminate()
+            try:
+                self.p.wait(timeout=2)
+            except Exception:
+                self.p.kill()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = max([int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()] or [0])
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm)}
+
+
+def algorithmic_bytes(batch, nnz):
+    """every input byte read once, every output byte written once."""
+    n_in = 8 * (batch.n_cells + 1) + 4 * batch.n_records + 4 * (batch.n_records + 1) + 4 * batch.n_refs_total
+    n_out = 8 * nnz + 8 * (batch.n_cells + 1) + 17 * batch.n_cells
+    return n_in + n_out
+
+
+def run_reference(args, spec, cells, res):
+    """--impl reference: the reference's CPU algorithm (oracle port) on all host cores."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    from alevin_fry_b200 import QuantOpts, synth
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    t2g = synth.tid_to_gid(spec)
+    opts = QuantOpts(resolution=res, usa_mode=spec.usa_mode, num_gene_ids=spec.num_gene_ids, num_rows=spec.num_rows)
+    probe = synth.generate(spec, 0, min(cells, 512))
+    t0 = time.perf_counter(); oracle_lib.oracle_quant(opts, t2g, probe, n_threads=cores); dt = time.perf_counter() - t0
+    rate = probe.n_cells / dt
+    total = args.steps + args.warmup
+    n_sample = int(max(256, min(cells, rate * min(8.0, 150.0 / max(total, 1)))))
+    sample = synth.generate(spec, 0, n_sample)
+    for _ in range(args.warmup):
+        oracle_lib.oracle_quant(opts, t2g, sample, n_threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle_lib.oracle_quant(opts, t2g, sample, n_threads=cores)
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    v = n_sample / dt
+    desc = f"first {n_sample} cells ({sample.n_records} records) of the workload per step"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "cells/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32", "data": "synthetic",
+        "config": {"workload": CONFIGS[args.config][2], "resolution": res, "cells_per_step": n_sample},
+        "cpu_baseline": {"value": v, "unit": "cells/s", "cores": cores, "kind": "port", "sample": desc,
+                         "note": "C++ restatement of the reference's Rust algorithm (reference not buildable here: no cargo/rustc)"},
+        "e2e": {"value": v, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def main():
+    args = parse_args()
+    from alevin_fry_b200 import synth
+    cells, res, desc = CONFIGS[args.config]
+    if args.cells:
+        cells = args.cells
+    if args.resolution:
+        res = args.resolution
+    spec = synth.config_spec(args.config)
+    if args.impl == "reference":
+        return run_reference(args, spec, cells, res)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from alevin_fry_b200 import QuantOpts, Quantifier
+    from alevin_fry_b200.hostmem import PinnedPool
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the afq product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- synthetic workload: this rank's shard of cells, generated into pinned host memory ----
+    pool = PinnedPool()
+    nthreads = max(1, (os.cpu_count() or 1) // max(1, min(world, 8)))
+    nb = max(1, min(args.e2e_batches, cells))
+    bounds = [cells * i // nb for i in range(nb + 1)]
+    # each part: pinned arrays with part-relative offsets (what a host RAD parser would hand over)
+    parts = [synth.generate(spec, rank * cells + bounds[i], bounds[i + 1] - bounds[i], n_threads=nthreads, alloc=pool.empty)
+             for i in range(nb)]
+    t2g = synth.tid_to_gid(spec)
+    opts = QuantOpts(resolution=res, usa_mode=spec.usa_mode, num_gene_ids=spec.num_gene_ids, num_rows=spec.num_rows, device=local)
+    q = Quantifier(opts, t2g)
+
+    # device-resident copy of the whole per-GPU workload as ONE batch (offsets re-based on the device)
+    def T(a, dt):
+        return torch.from_numpy(a.view(dt)).to(dev)
+    cro, umi, roff, refs, rbase, fbase = [], [], [], [], 0, 0
+    for i, p in enumerate(parts):
+        c = T(p.cell_rec_offsets, np.int64) + rbase
+        r = T(p.rec_ref_offsets, np.int32).to(torch.int64) + fbase
+        cro.append(c if i == nb - 1 else c[:-1])
+        roff.append(r if i == nb - 1 else r[:-1])
+        umi.append(T(p.rec_umi32, np.int32))
+        refs.append(T(p.refs, np.int32))
+        rbase += p.n_records
+        fbase += p.n_refs_total
+    if fbase >= 2 ** 32 - 16:
+        raise SystemExit("per-GPU workload exceeds 2^32 alignments; lower --cells")
+    roff64 = torch.cat(roff)
+    roff32 = torch.where(roff64 >= 2 ** 31, roff64 - 2 ** 32, roff64).to(torch.int32)  # u32 bit pattern in an int32 tensor
+    db = dict(cell_rec_offsets=torch.cat(cro), rec_umi32=torch.cat(umi), rec_ref_offsets=roff32, refs=torch.cat(refs))
+    del cro, umi, roff, refs, roff64, roff32
+
+    class batch:  # whole-workload sizes
+        n_cells, n_records, n_refs_total = cells, rbase, fbase
+    nc = batch.n_cells
+    do = dict(row_ptr=torch.empty(nc + 1, dtype=torch.int64, device=dev),
+              col=torch.empty(batch.n_refs_total, dtype=torch.int32, device=dev),
+              val=torch.empty(batch.n_refs_total, dtype=torch.float32, device=dev),
+              sum_umi=torch.empty(nc, dtype=torch.float32, device=dev), max_umi=torch.empty(nc, dtype=torch.float32, device=dev),
+              num_expr=torch.empty(nc, dtype=torch.int32, device=dev), num_over_mean=torch.empty(nc, dtype=torch.int32, device=dev),
+              flags=torch.empty(nc, dtype=torch.uint8, device=dev))
+    counts_all = torch.empty(world * nc, dtype=torch.int32, device=dev) if world > 1 else None
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step_device():
+        q.quant_device(db, do, stream)
+        if world > 1:  # global matrix index: every rank learns every rank's row lengths
+            dist.all_gather_into_tensor(counts_all, do["num_expr"])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing --------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    nnz = q.device_finish(stream, do["row_ptr"])
+    q.set_profiling(True)
+    q.profile_reset()
+    launches0 = q.launch_count
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = (q.launch_count - launches0) // max(args.steps, 1)
+    prof = q.profile()
+    q.set_profiling(False)
+    q.device_finish(stream)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+
+    # ---- e2e through the host C-ABI: pinned host batches, H2D + kernels + D2H per step ---------
+    h2d = sum(p.cell_rec_offsets.nbytes + p.rec_umi32.nbytes + p.rec_ref_offsets.nbytes + p.refs.nbytes for p in parts)
+
+    def step_e2e():
+        d2h, tickets = 0, []
+        for p in parts:
+            tickets.append(q.submit(p))
+            if len(tickets) == 3:
+                n_c, n_z = q.wait(tickets.pop(0), copy=False)
+                d2h += 8 * (n_c + 1) + 17 * n_c + 8 * n_z
+        for t in tickets:
+            n_c, n_z = q.wait(t, copy=False)
+            d2h += 8 * (n_c + 1) + 17 * n_c + 8 * n_z
+        return d2h
+    for _ in range(max(args.warmup, 3)):
+        d2h = step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        d2h = step_e2e()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- roofline of the dominant kernel family (per-cell resolve) -----------------------------
+    fam = {k: v for k, v in prof.items() if k.startswith(("k_resolve", "k_pug", "k_em"))}
+    fam_ms = sum(v[0] for v in fam.values()) / args.steps
+    fam_launches = sum(v[1] for v in fam.values()) // max(args.steps, 1)
+    abytes = algorithmic_bytes(batch, nnz)
+    peak, peak_src = peak_hbm()
+    achieved = abytes / (fam_ms * 1e-3) / 1e9 if fam_ms > 0 else 0.0
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(args.config)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "k_resolve_* (per-cell resolve family, %d launches/step)" % fam_launches,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "algorithmic_bytes_per_step": abytes, "kernel_ms_per_step": fam_ms, "peak_source": peak_src,
+                "per_kernel_ms": {k: v[0] / args.steps for k, v in prof.items()}}
+
+    # ---- CPU baseline (rank 0, N=1 only): oracle port on a bounded sample of the same workload --
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib
+        cores = os.cpu_count() or 1
+        probe = parts[0].slice_cells(0, min(parts[0].n_cells, 512))
+        t0 = time.perf_counter(); oracle_lib.oracle_quant(opts, t2g, probe, n_threads=cores); dt = time.perf_counter() - t0
+        n_sample = int(max(256, min(parts[0].n_cells, probe.n_cells / dt * args.cpu_sample_seconds)))
+        sample = parts[0].slice_cells(0, n_sample)
+        t0 = time.perf_counter(); oracle_lib.oracle_quant(opts, t2g, sample, n_threads=cores); dt = time.perf_counter() - t0
+        cpu = {"value": n_sample / dt, "unit": "cells/s", "cores": cores, "kind": "port",
+               "sample": f"first {n_sample} cells ({sample.n_records} records) of the workload, {dt:.1f} s of wall time on {cores} threads",
+               "note": "C++ restatement of the reference's Rust algorithm (reference not buildable here: no cargo/rustc)"}
+
+    if rank == 0:
+        total_cells = nc * world
+        print(json.dumps({
+            "metric": METRIC, "value": total_cells / (ms * 1e-3), "unit": "cells/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": desc, "resolution": res, "cells_per_gpu": nc, "records_per_gpu": batch.n_records,
+                       "refs_per_gpu": batch.n_refs_total, "nnz_per_gpu": nnz, "parallelism": f"cell-sharded x{world}",
+                       "l2_policy": "inputs (%.1f GB/GPU) larger than L2 (126 MB); no flush needed" % ((8 * batch.n_records + 4 * batch.n_refs_total) / 1e9),
+                       "seed": spec.seed},
+            "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": {"value": total_cells / e2e_s, "unit": "cells/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_s * 1e3, "host_batches_per_step": nb},
+            "gpu_launches": int(launches) + 0, "clocks": clocks,
+        }), flush=True)
+    q.close()
+    pool.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
