@@ -16,8 +16,7 @@
 #include <vector>
 
 #include "../../include/afq.h"
-#include "afq_kernels.cuh"
-#include "afq_pug.cuh"
+#include "afq_pipeline.cuh"
 
 using namespace afq;
 
@@ -72,11 +71,12 @@ struct Work {  // per-pipeline scratch (ordered on one stream)
   DBuf<u32> stage_col;
   DBuf<float> stage_val;
   DBuf<u64> tile_sums;
-  PugWork pug;
+  DBuf<u8> ge_arena[2];
+  DBuf<u32> adj_pool;
   cudaError_t ensure(u64 n_cells, u64 n_refs) {
     cudaError_t e;
     if ((e = ctl.ensure(1)) != cudaSuccess) return e;
-    if ((e = bin_list.ensure((size_t)NUM_BINS * n_cells)) != cudaSuccess) return e;
+    if ((e = bin_list.ensure((size_t)NUM_LISTS * n_cells)) != cudaSuccess) return e;
     if ((e = stage_col.ensure(n_refs + 1)) != cudaSuccess) return e;
     if ((e = stage_val.ensure(n_refs + 1)) != cudaSuccess) return e;
     if ((e = tile_sums.ensure(n_cells / SCAN_TILE + 2)) != cudaSuccess) return e;
@@ -84,7 +84,7 @@ struct Work {  // per-pipeline scratch (ordered on one stream)
   }
   void release() {
     ctl.release(); bin_list.release(); stage_col.release(); stage_val.release();
-    tile_sums.release(); pug.release();
+    tile_sums.release(); ge_arena[0].release(); ge_arena[1].release(); adj_pool.release();
   }
 };
 
@@ -116,12 +116,6 @@ struct Slot {  // one in-flight host batch
 };
 
 struct ProfRec { int kid; cudaEvent_t a, b; };
-constexpr int NUM_KID = 16;
-const char* const KID_NAMES[NUM_KID] = {
-    "k_bin_cells", "k_resolve_smem<0>", "k_resolve_smem<1>", "k_resolve_smem<2>",
-    "k_resolve_smem<3>", "k_resolve_smem<4>", "k_resolve_smem<5>", "k_resolve_large",
-    "k_scan_tile_sums", "k_scan_tiles", "k_scan_rows", "k_gather_rows",
-    "k_pug_cell", "k_em_cell", "k_geq_finish", "other"};
 
 }  // namespace
 
@@ -140,6 +134,7 @@ struct afq_ctx {
   u32 large_blocks = 32;
   int force_bin = -1;
   int grid_smem[NUM_SMEM_BINS] = {0};
+  int ge_grid = 0;
   // pipelines
   Work work_dev, work_host;
   static constexpr int NSLOT = 3;
@@ -185,27 +180,37 @@ int setup_bin(afq_ctx* c) {
   return AFQ_OK;
 }
 
-template <int BIN>
-void launch_bin(afq_ctx* c, const KArgs& a, cudaStream_t st) {
-  ProfScope ps(c, 1 + BIN, st);
-  const size_t smem = (size_t)12 << bin_cap_log2(BIN);
-  k_resolve_smem<BIN><<<c->grid_smem[BIN], bin_threads(BIN), smem, st>>>(a);
-}
-
-bool is_pug_resolution(int r) {
-  return r == AFQ_RES_PARSIMONY || r == AFQ_RES_PARSIMONY_EM || r == AFQ_RES_PARSIMONY_GENE ||
-         r == AFQ_RES_PARSIMONY_GENE_EM;
-}
-bool is_em_resolution(int r) {
-  return r == AFQ_RES_CR_LIKE_EM || r == AFQ_RES_PARSIMONY_EM || r == AFQ_RES_PARSIMONY_GENE_EM;
-}
+// Launcher for afq_pipeline.cuh: real launches on a CUDA stream, timed with event pairs when
+// profiling is on.
+struct CudaLauncher {
+  afq_ctx* c;
+  Work* w;
+  cudaStream_t st;
+  cudaError_t last = cudaSuccess;
+  const u32* t2g() const { return c->d_t2g; }
+  template <class... P, class... A>
+  void launch(int kid, void (*k)(P...), unsigned grid, unsigned block, size_t smem, A... args) {
+    ProfScope ps(c, kid, st);
+    k<<<grid, block, smem, st>>>(args...);
+  }
+  int memset_zero(void* p, size_t n) { return cudaMemsetAsync(p, 0, n, st) != cudaSuccess; }
+  int read_ctl(const Ctl* d, Ctl* h) {
+    if (cudaMemcpyAsync(c->h_ctl_dev, d, sizeof(Ctl), cudaMemcpyDeviceToHost, st) != cudaSuccess) return 1;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return 1;
+    *h = *c->h_ctl_dev;
+    return 0;
+  }
+  int grid_for_bin(int b) { return c->grid_smem[b]; }
+  int ge_blocks(int which) { return which == 0 ? 16 : c->ge_grid; }
+  u8* ge_arena(int which, u64 bytes, u32 blocks) {
+    if (w->ge_arena[which].ensure((size_t)bytes * blocks + 64) != cudaSuccess) return nullptr;
+    return w->ge_arena[which].p;
+  }
+  u32* adj_pool(u64 n) { return w->adj_pool.ensure((size_t)n) == cudaSuccess ? w->adj_pool.p : nullptr; }
+};
 
 // Enqueue the full device pipeline for one batch. All pointers are device pointers.
 int run_pipeline(afq_ctx* c, Work& w, const afq_batch& b, const afq_device_out& o, cudaStream_t st) {
-  if (b.n_cells == 0) {
-    CUDA_TRY(c, cudaMemsetAsync(o.row_ptr, 0, sizeof(u64), st));
-    return AFQ_OK;
-  }
   if (b.n_cells >= 0xFFFFFFF0ull || b.n_refs_total >= 0xFFFFFFF0ull || b.n_records >= 0xFFFFFFF0ull) {
     c->err = "batch too large: n_cells, n_records and n_refs_total must be < 2^32 (split the batch)";
     return AFQ_ERR_INVALID;
@@ -214,92 +219,21 @@ int run_pipeline(afq_ctx* c, Work& w, const afq_batch& b, const afq_device_out& 
     c->err = "afq_device_out capacities too small (need n_cells+1 rows and n_refs_total nnz)";
     return AFQ_ERR_INVALID;
   }
-  CUDA_TRY(c, w.ensure(b.n_cells, b.n_refs_total));
-  KArgs a{};
-  a.n_cells = b.n_cells;
-  a.cell_rec_off = b.cell_rec_offsets;
-  a.umi = b.rec_umi32;
-  a.ref_off = b.rec_ref_offsets;
-  a.refs = b.refs;
-  a.t2g = c->d_t2g;
-  a.mode = (c->cfg.resolution == AFQ_RES_TRIVIAL) ? MODE_TRIVIAL : MODE_CRLIKE;
-  a.usa_mode = c->cfg.usa_mode ? 1u : 0u;
-  a.num_rows = c->cfg.num_rows;
-  a.uo = c->cfg.usa_mode ? c->cfg.num_rows / 3 : 0;
-  a.ao = 2 * a.uo;
-  a.small_thresh = c->cfg.small_thresh;
-  a.tiny_eligible = c->cfg.sa_model == AFQ_SA_WINNER_TAKE_ALL ? 1u : 0u;
-  a.ctl = w.ctl.p;
-  a.bin_list = w.bin_list.p;
-  a.stage_col = w.stage_col.p;
-  a.stage_val = w.stage_val.p;
-  a.sum_umi = o.sum_umi;
-  a.max_umi = o.max_umi;
-  a.num_expr = o.num_expr;
-  a.num_over_mean = o.num_over_mean;
-  a.flags = o.flags;
-  a.large_keys = c->large_keys;
-  a.large_cnts = c->large_cnts;
-  a.large_cap_log2 = c->large_cap_log2;
-
-  CUDA_TRY(c, cudaMemsetAsync(w.ctl.p, 0, sizeof(Ctl), st));
-  const int res = c->cfg.resolution;
-  if (res == AFQ_RES_CR_LIKE || res == AFQ_RES_TRIVIAL) {
-    {
-      ProfScope ps(c, 0, st);
-      k_bin_cells<<<(unsigned)((b.n_cells + 255) / 256), 256, 0, st>>>(a, c->force_bin);
-    }
-    launch_bin<0>(c, a, st);
-    launch_bin<1>(c, a, st);
-    launch_bin<2>(c, a, st);
-    launch_bin<3>(c, a, st);
-    launch_bin<4>(c, a, st);
-    launch_bin<5>(c, a, st);
-    {
-      ProfScope ps(c, 7, st);
-      k_resolve_large<<<c->large_blocks, 1024, 0, st>>>(a);
-    }
-  } else {
-    // cr-like-em and the parsimony family: tiny cells keep the cr-like fast path
-    // (src/quant.rs:794-846); every other cell goes through the PUG / EM kernels.
-    int rc = run_pug_em_pipeline(c->cfg, c->num_sms, c->force_bin, a, w.pug, b, st,
-                                 [&](int kid) { c->launches++; c->kid_launches[kid]++; }, c->err);
-    if (rc != AFQ_OK) return rc;
-  }
-  CUDA_TRY(c, cudaGetLastError());
-
-  const u32 n_tiles = (u32)((b.n_cells + SCAN_TILE - 1) / SCAN_TILE);
-  {
-    ProfScope ps(c, 8, st);
-    k_scan_tile_sums<<<n_tiles, 1024, 0, st>>>(o.num_expr, b.n_cells, w.tile_sums.p);
-  }
-  {
-    ProfScope ps(c, 9, st);
-    k_scan_tiles<<<1, 1024, 0, st>>>(w.tile_sums.p, n_tiles, o.row_ptr, b.n_cells);
-  }
-  {
-    ProfScope ps(c, 10, st);
-    k_scan_rows<<<n_tiles, 1024, 0, st>>>(o.num_expr, b.n_cells, w.tile_sums.p, o.row_ptr);
-  }
-  {
-    ProfScope ps(c, 11, st);
-    k_gather_rows<<<(unsigned)((b.n_cells * 32 + 255) / 256), 256, 0, st>>>(a, o.row_ptr, o.col, o.val);
-  }
+  if (b.n_cells) CUDA_TRY(c, w.ensure(b.n_cells, b.n_refs_total));
+  PipeBufs pb{w.ctl.p, w.bin_list.p, w.stage_col.p, w.stage_val.p, w.tile_sums.p,
+              c->large_keys, c->large_cnts, c->large_cap_log2, c->large_blocks};
+  CudaLauncher l{c, &w, st};
+  int rc = enqueue_batch(l, c->cfg, c->force_bin, pb, b, o, c->err);
+  if (rc != AFQ_OK) return rc;
   CUDA_TRY(c, cudaGetLastError());
   return AFQ_OK;
 }
 
 int check_device_error(afq_ctx* c, const Ctl& h) {
-  if (h.error & DEV_ERR_CELL_TOO_LARGE) {
-    c->err = "a cell has " + std::to_string(h.max_cell_refs) +
-             " alignments, more than the giant-cell arena holds (raise AFQ_LARGE_CAP_LOG2)";
-    return AFQ_ERR_UNSUPPORTED;
-  }
-  if (h.error) {
-    c->err = "device-side error flags " + std::to_string(h.error);
-    return AFQ_ERR_INTERNAL;
-  }
-  return AFQ_OK;
+  if (!h.error) return AFQ_OK;
+  std::string buf;
+  c->err = device_error_string(h, buf);
+  return (h.error & (DEV_ERR_CELL_TOO_LARGE | DEV_ERR_ARENA | DEV_ERR_ADJ_POOL)) ? AFQ_ERR_UNSUPPORTED : AFQ_ERR_INTERNAL;
 }
 
 }  // namespace
@@ -367,8 +301,12 @@ int afq_create(const afq_config* cfg, const uint32_t* tid_to_gid, uint64_t n_ref
   if ((rc = setup_bin<0>(c)) || (rc = setup_bin<1>(c)) || (rc = setup_bin<2>(c)) ||
       (rc = setup_bin<3>(c)) || (rc = setup_bin<4>(c)) || (rc = setup_bin<5>(c)))
     return fail(rc);
-  std::string perr;
-  if ((rc = pug_em_setup(c->num_sms, perr)) != AFQ_OK) { c->err = perr; return fail(rc); }
+  {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gene_eqc, (int)GE_THREADS, 0) != cudaSuccess || occ < 1) occ = 1;
+    if (occ > 4) occ = 4;
+    c->ge_grid = occ * c->num_sms;
+  }
   *out = c;
   return AFQ_OK;
 }

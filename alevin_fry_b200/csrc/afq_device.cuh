@@ -6,7 +6,15 @@
 // kernels) or on a global-memory scratch arena (the giant-cell kernel).
 #pragma once
 #include <cstdint>
+#ifdef AFQ_EMU
+// test-only CPU emulation of the CUDA execution model (tests/emu/cuda_emu.h); never part
+// of the product build
+#include "cuda_emu.h"
+#define AFQ_DYN_SMEM(name) unsigned char* name = cuda_emu::g.dyn_smem
+#else
 #include <cuda_runtime.h>
+#define AFQ_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
 
 namespace afq {
 

@@ -30,11 +30,15 @@ __host__ __device__ constexpr u32 bin_threads(int b) {
 enum : u32 { MODE_CRLIKE = 0, MODE_TRIVIAL = 1 };
 enum : u32 { DEV_ERR_CELL_TOO_LARGE = 1 };
 
+constexpr int NUM_LISTS = NUM_BINS + 2;          // + two k_gene_eqc lists (big / normal cells)
 struct Ctl {                       // per-batch device control block (zeroed per batch)
-  u32 bin_count[NUM_BINS + 1];
-  u32 bin_cursor[NUM_BINS + 1];
+  u32 bin_count[NUM_LISTS + 1];
+  u32 bin_cursor[NUM_LISTS + 1];
   u32 error;
   u32 max_cell_refs;
+  u32 ge_max_n[2];                 // largest record / alignment count on the k_gene_eqc lists
+  u32 ge_max_p[2];
+  unsigned long long adj_used;     // bump pointer into the adjacency pool
 };
 
 struct KArgs {
@@ -51,7 +55,7 @@ struct KArgs {
   u32 tiny_eligible;
   // work lists
   Ctl* ctl;
-  u32* bin_list;                   // [NUM_BINS][n_cells]
+  u32* bin_list;                   // [NUM_LISTS][n_cells]
   // staging + per-cell outputs
   u32* stage_col;
   float* stage_val;
@@ -247,7 +251,7 @@ template <int BIN>
 __global__ void __launch_bounds__(bin_threads(BIN)) k_resolve_smem(KArgs a) {
   constexpr u32 LOG2CAP = bin_cap_log2(BIN);
   constexpr u32 CAP = 1u << LOG2CAP;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  AFQ_DYN_SMEM(smem_raw);
   u64* keys = reinterpret_cast<u64*>(smem_raw);
   u32* cnts = reinterpret_cast<u32*>(keys + CAP);
   __shared__ CellShared sh;

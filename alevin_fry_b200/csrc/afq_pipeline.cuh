@@ -1,0 +1,162 @@
+// afq_pipeline.cuh — the per-batch launch sequence, written once against a small Launcher
+// concept so that the CUDA library (afq_cuda.cu, real <<<>>> launches on a stream) and the
+// test-only CPU emulator harness (tests/emu) enqueue exactly the same kernels in the same
+// order with the same arguments.
+//
+// Launcher concept:
+//   template <class... P, class... A>
+//   void launch(int kid, void (*kernel)(P...), unsigned grid, unsigned block, size_t smem, A... args);
+//   int  memset_zero(void* dev, size_t bytes);                // 0 on success
+//   int  read_ctl(const Ctl* dev, Ctl* host);                 // synchronising read-back
+//   int  grid_for_bin(int bin);                               // persistent grid size
+//   int  ge_blocks(int which);                                // 0 big-cell grid, 1 normal grid
+//   u8*  ge_arena(int which, u64 bytes_per_block, u32 blocks);// grow-only, nullptr on failure
+//   u32* adj_pool(u64 entries);                               // grow-only, nullptr on failure
+#pragma once
+#include <string>
+
+#include "../../include/afq.h"
+#include "afq_kernels.cuh"
+#include "afq_pug.cuh"
+
+namespace afq {
+
+enum KernelId : int {
+  KID_BIN = 0, KID_SMEM0 = 1, KID_LARGE = 7, KID_SCAN_SUMS = 8, KID_SCAN_TILES = 9, KID_SCAN_ROWS = 10,
+  KID_GATHER = 11, KID_GENE_EQC = 12, KID_GENE_EQC_BIG = 13, KID_BIN_GE = 14, KID_OTHER = 15, NUM_KID = 16
+};
+static const char* const KID_NAMES[NUM_KID] = {
+    "k_bin_cells", "k_resolve_smem<0>", "k_resolve_smem<1>", "k_resolve_smem<2>", "k_resolve_smem<3>",
+    "k_resolve_smem<4>", "k_resolve_smem<5>", "k_resolve_large", "k_scan_tile_sums", "k_scan_tiles",
+    "k_scan_rows", "k_gather_rows", "k_gene_eqc", "k_gene_eqc(big cells)", "k_bin_cells_ge", "other"};
+
+struct PipeBufs {  // device scratch owned by the caller (one set per stream-ordered pipeline)
+  Ctl* ctl;
+  u32* bin_list;       // [NUM_LISTS][n_cells]
+  u32* stage_col;      // [n_refs_total + 1]
+  float* stage_val;
+  u64* tile_sums;      // [n_cells / SCAN_TILE + 2]
+  u64* large_keys;     // giant-cell arenas for k_resolve_large
+  u32* large_cnts;
+  u32 large_cap_log2, large_blocks;
+};
+
+inline bool res_is_pug(int r) {
+  return r == AFQ_RES_PARSIMONY || r == AFQ_RES_PARSIMONY_EM || r == AFQ_RES_PARSIMONY_GENE || r == AFQ_RES_PARSIMONY_GENE_EM;
+}
+inline bool res_is_em(int r) {
+  return r == AFQ_RES_CR_LIKE_EM || r == AFQ_RES_PARSIMONY_EM || r == AFQ_RES_PARSIMONY_GENE_EM;
+}
+
+template <int BIN, class L>
+inline void launch_smem_bin(L& l, const KArgs& a) {
+  const size_t smem = (size_t)12 << bin_cap_log2(BIN);
+  l.launch(KID_SMEM0 + BIN, k_resolve_smem<BIN>, (unsigned)l.grid_for_bin(BIN), bin_threads(BIN), smem, a);
+}
+
+template <class L>
+inline void launch_crlike_bins(L& l, const KArgs& a, const PipeBufs& pb) {
+  launch_smem_bin<0>(l, a);
+  launch_smem_bin<1>(l, a);
+  launch_smem_bin<2>(l, a);
+  launch_smem_bin<3>(l, a);
+  launch_smem_bin<4>(l, a);
+  launch_smem_bin<5>(l, a);
+  l.launch(KID_LARGE, k_resolve_large, pb.large_blocks, 1024u, (size_t)0, a);
+}
+
+// Enqueue the whole pipeline for one batch. All batch/out pointers are device pointers.
+template <class L>
+int enqueue_batch(L& l, const afq_config& cfg, int force_bin, const PipeBufs& pb, const afq_batch& b,
+                  const afq_device_out& o, std::string& err) {
+  if (b.n_cells == 0) return l.memset_zero(o.row_ptr, sizeof(u64)) ? AFQ_ERR_CUDA : AFQ_OK;
+  KArgs a{};
+  a.n_cells = b.n_cells;
+  a.cell_rec_off = b.cell_rec_offsets;
+  a.umi = b.rec_umi32;
+  a.ref_off = b.rec_ref_offsets;
+  a.refs = b.refs;
+  a.t2g = nullptr;  // filled by the launcher owner (see set_t2g)
+  a.mode = (cfg.resolution == AFQ_RES_TRIVIAL) ? MODE_TRIVIAL : MODE_CRLIKE;
+  a.usa_mode = cfg.usa_mode ? 1u : 0u;
+  a.num_rows = cfg.num_rows;
+  a.uo = cfg.usa_mode ? cfg.num_rows / 3 : 0;
+  a.ao = 2 * a.uo;
+  a.small_thresh = cfg.small_thresh;
+  a.tiny_eligible = cfg.sa_model == AFQ_SA_WINNER_TAKE_ALL ? 1u : 0u;
+  a.ctl = pb.ctl;
+  a.bin_list = pb.bin_list;
+  a.stage_col = pb.stage_col;
+  a.stage_val = pb.stage_val;
+  a.sum_umi = o.sum_umi;
+  a.max_umi = o.max_umi;
+  a.num_expr = o.num_expr;
+  a.num_over_mean = o.num_over_mean;
+  a.flags = o.flags;
+  a.large_keys = pb.large_keys;
+  a.large_cnts = pb.large_cnts;
+  a.large_cap_log2 = pb.large_cap_log2;
+  a.t2g = l.t2g();
+
+  if (l.memset_zero(pb.ctl, sizeof(Ctl))) { err = "memset(ctl) failed"; return AFQ_ERR_CUDA; }
+  const int res = cfg.resolution;
+  const unsigned bin_grid = (unsigned)((b.n_cells + 255) / 256);
+  if (res == AFQ_RES_CR_LIKE || res == AFQ_RES_TRIVIAL) {
+    l.launch(KID_BIN, k_bin_cells, bin_grid, 256u, (size_t)0, a, force_bin);
+    launch_crlike_bins(l, a, pb);
+  } else {
+    // cr-like-em and the parsimony family: tiny cells keep the cr-like fast path
+    // (src/quant.rs:794-846, regardless of -r); every other cell builds gene eq-classes.
+    if (cfg.large_graph_thresh > MAX_GRAPH_THRESH && res_is_pug(res)) {
+      err = "--large-graph-thresh above 4096 is not supported on the CUDA path";
+      return AFQ_ERR_UNSUPPORTED;
+    }
+    l.launch(KID_BIN_GE, k_bin_cells_ge, bin_grid, 256u, (size_t)0, a, force_bin, GE_BIG_RECORDS);
+    launch_crlike_bins(l, a, pb);
+    Ctl h{};
+    if (l.read_ctl(pb.ctl, &h)) { err = "reading the control block failed"; return AFQ_ERR_CUDA; }
+    GeArgs g{};
+    g.ge_mode = res_is_pug(res) ? ((res == AFQ_RES_PARSIMONY_GENE || res == AFQ_RES_PARSIMONY_GENE_EM) ? GE_MODE_PUG_GENE : GE_MODE_PUG_TXP)
+                                : GE_MODE_CRLIKE;
+    g.only_unique = res_is_em(res) ? 0u : 1u;
+    g.em_init_uniform = cfg.em_init_uniform ? 1u : 0u;
+    g.pug_exact_umi = cfg.pug_exact_umi ? 1u : 0u;
+    g.umi_len = cfg.umi_len;
+    g.large_graph_thresh = (u32)(cfg.large_graph_thresh > MAX_GRAPH_THRESH ? MAX_GRAPH_THRESH : cfg.large_graph_thresh);
+    g.num_alphas = cfg.usa_mode ? cfg.num_rows : cfg.num_gene_ids;
+    g.adj_cap = 4ull * b.n_records + (1ull << 20);
+    g.adj_pool = l.adj_pool(g.adj_cap);
+    g.adj_used = (u64*)&pb.ctl->adj_used;
+    if (!g.adj_pool) { err = "adjacency pool allocation failed"; return AFQ_ERR_CUDA; }
+    for (int which = 0; which < 2; ++which) {
+      const int list = which == 0 ? GE_LIST_BIG : GE_LIST_NORMAL;
+      if (h.bin_count[list] == 0) continue;
+      const u64 bytes = align8(ge_carve(nullptr, h.ge_max_n[which], h.ge_max_p[which], g.large_graph_thresh, nullptr)) + 64;
+      u32 blocks = (u32)l.ge_blocks(which);
+      if (blocks > h.bin_count[list]) blocks = h.bin_count[list];
+      g.arena = l.ge_arena(which, bytes, blocks);
+      if (!g.arena) { err = "gene-eq-class arena allocation failed (" + std::to_string(bytes) + " B x " + std::to_string(blocks) + ")"; return AFQ_ERR_CUDA; }
+      g.arena_bytes = bytes;
+      g.list_id = (u32)list;
+      l.launch(which == 0 ? KID_GENE_EQC_BIG : KID_GENE_EQC, k_gene_eqc, blocks, GE_THREADS, (size_t)0, a, g);
+    }
+  }
+  const u32 n_tiles = (u32)((b.n_cells + SCAN_TILE - 1) / SCAN_TILE);
+  l.launch(KID_SCAN_SUMS, k_scan_tile_sums, n_tiles, 1024u, (size_t)0, (const u32*)o.num_expr, (u64)b.n_cells, pb.tile_sums);
+  l.launch(KID_SCAN_TILES, k_scan_tiles, 1u, 1024u, (size_t)0, pb.tile_sums, n_tiles, (u64*)o.row_ptr, (u64)b.n_cells);
+  l.launch(KID_SCAN_ROWS, k_scan_rows, n_tiles, 1024u, (size_t)0, (const u32*)o.num_expr, (u64)b.n_cells, (const u64*)pb.tile_sums, (u64*)o.row_ptr);
+  l.launch(KID_GATHER, k_gather_rows, (unsigned)((b.n_cells * 32 + 255) / 256), 256u, (size_t)0, a, (const u64*)o.row_ptr, (u32*)o.col, (float*)o.val);
+  return AFQ_OK;
+}
+
+inline const char* device_error_string(const Ctl& h, std::string& buf) {
+  if (h.error & DEV_ERR_CELL_TOO_LARGE) buf = "a cell has " + std::to_string(h.max_cell_refs) + " alignments, more than the giant-cell arena holds (raise AFQ_LARGE_CAP_LOG2)";
+  else if (h.error & DEV_ERR_ADJ_POOL) buf = "PUG adjacency pool exhausted";
+  else if (h.error & DEV_ERR_ARENA) buf = "a cell does not fit the gene-eq-class arena";
+  else if (h.error & DEV_ERR_HASH) buf = "eq-class label hash collision not resolved after reseeding";
+  else if (h.error & DEV_ERR_LABEL) buf = "empty covering label in the PUG cover";
+  else buf = "device-side error flags " + std::to_string(h.error);
+  return buf.c_str();
+}
+
+}  // namespace afq

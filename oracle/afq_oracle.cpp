@@ -419,7 +419,9 @@ void trivial_counts(const EqMap& m, const u32* t2g, u32 num_genes, std::vector<f
       if (gid != prev && prev < UINT32_MAX) { multi = true; break; }
       prev = gid;
     }
-    if (!multi) {
+    // an empty label (record without alignments) would index counts[u32::MAX] and panic in
+    // the reference; a RAD writer never emits one (convert.rs:122). Skipped here.
+    if (!multi && prev != UINT32_MAX) {
       auto& v = gene_map[prev];
       for (auto& uc : m.eqc[e].umis) v.push_back(uc.first);
     }
@@ -657,7 +659,9 @@ constexpr u32 MIN_ITER = 2, MAX_ITER = 100;
 std::vector<std::pair<const Label*, u32>> canonical_classes(const GeneEqc& g) {
   std::vector<std::pair<const Label*, u32>> v;
   v.reserve(g.size());
-  for (auto& kv : g) v.push_back({&kv.first, kv.second});
+  // a record without alignments yields an empty label; the reference would panic on it
+  // (src/em.rs:481 `expect`), a RAD writer never produces one (convert.rs:122). Skipped.
+  for (auto& kv : g) if (!kv.first.empty()) v.push_back({&kv.first, kv.second});
   std::sort(v.begin(), v.end(), [](auto& a, auto& b) { return *a.first < *b.first; });
   return v;
 }

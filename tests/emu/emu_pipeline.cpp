@@ -1,0 +1,102 @@
+// emu_pipeline.cpp — TEST-ONLY: runs the product's kernels (alevin_fry_b200/csrc/*.cuh,
+// compiled for the host with -DAFQ_EMU) through the shared launch sequence of
+// afq_pipeline.cuh on the CPU emulator (cuda_emu.h). Used by tests/test_emu_parity.py to
+// check kernel logic against the oracle without a GPU, and for debugging. Never loaded by
+// the product: the product path is libafq.so on a real sm_100 device or an error.
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "cuda_emu.h"
+emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
+namespace cuda_emu { State g; }
+
+#include "../../alevin_fry_b200/csrc/afq_pipeline.cuh"
+
+using namespace afq;
+
+namespace {
+struct EmuLauncher {
+  const u32* t2g_ = nullptr;
+  std::vector<u8> arena[2];
+  std::vector<u32> adj;
+  u64 launches = 0;
+  int ge_threads_override = 0;
+  const u32* t2g() const { return t2g_; }
+  template <class... P, class... A>
+  void launch(int, void (*k)(P...), unsigned grid, unsigned block, size_t smem, A... args) {
+    ++launches;
+    // persistent kernels pull work from lists: one emulated CTA is enough (and much faster)
+    cuda_emu::launch(k, grid, block, smem, args...);
+  }
+  int memset_zero(void* p, size_t n) { memset(p, 0, n); return 0; }
+  int read_ctl(const Ctl* d, Ctl* h) { *h = *d; return 0; }
+  int grid_for_bin(int) { return 1; }
+  int ge_blocks(int) { return 2; }
+  u8* ge_arena(int which, u64 bytes, u32 blocks) {
+    arena[which].assign((size_t)bytes * blocks + 64, 0xCD);
+    return arena[which].data();
+  }
+  u32* adj_pool(u64 n) { adj.assign((size_t)n, 0xCDCDCDCDu); return adj.data(); }
+};
+
+struct EmuResult {
+  std::vector<u64> row_ptr;
+  std::vector<u32> col, num_expr, num_over_mean;
+  std::vector<float> val, sum_umi, max_umi;
+  std::vector<u8> flags;
+};
+}  // namespace
+
+extern "C" {
+
+// k_scan_* and k_bin_* use grids of many CTAs: honoured as is (sequential CTAs).
+int afq_emu_quant(const afq_config* cfg, const uint32_t* tid_to_gid, uint64_t n_refs, const afq_batch* b,
+                  afq_result* out, void** handle, char* errbuf, size_t errlen, uint32_t* dev_error) {
+  (void)n_refs;
+  EmuLauncher l;
+  l.t2g_ = tid_to_gid;
+  const u64 nc = b->n_cells, nf = b->n_refs_total;
+  std::vector<Ctl> ctl(1);
+  std::vector<u32> bin_list((size_t)NUM_LISTS * (nc + 1)), stage_col(nf + 1);
+  std::vector<float> stage_val(nf + 1);
+  std::vector<u64> tile_sums(nc / SCAN_TILE + 2);
+  const u32 large_cap_log2 = 16, large_blocks = 1;
+  std::vector<u64> large_keys((size_t)large_blocks << large_cap_log2);
+  std::vector<u32> large_cnts((size_t)large_blocks << large_cap_log2);
+  PipeBufs pb{ctl.data(), bin_list.data(), stage_col.data(), stage_val.data(), tile_sums.data(),
+              large_keys.data(), large_cnts.data(), large_cap_log2, large_blocks};
+  auto* r = new EmuResult();
+  r->row_ptr.assign(nc + 1, 0); r->col.assign(nf + 1, 0); r->val.assign(nf + 1, 0);
+  r->sum_umi.assign(nc + 1, 0); r->max_umi.assign(nc + 1, 0); r->num_expr.assign(nc + 1, 0);
+  r->num_over_mean.assign(nc + 1, 0); r->flags.assign(nc + 1, 0);
+  afq_device_out o{};
+  o.row_ptr = r->row_ptr.data(); o.cap_cells = nc + 1;
+  o.col = r->col.data(); o.val = r->val.data(); o.cap_nnz = nf + 1;
+  o.sum_umi = r->sum_umi.data(); o.max_umi = r->max_umi.data();
+  o.num_expr = r->num_expr.data(); o.num_over_mean = r->num_over_mean.data(); o.flags = r->flags.data();
+  std::string err;
+  int force_bin = -1;
+  if (const char* s = getenv("AFQ_FORCE_BIN")) force_bin = atoi(s);
+  int rc = enqueue_batch(l, *cfg, force_bin, pb, *b, o, err);
+  if (dev_error) *dev_error = ctl[0].error;
+  if (rc == AFQ_OK && ctl[0].error) {
+    std::string buf;
+    err = device_error_string(ctl[0], buf);
+    rc = AFQ_ERR_INTERNAL;
+  }
+  if (errbuf && errlen) { strncpy(errbuf, err.c_str(), errlen - 1); errbuf[errlen - 1] = 0; }
+  if (rc != AFQ_OK) { delete r; return rc; }
+  out->n_cells = nc;
+  out->nnz = r->row_ptr[nc];
+  out->row_ptr = r->row_ptr.data(); out->col = r->col.data(); out->val = r->val.data();
+  out->sum_umi = r->sum_umi.data(); out->max_umi = r->max_umi.data();
+  out->num_expr = r->num_expr.data(); out->num_over_mean = r->num_over_mean.data(); out->flags = r->flags.data();
+  *handle = r;
+  return AFQ_OK;
+}
+
+void afq_emu_release(void* h) { delete static_cast<EmuResult*>(h); }
+
+}  // extern "C"

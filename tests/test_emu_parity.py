@@ -1,0 +1,85 @@
+"""CPU-tier check of the CUDA kernels' LOGIC: the product's device code, compiled for the
+host against the test-only emulator (tests/emu), must reproduce the oracle bit-for-bit.
+(The real-GPU parity tests are in test_gpu_parity.py; this tier exists because the build
+container has no GPU, and it is also the debugging harness for the kernels.)"""
+import numpy as np
+import pytest
+
+import emu_lib
+import oracle_lib
+from alevin_fry_b200 import CellBatch, QuantOpts, synth, FLAG_ALT
+
+ALL_RES = ["cr-like", "trivial", "parsimony", "parsimony-gene", "cr-like-em", "parsimony-em", "parsimony-gene-em"]
+
+
+def check(opts, t2g, b, tag=""):
+    got = emu_lib.emu_quant(opts, t2g, b)
+    want = oracle_lib.oracle_quant(opts, t2g, b, n_threads=2)
+    assert np.array_equal(got.row_ptr, want.row_ptr), tag
+    assert np.array_equal(got.col, want.col), tag
+    # same operation order and roundings => bit-identical even for EM
+    assert np.array_equal(got.val, want.val), tag
+    assert np.array_equal(got.sum_umi, want.sum_umi), tag
+    assert np.array_equal(got.max_umi, want.max_umi), tag
+    assert np.array_equal(got.num_expr, want.num_expr), tag
+    assert np.array_equal(got.num_over_mean, want.num_over_mean), tag
+    assert np.array_equal(got.flags, want.flags), tag
+    return got
+
+
+def opts_for(spec, res, **kw):
+    return QuantOpts(resolution=res, usa_mode=spec.usa_mode, num_gene_ids=spec.num_gene_ids, num_rows=spec.num_rows,
+                     umi_len=spec.umi_len, **kw)
+
+
+@pytest.mark.parametrize("res", ALL_RES)
+def test_emu_mini_c2(res):
+    spec = synth.SynthSpec(reads_mean=400.0)
+    b = synth.generate(spec, 0, 12)
+    check(opts_for(spec, res), synth.tid_to_gid(spec), b, res)
+
+
+@pytest.mark.parametrize("res", ["cr-like", "cr-like-em", "parsimony", "parsimony-em"])
+def test_emu_mini_c4_usa(res):
+    spec = synth.SynthSpec(usa_mode=True, reads_mean=400.0, n_genes=2000)
+    b = synth.generate(spec, 0, 10)
+    check(opts_for(spec, res), synth.tid_to_gid(spec), b, res)
+
+
+@pytest.mark.parametrize("res", ["parsimony", "parsimony-em", "parsimony-gene", "cr-like-em"])
+@pytest.mark.parametrize("thresh", [1000, 40, 3, 0])
+def test_emu_dense_umi_space_components(res, thresh):
+    # 4-base UMIs (256 values) and few genes: large 1-Hamming components. thresh selects the
+    # mid-size cooperative cover (33..thresh), the per-thread cover (<= 32) or the cr-like
+    # fallback (> thresh, AFQ_FLAG_ALT)
+    spec = synth.SynthSpec(n_genes=40, umi_len=4, reads_mean=500.0, reads_per_umi=1.5, umi_err=0.05, zipf_s=0.7)
+    b = synth.generate(spec, 0, 6)
+    got = check(opts_for(spec, res, large_graph_thresh=thresh, small_thresh=0), synth.tid_to_gid(spec), b, f"{res}/{thresh}")
+    if thresh <= 3 and res.startswith("parsimony"):
+        assert (got.flags & FLAG_ALT).any()
+
+
+@pytest.mark.parametrize("res", ["parsimony", "parsimony-em"])
+def test_emu_exact_umi(res):
+    spec = synth.SynthSpec(n_genes=200, umi_len=5, reads_mean=300.0)
+    b = synth.generate(spec, 0, 6)
+    check(opts_for(spec, res, pug_exact_umi=True, small_thresh=0), synth.tid_to_gid(spec), b, res)
+
+
+@pytest.mark.parametrize("res", ALL_RES)
+def test_emu_edge_cases(res):
+    t2g = np.arange(10, dtype=np.uint32)
+    cells = [[], [(5, [1])], [(5, [1, 2])], [(7, [])], [(1, [0])] * 120 + [(2, [0, 3])] * 2, [],
+             [(9, [0, 1, 2, 3, 4]), (9, [0, 1, 2, 3, 5]), (8, [0, 1, 2]), (8, [0, 1, 2, 3])]]
+    b = CellBatch.from_cells(cells)
+    for st in (100, 0):
+        check(QuantOpts(resolution=res, num_gene_ids=10, num_rows=10, small_thresh=st), t2g, b, f"{res}/{st}")
+
+
+def test_emu_uniform_init_and_many_gene_labels():
+    spec = synth.SynthSpec(n_genes=60, reads_mean=300.0, p_multi2=0.3, p_multi3=0.3, reads_per_umi=2.0)
+    b = synth.generate(spec, 0, 6)
+    t2g = synth.tid_to_gid(spec)
+    for res in ("cr-like-em", "parsimony-em"):
+        check(opts_for(spec, res, init_uniform=True, small_thresh=0), t2g, b, res)
+        check(opts_for(spec, res, small_thresh=0), t2g, b, res)
