@@ -1,0 +1,593 @@
+// host_quant.cpp — C++ host side of `alevin-fry quant`: the replacement for
+// quant::quantify / do_quantify (reference src/quant.rs:359-396, 1327-1951) with the worker
+// pool (src/quant.rs:659-1325) delegated to the CUDA C-ABI (include/afq.h).
+//
+// Contract honoured: input-dir files, t2g parsing (src/utils.rs:487-662),
+// record-type sniffing (src/utils.rs:313-377), output files and their formats
+// (src/quant.rs:1588-1613, 1786-1847, 1913-1933). Rows are always emitted in chunk order
+// (the reference's order with one worker, `-t 2`).
+#include <charconv>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <string>
+#include <sys/stat.h>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+#include "../../include/afq.h"
+#include "../../include/afq_host.h"
+#include "rad.h"
+
+namespace {
+using namespace afqh;
+
+struct Fail { std::string msg; };
+#define REQUIRE(cond, m) do { if (!(cond)) throw Fail{m}; } while (0)
+
+bool file_exists(const std::string& p) { struct stat st; return stat(p.c_str(), &st) == 0; }
+void mkdirs(const std::string& p) {
+  std::string cur;
+  for (size_t i = 0; i <= p.size(); ++i) {
+    if (i == p.size() || p[i] == '/') { if (!cur.empty()) mkdir(cur.c_str(), 0755); }
+    if (i < p.size()) cur.push_back(p[i]);
+  }
+}
+std::string slurp(const std::string& p) {
+  std::ifstream f(p, std::ios::binary);
+  std::stringstream ss; ss << f.rdbuf();
+  return ss.str();
+}
+// minimal JSON probe: value of a top-level boolean key
+bool json_bool(const std::string& js, const std::string& key, bool& out) {
+  size_t k = js.find("\"" + key + "\"");
+  if (k == std::string::npos) return false;
+  size_t c = js.find(':', k);
+  if (c == std::string::npos) return false;
+  size_t v = js.find_first_not_of(" \t\r\n", c + 1);
+  if (v == std::string::npos) return false;
+  if (js.compare(v, 4, "true") == 0) { out = true; return true; }
+  if (js.compare(v, 5, "false") == 0) { out = false; return true; }
+  return false;
+}
+std::string json_escape(const std::string& s) {
+  std::string o;
+  for (unsigned char c : s) {
+    switch (c) {
+      case '"': o += "\\\""; break;
+      case '\\': o += "\\\\"; break;
+      case '\n': o += "\\n"; break;
+      case '\r': o += "\\r"; break;
+      case '\t': o += "\\t"; break;
+      default:
+        if (c < 0x20) { char b[8]; snprintf(b, sizeof b, "\\u%04x", c); o += b; } else o.push_back((char)c);
+    }
+  }
+  return o;
+}
+
+// Rust `{}` for f32: shortest round-trip digits, never scientific, "NaN" / "inf" spellings.
+void append_f32(std::string& out, float v) {
+  if (std::isnan(v)) { out += "NaN"; return; }
+  if (std::isinf(v)) { out += v < 0 ? "-inf" : "inf"; return; }
+  char buf[128];
+  auto r = std::to_chars(buf, buf + sizeof buf, v, std::chars_format::fixed);
+  out.append(buf, r.ptr);
+}
+void append_u64(std::string& out, uint64_t v) {
+  char buf[24];
+  auto r = std::to_chars(buf, buf + sizeof buf, v);
+  out.append(buf, r.ptr);
+}
+
+// needletail bitmer_to_bytes: A=0 C=1 G=2 T=3, first base in the most significant used bits
+std::string decode_barcode(uint64_t bc, unsigned len) {
+  static const char N[4] = {'A', 'C', 'G', 'T'};
+  std::string s(len, 'A');
+  for (unsigned i = 0; i < len; ++i) s[len - 1 - i] = N[(bc >> (2 * i)) & 3];
+  return s;
+}
+bool encode_barcode(const std::string& s, uint64_t& out) {
+  out = 0;
+  for (char c : s) {
+    uint64_t v;
+    switch (c) { case 'A': case 'a': case 'N': v = 0; break; case 'C': case 'c': v = 1; break;
+                 case 'G': case 'g': v = 2; break; case 'T': case 't': v = 3; break; default: return false; }
+    out = (out << 2) | v;
+  }
+  return true;
+}
+
+struct T2G {
+  std::vector<uint32_t> tid_to_gid;
+  std::vector<std::string> gene_names;
+  bool usa = false;
+  uint32_t num_gene_ids = 0, num_rows = 0;
+};
+
+// parse_tg_map (src/utils.rs:487-662): 2 columns => gene ids in first-seen order; 3 columns =>
+// spliced id 2k / unspliced 2k+1. Every RAD reference must be mapped.
+T2G parse_t2g(const std::string& path, const std::vector<std::string>& ref_names) {
+  std::unordered_map<std::string, uint32_t> rname;
+  rname.reserve(ref_names.size() * 2);
+  for (uint32_t i = 0; i < ref_names.size(); ++i) rname.emplace(ref_names[i], i);
+  std::ifstream f(path);
+  REQUIRE(f.good(), "couldn't open file " + path);
+  T2G t;
+  t.tid_to_gid.assign(ref_names.size(), UINT32_MAX);
+  std::unordered_map<std::string, uint32_t> gid;
+  std::string line;
+  int ncol = 0;
+  size_t found = 0;
+  uint32_t next_gid = 0;
+  while (std::getline(f, line)) {
+    if (!line.empty() && line.back() == '\r') line.pop_back();
+    if (line.empty()) continue;
+    std::vector<std::string> col;
+    size_t a = 0;
+    for (;;) { size_t b = line.find('\t', a); col.push_back(line.substr(a, b == std::string::npos ? b : b - a)); if (b == std::string::npos) break; a = b + 1; }
+    if (ncol == 0) {
+      ncol = (int)col.size();
+      REQUIRE(ncol == 2 || ncol == 3, "Transcript-gene mapping must have either 2 or 3 columns.");
+      t.usa = ncol == 3;
+    }
+    REQUIRE((int)col.size() == ncol, "failed to parse the transcript-to-gene map : inconsistent column count.");
+    uint32_t g;
+    auto it = gid.find(col[1]);
+    if (it == gid.end()) {
+      g = t.usa ? next_gid : (uint32_t)gid.size();
+      next_gid += 2;
+      gid.emplace(col[1], g);
+      t.gene_names.push_back(col[1]);
+    } else g = it->second;
+    auto rt = rname.find(col[0]);
+    if (rt != rname.end()) {
+      ++found;
+      if (!t.usa) t.tid_to_gid[rt->second] = g;
+      else if (col[2] == "U" || col[2] == "u") t.tid_to_gid[rt->second] = g + 1;
+      else if (col[2] == "S" || col[2] == "s") t.tid_to_gid[rt->second] = g;
+      else throw Fail{"Third column in 3 column txp-to-gene file must be S or U"};
+    }
+  }
+  REQUIRE(found == ref_names.size(), "The tg-map must contain a gene mapping for all transcripts in the header");
+  for (uint32_t v : t.tid_to_gid) REQUIRE(v != UINT32_MAX, "The tg-map must contain a gene mapping for all transcripts in the header");
+  const uint32_t G = (uint32_t)t.gene_names.size();
+  if (t.usa) { t.num_gene_ids = 2 * G; t.num_rows = 3 * G; }  // mid = max id + 2 = 2G; mid + mid/2 (src/quant.rs:1627-1645)
+  else { t.num_gene_ids = G; t.num_rows = G; }
+  return t;
+}
+
+const char* resolution_debug_name(const std::string& r) {  // ResolutionStrategy Debug names (src/quant.rs:81-97)
+  if (r == "trivial") return "Trivial";
+  if (r == "cr-like") return "CellRangerLike";
+  if (r == "cr-like-em") return "CellRangerLikeEm";
+  if (r == "parsimony-em") return "ParsimonyEm";
+  if (r == "parsimony") return "Parsimony";
+  if (r == "parsimony-gene-em") return "ParsimonyGeneEm";
+  if (r == "parsimony-gene") return "ParsimonyGene";
+  return nullptr;
+}
+int resolution_code(const std::string& r) {
+  if (r == "trivial") return AFQ_RES_TRIVIAL;
+  if (r == "cr-like") return AFQ_RES_CR_LIKE;
+  if (r == "cr-like-em") return AFQ_RES_CR_LIKE_EM;
+  if (r == "parsimony-em") return AFQ_RES_PARSIMONY_EM;
+  if (r == "parsimony") return AFQ_RES_PARSIMONY;
+  if (r == "parsimony-gene-em") return AFQ_RES_PARSIMONY_GENE_EM;
+  if (r == "parsimony-gene") return AFQ_RES_PARSIMONY_GENE;
+  return -1;
+}
+
+template <class T>
+struct Pinned {  // growable pinned array (afq_host_alloc)
+  T* p = nullptr; size_t n = 0, cap = 0;
+  ~Pinned() { if (p) afq_host_free(p); }
+  void reserve(size_t want) {
+    if (want <= cap) return;
+    size_t nc = cap ? cap : 1024;
+    while (nc < want) nc = nc + nc / 2 + 1024;
+    void* q = nullptr;
+    if (afq_host_alloc(&q, nc * sizeof(T)) != AFQ_OK) throw Fail{"pinned host allocation failed"};
+    if (n) memcpy(q, p, n * sizeof(T));
+    if (p) afq_host_free(p);
+    p = (T*)q; cap = nc;
+  }
+  void push(T v) { if (n == cap) reserve(n + 1); p[n++] = v; }
+  void clear() { n = 0; }
+};
+
+struct HostBatch {
+  Pinned<uint64_t> cell_rec_off;
+  Pinned<uint32_t> umi, ref_off, refs;
+  std::vector<uint64_t> barcodes;
+  std::vector<uint32_t> nrec;
+  uint64_t first_cell = 0;
+  void reset(uint64_t first) {
+    cell_rec_off.clear(); umi.clear(); ref_off.clear(); refs.clear(); barcodes.clear(); nrec.clear();
+    cell_rec_off.push(0); ref_off.push(0); first_cell = first;
+  }
+  uint64_t n_cells() const { return barcodes.size(); }
+};
+
+struct Outputs {
+  FILE* rows = nullptr;
+  FILE* feat = nullptr;
+  std::vector<std::string> mtx_chunks;
+  uint64_t nnz = 0, row_index = 0;
+  std::vector<uint64_t> alt, empty, tiny;
+};
+
+void consume(const HostBatch& hb, const afq_result& r, unsigned bc_len, Outputs& o) {
+  std::string rows, feat, mtx;
+  for (uint64_t c = 0; c < r.n_cells; ++c) {
+    const uint64_t cell_num = hb.first_cell + c;
+    if (r.flags[c] & AFQ_FLAG_ALT) o.alt.push_back(cell_num);
+    if (r.flags[c] & AFQ_FLAG_TINY) o.tiny.push_back(cell_num);
+    if (r.flags[c] & AFQ_FLAG_EMPTY) o.empty.push_back(cell_num);
+    const std::string bc = decode_barcode(hb.barcodes[c], bc_len);
+    rows += bc; rows.push_back('\n');
+    // featureDump (src/quant.rs:1181-1196, 1248-1260); unmapped counts unavailable => 0
+    const uint32_t num_mapped = hb.nrec[c], num_unmapped = 0;
+    const float sum_umi = r.sum_umi[c], max_umi = r.max_umi[c];
+    const float dedup_rate = sum_umi / (float)num_mapped;
+    const float mapping_rate = (float)num_mapped / (float)(num_mapped + num_unmapped);
+    const float mean_expr = sum_umi / (float)r.num_expr[c];
+    const float mean_by_max = mean_expr / max_umi;
+    feat += bc; feat.push_back('\t');
+    append_u64(feat, (uint64_t)num_mapped + num_unmapped); feat.push_back('\t');
+    append_u64(feat, num_mapped); feat.push_back('\t');
+    append_f32(feat, sum_umi); feat.push_back('\t');
+    append_f32(feat, mapping_rate); feat.push_back('\t');
+    append_f32(feat, dedup_rate); feat.push_back('\t');
+    append_f32(feat, mean_by_max); feat.push_back('\t');
+    append_u64(feat, r.num_expr[c]); feat.push_back('\t');
+    append_u64(feat, r.num_over_mean[c]); feat.push_back('\n');
+    for (uint64_t k = r.row_ptr[c]; k < r.row_ptr[c + 1]; ++k) {
+      append_u64(mtx, o.row_index + 1); mtx.push_back(' ');
+      append_u64(mtx, (uint64_t)r.col[k] + 1); mtx.push_back(' ');
+      append_f32(mtx, r.val[k]); mtx.push_back('\n');
+    }
+    ++o.row_index;
+  }
+  o.nnz += r.nnz;
+  fwrite(rows.data(), 1, rows.size(), o.rows);
+  fwrite(feat.data(), 1, feat.size(), o.feat);
+  o.mtx_chunks.push_back(std::move(mtx));
+}
+
+std::string lower(std::string s) { for (auto& c : s) c = (char)tolower((unsigned char)c); return s; }
+
+void json_u64_list(std::string& js, const std::vector<uint64_t>& v, const std::string& ind) {
+  if (v.empty()) { js += "[]"; return; }
+  js += "[\n";
+  for (size_t i = 0; i < v.size(); ++i) { js += ind + "  "; append_u64(js, v[i]); js += i + 1 < v.size() ? ",\n" : "\n"; }
+  js += ind + "]";
+}
+
+int quantify_impl(const afqh_quant_opts& o) {
+  REQUIRE(o.input_dir && o.tg_map && o.output_dir && o.resolution, "input_dir, tg_map, output_dir and resolution are required");
+  const std::string in = o.input_dir, out = o.output_dir;
+  const std::string res = lower(o.resolution);
+  REQUIRE(resolution_code(res) >= 0, "invalid value '" + std::string(o.resolution) + "' for '--resolution <RESOLUTION>'");
+  const std::string sa = o.sa_model ? lower(o.sa_model) : "winner-take-all";
+  REQUIRE(sa == "winner-take-all" || sa == "prefer-ambig", "invalid value for '--sa-model'");
+  REQUIRE(sa == "winner-take-all", "--sa-model prefer-ambig is not implemented on the CUDA path");
+  REQUIRE(o.num_bootstraps == 0, "bootstrapping (-b) is not implemented on the CUDA path (the reference's RNG is unseeded; see SURVEY.md §8(f) N4)");
+  REQUIRE(!o.dump_eq, "--dump-eqclasses is not implemented on the CUDA path yet (SURVEY.md §8(f) N3)");
+  // src/main.rs:733-734, 759, 812-820
+  REQUIRE(file_exists(in + "/generate_permit_list.json"), "The input directory " + in + " did not contain a generate_permit_list.json file; please run generate-permit-list and collate first.");
+  bool velo = false;
+  json_bool(slurp(in + "/generate_permit_list.json"), "velo_mode", velo);
+  REQUIRE(!velo, "velo_mode quantification is not implemented (reference: unimplemented!, src/quant.rs:2033)");
+  // src/quant.rs:364-371
+  REQUIRE(file_exists(in + "/collate.json"), "could not open the collate.json file.");
+  bool compressed = false;
+  REQUIRE(json_bool(slurp(in + "/collate.json"), "compressed_output", compressed), "could not read compressed_output field from collate metadata.");
+  REQUIRE(!compressed, "snappy-compressed collated RAD (map.collated.rad.sz) is not supported yet: re-run collate without --compress");
+  const std::string rad_path = in + "/map.collated.rad";
+  FILE* f = fopen(rad_path.c_str(), "rb");
+  REQUIRE(f, "run collate before quant (could not open " + rad_path + ")");
+  std::vector<char> iobuf(8 << 20);
+  setvbuf(f, iobuf.data(), _IOFBF, iobuf.size());
+  Reader rd(f);
+  RadPrelude pre;
+  std::string perr;
+  if (!parse_prelude(rd, pre, perr)) { fclose(f); throw Fail{"RAD prelude: " + perr}; }
+  // record-type sniffing (src/utils.rs:313-377)
+  if (auto nb = pre.file_tag("num_barcodes")) { if (nb->u > 1) { fclose(f); throw Fail{"multi-barcode RAD files are not supported by this build (SURVEY.md §8(f) N4)"}; } }
+  if (RadPrelude::has(pre.aln_tags, "as") && RadPrelude::has(pre.aln_tags, "start") && RadPrelude::has(pre.aln_tags, "end")) { fclose(f); throw Fail{"long-read RAD files are not supported by this build (SURVEY.md §8(f) N4)"}; }
+  if (RadPrelude::has(pre.aln_tags, "type") && RadPrelude::has(pre.aln_tags, "start_pos") && RadPrelude::has(pre.aln_tags, "frag_len")) { fclose(f); throw Fail{"To process atac-seq data, you should use the \"atac\" sub-command"}; }
+  const TagValue* cbl = pre.file_tag("cblen");
+  if (!cbl) cbl = pre.file_tag("b1len");
+  if (!cbl) cbl = pre.file_tag("b0len");
+  if (!cbl) { fclose(f); throw Fail{"tag map must contain cblen or bNlen for barcode length"}; }
+  const unsigned bc_len = (unsigned)cbl->u;
+  const TagValue* ul = pre.file_tag("ulen");
+  const unsigned umi_len = ul ? (unsigned)ul->u : 0;
+  RecordLayout lay;
+  if (!make_layout(pre, lay, perr)) { fclose(f); throw Fail{perr}; }
+  if (umi_len > 16 || lay.umi_size > 8) { fclose(f); throw Fail{"UMIs longer than 16 bases are not supported on the CUDA path"}; }
+
+  T2G t2g = parse_t2g(o.tg_map, pre.ref_names);
+
+  // --quant-subset (src/utils.rs:1074-1095): one barcode per line
+  bool filtering = false;
+  std::unordered_set<uint64_t> keep;
+  uint64_t num_cells = pre.num_chunks;
+  if (o.filter_list && *o.filter_list) {
+    std::ifstream fl(o.filter_list);
+    if (!fl.good()) { fclose(f); throw Fail{"couldn't open file " + std::string(o.filter_list)}; }
+    std::string line;
+    while (std::getline(fl, line)) {
+      if (!line.empty() && line.back() == '\r') line.pop_back();
+      if (line.empty()) continue;
+      uint64_t v;
+      if (!encode_barcode(line.substr(0, bc_len), v)) { fclose(f); throw Fail{"bad barcode in --quant-subset file: " + line}; }
+      keep.insert(v);
+    }
+    filtering = true;
+    num_cells = keep.size();
+  }
+
+  afq_config cfg{};
+  cfg.resolution = resolution_code(res);
+  cfg.usa_mode = t2g.usa;
+  cfg.em_init_uniform = o.init_uniform;
+  cfg.pug_exact_umi = o.pug_exact_umi;
+  cfg.sa_model = AFQ_SA_WINNER_TAKE_ALL;
+  cfg.num_gene_ids = t2g.num_gene_ids;
+  cfg.num_rows = t2g.num_rows;
+  cfg.small_thresh = o.small_thresh;
+  cfg.large_graph_thresh = o.large_graph_thresh;
+  cfg.barcode_len = (uint16_t)bc_len;
+  cfg.umi_len = (uint16_t)umi_len;
+  cfg.device = o.device;
+  afq_ctx* ctx = nullptr;
+  if (afq_create(&cfg, t2g.tid_to_gid.data(), t2g.tid_to_gid.size(), &ctx) != AFQ_OK) {
+    std::string m = afq_last_error(nullptr);
+    fclose(f);
+    throw Fail{"afq_create: " + m};
+  }
+
+  mkdirs(out);
+  mkdirs(out + "/alevin");
+  Outputs outs;
+  outs.rows = fopen((out + "/alevin/quants_mat_rows.txt").c_str(), "wb");
+  outs.feat = fopen((out + "/featureDump.txt").c_str(), "wb");
+  if (!outs.rows || !outs.feat) { afq_destroy(ctx); fclose(f); throw Fail{"could not create output files in " + out}; }
+  fputs("CB\tCorrectedReads\tMappedReads\tDeduplicatedReads\tMappingRate\tDedupRate\tMeanByMax\tNumGenesExpressed\tNumGenesOverMean\n", outs.feat);
+
+  const uint64_t batch_records = o.batch_records ? o.batch_records : (32ull << 20);
+  constexpr int NB = 3;
+  HostBatch hb[NB];
+  uint64_t tickets[NB] = {0};
+  bool inflight[NB] = {false};
+  int cur = 0;
+  uint64_t cells_seen = 0, total_records = 0;
+  std::string failure;
+  auto finish = [&](int i) {
+    afq_result r{};
+    if (afq_wait(ctx, tickets[i], &r) != AFQ_OK) throw Fail{std::string("afq_wait: ") + afq_last_error(ctx)};
+    consume(hb[i], r, bc_len, outs);
+    afq_result_release(ctx, &r);
+    inflight[i] = false;
+  };
+  auto submit = [&](int i) {
+    HostBatch& b = hb[i];
+    if (b.n_cells() == 0) return;
+    afq_batch ab{};
+    ab.first_cell_index = b.first_cell;
+    ab.n_cells = b.n_cells();
+    ab.n_records = b.umi.n;
+    ab.n_refs_total = b.refs.n;
+    ab.cell_rec_offsets = b.cell_rec_off.p;
+    ab.rec_umi32 = b.umi.p;
+    ab.rec_ref_offsets = b.ref_off.p;
+    ab.refs = b.refs.p;
+    if (afq_submit(ctx, &ab, &tickets[i]) != AFQ_OK) throw Fail{std::string("afq_submit: ") + afq_last_error(ctx)};
+    inflight[i] = true;
+  };
+  try {
+    hb[cur].reset(0);
+    std::vector<unsigned char> chunk;
+    for (uint64_t ch = 0; ch < pre.num_chunks; ++ch) {
+      uint32_t nbytes, nrec;
+      REQUIRE(rd.get(nbytes) && rd.get(nrec), "truncated chunk header in " + rad_path);
+      REQUIRE(nbytes >= 8, "corrupt chunk header");
+      chunk.resize(nbytes - 8);
+      REQUIRE(rd.read(chunk.data(), chunk.size()), "truncated chunk body");
+      const unsigned char* p = chunk.data();
+      const unsigned char* end = p + chunk.size();
+      HostBatch& b = hb[cur];
+      uint64_t bc = 0;
+      bool take = true;
+      const size_t rec_start = b.umi.n, ref_start = b.refs.n;
+      for (uint32_t r = 0; r < nrec; ++r) {
+        REQUIRE(p + 4 + lay.read_bytes <= end, "record overruns its chunk");
+        uint32_t na; memcpy(&na, p, 4); p += 4;
+        uint64_t rbc = 0, rumi = 0;
+        memcpy(&rbc, p + lay.bc_off, lay.bc_size);
+        memcpy(&rumi, p + lay.umi_off, lay.umi_size);
+        p += lay.read_bytes;
+        REQUIRE(p + (size_t)na * lay.aln_bytes <= end, "alignments overrun their chunk");
+        if (r == 0) { bc = rbc; if (filtering && !keep.count(bc)) take = false; }
+        if (take) {
+          b.umi.push((uint32_t)rumi);
+          for (uint32_t a = 0; a < na; ++a) {
+            uint32_t ref; memcpy(&ref, p + (size_t)a * lay.aln_bytes + lay.refid_off, 4);
+            b.refs.push(ref & 0x7FFFFFFFu);  // bit 31 = orientation (src/convert.rs:442-445)
+          }
+          b.ref_off.push((uint32_t)b.refs.n);
+        }
+        p += (size_t)na * lay.aln_bytes;
+      }
+      if (!take) { b.umi.n = rec_start; b.refs.n = ref_start; b.ref_off.n = rec_start + 1; continue; }
+      REQUIRE(nrec > 0, "Discovered empty chunk; should not happen!");
+      b.cell_rec_off.push(b.umi.n);
+      b.barcodes.push_back(bc);
+      b.nrec.push_back(nrec);
+      total_records += nrec;
+      ++cells_seen;
+      if (b.umi.n >= batch_records || b.refs.n >= (3ull << 30)) {
+        submit(cur);
+        const int nxt = (cur + 1) % NB;
+        if (inflight[nxt]) finish(nxt);
+        cur = nxt;
+        hb[cur].reset(cells_seen);
+      }
+    }
+    submit(cur);
+    for (int k = 1; k <= NB; ++k) { const int i = (cur + k) % NB; if (inflight[i]) finish(i); }
+  } catch (const Fail& e) { failure = e.msg; }
+  fclose(f);
+  if (!failure.empty()) {
+    for (int i = 0; i < NB; ++i) if (inflight[i]) { afq_result r{}; if (afq_wait(ctx, tickets[i], &r) == AFQ_OK) afq_result_release(ctx, &r); }
+    afq_destroy(ctx);
+    fclose(outs.rows); fclose(outs.feat);
+    throw Fail{failure};
+  }
+  afq_destroy(ctx);
+  fclose(outs.rows);
+  fclose(outs.feat);
+
+  // quants_mat_cols.txt (src/quant.rs:1786-1809)
+  {
+    std::string cols;
+    for (auto& g : t2g.gene_names) { cols += g; cols.push_back('\n'); }
+    if (t2g.usa) {
+      for (auto& g : t2g.gene_names) { cols += g; cols += "-U\n"; }
+      for (auto& g : t2g.gene_names) { cols += g; cols += "-A\n"; }
+    }
+    FILE* fc = fopen((out + "/alevin/quants_mat_cols.txt").c_str(), "wb");
+    REQUIRE(fc, "couldn't create gene name file.");
+    fwrite(cols.data(), 1, cols.size(), fc);
+    fclose(fc);
+  }
+  // quants_mat.mtx — sprs::io::write_matrix_market layout
+  {
+    FILE* fm = fopen((out + "/alevin/quants_mat.mtx").c_str(), "wb");
+    REQUIRE(fm, "couldn't create quants_mat.mtx");
+    std::string hdr = "%%MatrixMarket matrix coordinate real general\n% written by sprs\n";
+    append_u64(hdr, num_cells); hdr.push_back(' ');
+    append_u64(hdr, t2g.num_rows); hdr.push_back(' ');
+    append_u64(hdr, outs.nnz); hdr.push_back('\n');
+    fwrite(hdr.data(), 1, hdr.size(), fm);
+    for (auto& c : outs.mtx_chunks) fwrite(c.data(), 1, c.size(), fm);
+    fclose(fm);
+  }
+  // quant.json (src/quant.rs:1913-1933); keys in sorted order (serde_json Map without preserve_order)
+  {
+    std::string js = "{\n";
+    js += "  \"alt_resolved_cell_numbers\": "; json_u64_list(js, outs.alt, "  "); js += ",\n";
+    js += "  \"cmd\": \"" + json_escape(o.cmdline ? o.cmdline : "") + "\",\n";
+    js += std::string("  \"dump_eq\": ") + (o.dump_eq ? "true" : "false") + ",\n";
+    js += "  \"empty_resolved_cell_numbers\": "; json_u64_list(js, outs.empty, "  "); js += ",\n";
+    js += "  \"num_genes\": "; append_u64(js, t2g.num_rows); js += ",\n";
+    js += "  \"num_quantified_cells\": "; append_u64(js, num_cells); js += ",\n";
+    js += "  \"num_tiny_cell_resolved\": "; append_u64(js, outs.tiny.size()); js += ",\n";
+    js += "  \"quant_options\": {\n";
+    js += "    \"cmdline\": \"" + json_escape(o.cmdline ? o.cmdline : "") + "\",\n";
+    js += std::string("    \"dump_eq\": ") + (o.dump_eq ? "true" : "false") + ",\n";
+    js += std::string("    \"filter_list\": ") + ((o.filter_list && *o.filter_list) ? "\"" + json_escape(o.filter_list) + "\"" : std::string("null")) + ",\n";
+    js += std::string("    \"init_uniform\": ") + (o.init_uniform ? "true" : "false") + ",\n";
+    js += "    \"input_dir\": \"" + json_escape(in) + "\",\n";
+    js += "    \"large_graph_thresh\": "; append_u64(js, o.large_graph_thresh); js += ",\n";
+    js += "    \"num_bootstraps\": "; append_u64(js, o.num_bootstraps); js += ",\n";
+    js += "    \"num_threads\": "; append_u64(js, o.num_threads < 2 ? 2 : o.num_threads); js += ",\n";
+    js += "    \"output_dir\": \"" + json_escape(out) + "\",\n";
+    js += std::string("    \"pug_exact_umi\": ") + (o.pug_exact_umi ? "true" : "false") + ",\n";
+    js += std::string("    \"resolution\": \"") + resolution_debug_name(res) + "\",\n";
+    js += "    \"sa_model\": \"WinnerTakeAll\",\n";
+    js += "    \"small_thresh\": "; append_u64(js, o.small_thresh); js += ",\n";
+    js += std::string("    \"summary_stat\": ") + (o.summary_stat ? "true" : "false") + ",\n";
+    js += "    \"tg_map\": \"" + json_escape(o.tg_map) + "\",\n";
+    js += "    \"version\": \"" + json_escape(o.version ? o.version : "") + "\"\n";
+    js += "  },\n";
+    js += std::string("  \"resolution_strategy\": \"") + resolution_debug_name(res) + "\",\n";
+    js += "  \"tiny_cell_resolved_cell_numbers\": "; json_u64_list(js, outs.tiny, "  "); js += ",\n";
+    js += std::string("  \"usa_mode\": ") + (t2g.usa ? "true" : "false") + ",\n";
+    js += "  \"version_str\": \"" + json_escape(o.version ? o.version : "") + "\"\n";
+    js += "}";
+    FILE* fj = fopen((out + "/quant.json").c_str(), "wb");
+    REQUIRE(fj, "couldn't create quant.json file.");
+    fwrite(js.data(), 1, js.size(), fj);
+    fclose(fj);
+  }
+  (void)total_records;
+  return 0;
+}
+
+template <class T> void put(FILE* f, T v) { fwrite(&v, sizeof(T), 1, f); }
+void put_str16(FILE* f, const std::string& s) { put<uint16_t>(f, (uint16_t)s.size()); fwrite(s.data(), 1, s.size(), f); }
+void put_tag(FILE* f, const std::string& name, uint8_t type) { put_str16(f, name); put<uint8_t>(f, type); }
+
+}  // namespace
+
+extern "C" {
+
+int afqh_quantify(const afqh_quant_opts* opts, char* err, size_t errlen) {
+  if (!opts) return 1;
+  try {
+    return quantify_impl(*opts);
+  } catch (const Fail& e) {
+    if (err && errlen) { strncpy(err, e.msg.c_str(), errlen - 1); err[errlen - 1] = 0; }
+    return 1;
+  } catch (const std::exception& e) {
+    if (err && errlen) { strncpy(err, e.what(), errlen - 1); err[errlen - 1] = 0; }
+    return 1;
+  }
+}
+
+int afqh_write_collated_rad(const char* dir, uint64_t n_cells, const uint64_t* cell_rec_offsets,
+                            const uint64_t* cell_barcodes, const uint32_t* rec_umi32,
+                            const uint32_t* rec_ref_offsets, const uint32_t* refs,
+                            const char* const* ref_names, uint64_t n_refs, uint16_t bc_len,
+                            uint16_t umi_len, char* err, size_t errlen) {
+  auto fail = [&](const std::string& m) { if (err && errlen) { strncpy(err, m.c_str(), errlen - 1); err[errlen - 1] = 0; } return 1; };
+  if (bc_len == 0 || bc_len > 32 || umi_len == 0 || umi_len > 16) return fail("bc_len must be 1..32 and umi_len 1..16");
+  const std::string d = dir;
+  mkdirs(d);
+  FILE* f = fopen((d + "/map.collated.rad").c_str(), "wb");
+  if (!f) return fail("cannot create " + d + "/map.collated.rad");
+  auto width_type = [](unsigned len) -> uint8_t { return len <= 4 ? T_U8 : len <= 8 ? T_U16 : len <= 16 ? T_U32 : T_U64; };  // src/convert.rs:323-343
+  const uint8_t bt = width_type(bc_len), ut = width_type(umi_len);
+  put<uint8_t>(f, 0);
+  put<uint64_t>(f, n_refs);
+  for (uint64_t i = 0; i < n_refs; ++i) put_str16(f, ref_names[i]);
+  put<uint64_t>(f, n_cells);
+  put<uint16_t>(f, 2); put_tag(f, "cblen", T_U16); put_tag(f, "ulen", T_U16);
+  put<uint16_t>(f, 2); put_tag(f, "b", bt); put_tag(f, "u", ut);
+  put<uint16_t>(f, 1); put_tag(f, "compressed_ori_refid", T_U32);
+  put<uint16_t>(f, bc_len); put<uint16_t>(f, umi_len);
+  std::vector<unsigned char> buf;
+  for (uint64_t c = 0; c < n_cells; ++c) {
+    buf.clear();
+    auto app = [&](const void* p, size_t n) { const unsigned char* q = (const unsigned char*)p; buf.insert(buf.end(), q, q + n); };
+    const uint64_t r0 = cell_rec_offsets[c], r1 = cell_rec_offsets[c + 1];
+    for (uint64_t r = r0; r < r1; ++r) {
+      const uint32_t na = rec_ref_offsets[r + 1] - rec_ref_offsets[r];
+      app(&na, 4);
+      const uint64_t bc = cell_barcodes[c], um = rec_umi32[r];
+      app(&bc, type_size(bt));
+      app(&um, type_size(ut));
+      for (uint32_t k = 0; k < na; ++k) { const uint32_t v = refs[rec_ref_offsets[r] + k] | 0x80000000u; app(&v, 4); }
+    }
+    put<uint32_t>(f, (uint32_t)(buf.size() + 8));
+    put<uint32_t>(f, (uint32_t)(r1 - r0));
+    fwrite(buf.data(), 1, buf.size(), f);
+  }
+  fclose(f);
+  FILE* j = fopen((d + "/collate.json").c_str(), "wb");
+  if (!j) return fail("cannot create collate.json");
+  fputs("{\n  \"compressed_output\": false\n}\n", j); fclose(j);
+  j = fopen((d + "/generate_permit_list.json").c_str(), "wb");
+  if (!j) return fail("cannot create generate_permit_list.json");
+  fputs("{\n  \"velo_mode\": false,\n  \"max-ambig-record\": 8\n}\n", j); fclose(j);
+  return 0;
+}
+
+}  // extern "C"

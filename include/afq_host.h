@@ -1,0 +1,52 @@
+/* afq_host.h — host-side drop-in for `alevin_fry::quant::quantify(QuantOpts)`
+ * (reference src/quant.rs:359, src/prog_opts.rs:24-43) and the `alevin-fry quant` CLI
+ * (src/main.rs:294-348, 633-821): reads <input-dir>/{generate_permit_list.json,
+ * collate.json, map.collated.rad}, the t2g TSV, and writes <output-dir>/{alevin/quants_mat.mtx,
+ * alevin/quants_mat_rows.txt, alevin/quants_mat_cols.txt, featureDump.txt, quant.json}
+ * (src/quant.rs:1588-1613, 1786-1847, 1913-1933). All per-cell compute goes through the
+ * CUDA C-ABI of afq.h (afq_submit / afq_wait); there is no CPU compute path here.
+ */
+#ifndef AFQ_HOST_H
+#define AFQ_HOST_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct afqh_quant_opts {          /* mirrors QuantOpts (src/prog_opts.rs:24-43)       */
+  const char* input_dir;                  /* -i/--input-dir                                   */
+  const char* tg_map;                     /* -m/--tg-map                                      */
+  const char* output_dir;                 /* -o/--output-dir                                  */
+  uint32_t num_threads;                   /* -t/--threads (host parse/format threads; floor 2) */
+  uint32_t num_bootstraps;                /* -b (must be 0: bootstrap is not on the CUDA path) */
+  int32_t init_uniform, summary_stat, dump_eq;
+  const char* resolution;                 /* -r, case-insensitive                             */
+  int32_t pug_exact_umi;                  /* derived from --umi-edit-dist                     */
+  const char* sa_model;                   /* --sa-model (winner-take-all only)                */
+  uint64_t small_thresh;                  /* --small-thresh                                   */
+  uint64_t large_graph_thresh;            /* --large-graph-thresh                             */
+  const char* filter_list;                /* --quant-subset or NULL                           */
+  const char* cmdline;
+  const char* version;
+  int32_t device;                         /* CUDA device ordinal                              */
+  uint64_t batch_records;                 /* records per device batch (0 = default 32M)       */
+} afqh_quant_opts;
+
+/* Runs the whole quant stage. Returns 0 on success; on failure writes a message to err.    */
+int afqh_quantify(const afqh_quant_opts* opts, char* err, size_t errlen);
+
+/* Test/bench helper: write a collated RAD directory (map.collated.rad, collate.json,
+ * generate_permit_list.json) in the wire format of SURVEY.md §8(b) from SoA arrays:
+ * one chunk per cell, read tags b:u32|u64 (by bc_len), u:u32|u64 (by umi_len), alignment tag
+ * compressed_ori_refid:u32 (orientation bit set = forward).                                */
+int afqh_write_collated_rad(const char* dir, uint64_t n_cells, const uint64_t* cell_rec_offsets,
+                            const uint64_t* cell_barcodes, const uint32_t* rec_umi32,
+                            const uint32_t* rec_ref_offsets, const uint32_t* refs,
+                            const char* const* ref_names, uint64_t n_refs, uint16_t bc_len,
+                            uint16_t umi_len, char* err, size_t errlen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,134 @@
+"""Host side (C++ `quantify` drop-in + CLI): CPU-tier argument/contract checks, and GPU-tier
+end-to-end runs from a synthetic collated RAD directory compared with the oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib
+from alevin_fry_b200 import QuantOpts, host, synth
+
+
+def make_input(tmp_path, spec, n_cells, first=0):
+    b = synth.generate(spec, first, n_cells)
+    d = tmp_path / "in"
+    names = host.write_synth_t2g(str(tmp_path / "t2g.tsv"), spec)
+    bcs = host.make_barcodes(first, n_cells)
+    host.write_collated_rad(str(d), b, bcs, names, 16, spec.umi_len)
+    return b, bcs, str(d), str(tmp_path / "t2g.tsv")
+
+
+def test_rad_writer_layout(tmp_path):
+    spec = synth.SynthSpec(n_genes=5, fixed_reads=3)
+    b, bcs, d, _ = make_input(tmp_path, spec, 2)
+    raw = open(os.path.join(d, "map.collated.rad"), "rb").read()
+    assert raw[0] == 0 and int.from_bytes(raw[1:9], "little") == 15           # is_paired, ref_count
+    assert raw[9:11] == (2).to_bytes(2, "little") and raw[11:13] == b"t0"     # first name: u16 len + bytes
+    assert b"compressed_ori_refid" in raw and b"cblen" in raw
+    import json
+    assert json.load(open(os.path.join(d, "collate.json")))["compressed_output"] is False
+
+
+def test_cli_argument_validation(tmp_path):
+    cli = host.CLI_PATH
+    r = subprocess.run([cli, "quant", "-i", str(tmp_path), "-m", "x", "-o", "y", "-r", "cr-like", "--umi-edit-dist", "1"], capture_output=True, text=True)
+    assert r.returncode == 1 and "doesn't currently support 1-edit UMI resolution" in r.stderr   # src/main.rs:672-682
+    r = subprocess.run([cli, "quant", "-i", str(tmp_path), "-m", "x", "-o", "y", "-r", "cr-like", "-b", "5"], capture_output=True, text=True)
+    assert r.returncode == 1 and "bootstrapping can only be used" in r.stderr                     # src/main.rs:713-728
+    r = subprocess.run([cli, "quant", "-i", str(tmp_path), "-m", "x", "-o", "y", "-r", "trivial", "-d"], capture_output=True, text=True)
+    assert r.returncode == 1 and "not meaningful in case of Trivial" in r.stderr                  # src/main.rs:705-711
+    r = subprocess.run([cli, "quant", "-i", str(tmp_path), "-m", "x", "-o", "y", "-r", "cr-like", "--use-eds"], capture_output=True, text=True)
+    assert r.returncode == 1 and "--use-eds is no longer supported" in r.stderr                   # src/main.rs:639-643
+    r = subprocess.run([cli, "quant", "-i", str(tmp_path), "-m", "x", "-o", str(tmp_path / "o"), "-r", "CR-LIKE"], capture_output=True, text=True)
+    assert r.returncode == 1 and "generate_permit_list.json" in r.stderr                           # src/main.rs:812-820
+    r = subprocess.run([cli, "quant", "-i", str(tmp_path), "-m", "x", "-o", "y", "-r", "full"], capture_output=True, text=True)
+    assert r.returncode == 1 and "invalid value" in r.stderr
+
+
+def test_quantify_fails_loudly_without_gpu(tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    spec = synth.SynthSpec(n_genes=20, fixed_reads=10)
+    _, _, d, t2g = make_input(tmp_path, spec, 3)
+    with pytest.raises(RuntimeError) as ei:
+        host.quantify(d, t2g, str(tmp_path / "out"), "cr-like")
+    assert "no CPU fallback" in str(ei.value)
+    # t2g problems are reported before any device work
+    open(tmp_path / "bad.tsv", "w").write("t0\tg0\n")
+    with pytest.raises(RuntimeError) as ei:
+        host.quantify(d, str(tmp_path / "bad.tsv"), str(tmp_path / "out"), "cr-like")
+    assert "tg-map must contain a gene mapping for all transcripts" in str(ei.value)
+
+
+def fmt_f32(v):
+    """Rust `{}` for f32 as the host writes it (shortest round-trip, fixed notation)."""
+    v = np.float32(v)
+    if np.isnan(v):
+        return "NaN"
+    s = np.format_float_positional(v, unique=True, trim="-")
+    return s
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("res,usa", [("cr-like", False), ("parsimony", False), ("cr-like-em", True), ("trivial", False)])
+def test_cli_end_to_end_matches_oracle(tmp_path, res, usa):
+    spec = synth.SynthSpec(n_genes=300, reads_mean=300.0, usa_mode=usa)
+    b, bcs, d, t2g_path = make_input(tmp_path, spec, 120)
+    out = str(tmp_path / "out")
+    r = subprocess.run([host.CLI_PATH, "quant", "-i", d, "-m", t2g_path, "-o", out, "-r", res, "-t", "4"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    q = host.load_quant_dir(out)
+    t2g = synth.tid_to_gid(spec)
+    thresh = 1000 if res.startswith("parsimony") else 0
+    o = QuantOpts(resolution=res, usa_mode=usa, num_gene_ids=spec.num_gene_ids, num_rows=spec.num_rows, large_graph_thresh=thresh)
+    want = oracle_lib.oracle_quant(o, t2g, b)
+    # MTX layout pinned by the reference's tests (tests/infer_matrix_market.rs:54-73; multi_barcode_integration.rs:1491-1498)
+    assert q["header"][0] == "%%MatrixMarket matrix coordinate real general"
+    assert q["dims"] == (120, spec.num_rows, want.nnz)
+    assert q["rows"] == [host.decode_barcode(x, 16) for x in bcs]
+    G = spec.n_genes
+    names = [f"g{i}" for i in range(G)]
+    assert q["cols"] == (names + [n + "-U" for n in names] + [n + "-A" for n in names] if usa else names)
+    got_rows = np.array([t[0] for t in q["triplets"]], dtype=np.int64)
+    got_cols = np.array([t[1] for t in q["triplets"]], dtype=np.uint32)
+    exp_rows = np.repeat(np.arange(120), np.diff(want.row_ptr.astype(np.int64)))
+    assert np.array_equal(got_rows, exp_rows) and np.array_equal(got_cols, want.col)
+    if res.endswith("-em"):
+        np.testing.assert_allclose(np.array([float(t[2]) for t in q["triplets"]], dtype=np.float32), want.val, rtol=1e-5)
+    else:
+        assert [t[2] for t in q["triplets"]] == [fmt_f32(v) for v in want.val]   # byte-identical value text
+    # featureDump: 9 columns, header, per-cell integer fields
+    fd = q["feature_dump"]
+    assert fd[0] == ["CB", "CorrectedReads", "MappedReads", "DeduplicatedReads", "MappingRate", "DedupRate", "MeanByMax", "NumGenesExpressed", "NumGenesOverMean"]
+    nrec = np.diff(b.cell_rec_offsets.astype(np.int64))
+    for c in range(120):
+        row = fd[1 + c]
+        assert row[0] == q["rows"][c] and int(row[1]) == nrec[c] and int(row[2]) == nrec[c]
+        assert int(row[7]) == want.num_expr[c] and int(row[8]) == want.num_over_mean[c]
+        if not res.endswith("-em"):
+            assert row[3] == fmt_f32(want.sum_umi[c]) and row[4] == "1"
+            assert row[5] == fmt_f32(np.float32(want.sum_umi[c]) / np.float32(nrec[c]))
+    m = q["meta"]
+    assert m["num_quantified_cells"] == 120 and m["num_genes"] == spec.num_rows and m["usa_mode"] == usa
+    assert m["quant_options"]["small_thresh"] == 100 and m["num_tiny_cell_resolved"] == len(m["tiny_cell_resolved_cell_numbers"])
+    assert m["resolution_strategy"] == {"cr-like": "CellRangerLike", "parsimony": "Parsimony", "cr-like-em": "CellRangerLikeEm", "trivial": "Trivial"}[res]
+
+
+@pytest.mark.gpu
+def test_quant_subset_and_multi_batch(tmp_path):
+    spec = synth.SynthSpec(n_genes=300, reads_mean=200.0)
+    b, bcs, d, t2g_path = make_input(tmp_path, spec, 90)
+    keep = [0, 7, 8, 55, 89]
+    open(tmp_path / "subset.txt", "w").write("".join(host.decode_barcode(bcs[i], 16) + "\n" for i in keep))
+    out = str(tmp_path / "out")
+    host.quantify(d, t2g_path, out, "cr-like", filter_list=str(tmp_path / "subset.txt"), batch_records=2000)
+    q = host.load_quant_dir(out)
+    assert q["rows"] == [host.decode_barcode(bcs[i], 16) for i in keep] and q["dims"][0] == 5
+    out2 = str(tmp_path / "out2")
+    host.quantify(d, t2g_path, out2, "cr-like", batch_records=2000)   # many small device batches
+    out3 = str(tmp_path / "out3")
+    host.quantify(d, t2g_path, out3, "cr-like")                       # one batch
+    for fn in ("alevin/quants_mat.mtx", "alevin/quants_mat_rows.txt", "featureDump.txt"):
+        assert open(os.path.join(out2, fn), "rb").read() == open(os.path.join(out3, fn), "rb").read()

@@ -1,0 +1,55 @@
+"""N>1 path on CPU: two gloo ranks shard a batch by cells, each computes its shard (with the
+oracle standing in for the device kernels — this test is about the sharding / assembly logic),
+all-gather the row lengths and rebuild the global CSR index; must equal the single-process result."""
+import os
+import socket
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, n_cells, out):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle_lib
+    from alevin_fry_b200 import QuantOpts, synth, shard
+    spec = synth.SynthSpec(reads_mean=150.0, n_genes=500)
+    t2g = synth.tid_to_gid(spec)
+    opts = QuantOpts(resolution="cr-like", num_gene_ids=spec.num_gene_ids, num_rows=spec.num_rows)
+    first, cnt = shard.shard_range(n_cells, rank, world)
+    mine = oracle_lib.oracle_quant(opts, t2g, synth.generate(spec, first, cnt, n_threads=2), n_threads=2)
+    max_cells = max(shard.shard_range(n_cells, r, world)[1] for r in range(world))
+    lens = shard.gather_row_lengths(torch.from_numpy(mine.num_expr.astype(np.int32)), max_cells)
+    rp = shard.global_row_ptr(lens, n_cells, world)
+    # every rank's own rows land at rp[first : first+cnt+1]
+    assert torch.equal(rp[first:first + cnt + 1] - rp[first], torch.from_numpy(mine.row_ptr.astype(np.int64)))
+    if rank == 0:
+        whole = oracle_lib.oracle_quant(opts, t2g, synth.generate(spec, 0, n_cells, n_threads=2), n_threads=2)
+        out.put((rp.numpy().tolist() == whole.row_ptr.astype(np.int64).tolist(), int(rp[-1]), int(whole.nnz)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_cell_sharding_assembles_the_global_index():
+    from alevin_fry_b200 import shard
+    assert [shard.shard_range(10, r, 3) for r in range(3)] == [(0, 4), (4, 3), (7, 3)]
+    assert sum(shard.shard_range(1_000_003, r, 8)[1] for r in range(8)) == 1_000_003
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 41, out)) for r in range(2)]
+    for p in procs: p.start()
+    for p in procs: p.join(120)
+    assert all(p.exitcode == 0 for p in procs)
+    ok, nnz_a, nnz_b = out.get(timeout=5)
+    assert ok and nnz_a == nnz_b
