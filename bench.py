@@ -279,7 +279,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- roofline of the dominant kernel family (per-cell resolve) -----------------------------
-    fam = {k: v for k, v in prof.items() if k.startswith(("k_resolve", "k_pug", "k_em"))}
+    fam = {k: v for k, v in prof.items() if k.startswith(("k_resolve", "k_gene_eqc"))}
     fam_ms = sum(v[0] for v in fam.values()) / args.steps
     fam_launches = sum(v[1] for v in fam.values()) // max(args.steps, 1)
     abytes = algorithmic_bytes(batch, nnz)
@@ -290,7 +290,7 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(args.config)
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "k_resolve_* (per-cell resolve family, %d launches/step)" % fam_launches,
+    roofline = {"bound": "hbm", "kernel": "per-cell resolve family (k_resolve_smem<*>/k_resolve_large/k_gene_eqc), %d launches/step" % fam_launches,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "algorithmic_bytes_per_step": abytes, "kernel_ms_per_step": fam_ms, "peak_source": peak_src,
                 "per_kernel_ms": {k: v[0] / args.steps for k, v in prof.items()}}

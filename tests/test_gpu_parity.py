@@ -33,7 +33,7 @@ def assert_same(got, want, exact=True, ctx=""):
 def gpu_quant(opts, t2g, batch):
     with Quantifier(opts, t2g) as q:
         r = q.quantify_batch(batch)
-        assert q.launch_count > 0
+        assert q.launch_count > 0 or batch.n_cells == 0
     return r
 
 
