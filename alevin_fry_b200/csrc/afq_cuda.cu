@@ -130,11 +130,15 @@ struct afq_ctx {
   // giant-cell scratch
   u64* large_keys = nullptr;
   u32* large_cnts = nullptr;
-  u32 large_cap_log2 = 22;
-  u32 large_blocks = 32;
+  u32 large_cap_log2 = 21;
+  u32 large_blocks = 0;   // 0 = one per SM
   int force_bin = -1;
   int grid_smem[NUM_SMEM_BINS] = {0};
   int ge_grid = 0;
+  u32 need_shift = 0;          // arena-size bias, raised when a batch overflowed many arenas
+  bool no_lanes = false;       // AFQ_NO_LANES=1: launch the arena kernels back to back on the caller's stream
+  cudaStream_t lanes[NUM_BINS] = {nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_lane[NUM_BINS] = {nullptr};
   // pipelines
   Work work_dev, work_host;
   static constexpr int NSLOT = 3;
@@ -169,7 +173,7 @@ struct ProfScope {
 
 template <int BIN>
 int setup_bin(afq_ctx* c) {
-  const size_t smem = (size_t)12 << bin_cap_log2(BIN);
+  const size_t smem = bin_smem_bytes(BIN);
   CUDA_TRY(c, cudaFuncSetAttribute(k_resolve_smem<BIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem));
   int occ = 0;
@@ -185,13 +189,15 @@ int setup_bin(afq_ctx* c) {
 struct CudaLauncher {
   afq_ctx* c;
   Work* w;
-  cudaStream_t st;
-  cudaError_t last = cudaSuccess;
+  cudaStream_t st;          // the caller's stream
+  cudaStream_t cur;         // stream launches currently go to (st, or a lane between fork/join)
+  int nlanes = 0;
+  cudaEvent_t reg_a = nullptr, reg_b = nullptr;
   const u32* t2g() const { return c->d_t2g; }
   template <class... P, class... A>
   void launch(int kid, void (*k)(P...), unsigned grid, unsigned block, size_t smem, A... args) {
-    ProfScope ps(c, kid, st);
-    k<<<grid, block, smem, st>>>(args...);
+    ProfScope ps(c, kid, cur);
+    k<<<grid, block, smem, cur>>>(args...);
   }
   int memset_zero(void* p, size_t n) { return cudaMemsetAsync(p, 0, n, st) != cudaSuccess; }
   int read_ctl(const Ctl* d, Ctl* h) {
@@ -207,6 +213,26 @@ struct CudaLauncher {
     return w->ge_arena[which].p;
   }
   u32* adj_pool(u64 n) { return w->adj_pool.ensure((size_t)n) == cudaSuccess ? w->adj_pool.p : nullptr; }
+  u32 need_shift() { return c->need_shift; }
+  // fork / join: lanes are ctx-owned non-blocking streams ordered after / before the caller stream
+  void fork(int n) {
+    if (c->no_lanes) return;
+    nlanes = n;
+    cudaEventRecord(c->ev_fork, st);
+    for (int i = 0; i < n; ++i) cudaStreamWaitEvent(c->lanes[i], c->ev_fork, 0);
+  }
+  void lane(int i) { cur = c->no_lanes ? st : c->lanes[i]; }
+  void join() {
+    for (int i = 0; i < nlanes; ++i) { cudaEventRecord(c->ev_lane[i], c->lanes[i]); cudaStreamWaitEvent(st, c->ev_lane[i], 0); }
+    cur = st;
+    nlanes = 0;
+  }
+  void region_begin() {
+    if (c->profiling) { cudaEventCreate(&reg_a); cudaEventCreate(&reg_b); cudaEventRecord(reg_a, st); }
+  }
+  void region_end() {
+    if (c->profiling) { cudaEventRecord(reg_b, st); c->prof.push_back({KID_REGION, reg_a, reg_b}); c->kid_launches[KID_REGION]++; }
+  }
 };
 
 // Enqueue the full device pipeline for one batch. All pointers are device pointers.
@@ -222,14 +248,23 @@ int run_pipeline(afq_ctx* c, Work& w, const afq_batch& b, const afq_device_out& 
   if (b.n_cells) CUDA_TRY(c, w.ensure(b.n_cells, b.n_refs_total));
   PipeBufs pb{w.ctl.p, w.bin_list.p, w.stage_col.p, w.stage_val.p, w.tile_sums.p,
               c->large_keys, c->large_cnts, c->large_cap_log2, c->large_blocks};
-  CudaLauncher l{c, &w, st};
+  CudaLauncher l{c, &w, st, st};
   int rc = enqueue_batch(l, c->cfg, c->force_bin, pb, b, o, c->err);
   if (rc != AFQ_OK) return rc;
   CUDA_TRY(c, cudaGetLastError());
   return AFQ_OK;
 }
 
+// learn the arena-size bias: if > 2 % of a batch's cells overflowed their arena, later batches
+// start every cell one arena size up
+void learn_from(afq_ctx* c, const Ctl& h) {
+  u64 total = 0;
+  for (int i = 0; i < NUM_LISTS; ++i) if (i != OVF_LIST) total += h.bin_count[i];
+  if (total >= 64 && (u64)h.bin_count[OVF_LIST] * 50 > total && c->need_shift < 2) c->need_shift++;
+}
+
 int check_device_error(afq_ctx* c, const Ctl& h) {
+  learn_from(c, h);
   if (!h.error) return AFQ_OK;
   std::string buf;
   c->err = device_error_string(h, buf);
@@ -277,9 +312,11 @@ int afq_create(const afq_config* cfg, const uint32_t* tid_to_gid, uint64_t n_ref
   if (const char* s = getenv("AFQ_LARGE_CAP_LOG2")) c->large_cap_log2 = (u32)atoi(s);
   if (const char* s = getenv("AFQ_LARGE_BLOCKS")) c->large_blocks = (u32)atoi(s);
   if (const char* s = getenv("AFQ_FORCE_BIN")) c->force_bin = atoi(s);
+  if (const char* s = getenv("AFQ_NEED_SHIFT")) c->need_shift = (u32)atoi(s);
+  if (const char* s = getenv("AFQ_NO_LANES")) c->no_lanes = atoi(s) != 0;
   if (c->large_cap_log2 < 10) c->large_cap_log2 = 10;
   if (c->large_cap_log2 > 30) c->large_cap_log2 = 30;
-  if (c->large_blocks < 1) c->large_blocks = 1;
+  if (c->large_blocks < 1) c->large_blocks = (u32)c->num_sms;
   auto fail = [&](int code) { g_create_err = c->err; afq_destroy(c); return code; };
 #define CREATE_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { c->err = std::string(#expr) + ": " + cudaGetErrorString(_e); return fail(AFQ_ERR_CUDA); } } while (0)
   CREATE_TRY(cudaSetDevice(c->device));
@@ -292,6 +329,11 @@ int afq_create(const afq_config* cfg, const uint32_t* tid_to_gid, uint64_t n_ref
   CREATE_TRY(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
   CREATE_TRY(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
   CREATE_TRY(cudaHostAlloc((void**)&c->h_ctl_dev, sizeof(Ctl), cudaHostAllocDefault));
+  CREATE_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  for (int i = 0; i < NUM_BINS; ++i) {
+    CREATE_TRY(cudaStreamCreateWithFlags(&c->lanes[i], cudaStreamNonBlocking));
+    CREATE_TRY(cudaEventCreateWithFlags(&c->ev_lane[i], cudaEventDisableTiming));
+  }
   for (auto& s : c->slots) {
     CREATE_TRY(cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
     CREATE_TRY(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
@@ -323,6 +365,8 @@ void afq_destroy(afq_ctx* c) {
   if (c->large_keys) cudaFree(c->large_keys);
   if (c->large_cnts) cudaFree(c->large_cnts);
   if (c->h_ctl_dev) cudaFreeHost(c->h_ctl_dev);
+  for (int i = 0; i < NUM_BINS; ++i) { if (c->lanes[i]) cudaStreamDestroy(c->lanes[i]); if (c->ev_lane[i]) cudaEventDestroy(c->ev_lane[i]); }
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->s_copy) cudaStreamDestroy(c->s_copy);
   if (c->s_compute) cudaStreamDestroy(c->s_compute);
   if (c->s_d2h) cudaStreamDestroy(c->s_d2h);

@@ -98,6 +98,22 @@ __device__ inline u32 block_compact_u32(u32* a, u32 n, u32* s_warp) {
   return base;
 }
 
+// out[i] = sum_{j<i} in[j] for i in [0, n], i.e. out has n+1 entries (out[n] = total).
+// in/out must not alias. All threads of the CTA must call it.
+__device__ inline void block_exscan_array_small(const u32* in, u32* out, u32 n, u32* s_warp) {
+  u32 base = 0;
+  for (u32 c0 = 0; c0 < n; c0 += blockDim.x) {
+    const u32 i = c0 + threadIdx.x;
+    const u32 v = i < n ? in[i] : 0;
+    u32 tot;
+    const u32 ex = block_exscan(v, s_warp, &tot);
+    if (i < n) out[i] = base + ex;
+    base += tot;
+  }
+  if (threadIdx.x == 0) out[n] = base;
+  __syncthreads();
+}
+
 __device__ __forceinline__ u32 next_pow2(u32 v) {
   return v <= 1 ? 1u : 1u << (32 - __clz(v - 1));
 }

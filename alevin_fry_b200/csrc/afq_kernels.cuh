@@ -24,13 +24,14 @@ __host__ __device__ constexpr u32 bin_cap_log2(int b) {
   return b == 0 ? 8 : (b == 1 ? 10 : (b == 2 ? 11 : (b == 3 ? 12 : (b == 4 ? 13 : 14))));
 }
 __host__ __device__ constexpr u32 bin_threads(int b) {
-  return b == 0 ? 32 : (b == 1 ? 128 : (b == 2 ? 256 : (b == 3 ? 512 : 1024)));
+  return b == 0 ? 32 : (b == 1 ? 128 : (b == 2 ? 256 : (b == 3 ? 512 : (b == 4 ? 512 : 1024))));
 }
 
 enum : u32 { MODE_CRLIKE = 0, MODE_TRIVIAL = 1 };
 enum : u32 { DEV_ERR_CELL_TOO_LARGE = 1 };
 
-constexpr int NUM_LISTS = NUM_BINS + 2;          // + two k_gene_eqc lists (big / normal cells)
+constexpr int NUM_LISTS = NUM_BINS + 3;          // + two k_gene_eqc lists (big / normal cells) + arena-overflow list
+constexpr int OVF_LIST = NUM_BINS + 2;           // cells whose distinct pairs overflowed their shared-memory arena
 struct Ctl {                       // per-batch device control block (zeroed per batch)
   u32 bin_count[NUM_LISTS + 1];
   u32 bin_cursor[NUM_LISTS + 1];
@@ -77,18 +78,20 @@ struct CellShared {
   u32 job;
   u32 red_max;
   u32 red_cnt;
+  u32 nwin;
+  u32 nbig;
 };
 
 // ------------------------------------------------------------------------------------
 // classify cells into arena-size bins by record count
 // ------------------------------------------------------------------------------------
-__global__ void k_bin_cells(KArgs a, int force_bin) {
+__global__ void k_bin_cells(KArgs a, int force_bin, u32 need_shift) {
   const u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= a.n_cells) return;
   const u64 r0 = a.cell_rec_off[c], r1 = a.cell_rec_off[c + 1];
   const u64 n = r1 - r0;
   const u32 p = a.ref_off[r1] - a.ref_off[r0];
-  const u64 need = n < (u64)p ? n : (u64)p;  // distinct pairs <= refs; typically << records
+  const u64 need = (n < (u64)p ? n : (u64)p) << need_shift;  // distinct pairs <= refs; typically << records
   int b = NUM_SMEM_BINS;
 #pragma unroll
   for (int i = NUM_SMEM_BINS - 1; i >= 0; --i)
@@ -99,140 +102,318 @@ __global__ void k_bin_cells(KArgs a, int force_bin) {
   if (b == NUM_SMEM_BINS) atomicMax(&a.ctl->max_cell_refs, p);
 }
 
-// open-address insert-or-increment of one (umi, gene) key
-__device__ __forceinline__ void table_insert(u64* keys, u32* cnts, u64 key, u32 log2cap, u32 limit,
-                                             CellShared* sh) {
-  const u32 mask = (1u << log2cap) - 1;
-  u32 s = hash_key(key, log2cap);
-  for (;;) {
-    u64 cur = keys[s];
+// ------------------------------------------------------------------------------------
+// Per-cell resolve, version 3.
+//  * One open-address table hashed by the UMI ALONE holds the distinct (umi, gene) keys with read
+//    counts, so all genes of a UMI sit in one probe cluster; the cluster's first entry ("leader")
+//    scans to the cluster end and computes the arg-max gene set directly: no sort of the pairs.
+//  * Every new entry's slot is appended to a dense list, so the later phases run over dense work
+//    (bins 0-3; the two largest arenas iterate over slots instead to stay within shared memory).
+//  * Winner slots are ordered by bucket (slot >> shift): one thread per bucket derives the
+//    distinct slots from a <= 256-bit presence mask and counts them — no per-bucket sort; hot
+//    buckets are counted by the whole CTA. Small cells rank-sort their winners instead.
+//  * The record / entry / bucket loops are warp-uniform with an explicit __syncwarp() so that lanes
+//    reconverge every iteration (ncu r1c: 7.5 active lanes/instruction without it). Fully
+//    lock-stepped (vote-driven) probe loops were measured and are slower (r1e: +70 % warp
+//    instructions from the votes and predication), so the probe loops stay plainly divergent.
+// ------------------------------------------------------------------------------------
+__host__ __device__ constexpr u32 bin_buckets_log2(int b) { return b == 0 ? 7 : (b == 1 ? 8 : (b == 2 ? 9 : 10)); }
+__host__ __device__ constexpr bool bin_has_list(int b) { return b <= 3; }
+__host__ __device__ constexpr u32 bin_min_blocks(int b) { return b == 0 ? 16 : (b == 1 ? 10 : (b == 2 ? 5 : (b == 3 ? 3 : (b == 4 ? 2 : 1)))); }
+__host__ __device__ constexpr size_t bin_smem_bytes(int b) {
+  return ((size_t)12 << bin_cap_log2(b)) + (bin_has_list(b) ? ((size_t)3 << bin_cap_log2(b)) : 0) +
+         ((size_t)12 << bin_buckets_log2(b)) + 64;
+}
+constexpr u32 BIG_BUCKET = 64;       // buckets longer than this are counted cooperatively
+constexpr u32 RANK_SORT_MAX = 192;   // cells with at most this many winners rank-sort them
+
+struct CellArena {
+  u64* keys;   // [cap]   later reused as u32 sorted[2*cap]
+  u32* cnts;   // [cap]   read counts -> winner slot (or NONE32)
+  u32* list;   // [3*cap/4] slots of the distinct entries in creation order (nullptr: iterate slots)
+  u32* bcnt;   // [NB]
+  u32* boff;   // [NB+1]
+  u32* bdo;    // [NB+1]
+  u32 log2cap, nb_log2;
+};
+
+__device__ __forceinline__ u32 umi_home(u32 umi, u32 log2cap) { return (umi * 0x9E3779B1u) >> (32 - log2cap); }
+
+// insert-or-increment (umi, gene); the probe sequence depends on the UMI only
+template <bool LIST>
+__device__ __forceinline__ void table_insert(const CellArena& A, u32 umi, u32 gene, u32 limit, CellShared* sh) {
+  const u32 mask = (1u << A.log2cap) - 1;
+  const u64 key = ((u64)umi << 32) | gene;
+  u32 s = umi_home(umi, A.log2cap);
+  for (u32 probes = 0; probes <= mask; ++probes) {
+    u64 cur = A.keys[s];
     if (cur == EMPTY_KEY) {
-      cur = atomicCAS((unsigned long long*)&keys[s], (unsigned long long)EMPTY_KEY,
-                      (unsigned long long)key);
+      cur = atomicCAS((unsigned long long*)&A.keys[s], (unsigned long long)EMPTY_KEY, (unsigned long long)key);
       if (cur == EMPTY_KEY) {
-        if (atomicAdd(&sh->distinct, 1u) + 1 > limit) sh->abort = 1;
+        const u32 idx = atomicAdd(&sh->distinct, 1u);
+        if (idx >= limit) { sh->abort = 1; return; }
+        if (LIST) A.list[idx] = s;
         cur = key;
       }
     }
-    if (cur == key) { atomicAdd(&cnts[s], 1u); return; }
-    if (*(volatile u32*)&sh->abort) return;  // table may be full: stop probing
+    if (cur == key) { atomicAdd(&A.cnts[s], 1u); return; }
     s = (s + 1) & mask;
   }
+  sh->abort = 1;  // table full (only reachable after the distinct limit was crossed)
 }
 
-// ------------------------------------------------------------------------------------
-// one cell, block-cooperative. keys/cnts: arena of `cap` = 2^log2cap entries.
-// Returns false when the distinct-pair count exceeded `limit` (caller re-queues the cell
-// on a larger arena); nothing has been written for the cell in that case.
-// ------------------------------------------------------------------------------------
-__device__ inline bool resolve_cell(const KArgs& a, u32 cell, u64* keys, u32* cnts, u32 log2cap,
-                                    u32 limit, CellShared* sh) {
-  const u32 cap = 1u << log2cap;
+// Returns false when the distinct-pair count exceeded `limit` (caller re-queues the cell on a
+// larger arena); nothing has been written for the cell in that case.
+template <bool LIST>
+__device__ inline bool resolve_cell(const KArgs& a, u32 cell, const CellArena& A, u32 limit, CellShared* sh) {
+  const u32 cap = 1u << A.log2cap, mask = cap - 1;
+  const u32 NB = 1u << A.nb_log2;
+  const u32 T = blockDim.x, tid = threadIdx.x;
   const u64 r0 = a.cell_rec_off[cell], r1 = a.cell_rec_off[cell + 1];
-  for (u32 i = threadIdx.x; i < cap; i += blockDim.x) { keys[i] = EMPTY_KEY; cnts[i] = 0; }
-  if (threadIdx.x == 0) { sh->distinct = 0; sh->abort = 0; sh->red_max = 0; sh->red_cnt = 0; }
+  const u32 nrec = (u32)(r1 - r0);
+  for (u32 i = tid; i < cap; i += T) { A.keys[i] = EMPTY_KEY; A.cnts[i] = 0; }
+  for (u32 i = tid; i < NB; i += T) A.bcnt[i] = 0;
+  if (tid == 0) { sh->distinct = 0; sh->abort = 0; sh->red_max = 0; sh->red_cnt = 0; sh->nwin = 0; sh->nbig = 0; }
   __syncthreads();
 
-  // ---- phase 1: records -> (umi, gene) pairs, combined in the open-address table -------
-  for (u64 r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
-    if (*(volatile u32*)&sh->abort) break;
+  // ---- phase 1: records -> distinct (umi, gene) pairs with read counts --------------------
+  for (u32 base = 0; base < nrec; base += T) {
+    __syncwarp();
+    const u32 i = base + tid;
+    if (i >= nrec || *(volatile u32*)&sh->abort) continue;
+    const u64 r = r0 + i;
     const u32 umi = a.umi[r];
     const u32 o0 = a.ref_off[r], o1 = a.ref_off[r + 1];
+    if (o1 == o0) continue;
+    const u32 g0 = __ldg(a.t2g + a.refs[o0]);
     if (a.mode == MODE_TRIVIAL) {
-      // src/pugutils.rs:870-881: class is multi-gene iff two consecutive refs differ in gene
-      if (o1 == o0) continue;
-      const u32 g0 = __ldg(a.t2g + a.refs[o0]);
+      // src/pugutils.rs:870-881: a class is multi-gene iff two consecutive refs differ in gene
       bool multi = false;
       for (u32 k = o0 + 1; k < o1; ++k)
         if (__ldg(a.t2g + a.refs[k]) != g0) { multi = true; break; }
-      if (!multi) table_insert(keys, cnts, ((u64)umi << 32) | g0, log2cap, limit, sh);
+      if (!multi) table_insert<LIST>(A, umi, g0, limit, sh);
       continue;
     }
-    for (u32 k = o0; k < o1; ++k) {
+    table_insert<LIST>(A, umi, g0, limit, sh);
+    for (u32 k = o0 + 1; k < o1; ++k) {
       const u32 g = __ldg(a.t2g + a.refs[k]);
+      if (g == g0) continue;
       bool dup = false;
-      for (u32 j = o0; j < k; ++j)
+      for (u32 j = o0 + 1; j < k; ++j)
         if (__ldg(a.t2g + a.refs[j]) == g) { dup = true; break; }
-      if (dup) continue;
-      table_insert(keys, cnts, ((u64)umi << 32) | g, log2cap, limit, sh);
+      if (!dup) table_insert<LIST>(A, umi, g, limit, sh);
     }
   }
   __syncthreads();
   if (sh->abort) { __syncthreads(); return false; }
+  const u32 d = sh->distinct;
+  const u32 N = LIST ? d : cap;   // work items of phases 2-4: list entries or table slots
 
-  // ---- phase 2: compact + sort by (umi, gene) ------------------------------------------
-  const u32 d = block_compact_pairs(keys, cnts, cap, sh->scan);
-  const u32 D = next_pow2(d);
-  for (u32 i = d + threadIdx.x; i < D; i += blockDim.x) keys[i] = EMPTY_KEY;
-  __syncthreads();
-  block_bitonic_pairs(keys, cnts, D);
-
-  // ---- phase 3: per UMI, arg-max gene set -> output slot (written over cnts) ------------
-  for (u32 i = threadIdx.x; i < d; i += blockDim.x) {
-    const u64 ki = keys[i];
-    if (a.mode == MODE_TRIVIAL) { cnts[i] = (u32)ki; continue; }  // every (gene, umi) counts
-    const u32 u = (u32)(ki >> 32);
-    if (i > 0 && (u32)(keys[i - 1] >> 32) == u) continue;  // not the first entry of this UMI
+  // ---- phase 2: per UMI (cluster leader) the arg-max gene set -> output slot, into cnts ----
+  // A leader only writes cnts of entries of its own UMI and every entry's count is read by exactly
+  // one thread (its UMI's leader) before being overwritten, so the phase is race-free.
+  for (u32 base = 0; base < N; base += T) {
+    __syncwarp();
+    const u32 i = base + tid;
+    if (i >= N) continue;
+    const u32 s = LIST ? A.list[i] : i;
+    const u64 key = A.keys[s];
+    if (!LIST && key == EMPTY_KEY) { A.cnts[s] = NONE32; continue; }
+    if (a.mode == MODE_TRIVIAL) { A.cnts[s] = (u32)key; continue; }  // every distinct (gene, umi) counts
+    const u32 u = (u32)(key >> 32);
+    bool leader = true;
+    for (u32 t = umi_home(u, A.log2cap); t != s; t = (t + 1) & mask)
+      if ((u32)(A.keys[t] >> 32) == u) { leader = false; break; }
+    if (!leader) continue;               // retired by its leader
     u32 maxw = 0, nb = 0;
     u32 best[10];
-    u32 j = i;
-    for (; j < d; ++j) {
-      const u64 kj = keys[j];
-      if ((u32)(kj >> 32) != u) break;
-      const u32 w = cnts[j];
-      if (w > maxw) { maxw = w; nb = 1; best[0] = (u32)kj; }
-      else if (w == maxw) { if (nb < 10) best[nb] = (u32)kj; ++nb; }
+    for (u32 t = s;; t = (t + 1) & mask) {
+      const u64 kt = A.keys[t];
+      if (kt == EMPTY_KEY) break;
+      if ((u32)(kt >> 32) != u) continue;
+      const u32 w = A.cnts[t];
+      if (w > maxw) { maxw = w; nb = 1; best[0] = (u32)kt; }
+      else if (w == maxw) { if (nb < 10) best[nb] = (u32)kt; ++nb; }
+      if (t != s) A.cnts[t] = NONE32;
     }
-    u32 res;
-    if (!a.usa_mode) res = (nb == 1) ? best[0] : NONE32;
-    else res = (nb > 10) ? NONE32 : usa_slot_for_label(best, nb, a.uo, a.ao);
-    cnts[i] = res;
-    for (u32 k = i + 1; k < j; ++k) cnts[k] = NONE32;
+    u32 res = NONE32;
+    if (!a.usa_mode) { if (nb == 1) res = best[0]; }
+    else if (nb <= 10) {
+      for (u32 q = 1; q < nb; ++q) { const u32 x = best[q]; u32 j = q; while (j > 0 && best[j - 1] > x) { best[j] = best[j - 1]; --j; } best[j] = x; }
+      res = usa_slot_for_label(best, nb, a.uo, a.ao);
+    }
+    A.cnts[s] = res;
   }
   __syncthreads();
 
-  // ---- phase 4: sort winner slots, run-length count, emit ------------------------------
-  const u32 m = block_compact_u32(cnts, d, sh->scan);
-  const u32 M = next_pow2(m);
-  for (u32 i = m + threadIdx.x; i < M; i += blockDim.x) cnts[i] = NONE32;
+  // ---- phase 3: count winners; bucket histogram ----------------------------------------------
+  const u32 bits = 32 - __clz((int)(a.num_rows > 1 ? a.num_rows - 1 : 1));
+  const u32 shift = bits > A.nb_log2 ? bits - A.nb_log2 : 0;   // bucket = slot >> shift < NB
+  u32 local_m = 0;
+  for (u32 base = 0; base < N; base += T) {
+    const u32 i = base + tid;
+    if (i >= N) continue;
+    const u32 v = A.cnts[LIST ? A.list[i] : i];
+    if (v != NONE32) { atomicAdd(&A.bcnt[v >> shift], 1u); ++local_m; }
+  }
+  if (local_m) atomicAdd(&sh->nwin, local_m);
   __syncthreads();
-  block_bitonic_u32(cnts, M);
+  const u32 m = sh->nwin;
+  u32* sorted = reinterpret_cast<u32*>(A.keys);   // winners, over the dead key area
+  u32* tmp = sorted + cap;
+  const u64 out_base = a.ref_off[r0];             // this cell's staging rows start at its first ref
+  u32 nnz = 0, lmax = 0;
+  const bool rank_path = m <= RANK_SORT_MAX || shift > 8;
 
-  const u64 out_base = a.ref_off[r0];  // this cell's staging region starts at its first ref
-  u32 base = 0, lmax = 0;
-  for (u32 c0 = 0; c0 < m; c0 += blockDim.x) {
-    const u32 i = c0 + threadIdx.x;
-    u32 start = 0, slot = 0, len = 0;
-    if (i < m) {
-      slot = cnts[i];
-      start = (i == 0 || cnts[i - 1] != slot) ? 1u : 0u;
-      if (start) {
-        u32 j = i + 1;
-        while (j < m && cnts[j] == slot) ++j;
-        len = j - i;
+  if (rank_path) {
+    // ---- small cells (or huge gene axes): order the winners themselves -----------------------
+    for (u32 base = 0; base < N; base += T) {   // gather winners (unordered) into tmp
+      const u32 i = base + tid;
+      if (i >= N) continue;
+      const u32 v = A.cnts[LIST ? A.list[i] : i];
+      if (v != NONE32) tmp[atomicAdd(&sh->nbig, 1u)] = v;
+    }
+    __syncthreads();
+    if (m <= 1024) {
+      for (u32 i = tid; i < m; i += T) {        // rank sort: O(m^2 / T)
+        const u32 x = tmp[i];
+        u32 rank = 0;
+        for (u32 j = 0; j < m; ++j) { const u32 y = tmp[j]; rank += (y < x || (y == x && j < i)) ? 1u : 0u; }
+        sorted[rank] = x;
+      }
+      __syncthreads();
+    } else {
+      const u32 M = next_pow2(m);
+      for (u32 i = tid; i < M; i += T) sorted[i] = i < m ? tmp[i] : NONE32;
+      __syncthreads();
+      block_bitonic_u32(sorted, M);
+    }
+    // run starts -> tmp (positions), then (slot, run length)
+    u32 base = 0;
+    for (u32 c0 = 0; c0 < m; c0 += T) {
+      const u32 i = c0 + tid;
+      const u32 st = (i < m && (i == 0 || sorted[i - 1] != sorted[i])) ? 1u : 0u;
+      u32 tot;
+      const u32 pos = block_exscan(st, sh->scan, &tot);
+      if (st) tmp[base + pos] = i;
+      base += tot;
+    }
+    nnz = base;
+    __syncthreads();
+    for (u32 j = tid; j < nnz; j += T) {
+      const u32 i0 = tmp[j], i1 = (j + 1 < nnz) ? tmp[j + 1] : m;
+      a.stage_col[out_base + j] = sorted[i0];
+      a.stage_val[out_base + j] = (float)(i1 - i0);
+      lmax = (i1 - i0) > lmax ? (i1 - i0) : lmax;
+    }
+  } else {
+    // ---- bucket path ---------------------------------------------------------------------------
+    block_exscan_array_small(A.bcnt, A.boff, NB, sh->scan);   // boff[b] = start of bucket b; boff[NB] = m
+    for (u32 base = 0; base < N; base += T) {   // scatter winners into their bucket segments
+      const u32 i = base + tid;
+      if (i >= N) continue;
+      const u32 v = A.cnts[LIST ? A.list[i] : i];
+      if (v != NONE32) { const u32 b = v >> shift; sorted[A.boff[b] + atomicSub(&A.bcnt[b], 1u) - 1] = v; }
+    }
+    __syncthreads();
+    const u32 lowmask = (1u << shift) - 1;
+    // distinct slots per bucket from a presence mask over the low `shift` (<= 8) bits
+    for (u32 base = 0; base < NB; base += T) {
+      __syncwarp();
+      const u32 b = base + tid;
+      if (b >= NB) continue;
+      const u32 lo = A.boff[b], hi = A.boff[b + 1];
+      u32 nd = 0;
+      if (hi - lo > BIG_BUCKET) { tmp[atomicAdd(&sh->nbig, 1u)] = b; }
+      else if (hi > lo) {
+        unsigned long long w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+        for (u32 i = lo; i < hi; ++i) {
+          const u32 x = sorted[i] & lowmask;
+          const unsigned long long bit = 1ull << (x & 63);
+          const u32 w = x >> 6;
+          if (w == 0) w0 |= bit; else if (w == 1) w1 |= bit; else if (w == 2) w2 |= bit; else w3 |= bit;
+        }
+        nd = (u32)(__popcll(w0) + __popcll(w1) + __popcll(w2) + __popcll(w3));
+      }
+      A.bcnt[b] = nd;
+    }
+    __syncthreads();
+    const u32 nbig = sh->nbig;
+    u32* bigcnt = tmp + NB;                      // [256] counters for one hot bucket at a time
+    for (u32 q = 0; q < nbig; ++q) {
+      const u32 b = tmp[q];
+      const u32 lo = A.boff[b], hi = A.boff[b + 1];
+      for (u32 i = tid; i < 256; i += T) bigcnt[i] = 0;
+      if (tid == 0) sh->red_cnt = 0;
+      __syncthreads();
+      for (u32 i = lo + tid; i < hi; i += T) atomicAdd(&bigcnt[sorted[i] & lowmask], 1u);
+      __syncthreads();
+      u32 c = 0;
+      for (u32 i = tid; i < 256; i += T) if (bigcnt[i]) ++c;
+      if (c) atomicAdd(&sh->red_cnt, c);
+      __syncthreads();
+      if (tid == 0) A.bcnt[b] = sh->red_cnt;
+      __syncthreads();
+    }
+    block_exscan_array_small(A.bcnt, A.bdo, NB, sh->scan);
+    nnz = A.bdo[NB];
+    // emit small buckets: one thread per bucket walks its mask in ascending order
+    for (u32 base = 0; base < NB; base += T) {
+      __syncwarp();
+      const u32 b = base + tid;
+      if (b >= NB) continue;
+      const u32 lo = A.boff[b], hi = A.boff[b + 1];
+      if (hi == lo || hi - lo > BIG_BUCKET) continue;
+      unsigned long long wm[4] = {0, 0, 0, 0};
+      for (u32 i = lo; i < hi; ++i) { const u32 x = sorted[i] & lowmask; wm[x >> 6] |= 1ull << (x & 63); }
+      u64 o = out_base + A.bdo[b];
+      for (u32 w = 0; w < 4; ++w) {
+        unsigned long long mm = wm[w];
+        while (mm) {
+          const u32 low = w * 64 + (u32)__ffsll((long long)mm) - 1;
+          mm &= mm - 1;
+          u32 cnt = 0;
+          for (u32 i = lo; i < hi; ++i) cnt += ((sorted[i] & lowmask) == low) ? 1u : 0u;
+          a.stage_col[o] = (b << shift) | low;
+          a.stage_val[o] = (float)cnt;
+          lmax = cnt > lmax ? cnt : lmax;
+          ++o;
+        }
       }
     }
-    u32 tot;
-    const u32 pos = block_exscan(start, sh->scan, &tot);
-    if (start) {
-      a.stage_col[out_base + base + pos] = slot;
-      a.stage_val[out_base + base + pos] = (float)len;
-      lmax = len > lmax ? len : lmax;
+    for (u32 q = 0; q < nbig; ++q) {             // emit hot buckets cooperatively
+      const u32 b = tmp[q];
+      const u32 lo = A.boff[b], hi = A.boff[b + 1];
+      __syncthreads();
+      for (u32 i = tid; i < 256; i += T) bigcnt[i] = 0;
+      __syncthreads();
+      for (u32 i = lo + tid; i < hi; i += T) atomicAdd(&bigcnt[sorted[i] & lowmask], 1u);
+      __syncthreads();
+      if (tid == 0) {
+        u64 o = out_base + A.bdo[b];
+        for (u32 low = 0; low < 256; ++low) {
+          const u32 cnt = bigcnt[low];
+          if (!cnt) continue;
+          a.stage_col[o] = (b << shift) | low;
+          a.stage_val[o] = (float)cnt;
+          lmax = cnt > lmax ? cnt : lmax;
+          ++o;
+        }
+      }
     }
-    base += tot;
   }
-  const u32 nnz = base;
+  if (tid == 0) sh->red_cnt = 0;
   if (lmax) atomicMax(&sh->red_max, lmax);
   __syncthreads();
-  // NumGenesOverMean (src/quant.rs:1190-1194): mean over expressed genes, f32
+  // ---- statistics: NumGenesOverMean (src/quant.rs:1190-1194), mean over expressed genes, f32 ---
   const float sum = (float)m;
   const float mean = sum / (float)nnz;
   u32 lover = 0;
-  for (u32 i = threadIdx.x; i < nnz; i += blockDim.x)
+  for (u32 i = tid; i < nnz; i += T)
     if (a.stage_val[out_base + i] > mean) ++lover;
   if (lover) atomicAdd(&sh->red_cnt, lover);
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     a.sum_umi[cell] = sum;
     a.max_umi[cell] = (float)sh->red_max;
     a.num_expr[cell] = nnz;
@@ -248,12 +429,21 @@ __device__ inline bool resolve_cell(const KArgs& a, u32 cell, u64* keys, u32* cn
 
 // persistent kernel over one shared-memory bin: CTAs pull cells from the bin's list
 template <int BIN>
-__global__ void __launch_bounds__(bin_threads(BIN)) k_resolve_smem(KArgs a) {
+__global__ void __launch_bounds__(bin_threads(BIN), bin_min_blocks(BIN)) k_resolve_smem(KArgs a) {
   constexpr u32 LOG2CAP = bin_cap_log2(BIN);
   constexpr u32 CAP = 1u << LOG2CAP;
+  constexpr u32 NB = 1u << bin_buckets_log2(BIN);
+  constexpr bool LIST = bin_has_list(BIN);
   AFQ_DYN_SMEM(smem_raw);
-  u64* keys = reinterpret_cast<u64*>(smem_raw);
-  u32* cnts = reinterpret_cast<u32*>(keys + CAP);
+  CellArena A;
+  A.keys = reinterpret_cast<u64*>(smem_raw);
+  A.cnts = reinterpret_cast<u32*>(A.keys + CAP);
+  A.list = LIST ? A.cnts + CAP : nullptr;
+  A.bcnt = A.cnts + CAP + (LIST ? (CAP / 4) * 3 : 0);
+  A.boff = A.bcnt + NB;
+  A.bdo = A.boff + NB + 1;
+  A.log2cap = LOG2CAP;
+  A.nb_log2 = bin_buckets_log2(BIN);
   __shared__ CellShared sh;
   const u32 count = a.ctl->bin_count[BIN];
   const u32* list = a.bin_list + (u64)BIN * a.n_cells;
@@ -263,29 +453,36 @@ __global__ void __launch_bounds__(bin_threads(BIN)) k_resolve_smem(KArgs a) {
     const u32 job = sh.job;
     if (job >= count) break;
     const u32 cell = list[job];
-    const bool ok = resolve_cell(a, cell, keys, cnts, LOG2CAP, (CAP / 4) * 3, &sh);
+    const bool ok = resolve_cell<LIST>(a, cell, A, (CAP / 4) * 3, &sh);
     if (!ok && threadIdx.x == 0) {
-      const u32 idx = atomicAdd(&a.ctl->bin_count[BIN + 1], 1u);
-      a.bin_list[(u64)(BIN + 1) * a.n_cells + idx] = cell;
-      if (BIN + 1 == NUM_SMEM_BINS) {
-        const u64 r0 = a.cell_rec_off[cell], r1 = a.cell_rec_off[cell + 1];
-        atomicMax(&a.ctl->max_cell_refs, a.ref_off[r1] - a.ref_off[r0]);
-      }
+      // distinct pairs exceeded 75 % of this arena: hand the cell to the global-arena kernel
+      // (second k_resolve_large launch, after all arenas have drained)
+      const u32 idx = atomicAdd(&a.ctl->bin_count[OVF_LIST], 1u);
+      a.bin_list[(u64)OVF_LIST * a.n_cells + idx] = cell;
+      const u64 r0 = a.cell_rec_off[cell], r1 = a.cell_rec_off[cell + 1];
+      atomicMax(&a.ctl->max_cell_refs, a.ref_off[r1] - a.ref_off[r0]);
     }
     __syncthreads();
   }
 }
 
 // giant cells: same algorithm on a per-CTA global-memory arena (L2-resident working set)
-__global__ void __launch_bounds__(1024) k_resolve_large(KArgs a) {
+__global__ void __launch_bounds__(1024) k_resolve_large(KArgs a, u32 list_id) {
   __shared__ CellShared sh;
+  __shared__ u32 s_buckets[3 * 1024 + 2];
   const u64 arena = (u64)blockIdx.x << a.large_cap_log2;
-  u64* keys = a.large_keys + arena;
-  u32* cnts = a.large_cnts + arena;
-  const u32 count = a.ctl->bin_count[NUM_SMEM_BINS];
-  const u32* list = a.bin_list + (u64)NUM_SMEM_BINS * a.n_cells;
+  CellArena A;
+  A.keys = a.large_keys + arena;
+  A.cnts = a.large_cnts + arena;
+  A.list = nullptr;
+  A.bcnt = s_buckets;
+  A.boff = A.bcnt + 1024;
+  A.bdo = A.boff + 1025;
+  A.nb_log2 = 10;
+  const u32 count = a.ctl->bin_count[list_id];
+  const u32* list = a.bin_list + (u64)list_id * a.n_cells;
   for (;;) {
-    if (threadIdx.x == 0) sh.job = atomicAdd(&a.ctl->bin_cursor[NUM_SMEM_BINS], 1u);
+    if (threadIdx.x == 0) sh.job = atomicAdd(&a.ctl->bin_cursor[list_id], 1u);
     __syncthreads();
     const u32 job = sh.job;
     if (job >= count) break;
@@ -304,7 +501,8 @@ __global__ void __launch_bounds__(1024) k_resolve_large(KArgs a) {
       __syncthreads();
       continue;
     }
-    resolve_cell(a, cell, keys, cnts, log2cap, 0xFFFFFFFFu, &sh);
+    A.log2cap = log2cap;
+    resolve_cell<false>(a, cell, A, 0xFFFFFFFFu, &sh);
     __syncthreads();
   }
 }

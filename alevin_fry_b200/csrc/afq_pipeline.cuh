@@ -12,6 +12,9 @@
 //   int  ge_blocks(int which);                                // 0 big-cell grid, 1 normal grid
 //   u8*  ge_arena(int which, u64 bytes_per_block, u32 blocks);// grow-only, nullptr on failure
 //   u32* adj_pool(u64 entries);                               // grow-only, nullptr on failure
+//   void fork(int lanes); void lane(int i); void join();      // independent launches may overlap:
+//       between fork and join, launches go to lane i's stream (CUDA) / run in order (emulator)
+//   u32  need_shift();                                        // arena-size bias learnt from overflows
 #pragma once
 #include <string>
 
@@ -23,12 +26,12 @@ namespace afq {
 
 enum KernelId : int {
   KID_BIN = 0, KID_SMEM0 = 1, KID_LARGE = 7, KID_SCAN_SUMS = 8, KID_SCAN_TILES = 9, KID_SCAN_ROWS = 10,
-  KID_GATHER = 11, KID_GENE_EQC = 12, KID_GENE_EQC_BIG = 13, KID_BIN_GE = 14, KID_OTHER = 15, NUM_KID = 16
+  KID_GATHER = 11, KID_GENE_EQC = 12, KID_GENE_EQC_BIG = 13, KID_BIN_GE = 14, KID_REGION = 15, NUM_KID = 16
 };
 static const char* const KID_NAMES[NUM_KID] = {
     "k_bin_cells", "k_resolve_smem<0>", "k_resolve_smem<1>", "k_resolve_smem<2>", "k_resolve_smem<3>",
     "k_resolve_smem<4>", "k_resolve_smem<5>", "k_resolve_large", "k_scan_tile_sums", "k_scan_tiles",
-    "k_scan_rows", "k_gather_rows", "k_gene_eqc", "k_gene_eqc(big cells)", "k_bin_cells_ge", "other"};
+    "k_scan_rows", "k_gather_rows", "k_gene_eqc", "k_gene_eqc(big cells)", "k_bin_cells_ge", "resolve_region(wall)"};
 
 struct PipeBufs {  // device scratch owned by the caller (one set per stream-ordered pipeline)
   Ctl* ctl;
@@ -50,19 +53,27 @@ inline bool res_is_em(int r) {
 
 template <int BIN, class L>
 inline void launch_smem_bin(L& l, const KArgs& a) {
-  const size_t smem = (size_t)12 << bin_cap_log2(BIN);
+  const size_t smem = bin_smem_bytes(BIN);
   l.launch(KID_SMEM0 + BIN, k_resolve_smem<BIN>, (unsigned)l.grid_for_bin(BIN), bin_threads(BIN), smem, a);
 }
 
+// The arena kernels are independent of each other (overflowing cells go to a separate list that is
+// drained afterwards), so they are forked onto per-arena lanes and overlap on the device: small
+// CTAs fill the SMs while the few big-arena CTAs are still running.
 template <class L>
 inline void launch_crlike_bins(L& l, const KArgs& a, const PipeBufs& pb) {
-  launch_smem_bin<0>(l, a);
-  launch_smem_bin<1>(l, a);
-  launch_smem_bin<2>(l, a);
-  launch_smem_bin<3>(l, a);
-  launch_smem_bin<4>(l, a);
-  launch_smem_bin<5>(l, a);
-  l.launch(KID_LARGE, k_resolve_large, pb.large_blocks, 1024u, (size_t)0, a);
+  l.region_begin();
+  l.fork(NUM_BINS);
+  l.lane(5); launch_smem_bin<5>(l, a);
+  l.lane(6); l.launch(KID_LARGE, k_resolve_large, pb.large_blocks, 1024u, (size_t)0, a, (u32)NUM_SMEM_BINS);
+  l.lane(4); launch_smem_bin<4>(l, a);
+  l.lane(3); launch_smem_bin<3>(l, a);
+  l.lane(2); launch_smem_bin<2>(l, a);
+  l.lane(1); launch_smem_bin<1>(l, a);
+  l.lane(0); launch_smem_bin<0>(l, a);
+  l.join();
+  l.launch(KID_LARGE, k_resolve_large, pb.large_blocks, 1024u, (size_t)0, a, (u32)OVF_LIST);
+  l.region_end();
 }
 
 // Enqueue the whole pipeline for one batch. All batch/out pointers are device pointers.
@@ -102,7 +113,7 @@ int enqueue_batch(L& l, const afq_config& cfg, int force_bin, const PipeBufs& pb
   const int res = cfg.resolution;
   const unsigned bin_grid = (unsigned)((b.n_cells + 255) / 256);
   if (res == AFQ_RES_CR_LIKE || res == AFQ_RES_TRIVIAL) {
-    l.launch(KID_BIN, k_bin_cells, bin_grid, 256u, (size_t)0, a, force_bin);
+    l.launch(KID_BIN, k_bin_cells, bin_grid, 256u, (size_t)0, a, force_bin, l.need_shift());
     launch_crlike_bins(l, a, pb);
   } else {
     // cr-like-em and the parsimony family: tiny cells keep the cr-like fast path
@@ -111,7 +122,7 @@ int enqueue_batch(L& l, const afq_config& cfg, int force_bin, const PipeBufs& pb
       err = "--large-graph-thresh above 4096 is not supported on the CUDA path";
       return AFQ_ERR_UNSUPPORTED;
     }
-    l.launch(KID_BIN_GE, k_bin_cells_ge, bin_grid, 256u, (size_t)0, a, force_bin, GE_BIG_RECORDS);
+    l.launch(KID_BIN_GE, k_bin_cells_ge, bin_grid, 256u, (size_t)0, a, force_bin, GE_BIG_RECORDS, l.need_shift());
     launch_crlike_bins(l, a, pb);
     Ctl h{};
     if (l.read_ctl(pb.ctl, &h)) { err = "reading the control block failed"; return AFQ_ERR_CUDA; }

@@ -247,6 +247,62 @@ __device__ inline void block_bitonic_u64(u64* a, u32 n) {
   }
 }
 
+// ---- sorts staged through a shared-memory scratch (the arena itself is global memory, where a
+// bitonic stage costs an L2 round trip; in shared memory it costs ~50 cycles) ------------------
+constexpr u32 GE_SCRATCH_BYTES = 32768;
+
+__device__ inline void sort_pairs_staged(u64* keys, u32* vals, u32 n, u8* scratch) {
+  if ((u64)n * 12 <= GE_SCRATCH_BYTES && n > 1) {
+    u64* sk = reinterpret_cast<u64*>(scratch);
+    u32* sv = reinterpret_cast<u32*>(sk + n);
+    for (u32 i = threadIdx.x; i < n; i += blockDim.x) { sk[i] = keys[i]; sv[i] = vals[i]; }
+    __syncthreads();
+    block_bitonic_pairs(sk, sv, n);
+    for (u32 i = threadIdx.x; i < n; i += blockDim.x) { keys[i] = sk[i]; vals[i] = sv[i]; }
+    __syncthreads();
+  } else {
+    block_bitonic_pairs(keys, vals, n);
+  }
+}
+__device__ inline void sort_u64_staged(u64* a, u32 n, u8* scratch) {
+  if ((u64)n * 8 <= GE_SCRATCH_BYTES && n > 1) {
+    u64* sk = reinterpret_cast<u64*>(scratch);
+    for (u32 i = threadIdx.x; i < n; i += blockDim.x) sk[i] = a[i];
+    __syncthreads();
+    block_bitonic_u64(sk, n);
+    for (u32 i = threadIdx.x; i < n; i += blockDim.x) a[i] = sk[i];
+    __syncthreads();
+  } else {
+    block_bitonic_u64(a, n);
+  }
+}
+__device__ inline void sort_u32_staged(u32* a, u32 n, u8* scratch) {
+  if ((u64)n * 4 <= GE_SCRATCH_BYTES && n > 1) {
+    u32* sk = reinterpret_cast<u32*>(scratch);
+    for (u32 i = threadIdx.x; i < n; i += blockDim.x) sk[i] = a[i];
+    __syncthreads();
+    block_bitonic_u32(sk, n);
+    for (u32 i = threadIdx.x; i < n; i += blockDim.x) a[i] = sk[i];
+    __syncthreads();
+  } else {
+    block_bitonic_u32(a, n);
+  }
+}
+template <class Less>
+__device__ inline void sort_ids_staged(u32* ids, u32* pay, u32 n, u8* scratch, Less less) {
+  if ((u64)n * 8 <= GE_SCRATCH_BYTES && n > 1) {
+    u32* si = reinterpret_cast<u32*>(scratch);
+    u32* sp = si + n;
+    for (u32 i = threadIdx.x; i < n; i += blockDim.x) { si[i] = ids[i]; sp[i] = pay[i]; }
+    __syncthreads();
+    block_bitonic_ids(si, sp, n, less);
+    for (u32 i = threadIdx.x; i < n; i += blockDim.x) { ids[i] = si[i]; pay[i] = sp[i]; }
+    __syncthreads();
+  } else {
+    block_bitonic_ids(ids, pay, n, less);
+  }
+}
+
 // block-wide exclusive scan over an array in place-out: out[i] = sum_{j<i} in[j]; returns total.
 // in and out may alias.
 __device__ inline u32 block_exscan_array(const u32* in, u32* out, u32 n, u32* s_scan) {
@@ -271,6 +327,7 @@ struct GeCell {
   u64 r0;
   u32 f0;
   bool gene_labels;   // labels are gene ids (PUG_GENE) — else transcript ids
+  u8* scratch;        // GE_SCRATCH_BYTES of shared memory for staged sorts
   // label of record-local index i
   __device__ __forceinline__ const u32* rec_lab(u32 i) const {
     return gene_labels ? p.glab + (a->ref_off[r0 + i] - f0) : a->refs + a->ref_off[r0 + i];
@@ -292,30 +349,35 @@ __device__ __forceinline__ bool out_edge(u32 hd, u32 cx, u32 cy) {
   return hd == 0 || !(cy > 2 * cx - 1);
 }
 
-// Enumerate the PUG neighbours of vertex v: every vertex w != v whose UMI is within Hamming
-// distance <= 1 (== 0 with pug_exact_umi) and whose class label shares a reference with v's.
-// f(w, hd) is called once per neighbour.
+// Presence bitmap of the cell's UMIs (hashed) in shared memory: the 3*L substitution candidates
+// of a vertex almost never exist, and the bitmap rejects them with one shared-memory load instead
+// of a probe walk through the L2-resident UMI table.
+constexpr u32 GE_BITMAP_LOG2 = 17;                       // 128 Kbit = 16 KB of the staged-sort scratch
+__device__ __forceinline__ u32 umi_bit(u32 umi) { return (umi * 0x9E3779B1u) >> (32 - GE_BITMAP_LOG2); }
+
+// PUG neighbours of vertex v through candidate k (k == 0: v's own UMI, hd = 0; k >= 1: one of the
+// 3*umi_len single-base substitutions, hd = 1): every vertex w != v carrying that UMI whose class
+// label shares a reference with v's. f(w, hd) is called once per neighbour. The (v, k) items are
+// the unit of parallel work.
 template <class F>
-__device__ inline void for_each_neighbour(const GeCell& c, u32 v, u32 utab_mask, u32 utab_log2, F f) {
-  const u32 u = c.v_umi(v), cv = c.v_cls(v);
-  const u32* lv = c.cls_lab(cv);
-  const u32 lnv = c.cls_lab_len(cv);
-  const u32 ncand = c.g->pug_exact_umi ? 1u : 1u + 3u * c.g->umi_len;
-  for (u32 k = 0; k < ncand; ++k) {
-    u32 cu = u, hd = 0;
-    if (k > 0) {
-      const u32 pos = (k - 1) / 3, d = 1 + (k - 1) % 3;
-      cu = u ^ (d << (2 * pos));
-      hd = 1;
-    }
-    const u32 s = tab_find(c.p.ctab_h, utab_mask, utab_log2, (u64)cu);
-    if (s == NONE32) continue;
-    for (u32 w = c.p.ctab_r[s]; w != NONE32; w = c.p.vnext[w]) {
-      if (w == v) continue;
-      const u32 cw = c.v_cls(w);
-      if (cw != cv && !sorted_share(lv, lnv, c.cls_lab(cw), c.cls_lab_len(cw))) continue;
-      f(w, hd);
-    }
+__device__ __forceinline__ void visit_candidate(const GeCell& c, u32 v, u32 k, u32 utab_mask, u32 utab_log2, const u32* bitmap, F f) {
+  const u32 u = c.v_umi(v);
+  u32 cu = u, hd = 0;
+  if (k > 0) {
+    const u32 pos = (k - 1) / 3, d = 1 + (k - 1) % 3;
+    cu = u ^ (d << (2 * pos));
+    hd = 1;
+  }
+  const u32 bit = umi_bit(cu);
+  if (!(bitmap[bit >> 5] >> (bit & 31) & 1u)) return;
+  const u32 s = tab_find(c.p.ctab_h, utab_mask, utab_log2, (u64)cu);
+  if (s == NONE32) return;
+  const u32 cv = c.v_cls(v);
+  for (u32 w = c.p.ctab_r[s]; w != NONE32; w = c.p.vnext[w]) {
+    if (w == v) continue;
+    const u32 cw = c.v_cls(w);
+    if (cw != cv && !sorted_share(c.cls_lab(cv), c.cls_lab_len(cv), c.cls_lab(cw), c.cls_lab_len(cw))) continue;
+    f(w, hd);
   }
 }
 
@@ -620,7 +682,7 @@ __device__ inline void crlike_molecules_from_ltab(const GeCell& c, GeShared* sh,
   const u32 D = next_pow2(d);
   for (u32 i = d + threadIdx.x; i < D; i += blockDim.x) c.p.ltab_k[i] = EMPTY_KEY;
   __syncthreads();
-  block_bitonic_pairs(c.p.ltab_k, c.p.ltab_c, D);
+  sort_pairs_staged(c.p.ltab_k, c.p.ltab_c, D, c.scratch);
   for (u32 i = threadIdx.x; i < d; i += blockDim.x) {
     const u32 u = (u32)(c.p.ltab_k[i] >> 32);
     if (i > 0 && (u32)(c.p.ltab_k[i - 1] >> 32) == u) continue;
@@ -640,9 +702,9 @@ __device__ inline void crlike_molecules_from_ltab(const GeCell& c, GeShared* sh,
 // =============================================================================================
 // The kernel body for one cell. Produces this cell's sparse counts in the staging rows.
 // =============================================================================================
-__device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, u8* arena, GeShared* sh) {
+__device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, u8* arena, GeShared* sh, u8* scratch) {
   GeCell c;
-  c.a = &a; c.g = &g;
+  c.a = &a; c.g = &g; c.scratch = scratch;
   c.r0 = a.cell_rec_off[cell];
   const u64 r1 = a.cell_rec_off[cell + 1];
   const u32 n = (u32)(r1 - c.r0);
@@ -735,7 +797,7 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
     const u32 Cp = next_pow2(C);
     for (u32 i = C + tid; i < Cp; i += T) { p.cls_rep[i] = NONE32; p.cls_aux[i] = NONE32; }
     __syncthreads();
-    block_bitonic_ids(p.cls_rep, p.cls_aux, Cp, [&](u32 x, u32 y) {
+    sort_ids_staged(p.cls_rep, p.cls_aux, Cp, c.scratch, [&](u32 x, u32 y) {
       return label_less(c.rec_lab(x), c.rec_lab_len(x), c.rec_lab(y), c.rec_lab_len(y));
     });
     for (u32 j = tid; j < C; j += T) p.ctab_r[p.cls_aux[j]] = j;  // slot -> rank
@@ -755,28 +817,37 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
     const u32 Vp = next_pow2(V);
     for (u32 i = V + tid; i < Vp; i += T) p.vtab_k[i] = EMPTY_KEY;
     __syncthreads();
-    block_bitonic_pairs(p.vtab_k, p.vtab_c, Vp);   // canonical vertex order: (class rank, UMI)
+    sort_pairs_staged(p.vtab_k, p.vtab_c, Vp, c.scratch);   // canonical vertex order: (class rank, UMI)
 
     // ---------------- phase 3: UMI -> vertex chains (table time-shares the class table) ---------
+    u32* bitmap = reinterpret_cast<u32*>(c.scratch);
     for (u32 i = tid; i < N2; i += T) { p.ctab_h[i] = EMPTY_KEY; p.ctab_r[i] = NONE32; }
+    for (u32 i = tid; i < (1u << (GE_BITMAP_LOG2 - 5)); i += T) bitmap[i] = 0;
     __syncthreads();
     for (u32 v = tid; v < V; v += T) {
       bool fresh;
-      const u32 s = tab_find_or_claim(p.ctab_h, m2, l2, (u64)c.v_umi(v), &fresh);
+      const u32 um = c.v_umi(v);
+      const u32 s = tab_find_or_claim(p.ctab_h, m2, l2, (u64)um, &fresh);
       p.vnext[v] = atomicExch(&p.ctab_r[s], v);
       p.parent[v] = v;
+      p.adj_off[v] = 0;
+      p.vlab_off[v] = 0;      // fill cursor of the adjacency pass below
+      const u32 bit = umi_bit(um);
+      atomicOr(&bitmap[bit >> 5], 1u << (bit & 31));
     }
     __syncthreads();
 
     // ---------------- phase 4: out-degrees + union-find, then adjacency fill --------------------
-    for (u32 v = tid; v < V; v += T) {
-      u32 deg = 0;
+    // one warp per vertex, lanes over the candidate UMIs; almost all are rejected by the bitmap
+    const u32 ncand = g.pug_exact_umi ? 1u : 1u + 3u * g.umi_len;
+    const u32 wid = tid >> 5, lane = tid & 31, nwarps = T >> 5;
+    for (u32 v = wid; v < V; v += nwarps) {
       const u32 cx = c.v_cnt(v);
-      for_each_neighbour(c, v, m2, l2, [&](u32 w, u32 hd) {
-        if (w > v) uf_union(p.parent, v, w);
-        if (out_edge(hd, cx, c.v_cnt(w))) ++deg;
-      });
-      p.adj_off[v] = deg;
+      for (u32 k = lane; k < ncand; k += 32)
+        visit_candidate(c, v, k, m2, l2, bitmap, [&](u32 w, u32 hd) {
+          if (w > v) uf_union(p.parent, v, w);
+          if (out_edge(hd, cx, c.v_cnt(w))) atomicAdd(&p.adj_off[v], 1u);
+        });
     }
     __syncthreads();
     const u32 E = block_exscan_array(p.adj_off, p.adj_off, V, sh->scan);
@@ -796,13 +867,17 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
       return;
     }
     const u64 adj_base = (u64)sh->adj_base_hi << 32 | sh->adj_base_lo;
-    for (u32 v = tid; v < V; v += T) {
-      u32 e = p.adj_off[v];
-      const u32 cx = c.v_cnt(v);
-      for_each_neighbour(c, v, m2, l2, [&](u32 w, u32 hd) {
-        if (out_edge(hd, cx, c.v_cnt(w))) g.adj_pool[adj_base + e++] = w;
-      });
+    if (E > 0) {
+      for (u32 v = wid; v < V; v += nwarps) {
+        if (p.adj_off[v + 1] == p.adj_off[v]) continue;   // warp-uniform: no out-edges to record
+        const u32 cx = c.v_cnt(v);
+        for (u32 k = lane; k < ncand; k += 32)
+          visit_candidate(c, v, k, m2, l2, bitmap, [&](u32 w, u32 hd) {
+            if (out_edge(hd, cx, c.v_cnt(w))) g.adj_pool[adj_base + p.adj_off[v] + atomicAdd(&p.vlab_off[v], 1u)] = w;
+          });
+      }
     }
+    __syncthreads();
     // ---------------- phase 5: components (sorted by root, members ascending) -------------------
     for (u32 v = tid; v < V; v += T) p.ckey[v] = ((u64)uf_find(p.parent, v) << 32) | v;
     for (u32 i = V + tid; i < Vp; i += T) p.ckey[i] = EMPTY_KEY;
@@ -810,7 +885,7 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
     for (u32 v = tid; v < V; v += T) p.vlab_off[v] = c.cls_lab_len(c.v_cls(v));
     __syncthreads();
     block_exscan_array(p.vlab_off, p.vlab_off, V, sh->scan);
-    block_bitonic_u64(p.ckey, Vp);
+    sort_u64_staged(p.ckey, Vp, c.scratch);
     // component starts
     u32 K = 0;
     {
@@ -847,7 +922,7 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
       const u32 Bp = next_pow2(nbig);
       for (u32 i = nbig + tid; i < Bp; i += T) p.cbig[i] = NONE32;
       __syncthreads();
-      block_bitonic_u32(p.cbig, Bp);
+      sort_u32_staged(p.cbig, Bp, c.scratch);
     }
     for (u32 b = 0; b < nbig; ++b) {
       const u32 k = p.cbig[b];
@@ -891,7 +966,7 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
     }
   }
   __syncthreads();
-  block_bitonic_pairs(p.mkey, p.midx, Mp);
+  sort_pairs_staged(p.mkey, p.midx, Mp, c.scratch);
   // segments of equal 2-gene prefix; labels longer than 2 are ordered inside the segment by
   // one thread (insertion sort on the full label), then classes are counted
   auto mol_less = [&](u32 x, u32 y) {
@@ -981,7 +1056,7 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
       p.ent_idx[j] = cnt;
     }
     __syncthreads();
-    block_bitonic_u64(p.tkey, next_pow2(G));
+    sort_u64_staged(p.tkey, next_pow2(G), c.scratch);
     u32 base = 0, lmax = 0;
     for (u32 c0 = 0; c0 < G; c0 += T) {
       const u32 i = c0 + tid;
@@ -1064,7 +1139,7 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
       }
     }
     __syncthreads();
-    block_bitonic_u32(p.sup, Sp);
+    sort_u32_staged(p.sup, Sp, c.scratch);
     u32 S = 0;
     {  // unique in place (chunked, same hazard-free pattern as the compactions)
       u32 base = 0;
@@ -1105,7 +1180,7 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
     __syncthreads();
     for (u32 e = tid; e < Lt; e += T) p.tkey[e] = ((u64)p.ent_loc[e] << 32) | e;
     __syncthreads();
-    block_bitonic_u64(p.tkey, Lp);
+    sort_u64_staged(p.tkey, Lp, c.scratch);
     for (u32 s = tid; s <= S; s += T) {  // g_off[s] = first sorted entry whose support index is >= s
       u32 lo = 0, hi = Lt;
       while (lo < hi) { u32 mid = (lo + hi) >> 1; if ((u32)(p.tkey[mid] >> 32) < s) lo = mid + 1; else hi = mid; }
@@ -1235,6 +1310,7 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
 // persistent kernel: CTAs pull cells from work list `list_id` (largest cells first)
 __global__ void __launch_bounds__(GE_THREADS) k_gene_eqc(KArgs a, GeArgs g) {
   __shared__ GeShared sh;
+  __shared__ __align__(16) u8 s_scratch[GE_SCRATCH_BYTES];
   u8* arena = g.arena + (u64)blockIdx.x * g.arena_bytes;
   const u32 count = a.ctl->bin_count[g.list_id];
   const u32* list = a.bin_list + (u64)g.list_id * a.n_cells;
@@ -1244,7 +1320,7 @@ __global__ void __launch_bounds__(GE_THREADS) k_gene_eqc(KArgs a, GeArgs g) {
     const u32 job = sh.job;
     __syncthreads();
     if (job >= count) break;
-    gene_eqc_cell(a, g, list[job], arena, &sh);
+    gene_eqc_cell(a, g, list[job], arena, &sh, s_scratch);
   }
 }
 
@@ -1254,7 +1330,7 @@ constexpr int GE_LIST_BIG = NUM_BINS;      // bin_list row for cells > GE_BIG_RE
 constexpr int GE_LIST_NORMAL = NUM_BINS + 1;
 constexpr u32 GE_BIG_RECORDS = 1u << 16;
 
-__global__ void k_bin_cells_ge(KArgs a, int force_bin, u32 big_records) {
+__global__ void k_bin_cells_ge(KArgs a, int force_bin, u32 big_records, u32 need_shift) {
   const u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= a.n_cells) return;
   const u64 r0 = a.cell_rec_off[c], r1 = a.cell_rec_off[c + 1];
@@ -1262,7 +1338,7 @@ __global__ void k_bin_cells_ge(KArgs a, int force_bin, u32 big_records) {
   const u32 p = a.ref_off[r1] - a.ref_off[r0];
   int b;
   if (a.tiny_eligible && n < a.small_thresh) {
-    const u64 need = n < (u64)p ? n : (u64)p;
+    const u64 need = (n < (u64)p ? n : (u64)p) << need_shift;
     b = NUM_SMEM_BINS;
 #pragma unroll
     for (int i = NUM_SMEM_BINS - 1; i >= 0; --i)

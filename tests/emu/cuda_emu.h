@@ -23,7 +23,7 @@
 #define __global__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
-#define __align__(x) alignas(x)
+#define __align__(x) __attribute__((aligned(x)))
 #define __shared__ static
 #define __restrict__
 
@@ -209,6 +209,7 @@ inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned)v); }
 inline int __clzll(long long v) { return v == 0 ? 64 : __builtin_clzll((unsigned long long)v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }
+inline int __ffsll(long long v) { return __builtin_ffsll(v); }
 inline unsigned __brev(unsigned v) { unsigned r = 0; for (int i = 0; i < 32; ++i) if (v & (1u << i)) r |= 1u << (31 - i); return r; }
 template <class T> inline T __ldg(const T* p) { return *p; }
 inline float __fmul_rn(float a, float b) { return a * b; }

@@ -39,6 +39,12 @@ struct EmuLauncher {
     return arena[which].data();
   }
   u32* adj_pool(u64 n) { adj.assign((size_t)n, 0xCDCDCDCDu); return adj.data(); }
+  void fork(int) {}
+  void lane(int) {}
+  void join() {}
+  void region_begin() {}
+  void region_end() {}
+  u32 need_shift() { const char* s = getenv("AFQ_NEED_SHIFT"); return s ? (u32)atoi(s) : 0; }
 };
 
 struct EmuResult {

@@ -83,3 +83,32 @@ def test_emu_uniform_init_and_many_gene_labels():
     for res in ("cr-like-em", "parsimony-em"):
         check(opts_for(spec, res, init_uniform=True, small_thresh=0), t2g, b, res)
         check(opts_for(spec, res, small_thresh=0), t2g, b, res)
+
+
+@pytest.mark.parametrize("res", ["cr-like", "trivial"])
+def test_emu_resolve_hot_buckets_and_large_gene_axis(res, monkeypatch):
+    # few genes, many molecules: winner buckets hold hundreds of equal slots (cooperative hot-bucket path)
+    spec = synth.SynthSpec(n_genes=40, reads_mean=3000.0, reads_per_umi=1.5, zipf_s=1.3)
+    b = synth.generate(spec, 0, 4)
+    check(opts_for(spec, res), synth.tid_to_gid(spec), b, res + "/hot")
+    # 300k genes: slot >> shift needs > 8 low bits -> winners are ordered directly (rank / bitonic path)
+    spec = synth.SynthSpec(n_genes=300_000, reads_mean=2500.0, reads_per_umi=1.2, zipf_s=0.3)
+    b = synth.generate(spec, 0, 3)
+    check(opts_for(spec, res), synth.tid_to_gid(spec), b, res + "/wide")
+
+
+@pytest.mark.parametrize("force_bin", ["2", "3", "4", "6"])
+def test_emu_forced_arena(monkeypatch, force_bin):
+    monkeypatch.setenv("AFQ_FORCE_BIN", force_bin)
+    spec = synth.SynthSpec(reads_mean=600.0)
+    b = synth.generate(spec, 50, 6)
+    for res in ("cr-like", "trivial"):
+        check(opts_for(spec, res), synth.tid_to_gid(spec), b, f"{res}/bin{force_bin}")
+
+
+def test_emu_overflow_requeue():
+    # no duplication, several genes per read: distinct pairs exceed 75 % of the arena chosen from
+    # the record count, so cells are re-queued on the next arena size
+    spec = synth.SynthSpec(reads_mean=900.0, reads_per_umi=1.0, p_multi2=0.45, p_multi3=0.45, lognorm_sigma=0.3)
+    b = synth.generate(spec, 0, 6)
+    check(opts_for(spec, "cr-like"), synth.tid_to_gid(spec), b, "overflow")
