@@ -29,6 +29,13 @@ enum : u32 { GE_MODE_PUG_TXP = 0, GE_MODE_PUG_GENE = 1, GE_MODE_CRLIKE = 2 };
 enum : u32 { DEV_ERR_ADJ_POOL = 2, DEV_ERR_ARENA = 4, DEV_ERR_HASH = 8, DEV_ERR_LABEL = 16 };
 
 constexpr u32 GE_THREADS = 256;
+
+// CTA-strided loop with a warp-uniform trip count and a __syncwarp() per iteration: lanes that took a
+// long path in the body re-join their warp before the next element instead of drifting apart for the
+// rest of the phase (ncu r1f: loop headers of the divergent phases ran with ~5 of 32 lanes).
+#define GE_FOR(X, N) \
+  for (u32 X##_b = 0, X = threadIdx.x; (__syncwarp(), X##_b < (N)); X##_b += blockDim.x, X += blockDim.x) \
+    if (X < (N))
 constexpr u32 SMALL_COMP = 32;      // components up to this size are covered by one thread
 constexpr u32 MAX_GRAPH_THRESH = 4096;
 
@@ -731,9 +738,9 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
   if (g.ge_mode == GE_MODE_CRLIKE) {
     // ---------------- cr-like molecules: per UMI the arg-max gene set ------------------------
     const u32 cap = p.P2, l2 = ilog2(cap);
-    for (u32 i = tid; i < cap; i += T) { p.ltab_k[i] = EMPTY_KEY; p.ltab_c[i] = 0; }
+    GE_FOR(i, cap) { p.ltab_k[i] = EMPTY_KEY; p.ltab_c[i] = 0; }
     __syncthreads();
-    for (u32 i = tid; i < n; i += T) {
+    GE_FOR(i, n) {
       const u32 umi = a.umi[c.r0 + i];
       const u32 o0 = a.ref_off[c.r0 + i], o1 = a.ref_off[c.r0 + i + 1];
       for (u32 k = o0; k < o1; ++k) {
@@ -748,7 +755,7 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
   } else {
     // ---------------- phase 1: eq-classes -----------------------------------------------------
     if (c.gene_labels) {  // materialise the sorted-dedup gene projection of every record
-      for (u32 i = tid; i < n; i += T) {
+      GE_FOR(i, n) {
         const u32 o0 = a.ref_off[c.r0 + i], o1 = a.ref_off[c.r0 + i + 1];
         u32* dst = p.glab + (o0 - c.f0);
         for (u32 k = o0; k < o1; ++k) dst[k - o0] = __ldg(a.t2g + a.refs[k]);
@@ -759,17 +766,17 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
     const u32 N2 = p.N2, l2 = ilog2(N2), m2 = N2 - 1;
     u32 seed = 0;
     for (;; ++seed) {
-      for (u32 i = tid; i < N2; i += T) { p.ctab_h[i] = EMPTY_KEY; p.ctab_r[i] = NONE32; }
+      GE_FOR(i, N2) { p.ctab_h[i] = EMPTY_KEY; p.ctab_r[i] = NONE32; }
       if (tid == 0) sh->flag = 0;
       __syncthreads();
-      for (u32 i = tid; i < n; i += T) {
+      GE_FOR(i, n) {
         bool fresh;
         const u32 s = tab_find_or_claim(p.ctab_h, m2, l2, label_hash(c.rec_lab(i), c.rec_lab_len(i), seed), &fresh);
         atomicMin(&p.ctab_r[s], i);
         p.rec_slot[i] = s;
       }
       __syncthreads();
-      for (u32 i = tid; i < n; i += T) {
+      GE_FOR(i, n) {
         const u32 rep = p.ctab_r[p.rec_slot[i]];
         if (rep != i && !label_equal(c.rec_lab(i), c.rec_lab_len(i), c.rec_lab(rep), c.rec_lab_len(rep))) sh->flag = 1;
       }
@@ -800,13 +807,13 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
     sort_ids_staged(p.cls_rep, p.cls_aux, Cp, c.scratch, [&](u32 x, u32 y) {
       return label_less(c.rec_lab(x), c.rec_lab_len(x), c.rec_lab(y), c.rec_lab_len(y));
     });
-    for (u32 j = tid; j < C; j += T) p.ctab_r[p.cls_aux[j]] = j;  // slot -> rank
+    GE_FOR(j, C) p.ctab_r[p.cls_aux[j]] = j;  // slot -> rank
     __syncthreads();
 
     // ---------------- phase 2: vertices = distinct (class, UMI) with read counts ---------------
-    for (u32 i = tid; i < N2; i += T) { p.vtab_k[i] = EMPTY_KEY; p.vtab_c[i] = 0; }
+    GE_FOR(i, N2) { p.vtab_k[i] = EMPTY_KEY; p.vtab_c[i] = 0; }
     __syncthreads();
-    for (u32 i = tid; i < n; i += T) {
+    GE_FOR(i, n) {
       const u64 key = ((u64)p.ctab_r[p.rec_slot[i]] << 32) | a.umi[c.r0 + i];
       bool fresh;
       const u32 s = tab_find_or_claim(p.vtab_k, m2, l2, key, &fresh);
@@ -821,10 +828,10 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
 
     // ---------------- phase 3: UMI -> vertex chains (table time-shares the class table) ---------
     u32* bitmap = reinterpret_cast<u32*>(c.scratch);
-    for (u32 i = tid; i < N2; i += T) { p.ctab_h[i] = EMPTY_KEY; p.ctab_r[i] = NONE32; }
+    GE_FOR(i, N2) { p.ctab_h[i] = EMPTY_KEY; p.ctab_r[i] = NONE32; }
     for (u32 i = tid; i < (1u << (GE_BITMAP_LOG2 - 5)); i += T) bitmap[i] = 0;
     __syncthreads();
-    for (u32 v = tid; v < V; v += T) {
+    GE_FOR(v, V) {
       bool fresh;
       const u32 um = c.v_umi(v);
       const u32 s = tab_find_or_claim(p.ctab_h, m2, l2, (u64)um, &fresh);
@@ -841,13 +848,17 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
     // one warp per vertex, lanes over the candidate UMIs; almost all are rejected by the bitmap
     const u32 ncand = g.pug_exact_umi ? 1u : 1u + 3u * g.umi_len;
     const u32 wid = tid >> 5, lane = tid & 31, nwarps = T >> 5;
-    for (u32 v = wid; v < V; v += nwarps) {
+    for (u32 v = wid; v < V; v += nwarps) {   // v is warp-uniform
       const u32 cx = c.v_cnt(v);
-      for (u32 k = lane; k < ncand; k += 32)
-        visit_candidate(c, v, k, m2, l2, bitmap, [&](u32 w, u32 hd) {
-          if (w > v) uf_union(p.parent, v, w);
-          if (out_edge(hd, cx, c.v_cnt(w))) atomicAdd(&p.adj_off[v], 1u);
-        });
+      for (u32 k0 = 0; k0 < ncand; k0 += 32) {
+        __syncwarp();
+        const u32 k = k0 + lane;
+        if (k < ncand)
+          visit_candidate(c, v, k, m2, l2, bitmap, [&](u32 w, u32 hd) {
+            if (w > v) uf_union(p.parent, v, w);
+            if (out_edge(hd, cx, c.v_cnt(w))) atomicAdd(&p.adj_off[v], 1u);
+          });
+      }
     }
     __syncthreads();
     const u32 E = block_exscan_array(p.adj_off, p.adj_off, V, sh->scan);
@@ -871,18 +882,22 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
       for (u32 v = wid; v < V; v += nwarps) {
         if (p.adj_off[v + 1] == p.adj_off[v]) continue;   // warp-uniform: no out-edges to record
         const u32 cx = c.v_cnt(v);
-        for (u32 k = lane; k < ncand; k += 32)
-          visit_candidate(c, v, k, m2, l2, bitmap, [&](u32 w, u32 hd) {
-            if (out_edge(hd, cx, c.v_cnt(w))) g.adj_pool[adj_base + p.adj_off[v] + atomicAdd(&p.vlab_off[v], 1u)] = w;
-          });
+        for (u32 k0 = 0; k0 < ncand; k0 += 32) {
+          __syncwarp();
+          const u32 k = k0 + lane;
+          if (k < ncand)
+            visit_candidate(c, v, k, m2, l2, bitmap, [&](u32 w, u32 hd) {
+              if (out_edge(hd, cx, c.v_cnt(w))) g.adj_pool[adj_base + p.adj_off[v] + atomicAdd(&p.vlab_off[v], 1u)] = w;
+            });
+        }
       }
     }
     __syncthreads();
     // ---------------- phase 5: components (sorted by root, members ascending) -------------------
-    for (u32 v = tid; v < V; v += T) p.ckey[v] = ((u64)uf_find(p.parent, v) << 32) | v;
+    GE_FOR(v, V) p.ckey[v] = ((u64)uf_find(p.parent, v) << 32) | v;
     for (u32 i = V + tid; i < Vp; i += T) p.ckey[i] = EMPTY_KEY;
     // label storage offsets per vertex (molecule labels live at their first vertex's region)
-    for (u32 v = tid; v < V; v += T) p.vlab_off[v] = c.cls_lab_len(c.v_cls(v));
+    GE_FOR(v, V) p.vlab_off[v] = c.cls_lab_len(c.v_cls(v));
     __syncthreads();
     block_exscan_array(p.vlab_off, p.vlab_off, V, sh->scan);
     sort_u64_staged(p.ckey, Vp, c.scratch);
@@ -903,7 +918,7 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
       __syncthreads();
     }
     // ---------------- phase 6: molecules -------------------------------------------------------
-    for (u32 k = tid; k < K; k += T) {
+    GE_FOR(k, K) {
       const u32 pos = p.cstart[k], s = p.cstart[k + 1] - pos;
       if (s == 1) {
         const u32 v = (u32)p.ckey[pos];
@@ -930,9 +945,9 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
       if (s > g.large_graph_thresh) {
         if (tid == 0) sh->alt = 1;
         const u32 cap = p.P2, ll2 = ilog2(cap);
-        for (u32 i = tid; i < cap; i += T) { p.ltab_k[i] = EMPTY_KEY; p.ltab_c[i] = 0; }
+        GE_FOR(i, cap) { p.ltab_k[i] = EMPTY_KEY; p.ltab_c[i] = 0; }
         __syncthreads();
-        for (u32 i = tid; i < s; i += T) {
+        GE_FOR(i, s) {
           const u32 v = (u32)p.ckey[pos + i];
           const u32 cv = c.v_cls(v);
           u32* tmp = p.cmem + p.rows + p.vlab_off[v];  // scratch region sized like the label
@@ -952,7 +967,7 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
   // =================== stage B: molecules -> gene eq-classes in canonical order ===============
   const u32 M = sh->n_mol;
   const u32 Mp = next_pow2(M);
-  for (u32 i = tid; i < Mp; i += T) {
+  GE_FOR(i, Mp) {
     if (i < M) {
       const u32* lab = p.mlab + p.mol_off[i];
       const u32 len = p.mol_len[i];
@@ -975,7 +990,7 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
   auto mol_eq = [&](u32 x, u32 y) {
     return label_equal(p.mlab + p.mol_off[x], p.mol_len[x], p.mlab + p.mol_off[y], p.mol_len[y]);
   };
-  for (u32 i = tid; i < M; i += T) {
+  GE_FOR(i, M) {
     if (i > 0 && p.mkey[i - 1] == p.mkey[i]) continue;
     u32 j = i + 1;
     while (j < M && p.mkey[j] == p.mkey[i]) ++j;
@@ -1007,13 +1022,13 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
     __syncthreads();
   }
   // zero-length labels sort first (key 0) and never start a class; count = distance to next start
-  for (u32 j = tid; j < G; j += T) {
+  GE_FOR(j, G) {
     const u32 i = p.gcls_m[j];
     const u32 nxt = (j + 1 < G) ? p.gcls_m[j + 1] : M;
     p.gcls_cnt[j] = nxt - i;
   }
   __syncthreads();
-  for (u32 j = tid; j < G; j += T) p.gcls_m[j] = p.midx[p.gcls_m[j]];  // -> representative molecule id
+  GE_FOR(j, G) p.gcls_m[j] = p.midx[p.gcls_m[j]];  // -> representative molecule id
   __syncthreads();
   auto cls_label = [&](u32 j) { return p.mlab + p.mol_off[p.gcls_m[j]]; };
   auto cls_len = [&](u32 j) { return p.mol_len[p.gcls_m[j]]; };
@@ -1085,7 +1100,7 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
     // ------------------------------- EM ---------------------------------------------------------
     // entries = (class, label position) in class order; USA rewrites gene-id labels into S/U/A
     // slot labels (extract_usa_eqmap, src/utils.rs:842-926: adjacent S,U of one gene fuse to A).
-    for (u32 j = tid; j < G; j += T) {
+    GE_FOR(j, G) {
       u32 e = 0;
       if (!usa) e = cls_len(j);
       else {
@@ -1100,7 +1115,7 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
     const u32 Lt = block_exscan_array(p.gcls_eoff, p.gcls_eoff, G, sh->scan);
     if (tid == 0) p.gcls_eoff[G] = Lt;
     __syncthreads();
-    for (u32 j = tid; j < G; j += T) {
+    GE_FOR(j, G) {
       const u32* lab = cls_label(j);
       const u32 len = cls_len(j);
       u32 e = p.gcls_eoff[j];
@@ -1120,16 +1135,16 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
     // M1 (gene mode) always iterates.
     if (tid == 0) sh->flag = 0;
     __syncthreads();
-    for (u32 j = tid; j < G; j += T) if (p.gcls_eoff[j + 1] - p.gcls_eoff[j] > 1) sh->flag = 1;
+    GE_FOR(j, G) if (p.gcls_eoff[j + 1] - p.gcls_eoff[j] > 1) sh->flag = 1;
     __syncthreads();
     const bool needs_em = !usa || sh->flag;
     // support: label indices (+ USA siblings, src/em.rs:87-113), sorted unique
     const u32 per = usa ? 3u : 1u;
     const u32 Sraw = Lt * per;
     const u32 Sp = next_pow2(Sraw);
-    for (u32 e = tid; e < Sp; e += T) p.sup[e] = NONE32;
+    GE_FOR(e, Sp) p.sup[e] = NONE32;
     __syncthreads();
-    for (u32 e = tid; e < Lt; e += T) {
+    GE_FOR(e, Lt) {
       const u32 idx = p.ent_idx[e];
       p.sup[e * per] = idx;
       if (usa) {
@@ -1160,10 +1175,10 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
       while (lo < hi) { u32 mid = (lo + hi) >> 1; if (p.sup[mid] < idx) lo = mid + 1; else hi = mid; }
       return (lo < S && p.sup[lo] == idx) ? lo : NONE32;
     };
-    for (u32 e = tid; e < Lt; e += T) p.ent_loc[e] = loc_of(p.ent_idx[e]);
+    GE_FOR(e, Lt) p.ent_loc[e] = loc_of(p.ent_idx[e]);
     // USA sibling locations per support index: abundance (src/em.rs:167-187)
     //   A: a[U] + a[S] + a[A];  U: a[A] + a[U];  S: a[A] + a[S]
-    for (u32 s = tid; s < S; s += T) {
+    GE_FOR(s, S) {
       u32 sa = NONE32, sb = NONE32;
       if (usa) {
         const u32 idx = p.sup[s];
@@ -1176,9 +1191,9 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
     }
     // transposed CSR: entries grouped by support index, class order inside a group
     const u32 Lp = next_pow2(Lt);
-    for (u32 e = tid; e < Lp; e += T) p.tkey[e] = EMPTY_KEY;
+    GE_FOR(e, Lp) p.tkey[e] = EMPTY_KEY;
     __syncthreads();
-    for (u32 e = tid; e < Lt; e += T) p.tkey[e] = ((u64)p.ent_loc[e] << 32) | e;
+    GE_FOR(e, Lt) p.tkey[e] = ((u64)p.ent_loc[e] << 32) | e;
     __syncthreads();
     sort_u64_staged(p.tkey, Lp, c.scratch);
     for (u32 s = tid; s <= S; s += T) {  // g_off[s] = first sorted entry whose support index is >= s
@@ -1194,7 +1209,7 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
       return lo;
     };
     // singleton tallies, accumulated per index in class order (integers: exact)
-    for (u32 s = tid; s < S; s += T) {
+    GE_FOR(s, S) {
       float t = 0.0f;
       for (u32 q = p.g_off[s]; q < p.g_off[s + 1]; ++q) {
         const u32 e = (u32)p.tkey[q];
@@ -1206,7 +1221,7 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
     __syncthreads();
     if (needs_em) {
       const float uni = __fdiv_rn(1.0f, (float)g.num_alphas);
-      for (u32 s = tid; s < S; s += T)
+      GE_FOR(s, S)
         p.alpha_in[s] = g.em_init_uniform ? uni : __fmul_rn(__fadd_rn(p.alpha_in[s], 0.5f), 1e-3f);
       __syncthreads();
       auto abund = [&](u32 s) {
@@ -1223,7 +1238,7 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
       bool last_round = false;
       for (;;) {
         // E step, per class: inv = count / sum of abundances (label order)
-        for (u32 j = tid; j < G; j += T) {
+        GE_FOR(j, G) {
           const u32 e0 = p.gcls_eoff[j], e1 = p.gcls_eoff[j + 1];
           float inv = -1.0f;  // < 0: class contributes nothing
           if (e1 - e0 > 1) {
@@ -1236,7 +1251,7 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
         if (tid == 0) sh->flag = 0;
         __syncthreads();
         // M step, per support index, contributions added in class order
-        for (u32 s = tid; s < S; s += T) {
+        GE_FOR(s, S) {
           float out = 0.0f;
           const float ab = abund(s);
           for (u32 q = p.g_off[s]; q < p.g_off[s + 1]; ++q) {
@@ -1250,7 +1265,7 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
         }
         __syncthreads();
         const bool converged = sh->flag == 0;
-        for (u32 s = tid; s < S; s += T) p.alpha_in[s] = p.alpha_out[s];
+        GE_FOR(s, S) p.alpha_in[s] = p.alpha_out[s];
         __syncthreads();
         ++it;
         if (!usa) {  // M1: src/em.rs:538-565
@@ -1258,13 +1273,13 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
         } else {     // M2: src/em.rs:391-443 (clamp, then one last round)
           if (last_round) break;
           if (it >= 2 && converged) {
-            for (u32 s = tid; s < S; s += T) if (p.alpha_in[s] < 0.01f) p.alpha_in[s] = 0.0f;
+            GE_FOR(s, S) if (p.alpha_in[s] < 0.01f) p.alpha_in[s] = 0.0f;
             last_round = true;
             __syncthreads();
           } else if (!(it < 2 || (it < 100 && !converged))) break;
         }
       }
-      for (u32 s = tid; s < S; s += T) if (p.alpha_in[s] < 0.01f) p.alpha_in[s] = 0.0f;
+      GE_FOR(s, S) if (p.alpha_in[s] < 0.01f) p.alpha_in[s] = 0.0f;
       __syncthreads();
     }
     // emit positive alphas, ascending index
@@ -1291,7 +1306,7 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
   __syncthreads();
   const float mean = __fdiv_rn(sh->fsum, (float)nnz);
   u32 lover = 0;
-  for (u32 i = tid; i < nnz; i += T) if (a.stage_val[out_base + i] > mean) ++lover;
+  GE_FOR(i, nnz) if (a.stage_val[out_base + i] > mean) ++lover;
   if (lover) atomicAdd(&sh->cnt0, lover);
   __syncthreads();
   if (tid == 0) {
@@ -1308,7 +1323,7 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
 }
 
 // persistent kernel: CTAs pull cells from work list `list_id` (largest cells first)
-__global__ void __launch_bounds__(GE_THREADS) k_gene_eqc(KArgs a, GeArgs g) {
+__global__ void __launch_bounds__(GE_THREADS, 4) k_gene_eqc(KArgs a, GeArgs g) {
   __shared__ GeShared sh;
   __shared__ __align__(16) u8 s_scratch[GE_SCRATCH_BYTES];
   u8* arena = g.arena + (u64)blockIdx.x * g.arena_bytes;
