@@ -41,7 +41,7 @@ class AfqBatch(C.Structure):
         ("first_cell_index", C.c_uint64), ("n_cells", C.c_uint64), ("n_records", C.c_uint64),
         ("n_refs_total", C.c_uint64),
         ("cell_rec_offsets", C.c_void_p), ("rec_umi32", C.c_void_p),
-        ("rec_ref_offsets", C.c_void_p), ("refs", C.c_void_p),
+        ("rec_ref_offsets", C.c_void_p), ("refs", C.c_void_p), ("rec_na8", C.c_void_p),
     ]
 
 

@@ -73,6 +73,8 @@ struct Work {  // per-pipeline scratch (ordered on one stream)
   DBuf<u64> tile_sums;
   DBuf<u8> ge_arena[2];
   DBuf<u32> adj_pool;
+  DBuf<u64> na_tiles;      // rec_na8 -> offsets scan
+  DBuf<u32> na_ref_off;    // device API: offsets derived from rec_na8
   cudaError_t ensure(u64 n_cells, u64 n_refs) {
     cudaError_t e;
     if ((e = ctl.ensure(1)) != cudaSuccess) return e;
@@ -85,12 +87,14 @@ struct Work {  // per-pipeline scratch (ordered on one stream)
   void release() {
     ctl.release(); bin_list.release(); stage_col.release(); stage_val.release();
     tile_sums.release(); ge_arena[0].release(); ge_arena[1].release(); adj_pool.release();
+    na_tiles.release(); na_ref_off.release();
   }
 };
 
 struct Slot {  // one in-flight host batch
   DBuf<u64> cell_rec_off;
   DBuf<u32> umi, ref_off, refs;
+  DBuf<u8> na8;
   DBuf<u64> row_ptr;
   DBuf<u32> col;
   DBuf<float> val, sum_umi, max_umi;
@@ -105,7 +109,7 @@ struct Slot {  // one in-flight host batch
   u64 n_cells = 0, n_refs = 0, ticket = 0;
   bool busy = false;
   void release() {
-    cell_rec_off.release(); umi.release(); ref_off.release(); refs.release();
+    cell_rec_off.release(); umi.release(); ref_off.release(); refs.release(); na8.release();
     row_ptr.release(); col.release(); val.release(); sum_umi.release(); max_umi.release();
     num_expr.release(); num_over_mean.release(); flags.release();
     h_row_ptr.release(); h_col.release(); h_num_expr.release(); h_num_over_mean.release();
@@ -246,10 +250,18 @@ int run_pipeline(afq_ctx* c, Work& w, const afq_batch& b, const afq_device_out& 
     return AFQ_ERR_INVALID;
   }
   if (b.n_cells) CUDA_TRY(c, w.ensure(b.n_cells, b.n_refs_total));
+  afq_batch bb = b;
+  CudaLauncher l{c, &w, st, st};
+  if (!bb.rec_ref_offsets) {
+    if (!bb.rec_na8) { c->err = "afq_batch needs rec_ref_offsets or rec_na8"; return AFQ_ERR_INVALID; }
+    CUDA_TRY(c, w.na_tiles.ensure(bb.n_records / SCAN_TILE + 4));
+    CUDA_TRY(c, w.na_ref_off.ensure(bb.n_records + 2));
+    enqueue_na8_offsets(l, bb.rec_na8, bb.n_records, w.na_ref_off.p, w.na_tiles.p + 1, w.na_tiles.p);
+    bb.rec_ref_offsets = w.na_ref_off.p;
+  }
   PipeBufs pb{w.ctl.p, w.bin_list.p, w.stage_col.p, w.stage_val.p, w.tile_sums.p,
               c->large_keys, c->large_cnts, c->large_cap_log2, c->large_blocks};
-  CudaLauncher l{c, &w, st, st};
-  int rc = enqueue_batch(l, c->cfg, c->force_bin, pb, b, o, c->err);
+  int rc = enqueue_batch(l, c->cfg, c->force_bin, pb, bb, o, c->err);
   if (rc != AFQ_OK) return rc;
   CUDA_TRY(c, cudaGetLastError());
   return AFQ_OK;
@@ -415,7 +427,8 @@ int afq_submit(afq_ctx* c, const afq_batch* hb, uint64_t* ticket) {
   const u64 nc = hb->n_cells, nr = hb->n_records, nf = hb->n_refs_total;
   CUDA_TRY(c, s.cell_rec_off.ensure(nc + 1));
   CUDA_TRY(c, s.umi.ensure(nr + 1));
-  CUDA_TRY(c, s.ref_off.ensure(nr + 1));
+  CUDA_TRY(c, s.ref_off.ensure(nr + 2));
+  if (hb->rec_na8 && !hb->rec_ref_offsets) CUDA_TRY(c, s.na8.ensure(nr + 1));
   CUDA_TRY(c, s.refs.ensure(nf + 1));
   CUDA_TRY(c, s.row_ptr.ensure(nc + 1));
   CUDA_TRY(c, s.col.ensure(nf + 1));
@@ -435,14 +448,18 @@ int afq_submit(afq_ctx* c, const afq_batch* hb, uint64_t* ticket) {
   // H2D on the copy stream (overlaps the previous batch's kernels)
   CUDA_TRY(c, cudaMemcpyAsync(s.cell_rec_off.p, hb->cell_rec_offsets, (nc + 1) * sizeof(u64), cudaMemcpyHostToDevice, c->s_copy));
   if (nr) CUDA_TRY(c, cudaMemcpyAsync(s.umi.p, hb->rec_umi32, nr * sizeof(u32), cudaMemcpyHostToDevice, c->s_copy));
-  CUDA_TRY(c, cudaMemcpyAsync(s.ref_off.p, hb->rec_ref_offsets, (nr + 1) * sizeof(u32), cudaMemcpyHostToDevice, c->s_copy));
+  const bool use_na8 = hb->rec_na8 && !hb->rec_ref_offsets;
+  if (!use_na8 && !hb->rec_ref_offsets) { c->err = "afq_batch needs rec_ref_offsets or rec_na8"; return AFQ_ERR_INVALID; }
+  if (use_na8) { if (nr) CUDA_TRY(c, cudaMemcpyAsync(s.na8.p, hb->rec_na8, nr * sizeof(u8), cudaMemcpyHostToDevice, c->s_copy)); }
+  else CUDA_TRY(c, cudaMemcpyAsync(s.ref_off.p, hb->rec_ref_offsets, (nr + 1) * sizeof(u32), cudaMemcpyHostToDevice, c->s_copy));
   if (nf) CUDA_TRY(c, cudaMemcpyAsync(s.refs.p, hb->refs, nf * sizeof(u32), cudaMemcpyHostToDevice, c->s_copy));
   CUDA_TRY(c, cudaEventRecord(s.ev_h2d, c->s_copy));
   CUDA_TRY(c, cudaStreamWaitEvent(c->s_compute, s.ev_h2d, 0));
   afq_batch db = *hb;
   db.cell_rec_offsets = s.cell_rec_off.p;
   db.rec_umi32 = s.umi.p;
-  db.rec_ref_offsets = s.ref_off.p;
+  db.rec_ref_offsets = use_na8 ? nullptr : s.ref_off.p;
+  db.rec_na8 = use_na8 ? s.na8.p : nullptr;
   db.refs = s.refs.p;
   afq_device_out o{};
   o.row_ptr = s.row_ptr.p; o.cap_cells = nc + 1;

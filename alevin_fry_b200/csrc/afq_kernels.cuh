@@ -569,6 +569,35 @@ __global__ void __launch_bounds__(1024) k_scan_rows(const u32* num_expr, u64 n, 
   }
 }
 
+// ---- CSR offsets from per-record alignment counts (afq_batch.rec_na8) -------------------------
+__global__ void __launch_bounds__(1024) k_na_tile_sums(const u8* na, u64 n, u64* tile_sums) {
+  __shared__ u32 s_warp[40];
+  const u64 t0 = (u64)blockIdx.x * SCAN_TILE + (u64)threadIdx.x * 4;
+  u32 v = 0;
+#pragma unroll
+  for (u32 k = 0; k < 4; ++k) if (t0 + k < n) v += na[t0 + k];
+  u32 tot;
+  block_exscan(v, s_warp, &tot);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(1024) k_na_offsets(const u8* na, u64 n, const u64* tile_sums, u32* ref_off) {
+  __shared__ u32 s_warp[40];
+  const u64 t0 = (u64)blockIdx.x * SCAN_TILE + (u64)threadIdx.x * 4;
+  u32 v[4];
+  u32 s = 0;
+#pragma unroll
+  for (u32 k = 0; k < 4; ++k) { v[k] = (t0 + k < n) ? na[t0 + k] : 0; s += v[k]; }
+  u32 tot;
+  const u32 ex = block_exscan(s, s_warp, &tot);
+  u64 run = tile_sums[blockIdx.x] + ex;
+#pragma unroll
+  for (u32 k = 0; k < 4; ++k) {
+    if (t0 + k <= n) ref_off[t0 + k] = (u32)run;   // index n receives the closing offset
+    run += v[k];
+  }
+}
+
 // one warp per cell copies its staging row to its CSR row
 __global__ void __launch_bounds__(256) k_gather_rows(KArgs a, const u64* row_ptr, u32* col, float* val) {
   const u64 w = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;

@@ -26,12 +26,13 @@ namespace afq {
 
 enum KernelId : int {
   KID_BIN = 0, KID_SMEM0 = 1, KID_LARGE = 7, KID_SCAN_SUMS = 8, KID_SCAN_TILES = 9, KID_SCAN_ROWS = 10,
-  KID_GATHER = 11, KID_GENE_EQC = 12, KID_GENE_EQC_BIG = 13, KID_BIN_GE = 14, KID_REGION = 15, NUM_KID = 16
+  KID_GATHER = 11, KID_GENE_EQC = 12, KID_GENE_EQC_BIG = 13, KID_BIN_GE = 14, KID_REGION = 15, KID_NA_OFFSETS = 16, NUM_KID = 17
 };
 static const char* const KID_NAMES[NUM_KID] = {
     "k_bin_cells", "k_resolve_smem<0>", "k_resolve_smem<1>", "k_resolve_smem<2>", "k_resolve_smem<3>",
     "k_resolve_smem<4>", "k_resolve_smem<5>", "k_resolve_large", "k_scan_tile_sums", "k_scan_tiles",
-    "k_scan_rows", "k_gather_rows", "k_gene_eqc", "k_gene_eqc(big cells)", "k_bin_cells_ge", "resolve_region(wall)"};
+    "k_scan_rows", "k_gather_rows", "k_gene_eqc", "k_gene_eqc(big cells)", "k_bin_cells_ge", "resolve_region(wall)",
+    "k_na_offsets(+tile sums)"};
 
 struct PipeBufs {  // device scratch owned by the caller (one set per stream-ordered pipeline)
   Ctl* ctl;
@@ -74,6 +75,16 @@ inline void launch_crlike_bins(L& l, const KArgs& a, const PipeBufs& pb) {
   l.join();
   l.launch(KID_LARGE, k_resolve_large, pb.large_blocks, 1024u, (size_t)0, a, (u32)OVF_LIST);
   l.region_end();
+}
+
+// rec_na8 -> rec_ref_offsets on the device (three small launches). `na_tiles` needs
+// n_records / SCAN_TILE + 2 entries; a dummy u64 receives the (unused) grand total.
+template <class L>
+inline void enqueue_na8_offsets(L& l, const u8* na8, u64 n_records, u32* ref_off, u64* na_tiles, u64* total_slot) {
+  const u32 n_tiles = (u32)(n_records / SCAN_TILE + 1);  // covers index n_records (the closing offset)
+  l.launch(KID_NA_OFFSETS, k_na_tile_sums, n_tiles, 1024u, (size_t)0, na8, n_records, na_tiles);
+  l.launch(KID_NA_OFFSETS, k_scan_tiles, 1u, 1024u, (size_t)0, na_tiles, n_tiles, total_slot, (u64)0);
+  l.launch(KID_NA_OFFSETS, k_na_offsets, n_tiles, 1024u, (size_t)0, na8, n_records, (const u64*)na_tiles, ref_off);
 }
 
 // Enqueue the whole pipeline for one batch. All batch/out pointers are device pointers.

@@ -203,12 +203,14 @@ struct Pinned {  // growable pinned array (afq_host_alloc)
 struct HostBatch {
   Pinned<uint64_t> cell_rec_off;
   Pinned<uint32_t> umi, ref_off, refs;
+  Pinned<uint8_t> na8;           // alignment count per record (sent instead of ref_off when all <= 255)
+  bool na8_ok = true;
   std::vector<uint64_t> barcodes;
   std::vector<uint32_t> nrec;
   uint64_t first_cell = 0;
   void reset(uint64_t first) {
-    cell_rec_off.clear(); umi.clear(); ref_off.clear(); refs.clear(); barcodes.clear(); nrec.clear();
-    cell_rec_off.push(0); ref_off.push(0); first_cell = first;
+    cell_rec_off.clear(); umi.clear(); ref_off.clear(); refs.clear(); na8.clear(); barcodes.clear(); nrec.clear();
+    cell_rec_off.push(0); ref_off.push(0); first_cell = first; na8_ok = true;
   }
   uint64_t n_cells() const { return barcodes.size(); }
 };
@@ -386,7 +388,8 @@ int quantify_impl(const afqh_quant_opts& o) {
     ab.n_refs_total = b.refs.n;
     ab.cell_rec_offsets = b.cell_rec_off.p;
     ab.rec_umi32 = b.umi.p;
-    ab.rec_ref_offsets = b.ref_off.p;
+    if (b.na8_ok) { ab.rec_ref_offsets = nullptr; ab.rec_na8 = b.na8.p; }   // 1 byte instead of 4 per record over PCIe
+    else { ab.rec_ref_offsets = b.ref_off.p; ab.rec_na8 = nullptr; }
     ab.refs = b.refs.p;
     if (afq_submit(ctx, &ab, &tickets[i]) != AFQ_OK) throw Fail{std::string("afq_submit: ") + afq_last_error(ctx)};
     inflight[i] = true;
@@ -422,10 +425,12 @@ int quantify_impl(const afqh_quant_opts& o) {
             b.refs.push(ref & 0x7FFFFFFFu);  // bit 31 = orientation (src/convert.rs:442-445)
           }
           b.ref_off.push((uint32_t)b.refs.n);
+          b.na8.push((uint8_t)na);
+          if (na > 255) b.na8_ok = false;
         }
         p += (size_t)na * lay.aln_bytes;
       }
-      if (!take) { b.umi.n = rec_start; b.refs.n = ref_start; b.ref_off.n = rec_start + 1; continue; }
+      if (!take) { b.umi.n = rec_start; b.refs.n = ref_start; b.ref_off.n = rec_start + 1; b.na8.n = rec_start; continue; }
       REQUIRE(nrec > 0, "Discovered empty chunk; should not happen!");
       b.cell_rec_off.push(b.umi.n);
       b.barcodes.push_back(bc);

@@ -83,13 +83,28 @@ class CellBatch:
     @property
     def n_refs_total(self): return len(self.refs)
 
-    def to_c(self) -> AfqBatch:
+    def na8(self) -> np.ndarray:
+        """Per-record alignment counts as u8 (the compact alternative to rec_ref_offsets)."""
+        cached = getattr(self, "_na8", None)
+        if cached is None:
+            na = np.diff(self.rec_ref_offsets.astype(np.int64))
+            if len(na) and na.max() > 255:
+                raise ValueError("a record has more than 255 alignments: rec_na8 cannot be used")
+            cached = self._na8 = na.astype(np.uint8)
+        return cached
+
+    def to_c(self, use_na8: bool = False) -> AfqBatch:
         b = AfqBatch()
         b.first_cell_index = self.first_cell_index
         b.n_cells, b.n_records, b.n_refs_total = self.n_cells, self.n_records, self.n_refs_total
         b.cell_rec_offsets = _ptr(self.cell_rec_offsets)
         b.rec_umi32 = _ptr(self.rec_umi32)
-        b.rec_ref_offsets = _ptr(self.rec_ref_offsets)
+        if use_na8:
+            b.rec_ref_offsets = None
+            b.rec_na8 = _ptr(self.na8())
+        else:
+            b.rec_ref_offsets = _ptr(self.rec_ref_offsets)
+            b.rec_na8 = None
         b.refs = _ptr(self.refs)
         return b
 
@@ -185,8 +200,8 @@ class Quantifier:
             raise AfqError(rc, msg.decode() if msg else "")
 
     # ---- host API ---------------------------------------------------------------
-    def submit(self, batch: CellBatch) -> int:
-        cb = batch.to_c()
+    def submit(self, batch: CellBatch, use_na8: bool = False) -> int:
+        cb = batch.to_c(use_na8)
         t = C.c_uint64()
         self._check(self._lib.afq_submit(self._ctx, C.byref(cb), C.byref(t)))
         self._keep[t.value] = batch  # keep host arrays alive until the H2D copies are done
@@ -200,8 +215,8 @@ class Quantifier:
         self._lib.afq_result_release(self._ctx, C.byref(r))
         return out
 
-    def quantify_batch(self, batch: CellBatch) -> QuantResult:
-        return self.wait(self.submit(batch))
+    def quantify_batch(self, batch: CellBatch, use_na8: bool = False) -> QuantResult:
+        return self.wait(self.submit(batch, use_na8))
 
     # ---- device API (torch tensors on this ctx's GPU) ----------------------------
     def quant_device(self, dev_batch: dict, dev_out: dict, stream_ptr: int = 0):

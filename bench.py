@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument("--e2e-batches", type=int, default=8, help="host batches per e2e step (pipelined)")
     ap.add_argument("--cpu-sample-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-offsets", action="store_true",
+                    help="e2e: ship 4-byte rec_ref_offsets instead of the 1-byte rec_na8 alignment counts")
     return ap.parse_args()
 
 
@@ -251,12 +253,18 @@ def main():
         ms = float(t.item())
 
     # ---- e2e through the host C-ABI: pinned host batches, H2D + kernels + D2H per step ---------
-    h2d = sum(p.cell_rec_offsets.nbytes + p.rec_umi32.nbytes + p.rec_ref_offsets.nbytes + p.refs.nbytes for p in parts)
+    use_na8 = not args.e2e_offsets
+    if use_na8:  # the host keeps what a RAD record header stores (the alignment count, 1 byte) in pinned memory
+        for p in parts:
+            na = pool.empty(p.n_records, np.uint8)
+            np.subtract(p.rec_ref_offsets[1:], p.rec_ref_offsets[:-1], out=na, casting="unsafe")
+            p._na8 = na
+    h2d = sum(p.cell_rec_offsets.nbytes + p.rec_umi32.nbytes + (p._na8.nbytes if use_na8 else p.rec_ref_offsets.nbytes) + p.refs.nbytes for p in parts)
 
     def step_e2e():
         d2h, tickets = 0, []
         for p in parts:
-            tickets.append(q.submit(p))
+            tickets.append(q.submit(p, use_na8))
             if len(tickets) == 3:
                 n_c, n_z = q.wait(tickets.pop(0), copy=False)
                 d2h += 8 * (n_c + 1) + 17 * n_c + 8 * n_z
@@ -325,7 +333,8 @@ def main():
                        "seed": spec.seed},
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": total_cells / e2e_s, "unit": "cells/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_s * 1e3, "host_batches_per_step": nb},
+                    "ms_per_step": e2e_s * 1e3, "host_batches_per_step": nb,
+                    "input_encoding": "rec_umi32 + rec_na8 + refs (u32)" if use_na8 else "rec_umi32 + rec_ref_offsets + refs (u32)"},
             "gpu_launches": int(launches) + 0, "clocks": clocks,
         }), flush=True)
     q.close()

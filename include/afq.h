@@ -87,6 +87,11 @@ typedef struct afq_batch {
   const uint32_t* rec_umi32;        /* [n_records] 2-bit packed UMI (umi_len <= 16)      */
   const uint32_t* rec_ref_offsets;  /* [n_records+1] CSR into refs                       */
   const uint32_t* refs;             /* [n_refs_total]                                    */
+  const uint8_t* rec_na8;           /* optional, [n_records]: alignment count per record
+                                       (what the RAD record header stores, as one byte — every
+                                       count must be <= 255) INSTEAD of rec_ref_offsets (pass
+                                       NULL there): 1 byte instead of 4 per record over PCIe;
+                                       the device derives the CSR offsets with a scan          */
 } afq_batch;
 
 /* Per-cell results in input cell order. CSR with ascending columns inside a row — the

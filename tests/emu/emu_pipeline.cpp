@@ -85,7 +85,16 @@ int afq_emu_quant(const afq_config* cfg, const uint32_t* tid_to_gid, uint64_t n_
   std::string err;
   int force_bin = -1;
   if (const char* s = getenv("AFQ_FORCE_BIN")) force_bin = atoi(s);
-  int rc = enqueue_batch(l, *cfg, force_bin, pb, *b, o, err);
+  afq_batch bb = *b;
+  std::vector<u32> na_off;
+  std::vector<u64> na_tiles;
+  if (!bb.rec_ref_offsets && bb.rec_na8) {   // compact alignment counts -> offsets (device scan kernels)
+    na_off.assign(bb.n_records + 2, 0xCDCDCDCDu);
+    na_tiles.assign(bb.n_records / SCAN_TILE + 4, 0);
+    enqueue_na8_offsets(l, bb.rec_na8, bb.n_records, na_off.data(), na_tiles.data() + 1, na_tiles.data());
+    bb.rec_ref_offsets = na_off.data();
+  }
+  int rc = enqueue_batch(l, *cfg, force_bin, pb, bb, o, err);
   if (dev_error) *dev_error = ctl[0].error;
   if (rc == AFQ_OK && ctl[0].error) {
     std::string buf;

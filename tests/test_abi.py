@@ -30,7 +30,7 @@ def test_header_symbols_all_exported_and_bound():
 
 def test_struct_sizes_match_header_layout():
     assert C.sizeof(_abi.AfqConfig) == 56
-    assert C.sizeof(_abi.AfqBatch) == 64
+    assert C.sizeof(_abi.AfqBatch) == 72
     assert C.sizeof(_abi.AfqResult) == 80
     assert C.sizeof(_abi.AfqDeviceOut) == 80
 

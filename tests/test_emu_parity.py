@@ -112,3 +112,18 @@ def test_emu_overflow_requeue():
     spec = synth.SynthSpec(reads_mean=900.0, reads_per_umi=1.0, p_multi2=0.45, p_multi3=0.45, lognorm_sigma=0.3)
     b = synth.generate(spec, 0, 6)
     check(opts_for(spec, "cr-like"), synth.tid_to_gid(spec), b, "overflow")
+
+
+def test_emu_na8_compact_offsets():
+    # afq_batch.rec_na8: per-record alignment counts instead of CSR offsets; several scan tiles
+    spec = synth.SynthSpec(reads_mean=1500.0)
+    b = synth.generate(spec, 0, 9)
+    assert b.n_records > 2 * 4096
+    t2g = synth.tid_to_gid(spec)
+    for res in ("cr-like", "parsimony"):
+        o = opts_for(spec, res)
+        got = emu_lib.emu_quant(o, t2g, b, use_na8=True)
+        want = emu_lib.emu_quant(o, t2g, b)
+        assert np.array_equal(got.row_ptr, want.row_ptr) and np.array_equal(got.col, want.col) and np.array_equal(got.val, want.val)
+    with pytest.raises(ValueError):
+        CellBatch.from_cells([[(1, list(range(300)))]]).na8()

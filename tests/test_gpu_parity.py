@@ -159,3 +159,16 @@ def test_pipelined_submits_and_full_size_properties():
     for res in ("cr-like", "parsimony"):
         oo = opts_for(spec, res)
         assert_same(gpu_quant(oo, t2g, shuf), gpu_quant(oo, t2g, b.slice_cells(0, 200)), ctx="shuffle/" + res)
+
+
+def test_na8_compact_offsets_match():
+    # afq_batch.rec_na8 (1 B/record over PCIe instead of 4 B offsets) must give identical results
+    spec = synth.config_spec("C2")
+    b = synth.generate(spec, 2000, 400)
+    t2g = synth.tid_to_gid(spec)
+    for res in ("cr-like", "parsimony-em"):
+        o = opts_for(spec, res)
+        with Quantifier(o, t2g) as q:
+            a1 = q.quantify_batch(b)
+            a2 = q.quantify_batch(b, use_na8=True)
+        assert np.array_equal(a1.row_ptr, a2.row_ptr) and np.array_equal(a1.col, a2.col) and np.array_equal(a1.val, a2.val)
