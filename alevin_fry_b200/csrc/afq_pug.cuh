@@ -145,6 +145,7 @@ struct GeShared {
   u32 lab_bump;     // bump pointer into the upper half of mlab
   u32 alt;
   u32 adj_base_lo, adj_base_hi;
+  u32 need_lo;
   float fsum, fmax;
 };
 
@@ -328,9 +329,10 @@ __device__ inline u32 block_exscan_array(const u32* in, u32* out, u32 n, u32* s_
 
 // per-cell view used by the phases below
 struct GeCell {
+  __device__ GeCell(const GePtrs& ptrs) : p(ptrs) {}
   const KArgs* a;
   const GeArgs* g;
-  GePtrs p;
+  const GePtrs& p;    // lives in shared memory: ~50 pointers that must not be re-derived or spilled per use
   u64 r0;
   u32 f0;
   bool gene_labels;   // labels are gene ids (PUG_GENE) — else transcript ids
@@ -709,8 +711,9 @@ __device__ inline void crlike_molecules_from_ltab(const GeCell& c, GeShared* sh,
 // =============================================================================================
 // The kernel body for one cell. Produces this cell's sparse counts in the staging rows.
 // =============================================================================================
-__device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, u8* arena, GeShared* sh, u8* scratch) {
-  GeCell c;
+__device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, u8* arena, GeShared* sh, u8* scratch,
+                                     GePtrs* s_ptrs) {
+  GeCell c(*s_ptrs);
   c.a = &a; c.g = &g; c.scratch = scratch;
   c.r0 = a.cell_rec_off[cell];
   const u64 r1 = a.cell_rec_off[cell + 1];
@@ -718,13 +721,15 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
   c.f0 = a.ref_off[c.r0];
   const u32 P = a.ref_off[r1] - c.f0;
   c.gene_labels = g.ge_mode == GE_MODE_PUG_GENE;
-  const u64 need = ge_carve(arena, n, P, g.large_graph_thresh, &c.p);
   if (threadIdx.x == 0) {
+    sh->need_lo = 0;
+    const u64 need = ge_carve(arena, n, P, g.large_graph_thresh, s_ptrs);
+    sh->need_lo = need > g.arena_bytes ? 1u : 0u;
     sh->n_mol = 0; sh->lab_bump = 0; sh->alt = 0; sh->flag = 0;
     sh->cnt0 = sh->cnt1 = sh->cnt2 = sh->cnt3 = 0;
   }
   __syncthreads();
-  if (need > g.arena_bytes) {
+  if (sh->need_lo) {
     if (threadIdx.x == 0) {
       atomicOr(&a.ctl->error, (u32)DEV_ERR_ARENA);
       a.sum_umi[cell] = 0; a.max_umi[cell] = 0; a.num_expr[cell] = 0; a.num_over_mean[cell] = 0; a.flags[cell] = 4;
@@ -1326,6 +1331,7 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
 __global__ void __launch_bounds__(GE_THREADS, 4) k_gene_eqc(KArgs a, GeArgs g) {
   __shared__ GeShared sh;
   __shared__ __align__(16) u8 s_scratch[GE_SCRATCH_BYTES];
+  __shared__ GePtrs s_ptrs;
   u8* arena = g.arena + (u64)blockIdx.x * g.arena_bytes;
   const u32 count = a.ctl->bin_count[g.list_id];
   const u32* list = a.bin_list + (u64)g.list_id * a.n_cells;
@@ -1335,7 +1341,7 @@ __global__ void __launch_bounds__(GE_THREADS, 4) k_gene_eqc(KArgs a, GeArgs g) {
     const u32 job = sh.job;
     __syncthreads();
     if (job >= count) break;
-    gene_eqc_cell(a, g, list[job], arena, &sh, s_scratch);
+    gene_eqc_cell(a, g, list[job], arena, &sh, s_scratch, &s_ptrs);
   }
 }
 
