@@ -75,6 +75,7 @@ struct GePtrs {
   u32* rec_slot;
   u32* glab; u32* glen;
   u32* cls_rep; u32* cls_aux; u32* cls_vfirst;
+  u32* cls_loff; u32* cls_llen;   // per class rank: label offset (into refs / glab) and length
   u32* vnext; u32* adj_off; u32* parent;
   u64* ckey;
   u32* cstart; u32* cbig;
@@ -111,6 +112,7 @@ __host__ __device__ inline u64 ge_carve(u8* base, u32 n, u32 P, u32 thresh, GePt
   p.rec_slot = (u32*)take(4ull * n);
   p.glab = (u32*)take(4ull * P); p.glen = (u32*)take(4ull * n);
   p.cls_rep = (u32*)take(4ull * p.N1); p.cls_aux = (u32*)take(4ull * p.N1); p.cls_vfirst = (u32*)take(4ull * (n + 2));
+  p.cls_loff = (u32*)take(4ull * p.N1); p.cls_llen = (u32*)take(4ull * p.N1);
   p.vnext = (u32*)take(4ull * n); p.adj_off = (u32*)take(4ull * (n + 2)); p.parent = (u32*)take(4ull * n);
   p.ckey = (u64*)take(8ull * p.N1);
   p.cstart = (u32*)take(4ull * (n + 1)); p.cbig = (u32*)take(4ull * (n + 1));
@@ -258,9 +260,11 @@ __device__ inline void block_bitonic_u64(u64* a, u32 n) {
 // ---- sorts staged through a shared-memory scratch (the arena itself is global memory, where a
 // bitonic stage costs an L2 round trip; in shared memory it costs ~50 cycles) ------------------
 constexpr u32 GE_SCRATCH_BYTES = 32768;
+constexpr u32 GE_CLS_CACHE = 512;          // classes whose label offset/length are mirrored in shared memory
+constexpr u32 GE_VCACHE = (GE_SCRATCH_BYTES / 2) / 12;   // vertices mirrored in the upper half of the scratch
 
-__device__ inline void sort_pairs_staged(u64* keys, u32* vals, u32 n, u8* scratch) {
-  if ((u64)n * 12 <= GE_SCRATCH_BYTES && n > 1) {
+__device__ inline void sort_pairs_staged(u64* keys, u32* vals, u32 n, u8* scratch, u32 budget = GE_SCRATCH_BYTES) {
+  if ((u64)n * 12 <= budget && n > 1) {
     u64* sk = reinterpret_cast<u64*>(scratch);
     u32* sv = reinterpret_cast<u32*>(sk + n);
     for (u32 i = threadIdx.x; i < n; i += blockDim.x) { sk[i] = keys[i]; sv[i] = vals[i]; }
@@ -272,8 +276,8 @@ __device__ inline void sort_pairs_staged(u64* keys, u32* vals, u32 n, u8* scratc
     block_bitonic_pairs(keys, vals, n);
   }
 }
-__device__ inline void sort_u64_staged(u64* a, u32 n, u8* scratch) {
-  if ((u64)n * 8 <= GE_SCRATCH_BYTES && n > 1) {
+__device__ inline void sort_u64_staged(u64* a, u32 n, u8* scratch, u32 budget = GE_SCRATCH_BYTES) {
+  if ((u64)n * 8 <= budget && n > 1) {
     u64* sk = reinterpret_cast<u64*>(scratch);
     for (u32 i = threadIdx.x; i < n; i += blockDim.x) sk[i] = a[i];
     __syncthreads();
@@ -284,8 +288,8 @@ __device__ inline void sort_u64_staged(u64* a, u32 n, u8* scratch) {
     block_bitonic_u64(a, n);
   }
 }
-__device__ inline void sort_u32_staged(u32* a, u32 n, u8* scratch) {
-  if ((u64)n * 4 <= GE_SCRATCH_BYTES && n > 1) {
+__device__ inline void sort_u32_staged(u32* a, u32 n, u8* scratch, u32 budget = GE_SCRATCH_BYTES) {
+  if ((u64)n * 4 <= budget && n > 1) {
     u32* sk = reinterpret_cast<u32*>(scratch);
     for (u32 i = threadIdx.x; i < n; i += blockDim.x) sk[i] = a[i];
     __syncthreads();
@@ -297,8 +301,8 @@ __device__ inline void sort_u32_staged(u32* a, u32 n, u8* scratch) {
   }
 }
 template <class Less>
-__device__ inline void sort_ids_staged(u32* ids, u32* pay, u32 n, u8* scratch, Less less) {
-  if ((u64)n * 8 <= GE_SCRATCH_BYTES && n > 1) {
+__device__ inline void sort_ids_staged(u32* ids, u32* pay, u32 n, u8* scratch, Less less, u32 budget = GE_SCRATCH_BYTES) {
+  if ((u64)n * 8 <= budget && n > 1) {
     u32* si = reinterpret_cast<u32*>(scratch);
     u32* sp = si + n;
     for (u32 i = threadIdx.x; i < n; i += blockDim.x) { si[i] = ids[i]; sp[i] = pay[i]; }
@@ -327,16 +331,38 @@ __device__ inline u32 block_exscan_array(const u32* in, u32* out, u32 n, u32* s_
   return base;
 }
 
+// Out-of-place compaction with one contiguous index range per thread: count, one block scan,
+// write. Two barriers instead of three per blockDim-sized chunk.
+template <class Keep, class Write>
+__device__ inline u32 block_compact_ranges(u32 N, u32* s_scan, Keep keep, Write write) {
+  const u32 T = blockDim.x, K = (N + T - 1) / T;
+  u32 lo = threadIdx.x * K; if (lo > N) lo = N;
+  u32 hi = lo + K; if (hi > N) hi = N;
+  u32 cnt = 0;
+  for (u32 i = lo; i < hi; ++i) cnt += keep(i) ? 1u : 0u;
+  u32 tot;
+  u32 pos = block_exscan(cnt, s_scan, &tot);
+  for (u32 i = lo; i < hi; ++i) if (keep(i)) write(i, pos++);
+  __syncthreads();
+  return tot;
+}
+
 // per-cell view used by the phases below
 struct GeCell {
-  __device__ GeCell(const GePtrs& ptrs) : p(ptrs) {}
+  __device__ GeCell(GePtrs& ptrs) : pm(&ptrs), p(ptrs) {}
   const KArgs* a;
   const GeArgs* g;
+  GePtrs* pm;         // the same object, writable (thread 0 swaps table roles)
   const GePtrs& p;    // lives in shared memory: ~50 pointers that must not be re-derived or spilled per use
   u64 r0;
   u32 f0;
   bool gene_labels;   // labels are gene ids (PUG_GENE) — else transcript ids
   u8* scratch;        // GE_SCRATCH_BYTES of shared memory for staged sorts
+  u32 scratch_budget; // bytes of it the sorts may use right now (the upper half may hold the vertex cache)
+  const u64* vk_s;    // shared-memory copies of the dense vertex arrays while they fit (else nullptr)
+  const u32* vc_s;
+  const u32* cl_off_s; // shared-memory copies of the per-class label offset / length (else nullptr)
+  const u32* cl_len_s;
   // label of record-local index i
   __device__ __forceinline__ const u32* rec_lab(u32 i) const {
     return gene_labels ? p.glab + (a->ref_off[r0 + i] - f0) : a->refs + a->ref_off[r0 + i];
@@ -345,11 +371,11 @@ struct GeCell {
     return gene_labels ? p.glen[i] : a->ref_off[r0 + i + 1] - a->ref_off[r0 + i];
   }
   // label of class rank c (through its representative record)
-  __device__ __forceinline__ const u32* cls_lab(u32 c) const { return rec_lab(p.cls_rep[c]); }
-  __device__ __forceinline__ u32 cls_lab_len(u32 c) const { return rec_lab_len(p.cls_rep[c]); }
-  __device__ __forceinline__ u32 v_cls(u32 v) const { return (u32)(p.vtab_k[v] >> 32); }
-  __device__ __forceinline__ u32 v_umi(u32 v) const { return (u32)p.vtab_k[v]; }
-  __device__ __forceinline__ u32 v_cnt(u32 v) const { return p.vtab_c[v]; }
+  __device__ __forceinline__ const u32* cls_lab(u32 c) const { return (gene_labels ? p.glab : a->refs) + (cl_off_s ? cl_off_s[c] : p.cls_loff[c]); }
+  __device__ __forceinline__ u32 cls_lab_len(u32 c) const { return cl_len_s ? cl_len_s[c] : p.cls_llen[c]; }
+  __device__ __forceinline__ u32 v_cls(u32 v) const { return (u32)((vk_s ? vk_s[v] : p.vtab_k[v]) >> 32); }
+  __device__ __forceinline__ u32 v_umi(u32 v) const { return (u32)(vk_s ? vk_s[v] : p.vtab_k[v]); }
+  __device__ __forceinline__ u32 v_cnt(u32 v) const { return vc_s ? vc_s[v] : p.vtab_c[v]; }
 };
 
 // Does the directed edge x -> y exist, given Hamming distance hd in {0,1} (has_edge,
@@ -691,7 +717,7 @@ __device__ inline void crlike_molecules_from_ltab(const GeCell& c, GeShared* sh,
   const u32 D = next_pow2(d);
   for (u32 i = d + threadIdx.x; i < D; i += blockDim.x) c.p.ltab_k[i] = EMPTY_KEY;
   __syncthreads();
-  sort_pairs_staged(c.p.ltab_k, c.p.ltab_c, D, c.scratch);
+  sort_pairs_staged(c.p.ltab_k, c.p.ltab_c, D, c.scratch, c.scratch_budget);
   for (u32 i = threadIdx.x; i < d; i += blockDim.x) {
     const u32 u = (u32)(c.p.ltab_k[i] >> 32);
     if (i > 0 && (u32)(c.p.ltab_k[i - 1] >> 32) == u) continue;
@@ -712,9 +738,10 @@ __device__ inline void crlike_molecules_from_ltab(const GeCell& c, GeShared* sh,
 // The kernel body for one cell. Produces this cell's sparse counts in the staging rows.
 // =============================================================================================
 __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, u8* arena, GeShared* sh, u8* scratch,
-                                     GePtrs* s_ptrs) {
+                                     GePtrs* s_ptrs, u32* s_cls) {
   GeCell c(*s_ptrs);
-  c.a = &a; c.g = &g; c.scratch = scratch;
+  c.a = &a; c.g = &g; c.scratch = scratch; c.scratch_budget = GE_SCRATCH_BYTES;
+  c.vk_s = nullptr; c.vc_s = nullptr; c.cl_off_s = nullptr; c.cl_len_s = nullptr;
   c.r0 = a.cell_rec_off[cell];
   const u64 r1 = a.cell_rec_off[cell + 1];
   const u32 n = (u32)(r1 - c.r0);
@@ -792,28 +819,25 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
       if (seed >= 6) { if (tid == 0) atomicOr(&a.ctl->error, (u32)DEV_ERR_HASH); break; }
     }
     // compact classes -> (rep, slot), sort by label, assign ranks
-    u32 C = 0;
-    {
-      u32 base = 0;
-      for (u32 c0 = 0; c0 < N2; c0 += T) {
-        const u32 i = c0 + tid;
-        const u32 keep = (i < N2 && p.ctab_h[i] != EMPTY_KEY) ? 1u : 0u;
-        u32 tot;
-        const u32 pos = block_exscan(keep, sh->scan, &tot);
-        if (keep) { p.cls_rep[base + pos] = p.ctab_r[i]; p.cls_aux[base + pos] = i; }
-        base += tot;
-      }
-      C = base;
-      __syncthreads();
-    }
+    const u32 C = block_compact_ranges(N2, sh->scan, [&](u32 i) { return p.ctab_h[i] != EMPTY_KEY; },
+                                       [&](u32 i, u32 pos) { p.cls_rep[pos] = p.ctab_r[i]; p.cls_aux[pos] = i; });
     const u32 Cp = next_pow2(C);
     for (u32 i = C + tid; i < Cp; i += T) { p.cls_rep[i] = NONE32; p.cls_aux[i] = NONE32; }
     __syncthreads();
     sort_ids_staged(p.cls_rep, p.cls_aux, Cp, c.scratch, [&](u32 x, u32 y) {
       return label_less(c.rec_lab(x), c.rec_lab_len(x), c.rec_lab(y), c.rec_lab_len(y));
     });
-    GE_FOR(j, C) p.ctab_r[p.cls_aux[j]] = j;  // slot -> rank
+    GE_FOR(j, C) {
+      p.ctab_r[p.cls_aux[j]] = j;  // slot -> rank
+      const u32 rep = p.cls_rep[j];
+      const u32 lo_ = c.gene_labels ? a.ref_off[c.r0 + rep] - c.f0 : a.ref_off[c.r0 + rep];
+      const u32 ll_ = c.rec_lab_len(rep);
+      p.cls_loff[j] = lo_;
+      p.cls_llen[j] = ll_;
+      if (C <= GE_CLS_CACHE) { s_cls[j] = lo_; s_cls[GE_CLS_CACHE + j] = ll_; }
+    }
     __syncthreads();
+    if (C <= GE_CLS_CACHE) { c.cl_off_s = s_cls; c.cl_len_s = s_cls + GE_CLS_CACHE; }
 
     // ---------------- phase 2: vertices = distinct (class, UMI) with read counts ---------------
     GE_FOR(i, N2) { p.vtab_k[i] = EMPTY_KEY; p.vtab_c[i] = 0; }
@@ -825,7 +849,15 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
       atomicAdd(&p.vtab_c[s], 1u);
     }
     __syncthreads();
-    const u32 V = block_compact_pairs(p.vtab_k, p.vtab_c, N2, sh->scan);
+    // the class table is dead now (ranks are in the vertex keys): compact the vertex table into its
+    // memory and swap the two tables' roles
+    const u32 V = block_compact_ranges(N2, sh->scan, [&](u32 i) { return p.vtab_k[i] != EMPTY_KEY; },
+                                       [&](u32 i, u32 pos) { p.ctab_h[pos] = p.vtab_k[i]; p.ctab_r[pos] = p.vtab_c[i]; });
+    if (tid == 0) {
+      u64* tk = c.pm->vtab_k; c.pm->vtab_k = c.pm->ctab_h; c.pm->ctab_h = tk;
+      u32* tc = c.pm->vtab_c; c.pm->vtab_c = c.pm->ctab_r; c.pm->ctab_r = tc;
+    }
+    __syncthreads();
     const u32 Vp = next_pow2(V);
     for (u32 i = V + tid; i < Vp; i += T) p.vtab_k[i] = EMPTY_KEY;
     __syncthreads();
@@ -833,13 +865,22 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
 
     // ---------------- phase 3: UMI -> vertex chains (table time-shares the class table) ---------
     u32* bitmap = reinterpret_cast<u32*>(c.scratch);
-    GE_FOR(i, N2) { p.ctab_h[i] = EMPTY_KEY; p.ctab_r[i] = NONE32; }
+    if (V <= GE_VCACHE) {   // mirror the dense vertex arrays in the upper half of the scratch (phases 3-6)
+      u64* vk = reinterpret_cast<u64*>(c.scratch + GE_SCRATCH_BYTES / 2);
+      u32* vc = reinterpret_cast<u32*>(vk + GE_VCACHE);
+      GE_FOR(v, V) { vk[v] = p.vtab_k[v]; vc[v] = p.vtab_c[v]; }
+      c.vk_s = vk; c.vc_s = vc;
+      c.scratch_budget = GE_SCRATCH_BYTES / 2;
+    }
+    const u32 NU = pow2_ge(2 * V + 2, 64) < N2 ? pow2_ge(2 * V + 2, 64) : N2;   // UMI table sized by V, not by records
+    const u32 lu = ilog2(NU), mu = NU - 1;
+    GE_FOR(i, NU) { p.ctab_h[i] = EMPTY_KEY; p.ctab_r[i] = NONE32; }
     for (u32 i = tid; i < (1u << (GE_BITMAP_LOG2 - 5)); i += T) bitmap[i] = 0;
     __syncthreads();
     GE_FOR(v, V) {
       bool fresh;
       const u32 um = c.v_umi(v);
-      const u32 s = tab_find_or_claim(p.ctab_h, m2, l2, (u64)um, &fresh);
+      const u32 s = tab_find_or_claim(p.ctab_h, mu, lu, (u64)um, &fresh);
       p.vnext[v] = atomicExch(&p.ctab_r[s], v);
       p.parent[v] = v;
       p.adj_off[v] = 0;
@@ -859,7 +900,7 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
         __syncwarp();
         const u32 k = k0 + lane;
         if (k < ncand)
-          visit_candidate(c, v, k, m2, l2, bitmap, [&](u32 w, u32 hd) {
+          visit_candidate(c, v, k, mu, lu, bitmap, [&](u32 w, u32 hd) {
             if (w > v) uf_union(p.parent, v, w);
             if (out_edge(hd, cx, c.v_cnt(w))) atomicAdd(&p.adj_off[v], 1u);
           });
@@ -891,7 +932,7 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
           __syncwarp();
           const u32 k = k0 + lane;
           if (k < ncand)
-            visit_candidate(c, v, k, m2, l2, bitmap, [&](u32 w, u32 hd) {
+            visit_candidate(c, v, k, mu, lu, bitmap, [&](u32 w, u32 hd) {
               if (out_edge(hd, cx, c.v_cnt(w))) g.adj_pool[adj_base + p.adj_off[v] + atomicAdd(&p.vlab_off[v], 1u)] = w;
             });
         }
@@ -905,7 +946,7 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
     GE_FOR(v, V) p.vlab_off[v] = c.cls_lab_len(c.v_cls(v));
     __syncthreads();
     block_exscan_array(p.vlab_off, p.vlab_off, V, sh->scan);
-    sort_u64_staged(p.ckey, Vp, c.scratch);
+    sort_u64_staged(p.ckey, Vp, c.scratch, c.scratch_budget);
     // component starts
     u32 K = 0;
     {
@@ -942,7 +983,7 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
       const u32 Bp = next_pow2(nbig);
       for (u32 i = nbig + tid; i < Bp; i += T) p.cbig[i] = NONE32;
       __syncthreads();
-      sort_u32_staged(p.cbig, Bp, c.scratch);
+      sort_u32_staged(p.cbig, Bp, c.scratch, c.scratch_budget);
     }
     for (u32 b = 0; b < nbig; ++b) {
       const u32 k = p.cbig[b];
@@ -969,6 +1010,7 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
   }
   __syncthreads();
 
+  c.vk_s = nullptr; c.vc_s = nullptr; c.scratch_budget = GE_SCRATCH_BYTES;   // vertex cache is dead from here on
   // =================== stage B: molecules -> gene eq-classes in canonical order ===============
   const u32 M = sh->n_mol;
   const u32 Mp = next_pow2(M);
@@ -1332,6 +1374,7 @@ __global__ void __launch_bounds__(GE_THREADS, 4) k_gene_eqc(KArgs a, GeArgs g) {
   __shared__ GeShared sh;
   __shared__ __align__(16) u8 s_scratch[GE_SCRATCH_BYTES];
   __shared__ GePtrs s_ptrs;
+  __shared__ u32 s_cls[2 * GE_CLS_CACHE];
   u8* arena = g.arena + (u64)blockIdx.x * g.arena_bytes;
   const u32 count = a.ctl->bin_count[g.list_id];
   const u32* list = a.bin_list + (u64)g.list_id * a.n_cells;
@@ -1341,7 +1384,7 @@ __global__ void __launch_bounds__(GE_THREADS, 4) k_gene_eqc(KArgs a, GeArgs g) {
     const u32 job = sh.job;
     __syncthreads();
     if (job >= count) break;
-    gene_eqc_cell(a, g, list[job], arena, &sh, s_scratch, &s_ptrs);
+    gene_eqc_cell(a, g, list[job], arena, &sh, s_scratch, &s_ptrs, s_cls);
   }
 }
 
