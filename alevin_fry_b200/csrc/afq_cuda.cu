@@ -139,6 +139,8 @@ struct afq_ctx {
   int force_bin = -1;
   int grid_smem[NUM_SMEM_BINS] = {0};
   int ge_grid = 0;
+  int grid_smem5[NUM_SMEM_BINS] = {0};
+  int resolve_version = 3;     // AFQ_RESOLVE=5 selects the experimental partition-based resolve
   u32 need_shift = 0;          // arena-size bias, raised when a batch overflowed many arenas
   bool no_lanes = false;       // AFQ_NO_LANES=1: launch the arena kernels back to back on the caller's stream
   cudaStream_t lanes[NUM_BINS] = {nullptr};
@@ -188,6 +190,17 @@ int setup_bin(afq_ctx* c) {
   return AFQ_OK;
 }
 
+template <int BIN>
+int setup_bin5(afq_ctx* c) {
+  const size_t smem = bin5_smem_bytes(BIN);
+  CUDA_TRY(c, cudaFuncSetAttribute(k_resolve5_smem<BIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_resolve5_smem<BIN>, (int)bin5_threads(BIN), smem));
+  if (occ < 1) occ = 1;
+  c->grid_smem5[BIN] = occ * c->num_sms;
+  return AFQ_OK;
+}
+
 // Launcher for afq_pipeline.cuh: real launches on a CUDA stream, timed with event pairs when
 // profiling is on.
 struct CudaLauncher {
@@ -211,6 +224,8 @@ struct CudaLauncher {
     return 0;
   }
   int grid_for_bin(int b) { return c->grid_smem[b]; }
+  int grid_for_bin5(int b) { return c->grid_smem5[b]; }
+  int resolve_version() { return c->resolve_version; }
   int ge_blocks(int which) { return which == 0 ? 16 : c->ge_grid; }
   u8* ge_arena(int which, u64 bytes, u32 blocks) {
     if (w->ge_arena[which].ensure((size_t)bytes * blocks + 64) != cudaSuccess) return nullptr;
@@ -326,6 +341,7 @@ int afq_create(const afq_config* cfg, const uint32_t* tid_to_gid, uint64_t n_ref
   if (const char* s = getenv("AFQ_FORCE_BIN")) c->force_bin = atoi(s);
   if (const char* s = getenv("AFQ_NEED_SHIFT")) c->need_shift = (u32)atoi(s);
   if (const char* s = getenv("AFQ_NO_LANES")) c->no_lanes = atoi(s) != 0;
+  if (const char* s = getenv("AFQ_RESOLVE")) c->resolve_version = atoi(s) == 5 ? 5 : 3;
   if (c->large_cap_log2 < 10) c->large_cap_log2 = 10;
   if (c->large_cap_log2 > 30) c->large_cap_log2 = 30;
   if (c->large_blocks < 1) c->large_blocks = (u32)c->num_sms;
@@ -354,6 +370,9 @@ int afq_create(const afq_config* cfg, const uint32_t* tid_to_gid, uint64_t n_ref
   int rc;
   if ((rc = setup_bin<0>(c)) || (rc = setup_bin<1>(c)) || (rc = setup_bin<2>(c)) ||
       (rc = setup_bin<3>(c)) || (rc = setup_bin<4>(c)) || (rc = setup_bin<5>(c)))
+    return fail(rc);
+  if ((rc = setup_bin5<0>(c)) || (rc = setup_bin5<1>(c)) || (rc = setup_bin5<2>(c)) ||
+      (rc = setup_bin5<3>(c)) || (rc = setup_bin5<4>(c)) || (rc = setup_bin5<5>(c)))
     return fail(rc);
   {
     int occ = 0;

@@ -85,13 +85,15 @@ struct CellShared {
 // ------------------------------------------------------------------------------------
 // classify cells into arena-size bins by record count
 // ------------------------------------------------------------------------------------
-__global__ void k_bin_cells(KArgs a, int force_bin, u32 need_shift) {
+__global__ void k_bin_cells(KArgs a, int force_bin, u32 need_shift, u32 by_refs) {
   const u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= a.n_cells) return;
   const u64 r0 = a.cell_rec_off[c], r1 = a.cell_rec_off[c + 1];
   const u64 n = r1 - r0;
   const u32 p = a.ref_off[r1] - a.ref_off[r0];
-  const u64 need = (n < (u64)p ? n : (u64)p) << need_shift;  // distinct pairs <= refs; typically << records
+  // v3: distinct pairs <= min(records, refs), typically << records (optimistic, overflow list as backstop);
+  // v5 (by_refs): pairs <= refs is a hard bound, the arena can never overflow
+  const u64 need = by_refs ? (u64)p : ((n < (u64)p ? n : (u64)p) << need_shift);
   int b = NUM_SMEM_BINS;
 #pragma unroll
   for (int i = NUM_SMEM_BINS - 1; i >= 0; --i)

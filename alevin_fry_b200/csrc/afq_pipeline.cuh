@@ -15,12 +15,15 @@
 //   void fork(int lanes); void lane(int i); void join();      // independent launches may overlap:
 //       between fork and join, launches go to lane i's stream (CUDA) / run in order (emulator)
 //   u32  need_shift();                                        // arena-size bias learnt from overflows
+//   int  resolve_version();                                   // 3 (default) or 5 (AFQ_RESOLVE=5, experimental)
+//   int  grid_for_bin5(int bin);
 #pragma once
 #include <string>
 
 #include "../../include/afq.h"
 #include "afq_kernels.cuh"
 #include "afq_pug.cuh"
+#include "afq_resolve5.cuh"
 
 namespace afq {
 
@@ -58,6 +61,11 @@ inline void launch_smem_bin(L& l, const KArgs& a) {
   l.launch(KID_SMEM0 + BIN, k_resolve_smem<BIN>, (unsigned)l.grid_for_bin(BIN), bin_threads(BIN), smem, a);
 }
 
+template <int BIN, class L>
+inline void launch_smem_bin5(L& l, const KArgs& a) {
+  l.launch(KID_SMEM0 + BIN, k_resolve5_smem<BIN>, (unsigned)l.grid_for_bin5(BIN), bin5_threads(BIN), bin5_smem_bytes(BIN), a);
+}
+
 // The arena kernels are independent of each other (overflowing cells go to a separate list that is
 // drained afterwards), so they are forked onto per-arena lanes and overlap on the device: small
 // CTAs fill the SMs while the few big-arena CTAs are still running.
@@ -65,6 +73,18 @@ template <class L>
 inline void launch_crlike_bins(L& l, const KArgs& a, const PipeBufs& pb) {
   l.region_begin();
   l.fork(NUM_BINS);
+  if (l.resolve_version() == 5) {
+    l.lane(5); launch_smem_bin5<5>(l, a);
+    l.lane(6); l.launch(KID_LARGE, k_resolve5_large, pb.large_blocks, 1024u, (size_t)0, a, (u32)NUM_SMEM_BINS);
+    l.lane(4); launch_smem_bin5<4>(l, a);
+    l.lane(3); launch_smem_bin5<3>(l, a);
+    l.lane(2); launch_smem_bin5<2>(l, a);
+    l.lane(1); launch_smem_bin5<1>(l, a);
+    l.lane(0); launch_smem_bin5<0>(l, a);
+    l.join();
+    l.region_end();
+    return;
+  }
   l.lane(5); launch_smem_bin<5>(l, a);
   l.lane(6); l.launch(KID_LARGE, k_resolve_large, pb.large_blocks, 1024u, (size_t)0, a, (u32)NUM_SMEM_BINS);
   l.lane(4); launch_smem_bin<4>(l, a);
@@ -124,7 +144,7 @@ int enqueue_batch(L& l, const afq_config& cfg, int force_bin, const PipeBufs& pb
   const int res = cfg.resolution;
   const unsigned bin_grid = (unsigned)((b.n_cells + 255) / 256);
   if (res == AFQ_RES_CR_LIKE || res == AFQ_RES_TRIVIAL) {
-    l.launch(KID_BIN, k_bin_cells, bin_grid, 256u, (size_t)0, a, force_bin, l.need_shift());
+    l.launch(KID_BIN, k_bin_cells, bin_grid, 256u, (size_t)0, a, force_bin, l.need_shift(), (u32)(l.resolve_version() == 5));
     launch_crlike_bins(l, a, pb);
   } else {
     // cr-like-em and the parsimony family: tiny cells keep the cr-like fast path
@@ -133,7 +153,7 @@ int enqueue_batch(L& l, const afq_config& cfg, int force_bin, const PipeBufs& pb
       err = "--large-graph-thresh above 4096 is not supported on the CUDA path";
       return AFQ_ERR_UNSUPPORTED;
     }
-    l.launch(KID_BIN_GE, k_bin_cells_ge, bin_grid, 256u, (size_t)0, a, force_bin, GE_BIG_RECORDS, l.need_shift());
+    l.launch(KID_BIN_GE, k_bin_cells_ge, bin_grid, 256u, (size_t)0, a, force_bin, GE_BIG_RECORDS, l.need_shift(), (u32)(l.resolve_version() == 5));
     launch_crlike_bins(l, a, pb);
     Ctl h{};
     if (l.read_ctl(pb.ctl, &h)) { err = "reading the control block failed"; return AFQ_ERR_CUDA; }

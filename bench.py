@@ -107,7 +107,7 @@ def algorithmic_bytes(batch, nnz):
     return n_in + n_out
 
 
-def run_reference(args, spec, cells, res):
+def run_reference(args, spec, cells, res, emit):
     """--impl reference: the reference's CPU algorithm (oracle port) on all host cores."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
@@ -132,7 +132,7 @@ def run_reference(args, spec, cells, res):
     dt = (time.perf_counter() - t0) / max(args.steps, 1)
     v = n_sample / dt
     desc = f"first {n_sample} cells ({sample.n_records} records) of the workload per step"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "cells/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
@@ -140,11 +140,22 @@ def run_reference(args, spec, cells, res):
         "cpu_baseline": {"value": v, "unit": "cells/s", "cores": cores, "kind": "port", "sample": desc,
                          "note": "C++ restatement of the reference's Rust algorithm (reference not buildable here: no cargo/rustc)"},
         "e2e": {"value": v, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    })
 
 
 def main():
     args = parse_args()
+    # the contract is ONE JSON line on stdout: route everything else (NCCL banners, library chatter)
+    # to stderr until the line is printed
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(_real_stdout, 1)
+        print(json.dumps(obj), flush=True)
+        os.dup2(2, 1)
     from alevin_fry_b200 import synth
     cells, res, desc = CONFIGS[args.config]
     if args.cells:
@@ -153,7 +164,7 @@ def main():
         res = args.resolution
     spec = synth.config_spec(args.config)
     if args.impl == "reference":
-        return run_reference(args, spec, cells, res)
+        return run_reference(args, spec, cells, res, emit)
 
     import numpy as np
     import torch
@@ -323,7 +334,7 @@ def main():
 
     if rank == 0:
         total_cells = nc * world
-        print(json.dumps({
+        emit({
             "metric": METRIC, "value": total_cells / (ms * 1e-3), "unit": "cells/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
@@ -336,7 +347,7 @@ def main():
                     "ms_per_step": e2e_s * 1e3, "host_batches_per_step": nb,
                     "input_encoding": "rec_umi32 + rec_na8 + refs (u32)" if use_na8 else "rec_umi32 + rec_ref_offsets + refs (u32)"},
             "gpu_launches": int(launches) + 0, "clocks": clocks,
-        }), flush=True)
+        })
     q.close()
     pool.close()
     if world > 1:

@@ -39,6 +39,8 @@ struct EmuLauncher {
     return arena[which].data();
   }
   u32* adj_pool(u64 n) { adj.assign((size_t)n, 0xCDCDCDCDu); return adj.data(); }
+  int resolve_version() { const char* s = getenv("AFQ_RESOLVE"); return s ? atoi(s) : 3; }
+  int grid_for_bin5(int) { return 1; }
   void fork(int) {}
   void lane(int) {}
   void join() {}
