@@ -42,6 +42,7 @@ class AfqBatch(C.Structure):
         ("n_refs_total", C.c_uint64),
         ("cell_rec_offsets", C.c_void_p), ("rec_umi32", C.c_void_p),
         ("rec_ref_offsets", C.c_void_p), ("refs", C.c_void_p), ("rec_na8", C.c_void_p),
+        ("rec_umi24", C.c_void_p), ("refs24", C.c_void_p),
     ]
 
 

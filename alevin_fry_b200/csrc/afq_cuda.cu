@@ -75,6 +75,7 @@ struct Work {  // per-pipeline scratch (ordered on one stream)
   DBuf<u32> adj_pool;
   DBuf<u64> na_tiles;      // rec_na8 -> offsets scan
   DBuf<u32> na_ref_off;    // device API: offsets derived from rec_na8
+  DBuf<u32> umi_wide, refs_wide;   // rec_umi24 / refs24 widened to u32
   cudaError_t ensure(u64 n_cells, u64 n_refs) {
     cudaError_t e;
     if ((e = ctl.ensure(1)) != cudaSuccess) return e;
@@ -87,14 +88,14 @@ struct Work {  // per-pipeline scratch (ordered on one stream)
   void release() {
     ctl.release(); bin_list.release(); stage_col.release(); stage_val.release();
     tile_sums.release(); ge_arena[0].release(); ge_arena[1].release(); adj_pool.release();
-    na_tiles.release(); na_ref_off.release();
+    na_tiles.release(); na_ref_off.release(); umi_wide.release(); refs_wide.release();
   }
 };
 
 struct Slot {  // one in-flight host batch
   DBuf<u64> cell_rec_off;
   DBuf<u32> umi, ref_off, refs;
-  DBuf<u8> na8;
+  DBuf<u8> na8, umi24, refs24;
   DBuf<u64> row_ptr;
   DBuf<u32> col;
   DBuf<float> val, sum_umi, max_umi;
@@ -109,7 +110,7 @@ struct Slot {  // one in-flight host batch
   u64 n_cells = 0, n_refs = 0, ticket = 0;
   bool busy = false;
   void release() {
-    cell_rec_off.release(); umi.release(); ref_off.release(); refs.release(); na8.release();
+    cell_rec_off.release(); umi.release(); ref_off.release(); refs.release(); na8.release(); umi24.release(); refs24.release();
     row_ptr.release(); col.release(); val.release(); sum_umi.release(); max_umi.release();
     num_expr.release(); num_over_mean.release(); flags.release();
     h_row_ptr.release(); h_col.release(); h_num_expr.release(); h_num_over_mean.release();
@@ -139,8 +140,6 @@ struct afq_ctx {
   int force_bin = -1;
   int grid_smem[NUM_SMEM_BINS] = {0};
   int ge_grid = 0;
-  int grid_smem5[NUM_SMEM_BINS] = {0};
-  int resolve_version = 3;     // AFQ_RESOLVE=5 selects the experimental partition-based resolve
   u32 need_shift = 0;          // arena-size bias, raised when a batch overflowed many arenas
   bool no_lanes = false;       // AFQ_NO_LANES=1: launch the arena kernels back to back on the caller's stream
   cudaStream_t lanes[NUM_BINS] = {nullptr};
@@ -190,17 +189,6 @@ int setup_bin(afq_ctx* c) {
   return AFQ_OK;
 }
 
-template <int BIN>
-int setup_bin5(afq_ctx* c) {
-  const size_t smem = bin5_smem_bytes(BIN);
-  CUDA_TRY(c, cudaFuncSetAttribute(k_resolve5_smem<BIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int occ = 0;
-  CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_resolve5_smem<BIN>, (int)bin5_threads(BIN), smem));
-  if (occ < 1) occ = 1;
-  c->grid_smem5[BIN] = occ * c->num_sms;
-  return AFQ_OK;
-}
-
 // Launcher for afq_pipeline.cuh: real launches on a CUDA stream, timed with event pairs when
 // profiling is on.
 struct CudaLauncher {
@@ -224,8 +212,6 @@ struct CudaLauncher {
     return 0;
   }
   int grid_for_bin(int b) { return c->grid_smem[b]; }
-  int grid_for_bin5(int b) { return c->grid_smem5[b]; }
-  int resolve_version() { return c->resolve_version; }
   int ge_blocks(int which) { return which == 0 ? 16 : c->ge_grid; }
   u8* ge_arena(int which, u64 bytes, u32 blocks) {
     if (w->ge_arena[which].ensure((size_t)bytes * blocks + 64) != cudaSuccess) return nullptr;
@@ -267,6 +253,21 @@ int run_pipeline(afq_ctx* c, Work& w, const afq_batch& b, const afq_device_out& 
   if (b.n_cells) CUDA_TRY(c, w.ensure(b.n_cells, b.n_refs_total));
   afq_batch bb = b;
   CudaLauncher l{c, &w, st, st};
+  if (!bb.rec_umi32 && bb.n_records) {
+    if (!bb.rec_umi24) { c->err = "afq_batch needs rec_umi32 or rec_umi24"; return AFQ_ERR_INVALID; }
+    if (c->cfg.umi_len > 12) { c->err = "rec_umi24 needs umi_len <= 12"; return AFQ_ERR_INVALID; }
+    if ((uintptr_t)bb.rec_umi24 & 3) { c->err = "rec_umi24 must be 4-byte aligned"; return AFQ_ERR_INVALID; }
+    CUDA_TRY(c, w.umi_wide.ensure(bb.n_records + 4));
+    enqueue_unpack24(l, bb.rec_umi24, bb.n_records, w.umi_wide.p);
+    bb.rec_umi32 = w.umi_wide.p;
+  }
+  if (!bb.refs && bb.n_refs_total) {
+    if (!bb.refs24) { c->err = "afq_batch needs refs or refs24"; return AFQ_ERR_INVALID; }
+    if ((uintptr_t)bb.refs24 & 3) { c->err = "refs24 must be 4-byte aligned"; return AFQ_ERR_INVALID; }
+    CUDA_TRY(c, w.refs_wide.ensure(bb.n_refs_total + 4));
+    enqueue_unpack24(l, bb.refs24, bb.n_refs_total, w.refs_wide.p);
+    bb.refs = w.refs_wide.p;
+  }
   if (!bb.rec_ref_offsets) {
     if (!bb.rec_na8) { c->err = "afq_batch needs rec_ref_offsets or rec_na8"; return AFQ_ERR_INVALID; }
     CUDA_TRY(c, w.na_tiles.ensure(bb.n_records / SCAN_TILE + 4));
@@ -341,7 +342,6 @@ int afq_create(const afq_config* cfg, const uint32_t* tid_to_gid, uint64_t n_ref
   if (const char* s = getenv("AFQ_FORCE_BIN")) c->force_bin = atoi(s);
   if (const char* s = getenv("AFQ_NEED_SHIFT")) c->need_shift = (u32)atoi(s);
   if (const char* s = getenv("AFQ_NO_LANES")) c->no_lanes = atoi(s) != 0;
-  if (const char* s = getenv("AFQ_RESOLVE")) c->resolve_version = atoi(s) == 5 ? 5 : 3;
   if (c->large_cap_log2 < 10) c->large_cap_log2 = 10;
   if (c->large_cap_log2 > 30) c->large_cap_log2 = 30;
   if (c->large_blocks < 1) c->large_blocks = (u32)c->num_sms;
@@ -370,9 +370,6 @@ int afq_create(const afq_config* cfg, const uint32_t* tid_to_gid, uint64_t n_ref
   int rc;
   if ((rc = setup_bin<0>(c)) || (rc = setup_bin<1>(c)) || (rc = setup_bin<2>(c)) ||
       (rc = setup_bin<3>(c)) || (rc = setup_bin<4>(c)) || (rc = setup_bin<5>(c)))
-    return fail(rc);
-  if ((rc = setup_bin5<0>(c)) || (rc = setup_bin5<1>(c)) || (rc = setup_bin5<2>(c)) ||
-      (rc = setup_bin5<3>(c)) || (rc = setup_bin5<4>(c)) || (rc = setup_bin5<5>(c)))
     return fail(rc);
   {
     int occ = 0;
@@ -445,10 +442,12 @@ int afq_submit(afq_ctx* c, const afq_batch* hb, uint64_t* ticket) {
   }
   const u64 nc = hb->n_cells, nr = hb->n_records, nf = hb->n_refs_total;
   CUDA_TRY(c, s.cell_rec_off.ensure(nc + 1));
-  CUDA_TRY(c, s.umi.ensure(nr + 1));
+  const bool use_umi24 = hb->rec_umi24 && !hb->rec_umi32;
+  const bool use_refs24 = hb->refs24 && !hb->refs;
+  if (use_umi24) CUDA_TRY(c, s.umi24.ensure(3 * nr + 16)); else CUDA_TRY(c, s.umi.ensure(nr + 1));
   CUDA_TRY(c, s.ref_off.ensure(nr + 2));
   if (hb->rec_na8 && !hb->rec_ref_offsets) CUDA_TRY(c, s.na8.ensure(nr + 1));
-  CUDA_TRY(c, s.refs.ensure(nf + 1));
+  if (use_refs24) CUDA_TRY(c, s.refs24.ensure(3 * nf + 16)); else CUDA_TRY(c, s.refs.ensure(nf + 1));
   CUDA_TRY(c, s.row_ptr.ensure(nc + 1));
   CUDA_TRY(c, s.col.ensure(nf + 1));
   CUDA_TRY(c, s.val.ensure(nf + 1));
@@ -466,20 +465,30 @@ int afq_submit(afq_ctx* c, const afq_batch* hb, uint64_t* ticket) {
   CUDA_TRY(c, s.h_ctl.ensure(1));
   // H2D on the copy stream (overlaps the previous batch's kernels)
   CUDA_TRY(c, cudaMemcpyAsync(s.cell_rec_off.p, hb->cell_rec_offsets, (nc + 1) * sizeof(u64), cudaMemcpyHostToDevice, c->s_copy));
-  if (nr) CUDA_TRY(c, cudaMemcpyAsync(s.umi.p, hb->rec_umi32, nr * sizeof(u32), cudaMemcpyHostToDevice, c->s_copy));
+  if (!use_umi24 && !hb->rec_umi32 && nr) { c->err = "afq_batch needs rec_umi32 or rec_umi24"; return AFQ_ERR_INVALID; }
+  if (!use_refs24 && !hb->refs && nf) { c->err = "afq_batch needs refs or refs24"; return AFQ_ERR_INVALID; }
+  if (nr) {
+    if (use_umi24) CUDA_TRY(c, cudaMemcpyAsync(s.umi24.p, hb->rec_umi24, 3 * nr, cudaMemcpyHostToDevice, c->s_copy));
+    else CUDA_TRY(c, cudaMemcpyAsync(s.umi.p, hb->rec_umi32, nr * sizeof(u32), cudaMemcpyHostToDevice, c->s_copy));
+  }
   const bool use_na8 = hb->rec_na8 && !hb->rec_ref_offsets;
   if (!use_na8 && !hb->rec_ref_offsets) { c->err = "afq_batch needs rec_ref_offsets or rec_na8"; return AFQ_ERR_INVALID; }
   if (use_na8) { if (nr) CUDA_TRY(c, cudaMemcpyAsync(s.na8.p, hb->rec_na8, nr * sizeof(u8), cudaMemcpyHostToDevice, c->s_copy)); }
   else CUDA_TRY(c, cudaMemcpyAsync(s.ref_off.p, hb->rec_ref_offsets, (nr + 1) * sizeof(u32), cudaMemcpyHostToDevice, c->s_copy));
-  if (nf) CUDA_TRY(c, cudaMemcpyAsync(s.refs.p, hb->refs, nf * sizeof(u32), cudaMemcpyHostToDevice, c->s_copy));
+  if (nf) {
+    if (use_refs24) CUDA_TRY(c, cudaMemcpyAsync(s.refs24.p, hb->refs24, 3 * nf, cudaMemcpyHostToDevice, c->s_copy));
+    else CUDA_TRY(c, cudaMemcpyAsync(s.refs.p, hb->refs, nf * sizeof(u32), cudaMemcpyHostToDevice, c->s_copy));
+  }
   CUDA_TRY(c, cudaEventRecord(s.ev_h2d, c->s_copy));
   CUDA_TRY(c, cudaStreamWaitEvent(c->s_compute, s.ev_h2d, 0));
   afq_batch db = *hb;
   db.cell_rec_offsets = s.cell_rec_off.p;
-  db.rec_umi32 = s.umi.p;
+  db.rec_umi32 = use_umi24 ? nullptr : s.umi.p;
+  db.rec_umi24 = use_umi24 ? s.umi24.p : nullptr;
   db.rec_ref_offsets = use_na8 ? nullptr : s.ref_off.p;
   db.rec_na8 = use_na8 ? s.na8.p : nullptr;
-  db.refs = s.refs.p;
+  db.refs = use_refs24 ? nullptr : s.refs.p;
+  db.refs24 = use_refs24 ? s.refs24.p : nullptr;
   afq_device_out o{};
   o.row_ptr = s.row_ptr.p; o.cap_cells = nc + 1;
   o.col = s.col.p; o.val = s.val.p; o.cap_nnz = nf + 1;

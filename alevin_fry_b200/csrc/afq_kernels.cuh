@@ -85,15 +85,13 @@ struct CellShared {
 // ------------------------------------------------------------------------------------
 // classify cells into arena-size bins by record count
 // ------------------------------------------------------------------------------------
-__global__ void k_bin_cells(KArgs a, int force_bin, u32 need_shift, u32 by_refs) {
+__global__ void k_bin_cells(KArgs a, int force_bin, u32 need_shift) {
   const u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= a.n_cells) return;
   const u64 r0 = a.cell_rec_off[c], r1 = a.cell_rec_off[c + 1];
   const u64 n = r1 - r0;
   const u32 p = a.ref_off[r1] - a.ref_off[r0];
-  // v3: distinct pairs <= min(records, refs), typically << records (optimistic, overflow list as backstop);
-  // v5 (by_refs): pairs <= refs is a hard bound, the arena can never overflow
-  const u64 need = by_refs ? (u64)p : ((n < (u64)p ? n : (u64)p) << need_shift);
+  const u64 need = (n < (u64)p ? n : (u64)p) << need_shift;  // distinct pairs <= refs; typically << records
   int b = NUM_SMEM_BINS;
 #pragma unroll
   for (int i = NUM_SMEM_BINS - 1; i >= 0; --i)
@@ -597,6 +595,26 @@ __global__ void __launch_bounds__(1024) k_na_offsets(const u8* na, u64 n, const 
   for (u32 k = 0; k < 4; ++k) {
     if (t0 + k <= n) ref_off[t0 + k] = (u32)run;   // index n receives the closing offset
     run += v[k];
+  }
+}
+
+// ---- 24-bit packed wire arrays (afq_batch.rec_umi24 / refs24) -> u32 in HBM ------------------
+// One thread widens 4 values: three aligned 32-bit loads in, one 128-bit store out.
+__global__ void __launch_bounds__(256) k_unpack24(const u8* src, u64 n, u32* dst) {
+  const u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;   // group of 4 values
+  const u64 i0 = g * 4;
+  if (i0 >= n) return;
+  if (i0 + 4 <= n) {
+    const u32* w = reinterpret_cast<const u32*>(src) + g * 3;
+    const u32 a = w[0], b = w[1], c = w[2];
+    uint4 o;
+    o.x = a & 0xFFFFFFu;
+    o.y = (a >> 24) | ((b & 0xFFFFu) << 8);
+    o.z = (b >> 16) | ((c & 0xFFu) << 16);
+    o.w = c >> 8;
+    *reinterpret_cast<uint4*>(dst + i0) = o;
+  } else {
+    for (u64 i = i0; i < n; ++i) dst[i] = (u32)src[3 * i] | ((u32)src[3 * i + 1] << 8) | ((u32)src[3 * i + 2] << 16);
   }
 }
 

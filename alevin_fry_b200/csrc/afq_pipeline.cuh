@@ -15,27 +15,24 @@
 //   void fork(int lanes); void lane(int i); void join();      // independent launches may overlap:
 //       between fork and join, launches go to lane i's stream (CUDA) / run in order (emulator)
 //   u32  need_shift();                                        // arena-size bias learnt from overflows
-//   int  resolve_version();                                   // 3 (default) or 5 (AFQ_RESOLVE=5, experimental)
-//   int  grid_for_bin5(int bin);
 #pragma once
 #include <string>
 
 #include "../../include/afq.h"
 #include "afq_kernels.cuh"
 #include "afq_pug.cuh"
-#include "afq_resolve5.cuh"
 
 namespace afq {
 
 enum KernelId : int {
   KID_BIN = 0, KID_SMEM0 = 1, KID_LARGE = 7, KID_SCAN_SUMS = 8, KID_SCAN_TILES = 9, KID_SCAN_ROWS = 10,
-  KID_GATHER = 11, KID_GENE_EQC = 12, KID_GENE_EQC_BIG = 13, KID_BIN_GE = 14, KID_REGION = 15, KID_NA_OFFSETS = 16, NUM_KID = 17
+  KID_GATHER = 11, KID_GENE_EQC = 12, KID_GENE_EQC_BIG = 13, KID_BIN_GE = 14, KID_REGION = 15, KID_NA_OFFSETS = 16, KID_UNPACK24 = 17, NUM_KID = 18
 };
 static const char* const KID_NAMES[NUM_KID] = {
     "k_bin_cells", "k_resolve_smem<0>", "k_resolve_smem<1>", "k_resolve_smem<2>", "k_resolve_smem<3>",
     "k_resolve_smem<4>", "k_resolve_smem<5>", "k_resolve_large", "k_scan_tile_sums", "k_scan_tiles",
     "k_scan_rows", "k_gather_rows", "k_gene_eqc", "k_gene_eqc(big cells)", "k_bin_cells_ge", "resolve_region(wall)",
-    "k_na_offsets(+tile sums)"};
+    "k_na_offsets(+tile sums)", "k_unpack24"};
 
 struct PipeBufs {  // device scratch owned by the caller (one set per stream-ordered pipeline)
   Ctl* ctl;
@@ -61,11 +58,6 @@ inline void launch_smem_bin(L& l, const KArgs& a) {
   l.launch(KID_SMEM0 + BIN, k_resolve_smem<BIN>, (unsigned)l.grid_for_bin(BIN), bin_threads(BIN), smem, a);
 }
 
-template <int BIN, class L>
-inline void launch_smem_bin5(L& l, const KArgs& a) {
-  l.launch(KID_SMEM0 + BIN, k_resolve5_smem<BIN>, (unsigned)l.grid_for_bin5(BIN), bin5_threads(BIN), bin5_smem_bytes(BIN), a);
-}
-
 // The arena kernels are independent of each other (overflowing cells go to a separate list that is
 // drained afterwards), so they are forked onto per-arena lanes and overlap on the device: small
 // CTAs fill the SMs while the few big-arena CTAs are still running.
@@ -73,18 +65,6 @@ template <class L>
 inline void launch_crlike_bins(L& l, const KArgs& a, const PipeBufs& pb) {
   l.region_begin();
   l.fork(NUM_BINS);
-  if (l.resolve_version() == 5) {
-    l.lane(5); launch_smem_bin5<5>(l, a);
-    l.lane(6); l.launch(KID_LARGE, k_resolve5_large, pb.large_blocks, 1024u, (size_t)0, a, (u32)NUM_SMEM_BINS);
-    l.lane(4); launch_smem_bin5<4>(l, a);
-    l.lane(3); launch_smem_bin5<3>(l, a);
-    l.lane(2); launch_smem_bin5<2>(l, a);
-    l.lane(1); launch_smem_bin5<1>(l, a);
-    l.lane(0); launch_smem_bin5<0>(l, a);
-    l.join();
-    l.region_end();
-    return;
-  }
   l.lane(5); launch_smem_bin<5>(l, a);
   l.lane(6); l.launch(KID_LARGE, k_resolve_large, pb.large_blocks, 1024u, (size_t)0, a, (u32)NUM_SMEM_BINS);
   l.lane(4); launch_smem_bin<4>(l, a);
@@ -95,6 +75,14 @@ inline void launch_crlike_bins(L& l, const KArgs& a, const PipeBufs& pb) {
   l.join();
   l.launch(KID_LARGE, k_resolve_large, pb.large_blocks, 1024u, (size_t)0, a, (u32)OVF_LIST);
   l.region_end();
+}
+
+// 24-bit packed wire array -> u32 (dst must be 16-byte aligned with room for n values)
+template <class L>
+inline void enqueue_unpack24(L& l, const u8* src, u64 n, u32* dst) {
+  if (!n) return;
+  const u64 groups = (n + 3) / 4;
+  l.launch(KID_UNPACK24, k_unpack24, (unsigned)((groups + 255) / 256), 256u, (size_t)0, src, n, dst);
 }
 
 // rec_na8 -> rec_ref_offsets on the device (three small launches). `na_tiles` needs
@@ -144,7 +132,7 @@ int enqueue_batch(L& l, const afq_config& cfg, int force_bin, const PipeBufs& pb
   const int res = cfg.resolution;
   const unsigned bin_grid = (unsigned)((b.n_cells + 255) / 256);
   if (res == AFQ_RES_CR_LIKE || res == AFQ_RES_TRIVIAL) {
-    l.launch(KID_BIN, k_bin_cells, bin_grid, 256u, (size_t)0, a, force_bin, l.need_shift(), (u32)(l.resolve_version() == 5));
+    l.launch(KID_BIN, k_bin_cells, bin_grid, 256u, (size_t)0, a, force_bin, l.need_shift());
     launch_crlike_bins(l, a, pb);
   } else {
     // cr-like-em and the parsimony family: tiny cells keep the cr-like fast path
@@ -153,7 +141,7 @@ int enqueue_batch(L& l, const afq_config& cfg, int force_bin, const PipeBufs& pb
       err = "--large-graph-thresh above 4096 is not supported on the CUDA path";
       return AFQ_ERR_UNSUPPORTED;
     }
-    l.launch(KID_BIN_GE, k_bin_cells_ge, bin_grid, 256u, (size_t)0, a, force_bin, GE_BIG_RECORDS, l.need_shift(), (u32)(l.resolve_version() == 5));
+    l.launch(KID_BIN_GE, k_bin_cells_ge, bin_grid, 256u, (size_t)0, a, force_bin, GE_BIG_RECORDS, l.need_shift());
     launch_crlike_bins(l, a, pb);
     Ctl h{};
     if (l.read_ctl(pb.ctl, &h)) { err = "reading the control block failed"; return AFQ_ERR_CUDA; }

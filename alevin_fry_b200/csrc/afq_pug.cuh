@@ -1394,7 +1394,7 @@ constexpr int GE_LIST_BIG = NUM_BINS;      // bin_list row for cells > GE_BIG_RE
 constexpr int GE_LIST_NORMAL = NUM_BINS + 1;
 constexpr u32 GE_BIG_RECORDS = 1u << 16;
 
-__global__ void k_bin_cells_ge(KArgs a, int force_bin, u32 big_records, u32 need_shift, u32 by_refs) {
+__global__ void k_bin_cells_ge(KArgs a, int force_bin, u32 big_records, u32 need_shift) {
   const u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= a.n_cells) return;
   const u64 r0 = a.cell_rec_off[c], r1 = a.cell_rec_off[c + 1];
@@ -1402,7 +1402,7 @@ __global__ void k_bin_cells_ge(KArgs a, int force_bin, u32 big_records, u32 need
   const u32 p = a.ref_off[r1] - a.ref_off[r0];
   int b;
   if (a.tiny_eligible && n < a.small_thresh) {
-    const u64 need = by_refs ? (u64)p : ((n < (u64)p ? n : (u64)p) << need_shift);
+    const u64 need = (n < (u64)p ? n : (u64)p) << need_shift;
     b = NUM_SMEM_BINS;
 #pragma unroll
     for (int i = NUM_SMEM_BINS - 1; i >= 0; --i)

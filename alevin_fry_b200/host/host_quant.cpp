@@ -204,12 +204,29 @@ struct HostBatch {
   Pinned<uint64_t> cell_rec_off;
   Pinned<uint32_t> umi, ref_off, refs;
   Pinned<uint8_t> na8;           // alignment count per record (sent instead of ref_off when all <= 255)
+  Pinned<uint8_t> umi24, refs24; // pack24: 3-byte UMIs / transcript ids instead of umi / refs (afq_batch.rec_umi24 / refs24)
   bool na8_ok = true;
+  bool pack24 = false;
+  uint64_t n_rec = 0, n_ref = 0;
+  void push_umi(uint32_t v) {
+    if (pack24) { umi24.push((uint8_t)v); umi24.push((uint8_t)(v >> 8)); umi24.push((uint8_t)(v >> 16)); } else umi.push(v);
+    ++n_rec;
+  }
+  void push_ref(uint32_t v) {
+    if (pack24) { refs24.push((uint8_t)v); refs24.push((uint8_t)(v >> 8)); refs24.push((uint8_t)(v >> 16)); } else refs.push(v);
+    ++n_ref;
+  }
+  void truncate(uint64_t rec, uint64_t ref) {   // drop the records of a filtered-out cell
+    n_rec = rec; n_ref = ref;
+    if (pack24) { umi24.n = 3 * rec; refs24.n = 3 * ref; } else { umi.n = rec; refs.n = ref; }
+    ref_off.n = rec + 1; na8.n = rec;
+  }
   std::vector<uint64_t> barcodes;
   std::vector<uint32_t> nrec;
   uint64_t first_cell = 0;
   void reset(uint64_t first) {
     cell_rec_off.clear(); umi.clear(); ref_off.clear(); refs.clear(); na8.clear(); barcodes.clear(); nrec.clear();
+    umi24.clear(); refs24.clear(); n_rec = n_ref = 0;
     cell_rec_off.push(0); ref_off.push(0); first_cell = first; na8_ok = true;
   }
   uint64_t n_cells() const { return barcodes.size(); }
@@ -366,6 +383,9 @@ int quantify_impl(const afqh_quant_opts& o) {
   const uint64_t batch_records = o.batch_records ? o.batch_records : (32ull << 20);
   constexpr int NB = 3;
   HostBatch hb[NB];
+  // 24-bit wire arrays whenever the chemistry allows: UMI <= 12 bases and fewer than 2^24 targets
+  const bool pack24 = umi_len <= 12 && lay.umi_size <= 4 && pre.ref_names.size() < (1u << 24) && !getenv("AFQ_NO_PACK24");
+  for (auto& b : hb) b.pack24 = pack24;
   uint64_t tickets[NB] = {0};
   bool inflight[NB] = {false};
   int cur = 0;
@@ -384,13 +404,13 @@ int quantify_impl(const afqh_quant_opts& o) {
     afq_batch ab{};
     ab.first_cell_index = b.first_cell;
     ab.n_cells = b.n_cells();
-    ab.n_records = b.umi.n;
-    ab.n_refs_total = b.refs.n;
+    ab.n_records = b.n_rec;
+    ab.n_refs_total = b.n_ref;
     ab.cell_rec_offsets = b.cell_rec_off.p;
-    ab.rec_umi32 = b.umi.p;
+    if (b.pack24) { ab.rec_umi24 = b.umi24.p; ab.refs24 = b.refs24.p; }     // 3 bytes instead of 4 per UMI / id over PCIe
+    else { ab.rec_umi32 = b.umi.p; ab.refs = b.refs.p; }
     if (b.na8_ok) { ab.rec_ref_offsets = nullptr; ab.rec_na8 = b.na8.p; }   // 1 byte instead of 4 per record over PCIe
     else { ab.rec_ref_offsets = b.ref_off.p; ab.rec_na8 = nullptr; }
-    ab.refs = b.refs.p;
     if (afq_submit(ctx, &ab, &tickets[i]) != AFQ_OK) throw Fail{std::string("afq_submit: ") + afq_last_error(ctx)};
     inflight[i] = true;
   };
@@ -408,7 +428,7 @@ int quantify_impl(const afqh_quant_opts& o) {
       HostBatch& b = hb[cur];
       uint64_t bc = 0;
       bool take = true;
-      const size_t rec_start = b.umi.n, ref_start = b.refs.n;
+      const uint64_t rec_start = b.n_rec, ref_start = b.n_ref;
       for (uint32_t r = 0; r < nrec; ++r) {
         REQUIRE(p + 4 + lay.read_bytes <= end, "record overruns its chunk");
         uint32_t na; memcpy(&na, p, 4); p += 4;
@@ -419,25 +439,25 @@ int quantify_impl(const afqh_quant_opts& o) {
         REQUIRE(p + (size_t)na * lay.aln_bytes <= end, "alignments overrun their chunk");
         if (r == 0) { bc = rbc; if (filtering && !keep.count(bc)) take = false; }
         if (take) {
-          b.umi.push((uint32_t)rumi);
+          b.push_umi((uint32_t)rumi);
           for (uint32_t a = 0; a < na; ++a) {
             uint32_t ref; memcpy(&ref, p + (size_t)a * lay.aln_bytes + lay.refid_off, 4);
-            b.refs.push(ref & 0x7FFFFFFFu);  // bit 31 = orientation (src/convert.rs:442-445)
+            b.push_ref(ref & 0x7FFFFFFFu);  // bit 31 = orientation (src/convert.rs:442-445)
           }
-          b.ref_off.push((uint32_t)b.refs.n);
+          b.ref_off.push((uint32_t)b.n_ref);
           b.na8.push((uint8_t)na);
           if (na > 255) b.na8_ok = false;
         }
         p += (size_t)na * lay.aln_bytes;
       }
-      if (!take) { b.umi.n = rec_start; b.refs.n = ref_start; b.ref_off.n = rec_start + 1; b.na8.n = rec_start; continue; }
+      if (!take) { b.truncate(rec_start, ref_start); continue; }
       REQUIRE(nrec > 0, "Discovered empty chunk; should not happen!");
-      b.cell_rec_off.push(b.umi.n);
+      b.cell_rec_off.push(b.n_rec);
       b.barcodes.push_back(bc);
       b.nrec.push_back(nrec);
       total_records += nrec;
       ++cells_seen;
-      if (b.umi.n >= batch_records || b.refs.n >= (3ull << 30)) {
+      if (b.n_rec >= batch_records || b.n_ref >= (3ull << 30)) {
         submit(cur);
         const int nxt = (cur + 1) % NB;
         if (inflight[nxt]) finish(nxt);

@@ -93,19 +93,40 @@ class CellBatch:
             cached = self._na8 = na.astype(np.uint8)
         return cached
 
-    def to_c(self, use_na8: bool = False) -> AfqBatch:
+    def pack24(self, alloc=None):
+        """(rec_umi24, refs24): little-endian 24-bit packed copies of rec_umi32 / refs (the compact
+        wire arrays of afq_batch); `alloc(n_bytes, dtype)` may hand out pinned memory."""
+        cached = getattr(self, "_p24", None)
+        if cached is None:
+            alloc = alloc or (lambda n, dt: np.empty(n, dtype=dt))
+            out = []
+            for name, src in (("rec_umi32", self.rec_umi32), ("refs", self.refs)):
+                if len(src) and int(src.max()) >= 1 << 24:
+                    raise ValueError(f"{name} holds a value >= 2^24: the 24-bit wire array cannot be used")
+                dst = alloc(3 * len(src) + 16, np.uint8)
+                dst[:3 * len(src)].reshape(-1, 3)[:] = src.view(np.uint8).reshape(-1, 4)[:, :3]
+                out.append(dst)
+            cached = self._p24 = tuple(out)
+        return cached
+
+    def to_c(self, use_na8: bool = False, use_pack24: bool = False) -> AfqBatch:
         b = AfqBatch()
         b.first_cell_index = self.first_cell_index
         b.n_cells, b.n_records, b.n_refs_total = self.n_cells, self.n_records, self.n_refs_total
         b.cell_rec_offsets = _ptr(self.cell_rec_offsets)
-        b.rec_umi32 = _ptr(self.rec_umi32)
+        if use_pack24:
+            u24, r24 = self.pack24()
+            b.rec_umi32, b.refs = None, None
+            b.rec_umi24, b.refs24 = _ptr(u24), _ptr(r24)
+        else:
+            b.rec_umi32, b.refs = _ptr(self.rec_umi32), _ptr(self.refs)
+            b.rec_umi24, b.refs24 = None, None
         if use_na8:
             b.rec_ref_offsets = None
             b.rec_na8 = _ptr(self.na8())
         else:
             b.rec_ref_offsets = _ptr(self.rec_ref_offsets)
             b.rec_na8 = None
-        b.refs = _ptr(self.refs)
         return b
 
     def slice_cells(self, c0: int, c1: int) -> "CellBatch":
@@ -200,8 +221,8 @@ class Quantifier:
             raise AfqError(rc, msg.decode() if msg else "")
 
     # ---- host API ---------------------------------------------------------------
-    def submit(self, batch: CellBatch, use_na8: bool = False) -> int:
-        cb = batch.to_c(use_na8)
+    def submit(self, batch: CellBatch, use_na8: bool = False, use_pack24: bool = False) -> int:
+        cb = batch.to_c(use_na8, use_pack24)
         t = C.c_uint64()
         self._check(self._lib.afq_submit(self._ctx, C.byref(cb), C.byref(t)))
         self._keep[t.value] = batch  # keep host arrays alive until the H2D copies are done
@@ -215,8 +236,8 @@ class Quantifier:
         self._lib.afq_result_release(self._ctx, C.byref(r))
         return out
 
-    def quantify_batch(self, batch: CellBatch, use_na8: bool = False) -> QuantResult:
-        return self.wait(self.submit(batch, use_na8))
+    def quantify_batch(self, batch: CellBatch, use_na8: bool = False, use_pack24: bool = False) -> QuantResult:
+        return self.wait(self.submit(batch, use_na8, use_pack24))
 
     # ---- device API (torch tensors on this ctx's GPU) ----------------------------
     def quant_device(self, dev_batch: dict, dev_out: dict, stream_ptr: int = 0):

@@ -46,6 +46,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-offsets", action="store_true",
                     help="e2e: ship 4-byte rec_ref_offsets instead of the 1-byte rec_na8 alignment counts")
+    ap.add_argument("--e2e-u32", action="store_true",
+                    help="e2e: ship 4-byte UMIs / transcript ids instead of the 24-bit rec_umi24 / refs24 wire arrays")
     return ap.parse_args()
 
 
@@ -270,12 +272,17 @@ def main():
             na = pool.empty(p.n_records, np.uint8)
             np.subtract(p.rec_ref_offsets[1:], p.rec_ref_offsets[:-1], out=na, casting="unsafe")
             p._na8 = na
-    h2d = sum(p.cell_rec_offsets.nbytes + p.rec_umi32.nbytes + (p._na8.nbytes if use_na8 else p.rec_ref_offsets.nbytes) + p.refs.nbytes for p in parts)
+    use_p24 = not args.e2e_u32   # 12-base UMIs and < 2^24 transcripts: 3 bytes each on the wire
+    if use_p24:
+        for p in parts:
+            p.pack24(pool.empty)
+    h2d = sum(p.cell_rec_offsets.nbytes + (p._na8.nbytes if use_na8 else p.rec_ref_offsets.nbytes) +
+              (3 * (p.n_records + p.n_refs_total) if use_p24 else p.rec_umi32.nbytes + p.refs.nbytes) for p in parts)
 
     def step_e2e():
         d2h, tickets = 0, []
         for p in parts:
-            tickets.append(q.submit(p, use_na8))
+            tickets.append(q.submit(p, use_na8, use_p24))
             if len(tickets) == 3:
                 n_c, n_z = q.wait(tickets.pop(0), copy=False)
                 d2h += 8 * (n_c + 1) + 17 * n_c + 8 * n_z
@@ -345,7 +352,8 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": total_cells / e2e_s, "unit": "cells/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s * 1e3, "host_batches_per_step": nb,
-                    "input_encoding": "rec_umi32 + rec_na8 + refs (u32)" if use_na8 else "rec_umi32 + rec_ref_offsets + refs (u32)"},
+                    "input_encoding": ("rec_umi24 + " if use_p24 else "rec_umi32 + ") + ("rec_na8 + " if use_na8 else "rec_ref_offsets + ") +
+                                      ("refs24" if use_p24 else "refs (u32)")},
             "gpu_launches": int(launches) + 0, "clocks": clocks,
         })
     q.close()

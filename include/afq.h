@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define AFQ_ABI_VERSION 1
+#define AFQ_ABI_VERSION 2
 
 /* status codes */
 enum {
@@ -92,6 +92,14 @@ typedef struct afq_batch {
                                        count must be <= 255) INSTEAD of rec_ref_offsets (pass
                                        NULL there): 1 byte instead of 4 per record over PCIe;
                                        the device derives the CSR offsets with a scan          */
+  const uint8_t* rec_umi24;         /* optional, [3*n_records] little-endian 24-bit UMIs INSTEAD
+                                       of rec_umi32 (pass NULL there); needs umi_len <= 12 (10x v3
+                                       and every chemistry with a <= 12 bp UMI): 3 bytes instead
+                                       of 4 per record over PCIe. 4-byte aligned pointer.       */
+  const uint8_t* refs24;            /* optional, [3*n_refs_total] little-endian 24-bit transcript
+                                       ids INSTEAD of refs (pass NULL there); needs every id
+                                       < 2^24. 4-byte aligned pointer. The device widens both to
+                                       u32 in HBM (k_unpack24) before the resolve kernels run.  */
 } afq_batch;
 
 /* Per-cell results in input cell order. CSR with ascending columns inside a row — the

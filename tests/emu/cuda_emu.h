@@ -28,6 +28,7 @@
 #define __restrict__
 
 struct emu_dim3 { unsigned x = 1, y = 1, z = 1; };
+struct uint4 { unsigned x, y, z, w; };
 extern emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
 using cudaStream_t = void*;
 

@@ -39,8 +39,6 @@ struct EmuLauncher {
     return arena[which].data();
   }
   u32* adj_pool(u64 n) { adj.assign((size_t)n, 0xCDCDCDCDu); return adj.data(); }
-  int resolve_version() { const char* s = getenv("AFQ_RESOLVE"); return s ? atoi(s) : 3; }
-  int grid_for_bin5(int) { return 1; }
   void fork(int) {}
   void lane(int) {}
   void join() {}
@@ -90,6 +88,17 @@ int afq_emu_quant(const afq_config* cfg, const uint32_t* tid_to_gid, uint64_t n_
   afq_batch bb = *b;
   std::vector<u32> na_off;
   std::vector<u64> na_tiles;
+  std::vector<u32> umi_wide, refs_wide;
+  if (!bb.rec_umi32 && bb.rec_umi24) {
+    umi_wide.assign(bb.n_records + 4, 0xCDCDCDCDu);
+    enqueue_unpack24(l, bb.rec_umi24, bb.n_records, umi_wide.data());
+    bb.rec_umi32 = umi_wide.data();
+  }
+  if (!bb.refs && bb.refs24) {
+    refs_wide.assign(bb.n_refs_total + 4, 0xCDCDCDCDu);
+    enqueue_unpack24(l, bb.refs24, bb.n_refs_total, refs_wide.data());
+    bb.refs = refs_wide.data();
+  }
   if (!bb.rec_ref_offsets && bb.rec_na8) {   // compact alignment counts -> offsets (device scan kernels)
     na_off.assign(bb.n_records + 2, 0xCDCDCDCDu);
     na_tiles.assign(bb.n_records / SCAN_TILE + 4, 0);

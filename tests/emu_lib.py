@@ -41,10 +41,10 @@ def lib():
     return _lib
 
 
-def emu_quant(opts: QuantOpts, tid_to_gid, batch: CellBatch, use_na8: bool = False) -> QuantResult:
+def emu_quant(opts: QuantOpts, tid_to_gid, batch: CellBatch, use_na8: bool = False, use_pack24: bool = False) -> QuantResult:
     t2g = np.ascontiguousarray(tid_to_gid, dtype=np.uint32)
     cfg = opts.to_c()
-    cb = batch.to_c(use_na8)
+    cb = batch.to_c(use_na8, use_pack24)
     r = AfqResult()
     h = C.c_void_p()
     err = C.create_string_buffer(512)

@@ -25,12 +25,12 @@ def test_header_symbols_all_exported_and_bound():
     for n in names:
         assert hasattr(l, n), f"libafq.so does not export {n}"
         assert n in _abi.SYMBOLS, f"{n} missing from the ctypes binding table"
-    assert l.afq_abi_version() == 1
+    assert l.afq_abi_version() == 2
 
 
 def test_struct_sizes_match_header_layout():
     assert C.sizeof(_abi.AfqConfig) == 56
-    assert C.sizeof(_abi.AfqBatch) == 72
+    assert C.sizeof(_abi.AfqBatch) == 88
     assert C.sizeof(_abi.AfqResult) == 80
     assert C.sizeof(_abi.AfqDeviceOut) == 80
 

@@ -127,3 +127,25 @@ def test_emu_na8_compact_offsets():
         assert np.array_equal(got.row_ptr, want.row_ptr) and np.array_equal(got.col, want.col) and np.array_equal(got.val, want.val)
     with pytest.raises(ValueError):
         CellBatch.from_cells([[(1, list(range(300)))]]).na8()
+
+
+def test_emu_pack24_wire_arrays():
+    # afq_batch.rec_umi24 / refs24: 3-byte UMIs and transcript ids widened on the device (k_unpack24);
+    # record / ref counts that are not multiples of 4 exercise the tail path
+    spec = synth.SynthSpec(reads_mean=700.0)
+    t2g = synth.tid_to_gid(spec)
+    for ncell in (1, 7):
+        b = synth.generate(spec, 5, ncell)
+        for res in ("cr-like", "parsimony-em"):
+            o = opts_for(spec, res)
+            got = emu_lib.emu_quant(o, t2g, b, use_na8=True, use_pack24=True)
+            want = emu_lib.emu_quant(o, t2g, b)
+            assert np.array_equal(got.row_ptr, want.row_ptr) and np.array_equal(got.col, want.col) and np.array_equal(got.val, want.val)
+    tiny = CellBatch.from_cells([[(0xABCDEF, [5, 0xFFFFFF % len(t2g)]), (3, [1]), (0xFFFFFF, [2, 3, 4])]])
+    u24, r24 = tiny.pack24()
+    assert bytes(u24[:9]) == bytes([0xEF, 0xCD, 0xAB, 3, 0, 0, 0xFF, 0xFF, 0xFF])
+    o = opts_for(spec, "cr-like")
+    got, want = emu_lib.emu_quant(o, t2g, tiny, use_pack24=True), emu_lib.emu_quant(o, t2g, tiny)
+    assert np.array_equal(got.col, want.col) and np.array_equal(got.val, want.val)
+    with pytest.raises(ValueError):
+        CellBatch.from_cells([[(1 << 24, [1])]]).pack24()

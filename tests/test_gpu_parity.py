@@ -171,4 +171,9 @@ def test_na8_compact_offsets_match():
         with Quantifier(o, t2g) as q:
             a1 = q.quantify_batch(b)
             a2 = q.quantify_batch(b, use_na8=True)
+            a3 = q.quantify_batch(b, use_na8=True, use_pack24=True)   # + 24-bit UMIs / transcript ids
+            a4 = q.quantify_batch(b.slice_cells(0, 3), use_pack24=True)
+            a5 = q.quantify_batch(b.slice_cells(0, 3))
         assert np.array_equal(a1.row_ptr, a2.row_ptr) and np.array_equal(a1.col, a2.col) and np.array_equal(a1.val, a2.val)
+        assert np.array_equal(a1.row_ptr, a3.row_ptr) and np.array_equal(a1.col, a3.col) and np.array_equal(a1.val, a3.val)
+        assert np.array_equal(a4.row_ptr, a5.row_ptr) and np.array_equal(a4.col, a5.col) and np.array_equal(a4.val, a5.val)
