@@ -135,6 +135,7 @@ struct CellArena {
   u32* boff;   // [NB+1]
   u32* bdo;    // [NB+1]
   u32 log2cap, nb_log2;
+  bool smem;   // keys/cnts live in shared memory (the presence-bitmap form needs that)
 };
 
 __device__ __forceinline__ u32 umi_home(u32 umi, u32 log2cap) { return (umi * 0x9E3779B1u) >> (32 - log2cap); }
@@ -172,11 +173,73 @@ __device__ inline bool resolve_cell(const KArgs& a, u32 cell, const CellArena& A
   const u64 r0 = a.cell_rec_off[cell], r1 = a.cell_rec_off[cell + 1];
   const u32 nrec = (u32)(r1 - r0);
   for (u32 i = tid; i < cap; i += T) { A.keys[i] = EMPTY_KEY; A.cnts[i] = 0; }
-  for (u32 i = tid; i < NB; i += T) A.bcnt[i] = 0;
   if (tid == 0) { sh->distinct = 0; sh->abort = 0; sh->red_max = 0; sh->red_cnt = 0; sh->nwin = 0; sh->nbig = 0; }
   __syncthreads();
 
   // ---- phase 1: records -> distinct (umi, gene) pairs with read counts --------------------
+  // Flat form (one lane per ALIGNMENT, not per record): alignment counts vary from 1 to dozens,
+  // so a lane-per-record loop runs at the warp's longest record with most lanes idle (ncu r1d:
+  // 9.7 active lanes per instruction). Record heads are marked in a bitmap over the cell's refs,
+  // a lane finds its record by rank (prefix popcount) and the record's first ref by the highest
+  // head bit at or below it; a ref is inserted iff no earlier ref of its record maps to the same
+  // gene (src/pugutils.rs:774-781, 817-829: sorted-dedup gene projection). The bitmap and ranks
+  // live in the (still unused) bucket area. Cells with an alignment-free record, the `trivial`
+  // resolution and cells whose refs overflow the bitmap take the lane-per-record form below.
+  const u64 f0 = a.ref_off[r0];
+  const u32 P = (u32)(a.ref_off[r1] - f0);
+  const u32 W = (P >> 5) + 1;                       // bitmap words
+  u32* hb = A.bcnt;                                 // [W] record-head bits
+  u32* hr = A.bcnt + W;                             // [W] heads before word w
+  bool flat = a.mode != MODE_TRIVIAL && 2 * W <= 3 * NB && P > 0;
+  if (flat) {
+    for (u32 i = tid; i < W; i += T) hb[i] = 0;
+    if (tid == 0) sh->nbig = 0;                     // "some record has no alignment"
+    __syncthreads();
+    for (u32 i = tid; i < nrec; i += T) {
+      const u32 o0 = a.ref_off[r0 + i] - (u32)f0, o1 = a.ref_off[r0 + i + 1] - (u32)f0;
+      if (o1 > o0) atomicOr(&hb[o0 >> 5], 1u << (o0 & 31));
+      else sh->nbig = 1;
+    }
+    __syncthreads();
+    flat = sh->nbig == 0;
+    u32 run = 0;
+    for (u32 c0 = 0; c0 < W; c0 += T) {
+      const u32 i = c0 + tid;
+      const u32 v = i < W ? (u32)__popc(hb[i]) : 0u;
+      u32 tot;
+      const u32 ex = block_exscan(v, sh->scan, &tot);
+      if (i < W) hr[i] = run + ex;
+      run += tot;
+      __syncthreads();
+    }
+    if (tid == 0) sh->nbig = 0;
+  }
+  if (flat) {
+    for (u32 base = 0; base < P; base += T) {
+      // every lane runs the same control flow (inactive lanes are predicated off) and the warp
+      // reconverges before the insert: lanes leave the dedup loop at different trip counts and
+      // would otherwise run the whole probe sequence a few lanes at a time (ncu r1l: 3 lanes)
+      const u32 i = base + tid;
+      const bool act = i < P;
+      bool ins = false;
+      u32 g = 0, umi = 0;
+      if (act) {
+        g = __ldg(a.t2g + a.refs[f0 + i]);
+        const u32 w = i >> 5;
+        const u32 below = hb[w] & (0xFFFFFFFFu >> (31 - (i & 31)));   // heads at or below i in its word
+        umi = a.umi[r0 + hr[w] + (u32)__popc(below) - 1];
+        u32 start;
+        if (below) start = (w << 5) + 31 - (u32)__clz((int)below);
+        else { u32 ww = w - 1; while (hb[ww] == 0) --ww; start = (ww << 5) + 31 - (u32)__clz((int)hb[ww]); }
+        ins = true;
+        for (u32 j = start; j < i; ++j)
+          if (__ldg(a.t2g + a.refs[f0 + j]) == g) { ins = false; break; }
+      }
+      __syncwarp();
+      if (ins && !*(volatile u32*)&sh->abort) table_insert<LIST>(A, umi, g, limit, sh);
+      __syncwarp();
+    }
+  } else
   for (u32 base = 0; base < nrec; base += T) {
     __syncwarp();
     const u32 i = base + tid;
@@ -208,6 +271,7 @@ __device__ inline bool resolve_cell(const KArgs& a, u32 cell, const CellArena& A
   if (sh->abort) { __syncthreads(); return false; }
   const u32 d = sh->distinct;
   const u32 N = LIST ? d : cap;   // work items of phases 2-4: list entries or table slots
+  for (u32 i = tid; i < NB; i += T) A.bcnt[i] = 0;   // (the bucket area held phase 1's bitmap)
 
   // ---- phase 2: per UMI (cluster leader) the arg-max gene set -> output slot, into cnts ----
   // A leader only writes cnts of entries of its own UMI and every entry's count is read by exactly
@@ -215,29 +279,36 @@ __device__ inline bool resolve_cell(const KArgs& a, u32 cell, const CellArena& A
   for (u32 base = 0; base < N; base += T) {
     __syncwarp();
     const u32 i = base + tid;
-    if (i >= N) continue;
-    const u32 s = LIST ? A.list[i] : i;
-    const u64 key = A.keys[s];
-    if (!LIST && key == EMPTY_KEY) { A.cnts[s] = NONE32; continue; }
-    if (a.mode == MODE_TRIVIAL) { A.cnts[s] = (u32)key; continue; }  // every distinct (gene, umi) counts
-    const u32 u = (u32)(key >> 32);
-    bool leader = true;
-    for (u32 t = umi_home(u, A.log2cap); t != s; t = (t + 1) & mask)
-      if ((u32)(A.keys[t] >> 32) == u) { leader = false; break; }
-    if (!leader) continue;               // retired by its leader
-    u32 maxw = 0, nb = 0;
+    bool leader = false;
+    u32 s = 0, u = 0;
+    if (i < N) {
+      s = LIST ? A.list[i] : i;
+      const u64 key = A.keys[s];
+      if (!LIST && key == EMPTY_KEY) A.cnts[s] = NONE32;
+      else if (a.mode == MODE_TRIVIAL) A.cnts[s] = (u32)key;   // every distinct (gene, umi) counts
+      else {
+        u = (u32)(key >> 32);
+        leader = true;
+        for (u32 t = umi_home(u, A.log2cap); t != s; t = (t + 1) & mask)
+          if ((u32)(A.keys[t] >> 32) == u) { leader = false; break; }   // retired by its leader
+      }
+    }
+    __syncwarp();   // leaders start their cluster scan together
+    if (!leader) continue;
+    u32 maxw = 0, nb = 0, b0 = 0;
     u32 best[10];
+    const bool usa = a.usa_mode != 0;
     for (u32 t = s;; t = (t + 1) & mask) {
       const u64 kt = A.keys[t];
       if (kt == EMPTY_KEY) break;
       if ((u32)(kt >> 32) != u) continue;
       const u32 w = A.cnts[t];
-      if (w > maxw) { maxw = w; nb = 1; best[0] = (u32)kt; }
-      else if (w == maxw) { if (nb < 10) best[nb] = (u32)kt; ++nb; }
+      if (w > maxw) { maxw = w; nb = 1; b0 = (u32)kt; if (usa) best[0] = (u32)kt; }
+      else if (w == maxw) { if (usa && nb < 10) best[nb] = (u32)kt; ++nb; }
       if (t != s) A.cnts[t] = NONE32;
     }
     u32 res = NONE32;
-    if (!a.usa_mode) { if (nb == 1) res = best[0]; }
+    if (!usa) { if (nb == 1) res = b0; }
     else if (nb <= 10) {
       for (u32 q = 1; q < nb; ++q) { const u32 x = best[q]; u32 j = q; while (j > 0 && best[j - 1] > x) { best[j] = best[j - 1]; --j; } best[j] = x; }
       res = usa_slot_for_label(best, nb, a.uo, a.ao);
@@ -246,6 +317,54 @@ __device__ inline bool resolve_cell(const KArgs& a, u32 cell, const CellArena& A
   }
   __syncthreads();
 
+  const u64 out_base = a.ref_off[r0];             // this cell's staging rows start at its first ref
+  u32 m = 0, nnz = 0, lmax = 0;
+  // ---- phases 3-4, presence-bitmap form: one bit per output slot over the dead key area ---------
+  // winners set their slot's bit; a prefix popcount over the bitmap words ranks every expressed slot
+  // (ascending = the CSR column order), and each winner bumps the counter at its slot's rank.
+  // Flat and warp-uniform: every loop runs one lane per winner or per bitmap word. Needs
+  // 2 * ceil(num_rows / 32) + distinct words in the key area; other cells use the forms below.
+  const u32 Wg = (a.num_rows + 31) >> 5;
+  const bool bm_path = A.smem && d > RANK_SORT_MAX && (u64)2 * Wg + d <= (u64)2 * cap;
+  if (bm_path) {
+    u32* gbm = reinterpret_cast<u32*>(A.keys);     // [Wg] slot presence
+    u32* gpre = gbm + Wg;                          // [Wg] expressed slots before word w
+    u32* gcnt = gpre + Wg;                         // [nnz] molecules per expressed slot
+    for (u32 i = tid; i < Wg; i += T) gbm[i] = 0;
+    __syncthreads();
+    u32 local_m = 0;
+    for (u32 i = tid; i < N; i += T) {
+      const u32 v = A.cnts[LIST ? A.list[i] : i];
+      if (v != NONE32) { atomicOr(&gbm[v >> 5], 1u << (v & 31)); ++local_m; }
+    }
+    if (local_m) atomicAdd(&sh->nwin, local_m);
+    __syncthreads();
+    m = sh->nwin;
+    for (u32 c0 = 0; c0 < Wg; c0 += T) {
+      const u32 i = c0 + tid;
+      const u32 v = i < Wg ? (u32)__popc(gbm[i]) : 0u;
+      u32 tot;
+      const u32 ex = block_exscan(v, sh->scan, &tot);
+      if (i < Wg) gpre[i] = nnz + ex;
+      nnz += tot;
+      __syncthreads();
+    }
+    for (u32 i = tid; i < nnz; i += T) gcnt[i] = 0;
+    __syncthreads();
+    for (u32 i = tid; i < N; i += T) {
+      const u32 v = A.cnts[LIST ? A.list[i] : i];
+      if (v != NONE32) {
+        const u32 rank = gpre[v >> 5] + (u32)__popc(gbm[v >> 5] & ((1u << (v & 31)) - 1u));
+        if (atomicAdd(&gcnt[rank], 1u) == 0) a.stage_col[out_base + rank] = v;
+      }
+    }
+    __syncthreads();
+    for (u32 j = tid; j < nnz; j += T) {
+      const u32 c = gcnt[j];
+      a.stage_val[out_base + j] = (float)c;
+      lmax = c > lmax ? c : lmax;
+    }
+  } else {
   // ---- phase 3: count winners; bucket histogram ----------------------------------------------
   const u32 bits = 32 - __clz((int)(a.num_rows > 1 ? a.num_rows - 1 : 1));
   const u32 shift = bits > A.nb_log2 ? bits - A.nb_log2 : 0;   // bucket = slot >> shift < NB
@@ -258,11 +377,9 @@ __device__ inline bool resolve_cell(const KArgs& a, u32 cell, const CellArena& A
   }
   if (local_m) atomicAdd(&sh->nwin, local_m);
   __syncthreads();
-  const u32 m = sh->nwin;
+  m = sh->nwin;
   u32* sorted = reinterpret_cast<u32*>(A.keys);   // winners, over the dead key area
   u32* tmp = sorted + cap;
-  const u64 out_base = a.ref_off[r0];             // this cell's staging rows start at its first ref
-  u32 nnz = 0, lmax = 0;
   const bool rank_path = m <= RANK_SORT_MAX || shift > 8;
 
   if (rank_path) {
@@ -402,6 +519,7 @@ __device__ inline bool resolve_cell(const KArgs& a, u32 cell, const CellArena& A
       }
     }
   }
+  }  // !bm_path
   if (tid == 0) sh->red_cnt = 0;
   if (lmax) atomicMax(&sh->red_max, lmax);
   __syncthreads();
@@ -444,6 +562,7 @@ __global__ void __launch_bounds__(bin_threads(BIN), bin_min_blocks(BIN)) k_resol
   A.bdo = A.boff + NB + 1;
   A.log2cap = LOG2CAP;
   A.nb_log2 = bin_buckets_log2(BIN);
+  A.smem = true;
   __shared__ CellShared sh;
   const u32 count = a.ctl->bin_count[BIN];
   const u32* list = a.bin_list + (u64)BIN * a.n_cells;
@@ -479,6 +598,7 @@ __global__ void __launch_bounds__(1024) k_resolve_large(KArgs a, u32 list_id) {
   A.boff = A.bcnt + 1024;
   A.bdo = A.boff + 1025;
   A.nb_log2 = 10;
+  A.smem = false;
   const u32 count = a.ctl->bin_count[list_id];
   const u32* list = a.bin_list + (u64)list_id * a.n_cells;
   for (;;) {

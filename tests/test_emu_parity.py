@@ -149,3 +149,34 @@ def test_emu_pack24_wire_arrays():
     assert np.array_equal(got.col, want.col) and np.array_equal(got.val, want.val)
     with pytest.raises(ValueError):
         CellBatch.from_cells([[(1 << 24, [1])]]).pack24()
+
+
+def _wide_cells(rng, n_cells, n_rec, na_lo, na_hi, n_tx, n_umi, p_empty=0.0):
+    cells = []
+    for _ in range(n_cells):
+        recs = []
+        for _ in range(n_rec):
+            if rng.random() < p_empty:
+                recs.append((int(rng.integers(n_umi)), []))
+                continue
+            na = int(rng.integers(na_lo, na_hi + 1))
+            refs = np.sort(rng.choice(n_tx, size=min(na, n_tx), replace=False))
+            recs.append((int(rng.integers(n_umi)), [int(x) for x in refs]))
+        cells.append(recs)
+    return cells
+
+
+@pytest.mark.parametrize("res", ["cr-like", "trivial", "cr-like-em"])
+def test_emu_flat_alignment_loop_shapes(res):
+    # phase 1 of the resolve runs one lane per alignment: records wider than a bitmap word (head
+    # search walks back), a NON-monotone tid->gid map (duplicate genes far apart inside a record),
+    # records without alignments and cells whose refs overflow the bitmap (lane-per-record form)
+    rng = np.random.default_rng(7)
+    n_tx, n_genes = 400, 37
+    t2g = rng.integers(0, n_genes, size=n_tx).astype(np.uint32)
+    cells = (_wide_cells(rng, 2, 150, 30, 80, n_tx, 40) +            # wide records, flat form
+             _wide_cells(rng, 2, 300, 1, 6, n_tx, 60) +               # narrow records
+             _wide_cells(rng, 1, 120, 60, 90, n_tx, 30) +             # refs overflow the smallest arena's bitmap
+             _wide_cells(rng, 2, 200, 1, 5, n_tx, 50, p_empty=0.1))   # alignment-free records
+    b = CellBatch.from_cells(cells)
+    check(QuantOpts(resolution=res, num_gene_ids=n_genes, num_rows=n_genes), t2g, b, res)

@@ -177,3 +177,19 @@ def test_na8_compact_offsets_match():
         assert np.array_equal(a1.row_ptr, a2.row_ptr) and np.array_equal(a1.col, a2.col) and np.array_equal(a1.val, a2.val)
         assert np.array_equal(a1.row_ptr, a3.row_ptr) and np.array_equal(a1.col, a3.col) and np.array_equal(a1.val, a3.val)
         assert np.array_equal(a4.row_ptr, a5.row_ptr) and np.array_equal(a4.col, a5.col) and np.array_equal(a4.val, a5.val)
+
+
+@pytest.mark.parametrize("res", ["cr-like", "trivial", "cr-like-em"])
+def test_flat_alignment_loop_shapes(res):
+    # lane-per-alignment phase 1: wide records, non-monotone tid->gid, alignment-free records,
+    # bitmap overflow (same cases as tests/test_emu_parity.py::test_emu_flat_alignment_loop_shapes)
+    from test_emu_parity import _wide_cells
+    rng = np.random.default_rng(7)
+    n_tx, n_genes = 400, 37
+    t2g = rng.integers(0, n_genes, size=n_tx).astype(np.uint32)
+    cells = (_wide_cells(rng, 2, 150, 30, 80, n_tx, 40) + _wide_cells(rng, 2, 300, 1, 6, n_tx, 60) +
+             _wide_cells(rng, 1, 120, 60, 90, n_tx, 30) + _wide_cells(rng, 2, 200, 1, 5, n_tx, 50, p_empty=0.1) +
+             _wide_cells(rng, 1, 3000, 1, 9, n_tx, 700) + _wide_cells(rng, 1, 9000, 1, 4, n_tx, 3000))
+    b = CellBatch.from_cells(cells)
+    o = QuantOpts(resolution=res, num_gene_ids=n_genes, num_rows=n_genes)
+    assert_same(gpu_quant(o, t2g, b), oracle_lib.oracle_quant(o, t2g, b), exact=True, ctx="flat/" + res)
