@@ -103,15 +103,19 @@ __global__ void k_bin_cells(KArgs a, int force_bin, u32 need_shift) {
 }
 
 // ------------------------------------------------------------------------------------
-// Per-cell resolve, version 3.
-//  * One open-address table hashed by the UMI ALONE holds the distinct (umi, gene) keys with read
-//    counts, so all genes of a UMI sit in one probe cluster; the cluster's first entry ("leader")
-//    scans to the cluster end and computes the arg-max gene set directly: no sort of the pairs.
+// Per-cell resolve.
+//  * Phase 1 runs one lane per ALIGNMENT (not per record): a head bitmap over the cell's refs plus
+//    word ranks give every lane its record; the warp reconverges before the table insert.
+//  * One open-address table holds the distinct (umi, gene) keys with read counts; a pair starts
+//    probing at home(umi) + (gene mod UMI_WINDOW), so a UMI's genes share a small window (plus the
+//    occupied run behind it). The UMI's first entry from home ("leader") scans that window and
+//    computes the arg-max gene set directly: no sort of the pairs.
 //  * Every new entry's slot is appended to a dense list, so the later phases run over dense work
 //    (bins 0-3; the two largest arenas iterate over slots instead to stay within shared memory).
-//  * Winner slots are ordered by bucket (slot >> shift): one thread per bucket derives the
-//    distinct slots from a <= 256-bit presence mask and counts them — no per-bucket sort; hot
-//    buckets are counted by the whole CTA. Small cells rank-sort their winners instead.
+//  * Counting: a presence bitmap over the output slots (in the dead key area) ranks the expressed
+//    slots by prefix popcount and each winner bumps its slot's counter — flat, no sort. Cells whose
+//    gene axis does not fit the key area order winners by bucket (slot >> shift) with per-bucket
+//    presence masks; small cells rank-sort their winners.
 //  * The record / entry / bucket loops are warp-uniform with an explicit __syncwarp() so that lanes
 //    reconverge every iteration (ncu r1c: 7.5 active lanes/instruction without it). Fully
 //    lock-stepped (vote-driven) probe loops were measured and are slower (r1e: +70 % warp
@@ -139,28 +143,46 @@ struct CellArena {
 };
 
 __device__ __forceinline__ u32 umi_home(u32 umi, u32 log2cap) { return (umi * 0x9E3779B1u) >> (32 - log2cap); }
+// A pair starts probing at its UMI's home slot plus a gene-dependent offset inside a small window:
+// the genes of one UMI spread over UMI_WINDOW start slots instead of queueing behind each other
+// (ncu r1l: a multi-gene record's k-th gene needed k probes, so every warp ran the probe loop
+// 6-7 times with ~4 lanes). Invariant after phase 1: an entry of UMI u placed at slot p started
+// at home(u)+o (o < UMI_WINDOW) and every slot of [home(u)+o, p] is occupied — so all entries of
+// u lie in the fixed window [home, home+UMI_WINDOW) or in the occupied run that continues it.
+#ifndef AFQ_UMI_WINDOW
+#define AFQ_UMI_WINDOW 8
+#endif
+constexpr u32 UMI_WINDOW = AFQ_UMI_WINDOW;   // power of two; 1 = plain per-UMI clusters
 
-// insert-or-increment (umi, gene); the probe sequence depends on the UMI only
-template <bool LIST>
-__device__ __forceinline__ void table_insert(const CellArena& A, u32 umi, u32 gene, u32 limit, CellShared* sh) {
+// insert-or-increment (umi, gene). The probe loop only FINDS the slot; the counter bump and the
+// new-entry bookkeeping sit behind the loop, where the warp has reconverged, so they issue once per
+// call instead of once per probe round (ncu r1m: they ran ~6 times per warp at 4-6 lanes).
+// CONV: every lane of the warp calls (lanes with nothing to insert pass on = false) and the warp is
+// explicitly re-joined behind the probe loop.
+template <bool LIST, bool CONV = false>
+__device__ __forceinline__ void table_insert(const CellArena& A, u32 umi, u32 gene, u32 limit, CellShared* sh, bool on = true) {
   const u32 mask = (1u << A.log2cap) - 1;
   const u64 key = ((u64)umi << 32) | gene;
-  u32 s = umi_home(umi, A.log2cap);
-  for (u32 probes = 0; probes <= mask; ++probes) {
+  u32 s = (umi_home(umi, A.log2cap) + (gene & (UMI_WINDOW - 1))) & mask;
+  bool created = false, found = !on;
+  if (on) for (u32 probes = 0; probes <= mask; ++probes) {
     u64 cur = A.keys[s];
     if (cur == EMPTY_KEY) {
       cur = atomicCAS((unsigned long long*)&A.keys[s], (unsigned long long)EMPTY_KEY, (unsigned long long)key);
-      if (cur == EMPTY_KEY) {
-        const u32 idx = atomicAdd(&sh->distinct, 1u);
-        if (idx >= limit) { sh->abort = 1; return; }
-        if (LIST) A.list[idx] = s;
-        cur = key;
-      }
+      if (cur == EMPTY_KEY) { created = true; found = true; break; }
     }
-    if (cur == key) { atomicAdd(&A.cnts[s], 1u); return; }
+    if (cur == key) { found = true; break; }
     s = (s + 1) & mask;
   }
-  sh->abort = 1;  // table full (only reachable after the distinct limit was crossed)
+  if (CONV) __syncwarp();
+  if (!on) return;
+  if (!found) { sh->abort = 1; return; }   // table full (only reachable after the distinct limit was crossed)
+  atomicAdd(&A.cnts[s], 1u);
+  if (created) {
+    const u32 idx = atomicAdd(&sh->distinct, 1u);
+    if (idx >= limit) { sh->abort = 1; return; }
+    if (LIST) A.list[idx] = s;
+  }
 }
 
 // Returns false when the distinct-pair count exceeded `limit` (caller re-queues the cell on a
@@ -223,21 +245,29 @@ __device__ inline bool resolve_cell(const KArgs& a, u32 cell, const CellArena& A
       const bool act = i < P;
       bool ins = false;
       u32 g = 0, umi = 0;
+      if (act) g = __ldg(a.t2g + a.refs[f0 + i]);
+      // the three lanes below hold the genes of refs i-1..i-3 (tiles are warp-aligned): records with
+      // up to four alignments are de-duplicated without touching memory again
+      const u32 g1 = __shfl_up_sync(0xFFFFFFFFu, g, 1), g2 = __shfl_up_sync(0xFFFFFFFFu, g, 2),
+                g3 = __shfl_up_sync(0xFFFFFFFFu, g, 3);
       if (act) {
-        g = __ldg(a.t2g + a.refs[f0 + i]);
-        const u32 w = i >> 5;
+        const u32 w = i >> 5, lane = tid & 31;
         const u32 below = hb[w] & (0xFFFFFFFFu >> (31 - (i & 31)));   // heads at or below i in its word
         umi = a.umi[r0 + hr[w] + (u32)__popc(below) - 1];
         u32 start;
         if (below) start = (w << 5) + 31 - (u32)__clz((int)below);
         else { u32 ww = w - 1; while (hb[ww] == 0) --ww; start = (ww << 5) + 31 - (u32)__clz((int)hb[ww]); }
+        const u32 back = i - start;          // refs of this record before this one
         ins = true;
-        for (u32 j = start; j < i; ++j)
-          if (__ldg(a.t2g + a.refs[f0 + j]) == g) { ins = false; break; }
+        for (u32 k = 1; k <= back; ++k) {
+          u32 gk;
+          if (k <= 3 && lane >= k) gk = k == 1 ? g1 : (k == 2 ? g2 : g3);
+          else gk = __ldg(a.t2g + a.refs[f0 + i - k]);
+          if (gk == g) { ins = false; break; }
+        }
       }
       __syncwarp();
-      if (ins && !*(volatile u32*)&sh->abort) table_insert<LIST>(A, umi, g, limit, sh);
-      __syncwarp();
+      table_insert<LIST, true>(A, umi, g, limit, sh, ins && !*(volatile u32*)&sh->abort);
     }
   } else
   for (u32 base = 0; base < nrec; base += T) {
@@ -289,8 +319,10 @@ __device__ inline bool resolve_cell(const KArgs& a, u32 cell, const CellArena& A
       else {
         u = (u32)(key >> 32);
         leader = true;
-        for (u32 t = umi_home(u, A.log2cap); t != s; t = (t + 1) & mask)
-          if ((u32)(A.keys[t] >> 32) == u) { leader = false; break; }   // retired by its leader
+        for (u32 t = umi_home(u, A.log2cap); t != s; t = (t + 1) & mask) {   // leader = first entry of u from home
+          const u64 kt = A.keys[t];
+          if (kt != EMPTY_KEY && (u32)(kt >> 32) == u) { leader = false; break; }   // retired by its leader
+        }
       }
     }
     __syncwarp();   // leaders start their cluster scan together
@@ -298,9 +330,9 @@ __device__ inline bool resolve_cell(const KArgs& a, u32 cell, const CellArena& A
     u32 maxw = 0, nb = 0, b0 = 0;
     u32 best[10];
     const bool usa = a.usa_mode != 0;
-    for (u32 t = s;; t = (t + 1) & mask) {
+    for (u32 t = s, dist = (s - umi_home(u, A.log2cap)) & mask; dist <= mask; t = (t + 1) & mask, ++dist) {
       const u64 kt = A.keys[t];
-      if (kt == EMPTY_KEY) break;
+      if (kt == EMPTY_KEY) { if (dist >= UMI_WINDOW) break; continue; }   // holes only inside the window
       if ((u32)(kt >> 32) != u) continue;
       const u32 w = A.cnts[t];
       if (w > maxw) { maxw = w; nb = 1; b0 = (u32)kt; if (usa) best[0] = (u32)kt; }

@@ -390,29 +390,53 @@ __device__ __forceinline__ bool out_edge(u32 hd, u32 cx, u32 cy) {
 constexpr u32 GE_BITMAP_LOG2 = 17;                       // 128 Kbit = 16 KB of the staged-sort scratch
 __device__ __forceinline__ u32 umi_bit(u32 umi) { return (umi * 0x9E3779B1u) >> (32 - GE_BITMAP_LOG2); }
 
-// PUG neighbours of vertex v through candidate k (k == 0: v's own UMI, hd = 0; k >= 1: one of the
-// 3*umi_len single-base substitutions, hd = 1): every vertex w != v carrying that UMI whose class
-// label shares a reference with v's. f(w, hd) is called once per neighbour. The (v, k) items are
-// the unit of parallel work.
+__device__ __forceinline__ u32 umi_bit2(u32 umi) { return ((umi ^ (umi >> 15)) * 0x85EBCA6Bu) >> (32 - GE_BITMAP_LOG2); }
+__device__ __forceinline__ bool umi_maybe_present(const u32* bitmap, u32 umi) {   // 2-hash Bloom test
+  const u32 b1 = umi_bit(umi), b2 = umi_bit2(umi);
+  return ((bitmap[b1 >> 5] >> (b1 & 31)) & (bitmap[b2 >> 5] >> (b2 & 31)) & 1u) != 0;
+}
+
+// every vertex w != v carrying UMI cu whose class label shares a reference with class cv
 template <class F>
-__device__ __forceinline__ void visit_candidate(const GeCell& c, u32 v, u32 k, u32 utab_mask, u32 utab_log2, const u32* bitmap, F f) {
-  const u32 u = c.v_umi(v);
-  u32 cu = u, hd = 0;
-  if (k > 0) {
-    const u32 pos = (k - 1) / 3, d = 1 + (k - 1) % 3;
-    cu = u ^ (d << (2 * pos));
-    hd = 1;
-  }
-  const u32 bit = umi_bit(cu);
-  if (!(bitmap[bit >> 5] >> (bit & 31) & 1u)) return;
+__device__ __forceinline__ void visit_umi(const GeCell& c, u32 v, u32 cv, u32 cu, u32 utab_mask, u32 utab_log2, F f) {
   const u32 s = tab_find(c.p.ctab_h, utab_mask, utab_log2, (u64)cu);
   if (s == NONE32) return;
-  const u32 cv = c.v_cls(v);
   for (u32 w = c.p.ctab_r[s]; w != NONE32; w = c.p.vnext[w]) {
     if (w == v) continue;
     const u32 cw = c.v_cls(w);
     if (cw != cv && !sorted_share(c.cls_lab(cv), c.cls_lab_len(cv), c.cls_lab(cw), c.cls_lab_len(cw))) continue;
-    f(w, hd);
+    f(w);
+  }
+}
+
+// PUG neighbours of every vertex v with want(v): f(v, w, hd) once per neighbour w — hd = 0 through
+// v's own UMI, hd = 1 through one of its 3*umi_len single-base substitutions (umi_len == 0:
+// --umi-edit-dist 0, own UMI only). One lane per VERTEX in both passes (ncu r1m: with a warp per
+// vertex and lanes over the candidates, the own-UMI chain walk — the bulk of the edges — ran on
+// one lane of the warp, a quarter of the kernel's instructions at 1 active lane):
+//   pass A walks the chain of the vertex's own UMI;
+//   pass B lets all lanes test the SAME substitution of their own vertex's UMI against a 2-hash
+//   Bloom bitmap of the cell's UMIs in shared memory (a hit is rare) and re-joins the warp after
+//   every candidate.
+template <class Want, class F>
+__device__ __forceinline__ void visit_neighbours(const GeCell& c, u32 V, u32 umi_len, u32 utab_mask, u32 utab_log2,
+                                                 const u32* bitmap, Want want, F f) {
+  const u32 T = blockDim.x, tid = threadIdx.x;
+  GE_FOR(v, V) {
+    if (want(v)) visit_umi(c, v, c.v_cls(v), c.v_umi(v), utab_mask, utab_log2, [&](u32 w) { f(v, w, 0u); });
+  }
+  if (umi_len == 0) return;
+  for (u32 vb = 0; vb < V; vb += T) {
+    const u32 v = vb + tid;
+    const bool act = v < V && want(v);
+    const u32 u = act ? c.v_umi(v) : 0u, cv = act ? c.v_cls(v) : 0u;
+    for (u32 pos = 0; pos < umi_len; ++pos)
+      for (u32 d = 1; d <= 3; ++d) {
+        const u32 cu = u ^ (d << (2 * pos));
+        const bool hit = act && umi_maybe_present(bitmap, cu);
+        __syncwarp();
+        if (hit) visit_umi(c, v, cv, cu, utab_mask, utab_log2, [&](u32 w) { f(v, w, 1u); });
+      }
   }
 }
 
@@ -885,27 +909,18 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
       p.parent[v] = v;
       p.adj_off[v] = 0;
       p.vlab_off[v] = 0;      // fill cursor of the adjacency pass below
-      const u32 bit = umi_bit(um);
+      const u32 bit = umi_bit(um), bit2 = umi_bit2(um);
       atomicOr(&bitmap[bit >> 5], 1u << (bit & 31));
+      atomicOr(&bitmap[bit2 >> 5], 1u << (bit2 & 31));
     }
     __syncthreads();
 
     // ---------------- phase 4: out-degrees + union-find, then adjacency fill --------------------
-    // one warp per vertex, lanes over the candidate UMIs; almost all are rejected by the bitmap
-    const u32 ncand = g.pug_exact_umi ? 1u : 1u + 3u * g.umi_len;
-    const u32 wid = tid >> 5, lane = tid & 31, nwarps = T >> 5;
-    for (u32 v = wid; v < V; v += nwarps) {   // v is warp-uniform
-      const u32 cx = c.v_cnt(v);
-      for (u32 k0 = 0; k0 < ncand; k0 += 32) {
-        __syncwarp();
-        const u32 k = k0 + lane;
-        if (k < ncand)
-          visit_candidate(c, v, k, mu, lu, bitmap, [&](u32 w, u32 hd) {
-            if (w > v) uf_union(p.parent, v, w);
-            if (out_edge(hd, cx, c.v_cnt(w))) atomicAdd(&p.adj_off[v], 1u);
-          });
-      }
-    }
+    const u32 sub_len = g.pug_exact_umi ? 0u : g.umi_len;
+    visit_neighbours(c, V, sub_len, mu, lu, bitmap, [](u32) { return true; }, [&](u32 v, u32 w, u32 hd) {
+      if (w > v) uf_union(p.parent, v, w);
+      if (out_edge(hd, c.v_cnt(v), c.v_cnt(w))) atomicAdd(&p.adj_off[v], 1u);
+    });
     __syncthreads();
     const u32 E = block_exscan_array(p.adj_off, p.adj_off, V, sh->scan);
     if (tid == 0) {
@@ -924,20 +939,11 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
       return;
     }
     const u64 adj_base = (u64)sh->adj_base_hi << 32 | sh->adj_base_lo;
-    if (E > 0) {
-      for (u32 v = wid; v < V; v += nwarps) {
-        if (p.adj_off[v + 1] == p.adj_off[v]) continue;   // warp-uniform: no out-edges to record
-        const u32 cx = c.v_cnt(v);
-        for (u32 k0 = 0; k0 < ncand; k0 += 32) {
-          __syncwarp();
-          const u32 k = k0 + lane;
-          if (k < ncand)
-            visit_candidate(c, v, k, mu, lu, bitmap, [&](u32 w, u32 hd) {
-              if (out_edge(hd, cx, c.v_cnt(w))) g.adj_pool[adj_base + p.adj_off[v] + atomicAdd(&p.vlab_off[v], 1u)] = w;
-            });
-        }
-      }
-    }
+    if (E > 0)
+      visit_neighbours(c, V, sub_len, mu, lu, bitmap, [&](u32 v) { return p.adj_off[v + 1] != p.adj_off[v]; },
+                       [&](u32 v, u32 w, u32 hd) {
+        if (out_edge(hd, c.v_cnt(v), c.v_cnt(w))) g.adj_pool[adj_base + p.adj_off[v] + atomicAdd(&p.vlab_off[v], 1u)] = w;
+      });
     __syncthreads();
     // ---------------- phase 5: components (sorted by root, members ascending) -------------------
     GE_FOR(v, V) p.ckey[v] = ((u64)uf_find(p.parent, v) << 32) | v;

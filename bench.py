@@ -308,8 +308,9 @@ def main():
     fam = {k: v for k, v in prof.items() if k.startswith(("k_resolve", "k_gene_eqc"))}
     fam_ms = sum(v[0] for v in fam.values()) / args.steps
     region = prof.get("resolve_region(wall)")
-    if region:  # arena kernels overlap on lanes: the family's device time is the wall time of the region
-        fam_ms = region[0] / args.steps
+    if region:  # arena kernels overlap on lanes: their device time is the wall time of the region;
+        # the gene-eq-class kernels (parsimony / EM resolutions) run behind it, one after the other
+        fam_ms = (region[0] + sum(v[0] for k, v in fam.items() if k.startswith("k_gene_eqc"))) / args.steps
     fam_launches = sum(v[1] for v in fam.values()) // max(args.steps, 1)
     abytes = algorithmic_bytes(batch, nnz)
     peak, peak_src = peak_hbm()

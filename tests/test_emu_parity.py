@@ -180,3 +180,15 @@ def test_emu_flat_alignment_loop_shapes(res):
              _wide_cells(rng, 2, 200, 1, 5, n_tx, 50, p_empty=0.1))   # alignment-free records
     b = CellBatch.from_cells(cells)
     check(QuantOpts(resolution=res, num_gene_ids=n_genes, num_rows=n_genes), t2g, b, res)
+
+
+@pytest.mark.parametrize("res", ["cr-like", "cr-like-em"])
+def test_emu_all_ones_umi_and_window_holes(res):
+    # a 16-base UMI of all T's is 0xFFFFFFFF, the high half of the table's EMPTY marker: the windowed
+    # probe layout leaves empty slots between a UMI's entries, which must not be mistaken for it
+    t2g = np.arange(64, dtype=np.uint32)
+    U = 0xFFFFFFFF
+    recs = [(U, [1])] * 3 + [(U, [7])] * 5 + [(U, [9])] * 5 + [(U - 1, [7])] * 2 + [(5, [3, 4, 12])] * 4 + [(6, [3])]
+    recs = recs * 6 + [(i * 2654435761 % (1 << 32), [i % 64]) for i in range(150)]
+    b = CellBatch.from_cells([recs, recs[::-1]])
+    check(QuantOpts(resolution=res, num_gene_ids=64, num_rows=64, umi_len=16), t2g, b, res)
