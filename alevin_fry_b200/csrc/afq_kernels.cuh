@@ -246,24 +246,31 @@ __device__ inline bool resolve_cell(const KArgs& a, u32 cell, const CellArena& A
       bool ins = false;
       u32 g = 0, umi = 0;
       if (act) g = __ldg(a.t2g + a.refs[f0 + i]);
-      // the three lanes below hold the genes of refs i-1..i-3 (tiles are warp-aligned): records with
-      // up to four alignments are de-duplicated without touching memory again
-      const u32 g1 = __shfl_up_sync(0xFFFFFFFFu, g, 1), g2 = __shfl_up_sync(0xFFFFFFFFu, g, 2),
-                g3 = __shfl_up_sync(0xFFFFFFFFu, g, 3);
+      const u32 lane = tid & 31;
+      const u32 g1 = __shfl_up_sync(0xFFFFFFFFu, g, 1);   // gene of ref i-1 (tiles are warp-aligned)
+      u32 back = 0;                                       // refs of this record before this one
+      bool inv = false;
       if (act) {
-        const u32 w = i >> 5, lane = tid & 31;
+        const u32 w = i >> 5;
         const u32 below = hb[w] & (0xFFFFFFFFu >> (31 - (i & 31)));   // heads at or below i in its word
         umi = a.umi[r0 + hr[w] + (u32)__popc(below) - 1];
         u32 start;
         if (below) start = (w << 5) + 31 - (u32)__clz((int)below);
         else { u32 ww = w - 1; while (hb[ww] == 0) --ww; start = (ww << 5) + 31 - (u32)__clz((int)hb[ww]); }
-        const u32 back = i - start;          // refs of this record before this one
-        ins = true;
-        for (u32 k = 1; k <= back; ++k) {
-          u32 gk;
-          if (k <= 3 && lane >= k) gk = k == 1 ? g1 : (k == 2 ? g2 : g3);
-          else gk = __ldg(a.t2g + a.refs[f0 + i - k]);
-          if (gk == g) { ins = false; break; }
+        back = i - start;
+        inv = back >= 1 && lane >= 1 && g1 > g;
+      }
+      // Transcript ids ascend inside a record, and gene ids usually ascend with them: when no lane of
+      // the warp sees a gene id drop, a ref repeats an earlier gene of its record iff it repeats its
+      // predecessor's. Records that began in an earlier tile, and warps that do see a drop (arbitrary
+      // tid -> gid maps), compare against every earlier ref of the record instead.
+      const bool ascending = !__any_sync(0xFFFFFFFFu, inv);
+      if (act) {
+        if (ascending && back <= lane) ins = !(back >= 1 && g1 == g);
+        else {
+          ins = true;
+          for (u32 k = 1; k <= back; ++k)
+            if (__ldg(a.t2g + a.refs[f0 + i - k]) == g) { ins = false; break; }
         }
       }
       __syncwarp();

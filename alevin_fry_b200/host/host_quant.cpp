@@ -6,7 +6,17 @@
 // record-type sniffing (src/utils.rs:313-377), output files and their formats
 // (src/quant.rs:1588-1613, 1786-1847, 1913-1933). Rows are always emitted in chunk order
 // (the reference's order with one worker, `-t 2`).
+#include <atomic>
 #include <charconv>
+#include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <fcntl.h>
+#include <functional>
+#include <mutex>
+#include <sys/mman.h>
+#include <thread>
+#include <unistd.h>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -75,6 +85,11 @@ void append_f32(std::string& out, float v) {
   if (std::isnan(v)) { out += "NaN"; return; }
   if (std::isinf(v)) { out += v < 0 ? "-inf" : "inf"; return; }
   char buf[128];
+  if (v >= 0.0f && v < 16777216.0f && v == (float)(uint32_t)v) {   // whole numbers print as integers
+    auto r = std::to_chars(buf, buf + sizeof buf, (uint32_t)v);
+    out.append(buf, r.ptr);
+    return;
+  }
   auto r = std::to_chars(buf, buf + sizeof buf, v, std::chars_format::fixed);
   out.append(buf, r.ptr);
 }
@@ -200,36 +215,72 @@ struct Pinned {  // growable pinned array (afq_host_alloc)
   void clear() { n = 0; }
 };
 
-struct HostBatch {
+// fork-join helper over persistent threads: run(f) calls f(tid) on every worker and on the caller
+class Pool {
+ public:
+  explicit Pool(unsigned n) : n_(n < 1 ? 1 : n) {
+    for (unsigned i = 1; i < n_; ++i) th_.emplace_back([this, i] { loop(i); });
+  }
+  ~Pool() {
+    { std::lock_guard<std::mutex> lk(m_); stop_ = true; ++gen_; }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  unsigned size() const { return n_; }
+  void run(const std::function<void(unsigned)>& f) {
+    { std::lock_guard<std::mutex> lk(m_); job_ = &f; pending_ = n_ - 1; ++gen_; }
+    cv_.notify_all();
+    f(0);
+    std::unique_lock<std::mutex> lk(m_);
+    done_.wait(lk, [this] { return pending_ == 0; });
+    job_ = nullptr;
+  }
+ private:
+  void loop(unsigned tid) {
+    uint64_t seen = 0;
+    for (;;) {
+      const std::function<void(unsigned)>* j;
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (stop_) return;
+        j = job_;
+      }
+      (*j)(tid);
+      { std::lock_guard<std::mutex> lk(m_); if (--pending_ == 0) done_.notify_one(); }
+    }
+  }
+  unsigned n_;
+  std::vector<std::thread> th_;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  const std::function<void(unsigned)>* job_ = nullptr;
+  unsigned pending_ = 0;
+  uint64_t gen_ = 0;
+  bool stop_ = false;
+};
+
+// one collated chunk (= one cell), located by the header walk; everything a parser thread needs
+// to write the chunk's records straight into their final SoA positions
+struct ChunkInfo {
+  const unsigned char* body;     // first record
+  uint32_t body_bytes, nrec;
+  uint32_t n_aln;                // alignments in the chunk (derived from nbytes: fixed-size records)
+  uint64_t bc;
+  uint64_t rec_off, ref_off;     // positions inside the batch
+};
+
+struct HostBatch {   // pinned SoA arrays of one device batch, sized exactly by the header walk
   Pinned<uint64_t> cell_rec_off;
   Pinned<uint32_t> umi, ref_off, refs;
   Pinned<uint8_t> na8;           // alignment count per record (sent instead of ref_off when all <= 255)
-  Pinned<uint8_t> umi24, refs24; // pack24: 3-byte UMIs / transcript ids instead of umi / refs (afq_batch.rec_umi24 / refs24)
-  bool na8_ok = true;
+  Pinned<uint8_t> umi24, refs24; // 3-byte UMIs / transcript ids instead of umi / refs (afq_batch.rec_umi24 / refs24)
+  std::vector<ChunkInfo> chunks;
+  uint64_t first_cell = 0, n_rec = 0, n_ref = 0;
   bool pack24 = false;
-  uint64_t n_rec = 0, n_ref = 0;
-  void push_umi(uint32_t v) {
-    if (pack24) { umi24.push((uint8_t)v); umi24.push((uint8_t)(v >> 8)); umi24.push((uint8_t)(v >> 16)); } else umi.push(v);
-    ++n_rec;
-  }
-  void push_ref(uint32_t v) {
-    if (pack24) { refs24.push((uint8_t)v); refs24.push((uint8_t)(v >> 8)); refs24.push((uint8_t)(v >> 16)); } else refs.push(v);
-    ++n_ref;
-  }
-  void truncate(uint64_t rec, uint64_t ref) {   // drop the records of a filtered-out cell
-    n_rec = rec; n_ref = ref;
-    if (pack24) { umi24.n = 3 * rec; refs24.n = 3 * ref; } else { umi.n = rec; refs.n = ref; }
-    ref_off.n = rec + 1; na8.n = rec;
-  }
-  std::vector<uint64_t> barcodes;
-  std::vector<uint32_t> nrec;
-  uint64_t first_cell = 0;
-  void reset(uint64_t first) {
-    cell_rec_off.clear(); umi.clear(); ref_off.clear(); refs.clear(); na8.clear(); barcodes.clear(); nrec.clear();
-    umi24.clear(); refs24.clear(); n_rec = n_ref = 0;
-    cell_rec_off.push(0); ref_off.push(0); first_cell = first; na8_ok = true;
-  }
-  uint64_t n_cells() const { return barcodes.size(); }
+  std::atomic<bool> wide_na{false};   // some record has > 255 alignments
+  uint64_t n_cells() const { return chunks.size(); }
 };
 
 struct Outputs {
@@ -240,42 +291,136 @@ struct Outputs {
   std::vector<uint64_t> alt, empty, tiny;
 };
 
-void consume(const HostBatch& hb, const afq_result& r, unsigned bc_len, Outputs& o) {
-  std::string rows, feat, mtx;
+// parse the chunks of a batch in parallel (ingest must not be the bottleneck)
+void parse_batch(HostBatch& b, const RecordLayout& lay, Pool& pool, std::string& failure) {
+  const size_t nc = b.chunks.size();
+  b.cell_rec_off.reserve(nc + 1); b.cell_rec_off.n = nc + 1;
+  b.na8.reserve(b.n_rec + 16); b.na8.n = b.n_rec;
+  if (b.pack24) { b.umi24.reserve(3 * b.n_rec + 16); b.refs24.reserve(3 * b.n_ref + 16); }
+  else { b.umi.reserve(b.n_rec + 4); b.refs.reserve(b.n_ref + 4); }
+  b.wide_na = false;
+  std::atomic<size_t> next{0};
+  std::atomic<bool> bad{false};
+  std::mutex fm;
+  pool.run([&](unsigned) {
+    for (;;) {
+      const size_t c0 = next.fetch_add(8);
+      if (c0 >= nc || bad.load(std::memory_order_relaxed)) return;
+      const size_t c1 = c0 + 8 < nc ? c0 + 8 : nc;
+      for (size_t c = c0; c < c1; ++c) {
+        const ChunkInfo& ci = b.chunks[c];
+        b.cell_rec_off.p[c] = ci.rec_off;
+        const unsigned char* p = ci.body;
+        const unsigned char* end = p + ci.body_bytes;
+        uint64_t rec = ci.rec_off, ref = ci.ref_off;
+        const uint64_t ref_end = ci.ref_off + ci.n_aln;
+        bool ok = true;
+        for (uint32_t r = 0; r < ci.nrec && ok; ++r) {
+          if (p + 4 + lay.read_bytes > end) { ok = false; break; }
+          uint32_t na; memcpy(&na, p, 4); p += 4;
+          uint64_t rumi = 0;
+          memcpy(&rumi, p + lay.umi_off, lay.umi_size);
+          p += lay.read_bytes;
+          if ((uint64_t)na > ref_end - ref || p + (size_t)na * lay.aln_bytes > end) { ok = false; break; }
+          if (b.pack24) { uint8_t* d = b.umi24.p + 3 * rec; d[0] = (uint8_t)rumi; d[1] = (uint8_t)(rumi >> 8); d[2] = (uint8_t)(rumi >> 16); }
+          else b.umi.p[rec] = (uint32_t)rumi;
+          b.na8.p[rec] = (uint8_t)na;
+          if (na > 255) b.wide_na.store(true, std::memory_order_relaxed);
+          for (uint32_t a = 0; a < na; ++a) {
+            uint32_t id; memcpy(&id, p + lay.refid_off, 4); p += lay.aln_bytes;
+            id &= 0x7FFFFFFFu;   // bit 31 = orientation (src/convert.rs:442-445)
+            if (b.pack24) { uint8_t* d = b.refs24.p + 3 * ref; d[0] = (uint8_t)id; d[1] = (uint8_t)(id >> 8); d[2] = (uint8_t)(id >> 16); }
+            else b.refs.p[ref] = id;
+            ++ref;
+          }
+          ++rec;
+        }
+        if (!ok || ref != ref_end || p != end) {
+          bad = true;
+          std::lock_guard<std::mutex> lk(fm);
+          if (failure.empty()) failure = "record overruns its chunk (corrupt collated RAD, chunk " + std::to_string(b.first_cell + c) + ")";
+          return;
+        }
+      }
+    }
+  });
+  b.cell_rec_off.p[nc] = b.n_rec;
+  if (!bad && b.wide_na) {   // rare: CSR offsets instead of 1-byte counts (second walk over the record headers)
+    b.ref_off.reserve(b.n_rec + 2); b.ref_off.n = b.n_rec + 1;
+    next = 0;
+    pool.run([&](unsigned) {
+      for (;;) {
+        const size_t c = next.fetch_add(1);
+        if (c >= nc) return;
+        const ChunkInfo& ci = b.chunks[c];
+        const unsigned char* p = ci.body;
+        uint64_t ref = ci.ref_off;
+        for (uint32_t r = 0; r < ci.nrec; ++r) {
+          uint32_t na; memcpy(&na, p, 4);
+          b.ref_off.p[ci.rec_off + r] = (uint32_t)ref;
+          ref += na;
+          p += 4 + lay.read_bytes + (size_t)na * lay.aln_bytes;
+        }
+      }
+    });
+    b.ref_off.p[b.n_rec] = (uint32_t)b.n_ref;
+  }
+}
+
+// text for rows / featureDump / mtx of one finished batch, formatted in parallel (N2)
+void consume(const HostBatch& hb, const afq_result& r, unsigned bc_len, Outputs& o, Pool& pool) {
+  constexpr uint64_t BLK = 256;
+  const uint64_t nblk = (r.n_cells + BLK - 1) / BLK;
+  std::vector<std::string> rows(nblk), feat(nblk), mtx(nblk);
+  std::atomic<uint64_t> next{0};
+  const uint64_t row0 = o.row_index;
+  pool.run([&](unsigned) {
+    for (;;) {
+      const uint64_t k = next.fetch_add(1);
+      if (k >= nblk) return;
+      std::string& rs = rows[k]; std::string& fs = feat[k]; std::string& ms = mtx[k];
+      const uint64_t c0 = k * BLK, c1 = c0 + BLK < r.n_cells ? c0 + BLK : r.n_cells;
+      ms.reserve((r.row_ptr[c1] - r.row_ptr[c0]) * 16 + 16);
+      for (uint64_t c = c0; c < c1; ++c) {
+        const std::string bc = decode_barcode(hb.chunks[c].bc, bc_len);
+        rs += bc; rs.push_back('\n');
+        // featureDump (src/quant.rs:1181-1196, 1248-1260); unmapped counts unavailable => 0
+        const uint32_t num_mapped = hb.chunks[c].nrec, num_unmapped = 0;
+        const float sum_umi = r.sum_umi[c], max_umi = r.max_umi[c];
+        const float dedup_rate = sum_umi / (float)num_mapped;
+        const float mapping_rate = (float)num_mapped / (float)(num_mapped + num_unmapped);
+        const float mean_expr = sum_umi / (float)r.num_expr[c];
+        const float mean_by_max = mean_expr / max_umi;
+        fs += bc; fs.push_back('\t');
+        append_u64(fs, (uint64_t)num_mapped + num_unmapped); fs.push_back('\t');
+        append_u64(fs, num_mapped); fs.push_back('\t');
+        append_f32(fs, sum_umi); fs.push_back('\t');
+        append_f32(fs, mapping_rate); fs.push_back('\t');
+        append_f32(fs, dedup_rate); fs.push_back('\t');
+        append_f32(fs, mean_by_max); fs.push_back('\t');
+        append_u64(fs, r.num_expr[c]); fs.push_back('\t');
+        append_u64(fs, r.num_over_mean[c]); fs.push_back('\n');
+        for (uint64_t k2 = r.row_ptr[c]; k2 < r.row_ptr[c + 1]; ++k2) {
+          append_u64(ms, row0 + c + 1); ms.push_back(' ');
+          append_u64(ms, (uint64_t)r.col[k2] + 1); ms.push_back(' ');
+          append_f32(ms, r.val[k2]); ms.push_back('\n');
+        }
+      }
+    }
+  });
   for (uint64_t c = 0; c < r.n_cells; ++c) {
     const uint64_t cell_num = hb.first_cell + c;
     if (r.flags[c] & AFQ_FLAG_ALT) o.alt.push_back(cell_num);
     if (r.flags[c] & AFQ_FLAG_TINY) o.tiny.push_back(cell_num);
     if (r.flags[c] & AFQ_FLAG_EMPTY) o.empty.push_back(cell_num);
-    const std::string bc = decode_barcode(hb.barcodes[c], bc_len);
-    rows += bc; rows.push_back('\n');
-    // featureDump (src/quant.rs:1181-1196, 1248-1260); unmapped counts unavailable => 0
-    const uint32_t num_mapped = hb.nrec[c], num_unmapped = 0;
-    const float sum_umi = r.sum_umi[c], max_umi = r.max_umi[c];
-    const float dedup_rate = sum_umi / (float)num_mapped;
-    const float mapping_rate = (float)num_mapped / (float)(num_mapped + num_unmapped);
-    const float mean_expr = sum_umi / (float)r.num_expr[c];
-    const float mean_by_max = mean_expr / max_umi;
-    feat += bc; feat.push_back('\t');
-    append_u64(feat, (uint64_t)num_mapped + num_unmapped); feat.push_back('\t');
-    append_u64(feat, num_mapped); feat.push_back('\t');
-    append_f32(feat, sum_umi); feat.push_back('\t');
-    append_f32(feat, mapping_rate); feat.push_back('\t');
-    append_f32(feat, dedup_rate); feat.push_back('\t');
-    append_f32(feat, mean_by_max); feat.push_back('\t');
-    append_u64(feat, r.num_expr[c]); feat.push_back('\t');
-    append_u64(feat, r.num_over_mean[c]); feat.push_back('\n');
-    for (uint64_t k = r.row_ptr[c]; k < r.row_ptr[c + 1]; ++k) {
-      append_u64(mtx, o.row_index + 1); mtx.push_back(' ');
-      append_u64(mtx, (uint64_t)r.col[k] + 1); mtx.push_back(' ');
-      append_f32(mtx, r.val[k]); mtx.push_back('\n');
-    }
-    ++o.row_index;
   }
+  o.row_index += r.n_cells;
   o.nnz += r.nnz;
-  fwrite(rows.data(), 1, rows.size(), o.rows);
-  fwrite(feat.data(), 1, feat.size(), o.feat);
-  o.mtx_chunks.push_back(std::move(mtx));
+  for (uint64_t k = 0; k < nblk; ++k) {
+    fwrite(rows[k].data(), 1, rows[k].size(), o.rows);
+    fwrite(feat[k].data(), 1, feat[k].size(), o.feat);
+    o.mtx_chunks.push_back(std::move(mtx[k]));
+  }
 }
 
 std::string lower(std::string s) { for (auto& c : s) c = (char)tolower((unsigned char)c); return s; }
@@ -288,6 +433,7 @@ void json_u64_list(std::string& js, const std::vector<uint64_t>& v, const std::s
 }
 
 int quantify_impl(const afqh_quant_opts& o) {
+  const auto t_entry = std::chrono::steady_clock::now();
   REQUIRE(o.input_dir && o.tg_map && o.output_dir && o.resolution, "input_dir, tg_map, output_dir and resolution are required");
   const std::string in = o.input_dir, out = o.output_dir;
   const std::string res = lower(o.resolution);
@@ -314,6 +460,9 @@ int quantify_impl(const afqh_quant_opts& o) {
   setvbuf(f, iobuf.data(), _IOFBF, iobuf.size());
   Reader rd(f);
   RadPrelude pre;
+  // the CUDA context comes up (~0.3-0.5 s) in the background while the prelude and the t2g map are parsed
+  std::thread cuda_warm([] { void* w = nullptr; if (afq_host_alloc(&w, 4096) == AFQ_OK) afq_host_free(w); });
+  struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } warm_join{cuda_warm};
   std::string perr;
   if (!parse_prelude(rd, pre, perr)) { fclose(f); throw Fail{"RAD prelude: " + perr}; }
   // record-type sniffing (src/utils.rs:313-377)
@@ -331,7 +480,9 @@ int quantify_impl(const afqh_quant_opts& o) {
   if (!make_layout(pre, lay, perr)) { fclose(f); throw Fail{perr}; }
   if (umi_len > 16 || lay.umi_size > 8) { fclose(f); throw Fail{"UMIs longer than 16 bases are not supported on the CUDA path"}; }
 
+  const auto t_t2g0 = std::chrono::steady_clock::now();
   T2G t2g = parse_t2g(o.tg_map, pre.ref_names);
+  const auto t_t2g1 = std::chrono::steady_clock::now();
 
   // --quant-subset (src/utils.rs:1074-1095): one barcode per line
   bool filtering = false;
@@ -366,6 +517,8 @@ int quantify_impl(const afqh_quant_opts& o) {
   cfg.umi_len = (uint16_t)umi_len;
   cfg.device = o.device;
   afq_ctx* ctx = nullptr;
+  cuda_warm.join();
+  const auto t_create0 = std::chrono::steady_clock::now();
   if (afq_create(&cfg, t2g.tid_to_gid.data(), t2g.tid_to_gid.size(), &ctx) != AFQ_OK) {
     std::string m = afq_last_error(nullptr);
     fclose(f);
@@ -380,7 +533,31 @@ int quantify_impl(const afqh_quant_opts& o) {
   if (!outs.rows || !outs.feat) { afq_destroy(ctx); fclose(f); throw Fail{"could not create output files in " + out}; }
   fputs("CB\tCorrectedReads\tMappedReads\tDeduplicatedReads\tMappingRate\tDedupRate\tMeanByMax\tNumGenesExpressed\tNumGenesOverMean\n", outs.feat);
 
-  const uint64_t batch_records = o.batch_records ? o.batch_records : (32ull << 20);
+  using clk = std::chrono::steady_clock;
+  auto secs = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+  const auto t_begin = clk::now();
+  double t_wait = 0, t_format = 0, t_submit = 0, t_parse = 0, t_walk = 0;
+  uint64_t cells_seen = 0, total_records = 0;
+  std::string failure;
+
+  // ---- map the file and index the chunks (cells): every chunk header is read once, sequentially;
+  // record sizes are fixed, so a chunk's alignment count follows from its byte size and the SoA
+  // position of every chunk is known before any record is parsed
+  const uint64_t body_start = rd.pos();
+  fclose(f);
+  const int fd = open(rad_path.c_str(), O_RDONLY);
+  struct stat st {};
+  if (fd < 0 || fstat(fd, &st) != 0) { if (fd >= 0) close(fd); afq_destroy(ctx); fclose(outs.rows); fclose(outs.feat); throw Fail{"couldn't open " + rad_path}; }
+  const uint64_t fsize = (uint64_t)st.st_size;
+  const unsigned char* fmap = fsize ? (const unsigned char*)mmap(nullptr, fsize, PROT_READ, MAP_PRIVATE, fd, 0) : nullptr;
+  close(fd);
+  if (fsize && fmap == MAP_FAILED) { afq_destroy(ctx); fclose(outs.rows); fclose(outs.feat); throw Fail{"mmap failed for " + rad_path}; }
+  madvise((void*)fmap, fsize, MADV_SEQUENTIAL);
+
+  // half of the threads parse the next batch while the other half format the previous result
+  const unsigned n_threads = std::max(2u, std::min(o.num_threads < 2 ? 2u : o.num_threads, 128u));
+  Pool pool(n_threads / 2), fmt_pool(n_threads - n_threads / 2);
+  const uint64_t batch_records = o.batch_records ? o.batch_records : (16ull << 20);
   constexpr int NB = 3;
   HostBatch hb[NB];
   // 24-bit wire arrays whenever the chemistry allows: UMI <= 12 bases and fewer than 2^24 targets
@@ -388,19 +565,52 @@ int quantify_impl(const afqh_quant_opts& o) {
   for (auto& b : hb) b.pack24 = pack24;
   uint64_t tickets[NB] = {0};
   bool inflight[NB] = {false};
-  int cur = 0;
-  uint64_t cells_seen = 0, total_records = 0;
-  std::string failure;
   auto finish = [&](int i) {
     afq_result r{};
+    const auto ta = clk::now();
     if (afq_wait(ctx, tickets[i], &r) != AFQ_OK) throw Fail{std::string("afq_wait: ") + afq_last_error(ctx)};
-    consume(hb[i], r, bc_len, outs);
+    const auto tb = clk::now();
+    consume(hb[i], r, bc_len, outs, fmt_pool);
+    t_wait += secs(ta, tb); t_format += secs(tb, clk::now());
     afq_result_release(ctx, &r);
-    inflight[i] = false;
+  };
+  // results are collected, formatted and written by a consumer thread, in submission order
+  std::mutex qm;
+  std::condition_variable qcv;
+  std::deque<int> queue;
+  bool producer_done = false;
+  std::string consumer_failure;
+  std::thread consumer([&] {
+    for (;;) {
+      int i;
+      {
+        std::unique_lock<std::mutex> lk(qm);
+        qcv.wait(lk, [&] { return !queue.empty() || producer_done; });
+        if (queue.empty()) return;
+        i = queue.front(); queue.pop_front();
+      }
+      std::string msg;
+      try {
+        if (consumer_failure.empty()) finish(i);
+        else { afq_result r{}; if (afq_wait(ctx, tickets[i], &r) == AFQ_OK) afq_result_release(ctx, &r); }
+      } catch (const Fail& e) { msg = e.msg; }
+      { std::lock_guard<std::mutex> lk(qm); inflight[i] = false; if (!msg.empty() && consumer_failure.empty()) consumer_failure = msg; }
+      qcv.notify_all();
+    }
+  });
+  auto wait_free = [&](int i) {
+    std::unique_lock<std::mutex> lk(qm);
+    qcv.wait(lk, [&] { return !inflight[i]; });
+    if (!consumer_failure.empty()) throw Fail{consumer_failure};
   };
   auto submit = [&](int i) {
     HostBatch& b = hb[i];
     if (b.n_cells() == 0) return;
+    const auto t0 = clk::now();
+    std::string perr2;
+    parse_batch(b, lay, pool, perr2);
+    t_parse += secs(t0, clk::now());
+    if (!perr2.empty()) throw Fail{perr2};
     afq_batch ab{};
     ab.first_cell_index = b.first_cell;
     ab.n_cells = b.n_cells();
@@ -409,75 +619,72 @@ int quantify_impl(const afqh_quant_opts& o) {
     ab.cell_rec_offsets = b.cell_rec_off.p;
     if (b.pack24) { ab.rec_umi24 = b.umi24.p; ab.refs24 = b.refs24.p; }     // 3 bytes instead of 4 per UMI / id over PCIe
     else { ab.rec_umi32 = b.umi.p; ab.refs = b.refs.p; }
-    if (b.na8_ok) { ab.rec_ref_offsets = nullptr; ab.rec_na8 = b.na8.p; }   // 1 byte instead of 4 per record over PCIe
+    if (!b.wide_na) { ab.rec_ref_offsets = nullptr; ab.rec_na8 = b.na8.p; }   // 1 byte instead of 4 per record over PCIe
     else { ab.rec_ref_offsets = b.ref_off.p; ab.rec_na8 = nullptr; }
+    const auto ta = clk::now();
     if (afq_submit(ctx, &ab, &tickets[i]) != AFQ_OK) throw Fail{std::string("afq_submit: ") + afq_last_error(ctx)};
-    inflight[i] = true;
+    t_submit += secs(ta, clk::now());
+    { std::lock_guard<std::mutex> lk(qm); inflight[i] = true; queue.push_back(i); }
+    qcv.notify_all();
   };
   try {
-    hb[cur].reset(0);
-    std::vector<unsigned char> chunk;
+    int cur = 0;
+    auto reset = [&](HostBatch& b, uint64_t first) { b.chunks.clear(); b.first_cell = first; b.n_rec = b.n_ref = 0; };
+    reset(hb[cur], 0);
+    const unsigned char* p = fmap + body_start;
+    const unsigned char* fend = fmap + fsize;
+    const size_t rec_fixed = 4 + lay.read_bytes;
     for (uint64_t ch = 0; ch < pre.num_chunks; ++ch) {
+      const auto tw = clk::now();
+      REQUIRE(p + 8 <= fend, "truncated chunk header in " + rad_path);
       uint32_t nbytes, nrec;
-      REQUIRE(rd.get(nbytes) && rd.get(nrec), "truncated chunk header in " + rad_path);
+      memcpy(&nbytes, p, 4); memcpy(&nrec, p + 4, 4);
       REQUIRE(nbytes >= 8, "corrupt chunk header");
-      chunk.resize(nbytes - 8);
-      REQUIRE(rd.read(chunk.data(), chunk.size()), "truncated chunk body");
-      const unsigned char* p = chunk.data();
-      const unsigned char* end = p + chunk.size();
-      HostBatch& b = hb[cur];
-      uint64_t bc = 0;
-      bool take = true;
-      const uint64_t rec_start = b.n_rec, ref_start = b.n_ref;
-      for (uint32_t r = 0; r < nrec; ++r) {
-        REQUIRE(p + 4 + lay.read_bytes <= end, "record overruns its chunk");
-        uint32_t na; memcpy(&na, p, 4); p += 4;
-        uint64_t rbc = 0, rumi = 0;
-        memcpy(&rbc, p + lay.bc_off, lay.bc_size);
-        memcpy(&rumi, p + lay.umi_off, lay.umi_size);
-        p += lay.read_bytes;
-        REQUIRE(p + (size_t)na * lay.aln_bytes <= end, "alignments overrun their chunk");
-        if (r == 0) { bc = rbc; if (filtering && !keep.count(bc)) take = false; }
-        if (take) {
-          b.push_umi((uint32_t)rumi);
-          for (uint32_t a = 0; a < na; ++a) {
-            uint32_t ref; memcpy(&ref, p + (size_t)a * lay.aln_bytes + lay.refid_off, 4);
-            b.push_ref(ref & 0x7FFFFFFFu);  // bit 31 = orientation (src/convert.rs:442-445)
-          }
-          b.ref_off.push((uint32_t)b.n_ref);
-          b.na8.push((uint8_t)na);
-          if (na > 255) b.na8_ok = false;
-        }
-        p += (size_t)na * lay.aln_bytes;
-      }
-      if (!take) { b.truncate(rec_start, ref_start); continue; }
+      REQUIRE(p + nbytes <= fend, "truncated chunk body");
       REQUIRE(nrec > 0, "Discovered empty chunk; should not happen!");
-      b.cell_rec_off.push(b.n_rec);
-      b.barcodes.push_back(bc);
-      b.nrec.push_back(nrec);
+      const uint64_t payload = (uint64_t)nbytes - 8;
+      REQUIRE(payload >= (uint64_t)nrec * rec_fixed && lay.aln_bytes > 0 && (payload - (uint64_t)nrec * rec_fixed) % lay.aln_bytes == 0,
+              "record overruns its chunk");
+      ChunkInfo ci;
+      ci.body = p + 8; ci.body_bytes = (uint32_t)payload; ci.nrec = nrec;
+      ci.n_aln = (uint32_t)((payload - (uint64_t)nrec * rec_fixed) / lay.aln_bytes);
+      ci.bc = 0;
+      memcpy(&ci.bc, ci.body + 4 + lay.bc_off, lay.bc_size);   // collate key = barcode of the first record
+      p += nbytes;
+      t_walk += secs(tw, clk::now());
+      if (filtering && !keep.count(ci.bc)) continue;
+      HostBatch& b = hb[cur];
+      ci.rec_off = b.n_rec; ci.ref_off = b.n_ref;
+      b.n_rec += nrec; b.n_ref += ci.n_aln;
+      b.chunks.push_back(ci);
       total_records += nrec;
       ++cells_seen;
       if (b.n_rec >= batch_records || b.n_ref >= (3ull << 30)) {
         submit(cur);
         const int nxt = (cur + 1) % NB;
-        if (inflight[nxt]) finish(nxt);
+        wait_free(nxt);
         cur = nxt;
-        hb[cur].reset(cells_seen);
+        reset(hb[cur], cells_seen);
       }
     }
     submit(cur);
-    for (int k = 1; k <= NB; ++k) { const int i = (cur + k) % NB; if (inflight[i]) finish(i); }
   } catch (const Fail& e) { failure = e.msg; }
-  fclose(f);
+  { std::lock_guard<std::mutex> lk(qm); producer_done = true; }
+  qcv.notify_all();
+  consumer.join();
+  if (failure.empty()) failure = consumer_failure;
   if (!failure.empty()) {
-    for (int i = 0; i < NB; ++i) if (inflight[i]) { afq_result r{}; if (afq_wait(ctx, tickets[i], &r) == AFQ_OK) afq_result_release(ctx, &r); }
     afq_destroy(ctx);
+    if (fmap) munmap((void*)fmap, fsize);
     fclose(outs.rows); fclose(outs.feat);
     throw Fail{failure};
   }
+  const auto t_td0 = clk::now();
   afq_destroy(ctx);
+  if (fmap) munmap((void*)fmap, fsize);
   fclose(outs.rows);
   fclose(outs.feat);
+  const auto t_loop_end = clk::now();
 
   // quants_mat_cols.txt (src/quant.rs:1786-1809)
   {
@@ -501,8 +708,32 @@ int quantify_impl(const afqh_quant_opts& o) {
     append_u64(hdr, t2g.num_rows); hdr.push_back(' ');
     append_u64(hdr, outs.nnz); hdr.push_back('\n');
     fwrite(hdr.data(), 1, hdr.size(), fm);
-    for (auto& c : outs.mtx_chunks) fwrite(c.data(), 1, c.size(), fm);
+    fflush(fm);
+    // the body chunks go out in parallel at their final offsets
+    std::vector<uint64_t> offs(outs.mtx_chunks.size() + 1, hdr.size());
+    for (size_t i = 0; i < outs.mtx_chunks.size(); ++i) offs[i + 1] = offs[i] + outs.mtx_chunks[i].size();
+    const int mfd = fileno(fm);
+    bool wr_ok = ftruncate(mfd, (off_t)offs.back()) == 0;
+    std::atomic<size_t> nextc{0};
+    std::atomic<bool> wr_bad{false};
+    if (wr_ok) fmt_pool.run([&](unsigned) {
+      for (;;) {
+        const size_t i = nextc.fetch_add(16);
+        if (i >= outs.mtx_chunks.size()) return;
+        const size_t e = std::min(i + 16, outs.mtx_chunks.size());
+        for (size_t j = i; j < e; ++j) {
+          const std::string& c = outs.mtx_chunks[j];
+          size_t done = 0;
+          while (done < c.size()) {
+            const ssize_t w = pwrite(mfd, c.data() + done, c.size() - done, (off_t)(offs[j] + done));
+            if (w <= 0) { wr_bad = true; return; }
+            done += (size_t)w;
+          }
+        }
+      }
+    });
     fclose(fm);
+    REQUIRE(wr_ok && !wr_bad, "writing quants_mat.mtx failed");
   }
   // quant.json (src/quant.rs:1913-1933); keys in sorted order (serde_json Map without preserve_order)
   {
@@ -542,7 +773,12 @@ int quantify_impl(const afqh_quant_opts& o) {
     fwrite(js.data(), 1, js.size(), fj);
     fclose(fj);
   }
-  (void)total_records;
+  if (getenv("AFQ_TIMING")) {
+    const double tail = secs(t_loop_end, clk::now());
+    fprintf(stderr, "[afq timing] cells %llu records %llu threads %u | setup %.3f s (t2g %.3f, afq_create %.3f) | pipeline %.3f s (chunk index %.3f, parse %.3f, afq_submit %.3f, afq_wait %.3f, text formatting %.3f) | teardown %.3f s | final writes %.3f s\n",
+            (unsigned long long)cells_seen, (unsigned long long)total_records, n_threads, secs(t_entry, t_begin), secs(t_t2g0, t_t2g1), secs(t_create0, t_begin),
+            secs(t_begin, t_td0), t_walk, t_parse, t_submit, t_wait, t_format, secs(t_td0, t_loop_end), tail);
+  }
   return 0;
 }
 
