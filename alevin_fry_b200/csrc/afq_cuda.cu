@@ -374,7 +374,9 @@ int afq_create(const afq_config* cfg, const uint32_t* tid_to_gid, uint64_t n_ref
   {
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gene_eqc, (int)GE_THREADS, 0) != cudaSuccess || occ < 1) occ = 1;
-    if (occ > 4) occ = 4;
+    int cap = 4;   // CTAs per SM (AFQ_GE_OCC overrides for experiments)
+    if (const char* e = getenv("AFQ_GE_OCC")) cap = atoi(e) > 0 ? atoi(e) : cap;
+    if (occ > cap) occ = cap;
     c->ge_grid = occ * c->num_sms;
   }
   *out = c;

@@ -1376,7 +1376,10 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
 }
 
 // persistent kernel: CTAs pull cells from work list `list_id` (largest cells first)
-__global__ void __launch_bounds__(GE_THREADS, 4) k_gene_eqc(KArgs a, GeArgs g) {
+#ifndef AFQ_GE_MIN_BLOCKS
+#define AFQ_GE_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(GE_THREADS, AFQ_GE_MIN_BLOCKS) k_gene_eqc(KArgs a, GeArgs g) {
   __shared__ GeShared sh;
   __shared__ __align__(16) u8 s_scratch[GE_SCRATCH_BYTES];
   __shared__ GePtrs s_ptrs;

@@ -193,3 +193,49 @@ def test_flat_alignment_loop_shapes(res):
     b = CellBatch.from_cells(cells)
     o = QuantOpts(resolution=res, num_gene_ids=n_genes, num_rows=n_genes)
     assert_same(gpu_quant(o, t2g, b), oracle_lib.oracle_quant(o, t2g, b), exact=True, ctx="flat/" + res)
+
+
+@pytest.mark.parametrize("cfg,res,full_cells", [("C2", "cr-like", 100000), ("C3", "parsimony", 60000)])
+def test_full_size_invariants_and_sampled_parity(cfg, res, full_cells):
+    # BASELINE.json configs[1] at its full single-GPU size (100k cells, ~200M records) and half of
+    # configs[2]'s per-GPU share: size-independent properties over every cell, 8 pipelined host batches
+    # with the compact wire arrays vs a one-shot u32 pass, and bit-exact parity with the oracle on samples
+    spec = synth.config_spec(cfg)
+    t2g = synth.tid_to_gid(spec)
+    o = opts_for(spec, res, large_graph_thresh=1000) if res == "parsimony" else opts_for(spec, res)
+    n_cells = int(os.environ.get("AFQ_FULL_CELLS", str(full_cells)))
+    part = (n_cells + 7) // 8
+    parts = [synth.generate(spec, c0, min(part, n_cells - c0)) for c0 in range(0, n_cells, part)]
+    with Quantifier(o, t2g) as q:
+        tickets, rs = [], []
+        for p in parts:
+            tickets.append(q.submit(p, use_na8=True, use_pack24=True))
+            if len(tickets) == 3:
+                rs.append(q.wait(tickets.pop(0)))
+        rs += [q.wait(t) for t in tickets]
+        plain = q.quantify_batch(parts[3])            # u32 arrays, one shot
+    assert np.array_equal(plain.col, rs[3].col) and np.array_equal(plain.val, rs[3].val)
+    total_nnz = 0
+    for p, r in zip(parts, rs):
+        nrec = np.diff(p.cell_rec_offsets.astype(np.int64))
+        rp = r.row_ptr.astype(np.int64)
+        assert r.n_cells == p.n_cells and rp[-1] == r.nnz
+        # columns strictly ascending inside every row: only row starts may see a non-increase
+        d = np.diff(r.col.astype(np.int64))
+        bad = np.nonzero(d <= 0)[0] + 1
+        assert np.isin(bad, rp).all()
+        assert np.all(r.val >= 1) and np.all(r.val == np.floor(r.val))
+        row_sums = np.add.reduceat(r.val.astype(np.float64), rp[:-1][np.diff(rp) > 0]) if r.nnz else np.zeros(0)
+        assert np.array_equal(row_sums, r.sum_umi[np.diff(rp) > 0].astype(np.float64))
+        assert np.all(r.sum_umi <= nrec) and np.all(r.num_expr == np.diff(rp))
+        assert np.all(r.max_umi <= r.sum_umi)
+        total_nnz += r.nnz
+    assert total_nnz > 100 * n_cells      # ~230 expressed genes per cell at this shape
+    rng = np.random.default_rng(5)
+    for k in rng.choice(len(parts), size=2, replace=False):
+        c0 = int(rng.integers(0, parts[k].n_cells - 150))
+        sub = parts[k].slice_cells(c0, c0 + 150)
+        want = oracle_lib.oracle_quant(o, t2g, sub)
+        lo, hi = int(rs[k].row_ptr[c0]), int(rs[k].row_ptr[c0 + 150])
+        assert np.array_equal(rs[k].col[lo:hi], want.col) and np.array_equal(rs[k].val[lo:hi], want.val)
+        assert np.array_equal(rs[k].sum_umi[c0:c0 + 150], want.sum_umi)
