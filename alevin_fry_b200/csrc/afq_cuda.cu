@@ -140,6 +140,9 @@ struct afq_ctx {
   int force_bin = -1;
   int grid_smem[NUM_SMEM_BINS] = {0};
   int ge_grid = 0;
+  int grid_ps[PS_VARIANTS] = {0};
+  u32 ps_limit_words = 0;      // AFQ_PS_LIMIT_WORDS: smaller k_pug_smem arena (tests: forces fallbacks to k_gene_eqc)
+  bool no_ps = false;          // AFQ_NO_PS=1: parsimony cells all take the global-arena kernel (A/B experiments)
   u32 need_shift = 0;          // arena-size bias, raised when a batch overflowed many arenas
   bool no_lanes = false;       // AFQ_NO_LANES=1: launch the arena kernels back to back on the caller's stream
   cudaStream_t lanes[NUM_BINS] = {nullptr};
@@ -175,6 +178,17 @@ struct ProfScope {
     if (c->profiling) { cudaEventRecord(b, st); c->prof.push_back({kid, a, b}); }
   }
 };
+
+template <int VAR>
+int setup_ps(afq_ctx* c) {
+  const size_t smem = (size_t)ps_arena_words(VAR) * 4;
+  CUDA_TRY(c, cudaFuncSetAttribute(k_pug_smem<VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pug_smem<VAR>, (int)ps_threads(VAR), smem));
+  if (occ < 1) { c->err = "k_pug_smem variant does not fit an SM"; return AFQ_ERR_CUDA; }
+  c->grid_ps[VAR] = occ * c->num_sms;
+  return AFQ_OK;
+}
 
 template <int BIN>
 int setup_bin(afq_ctx* c) {
@@ -219,6 +233,8 @@ struct CudaLauncher {
   }
   u32* adj_pool(u64 n) { return w->adj_pool.ensure((size_t)n) == cudaSuccess ? w->adj_pool.p : nullptr; }
   u32 need_shift() { return c->need_shift; }
+  int ps_grid(int v) { return c->no_ps ? 0 : c->grid_ps[v]; }
+  u32 ps_limit_words() { return c->ps_limit_words; }
   // fork / join: lanes are ctx-owned non-blocking streams ordered after / before the caller stream
   void fork(int n) {
     if (c->no_lanes) return;
@@ -342,6 +358,8 @@ int afq_create(const afq_config* cfg, const uint32_t* tid_to_gid, uint64_t n_ref
   if (const char* s = getenv("AFQ_FORCE_BIN")) c->force_bin = atoi(s);
   if (const char* s = getenv("AFQ_NEED_SHIFT")) c->need_shift = (u32)atoi(s);
   if (const char* s = getenv("AFQ_NO_LANES")) c->no_lanes = atoi(s) != 0;
+  if (const char* s = getenv("AFQ_NO_PS")) c->no_ps = atoi(s) != 0;
+  if (const char* s = getenv("AFQ_PS_LIMIT_WORDS")) c->ps_limit_words = (u32)atoi(s);
   if (c->large_cap_log2 < 10) c->large_cap_log2 = 10;
   if (c->large_cap_log2 > 30) c->large_cap_log2 = 30;
   if (c->large_blocks < 1) c->large_blocks = (u32)c->num_sms;
@@ -369,7 +387,8 @@ int afq_create(const afq_config* cfg, const uint32_t* tid_to_gid, uint64_t n_ref
 #undef CREATE_TRY
   int rc;
   if ((rc = setup_bin<0>(c)) || (rc = setup_bin<1>(c)) || (rc = setup_bin<2>(c)) ||
-      (rc = setup_bin<3>(c)) || (rc = setup_bin<4>(c)) || (rc = setup_bin<5>(c)))
+      (rc = setup_bin<3>(c)) || (rc = setup_bin<4>(c)) || (rc = setup_bin<5>(c)) ||
+      (rc = setup_ps<0>(c)) || (rc = setup_ps<1>(c)) || (rc = setup_ps<2>(c)))
     return fail(rc);
   {
     int occ = 0;

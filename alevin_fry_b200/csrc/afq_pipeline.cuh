@@ -15,24 +15,28 @@
 //   void fork(int lanes); void lane(int i); void join();      // independent launches may overlap:
 //       between fork and join, launches go to lane i's stream (CUDA) / run in order (emulator)
 //   u32  need_shift();                                        // arena-size bias learnt from overflows
+//   int  ps_grid(int variant);                                // persistent grid of k_pug_smem<variant>; 0 = disabled
+//   u32  ps_limit_words();                                    // 0, or a smaller arena for k_pug_smem (tests: forces fallbacks)
 #pragma once
 #include <string>
 
 #include "../../include/afq.h"
 #include "afq_kernels.cuh"
 #include "afq_pug.cuh"
+#include "afq_pugs.cuh"
 
 namespace afq {
 
 enum KernelId : int {
   KID_BIN = 0, KID_SMEM0 = 1, KID_LARGE = 7, KID_SCAN_SUMS = 8, KID_SCAN_TILES = 9, KID_SCAN_ROWS = 10,
-  KID_GATHER = 11, KID_GENE_EQC = 12, KID_GENE_EQC_BIG = 13, KID_BIN_GE = 14, KID_REGION = 15, KID_NA_OFFSETS = 16, KID_UNPACK24 = 17, NUM_KID = 18
+  KID_GATHER = 11, KID_GENE_EQC = 12, KID_GENE_EQC_BIG = 13, KID_BIN_GE = 14, KID_REGION = 15, KID_NA_OFFSETS = 16, KID_UNPACK24 = 17,
+  KID_PUG_SMEM0 = 18, NUM_KID = 21
 };
 static const char* const KID_NAMES[NUM_KID] = {
     "k_bin_cells", "k_resolve_smem<0>", "k_resolve_smem<1>", "k_resolve_smem<2>", "k_resolve_smem<3>",
     "k_resolve_smem<4>", "k_resolve_smem<5>", "k_resolve_large", "k_scan_tile_sums", "k_scan_tiles",
     "k_scan_rows", "k_gather_rows", "k_gene_eqc", "k_gene_eqc(big cells)", "k_bin_cells_ge", "resolve_region(wall)",
-    "k_na_offsets(+tile sums)", "k_unpack24"};
+    "k_na_offsets(+tile sums)", "k_unpack24", "k_pug_smem<0>", "k_pug_smem<1>", "k_pug_smem<2>"};
 
 struct PipeBufs {  // device scratch owned by the caller (one set per stream-ordered pipeline)
   Ctl* ctl;
@@ -141,14 +145,20 @@ int enqueue_batch(L& l, const afq_config& cfg, int force_bin, const PipeBufs& pb
       err = "--large-graph-thresh above 4096 is not supported on the CUDA path";
       return AFQ_ERR_UNSUPPORTED;
     }
-    l.launch(KID_BIN_GE, k_bin_cells_ge, bin_grid, 256u, (size_t)0, a, force_bin, GE_BIG_RECORDS, l.need_shift());
-    launch_crlike_bins(l, a, pb);
-    Ctl h{};
-    if (l.read_ctl(pb.ctl, &h)) { err = "reading the control block failed"; return AFQ_ERR_CUDA; }
     GeArgs g{};
     g.ge_mode = res_is_pug(res) ? ((res == AFQ_RES_PARSIMONY_GENE || res == AFQ_RES_PARSIMONY_GENE_EM) ? GE_MODE_PUG_GENE : GE_MODE_PUG_TXP)
                                 : GE_MODE_CRLIKE;
     g.only_unique = res_is_em(res) ? 0u : 1u;
+    g.ps_limit_words = l.ps_limit_words();
+    // cells expected to fit a shared-memory arena take k_pug_smem (parsimony family); it hands cells
+    // it cannot finish (arena too small after all, a component of more than 32 vertices) back to
+    // the k_gene_eqc list, which is drained afterwards
+    const bool ps_on = g.ge_mode != GE_MODE_CRLIKE && l.ps_grid(0) > 0 && cfg.large_graph_thresh >= 2;
+    const u32 ps_mode = ps_on ? (1u | (g.ge_mode == GE_MODE_PUG_GENE ? 2u : 0u) | (g.only_unique ? 0u : 4u)) : 0u;
+    l.launch(KID_BIN_GE, k_bin_cells_ge, bin_grid, 256u, (size_t)0, a, force_bin, GE_BIG_RECORDS, l.need_shift(), ps_mode);
+    launch_crlike_bins(l, a, pb);
+    Ctl h{};
+    if (l.read_ctl(pb.ctl, &h)) { err = "reading the control block failed"; return AFQ_ERR_CUDA; }
     g.em_init_uniform = cfg.em_init_uniform ? 1u : 0u;
     g.pug_exact_umi = cfg.pug_exact_umi ? 1u : 0u;
     g.umi_len = cfg.umi_len;
@@ -158,12 +168,25 @@ int enqueue_batch(L& l, const afq_config& cfg, int force_bin, const PipeBufs& pb
     g.adj_pool = l.adj_pool(g.adj_cap);
     g.adj_used = (u64*)&pb.ctl->adj_used;
     if (!g.adj_pool) { err = "adjacency pool allocation failed"; return AFQ_ERR_CUDA; }
+    u32 ps_cells = 0;
+    for (int v = PS_VARIANTS - 1; v >= 0; --v) {   // biggest cells first
+      const u32 cnt = h.bin_count[PS_LIST0 + v];
+      if (!cnt) continue;
+      ps_cells += cnt;
+      u32 blocks = (u32)l.ps_grid(v);
+      if (blocks > cnt) blocks = cnt;
+      const size_t smem = (size_t)ps_arena_words(v) * 4;
+      if (v == 0) l.launch(KID_PUG_SMEM0 + 0, k_pug_smem<0>, blocks, ps_threads(0), smem, a, g);
+      else if (v == 1) l.launch(KID_PUG_SMEM0 + 1, k_pug_smem<1>, blocks, ps_threads(1), smem, a, g);
+      else l.launch(KID_PUG_SMEM0 + 2, k_pug_smem<2>, blocks, ps_threads(2), smem, a, g);
+    }
     for (int which = 0; which < 2; ++which) {
       const int list = which == 0 ? GE_LIST_BIG : GE_LIST_NORMAL;
-      if (h.bin_count[list] == 0) continue;
+      const u32 cells = h.bin_count[list] + (which == 1 ? ps_cells : 0u);   // upper bound: every k_pug_smem cell may come back
+      if (cells == 0) continue;
       const u64 bytes = align8(ge_carve(nullptr, h.ge_max_n[which], h.ge_max_p[which], g.large_graph_thresh, nullptr)) + 64;
       u32 blocks = (u32)l.ge_blocks(which);
-      if (blocks > h.bin_count[list]) blocks = h.bin_count[list];
+      if (blocks > cells) blocks = cells;
       g.arena = l.ge_arena(which, bytes, blocks);
       if (!g.arena) { err = "gene-eq-class arena allocation failed (" + std::to_string(bytes) + " B x " + std::to_string(blocks) + ")"; return AFQ_ERR_CUDA; }
       g.arena_bytes = bytes;

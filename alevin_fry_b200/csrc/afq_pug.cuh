@@ -56,6 +56,7 @@ struct GeArgs {
   u64* adj_used;        // in Ctl-adjacent memory
   // which work list this launch consumes
   u32 list_id;
+  u32 ps_limit_words;   // k_pug_smem: use at most this many arena words (0 = the variant's size; tests force fallbacks with it)
 };
 
 __host__ __device__ inline u64 align8(u64 x) { return (x + 7) & ~7ull; }
@@ -758,6 +759,9 @@ __device__ inline void crlike_molecules_from_ltab(const GeCell& c, GeShared* sh,
   __syncthreads();
 }
 
+struct GeCell;
+__device__ inline void ge_back(const KArgs& a, const GeArgs& g, u32 cell, GeCell& c, GeShared* sh);
+
 // =============================================================================================
 // The kernel body for one cell. Produces this cell's sparse counts in the staging rows.
 // =============================================================================================
@@ -1017,6 +1021,19 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
   __syncthreads();
 
   c.vk_s = nullptr; c.vc_s = nullptr; c.scratch_budget = GE_SCRATCH_BYTES;   // vertex cache is dead from here on
+  ge_back(a, g, cell, c, sh);
+}
+
+// =============================================================================================
+// Stages B and C for one cell: molecules (mlab / mol_off / mol_len, sh->n_mol of them) -> gene
+// eq-classes in canonical order -> counts or EM -> staging row + per-cell statistics. Shared by
+// the global-arena kernel above and the shared-memory kernel (afq_pugs.cuh); the arrays it uses
+// (GePtrs: mkey midx gcls_* tkey ent_* sup g_off alpha_* cls_inv sib_*) may live in either space.
+// c.scratch_budget = bytes of c.scratch the staged sorts may use (0: sort in place).
+// =============================================================================================
+__device__ inline void ge_back(const KArgs& a, const GeArgs& g, u32 cell, GeCell& c, GeShared* sh) {
+  const GePtrs& p = c.p;
+  const u32 T = blockDim.x, tid = threadIdx.x;
   // =================== stage B: molecules -> gene eq-classes in canonical order ===============
   const u32 M = sh->n_mol;
   const u32 Mp = next_pow2(M);
@@ -1034,7 +1051,7 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
     }
   }
   __syncthreads();
-  sort_pairs_staged(p.mkey, p.midx, Mp, c.scratch);
+  sort_pairs_staged(p.mkey, p.midx, Mp, c.scratch, c.scratch_budget);
   // segments of equal 2-gene prefix; labels longer than 2 are ordered inside the segment by
   // one thread (insertion sort on the full label), then classes are counted
   auto mol_less = [&](u32 x, u32 y) {
@@ -1124,7 +1141,7 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
       p.ent_idx[j] = cnt;
     }
     __syncthreads();
-    sort_u64_staged(p.tkey, next_pow2(G), c.scratch);
+    sort_u64_staged(p.tkey, next_pow2(G), c.scratch, c.scratch_budget);
     u32 base = 0, lmax = 0;
     for (u32 c0 = 0; c0 < G; c0 += T) {
       const u32 i = c0 + tid;
@@ -1207,7 +1224,7 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
       }
     }
     __syncthreads();
-    sort_u32_staged(p.sup, Sp, c.scratch);
+    sort_u32_staged(p.sup, Sp, c.scratch, c.scratch_budget);
     u32 S = 0;
     {  // unique in place (chunked, same hazard-free pattern as the compactions)
       u32 base = 0;
@@ -1248,7 +1265,7 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
     __syncthreads();
     GE_FOR(e, Lt) p.tkey[e] = ((u64)p.ent_loc[e] << 32) | e;
     __syncthreads();
-    sort_u64_staged(p.tkey, Lp, c.scratch);
+    sort_u64_staged(p.tkey, Lp, c.scratch, c.scratch_budget);
     for (u32 s = tid; s <= S; s += T) {  // g_off[s] = first sorted entry whose support index is >= s
       u32 lo = 0, hi = Lt;
       while (lo < hi) { u32 mid = (lo + hi) >> 1; if ((u32)(p.tkey[mid] >> 32) < s) lo = mid + 1; else hi = mid; }
@@ -1397,35 +1414,8 @@ __global__ void __launch_bounds__(GE_THREADS, AFQ_GE_MIN_BLOCKS) k_gene_eqc(KArg
   }
 }
 
-// classify cells for the gene-eq-class resolutions: tiny cells go to the cr-like arenas
-// (src/quant.rs:794-846), the rest to the k_gene_eqc lists (list NUM_SMEM_BINS+... by size)
 constexpr int GE_LIST_BIG = NUM_BINS;      // bin_list row for cells > GE_BIG_RECORDS
 constexpr int GE_LIST_NORMAL = NUM_BINS + 1;
 constexpr u32 GE_BIG_RECORDS = 1u << 16;
-
-__global__ void k_bin_cells_ge(KArgs a, int force_bin, u32 big_records, u32 need_shift) {
-  const u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= a.n_cells) return;
-  const u64 r0 = a.cell_rec_off[c], r1 = a.cell_rec_off[c + 1];
-  const u64 n = r1 - r0;
-  const u32 p = a.ref_off[r1] - a.ref_off[r0];
-  int b;
-  if (a.tiny_eligible && n < a.small_thresh) {
-    const u64 need = (n < (u64)p ? n : (u64)p) << need_shift;
-    b = NUM_SMEM_BINS;
-#pragma unroll
-    for (int i = NUM_SMEM_BINS - 1; i >= 0; --i)
-      if (need <= (1ull << bin_cap_log2(i))) b = i;
-    if (force_bin >= 0 && force_bin > b) b = force_bin < NUM_SMEM_BINS ? force_bin : NUM_SMEM_BINS;
-    if (b == NUM_SMEM_BINS) atomicMax(&a.ctl->max_cell_refs, p);
-  } else {
-    const int w = n > big_records ? 0 : 1;
-    b = w == 0 ? GE_LIST_BIG : GE_LIST_NORMAL;
-    atomicMax(&a.ctl->ge_max_n[w], (u32)n);
-    atomicMax(&a.ctl->ge_max_p[w], p);
-  }
-  const u32 idx = atomicAdd(&a.ctl->bin_count[b], 1u);
-  a.bin_list[(u64)b * a.n_cells + idx] = (u32)c;
-}
 
 }  // namespace afq

@@ -1,0 +1,720 @@
+// afq_pugs.cuh — the parsimony family (and cr-like-em) for one cell ENTIRELY IN SHARED MEMORY.
+//
+// Same reference behaviour as afq_pug.cuh (src/eq_class.rs:723-1036, src/pugutils.rs:65-391,
+// 989-1330, src/em.rs:167-582; determinism contract of DESIGN.md), re-laid-out so that a cell's
+// records are read from HBM exactly once (coalesced) and every later access is a shared-memory
+// access. ncu r1s showed the global-arena kernel (k_gene_eqc) at 544 k warp instructions per C3
+// cell, spread over block-wide sorts of record-sized arrays living in L2; this kernel sizes every
+// structure by what the cell actually contains and never sorts records:
+//
+//   load      refs / record offsets (16-bit, relative) / UMIs -> arena
+//   phase 1   record -> eq-class: open-address table of REPRESENTATIVE RECORD indices, labels
+//             compared in place (no stored hashes, no reseeding)
+//   phase 2   (class, UMI) vertices: same kind of table, read count in the entry's upper 16 bits
+//   compact   table slots -> dense vertex arrays  vumi[V], vinfo[V] = class << 16 | reads
+//   phase 3   UMI -> vertex chains (table of chain heads) + 2-hash Bloom bitmap of the UMIs
+//   phase 4   union-find over PUG edges: own-UMI chain successors + the 3*L substitutions that pass
+//             the Bloom test (one lane per vertex). The PUG is never stored.
+//   phase 5   components: singletons emit directly; the vertices of larger components are
+//             listed, sorted by root, and each component (<= 32 vertices) is covered by ONE thread
+//             that orders its members canonically (class label lexicographic, UMI), rebuilds the
+//             directed adjacency from pair tests, and runs the greedy monochromatic cover.
+//   counts    unique-only resolutions: winners (output slots) are sorted and run-length counted;
+//             EM resolutions hand their molecules to ge_back (afq_pug.cuh) on arena pointers.
+//
+// Anything that does not fit (arena too small for the cell's actual vertex count, a component
+// with more than 32 vertices, > large_graph_thresh) sends the WHOLE cell to the global-arena
+// kernel's work list, which runs afterwards — results are identical by construction because
+// both kernels implement the same canonical orders.
+#pragma once
+#include "afq_pug.cuh"
+
+namespace afq {
+
+
+constexpr int PS_VARIANTS = 3;       // arena sizes: 72 KB x 3 CTAs/SM, 108 KB x 2, 224 KB x 1
+__host__ __device__ constexpr u32 ps_threads(int v) { return v == 0 ? 256u : (v == 1 ? 512u : 1024u); }
+__host__ __device__ constexpr u32 ps_arena_words(int v) { return v == 0 ? 18u * 1024u : (v == 1 ? 27u * 1024u : 56u * 1024u); }
+__host__ __device__ constexpr u32 ps_min_blocks(int v) { return v == 0 ? 3u : (v == 1 ? 2u : 1u); }
+constexpr u32 PS_EMPTY = 0xFFFFFFFFu;
+constexpr u32 PS_MAX_RECORDS = 32768;   // record indices and read counts share a 32-bit table entry
+constexpr u32 PS_MAX_REFS = 65535;      // 16-bit relative record offsets
+
+__host__ __device__ inline u32 ps_table_size(u32 n) { return pow2_ge(n + n / 4 + 8, 64); }
+
+// Arena words a cell of n records / P alignments is EXPECTED to need (vertex count guessed at
+// n/2; the kernel re-checks with the real counts and falls back if they do not fit).
+__host__ __device__ inline u32 ps_need_words(u32 n, u32 P, bool gene, bool em) {
+  const u32 rec = n + (n + 1) / 2 + ps_table_size(n);          // UMIs, classes, table: dead after compaction
+  const u32 vest = n / 2 + 16;
+  u32 bw = pow2_ge(2 * vest, 64); if (bw > 4096) bw = 4096;
+  const u32 post = pow2_ge(vest + vest / 2 + 2, 64) + bw + 2 * vest + (em ? 0 : pow2_ge(vest, 1));
+  u32 w = P + (n + 2) / 2 + (gene ? (n + 1) / 2 : 0) + rec + 2 * vest + (post > rec ? post - rec : 0);
+  if (em) w += 2 * vest + P / 2 + 64;
+  return w;
+}
+// smallest arena variant that is expected to hold the cell, or -1
+__host__ __device__ inline int ps_variant_for(u64 n, u64 P, bool gene, bool em) {
+  if (n >= PS_MAX_RECORDS || P >= PS_MAX_REFS || n == 0) return -1;
+  const u32 need = ps_need_words((u32)n, (u32)P, gene, em);
+  for (int v = 0; v < PS_VARIANTS; ++v)
+    if (need <= ps_arena_words(v)) return v;
+  return -1;
+}
+
+struct PsExtra {
+  u32 fail;       // the cell must be redone by the global-arena kernel
+  u32 n_mlist;    // vertices in components of size > 1
+  u32 n_win;      // winners (unique-only resolutions)
+  u32 szc[SMALL_COMP + 4];   // multi-vertex components per size (counting sort of their roots)
+};
+
+// all 32 lanes of the warp call; lanes with pred get consecutive indices from *counter
+__device__ __forceinline__ u32 warp_bump(u32* counter, bool pred) {
+  const u32 m = __ballot_sync(0xFFFFFFFFu, pred);
+  if (!m) return 0;
+  const u32 lane = lane_id();
+  const u32 leader = (u32)__ffs((int)m) - 1;
+  u32 base = 0;
+  if (lane == leader) base = atomicAdd(counter, (u32)__popc(m));
+  base = __shfl_sync(0xFFFFFFFFu, base, (int)leader);
+  return base + (u32)__popc(m & ((1u << lane) - 1u));
+}
+
+struct PsCell {
+  const KArgs* a;
+  u32* refs;            // [P] transcript ids (gene ids after the in-place projection, PUG_GENE)
+  const u16* roff;      // [n+1] record offsets into refs
+  const u16* rlen;      // [n] label lengths (PUG_GENE) or nullptr (length = offset difference)
+  const u32* vumi;      // [V]
+  const u32* vinfo;     // [V] class (representative record) << 16 | read count
+  bool gene;            // labels already are gene ids
+  __device__ __forceinline__ const u32* lab(u32 r) const { return refs + roff[r]; }
+  __device__ __forceinline__ u32 len(u32 r) const { return rlen ? (u32)rlen[r] : (u32)roff[r + 1] - (u32)roff[r]; }
+  __device__ __forceinline__ u32 vcls(u32 v) const { return vinfo[v] >> 16; }
+  __device__ __forceinline__ u32 vcnt(u32 v) const { return vinfo[v] & 0xFFFFu; }
+  __device__ __forceinline__ u32 gene_of(u32 x) const { return gene ? x : __ldg(a->t2g + x); }
+  __device__ __forceinline__ bool related(u32 cv, u32 cw) const {   // classes share a reference
+    return cv == cw || sorted_share(lab(cv), len(cv), lab(cw), len(cw));
+  }
+};
+
+// where molecules go
+struct PsSink {
+  u32 mode;             // 0 unique-only gene mode, 1 unique-only USA, 2 labels for ge_back (EM)
+  u32 uo, ao;
+  u32* A;               // arena base (mode 2: labels are stored at word offsets from it)
+  u32 lab_lo, lab_hi;   // mode 2: label bump region [lab_lo, lab_hi)
+  u32* mol_off; u32* mol_len;
+  GeShared* sh;         // n_mol / lab_bump
+  PsExtra* ex;
+};
+
+// One molecule whose transcript label is { t in l0[0..n0) : keep(t) } (ascending). Returns the
+// output slot for the unique-only modes (NONE32: contributes nothing); mode 2 stores the sorted
+// gene label and returns NONE32.
+template <class Keep>
+__device__ __forceinline__ u32 ps_emit(const PsCell& c, const PsSink& sk, const u32* l0, u32 n0, Keep keep) {
+  if (sk.mode == 0) {
+    // em_optimize(only_unique), src/em.rs:499-514: only single-gene labels count
+    u32 g0 = NONE32;
+    for (u32 k = 0; k < n0; ++k) {
+      const u32 t = l0[k];
+      if (!keep(t)) continue;
+      const u32 gg = c.gene_of(t);
+      if (g0 == NONE32) g0 = gg;
+      else if (gg != g0) return NONE32;
+    }
+    return g0;
+  }
+  if (sk.mode == 1) {
+    // utils::extract_counts, src/utils.rs:673-756: sorted-unique gene label of <= 10 ids -> S/U/A slot
+    u32 best[11];
+    u32 nb = 0;
+    for (u32 k = 0; k < n0; ++k) {
+      const u32 t = l0[k];
+      if (!keep(t)) continue;
+      const u32 gg = c.gene_of(t);
+      u32 q = 0;
+      while (q < nb && best[q] < gg) ++q;
+      if (q < nb && best[q] == gg) continue;
+      if (nb == 11) continue;                       // already too long to matter
+      for (u32 j = nb; j > q; --j) best[j] = best[j - 1];
+      best[q] = gg;
+      ++nb;
+    }
+    if (nb > 10) return NONE32;
+    return usa_slot_for_label(best, nb, sk.uo, sk.ao);
+  }
+  const u32 used = atomicAdd(&sk.sh->lab_bump, n0) + n0;     // labels grow DOWN from lab_hi
+  if (used > sk.lab_hi - sk.lab_lo) { sk.ex->fail = 1; return NONE32; }
+  const u32 off = sk.lab_hi - used;
+  u32* dst = sk.A + off;
+  u32 m = 0;
+  for (u32 k = 0; k < n0; ++k) {
+    const u32 t = l0[k];
+    if (keep(t)) dst[m++] = c.gene_of(t);
+  }
+  if (!c.gene) m = sort_dedup_small(dst, m);
+  const u32 id = atomicAdd(&sk.sh->n_mol, 1u);
+  sk.mol_off[id] = off;
+  sk.mol_len[id] = m;
+  return NONE32;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Greedy cover of one component with 2..32 vertices by ONE thread (get_num_molecules cover loop,
+// src/pugutils.rs:1097-1261, + collapse_vertices, src/pugutils.rs:308-391). The members hang on
+// the root's list (head / nxt). Start vertices are visited in ascending (class label, UMI) order.
+// ---------------------------------------------------------------------------------------------
+__device__ inline void ps_cover(const PsCell& c, const PsSink& sk, u32* winners, const u32* head, const u32* nxt, u32 r, bool exact, u32* gbm) {
+  u32 mem[SMALL_COMP];
+  u32 am[SMALL_COMP];
+  u32 s = 0;
+  for (u32 x = head[r]; x != PS_EMPTY; x = nxt[x], ++s) {    // insertion sort into canonical order
+    const u32 cx = c.vcls(x), ux = c.vumi[x];
+    u32 j = s;
+    while (j > 0) {
+      const u32 y = mem[j - 1];
+      const u32 cy = c.vcls(y);
+      const bool less = cx == cy ? ux < c.vumi[y] : label_less(c.lab(cx), c.len(cx), c.lab(cy), c.len(cy));
+      if (!less) break;
+      mem[j] = y;
+      --j;
+    }
+    mem[j] = x;
+  }
+  for (u32 i = 0; i < s; ++i) am[i] = 0;
+  for (u32 i = 0; i < s; ++i) {    // has_edge, src/pugutils.rs:76-99
+    const u32 ui = c.vumi[mem[i]], ci = c.vcls(mem[i]), ni = c.vcnt(mem[i]);
+    for (u32 j = i + 1; j < s; ++j) {
+      const u32 x = ui ^ c.vumi[mem[j]];
+      const u32 hd = (u32)__popc((x | (x >> 1)) & 0x55555555u);
+      if (exact ? hd != 0 : hd > 1) continue;
+      const u32 cj = c.vcls(mem[j]);
+      if (!c.related(ci, cj)) continue;
+      const u32 nj = c.vcnt(mem[j]);
+      if (out_edge(hd, ni, nj)) am[i] |= 1u << j;
+      if (out_edge(hd, nj, ni)) am[j] |= 1u << i;
+    }
+  }
+  u32 unc = s == 32 ? 0xFFFFFFFFu : ((1u << s) - 1);
+  while (unc) {
+    u32 best_mask = 0, best_size = 0;
+    const u32 remaining = (u32)__popc(unc);
+    for (u32 i = 0; i < s && best_size < remaining; ++i) {
+      if (!(unc >> i & 1)) continue;
+      const u32 ci = c.vcls(mem[i]);
+      const u32* li = c.lab(ci);
+      const u32 ln = c.len(ci);
+      for (u32 k = 0; k < ln; ++k) {
+        const u32 t = li[k];
+        u32 vis = 1u << i, fr = 1u << i, got = 1u << i;
+        while (fr) {
+          u32 nx = 0;
+          u32 f = fr;
+          while (f) {
+            const u32 x = (u32)__ffs((int)f) - 1;
+            f &= f - 1;
+            u32 cand = am[x] & unc & ~vis;
+            vis |= cand;
+            while (cand) {
+              const u32 j = (u32)__ffs((int)cand) - 1;
+              cand &= cand - 1;
+              const u32 cj = c.vcls(mem[j]);
+              if (cj == ci || sorted_contains(c.lab(cj), c.len(cj), t)) nx |= 1u << j;
+            }
+          }
+          got |= nx;
+          fr = nx;
+        }
+        const u32 sz = (u32)__popc(got);
+        if (sz > best_size) { best_size = sz; best_mask = got; }
+        if (best_size == remaining) break;
+      }
+    }
+    if (best_mask == 0) {   // only a class with an empty label can get here: cover it alone
+      best_mask = unc & (0u - unc);
+    }
+    // label = intersection of the MCC's class labels (src/pugutils.rs:1161-1188), projected to genes
+    const u32 first = (u32)__ffs((int)best_mask) - 1;
+    const u32 cf = c.vcls(mem[first]);
+    const u32 rest = best_mask & (best_mask - 1);
+    const u32 slot = ps_emit(c, sk, c.lab(cf), c.len(cf), [&](u32 t) {
+      u32 r = rest;
+      while (r) {
+        const u32 j = (u32)__ffs((int)r) - 1;
+        r &= r - 1;
+        const u32 cj = c.vcls(mem[j]);
+        if (cj != cf && !sorted_contains(c.lab(cj), c.len(cj), t)) return false;
+      }
+      return true;
+    });
+    if (sk.mode != 2 && slot != NONE32) {
+      winners[atomicAdd(&sk.ex->n_win, 1u)] = slot;
+      if (gbm) atomicOr(&gbm[slot >> 5], 1u << (slot & 31));
+    }
+    unc &= ~best_mask;
+  }
+}
+
+// Bloom bitmap of the cell's UMIs with two GF(2)-LINEAR hashes: H(u ^ delta) = H(u) ^ H(delta), so
+// the 3*L single-base substitutions of a UMI cost one XOR with a compile-time constant each instead
+// of a multiplicative hash (ncu r1t: the Bloom tests were 15 % of the kernel's instructions).
+__host__ __device__ constexpr u32 ps_h1(u32 u) { return u ^ (u >> 6) ^ (u >> 15); }
+__host__ __device__ constexpr u32 ps_h2(u32 u) { return (u >> 3) ^ (u >> 10) ^ (u >> 20) ^ (u << 7); }
+__device__ __forceinline__ u32 ps_umi_slot(u32 umi, u32 log2cap) { return (umi * 0x9E3779B1u) >> (32 - log2cap); }
+
+// carve the ge_back arrays for M molecules / Lm label words from words [lo, hi) of the arena;
+// returns false if they do not fit
+__device__ inline bool ps_back_carve(u32* A, u32 lo, u32 hi, u32 M, u32 Lm, u32 per, GePtrs* o) {
+  u64 off = (u64)lo * 4;
+  auto take = [&](u64 bytes) { off = align8(off); u8* r = reinterpret_cast<u8*>(A) + off; off += bytes; return r; };
+  const u32 Mp = next_pow2(M ? M : 1), Lp = next_pow2(Lm ? Lm : 1), TK = Mp > Lp ? Mp : Lp;
+  const u32 Sp = next_pow2(Lm * per ? Lm * per : 1);
+  o->mkey = (u64*)take(8ull * Mp); o->midx = (u32*)take(4ull * Mp);
+  o->gcls_m = (u32*)take(4ull * (M + 1)); o->gcls_cnt = (u32*)take(4ull * (M + 1)); o->gcls_eoff = (u32*)take(4ull * (M + 2));
+  o->tkey = (u64*)take(8ull * TK);
+  o->ent_idx = (u32*)take(4ull * (TK + 1)); o->ent_loc = (u32*)take(4ull * (Lm + 1));
+  o->sup = (u32*)take(4ull * Sp); o->g_off = (u32*)take(4ull * (Sp + 2));
+  o->alpha_in = (float*)take(4ull * Sp); o->alpha_out = (float*)take(4ull * Sp); o->cls_inv = (float*)take(4ull * (M + 1));
+  o->sib_a = (u32*)take(4ull * Sp); o->sib_b = (u32*)take(4ull * Sp);
+  return align8(off) <= (u64)hi * 4;
+}
+
+// =============================================================================================
+// One cell. Returns false when the cell has to be redone by the global-arena kernel (nothing has
+// been written for it in that case).
+// =============================================================================================
+__device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A, u32 AW, GeShared* sh, PsExtra* ex,
+                               GePtrs* s_ptrs) {
+  const u32 T = blockDim.x, tid = threadIdx.x;
+  const u64 r0 = a.cell_rec_off[cell], r1 = a.cell_rec_off[cell + 1];
+  const u32 n = (u32)(r1 - r0);
+  const u32 f0 = a.ref_off[r0];
+  const u32 P = a.ref_off[r1] - f0;
+  const bool gene = g.ge_mode == GE_MODE_PUG_GENE;
+  const bool usa = a.usa_mode != 0;
+  const bool em = g.only_unique == 0;
+
+  // ---- arena layout, phase A --------------------------------------------------------------------
+  u32 off = 0;
+  u32* refs = A + off; off += P;
+  u16* roff = reinterpret_cast<u16*>(A + off); off += (n + 2) / 2;
+  u16* rlen = nullptr;
+  if (gene) { rlen = reinterpret_cast<u16*>(A + off); off += (n + 1) / 2; }
+  const u32 off_rec = off;                       // everything from here is re-carved after compaction
+  u32* umi = A + off; off += n;
+  u16* rcls = reinterpret_cast<u16*>(A + off); off += (n + 1) / 2;
+  const u32 TN = ps_table_size(n), tl2 = ilog2(TN), tmask = TN - 1;
+  u32* tab = A + off; off += TN;
+  const u32 off_dense = off;
+  if (tid == 0) { ex->fail = (off_dense > AW || n >= PS_MAX_RECORDS || P >= PS_MAX_REFS) ? 1u : 0u; ex->n_mlist = 0; ex->n_win = 0;
+                  sh->n_mol = 0; sh->lab_bump = 0; sh->alt = 0; sh->flag = 0; sh->cnt0 = sh->cnt1 = sh->cnt2 = sh->cnt3 = 0; }
+  __syncthreads();
+  if (ex->fail) { __syncthreads(); return false; }
+  // ---- load: the cell's records are read from HBM once, coalesced --------------------------------
+  for (u32 i = tid; i < P; i += T) refs[i] = a.refs[(u64)f0 + i];
+  for (u32 i = tid; i <= n; i += T) roff[i] = (u16)(a.ref_off[r0 + i] - f0);
+  for (u32 i = tid; i < n; i += T) umi[i] = a.umi[r0 + i];
+  for (u32 i = tid; i < TN; i += T) tab[i] = PS_EMPTY;
+  __syncthreads();
+  PsCell c;
+  c.a = &a; c.refs = refs; c.roff = roff; c.rlen = rlen; c.gene = gene; c.vumi = nullptr; c.vinfo = nullptr;
+  if (gene) {   // sorted-dedup gene projection of every record, in place (src/eq_class.rs:742-744)
+    GE_FOR(i, n) {
+      u32* dst = refs + roff[i];
+      const u32 ln = (u32)roff[i + 1] - roff[i];
+      for (u32 k = 0; k < ln; ++k) dst[k] = __ldg(a.t2g + dst[k]);
+      rlen[i] = (u16)sort_dedup_small(dst, ln);
+    }
+    __syncthreads();
+  }
+  // ---- phase 1: record -> eq-class (representative record) ----------------------------------------
+  GE_FOR(i, n) {
+    const u32* li = c.lab(i);
+    const u32 ln = c.len(i);
+    u32 h = (ln + 1) * 0x9E3779B1u;
+    for (u32 k = 0; k < ln; ++k) { h = (h ^ li[k]) * 0x85EBCA6Bu; h ^= h >> 13; }
+    u32 s = (h * 0x9E3779B1u) >> (32 - tl2);
+    for (;;) {
+      u32 cur = *(volatile u32*)&tab[s];
+      if (cur == PS_EMPTY) {
+        cur = atomicCAS(&tab[s], PS_EMPTY, i);
+        if (cur == PS_EMPTY) { rcls[i] = (u16)i; break; }
+      }
+      if (c.len(cur) == ln && label_equal(c.lab(cur), ln, li, ln)) { rcls[i] = (u16)cur; break; }
+      s = (s + 1) & tmask;
+    }
+  }
+  __syncthreads();
+  for (u32 i = tid; i < TN; i += T) tab[i] = PS_EMPTY;
+  __syncthreads();
+  // ---- phase 2: (class, UMI) vertices; entry = representative record | reads << 16 ---------------
+  GE_FOR(i, n) {
+    const u32 cc = rcls[i], u = umi[i];
+    u32 h = (u ^ (cc * 0x9E3779B1u)) * 0x85EBCA6Bu;
+    h ^= h >> 15;
+    u32 s = (h * 0xC2B2AE35u) >> (32 - tl2);
+    for (;;) {
+      u32 cur = *(volatile u32*)&tab[s];
+      if (cur == PS_EMPTY) {
+        cur = atomicCAS(&tab[s], PS_EMPTY, i | (1u << 16));
+        if (cur == PS_EMPTY) break;
+      }
+      const u32 r = cur & 0xFFFFu;
+      if (rcls[r] == cc && umi[r] == u) { atomicAdd(&tab[s], 1u << 16); break; }
+      s = (s + 1) & tmask;
+    }
+  }
+  __syncthreads();
+  // ---- compaction: table slots -> dense vertices (appended behind the table) ----------------------
+  u32 V;
+  {
+    const u32 K = (TN + T - 1) / T;
+    u32 lo = tid * K; if (lo > TN) lo = TN;
+    u32 hi = lo + K; if (hi > TN) hi = TN;
+    u32 cnt = 0;
+    for (u32 i = lo; i < hi; ++i) cnt += tab[i] != PS_EMPTY ? 1u : 0u;
+    u32 pos = block_exscan(cnt, sh->scan, &V);
+    // dense arrays + (EM) molecule offsets / lengths at the top of the arena must fit
+    const u32 top = em ? AW - 2 * V : AW;
+    if (off_dense + 2 * V > top || 2 * V > AW) return false;            // uniform: V is a block-wide value
+    u32* vumi_w = A + off_dense;
+    u32* vinfo_w = vumi_w + V;
+    for (u32 i = lo; i < hi; ++i) {
+      const u32 e = tab[i];
+      if (e == PS_EMPTY) continue;
+      const u32 r = e & 0xFFFFu;
+      vumi_w[pos] = umi[r];
+      vinfo_w[pos] = ((u32)rcls[r] << 16) | (e >> 16);
+      ++pos;
+    }
+    c.vumi = vumi_w; c.vinfo = vinfo_w;
+  }
+  __syncthreads();
+  const u32* vumi = c.vumi;
+
+  // ---- re-carve: chains, union-find, Bloom bitmap, winners go into the dead record arrays
+  // [off_rec, off_dense) first and into the free space behind the dense vertices after that ------
+  u32 segA = off_rec, segB = off_dense + 2 * V;
+  const u32 topB = em ? AW - 2 * V : AW;
+  bool fits = true;
+  auto alloc = [&](u32 words) -> u32* {
+    if (segA + words <= off_dense) { u32* r = A + segA; segA += words; return r; }
+    if (segB + words <= topB) { u32* r = A + segB; segB += words; return r; }
+    fits = false;
+    return A;
+  };
+  const u32 NU = pow2_ge(V + V / 2 + 2, 64), ul2 = ilog2(NU), umask = NU - 1;
+  u32 BW = pow2_ge(2 * V, 64); if (BW > 4096) BW = 4096;
+  u32* utab = alloc(NU);                              // later: the multi-vertex list, run starts
+  u32* bloom = alloc(BW);
+  u32* vnext = alloc(V);                              // later: root of every vertex
+  u32* parent = alloc(V);                             // later: component sizes
+  u32* winners = em ? A : alloc(next_pow2(V ? V : 1));
+  u32* nxt = BW >= V ? bloom : alloc(V);              // component member lists (the bitmap is dead by then)
+  if (!fits) return false;                            // uniform (V is block-wide)
+  const u32 Wg = (a.num_rows + 31) >> 5;
+  u32* gbm = nullptr;                                 // unique-only: presence bitmap + prefix over the output slots
+  if (!em) { gbm = alloc(2 * Wg); if (!fits) gbm = nullptr; }
+  // EM: molecule labels grow down from the molecule offsets / lengths at the top of the arena
+  PsSink sk;
+  sk.mode = em ? 2u : (usa ? 1u : 0u);
+  sk.uo = a.uo; sk.ao = a.ao; sk.A = A; sk.sh = sh; sk.ex = ex;
+  sk.lab_lo = segB; sk.lab_hi = em ? topB : segB;
+  sk.mol_off = A + (AW - V); sk.mol_len = A + (AW - 2 * V);
+  // ---- phase 3: UMI -> vertex chains, Bloom bitmap -------------------------------------------------
+  const u32 bmask = (32u * BW) - 1;
+  for (u32 i = tid; i < NU; i += T) utab[i] = PS_EMPTY;
+  for (u32 i = tid; i < BW; i += T) bloom[i] = 0;
+  if (gbm) for (u32 i = tid; i < 2 * Wg; i += T) gbm[i] = 0;
+  if (tid < 36) ex->szc[tid] = 0;
+  __syncthreads();
+  GE_FOR(v, V) {
+    const u32 um = vumi[v];
+    u32 s = ps_umi_slot(um, ul2);
+    for (;;) {
+      u32 cur = *(volatile u32*)&utab[s];
+      if (cur == PS_EMPTY) {
+        cur = atomicCAS(&utab[s], PS_EMPTY, v);
+        if (cur == PS_EMPTY) { vnext[v] = PS_EMPTY; break; }
+      }
+      if (vumi[cur] == um) { vnext[v] = atomicExch(&utab[s], v); break; }
+      s = (s + 1) & umask;
+    }
+    parent[v] = v;
+    const u32 b1 = ps_h1(um) & bmask, b2 = ps_h2(um) & bmask;
+    atomicOr(&bloom[b1 >> 5], 1u << (b1 & 31));
+    atomicOr(&bloom[b2 >> 5], 1u << (b2 & 31));
+  }
+  __syncthreads();
+  // ---- phase 4: union-find over the PUG's edges (any edge type connects; src/pugutils.rs:278-301) --
+  // (a) same UMI, another class sharing a reference: each chain pair once, from its earlier member
+  GE_FOR(v, V) {
+    const u32 cv = c.vcls(v);
+    for (u32 w = vnext[v]; w != PS_EMPTY; w = vnext[w])
+      if (c.related(cv, c.vcls(w))) uf_union(parent, v, w);
+  }
+  // (b) Hamming distance 1: every lane tests the 3*L substitutions of its own vertex's UMI against
+  // the Bloom bitmap in straight-line code (hits collected in a mask), then the rare hits are
+  // looked up in the chain table, the warp re-joining at a vote per round
+  const u32 sub_len = g.pug_exact_umi ? 0u : g.umi_len;
+  if (sub_len)
+    for (u32 vb = 0; vb < V; vb += T) {
+      const u32 v = vb + tid;
+      const bool act = v < V;
+      const u32 u = act ? vumi[v] : 0u, cv = act ? c.vcls(v) : 0u;
+      const u32 h1 = ps_h1(u), h2 = ps_h2(u);
+      unsigned long long hits = 0;
+#pragma unroll
+      for (u32 pos = 0; pos < 16; ++pos) {
+        if (pos < sub_len) {
+#pragma unroll
+          for (u32 d = 1; d <= 3; ++d) {
+            const u32 b1 = (h1 ^ ps_h1(d << (2 * pos))) & bmask, b2 = (h2 ^ ps_h2(d << (2 * pos))) & bmask;
+            const u32 bit = (bloom[b1 >> 5] >> (b1 & 31)) & (bloom[b2 >> 5] >> (b2 & 31)) & 1u;
+            hits |= (unsigned long long)bit << (pos * 3 + d - 1);
+          }
+        }
+      }
+      if (!act) hits = 0;
+      while (__any_sync(0xFFFFFFFFu, hits != 0)) {
+        if (hits) {
+          const u32 k = (u32)__ffsll((long long)hits) - 1;
+          hits &= hits - 1;
+          const u32 cu = u ^ ((k % 3 + 1) << (2 * (k / 3)));
+          u32 s = ps_umi_slot(cu, ul2);
+          for (;;) {
+            const u32 cur = utab[s];
+            if (cur == PS_EMPTY) break;
+            if (vumi[cur] == cu) {
+              for (u32 w = cur; w != PS_EMPTY; w = vnext[w])
+                if (w > v && c.related(cv, c.vcls(w))) uf_union(parent, v, w);   // each pair once
+              break;
+            }
+            s = (s + 1) & umask;
+          }
+        }
+      }
+    }
+  __syncthreads();
+  // ---- phase 5: components ------------------------------------------------------------------------
+  // members of a component hang on a list at its root; the roots of components with > 1 vertex are
+  // counting-sorted by component size so that the lanes of a warp cover components of (nearly)
+  // equal size (ncu r1t: one lane per sorted-list run start left 2-3 lanes active in the cover)
+  u32* root = vnext;
+  GE_FOR(v, V) root[v] = uf_find(parent, v);
+  __syncthreads();
+  u32* csz = parent;
+  u32* head = utab;                 // [V]   (NU >= V + V/2 + 2)
+  u32* clist = utab + V;            // [<= V/2] roots of the multi-vertex components, by size
+  GE_FOR(v, V) { csz[v] = 0; head[v] = PS_EMPTY; }
+  __syncthreads();
+  GE_FOR(v, V) atomicAdd(&csz[root[v]], 1u);
+  __syncthreads();
+  for (u32 vb = 0; vb < V; vb += T) {
+    const u32 v = vb + tid;
+    u32 slot = NONE32;
+    if (v < V) {
+      const u32 r = root[v];
+      const u32 sz = csz[r];
+      if (sz == 1) {   // singleton component: the class label itself (src/pugutils.rs:1262-1322)
+        const u32 cv = c.vcls(v);
+        slot = ps_emit(c, sk, c.lab(cv), c.len(cv), [](u32) { return true; });
+      } else {
+        nxt[v] = atomicExch(&head[r], v);
+        if (v == r) atomicAdd(&ex->szc[sz > SMALL_COMP ? SMALL_COMP + 1 : sz], 1u);
+      }
+    }
+    const u32 wi = warp_bump(&ex->n_win, slot != NONE32);
+    if (slot != NONE32) { winners[wi] = slot; if (gbm) atomicOr(&gbm[slot >> 5], 1u << (slot & 31)); }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    u32 run = 0;
+    for (u32 z = 0; z <= SMALL_COMP + 1; ++z) { const u32 t = ex->szc[z]; ex->szc[z] = run; run += t; }
+    ex->n_mlist = run;
+    // a component of more than 32 vertices (or beyond --large-graph-thresh): global-arena kernel
+    if (ex->szc[SMALL_COMP + 1] != run) ex->fail = 1;
+    for (u32 z = 2; z <= SMALL_COMP; ++z) if (z > g.large_graph_thresh && ex->szc[z] != (z == SMALL_COMP ? ex->szc[SMALL_COMP + 1] : ex->szc[z + 1])) ex->fail = 1;
+  }
+  __syncthreads();
+  if (ex->fail) { __syncthreads(); return false; }
+  const u32 K = ex->n_mlist;
+  if (K) {
+    GE_FOR(v, V) if (root[v] == v && csz[v] > 1) clist[atomicAdd(&ex->szc[csz[v]], 1u)] = v;
+    __syncthreads();
+    GE_FOR(k, K) ps_cover(c, sk, winners, head, nxt, clist[k], g.pug_exact_umi != 0, gbm);
+  }
+  __syncthreads();
+  if (ex->fail) { __syncthreads(); return false; }
+
+  const u64 out_base = f0;
+  if (em) {
+      // ---- EM resolutions: hand the molecules to the shared back end on arena pointers --------------
+    const u32 M = sh->n_mol, Lm = sh->lab_bump;
+    if (tid == 0) {
+      GePtrs pp{};
+      const bool ok = ps_back_carve(A, 0, sk.lab_hi - Lm, M, Lm, usa ? 3u : 1u, &pp);
+      pp.mlab = A; pp.mol_off = sk.mol_off; pp.mol_len = sk.mol_len;
+      *s_ptrs = pp;
+      // (a separate flag word: ex->fail was just read by the other threads without a barrier behind)
+      sh->flag = ok ? 0u : 1u;
+    }
+    __syncthreads();
+    if (sh->flag) { __syncthreads(); return false; }
+    GeCell gc(*s_ptrs);
+    gc.a = &a; gc.g = &g; gc.scratch = nullptr; gc.scratch_budget = 0;
+    gc.vk_s = nullptr; gc.vc_s = nullptr; gc.cl_off_s = nullptr; gc.cl_len_s = nullptr;
+    gc.r0 = r0; gc.f0 = f0; gc.gene_labels = gene;
+    ge_back(a, g, cell, gc, sh);
+    return true;
+  }
+  // ---- unique-only resolutions: count the winners per output slot -----------------------------------
+  const u32 m = ex->n_win;
+  u32 nnz = 0, lmax = 0;
+  if (m && gbm) {
+    // presence bitmap over the output slots (bits were set as the winners were produced): a prefix
+    // popcount ranks the expressed slots (= CSR column order), every winner bumps its slot's counter
+    u32* gpre = gbm + Wg;
+    u32* gcnt = utab;                  // [nnz <= m <= V] (lists are dead)
+    {
+      const u32 Kw = (Wg + T - 1) / T;
+      u32 lo = tid * Kw; if (lo > Wg) lo = Wg;
+      u32 hi = lo + Kw; if (hi > Wg) hi = Wg;
+      u32 cnt = 0;
+      for (u32 i = lo; i < hi; ++i) cnt += (u32)__popc(gbm[i]);
+      u32 pos = block_exscan(cnt, sh->scan, &nnz);
+      for (u32 i = lo; i < hi; ++i) { gpre[i] = pos; pos += (u32)__popc(gbm[i]); }
+    }
+    for (u32 i = tid; i < nnz; i += T) gcnt[i] = 0;
+    __syncthreads();
+    for (u32 i = tid; i < m; i += T) {
+      const u32 v = winners[i];
+      const u32 rank = gpre[v >> 5] + (u32)__popc(gbm[v >> 5] & ((1u << (v & 31)) - 1u));
+      if (atomicAdd(&gcnt[rank], 1u) == 0) a.stage_col[out_base + rank] = v;
+    }
+    __syncthreads();
+    const float mean = __fdiv_rn((float)m, (float)nnz);
+    u32 lover = 0;
+    for (u32 j = tid; j < nnz; j += T) {
+      const u32 cn = gcnt[j];
+      a.stage_val[out_base + j] = (float)cn;
+      lmax = cn > lmax ? cn : lmax;
+      if ((float)cn > mean) ++lover;
+    }
+    if (lmax) atomicMax(&sh->cnt3, lmax);
+    if (lover) atomicAdd(&sh->cnt0, lover);
+    __syncthreads();
+  } else if (m) {
+    // gene axis too wide for the arena: sort the winners, run-length count
+    const u32 Mp = next_pow2(m);
+    for (u32 i = m + tid; i < Mp; i += T) winners[i] = NONE32;
+    __syncthreads();
+    block_bitonic_u32(winners, Mp);
+    u32* starts = utab;                // run starts (the lists are dead)
+    u32 base = 0;
+    for (u32 c0 = 0; c0 < m; c0 += T) {
+      const u32 i = c0 + tid;
+      const u32 st = (i < m && (i == 0 || winners[i - 1] != winners[i])) ? 1u : 0u;
+      u32 tot;
+      const u32 pos = block_exscan(st, sh->scan, &tot);
+      if (st) starts[base + pos] = i;
+      base += tot;
+    }
+    nnz = base;
+    __syncthreads();
+    for (u32 j = tid; j < nnz; j += T) {
+      const u32 i0 = starts[j], i1 = (j + 1 < nnz) ? starts[j + 1] : m;
+      a.stage_col[out_base + j] = winners[i0];
+      a.stage_val[out_base + j] = (float)(i1 - i0);
+      lmax = (i1 - i0) > lmax ? (i1 - i0) : lmax;
+    }
+    if (lmax) atomicMax(&sh->cnt3, lmax);
+    __syncthreads();
+    // NumGenesOverMean (src/quant.rs:1190-1194)
+    const float mean = __fdiv_rn((float)m, (float)nnz);
+    u32 lover = 0;
+    for (u32 j = tid; j < nnz; j += T) {
+      const u32 i0 = starts[j], i1 = (j + 1 < nnz) ? starts[j + 1] : m;
+      if ((float)(i1 - i0) > mean) ++lover;
+    }
+    if (lover) atomicAdd(&sh->cnt0, lover);
+    __syncthreads();
+  }
+  if (tid == 0) {
+    a.sum_umi[cell] = (float)m;
+    a.max_umi[cell] = (float)sh->cnt3;
+    a.num_expr[cell] = nnz;
+    a.num_over_mean[cell] = sh->cnt0;
+    a.flags[cell] = nnz == 0 ? 4 : 0;
+  }
+  __syncthreads();
+  return true;
+}
+
+constexpr int PS_LIST0 = NUM_BINS + 3;      // bin_list rows of the three arena variants
+
+template <int VAR>
+__global__ void __launch_bounds__(ps_threads(VAR), ps_min_blocks(VAR)) k_pug_smem(KArgs a, GeArgs g) {
+  AFQ_DYN_SMEM(smem_raw);
+  u32* A = reinterpret_cast<u32*>(smem_raw);
+  __shared__ GeShared sh;
+  __shared__ PsExtra ex;
+  __shared__ GePtrs s_ptrs;
+  const u32 count = a.ctl->bin_count[PS_LIST0 + VAR];
+  const u32* list = a.bin_list + (u64)(PS_LIST0 + VAR) * a.n_cells;
+  for (;;) {
+    if (threadIdx.x == 0) sh.job = atomicAdd(&a.ctl->bin_cursor[PS_LIST0 + VAR], 1u);
+    __syncthreads();
+    const u32 job = sh.job;
+    __syncthreads();
+    if (job >= count) break;
+    const u32 cell = list[job];
+    const u32 AW = (g.ps_limit_words && g.ps_limit_words < ps_arena_words(VAR)) ? g.ps_limit_words : ps_arena_words(VAR);
+    const bool ok = ps_cell(a, g, cell, A, AW, &sh, &ex, &s_ptrs);
+    if (!ok && threadIdx.x == 0) {
+      const u32 idx = atomicAdd(&a.ctl->bin_count[GE_LIST_NORMAL], 1u);
+      a.bin_list[(u64)GE_LIST_NORMAL * a.n_cells + idx] = cell;
+    }
+    __syncthreads();
+  }
+}
+
+// classify cells for the gene-eq-class resolutions: tiny cells go to the cr-like arenas
+// (src/quant.rs:794-846); cells expected to fit a shared-memory arena go to k_pug_smem's lists
+// (ps_mode bit 0: enabled, bit 1: gene-level labels, bit 2: EM); the rest to the k_gene_eqc lists.
+// ge_max_n / ge_max_p cover every non-tiny cell of their size class because k_pug_smem may hand
+// any of its cells back to the k_gene_eqc list.
+__global__ void k_bin_cells_ge(KArgs a, int force_bin, u32 big_records, u32 need_shift, u32 ps_mode) {
+  const u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.n_cells) return;
+  const u64 r0 = a.cell_rec_off[c], r1 = a.cell_rec_off[c + 1];
+  const u64 n = r1 - r0;
+  const u32 p = a.ref_off[r1] - a.ref_off[r0];
+  int b;
+  if (a.tiny_eligible && n < a.small_thresh) {
+    const u64 need = (n < (u64)p ? n : (u64)p) << need_shift;
+    b = NUM_SMEM_BINS;
+#pragma unroll
+    for (int i = NUM_SMEM_BINS - 1; i >= 0; --i)
+      if (need <= (1ull << bin_cap_log2(i))) b = i;
+    if (force_bin >= 0 && force_bin > b) b = force_bin < NUM_SMEM_BINS ? force_bin : NUM_SMEM_BINS;
+    if (b == NUM_SMEM_BINS) atomicMax(&a.ctl->max_cell_refs, p);
+  } else {
+    const int w = n > big_records ? 0 : 1;
+    b = w == 0 ? GE_LIST_BIG : GE_LIST_NORMAL;
+    atomicMax(&a.ctl->ge_max_n[w], (u32)n);
+    atomicMax(&a.ctl->ge_max_p[w], p);
+    if (w == 1 && (ps_mode & 1u)) {
+      const int v = ps_variant_for(n, p, (ps_mode & 2u) != 0, (ps_mode & 4u) != 0);
+      if (v >= 0) b = PS_LIST0 + v;
+    }
+  }
+  const u32 idx = atomicAdd(&a.ctl->bin_count[b], 1u);
+  a.bin_list[(u64)b * a.n_cells + idx] = (u32)c;
+}
+
+}  // namespace afq

@@ -45,6 +45,8 @@ struct EmuLauncher {
   void region_begin() {}
   void region_end() {}
   u32 need_shift() { const char* s = getenv("AFQ_NEED_SHIFT"); return s ? (u32)atoi(s) : 0; }
+  u32 ps_limit_words() { const char* s = getenv("AFQ_PS_LIMIT_WORDS"); return s ? (u32)atoi(s) : 0; }
+  int ps_grid(int) { const char* s = getenv("AFQ_NO_PS"); return (s && atoi(s)) ? 0 : 1; }
 };
 
 struct EmuResult {
@@ -55,7 +57,12 @@ struct EmuResult {
 };
 }  // namespace
 
+static Ctl g_last_ctl;
+
 extern "C" {
+
+// bin_count[] of the last afq_emu_quant call (which kernel took how many cells; tests)
+void afq_emu_last_counts(uint32_t* out, int n) { for (int i = 0; i < n && i <= NUM_LISTS; ++i) out[i] = g_last_ctl.bin_count[i]; }
 
 // k_scan_* and k_bin_* use grids of many CTAs: honoured as is (sequential CTAs).
 int afq_emu_quant(const afq_config* cfg, const uint32_t* tid_to_gid, uint64_t n_refs, const afq_batch* b,
@@ -106,6 +113,7 @@ int afq_emu_quant(const afq_config* cfg, const uint32_t* tid_to_gid, uint64_t n_
     bb.rec_ref_offsets = na_off.data();
   }
   int rc = enqueue_batch(l, *cfg, force_bin, pb, bb, o, err);
+  g_last_ctl = ctl[0];
   if (dev_error) *dev_error = ctl[0].error;
   if (rc == AFQ_OK && ctl[0].error) {
     std::string buf;

@@ -35,6 +35,8 @@ def lib():
         l.afq_emu_quant.restype = C.c_int
         l.afq_emu_quant.argtypes = [C.POINTER(AfqConfig), C.c_void_p, C.c_uint64, C.POINTER(AfqBatch), C.POINTER(AfqResult),
                                     C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t, C.POINTER(C.c_uint32)]
+        l.afq_emu_last_counts.restype = None
+        l.afq_emu_last_counts.argtypes = [C.POINTER(C.c_uint32), C.c_int]
         l.afq_emu_release.restype = None
         l.afq_emu_release.argtypes = [C.c_void_p]
         _lib = l
@@ -56,3 +58,14 @@ def emu_quant(opts: QuantOpts, tid_to_gid, batch: CellBatch, use_na8: bool = Fal
     out = QuantResult.from_c(r)
     lib().afq_emu_release(h)
     return out
+
+
+# bin_list rows (alevin_fry_b200/csrc: NUM_BINS = 7)
+LIST_GE_BIG, LIST_GE_NORMAL, LIST_OVF, LIST_PS0 = 7, 8, 9, 10
+
+
+def last_counts():
+    """cells per work list in the last emu_quant call (which kernel took how many cells)"""
+    out = (C.c_uint32 * 14)()
+    lib().afq_emu_last_counts(out, 14)
+    return list(out)

@@ -192,3 +192,70 @@ def test_emu_all_ones_umi_and_window_holes(res):
     recs = recs * 6 + [(i * 2654435761 % (1 << 32), [i % 64]) for i in range(150)]
     b = CellBatch.from_cells([recs, recs[::-1]])
     check(QuantOpts(resolution=res, num_gene_ids=64, num_rows=64, umi_len=16), t2g, b, res)
+
+
+# ---- k_pug_smem (shared-memory parsimony kernel) -------------------------------------------------
+@pytest.mark.parametrize("res", ["parsimony", "parsimony-em", "parsimony-gene", "parsimony-gene-em"])
+def test_emu_pug_smem_takes_the_cells(res, monkeypatch):
+    spec = synth.SynthSpec(reads_mean=400.0)
+    b = synth.generate(spec, 0, 12)
+    t2g = synth.tid_to_gid(spec)
+    check(opts_for(spec, res), t2g, b, res)
+    cnt = emu_lib.last_counts()
+    n_ps = sum(cnt[emu_lib.LIST_PS0:emu_lib.LIST_PS0 + 3])
+    n_tiny = sum(cnt[:7])
+    assert n_ps > 0 and n_ps + n_tiny == b.n_cells, cnt      # every non-tiny cell binned to k_pug_smem
+    assert cnt[emu_lib.LIST_GE_NORMAL] == 0, cnt                # ... and none handed back
+    # same answer from the global-arena kernel alone
+    monkeypatch.setenv("AFQ_NO_PS", "1")
+    check(opts_for(spec, res), t2g, b, res + "/no-ps")
+    cnt = emu_lib.last_counts()
+    assert sum(cnt[emu_lib.LIST_PS0:emu_lib.LIST_PS0 + 3]) == 0 and cnt[emu_lib.LIST_GE_NORMAL] > 0, cnt
+
+
+@pytest.mark.parametrize("res", ["parsimony", "parsimony-em"])
+@pytest.mark.parametrize("limit", [600, 2500, 4000])
+def test_emu_pug_smem_hands_back_what_does_not_fit(res, limit, monkeypatch):
+    # a smaller arena than the binning assumed: cells fail at different points (layout, dense
+    # vertices, EM back end) and must come out of k_gene_eqc with identical results
+    monkeypatch.setenv("AFQ_PS_LIMIT_WORDS", str(limit))
+    spec = synth.SynthSpec(reads_mean=400.0)
+    b = synth.generate(spec, 0, 12)
+    check(opts_for(spec, res), synth.tid_to_gid(spec), b, f"{res}/{limit}")
+    cnt = emu_lib.last_counts()
+    assert cnt[emu_lib.LIST_GE_NORMAL] > 0, cnt
+
+
+@pytest.mark.parametrize("res", ["parsimony", "parsimony-em", "parsimony-gene"])
+def test_emu_pug_smem_big_components_fall_back(res):
+    # 4-base UMIs: components beyond 32 vertices are handed to the global-arena kernel (mid-size
+    # cooperative cover there); smaller ones are covered by k_pug_smem's per-thread cover
+    spec = synth.SynthSpec(n_genes=40, umi_len=4, reads_mean=500.0, reads_per_umi=1.5, umi_err=0.05, zipf_s=0.7)
+    b = synth.generate(spec, 0, 6)
+    check(opts_for(spec, res, small_thresh=0), synth.tid_to_gid(spec), b, res)
+    cnt = emu_lib.last_counts()
+    assert sum(cnt[emu_lib.LIST_PS0:emu_lib.LIST_PS0 + 3]) == b.n_cells, cnt
+    spec2 = synth.SynthSpec(n_genes=300, umi_len=6, reads_mean=600.0, reads_per_umi=1.5, umi_err=0.05)
+    b2 = synth.generate(spec2, 0, 6)   # 4096 UMI values: small multi-vertex components, covered in shared memory
+    check(opts_for(spec2, res, small_thresh=0), synth.tid_to_gid(spec2), b2, res + "/umi6")
+    cnt2 = emu_lib.last_counts()
+    assert cnt2[emu_lib.LIST_GE_NORMAL] < b2.n_cells, cnt2
+
+
+@pytest.mark.parametrize("res", ["parsimony", "parsimony-em"])
+def test_emu_pug_smem_usa_and_record_order(res):
+    spec = synth.SynthSpec(usa_mode=True, reads_mean=500.0, n_genes=2000)
+    b = synth.generate(spec, 0, 8)
+    t2g = synth.tid_to_gid(spec)
+    got = check(opts_for(spec, res), t2g, b, res)
+    assert sum(emu_lib.last_counts()[emu_lib.LIST_PS0:emu_lib.LIST_PS0 + 3]) > 0
+    # record order inside a cell must not matter (canonical orders)
+    rng = np.random.default_rng(5)
+    cells = []
+    for c in range(b.n_cells):
+        r0, r1 = int(b.cell_rec_offsets[c]), int(b.cell_rec_offsets[c + 1])
+        recs = [(int(b.rec_umi32[r]), b.refs[b.rec_ref_offsets[r]:b.rec_ref_offsets[r + 1]].tolist()) for r in range(r0, r1)]
+        rng.shuffle(recs)
+        cells.append(recs)
+    got2 = emu_lib.emu_quant(opts_for(spec, res), t2g, CellBatch.from_cells(cells))
+    assert np.array_equal(got.col, got2.col) and np.array_equal(got.val, got2.val)
