@@ -73,6 +73,7 @@ struct Work {  // per-pipeline scratch (ordered on one stream)
   DBuf<u64> tile_sums;
   DBuf<u8> ge_arena[2];
   DBuf<u32> adj_pool;
+  DBuf<u32> ps_garena;     // k_pug_smem<3> arenas
   DBuf<u64> na_tiles;      // rec_na8 -> offsets scan
   DBuf<u32> na_ref_off;    // device API: offsets derived from rec_na8
   DBuf<u32> umi_wide, refs_wide;   // rec_umi24 / refs24 widened to u32
@@ -87,7 +88,7 @@ struct Work {  // per-pipeline scratch (ordered on one stream)
   }
   void release() {
     ctl.release(); bin_list.release(); stage_col.release(); stage_val.release();
-    tile_sums.release(); ge_arena[0].release(); ge_arena[1].release(); adj_pool.release();
+    tile_sums.release(); ge_arena[0].release(); ge_arena[1].release(); adj_pool.release(); ps_garena.release();
     na_tiles.release(); na_ref_off.release(); umi_wide.release(); refs_wide.release();
   }
 };
@@ -142,6 +143,7 @@ struct afq_ctx {
   int ge_grid = 0;
   int grid_ps[PS_VARIANTS] = {0};
   u32 ps_limit_words = 0;      // AFQ_PS_LIMIT_WORDS: smaller k_pug_smem arena (tests: forces fallbacks to k_gene_eqc)
+  bool no_ps_global = false;   // AFQ_NO_PS_GLOBAL=1: cells beyond the shared-memory arenas take k_gene_eqc
   bool no_ps = false;          // AFQ_NO_PS=1: parsimony cells all take the global-arena kernel (A/B experiments)
   u32 need_shift = 0;          // arena-size bias, raised when a batch overflowed many arenas
   bool no_lanes = false;       // AFQ_NO_LANES=1: launch the arena kernels back to back on the caller's stream
@@ -181,8 +183,8 @@ struct ProfScope {
 
 template <int VAR>
 int setup_ps(afq_ctx* c) {
-  const size_t smem = (size_t)ps_arena_words(VAR) * 4;
-  CUDA_TRY(c, cudaFuncSetAttribute(k_pug_smem<VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = VAR < PS_SMEM_VARIANTS ? (size_t)ps_arena_words(VAR) * 4 : 0;
+  if (smem) CUDA_TRY(c, cudaFuncSetAttribute(k_pug_smem<VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
   CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pug_smem<VAR>, (int)ps_threads(VAR), smem));
   if (occ < 1) { c->err = "k_pug_smem variant does not fit an SM"; return AFQ_ERR_CUDA; }
@@ -233,7 +235,8 @@ struct CudaLauncher {
   }
   u32* adj_pool(u64 n) { return w->adj_pool.ensure((size_t)n) == cudaSuccess ? w->adj_pool.p : nullptr; }
   u32 need_shift() { return c->need_shift; }
-  int ps_grid(int v) { return c->no_ps ? 0 : c->grid_ps[v]; }
+  int ps_grid(int v) { return (c->no_ps || (v == 3 && c->no_ps_global)) ? 0 : c->grid_ps[v]; }
+  u32* ps_garena(u64 words, u32 blocks) { return w->ps_garena.ensure((size_t)words * blocks + 16) == cudaSuccess ? w->ps_garena.p : nullptr; }
   u32 ps_limit_words() { return c->ps_limit_words; }
   // fork / join: lanes are ctx-owned non-blocking streams ordered after / before the caller stream
   void fork(int n) {
@@ -359,6 +362,7 @@ int afq_create(const afq_config* cfg, const uint32_t* tid_to_gid, uint64_t n_ref
   if (const char* s = getenv("AFQ_NEED_SHIFT")) c->need_shift = (u32)atoi(s);
   if (const char* s = getenv("AFQ_NO_LANES")) c->no_lanes = atoi(s) != 0;
   if (const char* s = getenv("AFQ_NO_PS")) c->no_ps = atoi(s) != 0;
+  if (const char* s = getenv("AFQ_NO_PS_GLOBAL")) c->no_ps_global = atoi(s) != 0;
   if (const char* s = getenv("AFQ_PS_LIMIT_WORDS")) c->ps_limit_words = (u32)atoi(s);
   if (c->large_cap_log2 < 10) c->large_cap_log2 = 10;
   if (c->large_cap_log2 > 30) c->large_cap_log2 = 30;
@@ -388,7 +392,7 @@ int afq_create(const afq_config* cfg, const uint32_t* tid_to_gid, uint64_t n_ref
   int rc;
   if ((rc = setup_bin<0>(c)) || (rc = setup_bin<1>(c)) || (rc = setup_bin<2>(c)) ||
       (rc = setup_bin<3>(c)) || (rc = setup_bin<4>(c)) || (rc = setup_bin<5>(c)) ||
-      (rc = setup_ps<0>(c)) || (rc = setup_ps<1>(c)) || (rc = setup_ps<2>(c)))
+      (rc = setup_ps<0>(c)) || (rc = setup_ps<1>(c)) || (rc = setup_ps<2>(c)) || (rc = setup_ps<3>(c)))
     return fail(rc);
   {
     int occ = 0;

@@ -30,7 +30,7 @@ __host__ __device__ constexpr u32 bin_threads(int b) {
 enum : u32 { MODE_CRLIKE = 0, MODE_TRIVIAL = 1 };
 enum : u32 { DEV_ERR_CELL_TOO_LARGE = 1 };
 
-constexpr int NUM_LISTS = NUM_BINS + 6;          // + two k_gene_eqc lists (big / normal cells) + arena-overflow list + three k_pug_smem lists
+constexpr int NUM_LISTS = NUM_BINS + 7;          // + two k_gene_eqc lists (big / normal cells) + arena-overflow list + four k_pug_smem lists
 constexpr int OVF_LIST = NUM_BINS + 2;           // cells whose distinct pairs overflowed their shared-memory arena
 struct Ctl {                       // per-batch device control block (zeroed per batch)
   u32 bin_count[NUM_LISTS + 1];

@@ -16,6 +16,7 @@
 //       between fork and join, launches go to lane i's stream (CUDA) / run in order (emulator)
 //   u32  need_shift();                                        // arena-size bias learnt from overflows
 //   int  ps_grid(int variant);                                // persistent grid of k_pug_smem<variant>; 0 = disabled
+//   u32* ps_garena(u64 words_per_block, u32 blocks);          // grow-only global arenas of k_pug_smem<3>, nullptr on failure
 //   u32  ps_limit_words();                                    // 0, or a smaller arena for k_pug_smem (tests: forces fallbacks)
 #pragma once
 #include <string>
@@ -30,13 +31,13 @@ namespace afq {
 enum KernelId : int {
   KID_BIN = 0, KID_SMEM0 = 1, KID_LARGE = 7, KID_SCAN_SUMS = 8, KID_SCAN_TILES = 9, KID_SCAN_ROWS = 10,
   KID_GATHER = 11, KID_GENE_EQC = 12, KID_GENE_EQC_BIG = 13, KID_BIN_GE = 14, KID_REGION = 15, KID_NA_OFFSETS = 16, KID_UNPACK24 = 17,
-  KID_PUG_SMEM0 = 18, NUM_KID = 21
+  KID_PUG_SMEM0 = 18, NUM_KID = 22
 };
 static const char* const KID_NAMES[NUM_KID] = {
     "k_bin_cells", "k_resolve_smem<0>", "k_resolve_smem<1>", "k_resolve_smem<2>", "k_resolve_smem<3>",
     "k_resolve_smem<4>", "k_resolve_smem<5>", "k_resolve_large", "k_scan_tile_sums", "k_scan_tiles",
     "k_scan_rows", "k_gather_rows", "k_gene_eqc", "k_gene_eqc(big cells)", "k_bin_cells_ge", "resolve_region(wall)",
-    "k_na_offsets(+tile sums)", "k_unpack24", "k_pug_smem<0>", "k_pug_smem<1>", "k_pug_smem<2>"};
+    "k_na_offsets(+tile sums)", "k_unpack24", "k_pug_smem<0>", "k_pug_smem<1>", "k_pug_smem<2>", "k_pug_smem<3>(global arena)"};
 
 struct PipeBufs {  // device scratch owned by the caller (one set per stream-ordered pipeline)
   Ctl* ctl;
@@ -150,11 +151,11 @@ int enqueue_batch(L& l, const afq_config& cfg, int force_bin, const PipeBufs& pb
                                 : GE_MODE_CRLIKE;
     g.only_unique = res_is_em(res) ? 0u : 1u;
     g.ps_limit_words = l.ps_limit_words();
-    // cells expected to fit a shared-memory arena take k_pug_smem (parsimony family); it hands cells
+    // cells expected to fit a shared-memory arena take k_pug_smem (parsimony family, cr-like-em); it hands cells
     // it cannot finish (arena too small after all, a component of more than 32 vertices) back to
     // the k_gene_eqc list, which is drained afterwards
-    const bool ps_on = g.ge_mode != GE_MODE_CRLIKE && l.ps_grid(0) > 0 && cfg.large_graph_thresh >= 2;
-    const u32 ps_mode = ps_on ? (1u | (g.ge_mode == GE_MODE_PUG_GENE ? 2u : 0u) | (g.only_unique ? 0u : 4u)) : 0u;
+    const bool ps_on = l.ps_grid(0) > 0 && (g.ge_mode == GE_MODE_CRLIKE || cfg.large_graph_thresh >= 2);
+    const u32 ps_mode = ps_on ? (1u | (g.ge_mode == GE_MODE_PUG_GENE ? 2u : 0u) | (g.only_unique ? 0u : 4u) | (l.ps_grid(3) > 0 ? 8u : 0u)) : 0u;
     l.launch(KID_BIN_GE, k_bin_cells_ge, bin_grid, 256u, (size_t)0, a, force_bin, GE_BIG_RECORDS, l.need_shift(), ps_mode);
     launch_crlike_bins(l, a, pb);
     Ctl h{};
@@ -175,6 +176,14 @@ int enqueue_batch(L& l, const afq_config& cfg, int force_bin, const PipeBufs& pb
       ps_cells += cnt;
       u32 blocks = (u32)l.ps_grid(v);
       if (blocks > cnt) blocks = cnt;
+      if (v == 3) {
+        const u64 words = ps_global_words(h.ge_max_n[1], h.ge_max_p[1], cfg.num_rows);
+        g.ps_garena = l.ps_garena(words, blocks);
+        g.ps_garena_words = (u32)words;
+        if (!g.ps_garena) { err = "k_pug_smem global arena allocation failed"; return AFQ_ERR_CUDA; }
+        l.launch(KID_PUG_SMEM0 + 3, k_pug_smem<3>, blocks, ps_threads(3), (size_t)0, a, g);
+        continue;
+      }
       const size_t smem = (size_t)ps_arena_words(v) * 4;
       if (v == 0) l.launch(KID_PUG_SMEM0 + 0, k_pug_smem<0>, blocks, ps_threads(0), smem, a, g);
       else if (v == 1) l.launch(KID_PUG_SMEM0 + 1, k_pug_smem<1>, blocks, ps_threads(1), smem, a, g);
@@ -187,6 +196,7 @@ int enqueue_batch(L& l, const afq_config& cfg, int force_bin, const PipeBufs& pb
       const u64 bytes = align8(ge_carve(nullptr, h.ge_max_n[which], h.ge_max_p[which], g.large_graph_thresh, nullptr)) + 64;
       u32 blocks = (u32)l.ge_blocks(which);
       if (blocks > cells) blocks = cells;
+      if (which == 1 && ps_cells && blocks > h.bin_count[list] + 148u) blocks = h.bin_count[list] + 148u;   // hand-backs are rare
       g.arena = l.ge_arena(which, bytes, blocks);
       if (!g.arena) { err = "gene-eq-class arena allocation failed (" + std::to_string(bytes) + " B x " + std::to_string(blocks) + ")"; return AFQ_ERR_CUDA; }
       g.arena_bytes = bytes;

@@ -56,6 +56,8 @@ struct GeArgs {
   u64* adj_used;        // in Ctl-adjacent memory
   // which work list this launch consumes
   u32 list_id;
+  u32* ps_garena;       // k_pug_smem<3>: per-CTA global-memory arenas of ps_garena_words words
+  u32 ps_garena_words;
   u32 ps_limit_words;   // k_pug_smem: use at most this many arena words (0 = the variant's size; tests force fallbacks with it)
 };
 

@@ -32,10 +32,12 @@
 namespace afq {
 
 
-constexpr int PS_VARIANTS = 3;       // arena sizes: 72 KB x 3 CTAs/SM, 108 KB x 2, 224 KB x 1
-__host__ __device__ constexpr u32 ps_threads(int v) { return v == 0 ? 256u : (v == 1 ? 512u : 1024u); }
+constexpr int PS_VARIANTS = 4;       // arenas: 72 KB x 3 CTAs/SM, 108 KB x 2, 224 KB x 1 of shared memory; variant 3 = the same
+                                     // code on a per-CTA GLOBAL-memory arena (L2-resident) for cells beyond 224 KB
+constexpr int PS_SMEM_VARIANTS = 3;
+__host__ __device__ constexpr u32 ps_threads(int v) { return v == 0 ? 256u : (v == 1 ? 512u : (v == 2 ? 1024u : 512u)); }
 __host__ __device__ constexpr u32 ps_arena_words(int v) { return v == 0 ? 18u * 1024u : (v == 1 ? 27u * 1024u : 56u * 1024u); }
-__host__ __device__ constexpr u32 ps_min_blocks(int v) { return v == 0 ? 3u : (v == 1 ? 2u : 1u); }
+__host__ __device__ constexpr u32 ps_min_blocks(int v) { return v == 0 ? 3u : (v == 1 ? 2u : (v == 2 ? 1u : 2u)); }
 constexpr u32 PS_EMPTY = 0xFFFFFFFFu;
 constexpr u32 PS_MAX_RECORDS = 32768;   // record indices and read counts share a 32-bit table entry
 constexpr u32 PS_MAX_REFS = 65535;      // 16-bit relative record offsets
@@ -48,18 +50,26 @@ __host__ __device__ inline u32 ps_need_words(u32 n, u32 P, bool gene, bool em) {
   const u32 rec = n + (n + 1) / 2 + ps_table_size(n);          // UMIs, classes, table: dead after compaction
   const u32 vest = n / 2 + 16;
   u32 bw = pow2_ge(2 * vest, 64); if (bw > 4096) bw = 4096;
-  const u32 post = pow2_ge(vest + vest / 2 + 2, 64) + bw + 2 * vest + (em ? 0 : pow2_ge(vest, 1));
+  const u32 post = pow2_ge(vest + vest / 2 + 2, 64) + bw + 2 * vest + (em ? 0 : pow2_ge(vest, 1)) + 512;
   u32 w = P + (n + 2) / 2 + (gene ? (n + 1) / 2 : 0) + rec + 2 * vest + (post > rec ? post - rec : 0);
   if (em) w += 2 * vest + P / 2 + 64;
   return w;
 }
-// smallest arena variant that is expected to hold the cell, or -1
-__host__ __device__ inline int ps_variant_for(u64 n, u64 P, bool gene, bool em) {
+// smallest arena variant that is expected to hold the cell, or -1 (global_ok: variant 3 is available)
+__host__ __device__ inline int ps_variant_for(u64 n, u64 P, bool gene, bool em, bool global_ok) {
   if (n >= PS_MAX_RECORDS || P >= PS_MAX_REFS || n == 0) return -1;
   const u32 need = ps_need_words((u32)n, (u32)P, gene, em);
-  for (int v = 0; v < PS_VARIANTS; ++v)
+  for (int v = 0; v < PS_SMEM_VARIANTS; ++v)
     if (need <= ps_arena_words(v)) return v;
-  return -1;
+  return global_ok ? 3 : -1;
+}
+// words of global arena per CTA that hold ANY cell of up to n records / P alignments (every vertex distinct)
+__host__ __device__ inline u64 ps_global_words(u32 n, u32 P, u32 num_rows) {
+  if (n >= PS_MAX_RECORDS) n = PS_MAX_RECORDS - 1;
+  if (P >= PS_MAX_REFS) P = PS_MAX_REFS - 1;
+  const u64 rec = (u64)P + (n + 2) / 2 + (n + 1) / 2 + n + (n + 1) / 2 + ps_table_size(n);
+  const u64 post = (u64)pow2_ge(n + n / 2 + 2, 64) + 4096 + 3ull * n + pow2_ge(n, 1) + 2048 + 2ull * ((num_rows + 31) / 32);
+  return rec + 2ull * n + post + 2ull * n + P + 4096;   // + EM: molecule offsets / lengths and labels
 }
 
 struct PsExtra {
@@ -163,43 +173,107 @@ __device__ __forceinline__ u32 ps_emit(const PsCell& c, const PsSink& sk, const 
 }
 
 
+constexpr u32 PS_CRL_GENES = 24;     // cr-like-em: candidate genes of one UMI held by a thread
+
+// one molecule whose (ascending, distinct) gene label is given
+__device__ __forceinline__ u32 ps_emit_genes(const PsSink& sk, const u32* genes, u32 nb) {
+  if (sk.mode == 0) return nb == 1 ? genes[0] : NONE32;
+  if (sk.mode == 1) return nb <= 10 ? usa_slot_for_label(genes, nb, sk.uo, sk.ao) : NONE32;
+  const u32 used = atomicAdd(&sk.sh->lab_bump, nb) + nb;
+  if (used > sk.lab_hi - sk.lab_lo) { sk.ex->fail = 1; return NONE32; }
+  const u32 off = sk.lab_hi - used;
+  for (u32 q = 0; q < nb; ++q) sk.A[off + q] = genes[q];
+  const u32 id = atomicAdd(&sk.sh->n_mol, 1u);
+  sk.mol_off[id] = off;
+  sk.mol_len[id] = nb;
+  return NONE32;
+}
+
 // ---------------------------------------------------------------------------------------------
-// Greedy cover of one component with 2..32 vertices by ONE thread (get_num_molecules cover loop,
+// Greedy monochromatic cover of one component with 2..32 vertices (get_num_molecules cover loop,
 // src/pugutils.rs:1097-1261, + collapse_vertices, src/pugutils.rs:308-391). The members hang on
-// the root's list (head / nxt). Start vertices are visited in ascending (class label, UMI) order.
+// the root's list (head / nxt). Start vertices are visited in ascending (class label, UMI) order;
+// the first strictly larger MCC wins, i.e. the largest MCC of the earliest (start vertex,
+// transcript). Two forms: one THREAD per component (sizes 2..PS_WARP_COMP-1, the bulk) and one
+// WARP per component (lane i = start vertex i), because a component's cover costs O(s^2 |label|)
+// dependent shared-memory loads per round and a single thread on a 12-vertex component kept the
+// whole CTA waiting at the barrier (ncu r1u: 39 % of all stall samples).
 // ---------------------------------------------------------------------------------------------
-__device__ inline void ps_cover(const PsCell& c, const PsSink& sk, u32* winners, const u32* head, const u32* nxt, u32 r, bool exact, u32* gbm) {
-  u32 mem[SMALL_COMP];
-  u32 am[SMALL_COMP];
-  u32 s = 0;
-  for (u32 x = head[r]; x != PS_EMPTY; x = nxt[x], ++s) {    // insertion sort into canonical order
-    const u32 cx = c.vcls(x), ux = c.vumi[x];
-    u32 j = s;
-    while (j > 0) {
-      const u32 y = mem[j - 1];
-      const u32 cy = c.vcls(y);
-      const bool less = cx == cy ? ux < c.vumi[y] : label_less(c.lab(cx), c.len(cx), c.lab(cy), c.len(cy));
-      if (!less) break;
-      mem[j] = y;
-      --j;
+constexpr u32 PS_WARP_COMP = 6;
+
+__device__ __forceinline__ bool ps_canon_less(const PsCell& c, u32 x, u32 y) {   // (class label lexicographic, UMI)
+  const u32 cx = c.vcls(x), cy = c.vcls(y);
+  return cx == cy ? c.vumi[x] < c.vumi[y] : label_less(c.lab(cx), c.len(cx), c.lab(cy), c.len(cy));
+}
+// out-neighbour mask of member i (has_edge, src/pugutils.rs:76-99) over members j in [j0, s)
+__device__ __forceinline__ u32 ps_out_mask(const PsCell& c, const u32* mem, u32 s, u32 i, bool exact) {
+  const u32 ui = c.vumi[mem[i]], ci = c.vcls(mem[i]), ni = c.vcnt(mem[i]);
+  u32 m = 0;
+  for (u32 j = 0; j < s; ++j) {
+    if (j == i) continue;
+    const u32 x = ui ^ c.vumi[mem[j]];
+    const u32 hd = (u32)__popc((x | (x >> 1)) & 0x55555555u);
+    if (exact ? hd != 0 : hd > 1) continue;
+    if (!c.related(ci, c.vcls(mem[j]))) continue;
+    if (out_edge(hd, ni, c.vcnt(mem[j]))) m |= 1u << j;
+  }
+  return m;
+}
+// vertices reachable from member i over out-edges through uncovered vertices whose label holds t
+__device__ __forceinline__ u32 ps_bfs(const PsCell& c, const u32* mem, const u32* am, u32 unc, u32 i, u32 ci, u32 t) {
+  u32 vis = 1u << i, fr = 1u << i, got = 1u << i;
+  while (fr) {
+    u32 nx = 0;
+    u32 f = fr;
+    while (f) {
+      const u32 x = (u32)__ffs((int)f) - 1;
+      f &= f - 1;
+      u32 cand = am[x] & unc & ~vis;
+      vis |= cand;
+      while (cand) {
+        const u32 j = (u32)__ffs((int)cand) - 1;
+        cand &= cand - 1;
+        const u32 cj = c.vcls(mem[j]);
+        if (cj == ci || sorted_contains(c.lab(cj), c.len(cj), t)) nx |= 1u << j;
+      }
     }
+    got |= nx;
+    fr = nx;
+  }
+  return got;
+}
+// molecule of one MCC: label = intersection of its class labels (src/pugutils.rs:1161-1188) -> genes
+__device__ __forceinline__ void ps_emit_mcc(const PsCell& c, const PsSink& sk, u32* winners, u32* gbm, const u32* mem, u32 mask) {
+  const u32 first = (u32)__ffs((int)mask) - 1;
+  const u32 cf = c.vcls(mem[first]);
+  const u32 rest = mask & (mask - 1);
+  const u32 slot = ps_emit(c, sk, c.lab(cf), c.len(cf), [&](u32 t) {
+    u32 r = rest;
+    while (r) {
+      const u32 j = (u32)__ffs((int)r) - 1;
+      r &= r - 1;
+      const u32 cj = c.vcls(mem[j]);
+      if (cj != cf && !sorted_contains(c.lab(cj), c.len(cj), t)) return false;
+    }
+    return true;
+  });
+  if (sk.mode != 2 && slot != NONE32) {
+    winners[atomicAdd(&sk.ex->n_win, 1u)] = slot;
+    if (gbm) atomicOr(&gbm[slot >> 5], 1u << (slot & 31));
+  }
+}
+
+__device__ inline void ps_cover(const PsCell& c, const PsSink& sk, u32* winners, const u32* head, const u32* nxt, u32 r, bool exact, u32* gbm) {
+  u32 mem[PS_WARP_COMP];
+  u32 am[PS_WARP_COMP];
+  u32 s = 0;
+  for (u32 x = head[r]; x != PS_EMPTY && s < PS_WARP_COMP; x = nxt[x], ++s) {    // insertion sort into canonical order
+    u32 j = s;
+    while (j > 0 && ps_canon_less(c, x, mem[j - 1])) { mem[j] = mem[j - 1]; --j; }
     mem[j] = x;
   }
-  for (u32 i = 0; i < s; ++i) am[i] = 0;
-  for (u32 i = 0; i < s; ++i) {    // has_edge, src/pugutils.rs:76-99
-    const u32 ui = c.vumi[mem[i]], ci = c.vcls(mem[i]), ni = c.vcnt(mem[i]);
-    for (u32 j = i + 1; j < s; ++j) {
-      const u32 x = ui ^ c.vumi[mem[j]];
-      const u32 hd = (u32)__popc((x | (x >> 1)) & 0x55555555u);
-      if (exact ? hd != 0 : hd > 1) continue;
-      const u32 cj = c.vcls(mem[j]);
-      if (!c.related(ci, cj)) continue;
-      const u32 nj = c.vcnt(mem[j]);
-      if (out_edge(hd, ni, nj)) am[i] |= 1u << j;
-      if (out_edge(hd, nj, ni)) am[j] |= 1u << i;
-    }
-  }
-  u32 unc = s == 32 ? 0xFFFFFFFFu : ((1u << s) - 1);
+  for (u32 i = 0; i < s; ++i) am[i] = ps_out_mask(c, mem, s, i, exact);
+  u32 unc = (1u << s) - 1;
   while (unc) {
     u32 best_mask = 0, best_size = 0;
     const u32 remaining = (u32)__popc(unc);
@@ -209,53 +283,66 @@ __device__ inline void ps_cover(const PsCell& c, const PsSink& sk, u32* winners,
       const u32* li = c.lab(ci);
       const u32 ln = c.len(ci);
       for (u32 k = 0; k < ln; ++k) {
-        const u32 t = li[k];
-        u32 vis = 1u << i, fr = 1u << i, got = 1u << i;
-        while (fr) {
-          u32 nx = 0;
-          u32 f = fr;
-          while (f) {
-            const u32 x = (u32)__ffs((int)f) - 1;
-            f &= f - 1;
-            u32 cand = am[x] & unc & ~vis;
-            vis |= cand;
-            while (cand) {
-              const u32 j = (u32)__ffs((int)cand) - 1;
-              cand &= cand - 1;
-              const u32 cj = c.vcls(mem[j]);
-              if (cj == ci || sorted_contains(c.lab(cj), c.len(cj), t)) nx |= 1u << j;
-            }
-          }
-          got |= nx;
-          fr = nx;
-        }
+        const u32 got = ps_bfs(c, mem, am, unc, i, ci, li[k]);
         const u32 sz = (u32)__popc(got);
         if (sz > best_size) { best_size = sz; best_mask = got; }
         if (best_size == remaining) break;
       }
     }
-    if (best_mask == 0) {   // only a class with an empty label can get here: cover it alone
-      best_mask = unc & (0u - unc);
-    }
-    // label = intersection of the MCC's class labels (src/pugutils.rs:1161-1188), projected to genes
-    const u32 first = (u32)__ffs((int)best_mask) - 1;
-    const u32 cf = c.vcls(mem[first]);
-    const u32 rest = best_mask & (best_mask - 1);
-    const u32 slot = ps_emit(c, sk, c.lab(cf), c.len(cf), [&](u32 t) {
-      u32 r = rest;
-      while (r) {
-        const u32 j = (u32)__ffs((int)r) - 1;
-        r &= r - 1;
-        const u32 cj = c.vcls(mem[j]);
-        if (cj != cf && !sorted_contains(c.lab(cj), c.len(cj), t)) return false;
-      }
-      return true;
-    });
-    if (sk.mode != 2 && slot != NONE32) {
-      winners[atomicAdd(&sk.ex->n_win, 1u)] = slot;
-      if (gbm) atomicOr(&gbm[slot >> 5], 1u << (slot & 31));
-    }
+    if (best_mask == 0) best_mask = unc & (0u - unc);   // only a class with an empty label can get here: cover it alone
+    ps_emit_mcc(c, sk, winners, gbm, mem, best_mask);
     unc &= ~best_mask;
+  }
+}
+
+// one warp per component; wmem / wam: 32 words each of per-warp shared scratch. Every lane calls.
+__device__ inline void ps_cover_warp(const PsCell& c, const PsSink& sk, u32* winners, const u32* head, const u32* nxt, u32 r, bool exact,
+                                     u32* gbm, u32* wmem, u32* wam) {
+  const u32 lane = lane_id();
+  u32 s = 0;
+  if (lane == 0) for (u32 x = head[r]; x != PS_EMPTY; x = nxt[x]) wam[s++] = x;     // unordered members
+  s = __shfl_sync(0xFFFFFFFFu, s, 0);
+  __syncwarp();
+  u32 x = 0, rank = 0;
+  if (lane < s) {   // rank sort into canonical order (a strict total order: (class, UMI) is unique)
+    x = wam[lane];
+    for (u32 j = 0; j < s; ++j) if (j != lane && ps_canon_less(c, wam[j], x)) ++rank;
+  }
+  __syncwarp();
+  if (lane < s) wmem[rank] = x;
+  __syncwarp();
+  const u32 my_am = lane < s ? ps_out_mask(c, wmem, s, lane, exact) : 0u;
+  wam[lane] = my_am;
+  __syncwarp();
+  u32 unc = s == 32 ? 0xFFFFFFFFu : ((1u << s) - 1);
+  while (unc) {
+    const u32 remaining = (u32)__popc(unc);
+    u32 my_size = 0, my_mask = 0;
+    if (lane < s && (unc >> lane & 1)) {
+      const u32 ci = c.vcls(wmem[lane]);
+      const u32* li = c.lab(ci);
+      const u32 ln = c.len(ci);
+      for (u32 k = 0; k < ln; ++k) {
+        const u32 got = ps_bfs(c, wmem, wam, unc, lane, ci, li[k]);
+        const u32 sz = (u32)__popc(got);
+        if (sz > my_size) { my_size = sz; my_mask = got; }
+        if (my_size == remaining) break;
+      }
+    }
+    u32 best = my_size;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const u32 t = __shfl_xor_sync(0xFFFFFFFFu, best, o); best = t > best ? t : best; }
+    u32 mask;
+    u32 winner;
+    if (best == 0) { winner = (u32)__ffs((int)unc) - 1; mask = 1u << winner; }      // empty labels only: cover the first alone
+    else {
+      const u32 cand = __ballot_sync(0xFFFFFFFFu, my_size == best);
+      winner = (u32)__ffs((int)cand) - 1;                                           // earliest start vertex with the largest MCC
+      mask = __shfl_sync(0xFFFFFFFFu, my_mask, (int)winner);
+    }
+    if (lane == winner) ps_emit_mcc(c, sk, winners, gbm, wmem, mask);
+    unc &= ~mask;
+    __syncwarp();
   }
 }
 
@@ -415,6 +502,7 @@ __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A
   u32* parent = alloc(V);                             // later: component sizes
   u32* winners = em ? A : alloc(next_pow2(V ? V : 1));
   u32* nxt = BW >= V ? bloom : alloc(V);              // component member lists (the bitmap is dead by then)
+  u32* wscr = alloc((T >> 5) * 64);                   // per-warp scratch of the warp-cooperative cover
   if (!fits) return false;                            // uniform (V is block-wide)
   const u32 Wg = (a.num_rows + 31) >> 5;
   u32* gbm = nullptr;                                 // unique-only: presence bitmap + prefix over the output slots
@@ -450,6 +538,52 @@ __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A
     atomicOr(&bloom[b2 >> 5], 1u << (b2 & 31));
   }
   __syncthreads();
+  if (g.ge_mode == GE_MODE_CRLIKE) {
+    // ---- cr-like molecules (cr-like-em): per UMI the genes with the largest read count -----------
+    // get_num_molecules_cell_ranger_like (src/pugutils.rs:799-850) + resolver (src/pugutils.rs:644-749):
+    // W(u, g) = reads of u in classes whose gene projection holds g; label = arg-max gene set. One
+    // lane per UMI chain; a UMI with more than PS_CRL_GENES candidate genes sends the cell back.
+    GE_FOR(sl, NU) {
+      const u32 hd = utab[sl];
+      if (hd == PS_EMPTY) continue;
+      u32 gs[PS_CRL_GENES], ws[PS_CRL_GENES];
+      u32 ng = 0;
+      bool over = false;
+      for (u32 w = hd; w != PS_EMPTY && !over; w = vnext[w]) {
+        const u32 cw = c.vcls(w), nw_ = c.vcnt(w);
+        const u32* lw = c.lab(cw);
+        const u32 ln = c.len(cw);
+        u32 touched = 0;                                   // genes of THIS class already credited (sorted-dedup projection)
+        for (u32 k = 0; k < ln; ++k) {
+          const u32 gg = c.gene_of(lw[k]);
+          u32 q = 0;
+          while (q < ng && gs[q] != gg) ++q;
+          if (q == ng) {
+            if (ng == PS_CRL_GENES) { over = true; break; }
+            gs[ng] = gg; ws[ng] = 0; ++ng;
+          }
+          if (!(touched >> q & 1u)) { ws[q] += nw_; touched |= 1u << q; }
+        }
+      }
+      if (over) { ex->fail = 1; continue; }
+      u32 maxw = 0;
+      for (u32 q = 0; q < ng; ++q) maxw = ws[q] > maxw ? ws[q] : maxw;
+      u32 nb = 0;
+      for (u32 q = 0; q < ng; ++q)
+        if (ws[q] == maxw) {                               // keep the winners, ascending
+          const u32 x = gs[q];
+          u32 j = nb;
+          while (j > 0 && gs[j - 1] > x) { gs[j] = gs[j - 1]; --j; }
+          gs[j] = x;
+          ++nb;
+        }
+      const u32 slot = ps_emit_genes(sk, gs, nb);
+      if (slot != NONE32) {
+        winners[atomicAdd(&ex->n_win, 1u)] = slot;
+        if (gbm) atomicOr(&gbm[slot >> 5], 1u << (slot & 31));
+      }
+    }
+  } else {
   // ---- phase 4: union-find over the PUG's edges (any edge type connects; src/pugutils.rs:278-301) --
   // (a) same UMI, another class sharing a reference: each chain pair once, from its earlier member
   GE_FOR(v, V) {
@@ -546,7 +680,14 @@ __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A
   if (K) {
     GE_FOR(v, V) if (root[v] == v && csz[v] > 1) clist[atomicAdd(&ex->szc[csz[v]], 1u)] = v;
     __syncthreads();
-    GE_FOR(k, K) ps_cover(c, sk, winners, head, nxt, clist[k], g.pug_exact_umi != 0, gbm);
+    // after the scatter szc[z] = END of size z's range: components below PS_WARP_COMP come first
+    const u32 Ks = ex->szc[PS_WARP_COMP - 1];
+    GE_FOR(k, Ks) ps_cover(c, sk, winners, head, nxt, clist[k], g.pug_exact_umi != 0, gbm);
+    const u32 wid = tid >> 5, nw = T >> 5;
+    u32* wmem = wscr + wid * 64;
+    for (u32 k = K - 1 - wid; (int)k >= (int)Ks; k -= nw)        // largest components first
+      ps_cover_warp(c, sk, winners, head, nxt, clist[k], g.pug_exact_umi != 0, gbm, wmem, wmem + 32);
+  }
   }
   __syncthreads();
   if (ex->fail) { __syncthreads(); return false; }
@@ -660,7 +801,8 @@ constexpr int PS_LIST0 = NUM_BINS + 3;      // bin_list rows of the three arena 
 template <int VAR>
 __global__ void __launch_bounds__(ps_threads(VAR), ps_min_blocks(VAR)) k_pug_smem(KArgs a, GeArgs g) {
   AFQ_DYN_SMEM(smem_raw);
-  u32* A = reinterpret_cast<u32*>(smem_raw);
+  u32* A = VAR < PS_SMEM_VARIANTS ? reinterpret_cast<u32*>(smem_raw) : g.ps_garena + (u64)blockIdx.x * g.ps_garena_words;
+  const u32 AWmax = VAR < PS_SMEM_VARIANTS ? ps_arena_words(VAR) : g.ps_garena_words;
   __shared__ GeShared sh;
   __shared__ PsExtra ex;
   __shared__ GePtrs s_ptrs;
@@ -673,7 +815,7 @@ __global__ void __launch_bounds__(ps_threads(VAR), ps_min_blocks(VAR)) k_pug_sme
     __syncthreads();
     if (job >= count) break;
     const u32 cell = list[job];
-    const u32 AW = (g.ps_limit_words && g.ps_limit_words < ps_arena_words(VAR)) ? g.ps_limit_words : ps_arena_words(VAR);
+    const u32 AW = (g.ps_limit_words && g.ps_limit_words < AWmax) ? g.ps_limit_words : AWmax;
     const bool ok = ps_cell(a, g, cell, A, AW, &sh, &ex, &s_ptrs);
     if (!ok && threadIdx.x == 0) {
       const u32 idx = atomicAdd(&a.ctl->bin_count[GE_LIST_NORMAL], 1u);
@@ -685,7 +827,7 @@ __global__ void __launch_bounds__(ps_threads(VAR), ps_min_blocks(VAR)) k_pug_sme
 
 // classify cells for the gene-eq-class resolutions: tiny cells go to the cr-like arenas
 // (src/quant.rs:794-846); cells expected to fit a shared-memory arena go to k_pug_smem's lists
-// (ps_mode bit 0: enabled, bit 1: gene-level labels, bit 2: EM); the rest to the k_gene_eqc lists.
+// (ps_mode bit 0: enabled, bit 1: gene-level labels, bit 2: EM, bit 3: global-arena variant available); the rest to the k_gene_eqc lists.
 // ge_max_n / ge_max_p cover every non-tiny cell of their size class because k_pug_smem may hand
 // any of its cells back to the k_gene_eqc list.
 __global__ void k_bin_cells_ge(KArgs a, int force_bin, u32 big_records, u32 need_shift, u32 ps_mode) {
@@ -709,7 +851,7 @@ __global__ void k_bin_cells_ge(KArgs a, int force_bin, u32 big_records, u32 need
     atomicMax(&a.ctl->ge_max_n[w], (u32)n);
     atomicMax(&a.ctl->ge_max_p[w], p);
     if (w == 1 && (ps_mode & 1u)) {
-      const int v = ps_variant_for(n, p, (ps_mode & 2u) != 0, (ps_mode & 4u) != 0);
+      const int v = ps_variant_for(n, p, (ps_mode & 2u) != 0, (ps_mode & 4u) != 0, (ps_mode & 8u) != 0);
       if (v >= 0) b = PS_LIST0 + v;
     }
   }

@@ -20,7 +20,7 @@ namespace {
 struct EmuLauncher {
   const u32* t2g_ = nullptr;
   std::vector<u8> arena[2];
-  std::vector<u32> adj;
+  std::vector<u32> adj, garena;
   u64 launches = 0;
   int ge_threads_override = 0;
   const u32* t2g() const { return t2g_; }
@@ -45,8 +45,14 @@ struct EmuLauncher {
   void region_begin() {}
   void region_end() {}
   u32 need_shift() { const char* s = getenv("AFQ_NEED_SHIFT"); return s ? (u32)atoi(s) : 0; }
+  u32* ps_garena(u64 words, u32 blocks) { garena.assign((size_t)words * blocks + 16, 0xCDCDCDCDu); return garena.data(); }
   u32 ps_limit_words() { const char* s = getenv("AFQ_PS_LIMIT_WORDS"); return s ? (u32)atoi(s) : 0; }
-  int ps_grid(int) { const char* s = getenv("AFQ_NO_PS"); return (s && atoi(s)) ? 0 : 1; }
+  int ps_grid(int v) {
+    const char* s = getenv("AFQ_NO_PS");
+    if (s && atoi(s)) return 0;
+    const char* gq = getenv("AFQ_NO_PS_GLOBAL");
+    return (v == 3 && gq && atoi(gq)) ? 0 : 1;
+  }
 };
 
 struct EmuResult {

@@ -195,14 +195,14 @@ def test_emu_all_ones_umi_and_window_holes(res):
 
 
 # ---- k_pug_smem (shared-memory parsimony kernel) -------------------------------------------------
-@pytest.mark.parametrize("res", ["parsimony", "parsimony-em", "parsimony-gene", "parsimony-gene-em"])
+@pytest.mark.parametrize("res", ["parsimony", "parsimony-em", "parsimony-gene", "parsimony-gene-em", "cr-like-em"])
 def test_emu_pug_smem_takes_the_cells(res, monkeypatch):
     spec = synth.SynthSpec(reads_mean=400.0)
     b = synth.generate(spec, 0, 12)
     t2g = synth.tid_to_gid(spec)
     check(opts_for(spec, res), t2g, b, res)
     cnt = emu_lib.last_counts()
-    n_ps = sum(cnt[emu_lib.LIST_PS0:emu_lib.LIST_PS0 + 3])
+    n_ps = sum(cnt[emu_lib.LIST_PS0:emu_lib.LIST_PS0 + 4])
     n_tiny = sum(cnt[:7])
     assert n_ps > 0 and n_ps + n_tiny == b.n_cells, cnt      # every non-tiny cell binned to k_pug_smem
     assert cnt[emu_lib.LIST_GE_NORMAL] == 0, cnt                # ... and none handed back
@@ -210,7 +210,7 @@ def test_emu_pug_smem_takes_the_cells(res, monkeypatch):
     monkeypatch.setenv("AFQ_NO_PS", "1")
     check(opts_for(spec, res), t2g, b, res + "/no-ps")
     cnt = emu_lib.last_counts()
-    assert sum(cnt[emu_lib.LIST_PS0:emu_lib.LIST_PS0 + 3]) == 0 and cnt[emu_lib.LIST_GE_NORMAL] > 0, cnt
+    assert sum(cnt[emu_lib.LIST_PS0:emu_lib.LIST_PS0 + 4]) == 0 and cnt[emu_lib.LIST_GE_NORMAL] > 0, cnt
 
 
 @pytest.mark.parametrize("res", ["parsimony", "parsimony-em"])
@@ -234,7 +234,7 @@ def test_emu_pug_smem_big_components_fall_back(res):
     b = synth.generate(spec, 0, 6)
     check(opts_for(spec, res, small_thresh=0), synth.tid_to_gid(spec), b, res)
     cnt = emu_lib.last_counts()
-    assert sum(cnt[emu_lib.LIST_PS0:emu_lib.LIST_PS0 + 3]) == b.n_cells, cnt
+    assert sum(cnt[emu_lib.LIST_PS0:emu_lib.LIST_PS0 + 4]) == b.n_cells, cnt
     spec2 = synth.SynthSpec(n_genes=300, umi_len=6, reads_mean=600.0, reads_per_umi=1.5, umi_err=0.05)
     b2 = synth.generate(spec2, 0, 6)   # 4096 UMI values: small multi-vertex components, covered in shared memory
     check(opts_for(spec2, res, small_thresh=0), synth.tid_to_gid(spec2), b2, res + "/umi6")
@@ -242,13 +242,13 @@ def test_emu_pug_smem_big_components_fall_back(res):
     assert cnt2[emu_lib.LIST_GE_NORMAL] < b2.n_cells, cnt2
 
 
-@pytest.mark.parametrize("res", ["parsimony", "parsimony-em"])
+@pytest.mark.parametrize("res", ["parsimony", "parsimony-em", "cr-like-em"])
 def test_emu_pug_smem_usa_and_record_order(res):
     spec = synth.SynthSpec(usa_mode=True, reads_mean=500.0, n_genes=2000)
     b = synth.generate(spec, 0, 8)
     t2g = synth.tid_to_gid(spec)
     got = check(opts_for(spec, res), t2g, b, res)
-    assert sum(emu_lib.last_counts()[emu_lib.LIST_PS0:emu_lib.LIST_PS0 + 3]) > 0
+    assert sum(emu_lib.last_counts()[emu_lib.LIST_PS0:emu_lib.LIST_PS0 + 4]) > 0
     # record order inside a cell must not matter (canonical orders)
     rng = np.random.default_rng(5)
     cells = []
@@ -259,3 +259,49 @@ def test_emu_pug_smem_usa_and_record_order(res):
         cells.append(recs)
     got2 = emu_lib.emu_quant(opts_for(spec, res), t2g, CellBatch.from_cells(cells))
     assert np.array_equal(got.col, got2.col) and np.array_equal(got.val, got2.val)
+
+
+def _star_cells(rng, n_cells, n_genes):
+    """cells made of 1-Hamming 'stars' (a centre UMI + 2..6 of its single-base substitutions) over a
+    few overlapping transcript sets: components of 6..30 (class, UMI) vertices for the warp-cooperative cover"""
+    cells = []
+    for _ in range(n_cells):
+        recs = []
+        for _star in range(int(rng.integers(3, 7))):
+            centre = int(rng.integers(0, 1 << 24))
+            g = int(rng.integers(0, n_genes - 2))
+            labels = [[3 * g], [3 * g, 3 * g + 1], [3 * g, 3 * g + 1, 3 * g + 4], [3 * g + 1, 3 * g + 4], [3 * g + 4, 3 * g + 5]]
+            leaves = rng.choice(36, size=int(rng.integers(2, 7)), replace=False)
+            umis = [centre] + [centre ^ ((int(k) % 3 + 1) << (2 * (int(k) // 3))) for k in leaves]
+            for u in umis:
+                for _r in range(int(rng.integers(1, 4))):
+                    recs.append((u, labels[int(rng.integers(0, len(labels)))]))
+        for _bg in range(120):   # background so the cell is not tiny
+            recs.append((int(rng.integers(0, 1 << 24)), [3 * int(rng.integers(0, n_genes))]))
+        rng.shuffle(recs)
+        cells.append(recs)
+    return cells
+
+
+@pytest.mark.parametrize("res", ["parsimony", "parsimony-em", "parsimony-gene"])
+def test_emu_pug_smem_warp_cover_on_star_components(res):
+    rng = np.random.default_rng(11)
+    n_genes = 50
+    t2g = np.repeat(np.arange(n_genes, dtype=np.uint32), 3)
+    b = CellBatch.from_cells(_star_cells(rng, 5, n_genes))
+    o = QuantOpts(resolution=res, num_gene_ids=n_genes, num_rows=n_genes, umi_len=12)
+    check(o, t2g, b, res)
+    cnt = emu_lib.last_counts()
+    assert sum(cnt[emu_lib.LIST_PS0:emu_lib.LIST_PS0 + 4]) == b.n_cells and cnt[emu_lib.LIST_GE_NORMAL] == 0, cnt
+
+
+@pytest.mark.parametrize("res", ["parsimony", "parsimony-em"])
+def test_emu_pug_global_arena_variant(res, monkeypatch):
+    # cells beyond the shared-memory arenas run the same code on a global-memory arena (variant 3);
+    # a tiny arena limit pushes ordinary cells there
+    spec = synth.SynthSpec(fixed_reads=10000, n_genes=3000)
+    b = synth.generate(spec, 0, 2)
+    check(opts_for(spec, res), synth.tid_to_gid(spec), b, res)
+    cnt = emu_lib.last_counts()
+    assert cnt[emu_lib.LIST_PS0 + 3] > 0, cnt
+    assert cnt[emu_lib.LIST_GE_NORMAL] == 0, cnt
