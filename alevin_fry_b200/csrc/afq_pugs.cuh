@@ -39,8 +39,8 @@ __host__ __device__ constexpr u32 ps_threads(int v) { return v == 0 ? 256u : (v 
 __host__ __device__ constexpr u32 ps_arena_words(int v) { return v == 0 ? 18u * 1024u : (v == 1 ? 27u * 1024u : 56u * 1024u); }
 __host__ __device__ constexpr u32 ps_min_blocks(int v) { return v == 0 ? 3u : (v == 1 ? 2u : (v == 2 ? 1u : 2u)); }
 constexpr u32 PS_EMPTY = 0xFFFFFFFFu;
-constexpr u32 PS_MAX_RECORDS = 32768;   // record indices and read counts share a 32-bit table entry
-constexpr u32 PS_MAX_REFS = 65535;      // 16-bit relative record offsets
+constexpr u32 PS_MAX_RECORDS = 65535;   // record indices and read counts share a 32-bit table entry (16 bits each)
+constexpr u32 PS_MAX_REFS = 65535;      // 16-bit relative record offsets in the shared-memory variants (32-bit in variant 3)
 
 __host__ __device__ inline u32 ps_table_size(u32 n) { return pow2_ge(n + n / 4 + 8, 64); }
 
@@ -57,19 +57,20 @@ __host__ __device__ inline u32 ps_need_words(u32 n, u32 P, bool gene, bool em) {
 }
 // smallest arena variant that is expected to hold the cell, or -1 (global_ok: variant 3 is available)
 __host__ __device__ inline int ps_variant_for(u64 n, u64 P, bool gene, bool em, bool global_ok) {
-  if (n >= PS_MAX_RECORDS || P >= PS_MAX_REFS || n == 0) return -1;
-  const u32 need = ps_need_words((u32)n, (u32)P, gene, em);
-  for (int v = 0; v < PS_SMEM_VARIANTS; ++v)
-    if (need <= ps_arena_words(v)) return v;
+  if (n >= PS_MAX_RECORDS || P >= (1ull << 30) || n == 0) return -1;
+  if (P < PS_MAX_REFS) {
+    const u32 need = ps_need_words((u32)n, (u32)P, gene, em);
+    for (int v = 0; v < PS_SMEM_VARIANTS; ++v)
+      if (need <= ps_arena_words(v)) return v;
+  }
   return global_ok ? 3 : -1;
 }
 // words of global arena per CTA that hold ANY cell of up to n records / P alignments (every vertex distinct)
 __host__ __device__ inline u64 ps_global_words(u32 n, u32 P, u32 num_rows) {
   if (n >= PS_MAX_RECORDS) n = PS_MAX_RECORDS - 1;
-  if (P >= PS_MAX_REFS) P = PS_MAX_REFS - 1;
-  const u64 rec = (u64)P + (n + 2) / 2 + (n + 1) / 2 + n + (n + 1) / 2 + ps_table_size(n);
+  const u64 rec = (u64)P + (n + 2) + (n + 1) / 2 + n + (n + 1) / 2 + ps_table_size(n);
   const u64 post = (u64)pow2_ge(n + n / 2 + 2, 64) + 4096 + 3ull * n + pow2_ge(n, 1) + 2048 + 2ull * ((num_rows + 31) / 32);
-  return rec + 2ull * n + post + 2ull * n + P + 4096;   // + EM: molecule offsets / lengths and labels
+  return (rec + 2ull * n + post + 2ull * n + P + 4096 + 3) & ~3ull;   // + EM: molecule offsets / lengths and labels; 16-byte multiple
 }
 
 struct PsExtra {
@@ -77,6 +78,7 @@ struct PsExtra {
   u32 n_mlist;    // vertices in components of size > 1
   u32 n_win;      // winners (unique-only resolutions)
   u32 szc[SMALL_COMP + 4];   // multi-vertex components per size (counting sort of their roots)
+  u32 n_over;     // components of <= 8 vertices re-routed to the warp-cooperative cover (a label > 32 transcripts)
 };
 
 // all 32 lanes of the warp call; lanes with pred get consecutive indices from *counter
@@ -94,13 +96,15 @@ __device__ __forceinline__ u32 warp_bump(u32* counter, bool pred) {
 struct PsCell {
   const KArgs* a;
   u32* refs;            // [P] transcript ids (gene ids after the in-place projection, PUG_GENE)
-  const u16* roff;      // [n+1] record offsets into refs
+  const u16* roff;      // [n+1] record offsets into refs (shared-memory variants) ...
+  const u32* roff32;    // ... or 32-bit offsets (variant 3; then roff == nullptr)
   const u16* rlen;      // [n] label lengths (PUG_GENE) or nullptr (length = offset difference)
   const u32* vumi;      // [V]
   const u32* vinfo;     // [V] class (representative record) << 16 | read count
   bool gene;            // labels already are gene ids
-  __device__ __forceinline__ const u32* lab(u32 r) const { return refs + roff[r]; }
-  __device__ __forceinline__ u32 len(u32 r) const { return rlen ? (u32)rlen[r] : (u32)roff[r + 1] - (u32)roff[r]; }
+  __device__ __forceinline__ u32 off(u32 r) const { return roff ? (u32)roff[r] : roff32[r]; }
+  __device__ __forceinline__ const u32* lab(u32 r) const { return refs + off(r); }
+  __device__ __forceinline__ u32 len(u32 r) const { return rlen ? (u32)rlen[r] : off(r + 1) - off(r); }
   __device__ __forceinline__ u32 vcls(u32 v) const { return vinfo[v] >> 16; }
   __device__ __forceinline__ u32 vcnt(u32 v) const { return vinfo[v] & 0xFFFFu; }
   __device__ __forceinline__ u32 gene_of(u32 x) const { return gene ? x : __ldg(a->t2g + x); }
@@ -120,7 +124,7 @@ struct PsSink {
   PsExtra* ex;
 };
 
-// One molecule whose transcript label is { t in l0[0..n0) : keep(t) } (ascending). Returns the
+// One molecule whose transcript label is { t = l0[k], k in [0, n0) : keep(k, t) } (ascending). Returns the
 // output slot for the unique-only modes (NONE32: contributes nothing); mode 2 stores the sorted
 // gene label and returns NONE32.
 template <class Keep>
@@ -130,7 +134,7 @@ __device__ __forceinline__ u32 ps_emit(const PsCell& c, const PsSink& sk, const 
     u32 g0 = NONE32;
     for (u32 k = 0; k < n0; ++k) {
       const u32 t = l0[k];
-      if (!keep(t)) continue;
+      if (!keep(k, t)) continue;
       const u32 gg = c.gene_of(t);
       if (g0 == NONE32) g0 = gg;
       else if (gg != g0) return NONE32;
@@ -143,7 +147,7 @@ __device__ __forceinline__ u32 ps_emit(const PsCell& c, const PsSink& sk, const 
     u32 nb = 0;
     for (u32 k = 0; k < n0; ++k) {
       const u32 t = l0[k];
-      if (!keep(t)) continue;
+      if (!keep(k, t)) continue;
       const u32 gg = c.gene_of(t);
       u32 q = 0;
       while (q < nb && best[q] < gg) ++q;
@@ -156,16 +160,37 @@ __device__ __forceinline__ u32 ps_emit(const PsCell& c, const PsSink& sk, const 
     if (nb > 10) return NONE32;
     return usa_slot_for_label(best, nb, sk.uo, sk.ao);
   }
-  const u32 used = atomicAdd(&sk.sh->lab_bump, n0) + n0;     // labels grow DOWN from lab_hi
+  // mode 2: store the sorted-unique gene label. It is built in a small thread-local buffer first so
+  // that exactly its length is taken from the arena (a 40-transcript label is usually 1-2 genes)
+  u32 buf[32];
+  u32 nb = 0;
+  bool big = false;
+  for (u32 k = 0; k < n0 && !big; ++k) {
+    const u32 t = l0[k];
+    if (!keep(k, t)) continue;
+    const u32 gg = c.gene_of(t);
+    u32 q = nb;
+    if (!c.gene) { q = 0; while (q < nb && buf[q] < gg) ++q; if (q < nb && buf[q] == gg) continue; }
+    if (nb == 32) { big = true; break; }
+    for (u32 j = nb; j > q; --j) buf[j] = buf[j - 1];
+    buf[q] = gg;
+    ++nb;
+  }
+  const u32 want = big ? n0 : nb;
+  const u32 used = atomicAdd(&sk.sh->lab_bump, want) + want;     // labels grow DOWN from lab_hi
   if (used > sk.lab_hi - sk.lab_lo) { sk.ex->fail = 1; return NONE32; }
   const u32 off = sk.lab_hi - used;
   u32* dst = sk.A + off;
-  u32 m = 0;
-  for (u32 k = 0; k < n0; ++k) {
-    const u32 t = l0[k];
-    if (keep(t)) dst[m++] = c.gene_of(t);
+  u32 m = nb;
+  if (!big) { for (u32 q = 0; q < nb; ++q) dst[q] = buf[q]; }
+  else {      // more than 32 genes: project in place
+    m = 0;
+    for (u32 k = 0; k < n0; ++k) {
+      const u32 t = l0[k];
+      if (keep(k, t)) dst[m++] = c.gene_of(t);
+    }
+    if (!c.gene) m = sort_dedup_small(dst, m);
   }
-  if (!c.gene) m = sort_dedup_small(dst, m);
   const u32 id = atomicAdd(&sk.sh->n_mol, 1u);
   sk.mol_off[id] = off;
   sk.mol_len[id] = m;
@@ -199,7 +224,7 @@ __device__ __forceinline__ u32 ps_emit_genes(const PsSink& sk, const u32* genes,
 // dependent shared-memory loads per round and a single thread on a 12-vertex component kept the
 // whole CTA waiting at the barrier (ncu r1u: 39 % of all stall samples).
 // ---------------------------------------------------------------------------------------------
-constexpr u32 PS_WARP_COMP = 6;
+constexpr u32 PS_WARP_COMP = 9;       // components of this many vertices and more take the warp form
 
 __device__ __forceinline__ bool ps_canon_less(const PsCell& c, u32 x, u32 y) {   // (class label lexicographic, UMI)
   const u32 cx = c.vcls(x), cy = c.vcls(y);
@@ -247,7 +272,7 @@ __device__ __forceinline__ void ps_emit_mcc(const PsCell& c, const PsSink& sk, u
   const u32 first = (u32)__ffs((int)mask) - 1;
   const u32 cf = c.vcls(mem[first]);
   const u32 rest = mask & (mask - 1);
-  const u32 slot = ps_emit(c, sk, c.lab(cf), c.len(cf), [&](u32 t) {
+  const u32 slot = ps_emit(c, sk, c.lab(cf), c.len(cf), [&](u32, u32 t) {
     u32 r = rest;
     while (r) {
       const u32 j = (u32)__ffs((int)r) - 1;
@@ -263,35 +288,117 @@ __device__ __forceinline__ void ps_emit_mcc(const PsCell& c, const PsSink& sk, u
   }
 }
 
-__device__ inline void ps_cover(const PsCell& c, const PsSink& sk, u32* winners, const u32* head, const u32* nxt, u32 r, bool exact, u32* gbm) {
-  u32 mem[PS_WARP_COMP];
-  u32 am[PS_WARP_COMP];
-  u32 s = 0;
-  for (u32 x = head[r]; x != PS_EMPTY && s < PS_WARP_COMP; x = nxt[x], ++s) {    // insertion sort into canonical order
-    u32 j = s;
-    while (j > 0 && ps_canon_less(c, x, mem[j - 1])) { mem[j] = mem[j - 1]; --j; }
-    mem[j] = x;
-  }
-  for (u32 i = 0; i < s; ++i) am[i] = ps_out_mask(c, mem, s, i, exact);
-  u32 unc = (1u << s) - 1;
-  while (unc) {
-    u32 best_mask = 0, best_size = 0;
-    const u32 remaining = (u32)__popc(unc);
-    for (u32 i = 0; i < s && best_size < remaining; ++i) {
-      if (!(unc >> i & 1)) continue;
-      const u32 ci = c.vcls(mem[i]);
-      const u32* li = c.lab(ci);
-      const u32 ln = c.len(ci);
-      for (u32 k = 0; k < ln; ++k) {
-        const u32 got = ps_bfs(c, mem, am, unc, i, ci, li[k]);
-        const u32 sz = (u32)__popc(got);
-        if (sz > best_size) { best_size = sz; best_mask = got; }
-        if (best_size == remaining) break;
-      }
+// G lanes per component (G = 4 or 8, sizes <= G), 32/G components per warp pass; every lane of the
+// warp calls. Lane `sub` of a group owns start vertex `sub`. Everything a BFS needs is precomputed as
+// bitmasks RELATIVE TO THE LANE'S OWN LABEL: M[j] = positions k of my label whose transcript is in
+// vertex j's label. Then the BFS of ALL my transcripts at once is a fixed number of branch-free
+// relaxations reach[j] |= reach[x] & M[j] over the out-edges x -> j, in registers.
+// Components with a label longer than 32 transcripts are appended to `olist` for the warp form.
+template <int G>
+__device__ inline void ps_cover_group(const PsCell& c, const PsSink& sk, u32* winners, u32* gbm, const u32* head, const u32* nxt,
+                                      const u32* clist, u32 k0, u32 k1, bool exact, u32* olist, u32* n_over) {
+  const u32 lane = lane_id(), sub = lane % G, gbase = lane - sub;
+  const u32 wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  constexpr u32 PER = 32 / G;
+  for (u32 kb = k0 + wid * PER; kb < k1; kb += nw * PER) {     // warp-uniform
+    const u32 k = kb + lane / G;
+    const bool valid = k < k1;
+    const u32 r = valid ? clist[k] : 0u;
+    u32 v = valid ? head[r] : PS_EMPTY;
+    for (u32 q = 0; q < sub && v != PS_EMPTY; ++q) v = nxt[v];
+    bool has = v != PS_EMPTY;
+    u32 ci = 0, ui = 0, ni = 0, ln = 0;
+    const u32* li = nullptr;
+    if (has) { ci = c.vcls(v); ui = c.vumi[v]; ni = c.vcnt(v); li = c.lab(ci); ln = c.len(ci); }
+    __syncwarp();
+    // a label that does not fit a 32-bit position mask: the whole component takes the warp form
+    const u32 overm = __ballot_sync(0xFFFFFFFFu, has && ln > 32);
+    if ((overm >> gbase) & ((1u << G) - 1u)) {
+      if (sub == 0 && valid) olist[atomicAdd(n_over, 1u)] = r;
+      has = false;
     }
-    if (best_mask == 0) best_mask = unc & (0u - unc);   // only a class with an empty label can get here: cover it alone
-    ps_emit_mcc(c, sk, winners, gbm, mem, best_mask);
-    unc &= ~best_mask;
+    const u32 full = ln >= 32 ? 0xFFFFFFFFu : ((1u << ln) - 1u);
+    u32 M[G];
+    u32 am = 0, rank = 0;
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      const u32 vj = __shfl_sync(0xFFFFFFFFu, v, (int)gbase + j);
+      const bool hj = __shfl_sync(0xFFFFFFFFu, (u32)has, (int)gbase + j) != 0;
+      const u32 cj = __shfl_sync(0xFFFFFFFFu, ci, (int)gbase + j);
+      const u32 uj = __shfl_sync(0xFFFFFFFFu, ui, (int)gbase + j);
+      const u32 nj = __shfl_sync(0xFFFFFFFFu, ni, (int)gbase + j);
+      u32 m = 0;
+      if (has && hj) {
+        if ((u32)j == sub || cj == ci) m = full;
+        else {
+          const u32* lj = c.lab(cj);
+          const u32 lnj = c.len(cj);
+          for (u32 q = 0; q < ln; ++q) if (sorted_contains(lj, lnj, li[q])) m |= 1u << q;
+        }
+        if ((u32)j != sub) {
+          const u32 x = ui ^ uj;
+          const u32 hd = (u32)__popc((x | (x >> 1)) & 0x55555555u);
+          // has_edge (src/pugutils.rs:76-99): classes must share a reference (m != 0), Hamming distance <= 1
+          if ((exact ? hd == 0 : hd <= 1) && m != 0 && out_edge(hd, ni, nj)) am |= 1u << j;
+          if (cj == ci ? uj < ui : label_less(c.lab(cj), c.len(cj), li, ln)) ++rank;   // canonical order (class label, UMI)
+          (void)vj;
+        }
+      }
+      M[j] = m;
+      __syncwarp();
+    }
+    u32 amx[G];
+#pragma unroll
+    for (int x = 0; x < G; ++x) amx[x] = __shfl_sync(0xFFFFFFFFu, am, (int)gbase + x);
+    u32 unc = (__ballot_sync(0xFFFFFFFFu, has) >> gbase) & ((1u << G) - 1u);
+    while (__any_sync(0xFFFFFFFFu, unc != 0)) {
+      u32 my_size = 0, my_mask = 1u << sub, my_k = 0;
+      const bool start = has && ((unc >> sub) & 1u);
+      if (start) {
+        u32 reach[G];
+#pragma unroll
+        for (int j = 0; j < G; ++j) reach[j] = (u32)j == sub ? full : 0u;
+#pragma unroll
+        for (int round = 0; round < G - 1; ++round) {
+#pragma unroll
+          for (int x = 0; x < G; ++x) {
+            const u32 ax = amx[x] & unc;
+#pragma unroll
+            for (int j = 0; j < G; ++j)
+              if ((ax >> j) & 1u) reach[j] |= reach[x] & M[j];
+          }
+        }
+        for (u32 q = 0; q < ln; ++q) {            // first transcript with the largest reachable set
+          u32 sz = 0, mk = 0;
+#pragma unroll
+          for (int j = 0; j < G; ++j) { const u32 b = (reach[j] >> q) & 1u; sz += b; mk |= b << j; }
+          if (sz > my_size) { my_size = sz; my_mask = mk; my_k = q; }
+        }
+      }
+      __syncwarp();
+      // group arg-max: largest MCC, earliest start vertex in canonical order
+      const u32 key = start ? ((my_size << 8) | (255u - rank)) + 1u : 0u;
+      u32 best = key;
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) { const u32 t = __shfl_xor_sync(0xFFFFFFFFu, best, o); best = t > best ? t : best; }
+      const u32 wm = (__ballot_sync(0xFFFFFFFFu, start && key == best) >> gbase) & ((1u << G) - 1u);
+      const u32 wl = wm ? (u32)__ffs((int)wm) - 1 : 0u;
+      const u32 mask = __shfl_sync(0xFFFFFFFFu, my_mask, (int)(gbase + wl));
+      if (start && wm && sub == wl) {
+        // label = intersection of the MCC's class labels (src/pugutils.rs:1161-1188), as positions of mine
+        u32 inter = full;
+#pragma unroll
+        for (int j = 0; j < G; ++j) if ((mask >> j) & 1u) inter &= M[j];
+        (void)my_k;
+        const u32 slot = ps_emit(c, sk, li, ln, [&](u32 q, u32) { return ((inter >> q) & 1u) != 0; });
+        if (sk.mode != 2 && slot != NONE32) {
+          winners[atomicAdd(&sk.ex->n_win, 1u)] = slot;
+          if (gbm) atomicOr(&gbm[slot >> 5], 1u << (slot & 31));
+        }
+      }
+      if (wm) unc &= ~mask;
+      __syncwarp();
+    }
   }
 }
 
@@ -374,6 +481,7 @@ __device__ inline bool ps_back_carve(u32* A, u32 lo, u32 hi, u32 M, u32 Lm, u32 
 // One cell. Returns false when the cell has to be redone by the global-arena kernel (nothing has
 // been written for it in that case).
 // =============================================================================================
+template <bool WIDE>
 __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A, u32 AW, GeShared* sh, PsExtra* ex,
                                GePtrs* s_ptrs) {
   const u32 T = blockDim.x, tid = threadIdx.x;
@@ -388,7 +496,9 @@ __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A
   // ---- arena layout, phase A --------------------------------------------------------------------
   u32 off = 0;
   u32* refs = A + off; off += P;
-  u16* roff = reinterpret_cast<u16*>(A + off); off += (n + 2) / 2;
+  u16* roff = WIDE ? nullptr : reinterpret_cast<u16*>(A + off);
+  u32* roff32 = WIDE ? A + off : nullptr;
+  off += WIDE ? n + 1 : (n + 2) / 2;
   u16* rlen = nullptr;
   if (gene) { rlen = reinterpret_cast<u16*>(A + off); off += (n + 1) / 2; }
   const u32 off_rec = off;                       // everything from here is re-carved after compaction
@@ -397,22 +507,22 @@ __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A
   const u32 TN = ps_table_size(n), tl2 = ilog2(TN), tmask = TN - 1;
   u32* tab = A + off; off += TN;
   const u32 off_dense = off;
-  if (tid == 0) { ex->fail = (off_dense > AW || n >= PS_MAX_RECORDS || P >= PS_MAX_REFS) ? 1u : 0u; ex->n_mlist = 0; ex->n_win = 0;
+  if (tid == 0) { ex->fail = (off_dense > AW || n >= PS_MAX_RECORDS || (!WIDE && P >= PS_MAX_REFS)) ? 1u : 0u; ex->n_mlist = 0; ex->n_win = 0;
                   sh->n_mol = 0; sh->lab_bump = 0; sh->alt = 0; sh->flag = 0; sh->cnt0 = sh->cnt1 = sh->cnt2 = sh->cnt3 = 0; }
   __syncthreads();
   if (ex->fail) { __syncthreads(); return false; }
   // ---- load: the cell's records are read from HBM once, coalesced --------------------------------
   for (u32 i = tid; i < P; i += T) refs[i] = a.refs[(u64)f0 + i];
-  for (u32 i = tid; i <= n; i += T) roff[i] = (u16)(a.ref_off[r0 + i] - f0);
+  for (u32 i = tid; i <= n; i += T) { if (WIDE) roff32[i] = a.ref_off[r0 + i] - f0; else roff[i] = (u16)(a.ref_off[r0 + i] - f0); }
   for (u32 i = tid; i < n; i += T) umi[i] = a.umi[r0 + i];
   for (u32 i = tid; i < TN; i += T) tab[i] = PS_EMPTY;
   __syncthreads();
   PsCell c;
-  c.a = &a; c.refs = refs; c.roff = roff; c.rlen = rlen; c.gene = gene; c.vumi = nullptr; c.vinfo = nullptr;
+  c.a = &a; c.refs = refs; c.roff = roff; c.roff32 = roff32; c.rlen = rlen; c.gene = gene; c.vumi = nullptr; c.vinfo = nullptr;
   if (gene) {   // sorted-dedup gene projection of every record, in place (src/eq_class.rs:742-744)
     GE_FOR(i, n) {
-      u32* dst = refs + roff[i];
-      const u32 ln = (u32)roff[i + 1] - roff[i];
+      u32* dst = refs + c.off(i);
+      const u32 ln = c.off(i + 1) - c.off(i);
       for (u32 k = 0; k < ln; ++k) dst[k] = __ldg(a.t2g + dst[k]);
       rlen[i] = (u16)sort_dedup_small(dst, ln);
     }
@@ -503,6 +613,7 @@ __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A
   u32* winners = em ? A : alloc(next_pow2(V ? V : 1));
   u32* nxt = BW >= V ? bloom : alloc(V);              // component member lists (the bitmap is dead by then)
   u32* wscr = alloc((T >> 5) * 64);                   // per-warp scratch of the warp-cooperative cover
+  u32* olist = alloc(V / 2 + 2);                      // components re-routed from the group cover to the warp cover
   if (!fits) return false;                            // uniform (V is block-wide)
   const u32 Wg = (a.num_rows + 31) >> 5;
   u32* gbm = nullptr;                                 // unique-only: presence bitmap + prefix over the output slots
@@ -656,7 +767,7 @@ __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A
       const u32 sz = csz[r];
       if (sz == 1) {   // singleton component: the class label itself (src/pugutils.rs:1262-1322)
         const u32 cv = c.vcls(v);
-        slot = ps_emit(c, sk, c.lab(cv), c.len(cv), [](u32) { return true; });
+        slot = ps_emit(c, sk, c.lab(cv), c.len(cv), [](u32, u32) { return true; });
       } else {
         nxt[v] = atomicExch(&head[r], v);
         if (v == r) atomicAdd(&ex->szc[sz > SMALL_COMP ? SMALL_COMP + 1 : sz], 1u);
@@ -680,13 +791,20 @@ __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A
   if (K) {
     GE_FOR(v, V) if (root[v] == v && csz[v] > 1) clist[atomicAdd(&ex->szc[csz[v]], 1u)] = v;
     __syncthreads();
-    // after the scatter szc[z] = END of size z's range: components below PS_WARP_COMP come first
-    const u32 Ks = ex->szc[PS_WARP_COMP - 1];
-    GE_FOR(k, Ks) ps_cover(c, sk, winners, head, nxt, clist[k], g.pug_exact_umi != 0, gbm);
+    // after the scatter szc[z] = END of size z's range
+    const u32 K4 = ex->szc[4], K8 = ex->szc[8];
+    if (tid == 0) ex->n_over = 0;
+    __syncthreads();
+    ps_cover_group<4>(c, sk, winners, gbm, head, nxt, clist, 0, K4, g.pug_exact_umi != 0, olist, &ex->n_over);
+    ps_cover_group<8>(c, sk, winners, gbm, head, nxt, clist, K4, K8, g.pug_exact_umi != 0, olist, &ex->n_over);
     const u32 wid = tid >> 5, nw = T >> 5;
     u32* wmem = wscr + wid * 64;
-    for (u32 k = K - 1 - wid; (int)k >= (int)Ks; k -= nw)        // largest components first
+    for (u32 k = K - 1 - wid; (int)k >= (int)K8; k -= nw)        // largest components first
       ps_cover_warp(c, sk, winners, head, nxt, clist[k], g.pug_exact_umi != 0, gbm, wmem, wmem + 32);
+    __syncthreads();
+    const u32 KO = ex->n_over;                                   // small components with a long label
+    for (u32 k = wid; k < KO; k += nw)
+      ps_cover_warp(c, sk, winners, head, nxt, olist[k], g.pug_exact_umi != 0, gbm, wmem, wmem + 32);
   }
   }
   __syncthreads();
@@ -816,7 +934,7 @@ __global__ void __launch_bounds__(ps_threads(VAR), ps_min_blocks(VAR)) k_pug_sme
     if (job >= count) break;
     const u32 cell = list[job];
     const u32 AW = (g.ps_limit_words && g.ps_limit_words < AWmax) ? g.ps_limit_words : AWmax;
-    const bool ok = ps_cell(a, g, cell, A, AW, &sh, &ex, &s_ptrs);
+    const bool ok = ps_cell<(VAR >= PS_SMEM_VARIANTS)>(a, g, cell, A, AW, &sh, &ex, &s_ptrs);
     if (!ok && threadIdx.x == 0) {
       const u32 idx = atomicAdd(&a.ctl->bin_count[GE_LIST_NORMAL], 1u);
       a.bin_list[(u64)GE_LIST_NORMAL * a.n_cells + idx] = cell;

@@ -305,12 +305,12 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- roofline of the dominant kernel family (per-cell resolve) -----------------------------
-    fam = {k: v for k, v in prof.items() if k.startswith(("k_resolve", "k_gene_eqc"))}
+    fam = {k: v for k, v in prof.items() if k.startswith(("k_resolve", "k_gene_eqc", "k_pug_smem"))}
     fam_ms = sum(v[0] for v in fam.values()) / args.steps
     region = prof.get("resolve_region(wall)")
     if region:  # arena kernels overlap on lanes: their device time is the wall time of the region;
         # the gene-eq-class kernels (parsimony / EM resolutions) run behind it, one after the other
-        fam_ms = (region[0] + sum(v[0] for k, v in fam.items() if k.startswith("k_gene_eqc"))) / args.steps
+        fam_ms = (region[0] + sum(v[0] for k, v in fam.items() if k.startswith(("k_gene_eqc", "k_pug_smem")))) / args.steps
     fam_launches = sum(v[1] for v in fam.values()) // max(args.steps, 1)
     abytes = algorithmic_bytes(batch, nnz)
     peak, peak_src = peak_hbm()
@@ -320,7 +320,7 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(args.config)
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "per-cell resolve family (k_resolve_smem<*>/k_resolve_large/k_gene_eqc), %d launches/step" % fam_launches,
+    roofline = {"bound": "hbm", "kernel": "per-cell resolve family (k_resolve_smem<*>/k_resolve_large/k_pug_smem<*>/k_gene_eqc), %d launches/step" % fam_launches,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "algorithmic_bytes_per_step": abytes, "kernel_ms_per_step": fam_ms, "peak_source": peak_src,
                 "per_kernel_ms": {k: v[0] / args.steps for k, v in prof.items()}}

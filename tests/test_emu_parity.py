@@ -305,3 +305,34 @@ def test_emu_pug_global_arena_variant(res, monkeypatch):
     cnt = emu_lib.last_counts()
     assert cnt[emu_lib.LIST_PS0 + 3] > 0, cnt
     assert cnt[emu_lib.LIST_GE_NORMAL] == 0, cnt
+
+
+@pytest.mark.parametrize("res", ["parsimony", "parsimony-em"])
+def test_emu_pug_smem_long_labels_take_the_warp_cover(res):
+    # labels of more than 32 transcripts do not fit the group cover's position masks: such components
+    # are re-routed to the warp-cooperative cover inside the same kernel
+    rng = np.random.default_rng(3)
+    n_genes, per = 20, 50
+    t2g = np.repeat(np.arange(n_genes, dtype=np.uint32), per)
+    cells = []
+    for _ in range(4):
+        recs = []
+        for _u in range(30):
+            u = int(rng.integers(0, 1 << 24))
+            g = int(rng.integers(0, n_genes - 1))
+            a = list(range(g * per, g * per + 40))
+            bsub = list(range(g * per + 3, g * per + 38))
+            csub = list(range(g * per + 30, g * per + 62))          # spills into the next gene
+            for lab in (a, bsub, csub)[: int(rng.integers(2, 4))]:
+                for _r in range(int(rng.integers(1, 4))):
+                    recs.append((u, lab))
+            if rng.random() < 0.5:
+                recs.append((u ^ 1, a))                                # a 1-Hamming neighbour
+        for _bg in range(110):
+            recs.append((int(rng.integers(0, 1 << 24)), [int(rng.integers(0, n_genes * per))]))
+        rng.shuffle(recs)
+        cells.append(recs)
+    b = CellBatch.from_cells(cells)
+    check(QuantOpts(resolution=res, num_gene_ids=n_genes, num_rows=n_genes, umi_len=12), t2g, b, res)
+    cnt = emu_lib.last_counts()
+    assert sum(cnt[emu_lib.LIST_PS0:emu_lib.LIST_PS0 + 4]) == b.n_cells and cnt[emu_lib.LIST_GE_NORMAL] == 0, cnt
