@@ -1265,7 +1265,9 @@ __device__ inline void ge_back(const KArgs& a, const GeArgs& g, u32 cell, GeCell
     const u32 Lp = next_pow2(Lt);
     GE_FOR(e, Lp) p.tkey[e] = EMPTY_KEY;
     __syncthreads();
-    GE_FOR(e, Lt) p.tkey[e] = ((u64)p.ent_loc[e] << 32) | e;
+    // key = (support index, CLASS of the entry): a class holds an index at most once, so this sorts like
+    // (support index, entry) and the loops below read the class straight from the key
+    GE_FOR(j, G) for (u32 e = p.gcls_eoff[j]; e < p.gcls_eoff[j + 1]; ++e) p.tkey[e] = ((u64)p.ent_loc[e] << 32) | j;
     __syncthreads();
     sort_u64_staged(p.tkey, Lp, c.scratch, c.scratch_budget);
     for (u32 s = tid; s <= S; s += T) {  // g_off[s] = first sorted entry whose support index is >= s
@@ -1274,84 +1276,86 @@ __device__ inline void ge_back(const KArgs& a, const GeArgs& g, u32 cell, GeCell
       p.g_off[s] = lo;
     }
     __syncthreads();
-    // class of an entry: binary search in gcls_eoff
-    auto cls_of_entry = [&](u32 e) {
-      u32 lo = 0, hi = G;
-      while (lo + 1 < hi) { u32 mid = (lo + hi) >> 1; if (p.gcls_eoff[mid] <= e) lo = mid; else hi = mid; }
-      return lo;
-    };
-    // singleton tallies, accumulated per index in class order (integers: exact)
+    // singleton tallies, accumulated per index in class order (integers: exact). cls_inv[j] carries what
+    // class j adds to one of its indices in the M step: >= 0: abundance * cls_inv (multi-label class,
+    // set by the E step); -1: nothing; <= -3: the constant -(cls_inv + 2) = its count (singleton class)
+    GE_FOR(j, G) p.cls_inv[j] = (p.gcls_eoff[j + 1] - p.gcls_eoff[j] == 1) ? -((float)p.gcls_cnt[j] + 2.0f) : -1.0f;
+    __syncthreads();
     GE_FOR(s, S) {
       float t = 0.0f;
       for (u32 q = p.g_off[s]; q < p.g_off[s + 1]; ++q) {
-        const u32 e = (u32)p.tkey[q];
-        const u32 j = cls_of_entry(e);
-        if (p.gcls_eoff[j + 1] - p.gcls_eoff[j] == 1) t = __fadd_rn(t, (float)p.gcls_cnt[j]);
+        const float w = p.cls_inv[(u32)p.tkey[q]];
+        if (w < -2.0f) t = __fadd_rn(t, -w - 2.0f);
       }
       p.alpha_in[s] = t;
     }
     __syncthreads();
     if (needs_em) {
       const float uni = __fdiv_rn(1.0f, (float)g.num_alphas);
+      float* ain = p.alpha_in;     // ping-pong: the M step writes aout, then the two swap (no copy pass, one barrier less)
+      float* aout = p.alpha_out;
       GE_FOR(s, S)
-        p.alpha_in[s] = g.em_init_uniform ? uni : __fmul_rn(__fadd_rn(p.alpha_in[s], 0.5f), 1e-3f);
+        ain[s] = g.em_init_uniform ? uni : __fmul_rn(__fadd_rn(ain[s], 0.5f), 1e-3f);
       __syncthreads();
       auto abund = [&](u32 s) {
-        if (!usa) return p.alpha_in[s];
+        if (!usa) return ain[s];
         const u32 sa = p.sib_a[s], sb = p.sib_b[s];
         if (sb != NONE32 || p.sup[s] >= a.ao) {  // ambiguous: U + S + A
-          const float xu = sa != NONE32 ? p.alpha_in[sa] : 0.0f, xs = sb != NONE32 ? p.alpha_in[sb] : 0.0f;
-          return __fadd_rn(__fadd_rn(xu, xs), p.alpha_in[s]);
+          const float xu = sa != NONE32 ? ain[sa] : 0.0f, xs = sb != NONE32 ? ain[sb] : 0.0f;
+          return __fadd_rn(__fadd_rn(xu, xs), ain[s]);
         }
-        const float xa = sa != NONE32 ? p.alpha_in[sa] : 0.0f;   // U or S: A + self
-        return __fadd_rn(xa, p.alpha_in[s]);
+        const float xa = sa != NONE32 ? ain[sa] : 0.0f;   // U or S: A + self
+        return __fadd_rn(xa, ain[s]);
       };
       u32 it = 0;
       bool last_round = false;
+      if (tid == 0) { sh->flag = 0; sh->cnt1 = 0; }
+      __syncthreads();
       for (;;) {
         // E step, per class: inv = count / sum of abundances (label order)
         GE_FOR(j, G) {
           const u32 e0 = p.gcls_eoff[j], e1 = p.gcls_eoff[j + 1];
-          float inv = -1.0f;  // < 0: class contributes nothing
-          if (e1 - e0 > 1) {
+          if (e1 - e0 > 1) {     // (singleton classes keep their constant)
+            float inv = -1.0f;   // class contributes nothing
             float den = 0.0f;
             for (u32 e = e0; e < e1; ++e) den = __fadd_rn(den, abund(p.ent_loc[e]));
             if (den > 0.0f) inv = __fdiv_rn((float)p.gcls_cnt[j], den);
+            p.cls_inv[j] = inv;
           }
-          p.cls_inv[j] = inv;
         }
-        if (tid == 0) sh->flag = 0;
         __syncthreads();
+        // "some index moved" flags alternate between two words: the word of iteration it+1 is cleared
+        // here, behind a barrier every thread reached after it last read that word (iteration it-1)
+        u32* moved = (it & 1u) ? &sh->cnt1 : &sh->flag;
+        if (tid == 0) *((it & 1u) ? &sh->flag : &sh->cnt1) = 0;
         // M step, per support index, contributions added in class order
         GE_FOR(s, S) {
           float out = 0.0f;
           const float ab = abund(s);
           for (u32 q = p.g_off[s]; q < p.g_off[s + 1]; ++q) {
-            const u32 e = (u32)p.tkey[q];
-            const u32 j = cls_of_entry(e);
-            if (p.gcls_eoff[j + 1] - p.gcls_eoff[j] == 1) out = __fadd_rn(out, (float)p.gcls_cnt[j]);
-            else if (p.cls_inv[j] >= 0.0f) out = __fadd_rn(out, __fmul_rn(ab, p.cls_inv[j]));
+            const float w = p.cls_inv[(u32)p.tkey[q]];
+            if (w >= 0.0f) out = __fadd_rn(out, __fmul_rn(ab, w));
+            else if (w < -2.0f) out = __fadd_rn(out, -w - 2.0f);
           }
-          p.alpha_out[s] = out;
-          if (out > 1e-2f && fabsf(__fsub_rn(p.alpha_in[s], out)) > 1e-2f) sh->flag = 1;
+          aout[s] = out;
+          if (out > 1e-2f && fabsf(__fsub_rn(ain[s], out)) > 1e-2f) *moved = 1;
         }
         __syncthreads();
-        const bool converged = sh->flag == 0;
-        GE_FOR(s, S) p.alpha_in[s] = p.alpha_out[s];
-        __syncthreads();
+        const bool converged = *moved == 0;
+        { float* t = ain; ain = aout; aout = t; }
         ++it;
         if (!usa) {  // M1: src/em.rs:538-565
           if (!(it < 2 || (it < 100 && !converged))) break;
         } else {     // M2: src/em.rs:391-443 (clamp, then one last round)
           if (last_round) break;
           if (it >= 2 && converged) {
-            GE_FOR(s, S) if (p.alpha_in[s] < 0.01f) p.alpha_in[s] = 0.0f;
+            GE_FOR(s, S) if (ain[s] < 0.01f) ain[s] = 0.0f;
             last_round = true;
             __syncthreads();
           } else if (!(it < 2 || (it < 100 && !converged))) break;
         }
       }
-      GE_FOR(s, S) if (p.alpha_in[s] < 0.01f) p.alpha_in[s] = 0.0f;
+      GE_FOR(s, S) { const float x = ain[s]; p.alpha_in[s] = x < 0.01f ? 0.0f : x; }
       __syncthreads();
     }
     // emit positive alphas, ascending index

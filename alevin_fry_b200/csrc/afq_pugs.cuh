@@ -46,20 +46,27 @@ __host__ __device__ inline u32 ps_table_size(u32 n) { return pow2_ge(n + n / 4 +
 
 // Arena words a cell of n records / P alignments is EXPECTED to need (vertex count guessed at
 // n/2; the kernel re-checks with the real counts and falls back if they do not fit).
-__host__ __device__ inline u32 ps_need_words(u32 n, u32 P, bool gene, bool em) {
+__host__ __device__ inline u32 ps_need_words(u32 n, u32 P, bool gene, bool em, bool usa) {
   const u32 rec = n + (n + 1) / 2 + ps_table_size(n);          // UMIs, classes, table: dead after compaction
   const u32 vest = n / 2 + 16;
   u32 bw = pow2_ge(2 * vest, 64); if (bw > 4096) bw = 4096;
   const u32 post = pow2_ge(vest + vest / 2 + 2, 64) + bw + 2 * vest + (em ? 0 : pow2_ge(vest, 1)) + 512;
   u32 w = P + (n + 2) / 2 + (gene ? (n + 1) / 2 : 0) + rec + 2 * vest + (post > rec ? post - rec : 0);
-  if (em) w += 2 * vest + P / 2 + 64;
+  if (em) {
+    w += 2 * vest + P / 2 + 64;
+    // the EM back end (ps_back_carve) on ~n/3 molecules with ~1.4 label entries each, + molecules at the top
+    const u32 M = n / 3 + 8, Lm = M + M / 2, per = usa ? 3u : 1u;
+    const u32 Mp = pow2_ge(M, 1), TK = pow2_ge(Lm, 1), Sp = pow2_ge(Lm * per, 1), Sr = Lm * per + 4;
+    const u32 back = 3 * Mp + 3 * (M + 2) + 3 * TK + Lm + Sp + 5 * Sr + M + 2 * vest + Lm + 64;
+    if (back > w) w = back;
+  }
   return w;
 }
 // smallest arena variant that is expected to hold the cell, or -1 (global_ok: variant 3 is available)
-__host__ __device__ inline int ps_variant_for(u64 n, u64 P, bool gene, bool em, bool global_ok) {
+__host__ __device__ inline int ps_variant_for(u64 n, u64 P, bool gene, bool em, bool usa, bool global_ok) {
   if (n >= PS_MAX_RECORDS || P >= (1ull << 30) || n == 0) return -1;
   if (P < PS_MAX_REFS) {
-    const u32 need = ps_need_words((u32)n, (u32)P, gene, em);
+    const u32 need = ps_need_words((u32)n, (u32)P, gene, em, usa);
     for (int v = 0; v < PS_SMEM_VARIANTS; ++v)
       if (need <= ps_arena_words(v)) return v;
   }
@@ -224,7 +231,7 @@ __device__ __forceinline__ u32 ps_emit_genes(const PsSink& sk, const u32* genes,
 // dependent shared-memory loads per round and a single thread on a 12-vertex component kept the
 // whole CTA waiting at the barrier (ncu r1u: 39 % of all stall samples).
 // ---------------------------------------------------------------------------------------------
-constexpr u32 PS_WARP_COMP = 9;       // components of this many vertices and more take the warp form
+constexpr u32 PS_WARP_COMP = 17;      // components of this many vertices and more take the warp form
 
 __device__ __forceinline__ bool ps_canon_less(const PsCell& c, u32 x, u32 y) {   // (class label lexicographic, UMI)
   const u32 cx = c.vcls(x), cy = c.vcls(y);
@@ -288,7 +295,7 @@ __device__ __forceinline__ void ps_emit_mcc(const PsCell& c, const PsSink& sk, u
   }
 }
 
-// G lanes per component (G = 4 or 8, sizes <= G), 32/G components per warp pass; every lane of the
+// G lanes per component (G = 2, 4, 8 or 16, sizes <= G), 32/G components per warp pass; every lane of the
 // warp calls. Lane `sub` of a group owns start vertex `sub`. Everything a BFS needs is precomputed as
 // bitmasks RELATIVE TO THE LANE'S OWN LABEL: M[j] = positions k of my label whose transcript is in
 // vertex j's label. Then the BFS of ALL my transcripts at once is a fixed number of branch-free
@@ -331,9 +338,14 @@ __device__ inline void ps_cover_group(const PsCell& c, const PsSink& sk, u32* wi
       if (has && hj) {
         if ((u32)j == sub || cj == ci) m = full;
         else {
-          const u32* lj = c.lab(cj);
+          const u32* lj = c.lab(cj);      // positions of my label present in j's: one merge of the two sorted lists
           const u32 lnj = c.len(cj);
-          for (u32 q = 0; q < ln; ++q) if (sorted_contains(lj, lnj, li[q])) m |= 1u << q;
+          for (u32 qa = 0, qb = 0; qa < ln && qb < lnj;) {
+            const u32 x = li[qa], y = lj[qb];
+            if (x == y) { m |= 1u << qa; ++qa; ++qb; }
+            else if (x < y) ++qa;
+            else ++qb;
+          }
         }
         if ((u32)j != sub) {
           const u32 x = ui ^ uj;
@@ -358,15 +370,19 @@ __device__ inline void ps_cover_group(const PsCell& c, const PsSink& sk, u32* wi
         u32 reach[G];
 #pragma unroll
         for (int j = 0; j < G; ++j) reach[j] = (u32)j == sub ? full : 0u;
-#pragma unroll
-        for (int round = 0; round < G - 1; ++round) {
+        for (int round = 0; round < G - 1; ++round) {     // a path has at most G - 1 edges; usually 1-2 rounds
+          u32 changed = 0;
 #pragma unroll
           for (int x = 0; x < G; ++x) {
             const u32 ax = amx[x] & unc;
 #pragma unroll
-            for (int j = 0; j < G; ++j)
-              if ((ax >> j) & 1u) reach[j] |= reach[x] & M[j];
+            for (int j = 0; j < G; ++j) {
+              const u32 add = ((ax >> j) & 1u) ? (reach[x] & M[j] & ~reach[j]) : 0u;
+              reach[j] |= add;
+              changed |= add;
+            }
           }
+          if (!changed) break;
         }
         for (u32 q = 0; q < ln; ++q) {            // first transcript with the largest reachable set
           u32 sz = 0, mk = 0;
@@ -471,9 +487,10 @@ __device__ inline bool ps_back_carve(u32* A, u32 lo, u32 hi, u32 M, u32 Lm, u32 
   o->gcls_m = (u32*)take(4ull * (M + 1)); o->gcls_cnt = (u32*)take(4ull * (M + 1)); o->gcls_eoff = (u32*)take(4ull * (M + 2));
   o->tkey = (u64*)take(8ull * TK);
   o->ent_idx = (u32*)take(4ull * (TK + 1)); o->ent_loc = (u32*)take(4ull * (Lm + 1));
-  o->sup = (u32*)take(4ull * Sp); o->g_off = (u32*)take(4ull * (Sp + 2));
-  o->alpha_in = (float*)take(4ull * Sp); o->alpha_out = (float*)take(4ull * Sp); o->cls_inv = (float*)take(4ull * (M + 1));
-  o->sib_a = (u32*)take(4ull * Sp); o->sib_b = (u32*)take(4ull * Sp);
+  const u32 Sr = Lm * per + 2;     // support indices before de-duplication (only `sup` is sorted: power of two)
+  o->sup = (u32*)take(4ull * Sp); o->g_off = (u32*)take(4ull * (Sr + 2));
+  o->alpha_in = (float*)take(4ull * Sr); o->alpha_out = (float*)take(4ull * Sr); o->cls_inv = (float*)take(4ull * (M + 1));
+  o->sib_a = (u32*)take(4ull * Sr); o->sib_b = (u32*)take(4ull * Sr);
   return align8(off) <= (u64)hi * 4;
 }
 
@@ -792,14 +809,16 @@ __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A
     GE_FOR(v, V) if (root[v] == v && csz[v] > 1) clist[atomicAdd(&ex->szc[csz[v]], 1u)] = v;
     __syncthreads();
     // after the scatter szc[z] = END of size z's range
-    const u32 K4 = ex->szc[4], K8 = ex->szc[8];
+    const u32 K2 = ex->szc[2], K4 = ex->szc[4], K8 = ex->szc[8], K16 = ex->szc[16];
     if (tid == 0) ex->n_over = 0;
     __syncthreads();
-    ps_cover_group<4>(c, sk, winners, gbm, head, nxt, clist, 0, K4, g.pug_exact_umi != 0, olist, &ex->n_over);
+    ps_cover_group<2>(c, sk, winners, gbm, head, nxt, clist, 0, K2, g.pug_exact_umi != 0, olist, &ex->n_over);
+    ps_cover_group<4>(c, sk, winners, gbm, head, nxt, clist, K2, K4, g.pug_exact_umi != 0, olist, &ex->n_over);
     ps_cover_group<8>(c, sk, winners, gbm, head, nxt, clist, K4, K8, g.pug_exact_umi != 0, olist, &ex->n_over);
+    ps_cover_group<16>(c, sk, winners, gbm, head, nxt, clist, K8, K16, g.pug_exact_umi != 0, olist, &ex->n_over);
     const u32 wid = tid >> 5, nw = T >> 5;
     u32* wmem = wscr + wid * 64;
-    for (u32 k = K - 1 - wid; (int)k >= (int)K8; k -= nw)        // largest components first
+    for (u32 k = K - 1 - wid; (int)k >= (int)K16; k -= nw)       // largest components first
       ps_cover_warp(c, sk, winners, head, nxt, clist[k], g.pug_exact_umi != 0, gbm, wmem, wmem + 32);
     __syncthreads();
     const u32 KO = ex->n_over;                                   // small components with a long label
@@ -969,7 +988,7 @@ __global__ void k_bin_cells_ge(KArgs a, int force_bin, u32 big_records, u32 need
     atomicMax(&a.ctl->ge_max_n[w], (u32)n);
     atomicMax(&a.ctl->ge_max_p[w], p);
     if (w == 1 && (ps_mode & 1u)) {
-      const int v = ps_variant_for(n, p, (ps_mode & 2u) != 0, (ps_mode & 4u) != 0, (ps_mode & 8u) != 0);
+      const int v = ps_variant_for(n, p, (ps_mode & 2u) != 0, (ps_mode & 4u) != 0, a.usa_mode != 0, (ps_mode & 8u) != 0);
       if (v >= 0) b = PS_LIST0 + v;
     }
   }

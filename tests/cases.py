@@ -1,0 +1,52 @@
+"""Hand-built cells shared by the emulator tier and the GPU tier (test infrastructure)."""
+import numpy as np
+
+
+def star_cells(rng, n_cells, n_genes):
+    """cells made of 1-Hamming 'stars' (a centre UMI + 2..6 of its single-base substitutions) over a
+    few overlapping transcript sets: components of 6..30 (class, UMI) vertices for the warp-cooperative cover"""
+    cells = []
+    for _ in range(n_cells):
+        recs = []
+        for _star in range(int(rng.integers(3, 7))):
+            centre = int(rng.integers(0, 1 << 24))
+            g = int(rng.integers(0, n_genes - 2))
+            labels = [[3 * g], [3 * g, 3 * g + 1], [3 * g, 3 * g + 1, 3 * g + 4], [3 * g + 1, 3 * g + 4], [3 * g + 4, 3 * g + 5]]
+            leaves = rng.choice(36, size=int(rng.integers(2, 7)), replace=False)
+            umis = [centre] + [centre ^ ((int(k) % 3 + 1) << (2 * (int(k) // 3))) for k in leaves]
+            for u in umis:
+                for _r in range(int(rng.integers(1, 4))):
+                    recs.append((u, labels[int(rng.integers(0, len(labels)))]))
+        for _bg in range(120):   # background so the cell is not tiny
+            recs.append((int(rng.integers(0, 1 << 24)), [3 * int(rng.integers(0, n_genes))]))
+        rng.shuffle(recs)
+        cells.append(recs)
+    return cells
+
+
+
+
+def long_label_cells():
+    """cells whose eq-class labels hold 32..40 transcripts: (n_genes, tid_to_gid, cells)"""
+    rng = np.random.default_rng(3)
+    n_genes, per = 20, 50
+    t2g = np.repeat(np.arange(n_genes, dtype=np.uint32), per)
+    cells = []
+    for _ in range(4):
+        recs = []
+        for _u in range(30):
+            u = int(rng.integers(0, 1 << 24))
+            g = int(rng.integers(0, n_genes - 1))
+            a = list(range(g * per, g * per + 40))
+            bsub = list(range(g * per + 3, g * per + 38))
+            csub = list(range(g * per + 30, g * per + 62))          # spills into the next gene
+            for lab in (a, bsub, csub)[: int(rng.integers(2, 4))]:
+                for _r in range(int(rng.integers(1, 4))):
+                    recs.append((u, lab))
+            if rng.random() < 0.5:
+                recs.append((u ^ 1, a))                                # a 1-Hamming neighbour
+        for _bg in range(110):
+            recs.append((int(rng.integers(0, 1 << 24)), [int(rng.integers(0, n_genes * per))]))
+        rng.shuffle(recs)
+        cells.append(recs)
+    return n_genes, t2g, cells

@@ -5,6 +5,7 @@ container has no GPU, and it is also the debugging harness for the kernels.)"""
 import numpy as np
 import pytest
 
+import cases
 import emu_lib
 import oracle_lib
 from alevin_fry_b200 import CellBatch, QuantOpts, synth, FLAG_ALT
@@ -261,34 +262,12 @@ def test_emu_pug_smem_usa_and_record_order(res):
     assert np.array_equal(got.col, got2.col) and np.array_equal(got.val, got2.val)
 
 
-def _star_cells(rng, n_cells, n_genes):
-    """cells made of 1-Hamming 'stars' (a centre UMI + 2..6 of its single-base substitutions) over a
-    few overlapping transcript sets: components of 6..30 (class, UMI) vertices for the warp-cooperative cover"""
-    cells = []
-    for _ in range(n_cells):
-        recs = []
-        for _star in range(int(rng.integers(3, 7))):
-            centre = int(rng.integers(0, 1 << 24))
-            g = int(rng.integers(0, n_genes - 2))
-            labels = [[3 * g], [3 * g, 3 * g + 1], [3 * g, 3 * g + 1, 3 * g + 4], [3 * g + 1, 3 * g + 4], [3 * g + 4, 3 * g + 5]]
-            leaves = rng.choice(36, size=int(rng.integers(2, 7)), replace=False)
-            umis = [centre] + [centre ^ ((int(k) % 3 + 1) << (2 * (int(k) // 3))) for k in leaves]
-            for u in umis:
-                for _r in range(int(rng.integers(1, 4))):
-                    recs.append((u, labels[int(rng.integers(0, len(labels)))]))
-        for _bg in range(120):   # background so the cell is not tiny
-            recs.append((int(rng.integers(0, 1 << 24)), [3 * int(rng.integers(0, n_genes))]))
-        rng.shuffle(recs)
-        cells.append(recs)
-    return cells
-
-
 @pytest.mark.parametrize("res", ["parsimony", "parsimony-em", "parsimony-gene"])
 def test_emu_pug_smem_warp_cover_on_star_components(res):
     rng = np.random.default_rng(11)
     n_genes = 50
     t2g = np.repeat(np.arange(n_genes, dtype=np.uint32), 3)
-    b = CellBatch.from_cells(_star_cells(rng, 5, n_genes))
+    b = CellBatch.from_cells(cases.star_cells(rng, 5, n_genes))
     o = QuantOpts(resolution=res, num_gene_ids=n_genes, num_rows=n_genes, umi_len=12)
     check(o, t2g, b, res)
     cnt = emu_lib.last_counts()
@@ -311,27 +290,7 @@ def test_emu_pug_global_arena_variant(res, monkeypatch):
 def test_emu_pug_smem_long_labels_take_the_warp_cover(res):
     # labels of more than 32 transcripts do not fit the group cover's position masks: such components
     # are re-routed to the warp-cooperative cover inside the same kernel
-    rng = np.random.default_rng(3)
-    n_genes, per = 20, 50
-    t2g = np.repeat(np.arange(n_genes, dtype=np.uint32), per)
-    cells = []
-    for _ in range(4):
-        recs = []
-        for _u in range(30):
-            u = int(rng.integers(0, 1 << 24))
-            g = int(rng.integers(0, n_genes - 1))
-            a = list(range(g * per, g * per + 40))
-            bsub = list(range(g * per + 3, g * per + 38))
-            csub = list(range(g * per + 30, g * per + 62))          # spills into the next gene
-            for lab in (a, bsub, csub)[: int(rng.integers(2, 4))]:
-                for _r in range(int(rng.integers(1, 4))):
-                    recs.append((u, lab))
-            if rng.random() < 0.5:
-                recs.append((u ^ 1, a))                                # a 1-Hamming neighbour
-        for _bg in range(110):
-            recs.append((int(rng.integers(0, 1 << 24)), [int(rng.integers(0, n_genes * per))]))
-        rng.shuffle(recs)
-        cells.append(recs)
+    n_genes, t2g, cells = cases.long_label_cells()
     b = CellBatch.from_cells(cells)
     check(QuantOpts(resolution=res, num_gene_ids=n_genes, num_rows=n_genes, umi_len=12), t2g, b, res)
     cnt = emu_lib.last_counts()

@@ -5,6 +5,7 @@ import os
 import numpy as np
 import pytest
 
+import cases
 import oracle_lib
 from alevin_fry_b200 import CellBatch, QuantOpts, Quantifier, synth, FLAG_TINY
 
@@ -239,3 +240,87 @@ def test_full_size_invariants_and_sampled_parity(cfg, res, full_cells):
         lo, hi = int(rs[k].row_ptr[c0]), int(rs[k].row_ptr[c0 + 150])
         assert np.array_equal(rs[k].col[lo:hi], want.col) and np.array_equal(rs[k].val[lo:hi], want.val)
         assert np.array_equal(rs[k].sum_umi[c0:c0 + 150], want.sum_umi)
+
+
+# ---- k_pug_smem: the shared-memory kernel of the parsimony family / cr-like-em --------------------
+def gpu_quant_profiled(opts, t2g, batch):
+    """result + {kernel name: launches} of the run"""
+    with Quantifier(opts, t2g) as q:
+        q.set_profiling(True)
+        r = q.quantify_batch(batch)
+        prof = q.profile()
+    return r, {k: v[1] for k, v in prof.items()}
+
+
+PS_RES = ["parsimony", "parsimony-em", "parsimony-gene", "parsimony-gene-em", "cr-like-em"]
+
+
+@pytest.mark.parametrize("res", PS_RES)
+def test_pug_smem_runs_and_matches_the_global_arena_kernel(res, monkeypatch):
+    spec = synth.config_spec("C3")
+    b = synth.generate(spec, 200, 400)
+    t2g = synth.tid_to_gid(spec)
+    o = opts_for(spec, res)
+    got, launches = gpu_quant_profiled(o, t2g, b)
+    assert sum(n for k, n in launches.items() if k.startswith("k_pug_smem")) > 0, launches
+    want = oracle_lib.oracle_quant(o, t2g, b)
+    assert_same(got, want, exact=not res.endswith("-em"), ctx=res)
+    monkeypatch.setenv("AFQ_NO_PS", "1")            # the global-arena kernel alone
+    old, launches = gpu_quant_profiled(o, t2g, b)
+    assert sum(n for k, n in launches.items() if k.startswith("k_pug_smem")) == 0, launches
+    assert_same(old, want, exact=not res.endswith("-em"), ctx=res + "/no-ps")
+    if not res.endswith("-em"):
+        assert np.array_equal(old.val, got.val)
+
+
+@pytest.mark.parametrize("res", ["parsimony", "parsimony-em", "cr-like-em"])
+@pytest.mark.parametrize("limit", [700, 3000, 9000])
+def test_pug_smem_hands_back_cells_that_do_not_fit(res, limit, monkeypatch):
+    # a smaller arena than the binning assumed: cells fail at different points of k_pug_smem and are
+    # redone by k_gene_eqc; results must not change
+    monkeypatch.setenv("AFQ_PS_LIMIT_WORDS", str(limit))
+    monkeypatch.setenv("AFQ_NO_PS_GLOBAL", "1")
+    spec = synth.config_spec("C3")
+    b = synth.generate(spec, 900, 300)
+    t2g = synth.tid_to_gid(spec)
+    o = opts_for(spec, res)
+    got, launches = gpu_quant_profiled(o, t2g, b)
+    assert launches.get("k_gene_eqc", 0) > 0, launches
+    assert_same(got, oracle_lib.oracle_quant(o, t2g, b), exact=not res.endswith("-em"), ctx=f"{res}/{limit}")
+
+
+@pytest.mark.parametrize("res", ["parsimony", "parsimony-em", "cr-like-em"])
+def test_pug_global_arena_variant_big_cells(res):
+    spec = synth.SynthSpec(fixed_reads=12000, n_genes=3000)
+    b = synth.generate(spec, 0, 24)
+    t2g = synth.tid_to_gid(spec)
+    o = opts_for(spec, res)
+    got, launches = gpu_quant_profiled(o, t2g, b)
+    assert launches.get("k_pug_smem<3>(global arena)", 0) > 0, launches
+    assert_same(got, oracle_lib.oracle_quant(o, t2g, b), exact=not res.endswith("-em"), ctx=res)
+
+
+@pytest.mark.parametrize("res", ["parsimony", "parsimony-em", "parsimony-gene"])
+def test_pug_smem_group_and_warp_cover_hand_built_components(res):
+    rng = np.random.default_rng(11)
+    n_genes = 50
+    t2g = np.repeat(np.arange(n_genes, dtype=np.uint32), 3)
+    b = CellBatch.from_cells(cases.star_cells(rng, 40, n_genes))
+    o = QuantOpts(resolution=res, num_gene_ids=n_genes, num_rows=n_genes, umi_len=12)
+    assert_same(gpu_quant(o, t2g, b), oracle_lib.oracle_quant(o, t2g, b), exact=not res.endswith("-em"), ctx=res)
+    n_genes, t2g, cells = cases.long_label_cells()
+    b = CellBatch.from_cells(cells * 8)
+    o = QuantOpts(resolution=res, num_gene_ids=n_genes, num_rows=n_genes, umi_len=12)
+    assert_same(gpu_quant(o, t2g, b), oracle_lib.oracle_quant(o, t2g, b), exact=not res.endswith("-em"), ctx=res + "/long")
+
+
+def test_pug_smem_dense_umi_space_components():
+    # 4..6-base UMIs: components of every size up to > 32 vertices (those cells are handed back)
+    for umi_len, thresh in ((4, 1000), (6, 1000), (6, 5)):
+        spec = synth.SynthSpec(n_genes=300, umi_len=umi_len, reads_mean=600.0, reads_per_umi=1.5, umi_err=0.05)
+        b = synth.generate(spec, 0, 60)
+        t2g = synth.tid_to_gid(spec)
+        for res in ("parsimony", "parsimony-em"):
+            o = QuantOpts(resolution=res, usa_mode=spec.usa_mode, num_gene_ids=spec.num_gene_ids, num_rows=spec.num_rows,
+                          umi_len=umi_len, large_graph_thresh=thresh, small_thresh=0)
+            assert_same(gpu_quant(o, t2g, b), oracle_lib.oracle_quant(o, t2g, b), exact=not res.endswith("-em"), ctx=f"{res}/{umi_len}/{thresh}")
