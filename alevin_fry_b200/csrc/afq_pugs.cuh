@@ -39,6 +39,7 @@ __host__ __device__ constexpr u32 ps_threads(int v) { return v == 0 ? 256u : (v 
 __host__ __device__ constexpr u32 ps_arena_words(int v) { return v == 0 ? 18u * 1024u : (v == 1 ? 27u * 1024u : 56u * 1024u); }
 __host__ __device__ constexpr u32 ps_min_blocks(int v) { return v == 0 ? 3u : (v == 1 ? 2u : (v == 2 ? 1u : 2u)); }
 constexpr u32 PS_EMPTY = 0xFFFFFFFFu;
+constexpr u32 PS_MULTI_GENE = 0xFFFFFFFEu;
 constexpr u32 PS_MAX_RECORDS = 65535;   // record indices and read counts share a 32-bit table entry (16 bits each)
 constexpr u32 PS_MAX_REFS = 65535;      // 16-bit relative record offsets in the shared-memory variants (32-bit in variant 3)
 
@@ -51,7 +52,7 @@ __host__ __device__ inline u32 ps_need_words(u32 n, u32 P, bool gene, bool em, b
   const u32 vest = n / 2 + 16;
   u32 bw = pow2_ge(2 * vest, 64); if (bw > 4096) bw = 4096;
   const u32 post = pow2_ge(vest + vest / 2 + 2, 64) + bw + 2 * vest + (em ? 0 : pow2_ge(vest, 1)) + 512;
-  u32 w = P + (n + 2) / 2 + (gene ? (n + 1) / 2 : 0) + rec + 2 * vest + (post > rec ? post - rec : 0);
+  u32 w = P + (n + 2) / 2 + (gene ? (n + 1) / 2 : 0) + rec + 3 * vest + (post > rec ? post - rec : 0);
   if (em) {
     w += 2 * vest + P / 2 + 64;
     // the EM back end (ps_back_carve) on ~n/3 molecules with ~1.4 label entries each, + molecules at the top
@@ -77,7 +78,7 @@ __host__ __device__ inline u64 ps_global_words(u32 n, u32 P, u32 num_rows) {
   if (n >= PS_MAX_RECORDS) n = PS_MAX_RECORDS - 1;
   const u64 rec = (u64)P + (n + 2) + (n + 1) / 2 + n + (n + 1) / 2 + ps_table_size(n);
   const u64 post = (u64)pow2_ge(n + n / 2 + 2, 64) + 4096 + 3ull * n + pow2_ge(n, 1) + 2048 + 2ull * ((num_rows + 31) / 32);
-  return (rec + 2ull * n + post + 2ull * n + P + 4096 + 3) & ~3ull;   // + EM: molecule offsets / lengths and labels; 16-byte multiple
+  return (rec + 3ull * n + post + 2ull * n + P + 4096 + 3) & ~3ull;   // + EM: molecule offsets / lengths and labels; 16-byte multiple
 }
 
 struct PsExtra {
@@ -108,6 +109,7 @@ struct PsCell {
   const u16* rlen;      // [n] label lengths (PUG_GENE) or nullptr (length = offset difference)
   const u32* vumi;      // [V]
   const u32* vinfo;     // [V] class (representative record) << 16 | read count
+  const u32* vgene;     // [V] the class's gene if it has exactly one, PS_MULTI_GENE, or NONE32 (empty label)
   bool gene;            // labels already are gene ids
   __device__ __forceinline__ u32 off(u32 r) const { return roff ? (u32)roff[r] : roff32[r]; }
   __device__ __forceinline__ const u32* lab(u32 r) const { return refs + off(r); }
@@ -231,7 +233,8 @@ __device__ __forceinline__ u32 ps_emit_genes(const PsSink& sk, const u32* genes,
 // dependent shared-memory loads per round and a single thread on a 12-vertex component kept the
 // whole CTA waiting at the barrier (ncu r1u: 39 % of all stall samples).
 // ---------------------------------------------------------------------------------------------
-constexpr u32 PS_WARP_COMP = 17;      // components of this many vertices and more take the warp form
+constexpr u32 PS_WARP_COMP = 9;       // components of this many vertices and more take the warp form (a 16-lane group form
+                                      // was measured: register arrays of 16 spill 1.2 KB per thread and C5 got 25 % slower, r1x)
 
 __device__ __forceinline__ bool ps_canon_less(const PsCell& c, u32 x, u32 y) {   // (class label lexicographic, UMI)
   const u32 cx = c.vcls(x), cy = c.vcls(y);
@@ -295,7 +298,7 @@ __device__ __forceinline__ void ps_emit_mcc(const PsCell& c, const PsSink& sk, u
   }
 }
 
-// G lanes per component (G = 2, 4, 8 or 16, sizes <= G), 32/G components per warp pass; every lane of the
+// G lanes per component (G = 2, 4 or 8, sizes <= G), 32/G components per warp pass; every lane of the
 // warp calls. Lane `sub` of a group owns start vertex `sub`. Everything a BFS needs is precomputed as
 // bitmasks RELATIVE TO THE LANE'S OWN LABEL: M[j] = positions k of my label whose transcript is in
 // vertex j's label. Then the BFS of ALL my transcripts at once is a fixed number of branch-free
@@ -406,7 +409,9 @@ __device__ inline void ps_cover_group(const PsCell& c, const PsSink& sk, u32* wi
 #pragma unroll
         for (int j = 0; j < G; ++j) if ((mask >> j) & 1u) inter &= M[j];
         (void)my_k;
-        const u32 slot = ps_emit(c, sk, li, ln, [&](u32 q, u32) { return ((inter >> q) & 1u) != 0; });
+        const u32 gv = c.vgene[v];
+        const u32 slot = (gv < PS_MULTI_GENE && inter != 0) ? ps_emit_genes(sk, &gv, 1u)
+                                                            : ps_emit(c, sk, li, ln, [&](u32 q, u32) { return ((inter >> q) & 1u) != 0; });
         if (sk.mode != 2 && slot != NONE32) {
           winners[atomicAdd(&sk.ex->n_win, 1u)] = slot;
           if (gbm) atomicOr(&gbm[slot >> 5], 1u << (slot & 31));
@@ -535,7 +540,7 @@ __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A
   for (u32 i = tid; i < TN; i += T) tab[i] = PS_EMPTY;
   __syncthreads();
   PsCell c;
-  c.a = &a; c.refs = refs; c.roff = roff; c.roff32 = roff32; c.rlen = rlen; c.gene = gene; c.vumi = nullptr; c.vinfo = nullptr;
+  c.a = &a; c.refs = refs; c.roff = roff; c.roff32 = roff32; c.rlen = rlen; c.gene = gene; c.vumi = nullptr; c.vinfo = nullptr; c.vgene = nullptr;
   if (gene) {   // sorted-dedup gene projection of every record, in place (src/eq_class.rs:742-744)
     GE_FOR(i, n) {
       u32* dst = refs + c.off(i);
@@ -594,7 +599,7 @@ __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A
     u32 pos = block_exscan(cnt, sh->scan, &V);
     // dense arrays + (EM) molecule offsets / lengths at the top of the arena must fit
     const u32 top = em ? AW - 2 * V : AW;
-    if (off_dense + 2 * V > top || 2 * V > AW) return false;            // uniform: V is a block-wide value
+    if (off_dense + 3 * V > top || 3 * V > AW) return false;            // uniform: V is a block-wide value
     u32* vumi_w = A + off_dense;
     u32* vinfo_w = vumi_w + V;
     for (u32 i = lo; i < hi; ++i) {
@@ -609,10 +614,28 @@ __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A
   }
   __syncthreads();
   const u32* vumi = c.vumi;
+  // the gene of every vertex whose class maps to ONE gene (the usual case), looked up here with all
+  // lanes busy: the emission inside the serialised cover rounds then needs no tid_to_gid gather
+  // (ncu r1w: the winner lane's dependent __ldg chain sat on the cover's critical path)
+  u32* vgene = A + off_dense + 2 * V;
+  GE_FOR(v, V) {
+    const u32 cv = c.vcls(v);
+    const u32* lv = c.lab(cv);
+    const u32 ln = c.len(cv);
+    u32 g0 = NONE32;
+    for (u32 k = 0; k < ln; ++k) {
+      const u32 gg = c.gene_of(lv[k]);
+      if (g0 == NONE32) g0 = gg;
+      else if (gg != g0) { g0 = PS_MULTI_GENE; break; }
+    }
+    vgene[v] = g0;
+  }
+  c.vgene = vgene;
+  __syncthreads();
 
   // ---- re-carve: chains, union-find, Bloom bitmap, winners go into the dead record arrays
   // [off_rec, off_dense) first and into the free space behind the dense vertices after that ------
-  u32 segA = off_rec, segB = off_dense + 2 * V;
+  u32 segA = off_rec, segB = off_dense + 3 * V;
   const u32 topB = em ? AW - 2 * V : AW;
   bool fits = true;
   auto alloc = [&](u32 words) -> u32* {
@@ -783,8 +806,12 @@ __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A
       const u32 r = root[v];
       const u32 sz = csz[r];
       if (sz == 1) {   // singleton component: the class label itself (src/pugutils.rs:1262-1322)
-        const u32 cv = c.vcls(v);
-        slot = ps_emit(c, sk, c.lab(cv), c.len(cv), [](u32, u32) { return true; });
+        const u32 gv = vgene[v];
+        if (gv < PS_MULTI_GENE) slot = ps_emit_genes(sk, &gv, 1u);
+        else {
+          const u32 cv = c.vcls(v);
+          slot = ps_emit(c, sk, c.lab(cv), c.len(cv), [](u32, u32) { return true; });
+        }
       } else {
         nxt[v] = atomicExch(&head[r], v);
         if (v == r) atomicAdd(&ex->szc[sz > SMALL_COMP ? SMALL_COMP + 1 : sz], 1u);
@@ -809,16 +836,15 @@ __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A
     GE_FOR(v, V) if (root[v] == v && csz[v] > 1) clist[atomicAdd(&ex->szc[csz[v]], 1u)] = v;
     __syncthreads();
     // after the scatter szc[z] = END of size z's range
-    const u32 K2 = ex->szc[2], K4 = ex->szc[4], K8 = ex->szc[8], K16 = ex->szc[16];
+    const u32 K2 = ex->szc[2], K4 = ex->szc[4], K8 = ex->szc[8];
     if (tid == 0) ex->n_over = 0;
     __syncthreads();
     ps_cover_group<2>(c, sk, winners, gbm, head, nxt, clist, 0, K2, g.pug_exact_umi != 0, olist, &ex->n_over);
     ps_cover_group<4>(c, sk, winners, gbm, head, nxt, clist, K2, K4, g.pug_exact_umi != 0, olist, &ex->n_over);
     ps_cover_group<8>(c, sk, winners, gbm, head, nxt, clist, K4, K8, g.pug_exact_umi != 0, olist, &ex->n_over);
-    ps_cover_group<16>(c, sk, winners, gbm, head, nxt, clist, K8, K16, g.pug_exact_umi != 0, olist, &ex->n_over);
     const u32 wid = tid >> 5, nw = T >> 5;
     u32* wmem = wscr + wid * 64;
-    for (u32 k = K - 1 - wid; (int)k >= (int)K16; k -= nw)       // largest components first
+    for (u32 k = K - 1 - wid; (int)k >= (int)K8; k -= nw)        // largest components first
       ps_cover_warp(c, sk, winners, head, nxt, clist[k], g.pug_exact_umi != 0, gbm, wmem, wmem + 32);
     __syncthreads();
     const u32 KO = ex->n_over;                                   // small components with a long label
