@@ -444,11 +444,16 @@ __device__ __forceinline__ void visit_neighbours(const GeCell& c, u32 V, u32 umi
 }
 
 // lock-free union-find (roots are the minimum vertex id of their set)
+// (path halving: a non-root's parent is re-pointed at its grandparent with a plain store. Links are
+// only ever made by CAS on ROOTS (parent[hi] == hi), and a non-root never becomes a root again, so the
+// store cannot interfere with a link; it always points at an ancestor.)
 __device__ inline u32 uf_find(u32* parent, u32 x) {
   for (;;) {
     const u32 p = *(volatile u32*)&parent[x];
     if (p == x) return x;
-    x = p;
+    const u32 gp = *(volatile u32*)&parent[p];
+    if (gp != p) *(volatile u32*)&parent[x] = gp;
+    x = gp;
   }
 }
 __device__ inline void uf_union(u32* parent, u32 a, u32 b) {

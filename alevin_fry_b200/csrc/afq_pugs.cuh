@@ -38,6 +38,8 @@ constexpr int PS_SMEM_VARIANTS = 3;
 __host__ __device__ constexpr u32 ps_threads(int v) { return v == 0 ? 256u : (v == 1 ? 512u : (v == 2 ? 1024u : 512u)); }
 __host__ __device__ constexpr u32 ps_arena_words(int v) { return v == 0 ? 18u * 1024u : (v == 1 ? 27u * 1024u : 56u * 1024u); }
 __host__ __device__ constexpr u32 ps_min_blocks(int v) { return v == 0 ? 3u : (v == 1 ? 2u : (v == 2 ? 1u : 2u)); }
+constexpr u32 PS_WSCR_WORDS = 64 + 256; // per-warp scratch of the warp-cooperative cover (members, masks, 16 x 16 label masks)
+constexpr u32 PS_COVER_WARPS = 4;       // warps of a CTA that run the warp form (bounds its shared scratch: 5 KB)
 constexpr u32 PS_EMPTY = 0xFFFFFFFFu;
 constexpr u32 PS_MULTI_GENE = 0xFFFFFFFEu;
 constexpr u32 PS_MAX_RECORDS = 65535;   // record indices and read counts share a 32-bit table entry (16 bits each)
@@ -51,7 +53,7 @@ __host__ __device__ inline u32 ps_need_words(u32 n, u32 P, bool gene, bool em, b
   const u32 rec = n + (n + 1) / 2 + ps_table_size(n);          // UMIs, classes, table: dead after compaction
   const u32 vest = n / 2 + 16;
   u32 bw = pow2_ge(2 * vest, 64); if (bw > 4096) bw = 4096;
-  const u32 post = pow2_ge(vest + vest / 2 + 2, 64) + bw + 2 * vest + (em ? 0 : pow2_ge(vest, 1)) + 512;
+  const u32 post = pow2_ge(vest + vest / 2 + 2, 64) + bw + 2 * vest + (em ? 0 : pow2_ge(vest, 1)) + PS_COVER_WARPS * PS_WSCR_WORDS;
   u32 w = P + (n + 2) / 2 + (gene ? (n + 1) / 2 : 0) + rec + 3 * vest + (post > rec ? post - rec : 0);
   if (em) {
     w += 2 * vest + P / 2 + 64;
@@ -423,10 +425,17 @@ __device__ inline void ps_cover_group(const PsCell& c, const PsSink& sk, u32* wi
   }
 }
 
-// one warp per component; wmem / wam: 32 words each of per-warp shared scratch. Every lane calls.
+// one warp per component (lane i = start vertex i). Per-warp shared scratch: wmem[32] members in
+// canonical order, wam[32] out-neighbour masks, Mw[16 x 16] label-position masks. Every lane calls.
+// Components of <= 16 vertices whose labels hold <= 32 transcripts (nearly all) use the MASK form:
+// Mw[i][j] = positions of i's label present in j's label, built once by the whole warp (one merge
+// per pair); edges, every BFS and the label intersection are then bit operations on shared-memory
+// words. The BFS form with per-candidate label searches handles the rest (ncu r1z, C5: the BFS form
+// on 9-16 vertex components with 18-transcript labels kept 28 % of the stall samples at the barrier).
 __device__ inline void ps_cover_warp(const PsCell& c, const PsSink& sk, u32* winners, const u32* head, const u32* nxt, u32 r, bool exact,
                                      u32* gbm, u32* wmem, u32* wam) {
   const u32 lane = lane_id();
+  u32* Mw = wam + 32;
   u32 s = 0;
   if (lane == 0) for (u32 x = head[r]; x != PS_EMPTY; x = nxt[x]) wam[s++] = x;     // unordered members
   s = __shfl_sync(0xFFFFFFFFu, s, 0);
@@ -439,7 +448,45 @@ __device__ inline void ps_cover_warp(const PsCell& c, const PsSink& sk, u32* win
   __syncwarp();
   if (lane < s) wmem[rank] = x;
   __syncwarp();
-  const u32 my_am = lane < s ? ps_out_mask(c, wmem, s, lane, exact) : 0u;
+  u32 ci = 0, ln = 0;
+  const u32* li = nullptr;
+  if (lane < s) { ci = c.vcls(wmem[lane]); li = c.lab(ci); ln = c.len(ci); }
+  const bool masked = s <= 16 && !__any_sync(0xFFFFFFFFu, lane < s && ln > 32);
+  if (masked) {
+    for (u32 p = lane; p < s * s; p += 32) {      // all (i, j) pairs across the warp
+      const u32 i = p / s, j = p - i * s;
+      const u32 cI = c.vcls(wmem[i]), cJ = c.vcls(wmem[j]);
+      const u32 lnI = c.len(cI);
+      u32 m = 0;
+      if (i == j || cI == cJ) m = lnI >= 32 ? 0xFFFFFFFFu : ((1u << lnI) - 1u);
+      else {
+        const u32* lI = c.lab(cI);
+        const u32* lJ = c.lab(cJ);
+        const u32 lnJ = c.len(cJ);
+        for (u32 qa = 0, qb = 0; qa < lnI && qb < lnJ;) {
+          const u32 a_ = lI[qa], b_ = lJ[qb];
+          if (a_ == b_) { m |= 1u << qa; ++qa; ++qb; }
+          else if (a_ < b_) ++qa;
+          else ++qb;
+        }
+      }
+      Mw[i * 16 + j] = m;
+    }
+    __syncwarp();
+  }
+  u32 my_am = 0;
+  if (lane < s) {
+    if (!masked) my_am = ps_out_mask(c, wmem, s, lane, exact);
+    else {
+      const u32 ui = c.vumi[wmem[lane]], ni = c.vcnt(wmem[lane]);
+      for (u32 j = 0; j < s; ++j) {
+        if (j == lane) continue;
+        const u32 xx = ui ^ c.vumi[wmem[j]];
+        const u32 hd = (u32)__popc((xx | (xx >> 1)) & 0x55555555u);
+        if ((exact ? hd == 0 : hd <= 1) && Mw[lane * 16 + j] != 0 && out_edge(hd, ni, c.vcnt(wmem[j]))) my_am |= 1u << j;
+      }
+    }
+  }
   wam[lane] = my_am;
   __syncwarp();
   u32 unc = s == 32 ? 0xFFFFFFFFu : ((1u << s) - 1);
@@ -447,11 +494,23 @@ __device__ inline void ps_cover_warp(const PsCell& c, const PsSink& sk, u32* win
     const u32 remaining = (u32)__popc(unc);
     u32 my_size = 0, my_mask = 0;
     if (lane < s && (unc >> lane & 1)) {
-      const u32 ci = c.vcls(wmem[lane]);
-      const u32* li = c.lab(ci);
-      const u32 ln = c.len(ci);
       for (u32 k = 0; k < ln; ++k) {
-        const u32 got = ps_bfs(c, wmem, wam, unc, lane, ci, li[k]);
+        u32 got;
+        if (!masked) got = ps_bfs(c, wmem, wam, unc, lane, ci, li[k]);
+        else {
+          u32 ck = 0;                               // vertices whose label holds my transcript k
+          for (u32 j = 0; j < s; ++j) ck |= ((Mw[lane * 16 + j] >> k) & 1u) << j;
+          const u32 ok = ck & unc;
+          u32 fr = 1u << lane;
+          got = fr;
+          while (fr) {
+            u32 nx = 0;
+            for (u32 f = fr; f; f &= f - 1) nx |= wam[(u32)__ffs((int)f) - 1];
+            nx &= ok & ~got;
+            got |= nx;
+            fr = nx;
+          }
+        }
         const u32 sz = (u32)__popc(got);
         if (sz > my_size) { my_size = sz; my_mask = got; }
         if (my_size == remaining) break;
@@ -468,7 +527,20 @@ __device__ inline void ps_cover_warp(const PsCell& c, const PsSink& sk, u32* win
       winner = (u32)__ffs((int)cand) - 1;                                           // earliest start vertex with the largest MCC
       mask = __shfl_sync(0xFFFFFFFFu, my_mask, (int)winner);
     }
-    if (lane == winner) ps_emit_mcc(c, sk, winners, gbm, wmem, mask);
+    if (lane == winner) {
+      if (!masked) ps_emit_mcc(c, sk, winners, gbm, wmem, mask);
+      else {
+        u32 inter = 0xFFFFFFFFu;
+        for (u32 mm = mask; mm; mm &= mm - 1) inter &= Mw[lane * 16 + (u32)__ffs((int)mm) - 1];
+        const u32 gv = c.vgene[wmem[lane]];
+        const u32 slot = (gv < PS_MULTI_GENE && inter != 0) ? ps_emit_genes(sk, &gv, 1u)
+                                                            : ps_emit(c, sk, li, ln, [&](u32 q, u32) { return ((inter >> q) & 1u) != 0; });
+        if (sk.mode != 2 && slot != NONE32) {
+          winners[atomicAdd(&sk.ex->n_win, 1u)] = slot;
+          if (gbm) atomicOr(&gbm[slot >> 5], 1u << (slot & 31));
+        }
+      }
+    }
     unc &= ~mask;
     __syncwarp();
   }
@@ -497,6 +569,23 @@ __device__ inline bool ps_back_carve(u32* A, u32 lo, u32 hi, u32 M, u32 Lm, u32 
   o->alpha_in = (float*)take(4ull * Sr); o->alpha_out = (float*)take(4ull * Sr); o->cls_inv = (float*)take(4ull * (M + 1));
   o->sib_a = (u32*)take(4ull * Sr); o->sib_b = (u32*)take(4ull * Sr);
   return align8(off) <= (u64)hi * 4;
+}
+
+// L2 prefetch of a cell's record arrays (one 128-byte line per thread and step)
+__device__ __forceinline__ void ps_prefetch_lines(const void* lo, const void* hi) {
+#ifndef AFQ_EMU
+  const char* p = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(lo) & ~uintptr_t(127)) + (size_t)threadIdx.x * 128;
+  for (; p < reinterpret_cast<const char*>(hi); p += (size_t)blockDim.x * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)lo; (void)hi;
+#endif
+}
+__device__ __forceinline__ void ps_prefetch_cell(const KArgs& a, u32 cell) {
+  const u64 r0 = a.cell_rec_off[cell], r1 = a.cell_rec_off[cell + 1];
+  const u32 f0 = a.ref_off[r0], f1 = a.ref_off[r1];
+  ps_prefetch_lines(a.refs + f0, a.refs + f1);
+  ps_prefetch_lines(a.umi + r0, a.umi + r1);
+  ps_prefetch_lines(a.ref_off + r0, a.ref_off + r1 + 1);
 }
 
 // =============================================================================================
@@ -652,7 +741,7 @@ __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A
   u32* parent = alloc(V);                             // later: component sizes
   u32* winners = em ? A : alloc(next_pow2(V ? V : 1));
   u32* nxt = BW >= V ? bloom : alloc(V);              // component member lists (the bitmap is dead by then)
-  u32* wscr = alloc((T >> 5) * 64);                   // per-warp scratch of the warp-cooperative cover
+  u32* wscr = alloc(PS_COVER_WARPS * PS_WSCR_WORDS);  // per-warp scratch of the warp-cooperative cover
   u32* olist = alloc(V / 2 + 2);                      // components re-routed from the group cover to the warp cover
   if (!fits) return false;                            // uniform (V is block-wide)
   const u32 Wg = (a.num_rows + 31) >> 5;
@@ -842,14 +931,16 @@ __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A
     ps_cover_group<2>(c, sk, winners, gbm, head, nxt, clist, 0, K2, g.pug_exact_umi != 0, olist, &ex->n_over);
     ps_cover_group<4>(c, sk, winners, gbm, head, nxt, clist, K2, K4, g.pug_exact_umi != 0, olist, &ex->n_over);
     ps_cover_group<8>(c, sk, winners, gbm, head, nxt, clist, K4, K8, g.pug_exact_umi != 0, olist, &ex->n_over);
-    const u32 wid = tid >> 5, nw = T >> 5;
-    u32* wmem = wscr + wid * 64;
-    for (u32 k = K - 1 - wid; (int)k >= (int)K8; k -= nw)        // largest components first
-      ps_cover_warp(c, sk, winners, head, nxt, clist[k], g.pug_exact_umi != 0, gbm, wmem, wmem + 32);
+    const u32 wid = tid >> 5, nw = PS_COVER_WARPS;
+    u32* wmem = wscr + (wid < nw ? wid : 0u) * PS_WSCR_WORDS;
+    if (wid < nw)
+      for (u32 k = K - 1 - wid; (int)k >= (int)K8; k -= nw)      // largest components first
+        ps_cover_warp(c, sk, winners, head, nxt, clist[k], g.pug_exact_umi != 0, gbm, wmem, wmem + 32);
     __syncthreads();
     const u32 KO = ex->n_over;                                   // small components with a long label
-    for (u32 k = wid; k < KO; k += nw)
-      ps_cover_warp(c, sk, winners, head, nxt, olist[k], g.pug_exact_umi != 0, gbm, wmem, wmem + 32);
+    if (wid < nw)
+      for (u32 k = wid; k < KO; k += nw)
+        ps_cover_warp(c, sk, winners, head, nxt, olist[k], g.pug_exact_umi != 0, gbm, wmem, wmem + 32);
   }
   }
   __syncthreads();
@@ -971,12 +1062,18 @@ __global__ void __launch_bounds__(ps_threads(VAR), ps_min_blocks(VAR)) k_pug_sme
   __shared__ GePtrs s_ptrs;
   const u32 count = a.ctl->bin_count[PS_LIST0 + VAR];
   const u32* list = a.bin_list + (u64)(PS_LIST0 + VAR) * a.n_cells;
-  for (;;) {
+  // jobs are claimed one ahead so that the NEXT cell's records can be prefetched into L2 while this
+  // one is resolved (ncu r1y: 7 % of the stall samples sat on the three load loops, DRAM latency)
+  if (threadIdx.x == 0) sh.job = atomicAdd(&a.ctl->bin_cursor[PS_LIST0 + VAR], 1u);
+  __syncthreads();
+  u32 job = sh.job;
+  __syncthreads();
+  while (job < count) {
     if (threadIdx.x == 0) sh.job = atomicAdd(&a.ctl->bin_cursor[PS_LIST0 + VAR], 1u);
     __syncthreads();
-    const u32 job = sh.job;
+    const u32 next = sh.job;
     __syncthreads();
-    if (job >= count) break;
+    if (next < count) ps_prefetch_cell(a, list[next]);
     const u32 cell = list[job];
     const u32 AW = (g.ps_limit_words && g.ps_limit_words < AWmax) ? g.ps_limit_words : AWmax;
     const bool ok = ps_cell<(VAR >= PS_SMEM_VARIANTS)>(a, g, cell, A, AW, &sh, &ex, &s_ptrs);
@@ -985,6 +1082,7 @@ __global__ void __launch_bounds__(ps_threads(VAR), ps_min_blocks(VAR)) k_pug_sme
       a.bin_list[(u64)GE_LIST_NORMAL * a.n_cells + idx] = cell;
     }
     __syncthreads();
+    job = next;
   }
 }
 
