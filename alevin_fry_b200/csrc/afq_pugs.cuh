@@ -36,10 +36,15 @@ constexpr int PS_VARIANTS = 4;       // arenas: 72 KB x 3 CTAs/SM, 108 KB x 2, 2
                                      // code on a per-CTA GLOBAL-memory arena (L2-resident) for cells beyond 224 KB
 constexpr int PS_SMEM_VARIANTS = 3;
 __host__ __device__ constexpr u32 ps_threads(int v) { return v == 0 ? 256u : (v == 1 ? 512u : (v == 2 ? 1024u : 512u)); }
-__host__ __device__ constexpr u32 ps_arena_words(int v) { return v == 0 ? 18u * 1024u : (v == 1 ? 27u * 1024u : 56u * 1024u); }
-__host__ __device__ constexpr u32 ps_min_blocks(int v) { return v == 0 ? 3u : (v == 1 ? 2u : (v == 2 ? 1u : 2u)); }
+#ifndef AFQ_PS_V0_KWORDS
+#define AFQ_PS_V0_KWORDS 18
+#define AFQ_PS_V0_BLOCKS 3
+#endif
+__host__ __device__ constexpr u32 ps_arena_words(int v) { return v == 0 ? AFQ_PS_V0_KWORDS * 1024u : (v == 1 ? 27u * 1024u : 56u * 1024u); }
+__host__ __device__ constexpr u32 ps_min_blocks(int v) { return v == 0 ? (u32)AFQ_PS_V0_BLOCKS : (v == 1 ? 2u : (v == 2 ? 1u : 2u)); }
 constexpr u32 PS_WSCR_WORDS = 64 + 256; // per-warp scratch of the warp-cooperative cover (members, masks, 16 x 16 label masks)
-constexpr u32 PS_COVER_WARPS = 4;       // warps of a CTA that run the warp form (bounds its shared scratch: 5 KB)
+constexpr u32 PS_COVER_WARPS = 4;       // warps of a 256-thread CTA that run the warp form (bounds its shared scratch: 5 KB);
+                                        // 8 in the larger CTAs
 constexpr u32 PS_EMPTY = 0xFFFFFFFFu;
 constexpr u32 PS_MULTI_GENE = 0xFFFFFFFEu;
 constexpr u32 PS_MAX_RECORDS = 65535;   // record indices and read counts share a 32-bit table entry (16 bits each)
@@ -635,9 +640,12 @@ __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A
       u32* dst = refs + c.off(i);
       const u32 ln = c.off(i + 1) - c.off(i);
       for (u32 k = 0; k < ln; ++k) dst[k] = __ldg(a.t2g + dst[k]);
-      rlen[i] = (u16)sort_dedup_small(dst, ln);
+      const u32 gl = sort_dedup_small(dst, ln);
+      if (gl > 0xFFFFu) ex->fail = 1;               // (16-bit label lengths; only reachable in variant 3)
+      rlen[i] = (u16)gl;
     }
     __syncthreads();
+    if (ex->fail) { __syncthreads(); return false; }
   }
   // ---- phase 1: record -> eq-class (representative record) ----------------------------------------
   GE_FOR(i, n) {
@@ -741,7 +749,8 @@ __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A
   u32* parent = alloc(V);                             // later: component sizes
   u32* winners = em ? A : alloc(next_pow2(V ? V : 1));
   u32* nxt = BW >= V ? bloom : alloc(V);              // component member lists (the bitmap is dead by then)
-  u32* wscr = alloc(PS_COVER_WARPS * PS_WSCR_WORDS);  // per-warp scratch of the warp-cooperative cover
+  const u32 ncw = T >= 512 ? 2 * PS_COVER_WARPS : PS_COVER_WARPS;
+  u32* wscr = alloc(ncw * PS_WSCR_WORDS);             // per-warp scratch of the warp-cooperative cover
   u32* olist = alloc(V / 2 + 2);                      // components re-routed from the group cover to the warp cover
   if (!fits) return false;                            // uniform (V is block-wide)
   const u32 Wg = (a.num_rows + 31) >> 5;
@@ -931,7 +940,7 @@ __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A
     ps_cover_group<2>(c, sk, winners, gbm, head, nxt, clist, 0, K2, g.pug_exact_umi != 0, olist, &ex->n_over);
     ps_cover_group<4>(c, sk, winners, gbm, head, nxt, clist, K2, K4, g.pug_exact_umi != 0, olist, &ex->n_over);
     ps_cover_group<8>(c, sk, winners, gbm, head, nxt, clist, K4, K8, g.pug_exact_umi != 0, olist, &ex->n_over);
-    const u32 wid = tid >> 5, nw = PS_COVER_WARPS;
+    const u32 wid = tid >> 5, nw = ncw;
     u32* wmem = wscr + (wid < nw ? wid : 0u) * PS_WSCR_WORDS;
     if (wid < nw)
       for (u32 k = K - 1 - wid; (int)k >= (int)K8; k -= nw)      // largest components first
