@@ -1,6 +1,8 @@
 #!/bin/bash
-# A/B: k_pug_smem<0> with a 56 KB arena x 4 CTAs/SM (64 registers) vs 72 KB x 3 (80 registers)
+# GPU tier incl. golden vectors; A/B: k_pug_smem<0> with a 56 KB arena x 4 CTAs/SM (64 registers) vs 72 KB x 3 (80 registers)
 mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1
+tail -3 gpurun_out/pytest_gpu.log
 show() { python -c "
 import json,sys
 j=json.loads(open('$1').read().strip().splitlines()[-1]); pk=j['roofline']['per_kernel_ms']
