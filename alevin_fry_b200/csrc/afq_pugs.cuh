@@ -749,8 +749,11 @@ __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A
   u32* parent = alloc(V);                             // later: component sizes
   u32* winners = em ? A : alloc(next_pow2(V ? V : 1));
   u32* nxt = BW >= V ? bloom : alloc(V);              // component member lists (the bitmap is dead by then)
-  const u32 ncw = T >= 512 ? 2 * PS_COVER_WARPS : PS_COVER_WARPS;
-  u32* wscr = alloc(ncw * PS_WSCR_WORDS);             // per-warp scratch of the warp-cooperative cover
+  // per-warp scratch of the warp-cooperative cover: 8 warps in the larger CTAs when that still fits
+  u32 ncw = PS_COVER_WARPS;
+  if (T >= 512 && (segA + 2 * PS_COVER_WARPS * PS_WSCR_WORDS <= off_dense || segB + 2 * PS_COVER_WARPS * PS_WSCR_WORDS + V + V / 2 + 2 * ((a.num_rows + 31) >> 5) + 64 <= topB))
+    ncw = 2 * PS_COVER_WARPS;
+  u32* wscr = alloc(ncw * PS_WSCR_WORDS);
   u32* olist = alloc(V / 2 + 2);                      // components re-routed from the group cover to the warp cover
   if (!fits) return false;                            // uniform (V is block-wide)
   const u32 Wg = (a.num_rows + 31) >> 5;
