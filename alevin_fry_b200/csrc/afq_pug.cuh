@@ -1297,70 +1297,93 @@ __device__ inline void ge_back(const KArgs& a, const GeArgs& g, u32 cell, GeCell
     __syncthreads();
     if (needs_em) {
       const float uni = __fdiv_rn(1.0f, (float)g.num_alphas);
-      float* ain = p.alpha_in;     // ping-pong: the M step writes aout, then the two swap (no copy pass, one barrier less)
-      float* aout = p.alpha_out;
-      GE_FOR(s, S)
-        ain[s] = g.em_init_uniform ? uni : __fmul_rn(__fadd_rn(ain[s], 0.5f), 1e-3f);
-      __syncthreads();
-      auto abund = [&](u32 s) {
-        if (!usa) return ain[s];
-        const u32 sa = p.sib_a[s], sb = p.sib_b[s];
-        if (sb != NONE32 || p.sup[s] >= a.ao) {  // ambiguous: U + S + A
-          const float xu = sa != NONE32 ? ain[sa] : 0.0f, xs = sb != NONE32 ? ain[sb] : 0.0f;
-          return __fadd_rn(__fadd_rn(xu, xs), ain[s]);
+      // The EM iterations, written over (me, stride, sync) so that a SMALL problem (<= 96 support indices
+      // and classes: a high-duplication cell has ~50 molecules) runs on ONE warp with __syncwarp() between
+      // the steps instead of two block barriers per iteration (ncu r1zd, C5: 16 warps stalled at a barrier
+      // per issuing warp). Same operations in the same order either way.
+      auto em_loop = [&](const u32 me, const u32 stride, auto sync) {
+        float* ain = p.alpha_in;     // ping-pong: the M step writes aout, then the two swap (no copy pass)
+        float* aout = p.alpha_out;
+        for (u32 b = 0; b < S; b += stride) {
+          const u32 s_ = b + me;
+          if (s_ < S) ain[s_] = g.em_init_uniform ? uni : __fmul_rn(__fadd_rn(ain[s_], 0.5f), 1e-3f);
         }
-        const float xa = sa != NONE32 ? ain[sa] : 0.0f;   // U or S: A + self
-        return __fadd_rn(xa, ain[s]);
+        if (me == 0) { sh->flag = 0; sh->cnt1 = 0; }
+        sync();
+        auto abund = [&](u32 s_) {
+          if (!usa) return ain[s_];
+          const u32 sa = p.sib_a[s_], sb = p.sib_b[s_];
+          if (sb != NONE32 || p.sup[s_] >= a.ao) {  // ambiguous: U + S + A
+            const float xu = sa != NONE32 ? ain[sa] : 0.0f, xs = sb != NONE32 ? ain[sb] : 0.0f;
+            return __fadd_rn(__fadd_rn(xu, xs), ain[s_]);
+          }
+          const float xa = sa != NONE32 ? ain[sa] : 0.0f;   // U or S: A + self
+          return __fadd_rn(xa, ain[s_]);
+        };
+        u32 it = 0;
+        bool last_round = false;
+        for (;;) {
+          // E step, per class: inv = count / sum of abundances (label order)
+          for (u32 b = 0; b < G; b += stride) {
+            const u32 j = b + me;
+            if (j < G) {
+              const u32 e0 = p.gcls_eoff[j], e1 = p.gcls_eoff[j + 1];
+              if (e1 - e0 > 1) {     // (singleton classes keep their constant)
+                float inv = -1.0f;   // class contributes nothing
+                float den = 0.0f;
+                for (u32 e = e0; e < e1; ++e) den = __fadd_rn(den, abund(p.ent_loc[e]));
+                if (den > 0.0f) inv = __fdiv_rn((float)p.gcls_cnt[j], den);
+                p.cls_inv[j] = inv;
+              }
+            }
+            __syncwarp();
+          }
+          sync();
+          // "some index moved" flags alternate between two words: the word of iteration it+1 is cleared
+          // here, behind a barrier every thread reached after it last read that word (iteration it-1)
+          u32* moved = (it & 1u) ? &sh->cnt1 : &sh->flag;
+          if (me == 0) *((it & 1u) ? &sh->flag : &sh->cnt1) = 0;
+          // M step, per support index, contributions added in class order
+          for (u32 b = 0; b < S; b += stride) {
+            const u32 s_ = b + me;
+            if (s_ < S) {
+              float out = 0.0f;
+              const float ab = abund(s_);
+              for (u32 q = p.g_off[s_]; q < p.g_off[s_ + 1]; ++q) {
+                const float w = p.cls_inv[(u32)p.tkey[q]];
+                if (w >= 0.0f) out = __fadd_rn(out, __fmul_rn(ab, w));
+                else if (w < -2.0f) out = __fadd_rn(out, -w - 2.0f);
+              }
+              aout[s_] = out;
+              if (out > 1e-2f && fabsf(__fsub_rn(ain[s_], out)) > 1e-2f) *moved = 1;
+            }
+            __syncwarp();
+          }
+          sync();
+          const bool converged = *(volatile u32*)moved == 0;
+          { float* t = ain; ain = aout; aout = t; }
+          ++it;
+          if (!usa) {  // M1: src/em.rs:538-565
+            if (!(it < 2 || (it < 100 && !converged))) break;
+          } else {     // M2: src/em.rs:391-443 (clamp, then one last round)
+            if (last_round) break;
+            if (it >= 2 && converged) {
+              for (u32 b = 0; b < S; b += stride) { const u32 s_ = b + me; if (s_ < S && ain[s_] < 0.01f) ain[s_] = 0.0f; }
+              last_round = true;
+              sync();
+            } else if (!(it < 2 || (it < 100 && !converged))) break;
+          }
+        }
+        for (u32 b = 0; b < S; b += stride) {
+          const u32 s_ = b + me;
+          if (s_ < S) { const float x = ain[s_]; p.alpha_in[s_] = x < 0.01f ? 0.0f : x; }
+        }
       };
-      u32 it = 0;
-      bool last_round = false;
-      if (tid == 0) { sh->flag = 0; sh->cnt1 = 0; }
-      __syncthreads();
-      for (;;) {
-        // E step, per class: inv = count / sum of abundances (label order)
-        GE_FOR(j, G) {
-          const u32 e0 = p.gcls_eoff[j], e1 = p.gcls_eoff[j + 1];
-          if (e1 - e0 > 1) {     // (singleton classes keep their constant)
-            float inv = -1.0f;   // class contributes nothing
-            float den = 0.0f;
-            for (u32 e = e0; e < e1; ++e) den = __fadd_rn(den, abund(p.ent_loc[e]));
-            if (den > 0.0f) inv = __fdiv_rn((float)p.gcls_cnt[j], den);
-            p.cls_inv[j] = inv;
-          }
-        }
-        __syncthreads();
-        // "some index moved" flags alternate between two words: the word of iteration it+1 is cleared
-        // here, behind a barrier every thread reached after it last read that word (iteration it-1)
-        u32* moved = (it & 1u) ? &sh->cnt1 : &sh->flag;
-        if (tid == 0) *((it & 1u) ? &sh->flag : &sh->cnt1) = 0;
-        // M step, per support index, contributions added in class order
-        GE_FOR(s, S) {
-          float out = 0.0f;
-          const float ab = abund(s);
-          for (u32 q = p.g_off[s]; q < p.g_off[s + 1]; ++q) {
-            const float w = p.cls_inv[(u32)p.tkey[q]];
-            if (w >= 0.0f) out = __fadd_rn(out, __fmul_rn(ab, w));
-            else if (w < -2.0f) out = __fadd_rn(out, -w - 2.0f);
-          }
-          aout[s] = out;
-          if (out > 1e-2f && fabsf(__fsub_rn(ain[s], out)) > 1e-2f) *moved = 1;
-        }
-        __syncthreads();
-        const bool converged = *moved == 0;
-        { float* t = ain; ain = aout; aout = t; }
-        ++it;
-        if (!usa) {  // M1: src/em.rs:538-565
-          if (!(it < 2 || (it < 100 && !converged))) break;
-        } else {     // M2: src/em.rs:391-443 (clamp, then one last round)
-          if (last_round) break;
-          if (it >= 2 && converged) {
-            GE_FOR(s, S) if (ain[s] < 0.01f) ain[s] = 0.0f;
-            last_round = true;
-            __syncthreads();
-          } else if (!(it < 2 || (it < 100 && !converged))) break;
-        }
+      if (S <= 96 && G <= 96) {
+        if (tid < 32) em_loop(tid, 32u, [] { __syncwarp(); });
+      } else {
+        em_loop(tid, T, [] { __syncthreads(); });
       }
-      GE_FOR(s, S) { const float x = ain[s]; p.alpha_in[s] = x < 0.01f ? 0.0f : x; }
       __syncthreads();
     }
     // emit positive alphas, ascending index
