@@ -32,6 +32,11 @@ def lib():
         l = C.CDLL(HOST_LIB_PATH)
         l.afqh_quantify.restype = C.c_int
         l.afqh_quantify.argtypes = [C.POINTER(_Opts), C.c_char_p, C.c_size_t]
+        l.afqh_snappy_framed_decompress.restype = C.c_int
+        l.afqh_snappy_framed_decompress.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_uint32,
+                                                    C.c_char_p, C.c_size_t]
+        l.afqh_free.restype = None
+        l.afqh_free.argtypes = [C.c_void_p]
         l.afqh_write_collated_rad.restype = C.c_int
         l.afqh_write_collated_rad.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                               C.c_void_p, C.POINTER(C.c_char_p), C.c_uint64, C.c_uint16, C.c_uint16,
@@ -105,3 +110,17 @@ def load_quant_dir(path):
     fd = [l.split("\t") for l in open(os.path.join(path, "featureDump.txt")).read().split("\n")[:-1]]
     meta = json.load(open(os.path.join(path, "quant.json")))
     return dict(rows=rows, cols=cols, header=header, dims=dims, triplets=trip, feature_dump=fd, meta=meta)
+
+
+def snappy_framed_decompress(data: bytes, n_threads: int = 2) -> bytes:
+    """decode a Snappy framing-format stream (map.collated.rad.sz) with the host library's decoder"""
+    out = C.c_void_p()
+    n = C.c_size_t()
+    err = C.create_string_buffer(512)
+    rc = lib().afqh_snappy_framed_decompress(data, len(data), C.byref(out), C.byref(n), n_threads, err, 512)
+    if rc != 0:
+        raise RuntimeError("snappy: " + err.value.decode())
+    try:
+        return C.string_at(out.value, n.value)
+    finally:
+        lib().afqh_free(out)

@@ -452,12 +452,30 @@ int quantify_impl(const afqh_quant_opts& o) {
   REQUIRE(file_exists(in + "/collate.json"), "could not open the collate.json file.");
   bool compressed = false;
   REQUIRE(json_bool(slurp(in + "/collate.json"), "compressed_output", compressed), "could not read compressed_output field from collate metadata.");
-  REQUIRE(!compressed, "snappy-compressed collated RAD (map.collated.rad.sz) is not supported yet: re-run collate without --compress");
-  const std::string rad_path = in + "/map.collated.rad";
-  FILE* f = fopen(rad_path.c_str(), "rb");
-  REQUIRE(f, "run collate before quant (could not open " + rad_path + ")");
+  // src/quant.rs:373-395: map.collated.rad, or the snappy-framed map.collated.rad.sz of `collate --compress`
+  const std::string rad_path = in + (compressed ? "/map.collated.rad.sz" : "/map.collated.rad");
+  std::vector<unsigned char> zimage;   // the decompressed RAD image (compressed input only)
   std::vector<char> iobuf(8 << 20);
-  setvbuf(f, iobuf.data(), _IOFBF, iobuf.size());
+  FILE* f = nullptr;
+  if (compressed) {
+    const int zfd = open(rad_path.c_str(), O_RDONLY);
+    struct stat zst {};
+    REQUIRE(zfd >= 0 && fstat(zfd, &zst) == 0, "run collate before quant (could not open " + rad_path + ")");
+    const size_t zsize = (size_t)zst.st_size;
+    const unsigned char* zmap = zsize ? (const unsigned char*)mmap(nullptr, zsize, PROT_READ, MAP_PRIVATE, zfd, 0) : nullptr;
+    close(zfd);
+    REQUIRE(!zsize || zmap != MAP_FAILED, "mmap failed for " + rad_path);
+    std::string zerr;
+    const bool zok = snappy_framed_decompress(zmap, zsize, zimage, std::max(1u, std::min(o.num_threads, 64u)), zerr);
+    if (zmap) munmap((void*)zmap, zsize);
+    REQUIRE(zok, rad_path + ": " + zerr);
+    f = fmemopen(zimage.data(), zimage.size() ? zimage.size() : 1, "rb");
+    REQUIRE(f, "fmemopen failed");
+  } else {
+    f = fopen(rad_path.c_str(), "rb");
+    REQUIRE(f, "run collate before quant (could not open " + rad_path + ")");
+    setvbuf(f, iobuf.data(), _IOFBF, iobuf.size());
+  }
   Reader rd(f);
   RadPrelude pre;
   // the CUDA context comes up (~0.3-0.5 s) in the background while the prelude and the t2g map are parsed
@@ -545,14 +563,20 @@ int quantify_impl(const afqh_quant_opts& o) {
   // position of every chunk is known before any record is parsed
   const uint64_t body_start = rd.pos();
   fclose(f);
-  const int fd = open(rad_path.c_str(), O_RDONLY);
-  struct stat st {};
-  if (fd < 0 || fstat(fd, &st) != 0) { if (fd >= 0) close(fd); afq_destroy(ctx); fclose(outs.rows); fclose(outs.feat); throw Fail{"couldn't open " + rad_path}; }
-  const uint64_t fsize = (uint64_t)st.st_size;
-  const unsigned char* fmap = fsize ? (const unsigned char*)mmap(nullptr, fsize, PROT_READ, MAP_PRIVATE, fd, 0) : nullptr;
-  close(fd);
-  if (fsize && fmap == MAP_FAILED) { afq_destroy(ctx); fclose(outs.rows); fclose(outs.feat); throw Fail{"mmap failed for " + rad_path}; }
-  madvise((void*)fmap, fsize, MADV_SEQUENTIAL);
+  uint64_t fsize = 0;
+  const unsigned char* fmap = nullptr;
+  const bool mapped = !compressed;
+  if (compressed) { fmap = zimage.data(); fsize = zimage.size(); }
+  else {
+    const int fd = open(rad_path.c_str(), O_RDONLY);
+    struct stat st {};
+    if (fd < 0 || fstat(fd, &st) != 0) { if (fd >= 0) close(fd); afq_destroy(ctx); fclose(outs.rows); fclose(outs.feat); throw Fail{"couldn't open " + rad_path}; }
+    fsize = (uint64_t)st.st_size;
+    fmap = fsize ? (const unsigned char*)mmap(nullptr, fsize, PROT_READ, MAP_PRIVATE, fd, 0) : nullptr;
+    close(fd);
+    if (fsize && fmap == MAP_FAILED) { afq_destroy(ctx); fclose(outs.rows); fclose(outs.feat); throw Fail{"mmap failed for " + rad_path}; }
+    madvise((void*)fmap, fsize, MADV_SEQUENTIAL);
+  }
 
   // half of the threads parse the next batch while the other half format the previous result
   const unsigned n_threads = std::max(2u, std::min(o.num_threads < 2 ? 2u : o.num_threads, 128u));
@@ -675,13 +699,13 @@ int quantify_impl(const afqh_quant_opts& o) {
   if (failure.empty()) failure = consumer_failure;
   if (!failure.empty()) {
     afq_destroy(ctx);
-    if (fmap) munmap((void*)fmap, fsize);
+    if (fmap && mapped) munmap((void*)fmap, fsize);
     fclose(outs.rows); fclose(outs.feat);
     throw Fail{failure};
   }
   const auto t_td0 = clk::now();
   afq_destroy(ctx);
-  if (fmap) munmap((void*)fmap, fsize);
+  if (fmap && mapped) munmap((void*)fmap, fsize);
   fclose(outs.rows);
   fclose(outs.feat);
   const auto t_loop_end = clk::now();
@@ -850,5 +874,22 @@ int afqh_write_collated_rad(const char* dir, uint64_t n_cells, const uint64_t* c
   fputs("{\n  \"velo_mode\": false,\n  \"max-ambig-record\": 8\n}\n", j); fclose(j);
   return 0;
 }
+
+int afqh_snappy_framed_decompress(const uint8_t* src, size_t n, uint8_t** out, size_t* out_len, uint32_t n_threads,
+                                  char* err, size_t errlen) {
+  std::vector<unsigned char> buf;
+  std::string e;
+  if (!out || !out_len || !snappy_framed_decompress(src, n, buf, n_threads ? n_threads : 1, e)) {
+    if (err && errlen) { strncpy(err, e.empty() ? "null argument" : e.c_str(), errlen - 1); err[errlen - 1] = 0; }
+    return 1;
+  }
+  *out = (uint8_t*)malloc(buf.size() ? buf.size() : 1);
+  if (!*out) return 1;
+  memcpy(*out, buf.data(), buf.size());
+  *out_len = buf.size();
+  return 0;
+}
+
+void afqh_free(void* p) { free(p); }
 
 }  // extern "C"

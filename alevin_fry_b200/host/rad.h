@@ -69,4 +69,9 @@ struct RecordLayout {
 };
 bool make_layout(const RadPrelude& p, RecordLayout& l, std::string& err);
 
+// Snappy framing format (map.collated.rad.sz, `collate --compress`; reference reads it with
+// snap::read::FrameDecoder, src/quant.rs:373-395) -> the plain RAD image. Frames decode in parallel.
+bool snappy_framed_decompress(const unsigned char* src, size_t n, std::vector<unsigned char>& out, unsigned n_threads,
+                              std::string& err);
+
 }  // namespace afqh

@@ -1,7 +1,7 @@
 /* afq_host.h — host-side drop-in for `alevin_fry::quant::quantify(QuantOpts)`
  * (reference src/quant.rs:359, src/prog_opts.rs:24-43) and the `alevin-fry quant` CLI
  * (src/main.rs:294-348, 633-821): reads <input-dir>/{generate_permit_list.json,
- * collate.json, map.collated.rad}, the t2g TSV, and writes <output-dir>/{alevin/quants_mat.mtx,
+ * collate.json, map.collated.rad | map.collated.rad.sz}, the t2g TSV, and writes <output-dir>/{alevin/quants_mat.mtx,
  * alevin/quants_mat_rows.txt, alevin/quants_mat_cols.txt, featureDump.txt, quant.json}
  * (src/quant.rs:1588-1613, 1786-1847, 1913-1933). All per-cell compute goes through the
  * CUDA C-ABI of afq.h (afq_submit / afq_wait); there is no CPU compute path here.
@@ -45,6 +45,13 @@ int afqh_write_collated_rad(const char* dir, uint64_t n_cells, const uint64_t* c
                             const uint32_t* rec_ref_offsets, const uint32_t* refs,
                             const char* const* ref_names, uint64_t n_refs, uint16_t bc_len,
                             uint16_t umi_len, char* err, size_t errlen);
+
+/* Snappy FRAMING format (map.collated.rad.sz of `collate --compress`; the reference reads it with
+ * snap::read::FrameDecoder, src/quant.rs:373-395) -> plain bytes. *out is malloc'ed (free with
+ * afqh_free). Returns 0 on success.                                                          */
+int afqh_snappy_framed_decompress(const uint8_t* src, size_t n, uint8_t** out, size_t* out_len, uint32_t n_threads,
+                                  char* err, size_t errlen);
+void afqh_free(void* p);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,12 @@
+#!/bin/bash
+mkdir -p gpurun_out
+show() { python -c "
+import json,sys
+j=json.loads(open('$1').read().strip().splitlines()[-1]); pk=j['roofline']['per_kernel_ms']
+print('$2 value',round(j['value']),'ms',round(j['ms_per_step'],2),'e2e',round(j['e2e']['value']),'frac',round(j['roofline']['frac'],4), {k:round(v,2) for k,v in pk.items() if v>0.05})"; }
+timeout 1200 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1
+tail -2 gpurun_out/pytest_gpu.log
+for cfg in C5 C4 C3; do
+timeout 1200 python bench.py --config $cfg --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_${cfg}_full.json 2> gpurun_out/bench_${cfg}_full.err
+show gpurun_out/bench_${cfg}_full.json "$cfg full"
+done

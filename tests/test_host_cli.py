@@ -132,3 +132,45 @@ def test_quant_subset_and_multi_batch(tmp_path):
     host.quantify(d, t2g_path, out3, "cr-like")                       # one batch
     for fn in ("alevin/quants_mat.mtx", "alevin/quants_mat_rows.txt", "featureDump.txt"):
         assert open(os.path.join(out2, fn), "rb").read() == open(os.path.join(out3, fn), "rb").read()
+
+
+# ---- snappy-framed input (map.collated.rad.sz, `collate --compress`; src/quant.rs:373-395) ----------
+def test_snappy_framed_decoder_roundtrip_and_errors():
+    import snappy_ref
+    rng = np.random.default_rng(7)
+    assert snappy_ref.crc32c(b"123456789") == 0xE3069283                      # CRC-32C check value
+    payloads = [b"", b"a", b"abcd" * 5000, bytes(rng.integers(0, 256, 70000, dtype=np.uint8)),
+                bytes(rng.integers(0, 4, 200000, dtype=np.uint8)),              # long matches, overlapping copies
+                b"".join(int(x).to_bytes(4, "little") for x in rng.integers(0, 50, 40000))]
+    for i, data in enumerate(payloads):
+        for kw in ({}, {"block": 4096, "store_every": 3, "padding": True}, {"force4": True, "block": 30000}):
+            z = snappy_ref.frame(data, **kw)
+            assert host.snappy_framed_decompress(z, n_threads=1 + i % 4) == data, (i, kw)
+    z = bytearray(snappy_ref.frame(b"hello world, hello world, hello world" * 100))
+    z[-1] ^= 0x40
+    with pytest.raises(RuntimeError):
+        host.snappy_framed_decompress(bytes(z))
+    good = snappy_ref.frame(b"x" * 1000)
+    for bad in (good[:-3], good[10:], b"\x02\x01\x00\x00z" + good):
+        with pytest.raises(RuntimeError):
+            host.snappy_framed_decompress(bad)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("res", ["cr-like", "parsimony"])
+def test_cli_reads_snappy_compressed_collated_rad(tmp_path, res):
+    import json
+    import shutil
+    import snappy_ref
+    spec = synth.SynthSpec(reads_mean=300.0, n_genes=500)
+    b, bcs, d, t2g = make_input(tmp_path, spec, 40)
+    host.quantify(d, t2g, str(tmp_path / "plain"), res)
+    dz = tmp_path / "inz"
+    shutil.copytree(d, dz)
+    raw = open(dz / "map.collated.rad", "rb").read()
+    os.remove(dz / "map.collated.rad")
+    open(dz / "map.collated.rad.sz", "wb").write(snappy_ref.frame(raw, store_every=5, padding=True))
+    json.dump({"compressed_output": True}, open(dz / "collate.json", "w"))
+    host.quantify(str(dz), t2g, str(tmp_path / "fromz"), res)
+    for f in ("alevin/quants_mat.mtx", "alevin/quants_mat_rows.txt", "alevin/quants_mat_cols.txt", "featureDump.txt"):
+        assert open(tmp_path / "plain" / f, "rb").read() == open(tmp_path / "fromz" / f, "rb").read(), f
