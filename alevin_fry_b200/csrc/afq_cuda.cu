@@ -184,14 +184,9 @@ struct ProfScope {
 template <int VAR>
 int setup_ps(afq_ctx* c) {
   const size_t smem = VAR < PS_SMEM_VARIANTS ? (size_t)ps_arena_words(VAR) * 4 : 0;
-  if (smem) {
-    CUDA_TRY(c, cudaFuncSetAttribute(k_pug_smem<VAR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_TRY(c, cudaFuncSetAttribute(k_pug_smem<VAR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  }
-  int occ = 0, occ_em = 0;
-  CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pug_smem<VAR, false>, (int)ps_threads(VAR), smem));
-  CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_em, k_pug_smem<VAR, true>, (int)ps_threads(VAR), smem));
-  if (occ_em < occ) occ = occ_em;
+  if (smem) CUDA_TRY(c, cudaFuncSetAttribute(k_pug_smem<VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pug_smem<VAR>, (int)ps_threads(VAR), smem));
   if (occ < 1) { c->err = "k_pug_smem variant does not fit an SM"; return AFQ_ERR_CUDA; }
   c->grid_ps[VAR] = occ * c->num_sms;
   return AFQ_OK;

@@ -179,19 +179,18 @@ int enqueue_batch(L& l, const afq_config& cfg, int force_bin, const PipeBufs& pb
       ps_cells += cnt;
       u32 blocks = (u32)l.ps_grid(v);
       if (blocks > cnt) blocks = cnt;
-      const bool em = g.only_unique == 0;
       if (v == 3) {
         const u64 words = ps_global_words(h.ge_max_n[1], h.ge_max_p[1], cfg.num_rows);
         g.ps_garena = l.ps_garena(words, blocks);
         g.ps_garena_words = (u32)words;
         if (!g.ps_garena) { err = "k_pug_smem global arena allocation failed"; return AFQ_ERR_CUDA; }
+        l.launch(KID_PUG_SMEM0 + 3, k_pug_smem<3>, blocks, ps_threads(3), (size_t)0, a, g);
+        continue;
       }
-      const size_t smem = v < PS_SMEM_VARIANTS ? (size_t)ps_arena_words(v) * 4 : 0;
-      const int kid = KID_PUG_SMEM0 + v;
-      if (v == 0) { if (em) l.launch(kid, k_pug_smem<0, true>, blocks, ps_threads(0), smem, a, g); else l.launch(kid, k_pug_smem<0, false>, blocks, ps_threads(0), smem, a, g); }
-      else if (v == 1) { if (em) l.launch(kid, k_pug_smem<1, true>, blocks, ps_threads(1), smem, a, g); else l.launch(kid, k_pug_smem<1, false>, blocks, ps_threads(1), smem, a, g); }
-      else if (v == 2) { if (em) l.launch(kid, k_pug_smem<2, true>, blocks, ps_threads(2), smem, a, g); else l.launch(kid, k_pug_smem<2, false>, blocks, ps_threads(2), smem, a, g); }
-      else { if (em) l.launch(kid, k_pug_smem<3, true>, blocks, ps_threads(3), smem, a, g); else l.launch(kid, k_pug_smem<3, false>, blocks, ps_threads(3), smem, a, g); }
+      const size_t smem = (size_t)ps_arena_words(v) * 4;
+      if (v == 0) l.launch(KID_PUG_SMEM0 + 0, k_pug_smem<0>, blocks, ps_threads(0), smem, a, g);
+      else if (v == 1) l.launch(KID_PUG_SMEM0 + 1, k_pug_smem<1>, blocks, ps_threads(1), smem, a, g);
+      else l.launch(KID_PUG_SMEM0 + 2, k_pug_smem<2>, blocks, ps_threads(2), smem, a, g);
     }
     for (int which = 0; which < 2; ++which) {
       const int list = which == 0 ? GE_LIST_BIG : GE_LIST_NORMAL;

@@ -143,9 +143,9 @@ struct PsSink {
 // One molecule whose transcript label is { t = l0[k], k in [0, n0) : keep(k, t) } (ascending). Returns the
 // output slot for the unique-only modes (NONE32: contributes nothing); mode 2 stores the sorted
 // gene label and returns NONE32.
-template <bool EM, class Keep>
-__device__ __noinline__ u32 ps_emit(const PsCell& c, const PsSink& sk, const u32* l0, u32 n0, Keep keep) {
-  if (!EM && sk.mode == 0) {
+template <class Keep>
+__device__ __forceinline__ u32 ps_emit(const PsCell& c, const PsSink& sk, const u32* l0, u32 n0, Keep keep) {
+  if (sk.mode == 0) {
     // em_optimize(only_unique), src/em.rs:499-514: only single-gene labels count
     u32 g0 = NONE32;
     for (u32 k = 0; k < n0; ++k) {
@@ -157,7 +157,7 @@ __device__ __noinline__ u32 ps_emit(const PsCell& c, const PsSink& sk, const u32
     }
     return g0;
   }
-  if (!EM) {
+  if (sk.mode == 1) {
     // utils::extract_counts, src/utils.rs:673-756: sorted-unique gene label of <= 10 ids -> S/U/A slot
     u32 best[11];
     u32 nb = 0;
@@ -217,12 +217,9 @@ __device__ __noinline__ u32 ps_emit(const PsCell& c, const PsSink& sk, const u32
 constexpr u32 PS_CRL_GENES = 24;     // cr-like-em: candidate genes of one UMI held by a thread
 
 // one molecule whose (ascending, distinct) gene label is given
-template <bool EM>
 __device__ __forceinline__ u32 ps_emit_genes(const PsSink& sk, const u32* genes, u32 nb) {
-  if (!EM) {
-    if (sk.mode == 0) return nb == 1 ? genes[0] : NONE32;
-    return nb <= 10 ? usa_slot_for_label(genes, nb, sk.uo, sk.ao) : NONE32;
-  }
+  if (sk.mode == 0) return nb == 1 ? genes[0] : NONE32;
+  if (sk.mode == 1) return nb <= 10 ? usa_slot_for_label(genes, nb, sk.uo, sk.ao) : NONE32;
   const u32 used = atomicAdd(&sk.sh->lab_bump, nb) + nb;
   if (used > sk.lab_hi - sk.lab_lo) { sk.ex->fail = 1; return NONE32; }
   const u32 off = sk.lab_hi - used;
@@ -288,12 +285,11 @@ __device__ __forceinline__ u32 ps_bfs(const PsCell& c, const u32* mem, const u32
   return got;
 }
 // molecule of one MCC: label = intersection of its class labels (src/pugutils.rs:1161-1188) -> genes
-template <bool EM>
 __device__ __forceinline__ void ps_emit_mcc(const PsCell& c, const PsSink& sk, u32* winners, u32* gbm, const u32* mem, u32 mask) {
   const u32 first = (u32)__ffs((int)mask) - 1;
   const u32 cf = c.vcls(mem[first]);
   const u32 rest = mask & (mask - 1);
-  const u32 slot = ps_emit<EM>(c, sk, c.lab(cf), c.len(cf), [&](u32, u32 t) {
+  const u32 slot = ps_emit(c, sk, c.lab(cf), c.len(cf), [&](u32, u32 t) {
     u32 r = rest;
     while (r) {
       const u32 j = (u32)__ffs((int)r) - 1;
@@ -303,7 +299,7 @@ __device__ __forceinline__ void ps_emit_mcc(const PsCell& c, const PsSink& sk, u
     }
     return true;
   });
-  if (!EM && slot != NONE32) {
+  if (sk.mode != 2 && slot != NONE32) {
     winners[atomicAdd(&sk.ex->n_win, 1u)] = slot;
     if (gbm) atomicOr(&gbm[slot >> 5], 1u << (slot & 31));
   }
@@ -315,7 +311,7 @@ __device__ __forceinline__ void ps_emit_mcc(const PsCell& c, const PsSink& sk, u
 // vertex j's label. Then the BFS of ALL my transcripts at once is a fixed number of branch-free
 // relaxations reach[j] |= reach[x] & M[j] over the out-edges x -> j, in registers.
 // Components with a label longer than 32 transcripts are appended to `olist` for the warp form.
-template <int G, bool EM>
+template <int G>
 __device__ inline void ps_cover_group(const PsCell& c, const PsSink& sk, u32* winners, u32* gbm, const u32* head, const u32* nxt,
                                       const u32* clist, u32 k0, u32 k1, bool exact, u32* olist, u32* n_over) {
   const u32 lane = lane_id(), sub = lane % G, gbase = lane - sub;
@@ -421,9 +417,9 @@ __device__ inline void ps_cover_group(const PsCell& c, const PsSink& sk, u32* wi
         for (int j = 0; j < G; ++j) if ((mask >> j) & 1u) inter &= M[j];
         (void)my_k;
         const u32 gv = c.vgene[v];
-        const u32 slot = (gv < PS_MULTI_GENE && inter != 0) ? ps_emit_genes<EM>(sk, &gv, 1u)
-                                                            : ps_emit<EM>(c, sk, li, ln, [&](u32 q, u32) { return ((inter >> q) & 1u) != 0; });
-        if (!EM && slot != NONE32) {
+        const u32 slot = (gv < PS_MULTI_GENE && inter != 0) ? ps_emit_genes(sk, &gv, 1u)
+                                                            : ps_emit(c, sk, li, ln, [&](u32 q, u32) { return ((inter >> q) & 1u) != 0; });
+        if (sk.mode != 2 && slot != NONE32) {
           winners[atomicAdd(&sk.ex->n_win, 1u)] = slot;
           if (gbm) atomicOr(&gbm[slot >> 5], 1u << (slot & 31));
         }
@@ -441,7 +437,6 @@ __device__ inline void ps_cover_group(const PsCell& c, const PsSink& sk, u32* wi
 // per pair); edges, every BFS and the label intersection are then bit operations on shared-memory
 // words. The BFS form with per-candidate label searches handles the rest (ncu r1z, C5: the BFS form
 // on 9-16 vertex components with 18-transcript labels kept 28 % of the stall samples at the barrier).
-template <bool EM>
 __device__ inline void ps_cover_warp(const PsCell& c, const PsSink& sk, u32* winners, const u32* head, const u32* nxt, u32 r, bool exact,
                                      u32* gbm, u32* wmem, u32* wam) {
   const u32 lane = lane_id();
@@ -538,14 +533,14 @@ __device__ inline void ps_cover_warp(const PsCell& c, const PsSink& sk, u32* win
       mask = __shfl_sync(0xFFFFFFFFu, my_mask, (int)winner);
     }
     if (lane == winner) {
-      if (!masked) ps_emit_mcc<EM>(c, sk, winners, gbm, wmem, mask);
+      if (!masked) ps_emit_mcc(c, sk, winners, gbm, wmem, mask);
       else {
         u32 inter = 0xFFFFFFFFu;
         for (u32 mm = mask; mm; mm &= mm - 1) inter &= Mw[lane * 16 + (u32)__ffs((int)mm) - 1];
         const u32 gv = c.vgene[wmem[lane]];
-        const u32 slot = (gv < PS_MULTI_GENE && inter != 0) ? ps_emit_genes<EM>(sk, &gv, 1u)
-                                                            : ps_emit<EM>(c, sk, li, ln, [&](u32 q, u32) { return ((inter >> q) & 1u) != 0; });
-        if (!EM && slot != NONE32) {
+        const u32 slot = (gv < PS_MULTI_GENE && inter != 0) ? ps_emit_genes(sk, &gv, 1u)
+                                                            : ps_emit(c, sk, li, ln, [&](u32 q, u32) { return ((inter >> q) & 1u) != 0; });
+        if (sk.mode != 2 && slot != NONE32) {
           winners[atomicAdd(&sk.ex->n_win, 1u)] = slot;
           if (gbm) atomicOr(&gbm[slot >> 5], 1u << (slot & 31));
         }
@@ -602,7 +597,7 @@ __device__ __forceinline__ void ps_prefetch_cell(const KArgs& a, u32 cell) {
 // One cell. Returns false when the cell has to be redone by the global-arena kernel (nothing has
 // been written for it in that case).
 // =============================================================================================
-template <bool WIDE, bool EM>
+template <bool WIDE>
 __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A, u32 AW, GeShared* sh, PsExtra* ex,
                                GePtrs* s_ptrs) {
   const u32 T = blockDim.x, tid = threadIdx.x;
@@ -612,7 +607,7 @@ __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A
   const u32 P = a.ref_off[r1] - f0;
   const bool gene = g.ge_mode == GE_MODE_PUG_GENE;
   const bool usa = a.usa_mode != 0;
-  constexpr bool em = EM;
+  const bool em = g.only_unique == 0;
 
   // ---- arena layout, phase A --------------------------------------------------------------------
   u32 off = 0;
@@ -834,7 +829,7 @@ __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A
           gs[j] = x;
           ++nb;
         }
-      const u32 slot = ps_emit_genes<EM>(sk, gs, nb);
+      const u32 slot = ps_emit_genes(sk, gs, nb);
       if (slot != NONE32) {
         winners[atomicAdd(&ex->n_win, 1u)] = slot;
         if (gbm) atomicOr(&gbm[slot >> 5], 1u << (slot & 31));
@@ -913,10 +908,10 @@ __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A
       const u32 sz = csz[r];
       if (sz == 1) {   // singleton component: the class label itself (src/pugutils.rs:1262-1322)
         const u32 gv = vgene[v];
-        if (gv < PS_MULTI_GENE) slot = ps_emit_genes<EM>(sk, &gv, 1u);
+        if (gv < PS_MULTI_GENE) slot = ps_emit_genes(sk, &gv, 1u);
         else {
           const u32 cv = c.vcls(v);
-          slot = ps_emit<EM>(c, sk, c.lab(cv), c.len(cv), [](u32, u32) { return true; });
+          slot = ps_emit(c, sk, c.lab(cv), c.len(cv), [](u32, u32) { return true; });
         }
       } else {
         nxt[v] = atomicExch(&head[r], v);
@@ -945,19 +940,19 @@ __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A
     const u32 K2 = ex->szc[2], K4 = ex->szc[4], K8 = ex->szc[8];
     if (tid == 0) ex->n_over = 0;
     __syncthreads();
-    ps_cover_group<2, EM>(c, sk, winners, gbm, head, nxt, clist, 0, K2, g.pug_exact_umi != 0, olist, &ex->n_over);
-    ps_cover_group<4, EM>(c, sk, winners, gbm, head, nxt, clist, K2, K4, g.pug_exact_umi != 0, olist, &ex->n_over);
-    ps_cover_group<8, EM>(c, sk, winners, gbm, head, nxt, clist, K4, K8, g.pug_exact_umi != 0, olist, &ex->n_over);
+    ps_cover_group<2>(c, sk, winners, gbm, head, nxt, clist, 0, K2, g.pug_exact_umi != 0, olist, &ex->n_over);
+    ps_cover_group<4>(c, sk, winners, gbm, head, nxt, clist, K2, K4, g.pug_exact_umi != 0, olist, &ex->n_over);
+    ps_cover_group<8>(c, sk, winners, gbm, head, nxt, clist, K4, K8, g.pug_exact_umi != 0, olist, &ex->n_over);
     const u32 wid = tid >> 5, nw = ncw;
     u32* wmem = wscr + (wid < nw ? wid : 0u) * PS_WSCR_WORDS;
     if (wid < nw)
       for (u32 k = K - 1 - wid; (int)k >= (int)K8; k -= nw)      // largest components first
-        ps_cover_warp<EM>(c, sk, winners, head, nxt, clist[k], g.pug_exact_umi != 0, gbm, wmem, wmem + 32);
+        ps_cover_warp(c, sk, winners, head, nxt, clist[k], g.pug_exact_umi != 0, gbm, wmem, wmem + 32);
     __syncthreads();
     const u32 KO = ex->n_over;                                   // small components with a long label
     if (wid < nw)
       for (u32 k = wid; k < KO; k += nw)
-        ps_cover_warp<EM>(c, sk, winners, head, nxt, olist[k], g.pug_exact_umi != 0, gbm, wmem, wmem + 32);
+        ps_cover_warp(c, sk, winners, head, nxt, olist[k], g.pug_exact_umi != 0, gbm, wmem, wmem + 32);
   }
   }
   __syncthreads();
@@ -1069,9 +1064,7 @@ __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A
 
 constexpr int PS_LIST0 = NUM_BINS + 3;      // bin_list rows of the three arena variants
 
-// (EM is a template parameter so that the unique-only kernels do not carry the EM back end: the
-// 386 KB of SASS of a combined kernel showed up as instruction-fetch stalls, ncu r1zd: no_instruction 5.9 per issue)
-template <int VAR, bool EM>
+template <int VAR>
 __global__ void __launch_bounds__(ps_threads(VAR), ps_min_blocks(VAR)) k_pug_smem(KArgs a, GeArgs g) {
   AFQ_DYN_SMEM(smem_raw);
   u32* A = VAR < PS_SMEM_VARIANTS ? reinterpret_cast<u32*>(smem_raw) : g.ps_garena + (u64)blockIdx.x * g.ps_garena_words;
@@ -1095,7 +1088,7 @@ __global__ void __launch_bounds__(ps_threads(VAR), ps_min_blocks(VAR)) k_pug_sme
     if (next < count) ps_prefetch_cell(a, list[next]);
     const u32 cell = list[job];
     const u32 AW = (g.ps_limit_words && g.ps_limit_words < AWmax) ? g.ps_limit_words : AWmax;
-    const bool ok = ps_cell<(VAR >= PS_SMEM_VARIANTS), EM>(a, g, cell, A, AW, &sh, &ex, &s_ptrs);
+    const bool ok = ps_cell<(VAR >= PS_SMEM_VARIANTS)>(a, g, cell, A, AW, &sh, &ex, &s_ptrs);
     if (!ok && threadIdx.x == 0) {
       const u32 idx = atomicAdd(&a.ctl->bin_count[GE_LIST_NORMAL], 1u);
       a.bin_list[(u64)GE_LIST_NORMAL * a.n_cells + idx] = cell;
