@@ -174,6 +174,8 @@ __device__ __forceinline__ void table_insert(const CellArena& A, u32 umi, u32 ge
     if (cur == key) { found = true; break; }
     s = (s + 1) & mask;
   }
+  // (a warp-aggregated claim of the list positions — one atomic per warp instead of one per new entry —
+  // was measured slower: C2 8.45 vs 8.26 ms, scripts/gpu_round1zk.sh)
   if (CONV) __syncwarp();
   if (!on) return;
   if (!found) { sh->abort = 1; return; }   // table full (only reachable after the distinct limit was crossed)
