@@ -7,25 +7,33 @@
 // cell, spread over block-wide sorts of record-sized arrays living in L2; this kernel sizes every
 // structure by what the cell actually contains and never sorts records:
 //
-//   load      refs / record offsets (16-bit, relative) / UMIs -> arena
+//   load      refs / record offsets (16-bit, relative) / UMIs -> arena; the NEXT cell is prefetched into L2
 //   phase 1   record -> eq-class: open-address table of REPRESENTATIVE RECORD indices, labels
 //             compared in place (no stored hashes, no reseeding)
 //   phase 2   (class, UMI) vertices: same kind of table, read count in the entry's upper 16 bits
-//   compact   table slots -> dense vertex arrays  vumi[V], vinfo[V] = class << 16 | reads
-//   phase 3   UMI -> vertex chains (table of chain heads) + 2-hash Bloom bitmap of the UMIs
-//   phase 4   union-find over PUG edges: own-UMI chain successors + the 3*L substitutions that pass
-//             the Bloom test (one lane per vertex). The PUG is never stored.
-//   phase 5   components: singletons emit directly; the vertices of larger components are
-//             listed, sorted by root, and each component (<= 32 vertices) is covered by ONE thread
-//             that orders its members canonically (class label lexicographic, UMI), rebuilds the
-//             directed adjacency from pair tests, and runs the greedy monochromatic cover.
-//   counts    unique-only resolutions: winners (output slots) are sorted and run-length counted;
+//   compact   table slots -> dense vertex arrays  vumi[V], vinfo[V] = class << 16 | reads,
+//             vgene[V] = the class's gene when it has exactly one (emission needs no t2g gather then)
+//   phase 3   UMI -> vertex chains (table of chain heads) + Bloom bitmap of the UMIs with two
+//             GF(2)-linear hashes (a substitution costs one XOR with a compile-time constant)
+//   phase 4   union-find (path halving) over PUG edges: own-UMI chain successors + the 3*L
+//             substitutions that pass the Bloom test (one lane per vertex). The PUG is never stored.
+//   phase 5   components: singletons emit directly; members of larger components hang on per-root
+//             lists, the roots are counting-sorted by component size, and components are covered by
+//             groups of 2 / 4 / 8 lanes (lane = start vertex; label-position bitmasks make the BFS of
+//             all transcripts of a start vertex branch-free relaxations in registers) or, from 9
+//             vertices / 33-transcript labels on, by one warp (16 x 16 masks in shared memory). Start
+//             vertices are ranked canonically (class label lexicographic, UMI).
+//   cr-like-em (gene mode): instead of phases 4-5 one lane per UMI chain takes the arg-max gene set.
+//   counts    unique-only resolutions: presence bitmap over the output slots + prefix popcount
+//             (sort + run-length when the gene axis does not fit the arena);
 //             EM resolutions hand their molecules to ge_back (afq_pug.cuh) on arena pointers.
 //
-// Anything that does not fit (arena too small for the cell's actual vertex count, a component
-// with more than 32 vertices, > large_graph_thresh) sends the WHOLE cell to the global-arena
-// kernel's work list, which runs afterwards — results are identical by construction because
-// both kernels implement the same canonical orders.
+// Arena variants: 72 KB x 3 CTAs/SM, 108 KB x 2, 224 KB x 1 of shared memory, and the same code on a
+// per-CTA global-memory arena (32-bit offsets, up to 65 534 records). Anything that does not fit
+// after all (actual vertex count, EM back end), or holds a component with more than 32 vertices
+// / beyond --large-graph-thresh, sends the WHOLE cell to the global-arena kernel's work list, which
+// runs afterwards — results are identical by construction because both kernels implement the same
+// canonical orders (tests force every hand-back path: AFQ_PS_LIMIT_WORDS, AFQ_NO_PS[_GLOBAL]).
 #pragma once
 #include "afq_pug.cuh"
 

@@ -50,3 +50,30 @@ def long_label_cells():
         rng.shuffle(recs)
         cells.append(recs)
     return n_genes, t2g, cells
+
+
+def random_pug_cells(rng, n_cells, n_tx, umi_bits, n_labels, max_label, recs_lo, recs_hi, dup=3):
+    """adversarial small cells for the PUG kernels: a small UMI space (umi_bits) and a small pool of
+    overlapping transcript labels make components of every size (2 .. beyond 32), many cover ties,
+    directed and bidirected edges (skewed read counts)"""
+    cells = []
+    for _ in range(n_cells):
+        pool = []
+        for _l in range(n_labels):
+            k = int(rng.integers(1, max_label + 1))
+            start = int(rng.integers(0, max(1, n_tx - k)))
+            if rng.random() < 0.5:
+                lab = list(range(start, start + k))                      # a contiguous run (shared prefixes / suffixes)
+            else:
+                lab = sorted(set(int(x) for x in rng.integers(0, n_tx, size=k)))
+            pool.append(lab)
+        recs = []
+        n = int(rng.integers(recs_lo, recs_hi))
+        while len(recs) < n:
+            u = int(rng.integers(0, 1 << umi_bits))
+            lab = pool[int(rng.integers(0, len(pool)))]
+            reps = 1 + int(rng.geometric(1.0 / dup)) if rng.random() < 0.5 else 1
+            recs.extend([(u, lab)] * reps)
+        rng.shuffle(recs)
+        cells.append(recs[:n])
+    return cells

@@ -296,3 +296,37 @@ def test_emu_pug_smem_long_labels_take_the_warp_cover(res):
     check(QuantOpts(resolution=res, num_gene_ids=n_genes, num_rows=n_genes, umi_len=12), t2g, b, res)
     cnt = emu_lib.last_counts()
     assert sum(cnt[emu_lib.LIST_PS0:emu_lib.LIST_PS0 + 4]) == b.n_cells and cnt[emu_lib.LIST_GE_NORMAL] == 0, cnt
+
+
+RANDOM_REGIMES = [
+    # (seed, n_tx, tx per gene, umi_bits, n_labels, max_label, records lo, hi)
+    (101, 24, 3, 6, 6, 3, 120, 260),      # 64 UMIs: very dense, components often beyond 32 (hand-backs)
+    (102, 60, 3, 8, 12, 4, 120, 300),     # 256 UMIs
+    (103, 90, 3, 10, 20, 6, 150, 400),    # 1024 UMIs: mostly 2..16 vertex components
+    (104, 200, 5, 12, 30, 40, 150, 350),  # long labels (up to 40 transcripts, beyond the 32-bit position masks)
+    (105, 12, 1, 7, 5, 5, 110, 200),      # every transcript its own gene: multi-gene labels everywhere
+]
+
+
+@pytest.mark.parametrize("regime", RANDOM_REGIMES, ids=lambda r: f"seed{r[0]}")
+@pytest.mark.parametrize("res", ["parsimony", "parsimony-em", "parsimony-gene", "cr-like-em"])
+def test_emu_random_adversarial_cells(regime, res):
+    seed, n_tx, per_gene, umi_bits, n_labels, max_label, lo, hi = regime
+    rng = np.random.default_rng(seed)
+    n_genes = (n_tx + per_gene - 1) // per_gene
+    t2g = (np.arange(n_tx, dtype=np.uint32) // per_gene).astype(np.uint32)
+    b = CellBatch.from_cells(cases.random_pug_cells(rng, 8, n_tx, umi_bits, n_labels, max_label, lo, hi))
+    umi_len = (umi_bits + 1) // 2
+    for thresh in (1000, 6):
+        o = QuantOpts(resolution=res, num_gene_ids=n_genes, num_rows=n_genes, umi_len=umi_len, large_graph_thresh=thresh, small_thresh=0)
+        check(o, t2g, b, f"{res}/seed{seed}/thresh{thresh}")
+
+
+@pytest.mark.parametrize("res", ["parsimony", "parsimony-em", "cr-like-em", "cr-like"])
+def test_emu_random_adversarial_cells_usa(res):
+    rng = np.random.default_rng(207)
+    n_genes, per = 20, 4                                   # 3 spliced + 1 unspliced transcript per gene
+    t2g = np.array([2 * (t // per) + (1 if t % per == 3 else 0) for t in range(n_genes * per)], dtype=np.uint32)
+    b = CellBatch.from_cells(cases.random_pug_cells(rng, 8, n_genes * per, 9, 16, 5, 130, 320))
+    o = QuantOpts(resolution=res, usa_mode=True, num_gene_ids=2 * n_genes, num_rows=3 * n_genes, umi_len=5, small_thresh=0)
+    check(o, t2g, b, res)
