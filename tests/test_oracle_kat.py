@@ -138,6 +138,18 @@ def test_hamming_2bit():
     assert h(0b00, 0b01) == 1 and h(0b00, 0b10) == 1 and h(0b00, 0b11) == 1
     assert h(0b0100, 0b0001) == 2
     assert h(0xFFFFFF, 0x000000) == 12
+
+
+def test_single_base_substitutions_match_the_reference_snp_vector():
+    # src/utils.rs:1207-1213 (test_get_all_snps): the SNP neighbours of barcode 7 at length 3. The PUG
+    # kernels enumerate a UMI's 1-Hamming neighbourhood as u ^ (d << 2*pos), d = 1..3 (afq_pug.cuh
+    # visit_neighbours, afq_pugs.cuh phase 4): same 2-bit packing, same set.
+    golden = [3, 4, 5, 6, 11, 15, 23, 39, 55]
+    mine = sorted(7 ^ (d << (2 * pos)) for pos in range(3) for d in (1, 2, 3))
+    assert mine == golden
+    h = oracle_lib.lib().afq_oracle_hamming
+    assert all(h(7, x) == 1 for x in golden)
+    assert sorted(x for x in range(64) if h(7, x) == 1) == golden
     # neighbours of barcode 7 at length 3 (src/utils.rs:1207-1256 conventions): all 9 SNPs at distance 1
     base = 7
     for pos in range(3):
