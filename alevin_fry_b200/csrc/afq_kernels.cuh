@@ -40,6 +40,7 @@ struct Ctl {                       // per-batch device control block (zeroed per
   u32 ge_max_n[2];                 // largest record / alignment count on the k_gene_eqc lists
   u32 ge_max_p[2];
   unsigned long long adj_used;     // bump pointer into the adjacency pool
+  u32 ps3_max_n, ps3_max_p;        // largest cell on k_pug_smem<3>'s list (sizes its global arenas)
 };
 
 struct KArgs {

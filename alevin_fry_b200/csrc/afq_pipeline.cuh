@@ -180,7 +180,7 @@ int enqueue_batch(L& l, const afq_config& cfg, int force_bin, const PipeBufs& pb
       u32 blocks = (u32)l.ps_grid(v);
       if (blocks > cnt) blocks = cnt;
       if (v == 3) {
-        const u64 words = ps_global_words(h.ge_max_n[1], h.ge_max_p[1], cfg.num_rows);
+        const u64 words = ps_global_words(h.ps3_max_n, h.ps3_max_p, cfg.num_rows);   // (< 2^32: P < 2^30 on this list)
         g.ps_garena = l.ps_garena(words, blocks);
         g.ps_garena_words = (u32)words;
         if (!g.ps_garena) { err = "k_pug_smem global arena allocation failed"; return AFQ_ERR_CUDA; }

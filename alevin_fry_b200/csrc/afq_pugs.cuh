@@ -92,7 +92,8 @@ __host__ __device__ inline int ps_variant_for(u64 n, u64 P, bool gene, bool em, 
 __host__ __device__ inline u64 ps_global_words(u32 n, u32 P, u32 num_rows) {
   if (n >= PS_MAX_RECORDS) n = PS_MAX_RECORDS - 1;
   const u64 rec = (u64)P + (n + 2) + (n + 1) / 2 + n + (n + 1) / 2 + ps_table_size(n);
-  const u64 post = (u64)pow2_ge(n + n / 2 + 2, 64) + 4096 + 3ull * n + pow2_ge(n, 1) + 2048 + 2ull * ((num_rows + 31) / 32);
+  const u64 post = (u64)pow2_ge(n + n / 2 + 2, 64) + 4096 + 3ull * n + pow2_ge(n, 1) + 2ull * PS_COVER_WARPS * PS_WSCR_WORDS + n / 2 + 2 +
+                   2ull * ((num_rows + 31) / 32);   // chain table, bitmap, vnext / parent / nxt, winners, cover scratch, re-route list, slot bitmap
   return (rec + 3ull * n + post + 2ull * n + P + 4096 + 3) & ~3ull;   // + EM: molecule offsets / lengths and labels; 16-byte multiple
 }
 
@@ -1134,6 +1135,7 @@ __global__ void k_bin_cells_ge(KArgs a, int force_bin, u32 big_records, u32 need
     if (w == 1 && (ps_mode & 1u)) {
       const int v = ps_variant_for(n, p, (ps_mode & 2u) != 0, (ps_mode & 4u) != 0, a.usa_mode != 0, (ps_mode & 8u) != 0);
       if (v >= 0) b = PS_LIST0 + v;
+      if (v == 3) { atomicMax(&a.ctl->ps3_max_n, (u32)n); atomicMax(&a.ctl->ps3_max_p, p); }
     }
   }
   const u32 idx = atomicAdd(&a.ctl->bin_count[b], 1u);
