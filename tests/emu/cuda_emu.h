@@ -57,12 +57,31 @@ extern State g;
 
 inline void set_tid(unsigned t) { threadIdx.x = t; g.cur = t; }
 
-// switch from the current fiber to the next unfinished one (round robin)
+// Fiber schedule: 0 = round robin (default), 1 = reverse round robin, >= 2 = pseudo-random with that
+// seed (env AFQ_EMU_SCHED). Other schedules shake out code that only works because thread 0 reaches a
+// barrier first (e.g. a flag read by the others after thread 0 already rewrote it).
+inline unsigned sched_mode() {
+  static int m = -1;
+  if (m < 0) { const char* e = getenv("AFQ_EMU_SCHED"); m = e ? atoi(e) : 0; }
+  return (unsigned)m;
+}
+inline unsigned sched_rand() {
+  static unsigned long long x = 0;
+  if (!x) x = 0x9E3779B97F4A7C15ull * (sched_mode() + 1);
+  x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+  return (unsigned)(x >> 33);
+}
+// switch from the current fiber to another unfinished one
 inline void yield() {
   const unsigned me = g.cur;
   unsigned nxt = me;
+  const unsigned mode = sched_mode();
+  const unsigned start = mode >= 2 ? sched_rand() % g.nthreads : 0;
   for (unsigned k = 1; k <= g.nthreads; ++k) {
-    unsigned c = (me + k) % g.nthreads;
+    unsigned c = mode == 0 ? (me + k) % g.nthreads
+               : mode == 1 ? (me + g.nthreads - k) % g.nthreads
+                           : (start + k) % g.nthreads;
+    if (c == me) continue;
     if (!g.fibers[c].done) { nxt = c; break; }
   }
   if (nxt == me) return;
@@ -110,8 +129,9 @@ void run_block(unsigned nthreads, F&& body) {
     f.ctx.uc_link = nullptr;
     makecontext(&f.ctx, (void (*)())trampoline, 0);
   }
-  set_tid(0);
-  swapcontext(&g.sched, &g.fibers[0].ctx);
+  const unsigned first = sched_mode() == 1 ? nthreads - 1 : (sched_mode() >= 2 ? sched_rand() % nthreads : 0);
+  set_tid(first);
+  swapcontext(&g.sched, &g.fibers[first].ctx);
 }
 
 // launch<<<grid, block, smem>>>: blocks run sequentially
@@ -195,14 +215,21 @@ inline int __all_sync(unsigned m, int p) {
 }
 
 // ---- atomics (single OS thread => plain RMW) ----------------------------------------------
-template <class T> inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
-template <class T> inline T atomicSub(T* p, T v) { T o = *p; *p = o - v; return o; }
-template <class T> inline T atomicMax(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }
-template <class T> inline T atomicMin(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }
-template <class T> inline T atomicOr(T* p, T v) { T o = *p; *p = o | v; return o; }
-template <class T> inline T atomicAnd(T* p, T v) { T o = *p; *p = o & v; return o; }
-template <class T> inline T atomicExch(T* p, T v) { T o = *p; *p = v; return o; }
-template <class T> inline T atomicCAS(T* p, T cmp, T v) { T o = *p; if (o == cmp) *p = v; return o; }
+// With a pseudo-random schedule (AFQ_EMU_SCHED >= 2) a fiber may be pre-empted right BEFORE an atomic:
+// other threads then get in between a plain read and the CAS that follows it, so the lost-race
+// paths of the kernels' open-address tables and lists (CAS returns someone else's value) are run.
+inline void emu_preempt() {
+  using namespace cuda_emu;
+  if (sched_mode() >= 2 && g.nthreads > 1 && (sched_rand() & 7u) == 0) yield();
+}
+template <class T> inline T atomicAdd(T* p, T v) { emu_preempt(); T o = *p; *p = o + v; return o; }
+template <class T> inline T atomicSub(T* p, T v) { emu_preempt(); T o = *p; *p = o - v; return o; }
+template <class T> inline T atomicMax(T* p, T v) { emu_preempt(); T o = *p; if (v > o) *p = v; return o; }
+template <class T> inline T atomicMin(T* p, T v) { emu_preempt(); T o = *p; if (v < o) *p = v; return o; }
+template <class T> inline T atomicOr(T* p, T v) { emu_preempt(); T o = *p; *p = o | v; return o; }
+template <class T> inline T atomicAnd(T* p, T v) { emu_preempt(); T o = *p; *p = o & v; return o; }
+template <class T> inline T atomicExch(T* p, T v) { emu_preempt(); T o = *p; *p = v; return o; }
+template <class T> inline T atomicCAS(T* p, T cmp, T v) { emu_preempt(); T o = *p; if (o == cmp) *p = v; return o; }
 
 // ---- intrinsics ----------------------------------------------------------------------------
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
