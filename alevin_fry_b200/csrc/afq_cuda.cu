@@ -341,7 +341,7 @@ int afq_create(const afq_config* cfg, const uint32_t* tid_to_gid, uint64_t n_ref
   }
   if (cfg->device < 0 || cfg->device >= ndev) { g_create_err = "afq_create: bad device ordinal"; return AFQ_ERR_INVALID; }
   if (cfg->umi_len > 16) { g_create_err = "umi_len > 16 is not supported on the CUDA path (UMI packed in 32 bits)"; return AFQ_ERR_UNSUPPORTED; }
-  if (cfg->sa_model != AFQ_SA_WINNER_TAKE_ALL) { g_create_err = "--sa-model prefer-ambig is not implemented on the CUDA path"; return AFQ_ERR_UNSUPPORTED; }
+  if (cfg->sa_model != AFQ_SA_WINNER_TAKE_ALL && cfg->sa_model != AFQ_SA_PREFER_AMBIG) { g_create_err = "bad sa_model"; return AFQ_ERR_INVALID; }
   if (cfg->resolution < AFQ_RES_TRIVIAL || cfg->resolution > AFQ_RES_PARSIMONY_GENE) { g_create_err = "bad resolution"; return AFQ_ERR_INVALID; }
   if (cfg->usa_mode && (cfg->num_rows % 3 != 0)) { g_create_err = "USA mode needs num_rows = 3G"; return AFQ_ERR_INVALID; }
   cudaDeviceProp prop;

@@ -119,6 +119,7 @@ int enqueue_batch(L& l, const afq_config& cfg, int force_bin, const PipeBufs& pb
   a.ao = 2 * a.uo;
   a.small_thresh = cfg.small_thresh;
   a.tiny_eligible = cfg.sa_model == AFQ_SA_WINNER_TAKE_ALL ? 1u : 0u;
+  a.prefer_ambig = cfg.sa_model == AFQ_SA_PREFER_AMBIG ? 1u : 0u;
   a.ctl = pb.ctl;
   a.bin_list = pb.bin_list;
   a.stage_col = pb.stage_col;
@@ -157,7 +158,7 @@ int enqueue_batch(L& l, const afq_config& cfg, int force_bin, const PipeBufs& pb
     // (cr-like-em in USA mode stays on k_gene_eqc: its EM back end over 3 slots per gene needs the
     // 224 KB / global arenas for ordinary cells, where one CTA per SM iterates slower than k_gene_eqc's
     // four — measured r1x: C4 76.4 ms with k_pug_smem vs 64.2 ms without)
-    const bool ps_on = l.ps_grid(0) > 0 && (g.ge_mode == GE_MODE_CRLIKE ? !cfg.usa_mode : cfg.large_graph_thresh >= 2);
+    const bool ps_on = l.ps_grid(0) > 0 && (g.ge_mode == GE_MODE_CRLIKE ? (!cfg.usa_mode && !a.prefer_ambig) : cfg.large_graph_thresh >= 2);
     const u32 ps_mode = ps_on ? (1u | (g.ge_mode == GE_MODE_PUG_GENE ? 2u : 0u) | (g.only_unique ? 0u : 4u) | (l.ps_grid(3) > 0 ? 8u : 0u)) : 0u;
     l.launch(KID_BIN_GE, k_bin_cells_ge, bin_grid, 256u, (size_t)0, a, force_bin, GE_BIG_RECORDS, l.need_shift(), ps_mode);
     launch_crlike_bins(l, a, pb);

@@ -744,7 +744,7 @@ __device__ __forceinline__ void ltab_add(const GeCell& c, u32 log2cap, u32 umi, 
 }
 
 // after the pair table is filled: compact, sort by (umi, gene), walk each UMI, emit molecules
-__device__ inline void crlike_molecules_from_ltab(const GeCell& c, GeShared* sh, u32 cap) {
+__device__ inline void crlike_molecules_from_ltab(const GeCell& c, GeShared* sh, u32 cap, bool prefer_ambig = false) {
   const u32 d = block_compact_pairs(c.p.ltab_k, c.p.ltab_c, cap, sh->scan);
   const u32 D = next_pow2(d);
   for (u32 i = d + threadIdx.x; i < D; i += blockDim.x) c.p.ltab_k[i] = EMPTY_KEY;
@@ -753,14 +753,24 @@ __device__ inline void crlike_molecules_from_ltab(const GeCell& c, GeShared* sh,
   for (u32 i = threadIdx.x; i < d; i += blockDim.x) {
     const u32 u = (u32)(c.p.ltab_k[i] >> 32);
     if (i > 0 && (u32)(c.p.ltab_k[i - 1] >> 32) == u) continue;
-    u32 maxw = 0, nb = 0, j = i;
-    for (; j < d && (u32)(c.p.ltab_k[j] >> 32) == u; ++j) {
-      const u32 w = c.p.ltab_c[j];
-      if (w > maxw) { maxw = w; nb = 1; } else if (w == maxw) ++nb;
-    }
+    u32 j = i;
+    while (j < d && (u32)(c.p.ltab_k[j] >> 32) == u) ++j;
+    // weight an entry votes with: its own count, or (--sa-model prefer-ambig, src/pugutils.rs:505-641) the
+    // combined count of the ids 2k / 2k+1 of its gene, which are adjacent in the sorted segment
+    auto weight = [&](u32 k) {
+      u32 w = c.p.ltab_c[k];
+      if (prefer_ambig) {
+        const u32 gk = (u32)c.p.ltab_k[k];
+        if (k > i && (((u32)c.p.ltab_k[k - 1]) | 1u) == (gk | 1u)) w += c.p.ltab_c[k - 1];
+        if (k + 1 < j && (((u32)c.p.ltab_k[k + 1]) | 1u) == (gk | 1u)) w += c.p.ltab_c[k + 1];
+      }
+      return w;
+    };
+    u32 maxw = 0, nb = 0;
+    for (u32 k = i; k < j; ++k) { const u32 w = weight(k); if (w > maxw) { maxw = w; nb = 1; } else if (w == maxw) ++nb; }
     const u32 off = c.p.P + atomicAdd(&sh->lab_bump, nb);  // upper half of mlab
     u32 q = 0;
-    for (u32 k = i; k < j; ++k) if (c.p.ltab_c[k] == maxw) c.p.mlab[off + q++] = (u32)c.p.ltab_k[k];
+    for (u32 k = i; k < j; ++k) if (weight(k) == maxw) c.p.mlab[off + q++] = (u32)c.p.ltab_k[k];
     emit_molecule(c, sh, off, nb);
   }
   __syncthreads();
@@ -818,7 +828,7 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
       }
     }
     __syncthreads();
-    crlike_molecules_from_ltab(c, sh, cap);
+    crlike_molecules_from_ltab(c, sh, cap, a.prefer_ambig != 0);
   } else {
     // ---------------- phase 1: eq-classes -----------------------------------------------------
     if (c.gene_labels) {  // materialise the sorted-dedup gene projection of every record

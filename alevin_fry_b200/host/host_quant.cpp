@@ -440,7 +440,6 @@ int quantify_impl(const afqh_quant_opts& o) {
   REQUIRE(resolution_code(res) >= 0, "invalid value '" + std::string(o.resolution) + "' for '--resolution <RESOLUTION>'");
   const std::string sa = o.sa_model ? lower(o.sa_model) : "winner-take-all";
   REQUIRE(sa == "winner-take-all" || sa == "prefer-ambig", "invalid value for '--sa-model'");
-  REQUIRE(sa == "winner-take-all", "--sa-model prefer-ambig is not implemented on the CUDA path");
   REQUIRE(o.num_bootstraps == 0, "bootstrapping (-b) is not implemented on the CUDA path (the reference's RNG is unseeded; see SURVEY.md §8(f) N4)");
   REQUIRE(!o.dump_eq, "--dump-eqclasses is not implemented on the CUDA path yet (SURVEY.md §8(f) N3)");
   // src/main.rs:733-734, 759, 812-820
@@ -526,7 +525,13 @@ int quantify_impl(const afqh_quant_opts& o) {
   cfg.usa_mode = t2g.usa;
   cfg.em_init_uniform = o.init_uniform;
   cfg.pug_exact_umi = o.pug_exact_umi;
-  cfg.sa_model = AFQ_SA_WINNER_TAKE_ALL;
+  // src/quant.rs:1457-1467: prefer-ambig only makes sense in USA mode; otherwise it is ignored (with a note)
+  bool prefer_ambig = sa == "prefer-ambig";
+  if (prefer_ambig && !t2g.usa) {
+    fprintf(stderr, "When not operating in USA-mode (all-in-one unspliced/spliced/ambiguous), the SplicedAmbiguityModel will be ignored.\n");
+    prefer_ambig = false;
+  }
+  cfg.sa_model = prefer_ambig ? AFQ_SA_PREFER_AMBIG : AFQ_SA_WINNER_TAKE_ALL;
   cfg.num_gene_ids = t2g.num_gene_ids;
   cfg.num_rows = t2g.num_rows;
   cfg.small_thresh = o.small_thresh;
@@ -781,7 +786,7 @@ int quantify_impl(const afqh_quant_opts& o) {
     js += "    \"output_dir\": \"" + json_escape(out) + "\",\n";
     js += std::string("    \"pug_exact_umi\": ") + (o.pug_exact_umi ? "true" : "false") + ",\n";
     js += std::string("    \"resolution\": \"") + resolution_debug_name(res) + "\",\n";
-    js += "    \"sa_model\": \"WinnerTakeAll\",\n";
+    js += std::string("    \"sa_model\": \"") + (sa == "prefer-ambig" ? "PreferAmbiguity" : "WinnerTakeAll") + "\",\n";
     js += "    \"small_thresh\": "; append_u64(js, o.small_thresh); js += ",\n";
     js += std::string("    \"summary_stat\": ") + (o.summary_stat ? "true" : "false") + ",\n";
     js += "    \"tg_map\": \"" + json_escape(o.tg_map) + "\",\n";

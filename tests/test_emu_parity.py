@@ -330,3 +330,34 @@ def test_emu_random_adversarial_cells_usa(res):
     b = CellBatch.from_cells(cases.random_pug_cells(rng, 8, n_genes * per, 9, 16, 5, 130, 320))
     o = QuantOpts(resolution=res, usa_mode=True, num_gene_ids=2 * n_genes, num_rows=3 * n_genes, umi_len=5, small_thresh=0)
     check(o, t2g, b, res)
+
+
+# ---- --sa-model prefer-ambig (src/pugutils.rs:505-641) ----------------------
+@pytest.mark.parametrize("res", ["cr-like", "cr-like-em"])
+def test_emu_prefer_ambig_usa(res):
+    spec = synth.SynthSpec(usa_mode=True, reads_mean=400.0, n_genes=300)
+    b = synth.generate(spec, 0, 10)
+    t2g = synth.tid_to_gid(spec)
+    wta = check(opts_for(spec, res), t2g, b, res + "/wta")
+    pa = check(opts_for(spec, res, sa_model="prefer-ambig"), t2g, b, res + "/prefer-ambig")
+    # the option must actually change something on USA data with spliced + unspliced evidence
+    assert not (np.array_equal(wta.col, pa.col) and np.array_equal(wta.val, pa.val))
+    # the tiny-cell fast path is switched off by it (src/quant.rs:794)
+    tiny = synth.generate(synth.SynthSpec(usa_mode=True, fixed_reads=40, n_genes=300), 0, 12)
+    got = check(opts_for(spec, res, sa_model="prefer-ambig"), t2g, tiny, res + "/prefer-ambig/tiny")
+    assert not (got.flags & 1).any()
+
+
+@pytest.mark.parametrize("res", ["cr-like", "cr-like-em", "parsimony"])
+def test_emu_prefer_ambig_adversarial_and_gene_mode(res):
+    rng = np.random.default_rng(311)
+    n_genes, per = 20, 4
+    t2g = np.array([2 * (t // per) + (1 if t % per == 3 else 0) for t in range(n_genes * per)], dtype=np.uint32)
+    b = CellBatch.from_cells(cases.random_pug_cells(rng, 8, n_genes * per, 9, 16, 5, 130, 320))
+    o = QuantOpts(resolution=res, usa_mode=True, num_gene_ids=2 * n_genes, num_rows=3 * n_genes, umi_len=5, small_thresh=0,
+                  sa_model="prefer-ambig")
+    check(o, t2g, b, res + "/usa")
+    # the library applies the model as given in gene mode too (the CLI host resets it there, as the reference does)
+    spec = synth.SynthSpec(reads_mean=300.0, n_genes=200)
+    bg = synth.generate(spec, 0, 8)
+    check(opts_for(spec, res, sa_model="prefer-ambig"), synth.tid_to_gid(spec), bg, res + "/gene")

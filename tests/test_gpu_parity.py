@@ -324,3 +324,13 @@ def test_pug_smem_dense_umi_space_components():
             o = QuantOpts(resolution=res, usa_mode=spec.usa_mode, num_gene_ids=spec.num_gene_ids, num_rows=spec.num_rows,
                           umi_len=umi_len, large_graph_thresh=thresh, small_thresh=0)
             assert_same(gpu_quant(o, t2g, b), oracle_lib.oracle_quant(o, t2g, b), exact=not res.endswith("-em"), ctx=f"{res}/{umi_len}/{thresh}")
+
+
+@pytest.mark.parametrize("res", ["cr-like", "cr-like-em"])
+def test_prefer_ambig_usa(res):
+    # --sa-model prefer-ambig (src/pugutils.rs:505-641): spliced / unspliced ids of one gene vote together
+    spec = synth.config_spec("C4")
+    b = synth.generate(spec, 0, 200)
+    t2g = synth.tid_to_gid(spec)
+    o = opts_for(spec, res, sa_model="prefer-ambig")
+    assert_same(gpu_quant(o, t2g, b), oracle_lib.oracle_quant(o, t2g, b), exact=not res.endswith("-em"), ctx=res + "/prefer-ambig")
