@@ -189,6 +189,44 @@ __device__ __forceinline__ void table_insert(const CellArena& A, u32 umi, u32 ge
   }
 }
 
+// --sa-model prefer-ambig (resolve_num_molecules_crlike_from_vec_prefer_ambig, src/pugutils.rs:505-641),
+// called by the leader (slot s) of UMI u in phase 2: the ids 2k / 2k+1 (spliced / unspliced of one gene)
+// vote TOGETHER; the label lists the ids present of every gene attaining the largest combined count,
+// ascending; returns the output slot (or NONE32) and retires the UMI's other entries. The entries are
+// re-scanned instead of being copied out, and the function is kept out of line so that the hidden
+// option costs the default path neither registers nor stack.
+__device__ __noinline__ u32 prefer_ambig_slot(const u64* keys, u32* cnts, u32 log2cap, u32 s, u32 u, u32 usa, u32 uo, u32 ao) {
+  const u32 mask = (1u << log2cap) - 1;
+  const u32 home = umi_home(u, log2cap);
+  auto for_entries = [&](auto f) {
+    for (u32 t = s, dist = (s - home) & mask; dist <= mask; t = (t + 1) & mask, ++dist) {
+      const u64 kt = keys[t];
+      if (kt == EMPTY_KEY) { if (dist >= UMI_WINDOW) break; continue; }
+      if ((u32)(kt >> 32) != u) continue;
+      f(t, (u32)kt);
+    }
+  };
+  auto group_weight = [&](u32 gene) {
+    u32 w = 0;
+    for_entries([&](u32 t, u32 g2) { if ((g2 | 1u) == (gene | 1u)) w += cnts[t]; });
+    return w;
+  };
+  u32 maxw = 0;
+  for_entries([&](u32, u32 gene) { const u32 w = group_weight(gene); maxw = w > maxw ? w : maxw; });
+  u32 lab[11] = {0};
+  u32 nl = 0;
+  for_entries([&](u32, u32 gene) {
+    if (group_weight(gene) != maxw || nl == 11) return;
+    u32 q = nl;
+    while (q > 0 && lab[q - 1] > gene) { lab[q] = lab[q - 1]; --q; }
+    lab[q] = gene;
+    ++nl;
+  });
+  for_entries([&](u32 t, u32) { if (t != s) cnts[t] = NONE32; });
+  if (!usa) return nl == 1 ? lab[0] : NONE32;
+  return nl <= 10 ? usa_slot_for_label(lab, nl, uo, ao) : NONE32;
+}
+
 // Returns false when the distinct-pair count exceeded `limit` (caller re-queues the cell on a
 // larger arena); nothing has been written for the cell in that case.
 template <bool LIST>
@@ -341,42 +379,7 @@ __device__ inline bool resolve_cell(const KArgs& a, u32 cell, const CellArena& A
     u32 maxw = 0, nb = 0, b0 = 0;
     u32 best[10];
     const bool usa = a.usa_mode != 0;
-    if (a.prefer_ambig) {
-      // --sa-model prefer-ambig (resolve_num_molecules_crlike_from_vec_prefer_ambig, src/pugutils.rs:505-641):
-      // the ids 2k / 2k+1 (spliced / unspliced of one gene) vote TOGETHER; the label lists the ids
-      // present of every gene attaining the largest combined count, ascending. The UMI's entries are
-      // re-scanned instead of being copied out (a hidden option: clarity over speed).
-      const u32 home = umi_home(u, A.log2cap);
-      auto for_entries = [&](auto f) {
-        for (u32 t = s, dist = (s - home) & mask; dist <= mask; t = (t + 1) & mask, ++dist) {
-          const u64 kt = A.keys[t];
-          if (kt == EMPTY_KEY) { if (dist >= UMI_WINDOW) break; continue; }
-          if ((u32)(kt >> 32) != u) continue;
-          f(t, (u32)kt);
-        }
-      };
-      auto group_weight = [&](u32 gene) {
-        u32 w = 0;
-        for_entries([&](u32 t, u32 g2) { if ((g2 | 1u) == (gene | 1u)) w += A.cnts[t]; });
-        return w;
-      };
-      for_entries([&](u32, u32 gene) { const u32 w = group_weight(gene); maxw = w > maxw ? w : maxw; });
-      u32 lab[11] = {0};
-      u32 nl = 0;
-      for_entries([&](u32, u32 gene) {
-        if (group_weight(gene) != maxw || nl == 11) return;
-        u32 q = nl;
-        while (q > 0 && lab[q - 1] > gene) { lab[q] = lab[q - 1]; --q; }
-        lab[q] = gene;
-        ++nl;
-      });
-      for_entries([&](u32 t, u32) { if (t != s) A.cnts[t] = NONE32; });
-      u32 res = NONE32;
-      if (!usa) { if (nl == 1) res = lab[0]; }
-      else if (nl <= 10) res = usa_slot_for_label(lab, nl, a.uo, a.ao);
-      A.cnts[s] = res;
-      continue;
-    }
+    if (a.prefer_ambig) { A.cnts[s] = prefer_ambig_slot(A.keys, A.cnts, A.log2cap, s, u, a.usa_mode, a.uo, a.ao); continue; }   // (out of line: a hidden option)
     for (u32 t = s, dist = (s - umi_home(u, A.log2cap)) & mask; dist <= mask; t = (t + 1) & mask, ++dist) {
       const u64 kt = A.keys[t];
       if (kt == EMPTY_KEY) { if (dist >= UMI_WINDOW) break; continue; }   // holes only inside the window
