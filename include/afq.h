@@ -61,7 +61,9 @@ typedef struct afq_config {
   int32_t usa_mode;           /* 3-column t2g: gene ids are 2k (spliced) / 2k+1 (unspl.) */
   int32_t em_init_uniform;    /* --init-uniform (EmInitType::Uniform) else Informative  */
   int32_t pug_exact_umi;      /* --umi-edit-dist 0                                      */
-  int32_t sa_model;           /* AFQ_SA_*                                               */
+  int32_t sa_model;           /* AFQ_SA_* (prefer-ambig: src/pugutils.rs:505-641; applied as
+                                 given — the host ignores it outside USA mode like
+                                 src/quant.rs:1457-1467; switches the tiny-cell path off)   */
   int32_t reserved0;
   uint32_t num_gene_ids;      /* size of the tid_to_gid value space: G (gene mode) or 2G */
   uint32_t num_rows;          /* output columns: G (gene mode) or 3G (USA)               */
