@@ -10,7 +10,7 @@ CSRC := $(PKG)/csrc
 
 all: $(PKG)/libafq.so oracle/libafq_oracle.so synth/libafq_synth.so $(PKG)/libafq_host.so bin/alevin-fry
 
-$(PKG)/libafq.so: $(CSRC)/afq_cuda.cu $(CSRC)/afq_kernels.cuh $(CSRC)/afq_device.cuh $(CSRC)/afq_pug.cuh include/afq.h
+$(PKG)/libafq.so: $(CSRC)/afq_cuda.cu $(wildcard $(CSRC)/*.cuh) include/afq.h
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/afq_cuda.cu
 
 oracle/libafq_oracle.so: oracle/afq_oracle.cpp include/afq.h

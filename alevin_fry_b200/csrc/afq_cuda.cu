@@ -107,7 +107,7 @@ struct Slot {  // one in-flight host batch
   HBuf<float> h_val, h_sum, h_max;
   HBuf<u8> h_flags;
   HBuf<Ctl> h_ctl;
-  cudaEvent_t ev_h2d = nullptr, ev_done = nullptr;
+  cudaEvent_t ev_h2d = nullptr, ev_done = nullptr, ev_d2h = nullptr;
   u64 n_cells = 0, n_refs = 0, ticket = 0;
   bool busy = false;
   void release() {
@@ -118,6 +118,7 @@ struct Slot {  // one in-flight host batch
     h_val.release(); h_sum.release(); h_max.release(); h_flags.release(); h_ctl.release();
     if (ev_h2d) cudaEventDestroy(ev_h2d);
     if (ev_done) cudaEventDestroy(ev_done);
+    if (ev_d2h) cudaEventDestroy(ev_d2h);
   }
 };
 
@@ -341,6 +342,10 @@ int afq_create(const afq_config* cfg, const uint32_t* tid_to_gid, uint64_t n_ref
   }
   if (cfg->device < 0 || cfg->device >= ndev) { g_create_err = "afq_create: bad device ordinal"; return AFQ_ERR_INVALID; }
   if (cfg->umi_len > 16) { g_create_err = "umi_len > 16 is not supported on the CUDA path (UMI packed in 32 bits)"; return AFQ_ERR_UNSUPPORTED; }
+  if (cfg->umi_len == 0 && !cfg->pug_exact_umi && res_is_pug(cfg->resolution)) {
+    g_create_err = "umi_len = 0 with a parsimony resolution: the 1-edit UMI neighbourhood needs the UMI length (set umi_len, or pug_exact_umi)";
+    return AFQ_ERR_INVALID;
+  }
   if (cfg->sa_model != AFQ_SA_WINNER_TAKE_ALL && cfg->sa_model != AFQ_SA_PREFER_AMBIG) { g_create_err = "bad sa_model"; return AFQ_ERR_INVALID; }
   if (cfg->resolution < AFQ_RES_TRIVIAL || cfg->resolution > AFQ_RES_PARSIMONY_GENE) { g_create_err = "bad resolution"; return AFQ_ERR_INVALID; }
   if (cfg->usa_mode && (cfg->num_rows % 3 != 0)) { g_create_err = "USA mode needs num_rows = 3G"; return AFQ_ERR_INVALID; }
@@ -387,6 +392,7 @@ int afq_create(const afq_config* cfg, const uint32_t* tid_to_gid, uint64_t n_ref
   for (auto& s : c->slots) {
     CREATE_TRY(cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
     CREATE_TRY(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+    CREATE_TRY(cudaEventCreateWithFlags(&s.ev_d2h, cudaEventDisableTiming));
   }
 #undef CREATE_TRY
   int rc;
@@ -542,11 +548,17 @@ int afq_submit(afq_ctx* c, const afq_batch* hb, uint64_t* ticket) {
 
 int afq_wait(afq_ctx* c, uint64_t ticket, afq_result* out) {
   if (!c || !out) return AFQ_ERR_INVALID;
-  std::lock_guard<std::mutex> lk(c->mu);
+  // The context lock is held for the slot look-up and the bookkeeping only, never across a CUDA
+  // synchronisation: a producer thread's afq_submit (H2D of the next batch) must not wait for this
+  // batch's kernels. The slot's busy flag protects its buffers in between.
+  std::unique_lock<std::mutex> lk(c->mu);
   cudaSetDevice(c->device);
   Slot& s = c->slots[ticket % afq_ctx::NSLOT];
   if (!s.busy || s.ticket != ticket) { c->err = "afq_wait: unknown or already-collected ticket"; return AFQ_ERR_INVALID; }
-  CUDA_TRY(c, cudaEventSynchronize(s.ev_done));
+  lk.unlock();
+  cudaError_t e = cudaEventSynchronize(s.ev_done);
+  lk.lock();
+  if (e != cudaSuccess) { c->err = std::string("cudaEventSynchronize(ev_done): ") + cudaGetErrorString(e); s.busy = false; return AFQ_ERR_CUDA; }
   int rc = check_device_error(c, *s.h_ctl.p);
   if (rc != AFQ_OK) { s.busy = false; return rc; }
   const u64 nnz = s.h_row_ptr.p[s.n_cells];
@@ -555,7 +567,11 @@ int afq_wait(afq_ctx* c, uint64_t ticket, afq_result* out) {
   if (nnz) {
     CUDA_TRY(c, cudaMemcpyAsync(s.h_col.p, s.col.p, nnz * sizeof(u32), cudaMemcpyDeviceToHost, c->s_d2h));
     CUDA_TRY(c, cudaMemcpyAsync(s.h_val.p, s.val.p, nnz * sizeof(float), cudaMemcpyDeviceToHost, c->s_d2h));
-    CUDA_TRY(c, cudaStreamSynchronize(c->s_d2h));
+    CUDA_TRY(c, cudaEventRecord(s.ev_d2h, c->s_d2h));
+    lk.unlock();
+    e = cudaEventSynchronize(s.ev_d2h);
+    lk.lock();
+    if (e != cudaSuccess) { c->err = std::string("cudaEventSynchronize(ev_d2h): ") + cudaGetErrorString(e); s.busy = false; return AFQ_ERR_CUDA; }
   }
   out->n_cells = s.n_cells;
   out->nnz = nnz;

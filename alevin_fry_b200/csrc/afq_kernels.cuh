@@ -236,6 +236,8 @@ __device__ inline bool resolve_cell(const KArgs& a, u32 cell, const CellArena& A
   const u32 T = blockDim.x, tid = threadIdx.x;
   const u64 r0 = a.cell_rec_off[cell], r1 = a.cell_rec_off[cell + 1];
   const u32 nrec = (u32)(r1 - r0);
+  // a tiny cell takes the cr-like fast path whatever -r says (src/quant.rs:780-846)
+  const bool trivial = a.mode == MODE_TRIVIAL && !(a.tiny_eligible && (r1 - r0) < a.small_thresh);
   for (u32 i = tid; i < cap; i += T) { A.keys[i] = EMPTY_KEY; A.cnts[i] = 0; }
   if (tid == 0) { sh->distinct = 0; sh->abort = 0; sh->red_max = 0; sh->red_cnt = 0; sh->nwin = 0; sh->nbig = 0; }
   __syncthreads();
@@ -254,7 +256,7 @@ __device__ inline bool resolve_cell(const KArgs& a, u32 cell, const CellArena& A
   const u32 W = (P >> 5) + 1;                       // bitmap words
   u32* hb = A.bcnt;                                 // [W] record-head bits
   u32* hr = A.bcnt + W;                             // [W] heads before word w
-  bool flat = a.mode != MODE_TRIVIAL && 2 * W <= 3 * NB && P > 0;
+  bool flat = !trivial && 2 * W <= 3 * NB && P > 0;
   if (flat) {
     for (u32 i = tid; i < W; i += T) hb[i] = 0;
     if (tid == 0) sh->nbig = 0;                     // "some record has no alignment"
@@ -328,7 +330,7 @@ __device__ inline bool resolve_cell(const KArgs& a, u32 cell, const CellArena& A
     const u32 o0 = a.ref_off[r], o1 = a.ref_off[r + 1];
     if (o1 == o0) continue;
     const u32 g0 = __ldg(a.t2g + a.refs[o0]);
-    if (a.mode == MODE_TRIVIAL) {
+    if (trivial) {
       // src/pugutils.rs:870-881: a class is multi-gene iff two consecutive refs differ in gene
       bool multi = false;
       for (u32 k = o0 + 1; k < o1; ++k)
@@ -364,7 +366,7 @@ __device__ inline bool resolve_cell(const KArgs& a, u32 cell, const CellArena& A
       s = LIST ? A.list[i] : i;
       const u64 key = A.keys[s];
       if (!LIST && key == EMPTY_KEY) A.cnts[s] = NONE32;
-      else if (a.mode == MODE_TRIVIAL) A.cnts[s] = (u32)key;   // every distinct (gene, umi) counts
+      else if (trivial) A.cnts[s] = (u32)key;   // every distinct (gene, umi) counts
       else {
         u = (u32)(key >> 32);
         leader = true;

@@ -283,6 +283,37 @@ struct HostBatch {   // pinned SoA arrays of one device batch, sized exactly by 
   uint64_t n_cells() const { return chunks.size(); }
 };
 
+// unmapped_bc_count_collated.bin (src/quant.rs:1484-1494): corrected barcode -> number of unmapped reads.
+// libradicl 0.18's CollatedUnmappedCounts layout is not available here (the crate is not vendored); what IS
+// stated in the reference tree is the bincode form of a HashMap<u64, u32> (src/atac/collate.rs:270-283: u64
+// entry count, then (u64 key, u32 value) pairs, little-endian), which is also what alevin-fry wrote before the
+// libradicl type existed. That form is read exactly (size-checked); anything else is reported and treated like
+// the reference treats an unreadable file (empty map), so that the run never silently pretends to know it.
+struct UnmappedCounts {
+  std::unordered_map<uint64_t, uint32_t> map;
+  bool present = false, understood = false;
+  uint32_t get(uint64_t bc) const { auto it = map.find(bc); return it == map.end() ? 0u : it->second; }
+};
+UnmappedCounts load_unmapped(const std::string& path) {
+  UnmappedCounts u;
+  if (!file_exists(path)) return u;
+  u.present = true;
+  const std::string raw = slurp(path);
+  if (raw.size() >= 8) {
+    uint64_t n; memcpy(&n, raw.data(), 8);
+    if (n <= raw.size() / 12 && raw.size() == 8 + n * 12) {
+      u.map.reserve(n * 2);
+      for (uint64_t i = 0; i < n; ++i) {
+        uint64_t k; uint32_t v;
+        memcpy(&k, raw.data() + 8 + i * 12, 8); memcpy(&v, raw.data() + 16 + i * 12, 4);
+        u.map[k] += v;
+      }
+      u.understood = true;
+    }
+  } else if (raw.empty()) u.understood = true;   // "no unmapped reads"
+  return u;
+}
+
 struct Outputs {
   FILE* rows = nullptr;
   FILE* feat = nullptr;
@@ -321,7 +352,9 @@ void parse_batch(HostBatch& b, const RecordLayout& lay, Pool& pool, std::string&
           uint64_t rumi = 0;
           memcpy(&rumi, p + lay.umi_off, lay.umi_size);
           p += lay.read_bytes;
-          if ((uint64_t)na > ref_end - ref || p + (size_t)na * lay.aln_bytes > end) { ok = false; break; }
+          // (a record without alignments cannot come out of a mapper / collate: the reference's writer asserts it,
+          // src/convert.rs:134, and its resolvers index label[0])
+          if (na == 0 || (uint64_t)na > ref_end - ref || p + (size_t)na * lay.aln_bytes > end) { ok = false; break; }
           if (b.pack24) { uint8_t* d = b.umi24.p + 3 * rec; d[0] = (uint8_t)rumi; d[1] = (uint8_t)(rumi >> 8); d[2] = (uint8_t)(rumi >> 16); }
           else b.umi.p[rec] = (uint32_t)rumi;
           b.na8.p[rec] = (uint8_t)na;
@@ -338,7 +371,7 @@ void parse_batch(HostBatch& b, const RecordLayout& lay, Pool& pool, std::string&
         if (!ok || ref != ref_end || p != end) {
           bad = true;
           std::lock_guard<std::mutex> lk(fm);
-          if (failure.empty()) failure = "record overruns its chunk (corrupt collated RAD, chunk " + std::to_string(b.first_cell + c) + ")";
+          if (failure.empty()) failure = "record without alignments or overrunning its chunk (corrupt collated RAD, chunk " + std::to_string(b.first_cell + c) + ")";
           return;
         }
       }
@@ -368,7 +401,7 @@ void parse_batch(HostBatch& b, const RecordLayout& lay, Pool& pool, std::string&
 }
 
 // text for rows / featureDump / mtx of one finished batch, formatted in parallel (N2)
-void consume(const HostBatch& hb, const afq_result& r, unsigned bc_len, Outputs& o, Pool& pool) {
+void consume(const HostBatch& hb, const afq_result& r, unsigned bc_len, const UnmappedCounts& unmapped, Outputs& o, Pool& pool) {
   constexpr uint64_t BLK = 256;
   const uint64_t nblk = (r.n_cells + BLK - 1) / BLK;
   std::vector<std::string> rows(nblk), feat(nblk), mtx(nblk);
@@ -384,8 +417,8 @@ void consume(const HostBatch& hb, const afq_result& r, unsigned bc_len, Outputs&
       for (uint64_t c = c0; c < c1; ++c) {
         const std::string bc = decode_barcode(hb.chunks[c].bc, bc_len);
         rs += bc; rs.push_back('\n');
-        // featureDump (src/quant.rs:1181-1196, 1248-1260); unmapped counts unavailable => 0
-        const uint32_t num_mapped = hb.chunks[c].nrec, num_unmapped = 0;
+        // featureDump (src/quant.rs:1181-1196, 1248-1260)
+        const uint32_t num_mapped = hb.chunks[c].nrec, num_unmapped = unmapped.get(hb.chunks[c].bc);
         const float sum_umi = r.sum_umi[c], max_umi = r.max_umi[c];
         const float dedup_rate = sum_umi / (float)num_mapped;
         const float mapping_rate = (float)num_mapped / (float)(num_mapped + num_unmapped);
@@ -492,11 +525,18 @@ int quantify_impl(const afqh_quant_opts& o) {
   if (!cbl) { fclose(f); throw Fail{"tag map must contain cblen or bNlen for barcode length"}; }
   const unsigned bc_len = (unsigned)cbl->u;
   const TagValue* ul = pre.file_tag("ulen");
-  const unsigned umi_len = ul ? (unsigned)ul->u : 0;
   RecordLayout lay;
   if (!make_layout(pre, lay, perr)) { fclose(f); throw Fail{perr}; }
+  // the reference's quant never reads `ulen` (it compares packed UMIs); without the tag the widest UMI the
+  // stored integer can hold is assumed, which is exact for the 1-edit enumeration (absent bases are zero bits)
+  const unsigned umi_len = ul ? (unsigned)ul->u : (unsigned)(4 * lay.umi_size);
   if (umi_len > 16 || lay.umi_size > 8) { fclose(f); throw Fail{"UMIs longer than 16 bases are not supported on the CUDA path"}; }
 
+  const UnmappedCounts unmapped = load_unmapped(in + "/unmapped_bc_count_collated.bin");
+  if (unmapped.present && !unmapped.understood)
+    fprintf(stderr, "warning: %s/unmapped_bc_count_collated.bin is not in the bincode HashMap<u64,u32> form this build reads "
+                    "(libradicl's CollatedUnmappedCounts layout is unavailable); CorrectedReads / MappingRate in featureDump.txt "
+                    "are computed with 0 unmapped reads per barcode, as the reference does when it cannot read the file\n", in.c_str());
   const auto t_t2g0 = std::chrono::steady_clock::now();
   T2G t2g = parse_t2g(o.tg_map, pre.ref_names);
   const auto t_t2g1 = std::chrono::steady_clock::now();
@@ -590,7 +630,7 @@ int quantify_impl(const afqh_quant_opts& o) {
   constexpr int NB = 3;
   HostBatch hb[NB];
   // 24-bit wire arrays whenever the chemistry allows: UMI <= 12 bases and fewer than 2^24 targets
-  const bool pack24 = umi_len <= 12 && lay.umi_size <= 4 && pre.ref_names.size() < (1u << 24) && !getenv("AFQ_NO_PACK24");
+  const bool pack24 = ul && umi_len <= 12 && lay.umi_size <= 4 && pre.ref_names.size() < (1u << 24) && !getenv("AFQ_NO_PACK24");
   for (auto& b : hb) b.pack24 = pack24;
   uint64_t tickets[NB] = {0};
   bool inflight[NB] = {false};
@@ -599,7 +639,7 @@ int quantify_impl(const afqh_quant_opts& o) {
     const auto ta = clk::now();
     if (afq_wait(ctx, tickets[i], &r) != AFQ_OK) throw Fail{std::string("afq_wait: ") + afq_last_error(ctx)};
     const auto tb = clk::now();
-    consume(hb[i], r, bc_len, outs, fmt_pool);
+    consume(hb[i], r, bc_len, unmapped, outs, fmt_pool);
     t_wait += secs(ta, tb); t_format += secs(tb, clk::now());
     afq_result_release(ctx, &r);
   };

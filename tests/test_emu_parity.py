@@ -77,6 +77,20 @@ def test_emu_edge_cases(res):
         check(QuantOpts(resolution=res, num_gene_ids=10, num_rows=10, small_thresh=st), t2g, b, f"{res}/{st}")
 
 
+@pytest.mark.parametrize("res", ALL_RES)
+@pytest.mark.parametrize("usa", [False, True])
+def test_emu_tiny_cells_take_the_crlike_path_whatever_the_resolution(res, usa):
+    # src/quant.rs:780-846: a cell below --small-thresh is resolved cr-like regardless of -r. These cells
+    # separate the two semantics for `trivial` (a UMI seen on two genes: trivial counts both, cr-like drops the tie)
+    t2g = np.arange(10, dtype=np.uint32)
+    cells = [[(5, [1]), (5, [2])], [(5, [1]), (5, [1]), (5, [2]), (6, [3])], [(5, [2, 3]), (5, [2]), (7, [4, 5])],
+             [(1, [0])] * 99 + [(1, [1])], [(1, [0])] * 100 + [(1, [1])]]
+    b = CellBatch.from_cells(cells)
+    n = 4 if usa else 10
+    for st in (100, 3, 0):
+        check(QuantOpts(resolution=res, usa_mode=usa, num_gene_ids=10, num_rows=15 if usa else 10, small_thresh=st), t2g, b, f"{res}/{st}/{usa}")
+
+
 def test_emu_uniform_init_and_many_gene_labels():
     spec = synth.SynthSpec(n_genes=60, reads_mean=300.0, p_multi2=0.3, p_multi3=0.3, reads_per_umi=2.0)
     b = synth.generate(spec, 0, 6)

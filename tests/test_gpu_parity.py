@@ -101,6 +101,19 @@ def test_edge_cases_empty_ragged():
     assert r.n_cells == 0 and r.nnz == 0
 
 
+@pytest.mark.parametrize("res", INT_RES + EM_RES)
+def test_tiny_cells_take_the_crlike_path_whatever_the_resolution(res):
+    # src/quant.rs:780-846 (`-r trivial` resolved tiny cells with trivial semantics)
+    t2g = np.arange(10, dtype=np.uint32)
+    cells = [[(5, [1]), (5, [2])], [(5, [1]), (5, [1]), (5, [2]), (6, [3])], [(5, [2, 3]), (5, [2]), (7, [4, 5])],
+             [(1, [0])] * 99 + [(1, [1])], [(1, [0])] * 100 + [(1, [1])]]
+    b = CellBatch.from_cells(cells)
+    for usa in (False, True):
+        for st in (100, 3, 0):
+            o = QuantOpts(resolution=res, usa_mode=usa, num_gene_ids=10, num_rows=15 if usa else 10, small_thresh=st)
+            assert_same(gpu_quant(o, t2g, b), oracle_lib.oracle_quant(o, t2g, b), exact=res in INT_RES, ctx=f"{res}/{st}/{usa}")
+
+
 def test_skewed_cells_hit_every_arena_bin(monkeypatch):
     # lognormal sigma 1.6 spreads cells from a few records to > 16k: exercises all shared-memory
     # arenas, the overflow re-queue and the giant-cell global arena
