@@ -255,8 +255,8 @@ struct CudaLauncher {
   void region_begin() {
     if (c->profiling) { cudaEventCreate(&reg_a); cudaEventCreate(&reg_b); cudaEventRecord(reg_a, st); }
   }
-  void region_end() {
-    if (c->profiling) { cudaEventRecord(reg_b, st); c->prof.push_back({KID_REGION, reg_a, reg_b}); c->kid_launches[KID_REGION]++; }
+  void region_end(int kid) {
+    if (c->profiling) { cudaEventRecord(reg_b, st); c->prof.push_back({kid, reg_a, reg_b}); c->kid_launches[kid]++; }
   }
 };
 

@@ -12,6 +12,7 @@
 //   int  ge_blocks(int which);                                // 0 big-cell grid, 1 normal grid
 //   u8*  ge_arena(int which, u64 bytes_per_block, u32 blocks);// grow-only, nullptr on failure
 //   u32* adj_pool(u64 entries);                               // grow-only, nullptr on failure
+//   void region_begin(); void region_end(int kid);            // wall time of a forked region (profiling)
 //   void fork(int lanes); void lane(int i); void join();      // independent launches may overlap:
 //       between fork and join, launches go to lane i's stream (CUDA) / run in order (emulator)
 //   u32  need_shift();                                        // arena-size bias learnt from overflows
@@ -31,13 +32,13 @@ namespace afq {
 enum KernelId : int {
   KID_BIN = 0, KID_SMEM0 = 1, KID_LARGE = 7, KID_SCAN_SUMS = 8, KID_SCAN_TILES = 9, KID_SCAN_ROWS = 10,
   KID_GATHER = 11, KID_GENE_EQC = 12, KID_GENE_EQC_BIG = 13, KID_BIN_GE = 14, KID_REGION = 15, KID_NA_OFFSETS = 16, KID_UNPACK24 = 17,
-  KID_PUG_SMEM0 = 18, NUM_KID = 22
+  KID_PUG_SMEM0 = 18, KID_PUG_REGION = 22, NUM_KID = 23
 };
 static const char* const KID_NAMES[NUM_KID] = {
     "k_bin_cells", "k_resolve_smem<0>", "k_resolve_smem<1>", "k_resolve_smem<2>", "k_resolve_smem<3>",
     "k_resolve_smem<4>", "k_resolve_smem<5>", "k_resolve_large", "k_scan_tile_sums", "k_scan_tiles",
     "k_scan_rows", "k_gather_rows", "k_gene_eqc", "k_gene_eqc(big cells)", "k_bin_cells_ge", "resolve_region(wall)",
-    "k_na_offsets(+tile sums)", "k_unpack24", "k_pug_smem<0>", "k_pug_smem<1>", "k_pug_smem<2>", "k_pug_smem<3>(global arena)"};
+    "k_na_offsets(+tile sums)", "k_unpack24", "k_pug_smem<0>", "k_pug_smem<1>", "k_pug_smem<2>", "k_pug_smem<3>(global arena)", "pug_region(wall)"};
 
 struct PipeBufs {  // device scratch owned by the caller (one set per stream-ordered pipeline)
   Ctl* ctl;
@@ -79,7 +80,7 @@ inline void launch_crlike_bins(L& l, const KArgs& a, const PipeBufs& pb) {
   l.lane(0); launch_smem_bin<0>(l, a);
   l.join();
   l.launch(KID_LARGE, k_resolve_large, pb.large_blocks, 1024u, (size_t)0, a, (u32)OVF_LIST);
-  l.region_end();
+  l.region_end(KID_REGION);
 }
 
 // 24-bit packed wire array -> u32 (dst must be 16-byte aligned with room for n values)
@@ -173,18 +174,24 @@ int enqueue_batch(L& l, const afq_config& cfg, int force_bin, const PipeBufs& pb
     g.adj_pool = l.adj_pool(g.adj_cap);
     g.adj_used = (u64*)&pb.ctl->adj_used;
     if (!g.adj_pool) { err = "adjacency pool allocation failed"; return AFQ_ERR_CUDA; }
+    // the arena variants of k_pug_smem are independent of each other (cells they cannot finish go to k_gene_eqc's
+    // list, drained afterwards): forked onto lanes like the cr-like arenas so that every persistent kernel's tail
+    // overlaps the others instead of idling the chip (14.5 + 7.3 + 10.3 + 5.5 ms back to back)
     u32 ps_cells = 0;
+    l.region_begin();
+    l.fork(PS_VARIANTS);
     for (int v = PS_VARIANTS - 1; v >= 0; --v) {   // biggest cells first
       const u32 cnt = h.bin_count[PS_LIST0 + v];
       if (!cnt) continue;
       ps_cells += cnt;
       u32 blocks = (u32)l.ps_grid(v);
       if (blocks > cnt) blocks = cnt;
+      l.lane(v);
       if (v == 3) {
         const u64 words = ps_global_words(h.ps3_max_n, h.ps3_max_p, cfg.num_rows);   // (< 2^32: P < 2^30 on this list)
         g.ps_garena = l.ps_garena(words, blocks);
         g.ps_garena_words = (u32)words;
-        if (!g.ps_garena) { err = "k_pug_smem global arena allocation failed"; return AFQ_ERR_CUDA; }
+        if (!g.ps_garena) { l.join(); err = "k_pug_smem global arena allocation failed"; return AFQ_ERR_CUDA; }
         l.launch(KID_PUG_SMEM0 + 3, k_pug_smem<3>, blocks, ps_threads(3), (size_t)0, a, g);
         continue;
       }
@@ -193,6 +200,8 @@ int enqueue_batch(L& l, const afq_config& cfg, int force_bin, const PipeBufs& pb
       else if (v == 1) l.launch(KID_PUG_SMEM0 + 1, k_pug_smem<1>, blocks, ps_threads(1), smem, a, g);
       else l.launch(KID_PUG_SMEM0 + 2, k_pug_smem<2>, blocks, ps_threads(2), smem, a, g);
     }
+    l.join();
+    l.region_end(KID_PUG_REGION);
     for (int which = 0; which < 2; ++which) {
       const int list = which == 0 ? GE_LIST_BIG : GE_LIST_NORMAL;
       const u32 cells = h.bin_count[list] + (which == 1 ? ps_cells : 0u);   // upper bound: every k_pug_smem cell may come back

@@ -43,11 +43,23 @@ namespace afq {
 constexpr int PS_VARIANTS = 4;       // arenas: 72 KB x 3 CTAs/SM, 108 KB x 2, 224 KB x 1 of shared memory; variant 3 = the same
                                      // code on a per-CTA GLOBAL-memory arena (L2-resident) for cells beyond 224 KB
 constexpr int PS_SMEM_VARIANTS = 3;
-__host__ __device__ constexpr u32 ps_threads(int v) { return v == 0 ? 256u : (v == 1 ? 512u : (v == 2 ? 1024u : 512u)); }
 #ifndef AFQ_PS_V0_KWORDS
 #define AFQ_PS_V0_KWORDS 18
 #define AFQ_PS_V0_BLOCKS 3
 #endif
+#ifndef AFQ_PS_V0_THREADS
+#define AFQ_PS_V0_THREADS 256
+#endif
+#ifndef AFQ_PS_V1_THREADS
+#define AFQ_PS_V1_THREADS 512
+#endif
+#ifndef AFQ_PS_V2_THREADS
+#define AFQ_PS_V2_THREADS 1024
+#endif
+#ifndef AFQ_PS_V3_THREADS
+#define AFQ_PS_V3_THREADS 512
+#endif
+__host__ __device__ constexpr u32 ps_threads(int v) { return v == 0 ? (u32)AFQ_PS_V0_THREADS : (v == 1 ? (u32)AFQ_PS_V1_THREADS : (v == 2 ? (u32)AFQ_PS_V2_THREADS : (u32)AFQ_PS_V3_THREADS)); }
 __host__ __device__ constexpr u32 ps_arena_words(int v) { return v == 0 ? AFQ_PS_V0_KWORDS * 1024u : (v == 1 ? 27u * 1024u : 56u * 1024u); }
 __host__ __device__ constexpr u32 ps_min_blocks(int v) { return v == 0 ? (u32)AFQ_PS_V0_BLOCKS : (v == 1 ? 2u : (v == 2 ? 1u : 2u)); }
 constexpr u32 PS_WSCR_WORDS = 64 + 256; // per-warp scratch of the warp-cooperative cover (members, masks, 16 x 16 label masks)
@@ -103,7 +115,15 @@ struct PsExtra {
   u32 n_win;      // winners (unique-only resolutions)
   u32 szc[SMALL_COMP + 4];   // multi-vertex components per size (counting sort of their roots)
   u32 n_over;     // components of <= 8 vertices re-routed to the warp-cooperative cover (a label > 32 transcripts)
+  u32 next_w, next_g;   // cover work queues: warp-form components / group passes handed out to the warps
 };
+
+// all lanes of a warp call: the warp claims the next item of a shared-memory work counter
+__device__ __forceinline__ u32 warp_claim(u32* counter) {
+  u32 it = 0;
+  if (lane_id() == 0) it = atomicAdd(counter, 1u);
+  return __shfl_sync(0xFFFFFFFFu, it, 0);
+}
 
 // all 32 lanes of the warp call; lanes with pred get consecutive indices from *counter
 __device__ __forceinline__ u32 warp_bump(u32* counter, bool pred) {
@@ -322,11 +342,9 @@ __device__ __forceinline__ void ps_emit_mcc(const PsCell& c, const PsSink& sk, u
 // Components with a label longer than 32 transcripts are appended to `olist` for the warp form.
 template <int G>
 __device__ inline void ps_cover_group(const PsCell& c, const PsSink& sk, u32* winners, u32* gbm, const u32* head, const u32* nxt,
-                                      const u32* clist, u32 k0, u32 k1, bool exact, u32* olist, u32* n_over) {
+                                      const u32* clist, u32 kb, u32 k1, bool exact, u32* olist, u32* n_over) {
   const u32 lane = lane_id(), sub = lane % G, gbase = lane - sub;
-  const u32 wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  constexpr u32 PER = 32 / G;
-  for (u32 kb = k0 + wid * PER; kb < k1; kb += nw * PER) {     // warp-uniform
+  {     // one warp pass: components clist[kb .. kb + 32/G) (warp-uniform kb; the caller hands out the passes)
     const u32 k = kb + lane / G;
     const bool valid = k < k1;
     const u32 r = valid ? clist[k] : 0u;
@@ -697,7 +715,7 @@ __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A
   // ---- compaction: table slots -> dense vertices (appended behind the table) ----------------------
   u32 V;
   {
-    const u32 K = (TN + T - 1) / T;
+    const u32 K = ((TN + T - 1) / T) | 1u;        // odd chunk length: the threads' strided reads hit distinct banks
     u32 lo = tid * K; if (lo > TN) lo = TN;
     u32 hi = lo + K; if (hi > TN) hi = TN;
     u32 cnt = 0;
@@ -947,21 +965,39 @@ __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A
     __syncthreads();
     // after the scatter szc[z] = END of size z's range
     const u32 K2 = ex->szc[2], K4 = ex->szc[4], K8 = ex->szc[8];
-    if (tid == 0) ex->n_over = 0;
+    if (tid == 0) { ex->n_over = 0; ex->next_w = 0; ex->next_g = 0; }
     __syncthreads();
-    ps_cover_group<2>(c, sk, winners, gbm, head, nxt, clist, 0, K2, g.pug_exact_umi != 0, olist, &ex->n_over);
-    ps_cover_group<4>(c, sk, winners, gbm, head, nxt, clist, K2, K4, g.pug_exact_umi != 0, olist, &ex->n_over);
-    ps_cover_group<8>(c, sk, winners, gbm, head, nxt, clist, K4, K8, g.pug_exact_umi != 0, olist, &ex->n_over);
+    // The cover work is handed out to the warps from two shared-memory queues, most expensive items first
+    // (warp-form components by decreasing size, then passes of the 8-, 4- and 2-lane group form): a static
+    // split left warps 0-3 with three passes and warps 6-7 with one, and the barrier behind the cover held
+    // 20 % of all stall samples (ncu r2a).
+    const bool exact = g.pug_exact_umi != 0;
     const u32 wid = tid >> 5, nw = ncw;
     u32* wmem = wscr + (wid < nw ? wid : 0u) * PS_WSCR_WORDS;
     if (wid < nw)
-      for (u32 k = K - 1 - wid; (int)k >= (int)K8; k -= nw)      // largest components first
-        ps_cover_warp(c, sk, winners, head, nxt, clist[k], g.pug_exact_umi != 0, gbm, wmem, wmem + 32);
+      for (;;) {
+        const u32 it = warp_claim(&ex->next_w);
+        if (it >= K - K8) break;
+        ps_cover_warp(c, sk, winners, head, nxt, clist[K - 1 - it], exact, gbm, wmem, wmem + 32);   // largest components first
+      }
+    const u32 n8 = (K8 - K4 + 3) / 4, n4 = (K4 - K2 + 7) / 8, n2 = (K2 + 15) / 16;
+    for (;;) {
+      const u32 it = warp_claim(&ex->next_g);
+      if (it >= n8 + n4 + n2) break;
+      if (it < n8) ps_cover_group<8>(c, sk, winners, gbm, head, nxt, clist, K4 + it * 4, K8, exact, olist, &ex->n_over);
+      else if (it < n8 + n4) ps_cover_group<4>(c, sk, winners, gbm, head, nxt, clist, K2 + (it - n8) * 8, K4, exact, olist, &ex->n_over);
+      else ps_cover_group<2>(c, sk, winners, gbm, head, nxt, clist, (it - n8 - n4) * 16, K2, exact, olist, &ex->n_over);
+    }
     __syncthreads();
     const u32 KO = ex->n_over;                                   // small components with a long label
-    if (wid < nw)
-      for (u32 k = wid; k < KO; k += nw)
-        ps_cover_warp(c, sk, winners, head, nxt, olist[k], g.pug_exact_umi != 0, gbm, wmem, wmem + 32);
+    if (tid == 0) ex->next_w = 0;
+    __syncthreads();
+    if (KO && wid < nw)
+      for (;;) {
+        const u32 it = warp_claim(&ex->next_w);
+        if (it >= KO) break;
+        ps_cover_warp(c, sk, winners, head, nxt, olist[it], exact, gbm, wmem, wmem + 32);
+      }
   }
   }
   __syncthreads();
@@ -997,7 +1033,7 @@ __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A
     u32* gpre = gbm + Wg;
     u32* gcnt = utab;                  // [nnz <= m <= V] (lists are dead)
     {
-      const u32 Kw = (Wg + T - 1) / T;
+      const u32 Kw = ((Wg + T - 1) / T) | 1u;      // (odd: conflict-free)
       u32 lo = tid * Kw; if (lo > Wg) lo = Wg;
       u32 hi = lo + Kw; if (hi > Wg) hi = Wg;
       u32 cnt = 0;

@@ -21,6 +21,15 @@ class _Opts(C.Structure):
                 ("cmdline", C.c_char_p), ("version", C.c_char_p), ("device", C.c_int32), ("batch_records", C.c_uint64)]
 
 
+class RadInfo(C.Structure):
+    _fields_ = [("n_refs", C.c_uint64), ("num_chunks", C.c_uint64), ("n_records", C.c_uint64), ("n_alignments", C.c_uint64),
+                ("sum_bc", C.c_uint64), ("sum_umi", C.c_uint64), ("sum_refs", C.c_uint64),
+                ("bc_len", C.c_uint32), ("umi_len", C.c_uint32),
+                ("read_bytes", C.c_uint32), ("aln_bytes", C.c_uint32), ("bc_size", C.c_uint32), ("umi_size", C.c_uint32),
+                ("bc_off", C.c_uint32), ("umi_off", C.c_uint32), ("refid_off", C.c_uint32),
+                ("n_file_tags", C.c_uint32), ("n_read_tags", C.c_uint32), ("n_aln_tags", C.c_uint32)]
+
+
 _lib = None
 
 
@@ -35,6 +44,8 @@ def lib():
         l.afqh_snappy_framed_decompress.restype = C.c_int
         l.afqh_snappy_framed_decompress.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_uint32,
                                                     C.c_char_p, C.c_size_t]
+        l.afqh_rad_summary.restype = C.c_int
+        l.afqh_rad_summary.argtypes = [C.c_char_p, C.POINTER(RadInfo), C.c_char_p, C.c_size_t]
         l.afqh_free.restype = None
         l.afqh_free.argtypes = [C.c_void_p]
         l.afqh_write_collated_rad.restype = C.c_int
@@ -59,6 +70,15 @@ def quantify(input_dir, tg_map, output_dir, resolution, num_threads=2, small_thr
     rc = lib().afqh_quantify(C.byref(o), err, 2048)
     if rc != 0:
         raise RuntimeError(err.value.decode(errors="replace"))
+
+
+def rad_summary(path) -> RadInfo:
+    """CPU-only probe of a collated RAD file through the quantifier's own prelude / layout / chunk-walk code."""
+    info = RadInfo()
+    err = C.create_string_buffer(1024)
+    if lib().afqh_rad_summary(os.fsencode(path), C.byref(info), err, 1024) != 0:
+        raise RuntimeError(err.value.decode(errors="replace"))
+    return info
 
 
 def make_barcodes(first_cell, n_cells, bc_len=16):

@@ -920,6 +920,56 @@ int afqh_write_collated_rad(const char* dir, uint64_t n_cells, const uint64_t* c
   return 0;
 }
 
+int afqh_rad_summary(const char* rad_path, afqh_rad_info* info, char* err, size_t errlen) {
+  auto fail = [&](const std::string& m) { if (err && errlen) { strncpy(err, m.c_str(), errlen - 1); err[errlen - 1] = 0; } return 1; };
+  if (!rad_path || !info) return fail("null argument");
+  memset(info, 0, sizeof(*info));
+  FILE* f = fopen(rad_path, "rb");
+  if (!f) return fail(std::string("cannot open ") + rad_path);
+  Reader rd(f);
+  RadPrelude pre;
+  std::string perr;
+  if (!parse_prelude(rd, pre, perr)) { fclose(f); return fail("RAD prelude: " + perr); }
+  RecordLayout lay;
+  if (!make_layout(pre, lay, perr)) { fclose(f); return fail(perr); }
+  info->n_refs = pre.ref_names.size(); info->num_chunks = pre.num_chunks;
+  const TagValue* cbl = pre.file_tag("cblen");
+  const TagValue* ul = pre.file_tag("ulen");
+  info->bc_len = cbl ? (uint32_t)cbl->u : 0; info->umi_len = ul ? (uint32_t)ul->u : 0;
+  info->read_bytes = (uint32_t)lay.read_bytes; info->aln_bytes = (uint32_t)lay.aln_bytes;
+  info->bc_size = (uint32_t)lay.bc_size; info->umi_size = (uint32_t)lay.umi_size;
+  info->bc_off = (uint32_t)lay.bc_off; info->umi_off = (uint32_t)lay.umi_off; info->refid_off = (uint32_t)lay.refid_off;
+  info->n_file_tags = (uint32_t)pre.file_tags.size(); info->n_read_tags = (uint32_t)pre.read_tags.size();
+  info->n_aln_tags = (uint32_t)pre.aln_tags.size();
+  uint64_t hb = 0xCBF29CE484222325ull, hu = hb, hr = hb;
+  auto mix = [](uint64_t& h, uint64_t v) { h = (h ^ v) * 0x100000001B3ull; };
+  std::vector<unsigned char> buf;
+  for (uint64_t ch = 0; ch < pre.num_chunks; ++ch) {
+    uint32_t nbytes, nrec;
+    if (!rd.get(nbytes) || !rd.get(nrec) || nbytes < 8) { fclose(f); return fail("truncated or corrupt chunk header"); }
+    buf.resize(nbytes - 8);
+    if (!rd.read(buf.data(), buf.size())) { fclose(f); return fail("truncated chunk body"); }
+    const unsigned char* p = buf.data();
+    const unsigned char* end = p + buf.size();
+    for (uint32_t r = 0; r < nrec; ++r) {
+      if (p + 4 + lay.read_bytes > end) { fclose(f); return fail("record overruns its chunk"); }
+      uint32_t na; memcpy(&na, p, 4); p += 4;
+      uint64_t bc = 0, um = 0;
+      memcpy(&bc, p + lay.bc_off, lay.bc_size); memcpy(&um, p + lay.umi_off, lay.umi_size);
+      p += lay.read_bytes;
+      if (p + (size_t)na * lay.aln_bytes > end) { fclose(f); return fail("record overruns its chunk"); }
+      mix(hb, bc); mix(hu, um);
+      for (uint32_t a = 0; a < na; ++a) { uint32_t id; memcpy(&id, p + lay.refid_off, 4); p += lay.aln_bytes; mix(hr, id & 0x7FFFFFFFu); }
+      info->n_alignments += na;
+    }
+    if (p != end) { fclose(f); return fail("chunk size does not match its records"); }
+    info->n_records += nrec;
+  }
+  fclose(f);
+  info->sum_bc = hb; info->sum_umi = hu; info->sum_refs = hr;
+  return 0;
+}
+
 int afqh_snappy_framed_decompress(const uint8_t* src, size_t n, uint8_t** out, size_t* out_len, uint32_t n_threads,
                                   char* err, size_t errlen) {
   std::vector<unsigned char> buf;

@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument("--e2e-batches", type=int, default=8, help="host batches per e2e step (pipelined)")
     ap.add_argument("--cpu-sample-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--others", default="C3,C4,C5", help="configurations measured after the default C2 headline (other_configs)")
+    ap.add_argument("--no-others", action="store_true", help="measure the headline configuration only")
     ap.add_argument("--e2e-offsets", action="store_true",
                     help="e2e: ship 4-byte rec_ref_offsets instead of the 1-byte rec_na8 alignment counts")
     ap.add_argument("--e2e-u32", action="store_true",
@@ -109,80 +111,97 @@ def algorithmic_bytes(batch, nnz):
     return n_in + n_out
 
 
-def run_reference(args, spec, cells, res, emit):
-    """--impl reference: the reference's CPU algorithm (oracle port) on all host cores."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
+def build_hash():
+    """sha256 (16 hex) over the CUDA sources libafq.so is built from: ties profiles/ncu_traffic.json to a build."""
+    import glob
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(ROOT, "alevin_fry_b200", "csrc", "*"))):
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
+def workload_config(synth, name, spec, cells, res, world, rank=0):
+    """The `config` object of the JSON line — identical keys and values on both arms (the sizes come from the
+    generator's size pass, which costs a fraction of a second and needs no GPU)."""
+    n_rec, n_ref = synth.sizes(spec, rank * cells, cells)
+    return {"workload": CONFIGS[name][2], "resolution": res, "cells_per_gpu": cells, "records_per_gpu": n_rec,
+            "refs_per_gpu": n_ref, "parallelism": f"cell-sharded x{world}",
+            "l2_policy": "inputs (%.1f GB/GPU) larger than L2 (126 MB); no flush needed" % ((8 * n_rec + 4 * n_ref) / 1e9),
+            "seed": spec.seed}
+
+
+def reference_leg(args, name, cells, res, steps, warmup, step_seconds):
+    """The reference's CPU algorithm (oracle port) on all host cores, on a bounded sample of config `name`."""
     import oracle_lib
-    from alevin_fry_b200 import QuantOpts, synth
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+    from alevin_fry_b200 import QuantOpts
+    import synth
+    spec = synth.config_spec(name)
     cores = os.cpu_count() or 1
     t2g = synth.tid_to_gid(spec)
     opts = QuantOpts(resolution=res, usa_mode=spec.usa_mode, num_gene_ids=spec.num_gene_ids, num_rows=spec.num_rows)
-    probe = synth.generate(spec, 0, min(cells, 512))
+    probe = synth.generate(spec, 0, min(cells, 2048))
+    oracle_lib.oracle_quant(opts, t2g, probe.slice_cells(0, min(64, probe.n_cells)), n_threads=cores)   # thread start-up
     t0 = time.perf_counter(); oracle_lib.oracle_quant(opts, t2g, probe, n_threads=cores); dt = time.perf_counter() - t0
     rate = probe.n_cells / dt
-    total = args.steps + args.warmup
-    n_sample = int(max(256, min(cells, rate * min(8.0, 150.0 / max(total, 1)))))
+    n_sample = int(max(256, min(cells, rate * step_seconds)))
     sample = synth.generate(spec, 0, n_sample)
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         oracle_lib.oracle_quant(opts, t2g, sample, n_threads=cores)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         oracle_lib.oracle_quant(opts, t2g, sample, n_threads=cores)
-    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
     v = n_sample / dt
-    desc = f"first {n_sample} cells ({sample.n_records} records) of the workload per step"
-    emit({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": "cells/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u32", "data": "synthetic",
-        "config": {"workload": CONFIGS[args.config][2], "resolution": res, "cells_per_step": n_sample},
+    desc = f"first {n_sample} cells ({sample.n_records} records) of the workload per step, {steps} steps after {warmup} warm-up"
+    return {
+        "value": v, "unit": "cells/s", "ms_per_step": dt * 1e3,
+        "config": workload_config(synth, name, spec, cells, res, args.gpus),
         "cpu_baseline": {"value": v, "unit": "cells/s", "cores": cores, "kind": "port", "sample": desc,
                          "note": "C++ restatement of the reference's Rust algorithm (reference not buildable here: no cargo/rustc)"},
         "e2e": {"value": v, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    })
+    }
 
 
-def main():
-    args = parse_args()
-    # the contract is ONE JSON line on stdout: route everything else (NCCL banners, library chatter)
-    # to stderr until the line is printed
-    sys.stdout.flush()
-    _real_stdout = os.dup(1)
-    os.dup2(2, 1)
+def run_reference(args, names, emit):
+    """--impl reference: rank 0 alone runs; the headline config with the requested steps, the other configs briefly."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    total = args.steps + args.warmup
+    legs = {}
+    for i, name in enumerate(names):
+        cells, res = CONFIGS[name][0], CONFIGS[name][1]
+        if args.cells:
+            cells = args.cells
+        if args.resolution and i == 0:
+            res = args.resolution
+        if i == 0:
+            legs[name] = reference_leg(args, name, cells, res, args.steps, args.warmup, min(8.0, 150.0 / max(total, 1)))
+        else:
+            legs[name] = reference_leg(args, name, cells, res, 2, 1, 5.0)
+    hl = legs[names[0]]
+    line = {"impl": "reference", "metric": METRIC, "value": hl["value"], "unit": "cells/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": hl["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic", "config": hl["config"], "cpu_baseline": hl["cpu_baseline"], "e2e": hl["e2e"]}
+    if len(names) > 1:
+        line["other_configs"] = {n: legs[n] for n in names[1:]}
+    emit(line)
 
-    def emit(obj):
-        sys.stdout.flush()
-        os.dup2(_real_stdout, 1)
-        print(json.dumps(obj), flush=True)
-        os.dup2(2, 1)
-    from alevin_fry_b200 import synth
-    cells, res, desc = CONFIGS[args.config]
-    if args.cells:
-        cells = args.cells
-    if args.resolution:
-        res = args.resolution
-    spec = synth.config_spec(args.config)
-    if args.impl == "reference":
-        return run_reference(args, spec, cells, res, emit)
 
+def measure_config(args, name, cells, res, ctx):
+    """One configuration on this rank's GPU: device-resident value, e2e through the host C-ABI, roofline of the
+    per-cell resolve family, CPU baseline (rank 0, N=1). Returns the dict that becomes the line / an other_configs entry."""
     import numpy as np
     import torch
     import torch.distributed as dist
     from alevin_fry_b200 import QuantOpts, Quantifier
+    import synth
     from alevin_fry_b200.hostmem import PinnedPool
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (the afq product path has no CPU fallback)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    world, rank, local, dev = ctx["world"], ctx["rank"], ctx["local"], ctx["dev"]
+    steps, warmup = ctx["steps"], ctx["warmup"]
+    spec = synth.config_spec(name)
+    desc = CONFIGS[name][2]
 
     # ---- synthetic workload: this rank's shard of cells, generated into pinned host memory ----
     pool = PinnedPool()
@@ -239,7 +258,7 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident timing --------------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warmup):
         step_device()
     nnz = q.device_finish(stream, do["row_ptr"])
     q.set_profiling(True)
@@ -251,12 +270,12 @@ def main():
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step_device()
     e1.record()
     barrier()
-    ms = e0.elapsed_time(e1) / args.steps
-    launches = (q.launch_count - launches0) // max(args.steps, 1)
+    ms = e0.elapsed_time(e1) / steps
+    launches = (q.launch_count - launches0) // max(steps, 1)
     prof = q.profile()
     q.set_profiling(False)
     q.device_finish(stream)
@@ -290,14 +309,14 @@ def main():
             n_c, n_z = q.wait(t, copy=False)
             d2h += 8 * (n_c + 1) + 17 * n_c + 8 * n_z
         return d2h
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warmup):
         d2h = step_e2e()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         d2h = step_e2e()
     barrier()
-    e2e_s = (time.perf_counter() - t0) / args.steps
+    e2e_s = (time.perf_counter() - t0) / steps
     if world > 1:
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -306,34 +325,43 @@ def main():
 
     # ---- roofline of the dominant kernel family (per-cell resolve) -----------------------------
     fam = {k: v for k, v in prof.items() if k.startswith(("k_resolve", "k_gene_eqc", "k_pug_smem"))}
-    fam_ms = sum(v[0] for v in fam.values()) / args.steps
+    fam_ms = sum(v[0] for v in fam.values()) / steps
     region = prof.get("resolve_region(wall)")
-    if region:  # arena kernels overlap on lanes: their device time is the wall time of the region;
-        # the gene-eq-class kernels (parsimony / EM resolutions) run behind it, one after the other
-        fam_ms = (region[0] + sum(v[0] for k, v in fam.items() if k.startswith(("k_gene_eqc", "k_pug_smem")))) / args.steps
-    fam_launches = sum(v[1] for v in fam.values()) // max(args.steps, 1)
+    pug_region = prof.get("pug_region(wall)")
+    if region:  # arena kernels overlap on lanes: their device time is the wall time of the region(s)
+        fam_ms = region[0] / steps
+        if pug_region:   # the k_pug_smem variants overlap on lanes too; k_gene_eqc (handed-back cells) runs behind them
+            fam_ms += (pug_region[0] + sum(v[0] for k, v in fam.items() if k.startswith("k_gene_eqc"))) / steps
+        else:
+            fam_ms += sum(v[0] for k, v in fam.items() if k.startswith(("k_gene_eqc", "k_pug_smem"))) / steps
+    fam_launches = sum(v[1] for v in fam.values()) // max(steps, 1)
     abytes = algorithmic_bytes(batch, nnz)
     peak, peak_src = peak_hbm()
     achieved = abytes / (fam_ms * 1e-3) / 1e9 if fam_ms > 0 else 0.0
-    traffic = None
+    traffic, traffic_note = None, "no capture for this configuration"
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(args.config)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        if tj.get("build") == build_hash():
+            traffic = tj.get(name)
+            traffic_note = tj.get("source")
+        else:
+            traffic_note = "profiles/ncu_traffic.json was captured on another build of csrc/ (%s): not reported" % tj.get("build")
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": "per-cell resolve family (k_resolve_smem<*>/k_resolve_large/k_pug_smem<*>/k_gene_eqc), %d launches/step" % fam_launches,
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "algorithmic_bytes_per_step": abytes, "kernel_ms_per_step": fam_ms, "peak_source": peak_src,
-                "per_kernel_ms": {k: v[0] / args.steps for k, v in prof.items()}}
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note,
+                "algorithmic_bytes_per_step": abytes, "kernel_ms_per_step": fam_ms, "peak_source": peak_src, "nnz_per_gpu": nnz,
+                "per_kernel_ms": {k: v[0] / steps for k, v in prof.items()}}
 
     # ---- CPU baseline (rank 0, N=1 only): oracle port on a bounded sample of the same workload --
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_lib
         cores = os.cpu_count() or 1
+        budget = ctx["cpu_seconds"]
         probe = parts[0].slice_cells(0, min(parts[0].n_cells, 512))
         t0 = time.perf_counter(); oracle_lib.oracle_quant(opts, t2g, probe, n_threads=cores); dt = time.perf_counter() - t0
-        n_sample = int(max(256, min(parts[0].n_cells, probe.n_cells / dt * args.cpu_sample_seconds)))
+        n_sample = int(max(256, min(parts[0].n_cells, probe.n_cells / dt * budget)))
         # the 512-cell probe is dominated by thread start-up and under-estimates the rate: re-size once so that
         # the timed sample is >= ~20 CPU-seconds of work (and >= 1.5 s of wall time), bounded by the workload
         for attempt in range(2):
@@ -347,25 +375,78 @@ def main():
                "sample": f"first {n_sample} cells ({sample.n_records} records) of the workload, {dt:.1f} s of wall time on {cores} threads",
                "note": "C++ restatement of the reference's Rust algorithm (reference not buildable here: no cargo/rustc)"}
 
-    if rank == 0:
-        total_cells = nc * world
-        emit({
-            "metric": METRIC, "value": total_cells / (ms * 1e-3), "unit": "cells/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": desc, "resolution": res, "cells_per_gpu": nc, "records_per_gpu": batch.n_records,
-                       "refs_per_gpu": batch.n_refs_total, "nnz_per_gpu": nnz, "parallelism": f"cell-sharded x{world}",
-                       "l2_policy": "inputs (%.1f GB/GPU) larger than L2 (126 MB); no flush needed" % ((8 * batch.n_records + 4 * batch.n_refs_total) / 1e9),
-                       "seed": spec.seed},
-            "roofline": roofline, "cpu_baseline": cpu,
-            "e2e": {"value": total_cells / e2e_s, "unit": "cells/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_s * 1e3, "host_batches_per_step": nb,
-                    "input_encoding": ("rec_umi24 + " if use_p24 else "rec_umi32 + ") + ("rec_na8 + " if use_na8 else "rec_ref_offsets + ") +
-                                      ("refs24" if use_p24 else "refs (u32)")},
-            "gpu_launches": int(launches) + 0, "clocks": clocks,
-        })
+    total_cells = nc * world
+    cfg = workload_config(synth, name, spec, cells, res, world, rank)
+    out = {
+        "value": total_cells / (ms * 1e-3), "unit": "cells/s", "ms_per_step": ms, "steps": steps, "warmup": warmup,
+        "config": cfg, "roofline": roofline, "cpu_baseline": cpu,
+        "e2e": {"value": total_cells / e2e_s, "unit": "cells/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_s * 1e3, "host_batches_per_step": nb,
+                "input_encoding": ("rec_umi24 + " if use_p24 else "rec_umi32 + ") + ("rec_na8 + " if use_na8 else "rec_ref_offsets + ") +
+                                  ("refs24" if use_p24 else "refs (u32)")},
+        "gpu_launches": int(launches) + 0, "clocks": clocks,
+    }
     q.close()
+    del db, do, counts_all, parts
     pool.close()
+    torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    args = parse_args()
+    # the contract is ONE JSON line on stdout: route everything else (NCCL banners, library chatter)
+    # to stderr until the line is printed
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(_real_stdout, 1)
+        print(json.dumps(obj), flush=True)
+        os.dup2(2, 1)
+    # the headline configuration first; a default run (C2) also measures the parsimony / EM configurations of
+    # BASELINE.json (configs[2..4]) and reports them under "other_configs" on both arms
+    names = [args.config]
+    if args.config == "C2" and not args.no_others and not args.cells and not args.resolution:
+        names += [n for n in args.others.split(",") if n and n in CONFIGS and n != "C2"]
+    if args.impl == "reference":
+        return run_reference(args, names, emit)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the afq product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    ctx = {"world": world, "rank": rank, "local": local, "dev": dev, "steps": args.steps, "warmup": max(args.warmup, 3),
+           "cpu_seconds": args.cpu_sample_seconds}
+    legs = {}
+    for i, name in enumerate(names):
+        cells, res = CONFIGS[name][0], CONFIGS[name][1]
+        if args.cells:
+            cells = args.cells
+        if args.resolution:
+            res = args.resolution
+        if i > 0:   # the other configurations: 3 warm-up + 3 timed steps, a shorter CPU sample
+            ctx = dict(ctx, steps=min(args.steps, 3), warmup=3, cpu_seconds=min(args.cpu_sample_seconds, 6.0))
+        legs[name] = measure_config(args, name, cells, res, ctx)
+    if rank == 0:
+        hl = legs[names[0]]
+        line = {"metric": METRIC, "value": hl["value"], "unit": "cells/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": hl["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": hl["config"], "roofline": hl["roofline"],
+                "cpu_baseline": hl["cpu_baseline"], "e2e": hl["e2e"], "gpu_launches": hl["gpu_launches"], "clocks": hl["clocks"]}
+        if len(names) > 1:
+            line["other_configs"] = {n: legs[n] for n in names[1:]}
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -46,6 +46,21 @@ int afqh_write_collated_rad(const char* dir, uint64_t n_cells, const uint64_t* c
                             const char* const* ref_names, uint64_t n_refs, uint16_t bc_len,
                             uint16_t umi_len, char* err, size_t errlen);
 
+/* CPU-only probe of a collated RAD file (plain, not .sz): runs the SAME prelude / tag-section / record-layout
+ * code the quantifier uses and walks every chunk and record. Used by the tests to check the reader against
+ * files written byte by byte from the reference's own statements (src/convert.rs:92-144, 254, 280-383,
+ * 472-491) instead of against this repo's writer. Checksums: h = (h ^ value) * 0x100000001B3 over the values
+ * in file order, starting from 0xCBF29CE484222325 (barcode of every record, UMI of every record, reference id of
+ * every alignment with the orientation bit cleared).                                          */
+typedef struct afqh_rad_info {
+  uint64_t n_refs, num_chunks, n_records, n_alignments;
+  uint64_t sum_bc, sum_umi, sum_refs;
+  uint32_t bc_len, umi_len;                 /* cblen / ulen file tags (0 if absent)             */
+  uint32_t read_bytes, aln_bytes, bc_size, umi_size, bc_off, umi_off, refid_off;
+  uint32_t n_file_tags, n_read_tags, n_aln_tags;
+} afqh_rad_info;
+int afqh_rad_summary(const char* rad_path, afqh_rad_info* info, char* err, size_t errlen);
+
 /* Snappy FRAMING format (map.collated.rad.sz of `collate --compress`; the reference reads it with
  * snap::read::FrameDecoder, src/quant.rs:373-395) -> plain bytes. *out is malloc'ed (free with
  * afqh_free). Returns 0 on success.                                                          */

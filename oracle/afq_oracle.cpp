@@ -27,6 +27,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <iterator>
 #include <map>
 #include <string>
 #include <thread>
@@ -911,6 +912,204 @@ void quant_cell(const CellView& c, const u32* t2g, const Cfg& cfg, CellOut& o) {
   for (float v : o.val) if (v > mean_expr) ++o.num_over_mean;
 }
 
+// ---------------------------------------------------------------------------------
+// TIE CENSUS: how much of a parsimony result can depend on the order in
+// which the cover loop visits start vertices — the one place where the reference follows
+// ahash/hashbrown iteration order (src/pugutils.rs:1090-1093, 1110) and this repo a canonical
+// order. In one round of the loop (src/pugutils.rs:1097-1145) the winner is the FIRST visited
+// vertex whose largest MCC has the maximal size; a round is order-free iff every maximal
+// candidate yields the same vertex set. If every round along the canonical path is order-free,
+// every visiting order takes the same path (exact criterion, "tie_path"). For components that do
+// see a tie, every distinct choice is explored (memoised over the uncovered set) and the
+// component is "label sensitive" iff two orders end in different gene-label multisets, and
+// "count sensitive" iff they differ in the single-gene labels (what unique-only counting sees).
+// ---------------------------------------------------------------------------------
+enum { TC_CELLS = 0, TC_MOLECULES, TC_COMPS_MULTI, TC_COMPS_TIE_PATH, TC_COMPS_LABEL_SENS, TC_COMPS_CAPPED,
+       TC_MOL_LABEL_SENS, TC_CELLS_LABEL_SENS, TC_COMPS_COUNT_SENS, TC_MOL_COUNT_SENS, TC_CELLS_COUNT_SENS,
+       TC_MOL_TIE_PATH, TC_MOL_CHANGED_WORST, TC_N };
+
+struct TieExplorer {
+  const Pug& g; const EqMap& m; const u32* t2g;
+  std::vector<uint8_t>& uncovered; std::vector<u32>& visited_stamp; u32& stamp;
+  const std::vector<u32>& comp;                       // canonical order, <= 64 vertices
+  TieExplorer(const Pug& g_, const EqMap& m_, const u32* t, std::vector<uint8_t>& unc, std::vector<u32>& vs, u32& st,
+              const std::vector<u32>& comp_) : g(g_), m(m_), t2g(t), uncovered(unc), visited_stamp(vs), stamp(st), comp(comp_) {}
+  std::map<Label, u32> label_ids;                     // gene label -> small id
+  std::vector<uint8_t> label_single;                  // id -> label has exactly one gene
+  std::map<u64, std::vector<std::vector<u32>>> memo;  // uncovered mask -> possible outcomes (sorted label-id lists)
+  size_t budget = 20000;                              // explored (state, choice) pairs before giving up
+  bool capped = false, tie_on_canonical_path = false;
+  std::vector<u32> cand;
+
+  u32 label_of(u64 mask) {
+    std::vector<u32> txps;
+    bool first = true;
+    for (u32 i = 0; i < comp.size(); ++i) {
+      if (!((mask >> i) & 1)) continue;
+      const u32 e = g.node_eq[comp[i]];
+      const u32* lb = m.label(e);
+      const u32 ln = m.label_len(e);
+      if (first) { txps.assign(lb, lb + ln); first = false; }
+      else {
+        std::vector<u32> keep;
+        for (u32 t : txps) if (std::binary_search(lb, lb + ln, t)) keep.push_back(t);
+        txps.swap(keep);
+      }
+    }
+    Label genes;
+    for (u32 t : txps) genes.push_back(m.gene_level ? t : t2g[t]);
+    std::sort(genes.begin(), genes.end());
+    genes.erase(std::unique(genes.begin(), genes.end()), genes.end());
+    auto it = label_ids.find(genes);
+    if (it != label_ids.end()) return it->second;
+    const u32 id = (u32)label_ids.size();
+    label_ids.emplace(genes, id);
+    label_single.push_back(genes.size() == 1);
+    return id;
+  }
+  // distinct maximal MCCs of the state, in canonical start-vertex order
+  std::vector<u64> choices(u64 U) {
+    for (u32 i = 0; i < comp.size(); ++i) uncovered[comp[i]] = (U >> i) & 1;
+    std::vector<u64> masks;
+    std::vector<u32> sizes;
+    u32 best = 0;
+    for (u32 i = 0; i < comp.size(); ++i) {
+      if (!((U >> i) & 1)) continue;
+      u32 txp;
+      collapse_vertices(comp[i], uncovered, g, m, visited_stamp, stamp, cand, txp);
+      u64 mk = 0;
+      for (u32 v : cand) mk |= 1ull << (u32)(std::find(comp.begin(), comp.end(), v) - comp.begin());
+      masks.push_back(mk);
+      sizes.push_back((u32)cand.size());
+      best = std::max(best, (u32)cand.size());
+    }
+    std::vector<u64> out;
+    for (size_t k = 0; k < masks.size(); ++k)
+      if (sizes[k] == best && std::find(out.begin(), out.end(), masks[k]) == out.end()) out.push_back(masks[k]);
+    for (u32 i = 0; i < comp.size(); ++i) uncovered[comp[i]] = 0;
+    return out;
+  }
+  const std::vector<std::vector<u32>>& outcomes(u64 U, bool on_canonical_path) {
+    auto it = memo.find(U);
+    if (it != memo.end() && !on_canonical_path) return it->second;
+    std::vector<std::vector<u32>> res;
+    if (U == 0) res.push_back({});
+    else {
+      const std::vector<u64> ch = choices(U);
+      if (on_canonical_path && ch.size() > 1) tie_on_canonical_path = true;
+      for (size_t k = 0; k < ch.size() && !capped; ++k) {
+        if (budget == 0) { capped = true; break; }
+        --budget;
+        const u32 lid = label_of(ch[k]);
+        for (const auto& rest : outcomes(U & ~ch[k], on_canonical_path && k == 0)) {
+          std::vector<u32> o = rest;
+          o.insert(std::upper_bound(o.begin(), o.end(), lid), lid);
+          if (std::find(res.begin(), res.end(), o) == res.end()) res.push_back(std::move(o));
+          if (res.size() > 512) { capped = true; break; }
+        }
+      }
+    }
+    return memo[U] = std::move(res);
+  }
+};
+
+void tie_census_cell(const CellView& c, const u32* t2g, const Cfg& cfg, u64* tc) {
+  const bool tiny_eligible = cfg.sa_model == AFQ_SA_WINNER_TAKE_ALL;
+  if (tiny_eligible && c.nrec < cfg.small_thresh) return;
+  const int res = cfg.resolution;
+  EqMap m;
+  if (res == AFQ_RES_PARSIMONY_GENE || res == AFQ_RES_PARSIMONY_GENE_EM) m.init_from_chunk_gene_level(c, t2g);
+  else m.init_from_chunk(c);
+  Pug g;
+  extract_graph(m, cfg.pug_exact_umi != 0, g);
+  const u32 nv = (u32)g.node_eq.size();
+  UnionFind uf(nv);
+  for (auto& e : g.undirected) uf.unite(e.first, e.second);
+  const u32 neq = (u32)m.num();
+  std::vector<u32> order(neq), rank(neq);
+  for (u32 e = 0; e < neq; ++e) order[e] = e;
+  std::sort(order.begin(), order.end(), [&](u32 a, u32 b) {
+    return std::lexicographical_compare(m.label(a), m.label(a) + m.label_len(a), m.label(b), m.label(b) + m.label_len(b));
+  });
+  for (u32 i = 0; i < neq; ++i) rank[order[i]] = i;
+  std::map<u32, std::vector<u32>> comps;
+  for (u32 v = 0; v < nv; ++v) comps[uf.find(v)].push_back(v);
+  std::vector<uint8_t> uncovered(nv, 0);
+  std::vector<u32> visited_stamp(nv, 0);
+  u32 stamp = 0;
+  tc[TC_CELLS] += 1;
+  bool cell_label = false, cell_count = false;
+  for (auto& kv : comps) {
+    auto& comp = kv.second;
+    if (comp.size() == 1) { tc[TC_MOLECULES] += 1; continue; }
+    if (comp.size() > cfg.large_graph_thresh) continue;     // cr-like fallback: order-free
+    tc[TC_COMPS_MULTI] += 1;
+    std::sort(comp.begin(), comp.end(), [&](u32 a, u32 b) {
+      const u32 ra = rank[g.node_eq[a]], rb = rank[g.node_eq[b]];
+      return ra != rb ? ra < rb : g.node_rank[a] < g.node_rank[b];
+    });
+    if (comp.size() > 64) {
+      // beyond the bitmask explorer: only the canonical path is walked; a tie on it counts as sensitive (capped)
+      for (u32 v : comp) uncovered[v] = 1;
+      size_t remaining = comp.size();
+      bool tie = false;
+      u64 mol = 0;
+      std::vector<u32> cand, best;
+      while (remaining) {
+        best.clear();
+        std::vector<std::vector<u32>> maxsets;
+        for (u32 v : comp) {
+          if (!uncovered[v]) continue;
+          u32 txp;
+          collapse_vertices(v, uncovered, g, m, visited_stamp, stamp, cand, txp);
+          std::vector<u32> sset = cand;
+          std::sort(sset.begin(), sset.end());
+          if (cand.size() > best.size()) { best = cand; maxsets.clear(); maxsets.push_back(sset); }
+          else if (cand.size() == best.size() && std::find(maxsets.begin(), maxsets.end(), sset) == maxsets.end()) maxsets.push_back(sset);
+        }
+        if (maxsets.size() > 1) tie = true;
+        for (u32 v : best) uncovered[v] = 0;
+        remaining -= best.size();
+        ++mol;
+      }
+      tc[TC_MOLECULES] += mol;
+      if (tie) {
+        tc[TC_COMPS_TIE_PATH] += 1; tc[TC_MOL_TIE_PATH] += mol;
+        tc[TC_COMPS_LABEL_SENS] += 1; tc[TC_COMPS_CAPPED] += 1; tc[TC_MOL_LABEL_SENS] += mol;
+        tc[TC_COMPS_COUNT_SENS] += 1; tc[TC_MOL_COUNT_SENS] += mol; tc[TC_MOL_CHANGED_WORST] += mol;
+        cell_label = cell_count = true;
+      }
+      continue;
+    }
+    TieExplorer ex(g, m, t2g, uncovered, visited_stamp, stamp, comp);
+    const u64 full = comp.size() == 64 ? ~0ull : ((1ull << comp.size()) - 1);
+    const auto outs = ex.outcomes(full, true);
+    const u64 mol = outs.empty() ? 0 : outs[0].size();      // outs[0] = the canonical path
+    tc[TC_MOLECULES] += mol;
+    if (!ex.tie_on_canonical_path) continue;
+    tc[TC_COMPS_TIE_PATH] += 1; tc[TC_MOL_TIE_PATH] += mol;
+    bool label_sens = ex.capped || outs.size() > 1, count_sens = ex.capped;
+    if (!ex.capped && outs.size() > 1) {
+      auto singles = [&](const std::vector<u32>& o) { std::vector<u32> r; for (u32 id : o) if (ex.label_single[id]) r.push_back(id); return r; };
+      const auto s0 = singles(outs[0]);
+      for (size_t k = 1; k < outs.size(); ++k) if (singles(outs[k]) != s0) { count_sens = true; break; }
+    }
+    // worst case over the visiting orders: molecules of this component whose gene label differs from the canonical result
+    u64 worst = ex.capped ? mol : 0;
+    for (size_t k = 1; k < outs.size() && !ex.capped; ++k) {
+      std::vector<u32> common;
+      std::set_intersection(outs[0].begin(), outs[0].end(), outs[k].begin(), outs[k].end(), std::back_inserter(common));
+      worst = std::max<u64>(worst, std::max(outs[0].size(), outs[k].size()) - common.size());
+    }
+    tc[TC_MOL_CHANGED_WORST] += worst;
+    if (ex.capped) tc[TC_COMPS_CAPPED] += 1;
+    if (label_sens) { tc[TC_COMPS_LABEL_SENS] += 1; tc[TC_MOL_LABEL_SENS] += mol; cell_label = true; }
+    if (count_sens) { tc[TC_COMPS_COUNT_SENS] += 1; tc[TC_MOL_COUNT_SENS] += mol; cell_count = true; }
+  }
+  if (cell_label) tc[TC_CELLS_LABEL_SENS] += 1;
+  if (cell_count) tc[TC_CELLS_COUNT_SENS] += 1;
+}
+
 struct OracleResult {
   std::vector<u64> row_ptr;
   std::vector<u32> col;
@@ -1009,6 +1208,44 @@ int afq_oracle_em_dense(const uint32_t* labels, const uint32_t* starts, uint32_t
   std::vector<float> a;
   em_optimize(g, init_uniform != 0, num_alphas, only_unique != 0, a);
   std::copy(a.begin(), a.end(), out_alphas);
+  return AFQ_OK;
+}
+
+// Tie census of the parsimony cover over a host batch (see tie_census_cell). out[13]:
+// cells analysed (non-tiny), molecules (canonical cover), multi-vertex components, components with a
+// tie on the canonical path, components whose gene-label multiset depends on the visiting order, of
+// those: exploration capped (counted as sensitive), molecules in label-sensitive components, cells
+// with one, components / molecules / cells whose SINGLE-gene labels (unique-only counts) depend on
+// the order, molecules in tie-path components, and the worst case over all orders of the number of
+// molecules whose gene label differs from the canonical result.
+int afq_oracle_tie_census(const afq_config* cfg_in, const uint32_t* tid_to_gid, uint64_t n_refs,
+                          const afq_batch* b, int n_threads, uint64_t* out12) {
+  (void)n_refs;
+  if (!cfg_in || !b || !out12) return AFQ_ERR_INVALID;
+  Cfg cfg{cfg_in->resolution, cfg_in->usa_mode, cfg_in->em_init_uniform, cfg_in->pug_exact_umi,
+          cfg_in->sa_model, cfg_in->num_gene_ids, cfg_in->num_rows, cfg_in->small_thresh,
+          cfg_in->large_graph_thresh};
+  const u64 nc = b->n_cells;
+  if (n_threads < 1) n_threads = 1;
+  std::atomic<u64> next{0};
+  std::vector<std::vector<u64>> part(n_threads, std::vector<u64>(TC_N, 0));
+  auto work = [&](int t) {
+    for (;;) {
+      u64 c0 = next.fetch_add(16);
+      if (c0 >= nc) break;
+      u64 c1 = std::min(nc, c0 + 16);
+      for (u64 c = c0; c < c1; ++c) {
+        u64 r0 = b->cell_rec_offsets[c], r1 = b->cell_rec_offsets[c + 1];
+        CellView cv{r1 - r0, b->rec_umi32 + r0, b->rec_ref_offsets + r0, b->refs};
+        tie_census_cell(cv, tid_to_gid, cfg, part[t].data());
+      }
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < n_threads; ++t) th.emplace_back(work, t);
+  work(0);
+  for (auto& t : th) t.join();
+  for (int k = 0; k < TC_N; ++k) { out12[k] = 0; for (auto& p : part) out12[k] += p[k]; }
   return AFQ_OK;
 }
 

@@ -5,7 +5,8 @@ usage: cli_bench.py [CONFIG=C2] [N_CELLS=20000] [RESOLUTION=cr-like] [REPEATS=3]
 import json, os, shutil, subprocess, sys, tempfile, time
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
-from alevin_fry_b200 import host, synth
+from alevin_fry_b200 import host
+import synth
 
 cfg = sys.argv[1] if len(sys.argv) > 1 else "C2"
 n_cells = int(sys.argv[2]) if len(sys.argv) > 2 else 20000

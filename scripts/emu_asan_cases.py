@@ -6,7 +6,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, 'tests')); sys.path.insert(0, ROOT)
 QUICK = len(sys.argv) > 1 and sys.argv[1] == 'quick'
 import numpy as np, cases, emu_lib, oracle_lib
-from alevin_fry_b200 import CellBatch, QuantOpts, synth
+from alevin_fry_b200 import CellBatch, QuantOpts
+import synth
 import test_emu_parity as T
 def run(o,t2g,b,tag):
     got=emu_lib.emu_quant(o,t2g,b); want=oracle_lib.oracle_quant(o,t2g,b,n_threads=2)

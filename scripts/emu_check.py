@@ -3,7 +3,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 import oracle_lib, emu_lib
-from alevin_fry_b200 import QuantOpts, synth
+from alevin_fry_b200 import QuantOpts
+import synth
 
 def cmp(got, want, tag, exact=True):
     ok = np.array_equal(got.row_ptr, want.row_ptr) and np.array_equal(got.col, want.col)

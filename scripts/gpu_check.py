@@ -5,7 +5,8 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 import torch
 import oracle_lib
-from alevin_fry_b200 import QuantOpts, Quantifier, synth
+from alevin_fry_b200 import QuantOpts, Quantifier
+import synth
 
 def cmp(got, want, tag, exact=True):
     ok = np.array_equal(got.row_ptr, want.row_ptr) and np.array_equal(got.col, want.col)

@@ -1,4 +1,5 @@
-"""Deterministic synthetic collated-cell generator (bench/test infrastructure).
+"""Deterministic synthetic collated-cell generator (bench/test infrastructure — deliberately OUTSIDE the
+product package alevin_fry_b200/).
 
 ctypes wrapper over synth/libafq_synth.so; see synth/afq_synth.cpp for the model and
 SURVEY.md §8(d) for the named configurations C1-C5.
@@ -9,8 +10,8 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from ._abi import REPO_ROOT
-from .quant import CellBatch
+from alevin_fry_b200._abi import REPO_ROOT
+from alevin_fry_b200.quant import CellBatch
 
 SYNTH_LIB_PATH = os.path.join(REPO_ROOT, "synth", "libafq_synth.so")
 GLOBAL_SEED = 20260925
@@ -89,6 +90,18 @@ def tid_to_gid(spec: SynthSpec) -> np.ndarray:
     cs = spec.to_c()
     _synth_lib().afq_synth_t2g(C.byref(cs), t.ctypes.data_as(C.c_void_p))
     return t
+
+
+def sizes(spec: SynthSpec, first_cell: int, n_cells: int, n_threads: int = 0):
+    """(n_records, n_refs_total) of cells [first_cell, first_cell+n_cells) without generating them."""
+    if n_threads <= 0:
+        n_threads = os.cpu_count() or 1
+    cs = spec.to_c()
+    nrec = np.zeros(n_cells, dtype=np.uint64)
+    nref = np.zeros(n_cells, dtype=np.uint64)
+    _synth_lib().afq_synth_sizes(C.byref(cs), first_cell, n_cells, nrec.ctypes.data_as(C.c_void_p),
+                                 nref.ctypes.data_as(C.c_void_p), n_threads)
+    return int(nrec.sum()), int(nref.sum())
 
 
 def generate(spec: SynthSpec, first_cell: int, n_cells: int, n_threads: int = 0, alloc=None) -> CellBatch:

@@ -43,7 +43,7 @@ struct EmuLauncher {
   void lane(int) {}
   void join() {}
   void region_begin() {}
-  void region_end() {}
+  void region_end(int) {}
   u32 need_shift() { const char* s = getenv("AFQ_NEED_SHIFT"); return s ? (u32)atoi(s) : 0; }
   u32* ps_garena(u64 words, u32 blocks) { garena.assign((size_t)words * blocks + 16, 0xCDCDCDCDu); return garena.data(); }
   u32 ps_limit_words() { const char* s = getenv("AFQ_PS_LIMIT_WORDS"); return s ? (u32)atoi(s) : 0; }

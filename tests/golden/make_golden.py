@@ -14,7 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 import oracle_lib  # noqa: E402
-from alevin_fry_b200 import QuantOpts, synth  # noqa: E402
+from alevin_fry_b200 import QuantOpts  # noqa: E402
+import synth  # noqa: E402
 
 ALL_RES = ["trivial", "cr-like", "cr-like-em", "parsimony", "parsimony-em", "parsimony-gene", "parsimony-gene-em"]
 CASES = {

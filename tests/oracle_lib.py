@@ -27,6 +27,8 @@ def lib():
         l.afq_oracle_em_dense.restype = C.c_int
         l.afq_oracle_em_dense.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.c_uint32,
                                           C.c_int, C.c_void_p]
+        l.afq_oracle_tie_census.restype = C.c_int
+        l.afq_oracle_tie_census.argtypes = [C.POINTER(AfqConfig), C.c_void_p, C.c_uint64, C.POINTER(AfqBatch), C.c_int, C.c_void_p]
         l.afq_oracle_hamming.restype = C.c_int
         l.afq_oracle_hamming.argtypes = [C.c_uint64, C.c_uint64]
         _lib = l
@@ -47,6 +49,31 @@ def oracle_quant(opts: QuantOpts, tid_to_gid: np.ndarray, batch: CellBatch, n_th
     out = QuantResult.from_c(r)
     lib().afq_oracle_release(h)
     return out
+
+
+TIE_CENSUS_FIELDS = ("cells", "molecules", "components_multi", "components_tie_on_path", "components_label_sensitive",
+                     "components_capped", "molecules_label_sensitive", "cells_label_sensitive", "components_count_sensitive",
+                     "molecules_count_sensitive", "cells_count_sensitive", "molecules_tie_on_path", "molecules_changed_worst_case")
+
+
+def tie_census(opts: QuantOpts, tid_to_gid: np.ndarray, batch: CellBatch, n_threads: int = 0) -> dict:
+    """How much of a parsimony result can depend on the cover loop's start-vertex order (the reference follows
+    hash-iteration order there, src/pugutils.rs:1090-1110): see tie_census_cell in oracle/afq_oracle.cpp."""
+    if n_threads <= 0:
+        n_threads = os.cpu_count() or 1
+    t2g = np.ascontiguousarray(tid_to_gid, dtype=np.uint32)
+    cfg = opts.to_c()
+    cb = batch.to_c()
+    out = np.zeros(len(TIE_CENSUS_FIELDS), dtype=np.uint64)
+    rc = lib().afq_oracle_tie_census(C.byref(cfg), t2g.ctypes.data_as(C.c_void_p), len(t2g), C.byref(cb), n_threads, out.ctypes.data)
+    assert rc == 0, rc
+    d = {k: int(v) for k, v in zip(TIE_CENSUS_FIELDS, out)}
+    mol = max(d["molecules"], 1)
+    d["frac_molecules_label_sensitive"] = d["molecules_label_sensitive"] / mol
+    d["frac_molecules_count_sensitive"] = d["molecules_count_sensitive"] / mol
+    d["frac_molecules_changed_worst_case"] = d["molecules_changed_worst_case"] / mol
+    d["frac_cells_count_sensitive"] = d["cells_count_sensitive"] / max(d["cells"], 1)
+    return d
 
 
 def _csr(classes):

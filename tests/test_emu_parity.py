@@ -8,7 +8,8 @@ import pytest
 import cases
 import emu_lib
 import oracle_lib
-from alevin_fry_b200 import CellBatch, QuantOpts, synth, FLAG_ALT
+from alevin_fry_b200 import CellBatch, QuantOpts, FLAG_ALT
+import synth
 
 ALL_RES = ["cr-like", "trivial", "parsimony", "parsimony-gene", "cr-like-em", "parsimony-em", "parsimony-gene-em"]
 

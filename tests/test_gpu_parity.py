@@ -7,7 +7,8 @@ import pytest
 
 import cases
 import oracle_lib
-from alevin_fry_b200 import CellBatch, QuantOpts, Quantifier, synth, FLAG_TINY
+from alevin_fry_b200 import CellBatch, QuantOpts, Quantifier, FLAG_TINY
+import synth
 
 pytestmark = pytest.mark.gpu
 
@@ -209,14 +210,19 @@ def test_flat_alignment_loop_shapes(res):
     assert_same(gpu_quant(o, t2g, b), oracle_lib.oracle_quant(o, t2g, b), exact=True, ctx="flat/" + res)
 
 
-@pytest.mark.parametrize("cfg,res,full_cells", [("C2", "cr-like", 100000), ("C3", "parsimony", 60000)])
-def test_full_size_invariants_and_sampled_parity(cfg, res, full_cells):
-    # BASELINE.json configs[1] at its full single-GPU size (100k cells, ~200M records) and half of
-    # configs[2]'s per-GPU share: size-independent properties over every cell, 8 pipelined host batches
-    # with the compact wire arrays vs a one-shot u32 pass, and bit-exact parity with the oracle on samples
+FULL = [("C2", "cr-like", 100000), ("C3", "parsimony", 125000), ("C4", "cr-like-em", 125000), ("C5", "parsimony-em", 100000)]
+
+
+@pytest.mark.parametrize("cfg,res,full_cells", FULL)
+def test_full_size_every_cell_matches_the_oracle(cfg, res, full_cells):
+    # BASELINE.json configs[1..4] at their full single-GPU shares (C2: 100k cells / ~200M reads; C3: 125k = 1M / 8 GPUs;
+    # C4: 125k = 500k / 4 GPUs, USA; C5: 100k, 40 reads/UMI): 8 pipelined host batches with the compact wire arrays;
+    # EVERY cell is compared with the oracle (bit-exact integers; EM values within the north-star 1e-5 relative),
+    # plus the size-independent invariants and a one-shot u32 pass of one part
     spec = synth.config_spec(cfg)
     t2g = synth.tid_to_gid(spec)
-    o = opts_for(spec, res, large_graph_thresh=1000) if res == "parsimony" else opts_for(spec, res)
+    o = opts_for(spec, res)
+    exact = not res.endswith("-em")
     n_cells = int(os.environ.get("AFQ_FULL_CELLS", str(full_cells)))
     part = (n_cells + 7) // 8
     parts = [synth.generate(spec, c0, min(part, n_cells - c0)) for c0 in range(0, n_cells, part)]
@@ -227,10 +233,11 @@ def test_full_size_invariants_and_sampled_parity(cfg, res, full_cells):
             if len(tickets) == 3:
                 rs.append(q.wait(tickets.pop(0)))
         rs += [q.wait(t) for t in tickets]
-        plain = q.quantify_batch(parts[3])            # u32 arrays, one shot
-    assert np.array_equal(plain.col, rs[3].col) and np.array_equal(plain.val, rs[3].val)
+        k1 = min(3, len(parts) - 1)
+        plain = q.quantify_batch(parts[k1])            # u32 arrays, one shot
+    assert np.array_equal(plain.col, rs[k1].col) and np.array_equal(plain.val, rs[k1].val)
     total_nnz = 0
-    for p, r in zip(parts, rs):
+    for k, (p, r) in enumerate(zip(parts, rs)):
         nrec = np.diff(p.cell_rec_offsets.astype(np.int64))
         rp = r.row_ptr.astype(np.int64)
         assert r.n_cells == p.n_cells and rp[-1] == r.nnz
@@ -238,21 +245,18 @@ def test_full_size_invariants_and_sampled_parity(cfg, res, full_cells):
         d = np.diff(r.col.astype(np.int64))
         bad = np.nonzero(d <= 0)[0] + 1
         assert np.isin(bad, rp).all()
-        assert np.all(r.val >= 1) and np.all(r.val == np.floor(r.val))
-        row_sums = np.add.reduceat(r.val.astype(np.float64), rp[:-1][np.diff(rp) > 0]) if r.nnz else np.zeros(0)
-        assert np.array_equal(row_sums, r.sum_umi[np.diff(rp) > 0].astype(np.float64))
-        assert np.all(r.sum_umi <= nrec) and np.all(r.num_expr == np.diff(rp))
-        assert np.all(r.max_umi <= r.sum_umi)
+        assert np.all(r.num_expr == np.diff(rp))
+        assert np.all(r.max_umi <= r.sum_umi * (1 + 1e-6))
+        assert np.all(r.sum_umi <= nrec * (1 + 1e-6))
+        if exact:
+            assert np.all(r.val >= 1) and np.all(r.val == np.floor(r.val))
+            row_sums = np.add.reduceat(r.val.astype(np.float64), rp[:-1][np.diff(rp) > 0]) if r.nnz else np.zeros(0)
+            assert np.array_equal(row_sums, r.sum_umi[np.diff(rp) > 0].astype(np.float64))
         total_nnz += r.nnz
-    assert total_nnz > 100 * n_cells      # ~230 expressed genes per cell at this shape
-    rng = np.random.default_rng(5)
-    for k in rng.choice(len(parts), size=2, replace=False):
-        c0 = int(rng.integers(0, parts[k].n_cells - 150))
-        sub = parts[k].slice_cells(c0, c0 + 150)
-        want = oracle_lib.oracle_quant(o, t2g, sub)
-        lo, hi = int(rs[k].row_ptr[c0]), int(rs[k].row_ptr[c0 + 150])
-        assert np.array_equal(rs[k].col[lo:hi], want.col) and np.array_equal(rs[k].val[lo:hi], want.val)
-        assert np.array_equal(rs[k].sum_umi[c0:c0 + 150], want.sum_umi)
+        p._p24 = None                                   # (free the packed copies before the oracle runs)
+        want = oracle_lib.oracle_quant(o, t2g, p)
+        assert_same(r, want, exact=exact, ctx=f"{cfg}/{res}/part{k}")
+    assert total_nnz > 20 * n_cells
 
 
 # ---- k_pug_smem: the shared-memory kernel of the parsimony family / cr-like-em --------------------

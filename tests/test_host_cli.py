@@ -7,7 +7,8 @@ import numpy as np
 import pytest
 
 import oracle_lib
-from alevin_fry_b200 import QuantOpts, host, synth
+from alevin_fry_b200 import QuantOpts, host
+import synth
 
 
 def make_input(tmp_path, spec, n_cells, first=0):
@@ -174,3 +175,145 @@ def test_cli_reads_snappy_compressed_collated_rad(tmp_path, res):
     host.quantify(str(dz), t2g, str(tmp_path / "fromz"), res)
     for f in ("alevin/quants_mat.mtx", "alevin/quants_mat_rows.txt", "alevin/quants_mat_cols.txt", "featureDump.txt"):
         assert open(tmp_path / "plain" / f, "rb").read() == open(tmp_path / "fromz" / f, "rb").read(), f
+
+
+# ---- the RAD reader against files written from the REFERENCE's byte-level statements ---------
+def _fixture_cells(rng, n_cells, n_refs, bc_len, umi_len, min_recs=3, max_recs=40):
+    cells = []
+    for c in range(n_cells):
+        bc = int(rng.integers(0, 1 << min(2 * bc_len, 62)))
+        recs = []
+        for _ in range(int(rng.integers(min_recs, max_recs))):
+            na = int(rng.integers(1, 5))
+            refs = sorted(set(int(x) for x in rng.integers(0, n_refs, size=na)))
+            recs.append((int(rng.integers(0, 1 << min(2 * umi_len, 62))), refs, [bool(x) for x in rng.integers(0, 2, size=len(refs))]))
+        cells.append((bc, recs))
+    return cells
+
+
+def _expect(cells):
+    import rad_fixture
+    return (rad_fixture.fnv([bc for bc, recs in cells for _ in recs]), rad_fixture.fnv([r[0] for _, recs in cells for r in recs]),
+            rad_fixture.fnv([x for _, recs in cells for r in recs for x in r[1]]),
+            sum(len(recs) for _, recs in cells), sum(len(r[1]) for _, recs in cells for r in recs))
+
+
+@pytest.mark.parametrize("bc_len,umi_len", [(16, 12), (16, 10), (8, 4), (24, 12), (14, 16), (3, 7)])
+def test_rad_reader_on_reference_layout_fixture(tmp_path, bc_len, umi_len):
+    # the plain layout `alevin-fry convert` writes (src/convert.rs:280-383): widths follow the barcode / UMI lengths
+    import rad_fixture
+    rng = np.random.default_rng(bc_len * 100 + umi_len)
+    names = [f"tx{i}" for i in range(37)]
+    cells = _fixture_cells(rng, 9, len(names), bc_len, umi_len)
+    p = str(tmp_path / "map.collated.rad")
+    rad_fixture.write_collated_rad(p, names, cells, bc_len, umi_len)
+    info = host.rad_summary(p)
+    hb, hu, hr, nrec, naln = _expect(cells)
+    size = {"u8": 1, "u16": 2, "u32": 4, "u64": 8}
+    assert (info.n_refs, info.num_chunks, info.n_records, info.n_alignments) == (37, 9, nrec, naln)
+    assert (info.bc_len, info.umi_len) == (bc_len, umi_len)
+    assert info.bc_size == size[rad_fixture.width_type(bc_len)] and info.umi_size == size[rad_fixture.width_type(umi_len)]
+    assert (info.bc_off, info.umi_off, info.read_bytes, info.aln_bytes, info.refid_off) == (0, info.bc_size, info.bc_size + info.umi_size, 4, 0)
+    assert (info.sum_bc, info.sum_umi, info.sum_refs) == (hb, hu, hr)
+
+
+def test_rad_reader_skips_extra_tags_of_every_type(tmp_path):
+    # tags a mapper may add around the standard ones: string / array / float file tags (e.g. `known_rad_type`,
+    # tests/multi_barcode_integration.rs:72-75), extra read-level and alignment-level tags before or after b / u / refid
+    import rad_fixture
+    rng = np.random.default_rng(99)
+    names = [f"gene_{i}" for i in range(12)]
+    cells = _fixture_cells(rng, 5, len(names), 16, 12)
+    hb, hu, hr, nrec, naln = _expect(cells)
+    extra_file = [(("known_rad_type", "string"), "sc_rna_basic"), (("ref_lengths", "array", "u32", "u32"), list(range(12))),
+                  (("frac", "f32"), 0.25), (("scale", "f64"), 2.5), (("flag", "bool"), 1), (("big", "u64"), 1 << 40)]
+    for first in (False, True):
+        p = str(tmp_path / f"extra_{first}.rad")
+        rad_fixture.write_collated_rad(p, names, cells, 16, 12, extra_file_tags=extra_file,
+                                       extra_read_tags=[(("frag_q", "u8"), 7), (("score", "f32"), 1.5)],
+                                       extra_aln_tags=[(("pos", "u32"), 123456), (("mapq", "u16"), 60)], extra_first=first)
+        info = host.rad_summary(p)
+        assert (info.n_file_tags, info.n_read_tags, info.n_aln_tags) == (8, 4, 3)
+        assert (info.n_records, info.n_alignments, info.bc_len, info.umi_len) == (nrec, naln, 16, 12)
+        assert (info.sum_bc, info.sum_umi, info.sum_refs) == (hb, hu, hr)
+        assert (info.bc_off, info.umi_off, info.refid_off) == ((5, 9, 6) if first else (0, 4, 0))
+        assert (info.read_bytes, info.aln_bytes) == (13, 10)
+    # this repo's own writer and the reference-derived writer agree byte for byte on the plain layout
+    spec = synth.SynthSpec(n_genes=4, fixed_reads=5)
+    b, bcs, d, _ = make_input(tmp_path, spec, 3)
+    cells2 = []
+    for c in range(3):
+        r0, r1 = int(b.cell_rec_offsets[c]), int(b.cell_rec_offsets[c + 1])
+        cells2.append((int(bcs[c]), [(int(b.rec_umi32[r]), [int(x) for x in b.refs[b.rec_ref_offsets[r]:b.rec_ref_offsets[r + 1]]]) for r in range(r0, r1)]))
+    p2 = str(tmp_path / "ref_layout.rad")
+    rad_fixture.write_collated_rad(p2, [f"t{i}" for i in range(spec.num_refs)], cells2, 16, spec.umi_len)
+    assert open(p2, "rb").read() == open(os.path.join(d, "map.collated.rad"), "rb").read()
+
+
+def test_rad_reader_rejects_corrupt_files(tmp_path):
+    import rad_fixture
+    rng = np.random.default_rng(5)
+    names = [f"t{i}" for i in range(6)]
+    cells = _fixture_cells(rng, 4, 6, 16, 12)
+    p = str(tmp_path / "ok.rad")
+    n = rad_fixture.write_collated_rad(p, names, cells)
+    raw = open(p, "rb").read()
+    for cut in (n - 1, n - 9, 40, 3):
+        open(tmp_path / "cut.rad", "wb").write(raw[:cut])
+        with pytest.raises(RuntimeError):
+            host.rad_summary(str(tmp_path / "cut.rad"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("res", ["cr-like", "parsimony"])
+def test_cli_on_reference_layout_fixture_with_extra_tags(tmp_path, res):
+    # end to end from a file written by tests/rad_fixture.py (NOT by this repo's writer), with extra tags of every kind
+    # and no `ulen` tag in the second pass (the reference's quant never reads it)
+    import json
+    import rad_fixture
+    spec = synth.SynthSpec(n_genes=200, reads_mean=250.0)
+    b = synth.generate(spec, 0, 60)
+    bcs = host.make_barcodes(0, 60)
+    names = host.write_synth_t2g(str(tmp_path / "t2g.tsv"), spec)
+    cells = []
+    for c in range(60):
+        r0, r1 = int(b.cell_rec_offsets[c]), int(b.cell_rec_offsets[c + 1])
+        cells.append((int(bcs[c]), [(int(b.rec_umi32[r]), [int(x) for x in b.refs[b.rec_ref_offsets[r]:b.rec_ref_offsets[r + 1]]]) for r in range(r0, r1)]))
+    t2g = synth.tid_to_gid(spec)
+    o = QuantOpts(resolution=res, num_gene_ids=spec.num_gene_ids, num_rows=spec.num_rows, large_graph_thresh=1000 if res == "parsimony" else 0)
+    want = oracle_lib.oracle_quant(o, t2g, b)
+    for k, with_ulen in enumerate((True, False)):
+        d = tmp_path / f"in{k}"
+        os.makedirs(d)
+        rad_fixture.write_collated_rad(str(d / "map.collated.rad"), names, cells, 16, 12, with_ulen=with_ulen, extra_first=bool(k),
+                                       extra_file_tags=[(("known_rad_type", "string"), "sc_rna_basic"), (("lens", "array", "u16", "u32"), [1, 2, 3])],
+                                       extra_read_tags=[(("q", "u8"), 3)], extra_aln_tags=[(("pos", "u32"), 77)])
+        json.dump({"compressed_output": False}, open(d / "collate.json", "w"))
+        json.dump({"velo_mode": False}, open(d / "generate_permit_list.json", "w"))
+        out = str(tmp_path / f"out{k}")
+        host.quantify(str(d), str(tmp_path / "t2g.tsv"), out, res)
+        q = host.load_quant_dir(out)
+        assert q["dims"] == (60, spec.num_rows, want.nnz)
+        assert np.array_equal(np.array([t[1] for t in q["triplets"]], dtype=np.uint32), want.col)
+        assert [t[2] for t in q["triplets"]] == [fmt_f32(v) for v in want.val]
+
+
+@pytest.mark.gpu
+def test_unmapped_counts_file_feeds_feature_dump(tmp_path):
+    # unmapped_bc_count_collated.bin (src/quant.rs:1484-1494, 1181-1196): CorrectedReads = mapped + unmapped, MappingRate
+    import struct
+    spec = synth.SynthSpec(n_genes=100, reads_mean=150.0)
+    b, bcs, d, t2g_path = make_input(tmp_path, spec, 30)
+    unm = {int(bcs[i]): 10 * (i + 1) for i in range(0, 30, 3)}
+    with open(os.path.join(d, "unmapped_bc_count_collated.bin"), "wb") as f:      # bincode HashMap<u64, u32> (src/atac/collate.rs:270-283)
+        f.write(struct.pack("<Q", len(unm)))
+        for k, v in unm.items():
+            f.write(struct.pack("<QI", k, v))
+    out = str(tmp_path / "out")
+    host.quantify(d, t2g_path, out, "cr-like")
+    fd = host.load_quant_dir(out)["feature_dump"]
+    nrec = np.diff(b.cell_rec_offsets.astype(np.int64))
+    for c in range(30):
+        u = unm.get(int(bcs[c]), 0)
+        assert int(fd[1 + c][1]) == nrec[c] + u and int(fd[1 + c][2]) == nrec[c]
+        assert fd[1 + c][4] == fmt_f32(np.float32(nrec[c]) / np.float32(nrec[c] + u))

@@ -22,7 +22,8 @@ def _worker(rank, world, port, n_cells, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import oracle_lib
-    from alevin_fry_b200 import QuantOpts, synth, shard
+    from alevin_fry_b200 import QuantOpts, shard
+    import synth
     spec = synth.SynthSpec(reads_mean=150.0, n_genes=500)
     t2g = synth.tid_to_gid(spec)
     opts = QuantOpts(resolution="cr-like", num_gene_ids=spec.num_gene_ids, num_rows=spec.num_rows)
