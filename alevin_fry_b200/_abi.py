@@ -76,6 +76,7 @@ SYMBOLS = {
     "afq_device_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p, C.c_uint64]),
     "afq_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "afq_host_free": (None, [C.c_void_p]),
+    "afq_device_count": (C.c_int, []),
     "afq_abi_version": (C.c_int, []),
     "afq_launch_count": (C.c_uint64, [C.c_void_p]),
     "afq_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),

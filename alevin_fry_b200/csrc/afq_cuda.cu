@@ -58,7 +58,7 @@ struct HBuf {  // grow-only pinned host buffer
     if (p) cudaFreeHost(p);
     p = nullptr;
     size_t want = n + n / 8 + 64;
-    cudaError_t e = cudaHostAlloc((void**)&p, want * sizeof(T), cudaHostAllocDefault);
+    cudaError_t e = cudaHostAlloc((void**)&p, want * sizeof(T), cudaHostAllocPortable);
     cap = (e == cudaSuccess) ? want : 0;
     return e;
   }
@@ -74,6 +74,7 @@ struct Work {  // per-pipeline scratch (ordered on one stream)
   DBuf<u8> ge_arena[2];
   DBuf<u32> adj_pool;
   DBuf<u32> ps_garena;     // k_pug_smem<3> arenas
+  DBuf<u32> ps_win, ps_nwin, ps_mem, ps_desc, ps_glab;   // split parsimony path (afq_pugc.cuh)
   DBuf<u64> na_tiles;      // rec_na8 -> offsets scan
   DBuf<u32> na_ref_off;    // device API: offsets derived from rec_na8
   DBuf<u32> umi_wide, refs_wide;   // rec_umi24 / refs24 widened to u32
@@ -89,6 +90,7 @@ struct Work {  // per-pipeline scratch (ordered on one stream)
   void release() {
     ctl.release(); bin_list.release(); stage_col.release(); stage_val.release();
     tile_sums.release(); ge_arena[0].release(); ge_arena[1].release(); adj_pool.release(); ps_garena.release();
+    ps_win.release(); ps_nwin.release(); ps_mem.release(); ps_desc.release(); ps_glab.release();
     na_tiles.release(); na_ref_off.release(); umi_wide.release(); refs_wide.release();
   }
 };
@@ -148,6 +150,8 @@ struct afq_ctx {
   bool no_ps = false;          // AFQ_NO_PS=1: parsimony cells all take the global-arena kernel (A/B experiments)
   u32 need_shift = 0;          // arena-size bias, raised when a batch overflowed many arenas
   bool no_lanes = false;       // AFQ_NO_LANES=1: launch the arena kernels back to back on the caller's stream
+  bool no_ps_split = false;    // AFQ_NO_PS_SPLIT=1: unique-only parsimony stays on the single-kernel k_pug_smem (A/B, tests)
+  int grid_count = 0;          // k_pug_count's persistent grid (0: its shared memory does not fit => no split path)
   cudaStream_t lanes[NUM_BINS] = {nullptr};
   cudaEvent_t ev_fork = nullptr, ev_lane[NUM_BINS] = {nullptr};
   // pipelines
@@ -186,6 +190,7 @@ template <int VAR>
 int setup_ps(afq_ctx* c) {
   const size_t smem = VAR < PS_SMEM_VARIANTS ? (size_t)ps_arena_words(VAR) * 4 : 0;
   if (smem) CUDA_TRY(c, cudaFuncSetAttribute(k_pug_smem<VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem) CUDA_TRY(c, cudaFuncSetAttribute(k_pug_build<VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
   CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pug_smem<VAR>, (int)ps_threads(VAR), smem));
   if (occ < 1) { c->err = "k_pug_smem variant does not fit an SM"; return AFQ_ERR_CUDA; }
@@ -239,6 +244,19 @@ struct CudaLauncher {
   int ps_grid(int v) { return (c->no_ps || (v == 3 && c->no_ps_global)) ? 0 : c->grid_ps[v]; }
   u32* ps_garena(u64 words, u32 blocks) { return w->ps_garena.ensure((size_t)words * blocks + 16) == cudaSuccess ? w->ps_garena.p : nullptr; }
   u32 ps_limit_words() { return c->ps_limit_words; }
+  bool ps_split(u64 n_records, u64 n_refs, u64 n_cells, bool gene_labels, PsSplitBufs* o) {
+    if (c->no_ps_split || c->grid_count <= 0) return false;
+    const size_t desc_slots = (size_t)(n_records / 2 + n_records / 3 + n_records / 5 + n_records / 9 + 8);
+    if (w->ps_win.ensure(n_records + 4) != cudaSuccess || w->ps_nwin.ensure(n_cells + 4) != cudaSuccess ||
+        w->ps_mem.ensure(4 * (size_t)n_records + 16) != cudaSuccess || w->ps_desc.ensure(2 * desc_slots) != cudaSuccess ||
+        (gene_labels && w->ps_glab.ensure(n_refs + 4) != cudaSuccess)) {
+      cudaGetLastError();      // out of memory for the split buffers: the single-kernel path still works
+      return false;
+    }
+    o->win = w->ps_win.p; o->nwin = w->ps_nwin.p; o->mem = w->ps_mem.p; o->desc = w->ps_desc.p; o->glab = gene_labels ? w->ps_glab.p : nullptr;
+    return true;
+  }
+  int pc_grid(int which, size_t) { return which == 0 ? c->num_sms * 8 : c->grid_count; }
   // fork / join: lanes are ctx-owned non-blocking streams ordered after / before the caller stream
   void fork(int n) {
     if (c->no_lanes) return;
@@ -368,6 +386,7 @@ int afq_create(const afq_config* cfg, const uint32_t* tid_to_gid, uint64_t n_ref
   if (const char* s = getenv("AFQ_NO_LANES")) c->no_lanes = atoi(s) != 0;
   if (const char* s = getenv("AFQ_NO_PS")) c->no_ps = atoi(s) != 0;
   if (const char* s = getenv("AFQ_NO_PS_GLOBAL")) c->no_ps_global = atoi(s) != 0;
+  if (const char* s = getenv("AFQ_NO_PS_SPLIT")) c->no_ps_split = atoi(s) != 0;
   if (const char* s = getenv("AFQ_PS_LIMIT_WORDS")) c->ps_limit_words = (u32)atoi(s);
   if (c->large_cap_log2 < 10) c->large_cap_log2 = 10;
   if (c->large_cap_log2 > 30) c->large_cap_log2 = 30;
@@ -400,6 +419,15 @@ int afq_create(const afq_config* cfg, const uint32_t* tid_to_gid, uint64_t n_ref
       (rc = setup_bin<3>(c)) || (rc = setup_bin<4>(c)) || (rc = setup_bin<5>(c)) ||
       (rc = setup_ps<0>(c)) || (rc = setup_ps<1>(c)) || (rc = setup_ps<2>(c)) || (rc = setup_ps<3>(c)))
     return fail(rc);
+  {   // k_pug_count: presence bitmap over the output slots + counters in dynamic shared memory
+    const size_t csm = pc_count_smem_bytes(cfg->num_rows);
+    int occ = 0;
+    if (csm <= 200 * 1024 &&
+        cudaFuncSetAttribute(k_pug_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pug_count, (int)PC_THREADS, csm) == cudaSuccess && occ >= 1)
+      c->grid_count = occ * c->num_sms;
+    else cudaGetLastError();
+  }
   {
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gene_eqc, (int)GE_THREADS, 0) != cudaSuccess || occ < 1) occ = 1;
@@ -596,8 +624,12 @@ void afq_result_release(afq_ctx* c, afq_result* res) {
 
 int afq_host_alloc(void** ptr, size_t bytes) {
   if (!ptr) return AFQ_ERR_INVALID;
-  cudaError_t e = cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault);
+  cudaError_t e = cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable);
   return e == cudaSuccess ? AFQ_OK : AFQ_ERR_CUDA;
+}
+int afq_device_count(void) {
+  int n = 0;
+  return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
 }
 void afq_host_free(void* ptr) { if (ptr) cudaFreeHost(ptr); }
 

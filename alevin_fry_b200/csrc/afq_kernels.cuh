@@ -41,6 +41,9 @@ struct Ctl {                       // per-batch device control block (zeroed per
   u32 ge_max_p[2];
   unsigned long long adj_used;     // bump pointer into the adjacency pool
   u32 ps3_max_n, ps3_max_p;        // largest cell on k_pug_smem<3>'s list (sizes its global arenas)
+  u32 desc_count[4];               // split path: component descriptors on the lists of sizes 2 | 3-4 | 5-8 | 9-32
+  u32 desc_cursor[4];              // ... and the cover kernels' work cursors
+  u32 count_cursor;                // k_pug_count's work cursor over the cells of the four k_pug_build lists
 };
 
 struct KArgs {

@@ -19,6 +19,9 @@
 //   int  ps_grid(int variant);                                // persistent grid of k_pug_smem<variant>; 0 = disabled
 //   u32* ps_garena(u64 words_per_block, u32 blocks);          // grow-only global arenas of k_pug_smem<3>, nullptr on failure
 //   u32  ps_limit_words();                                    // 0, or a smaller arena for k_pug_smem (tests: forces fallbacks)
+//   bool ps_split(u64 n_records, u64 n_refs, u64 n_cells, bool gene_labels, PsSplitBufs* out);
+//                                                              // grow-only global buffers of the split parsimony path; false = not available
+//   int  pc_grid(int which, size_t smem);                     // grid of the flat cover kernels (0) / of k_pug_count (1)
 #pragma once
 #include <string>
 
@@ -26,19 +29,23 @@
 #include "afq_kernels.cuh"
 #include "afq_pug.cuh"
 #include "afq_pugs.cuh"
+#include "afq_pugc.cuh"
 
 namespace afq {
 
 enum KernelId : int {
   KID_BIN = 0, KID_SMEM0 = 1, KID_LARGE = 7, KID_SCAN_SUMS = 8, KID_SCAN_TILES = 9, KID_SCAN_ROWS = 10,
   KID_GATHER = 11, KID_GENE_EQC = 12, KID_GENE_EQC_BIG = 13, KID_BIN_GE = 14, KID_REGION = 15, KID_NA_OFFSETS = 16, KID_UNPACK24 = 17,
-  KID_PUG_SMEM0 = 18, KID_PUG_REGION = 22, NUM_KID = 23
+  KID_PUG_SMEM0 = 18, KID_PUG_REGION = 22, KID_PUG_BUILD0 = 23, KID_PUG_COVER2 = 27, KID_PUG_COVER4 = 28,
+  KID_PUG_COVER8 = 29, KID_PUG_COVERW = 30, KID_PUG_COUNT = 31, KID_COVER_REGION = 32, NUM_KID = 33
 };
 static const char* const KID_NAMES[NUM_KID] = {
     "k_bin_cells", "k_resolve_smem<0>", "k_resolve_smem<1>", "k_resolve_smem<2>", "k_resolve_smem<3>",
     "k_resolve_smem<4>", "k_resolve_smem<5>", "k_resolve_large", "k_scan_tile_sums", "k_scan_tiles",
     "k_scan_rows", "k_gather_rows", "k_gene_eqc", "k_gene_eqc(big cells)", "k_bin_cells_ge", "resolve_region(wall)",
-    "k_na_offsets(+tile sums)", "k_unpack24", "k_pug_smem<0>", "k_pug_smem<1>", "k_pug_smem<2>", "k_pug_smem<3>(global arena)", "pug_region(wall)"};
+    "k_na_offsets(+tile sums)", "k_unpack24", "k_pug_smem<0>", "k_pug_smem<1>", "k_pug_smem<2>", "k_pug_smem<3>(global arena)", "pug_region(wall)",
+    "k_pug_build<0>", "k_pug_build<1>", "k_pug_build<2>", "k_pug_build<3>(global arena)", "k_pug_cover2", "k_pug_cover_g<4>", "k_pug_cover_g<8>",
+    "k_pug_cover_w", "k_pug_count", "cover_region(wall)"};
 
 struct PipeBufs {  // device scratch owned by the caller (one set per stream-ordered pipeline)
   Ctl* ctl;
@@ -50,6 +57,8 @@ struct PipeBufs {  // device scratch owned by the caller (one set per stream-ord
   u32* large_cnts;
   u32 large_cap_log2, large_blocks;
 };
+
+struct PsSplitBufs { u32* win; u32* nwin; u32* mem; u32* desc; u32* glab; };
 
 inline bool res_is_pug(int r) {
   return r == AFQ_RES_PARSIMONY || r == AFQ_RES_PARSIMONY_EM || r == AFQ_RES_PARSIMONY_GENE || r == AFQ_RES_PARSIMONY_GENE_EM;
@@ -178,6 +187,19 @@ int enqueue_batch(L& l, const afq_config& cfg, int force_bin, const PipeBufs& pb
     // list, drained afterwards): forked onto lanes like the cr-like arenas so that every persistent kernel's tail
     // overlaps the others instead of idling the chip (14.5 + 7.3 + 10.3 + 5.5 ms back to back)
     u32 ps_cells = 0;
+    // unique-only parsimony resolutions take the SPLIT form (afq_pugc.cuh): build per cell, cover flat over the batch, count per cell
+    PsSplitBufs sb{};
+    const bool split = ps_on && g.only_unique && g.ge_mode != GE_MODE_CRLIKE && b.n_cells < (1ull << 24) &&
+                       pc_count_smem_bytes(cfg.num_rows) <= 200 * 1024 &&
+                       l.ps_split(b.n_records, b.n_refs_total, b.n_cells, g.ge_mode == GE_MODE_PUG_GENE, &sb);
+    if (split) {
+      g.ps_win = sb.win; g.ps_nwin = sb.nwin; g.ps_mem = sb.mem; g.ps_desc = sb.desc; g.ps_glab = sb.glab;
+      const u64 nr = b.n_records;
+      g.ps_desc_base[0] = 0;
+      g.ps_desc_base[1] = (u32)(nr / 2 + 1);
+      g.ps_desc_base[2] = g.ps_desc_base[1] + (u32)(nr / 3 + 1);
+      g.ps_desc_base[3] = g.ps_desc_base[2] + (u32)(nr / 5 + 1);
+    }
     l.region_begin();
     l.fork(PS_VARIANTS);
     for (int v = PS_VARIANTS - 1; v >= 0; --v) {   // biggest cells first
@@ -192,16 +214,39 @@ int enqueue_batch(L& l, const afq_config& cfg, int force_bin, const PipeBufs& pb
         g.ps_garena = l.ps_garena(words, blocks);
         g.ps_garena_words = (u32)words;
         if (!g.ps_garena) { l.join(); err = "k_pug_smem global arena allocation failed"; return AFQ_ERR_CUDA; }
-        l.launch(KID_PUG_SMEM0 + 3, k_pug_smem<3>, blocks, ps_threads(3), (size_t)0, a, g);
+        if (split) l.launch(KID_PUG_BUILD0 + 3, k_pug_build<3>, blocks, ps_threads(3), (size_t)0, a, g);
+        else l.launch(KID_PUG_SMEM0 + 3, k_pug_smem<3>, blocks, ps_threads(3), (size_t)0, a, g);
         continue;
       }
       const size_t smem = (size_t)ps_arena_words(v) * 4;
-      if (v == 0) l.launch(KID_PUG_SMEM0 + 0, k_pug_smem<0>, blocks, ps_threads(0), smem, a, g);
-      else if (v == 1) l.launch(KID_PUG_SMEM0 + 1, k_pug_smem<1>, blocks, ps_threads(1), smem, a, g);
-      else l.launch(KID_PUG_SMEM0 + 2, k_pug_smem<2>, blocks, ps_threads(2), smem, a, g);
+      if (split) {
+        if (v == 0) l.launch(KID_PUG_BUILD0 + 0, k_pug_build<0>, blocks, ps_threads(0), smem, a, g);
+        else if (v == 1) l.launch(KID_PUG_BUILD0 + 1, k_pug_build<1>, blocks, ps_threads(1), smem, a, g);
+        else l.launch(KID_PUG_BUILD0 + 2, k_pug_build<2>, blocks, ps_threads(2), smem, a, g);
+      } else {
+        if (v == 0) l.launch(KID_PUG_SMEM0 + 0, k_pug_smem<0>, blocks, ps_threads(0), smem, a, g);
+        else if (v == 1) l.launch(KID_PUG_SMEM0 + 1, k_pug_smem<1>, blocks, ps_threads(1), smem, a, g);
+        else l.launch(KID_PUG_SMEM0 + 2, k_pug_smem<2>, blocks, ps_threads(2), smem, a, g);
+      }
     }
     l.join();
     l.region_end(KID_PUG_REGION);
+    if (split && ps_cells) {
+      // the four size classes are independent: forked onto lanes, rarest / most expensive first
+      const unsigned cg = (unsigned)l.pc_grid(0, 0);
+      l.region_begin();
+      l.fork(4);
+      l.lane(3); l.launch(KID_PUG_COVERW, k_pug_cover_w, cg, PC_THREADS, (size_t)0, a, g);
+      l.lane(2); l.launch(KID_PUG_COVER8, k_pug_cover_g<8, 2>, cg, PC_THREADS, (size_t)0, a, g);
+      l.lane(1); l.launch(KID_PUG_COVER4, k_pug_cover_g<4, 1>, cg, PC_THREADS, (size_t)0, a, g);
+      l.lane(0); l.launch(KID_PUG_COVER2, k_pug_cover2, cg, PC_THREADS, (size_t)0, a, g);
+      l.join();
+      l.region_end(KID_COVER_REGION);
+      const size_t csm = pc_count_smem_bytes(cfg.num_rows);
+      unsigned cb = (unsigned)l.pc_grid(1, csm);
+      if (cb > ps_cells) cb = ps_cells;
+      l.launch(KID_PUG_COUNT, k_pug_count, cb, PC_THREADS, csm, a, g);
+    }
     for (int which = 0; which < 2; ++which) {
       const int list = which == 0 ? GE_LIST_BIG : GE_LIST_NORMAL;
       const u32 cells = h.bin_count[list] + (which == 1 ? ps_cells : 0u);   // upper bound: every k_pug_smem cell may come back

@@ -59,6 +59,13 @@ struct GeArgs {
   u32* ps_garena;       // k_pug_smem<3>: per-CTA global-memory arenas of ps_garena_words words
   u32 ps_garena_words;
   u32 ps_limit_words;   // k_pug_smem: use at most this many arena words (0 = the variant's size; tests force fallbacks with it)
+  // split path (k_pug_build -> k_pug_cover* -> k_pug_count, afq_pugc.cuh): per-batch global buffers
+  u32* ps_win;          // [n_records]   winners (output slots) of cell c at [r0, r0 + ps_nwin[c])
+  u32* ps_nwin;         // [n_cells]     molecules emitted so far (NONE32: the cell was handed back)
+  u32* ps_mem;          // [4 * n_records] exported members of multi-vertex components: umi, reads << 16 | label length, label offset, gene hint
+  u32* ps_desc;         // [2 * ...]     component descriptors: first member, size << 24 | cell; four size-class lists
+  u32* ps_glab;         // [n_refs_total] gene-level labels (parsimony-gene); transcript-level labels are read from the input refs
+  u32 ps_desc_base[4];  // first descriptor slot of the lists of sizes 2 | 3-4 | 5-8 | 9-32
 };
 
 __host__ __device__ inline u64 align8(u64 x) { return (x + 7) & ~7ull; }

@@ -65,6 +65,7 @@ __host__ __device__ constexpr u32 ps_min_blocks(int v) { return v == 0 ? (u32)AF
 constexpr u32 PS_WSCR_WORDS = 64 + 256; // per-warp scratch of the warp-cooperative cover (members, masks, 16 x 16 label masks)
 constexpr u32 PS_COVER_WARPS = 4;       // warps of a 256-thread CTA that run the warp form (bounds its shared scratch: 5 KB);
                                         // 8 in the larger CTAs
+constexpr u32 PC_MAX_WINNERS = 16384;    // split path: most molecules a cell may have (k_pug_count's shared-memory counters)
 constexpr u32 PS_EMPTY = 0xFFFFFFFFu;
 constexpr u32 PS_MULTI_GENE = 0xFFFFFFFEu;
 constexpr u32 PS_MAX_RECORDS = 65535;   // record indices and read counts share a 32-bit table entry (16 bits each)
@@ -116,6 +117,7 @@ struct PsExtra {
   u32 szc[SMALL_COMP + 4];   // multi-vertex components per size (counting sort of their roots)
   u32 n_over;     // components of <= 8 vertices re-routed to the warp-cooperative cover (a label > 32 transcripts)
   u32 next_w, next_g;   // cover work queues: warp-form components / group passes handed out to the warps
+  u32 dbase[4];         // SPLIT: this cell's first descriptor on each size-class list
 };
 
 // all lanes of a warp call: the warp claims the next item of a shared-memory work counter
@@ -624,7 +626,10 @@ __device__ __forceinline__ void ps_prefetch_cell(const KArgs& a, u32 cell) {
 // One cell. Returns false when the cell has to be redone by the global-arena kernel (nothing has
 // been written for it in that case).
 // =============================================================================================
-template <bool WIDE>
+// SPLIT (unique-only parsimony resolutions): the cell is only BUILT here — classes, vertices, components; singleton
+// components are emitted straight into the cell's winner list in global memory and every multi-vertex component
+// is exported (members + a descriptor on its size class's list) for the flat cover kernels of afq_pugc.cuh.
+template <bool WIDE, bool SPLIT = false>
 __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A, u32 AW, GeShared* sh, PsExtra* ex,
                                GePtrs* s_ptrs) {
   const u32 T = blockDim.x, tid = threadIdx.x;
@@ -753,6 +758,7 @@ __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A
       else if (gg != g0) { g0 = PS_MULTI_GENE; break; }
     }
     vgene[v] = g0;
+    if (SPLIT && ln > 0xFFFFu) ex->fail = 1;          // (16-bit label lengths in the exported member records)
   }
   c.vgene = vgene;
   __syncthreads();
@@ -774,18 +780,20 @@ __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A
   u32* bloom = alloc(BW);
   u32* vnext = alloc(V);                              // later: root of every vertex
   u32* parent = alloc(V);                             // later: component sizes
-  u32* winners = em ? A : alloc(next_pow2(V ? V : 1));
+  u32* winners = (em || SPLIT) ? A : alloc(next_pow2(V ? V : 1));
   u32* nxt = BW >= V ? bloom : alloc(V);              // component member lists (the bitmap is dead by then)
   // per-warp scratch of the warp-cooperative cover: 8 warps in the larger CTAs when that still fits
   u32 ncw = PS_COVER_WARPS;
   if (T >= 512 && (segA + 2 * PS_COVER_WARPS * PS_WSCR_WORDS <= off_dense || segB + 2 * PS_COVER_WARPS * PS_WSCR_WORDS + V + V / 2 + 2 * ((a.num_rows + 31) >> 5) + 64 <= topB))
     ncw = 2 * PS_COVER_WARPS;
-  u32* wscr = alloc(ncw * PS_WSCR_WORDS);
-  u32* olist = alloc(V / 2 + 2);                      // components re-routed from the group cover to the warp cover
+  u32* swin = SPLIT ? alloc(V) : nullptr;             // SPLIT: the singleton components' slots, staged until the cell is known to succeed
+  u32* wscr = SPLIT ? A : alloc(ncw * PS_WSCR_WORDS);
+  u32* olist = SPLIT ? A : alloc(V / 2 + 2);          // components re-routed from the group cover to the warp cover
   if (!fits) return false;                            // uniform (V is block-wide)
+  if (SPLIT && V > PC_MAX_WINNERS) return false;      // (the count kernel's counters are sized for this many molecules)
   const u32 Wg = (a.num_rows + 31) >> 5;
   u32* gbm = nullptr;                                 // unique-only: presence bitmap + prefix over the output slots
-  if (!em) { gbm = alloc(2 * Wg); if (!fits) gbm = nullptr; }
+  if (!em && !SPLIT) { gbm = alloc(2 * Wg); if (!fits) gbm = nullptr; }
   // EM: molecule labels grow down from the molecule offsets / lengths at the top of the arena
   PsSink sk;
   sk.mode = em ? 2u : (usa ? 1u : 0u);
@@ -941,12 +949,15 @@ __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A
           slot = ps_emit(c, sk, c.lab(cv), c.len(cv), [](u32, u32) { return true; });
         }
       } else {
-        nxt[v] = atomicExch(&head[r], v);
+        if (!SPLIT) nxt[v] = atomicExch(&head[r], v);
         if (v == r) atomicAdd(&ex->szc[sz > SMALL_COMP ? SMALL_COMP + 1 : sz], 1u);
       }
     }
     const u32 wi = warp_bump(&ex->n_win, slot != NONE32);
-    if (slot != NONE32) { winners[wi] = slot; if (gbm) atomicOr(&gbm[slot >> 5], 1u << (slot & 31)); }
+    if (slot != NONE32) {
+      if (SPLIT) swin[wi] = slot;     // (staged in shared memory: nothing may reach global memory before the cell is known to succeed)
+      else { winners[wi] = slot; if (gbm) atomicOr(&gbm[slot >> 5], 1u << (slot & 31)); }
+    }
   }
   __syncthreads();
   if (tid == 0) {
@@ -960,6 +971,55 @@ __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A
   __syncthreads();
   if (ex->fail) { __syncthreads(); return false; }
   const u32 K = ex->n_mlist;
+  if (SPLIT) {
+    // ---- export (nothing can fail from here on) ------------------------------------------------------
+    const u32 r0w = (u32)r0;
+    const u32 nsingle = ex->n_win;
+    for (u32 i = tid; i < nsingle; i += T) g.ps_win[r0w + i] = swin[i];
+    if (K) {
+      GE_FOR(v, V) if (root[v] == v && csz[v] > 1) clist[atomicAdd(&ex->szc[csz[v]], 1u)] = v;
+      __syncthreads();
+      // after the scatter szc[z] = END of size z's range: size classes 2 | 3-4 | 5-8 | 9-32 are contiguous in clist
+      const u32 Kc[5] = {0u, ex->szc[2], ex->szc[4], ex->szc[8], K};
+      if (tid < 4) {   // reserve this cell's descriptor ranges on the four global lists
+        const u32 cnt = Kc[tid + 1] - Kc[tid];
+        ex->dbase[tid] = cnt ? atomicAdd(&a.ctl->desc_count[tid], cnt) : 0u;
+      }
+      // member offsets of the components inside the cell's member region [r0, r0 + n), in clist order
+      u32 base = 0;
+      for (u32 c0 = 0; c0 < K; c0 += T) {
+        const u32 k = c0 + tid;
+        const u32 sz = k < K ? csz[clist[k]] : 0u;
+        u32 tot;
+        const u32 exs = block_exscan(sz, sh->scan, &tot);
+        if (k < K) { head[clist[k]] = base + exs; nxt[clist[k]] = 0; }
+        base += tot;
+      }
+      __syncthreads();
+      GE_FOR(k, K) {
+        const u32 r = clist[k];
+        const u32 cls = k < Kc[1] ? 0u : (k < Kc[2] ? 1u : (k < Kc[3] ? 2u : 3u));
+        const u64 pos = (u64)g.ps_desc_base[cls] + ex->dbase[cls] + (k - Kc[cls]);
+        g.ps_desc[2 * pos] = r0w + head[r];
+        g.ps_desc[2 * pos + 1] = (csz[r] << 24) | cell;
+      }
+      const u32* labsrc = refs;
+      GE_FOR(v, V) {
+        const u32 r = root[v];
+        if (csz[r] <= 1) continue;
+        const u32 idx = r0w + head[r] + atomicAdd(&nxt[r], 1u);
+        const u32 cv = c.vcls(v);
+        const u32 ln = c.len(cv), lo = f0 + c.off(cv);
+        u32* m = g.ps_mem + 4ull * idx;
+        m[0] = vumi[v]; m[1] = (c.vcnt(v) << 16) | ln; m[2] = lo; m[3] = vgene[v];
+        if (gene) for (u32 q = 0; q < ln; ++q) g.ps_glab[(u64)lo + q] = labsrc[c.off(cv) + q];   // projected labels (same values from every writer)
+      }
+    }
+    __syncthreads();
+    if (tid == 0) g.ps_nwin[cell] = nsingle;
+    __syncthreads();
+    return true;
+  }
   if (K) {
     GE_FOR(v, V) if (root[v] == v && csz[v] > 1) clist[atomicAdd(&ex->szc[csz[v]], 1u)] = v;
     __syncthreads();
@@ -1135,6 +1195,41 @@ __global__ void __launch_bounds__(ps_threads(VAR), ps_min_blocks(VAR)) k_pug_sme
     const u32 AW = (g.ps_limit_words && g.ps_limit_words < AWmax) ? g.ps_limit_words : AWmax;
     const bool ok = ps_cell<(VAR >= PS_SMEM_VARIANTS)>(a, g, cell, A, AW, &sh, &ex, &s_ptrs);
     if (!ok && threadIdx.x == 0) {
+      const u32 idx = atomicAdd(&a.ctl->bin_count[GE_LIST_NORMAL], 1u);
+      a.bin_list[(u64)GE_LIST_NORMAL * a.n_cells + idx] = cell;
+    }
+    __syncthreads();
+    job = next;
+  }
+}
+
+// The build-only form (SPLIT) of the same persistent loop: unique-only parsimony resolutions. Without the cover, the
+// counting and the EM back end the kernel needs fewer registers and a fraction of the code (instruction cache).
+__host__ __device__ constexpr u32 ps_build_min_blocks(int v) { return v == 0 ? (u32)AFQ_PS_V0_BLOCKS : (v == 1 ? 2u : (v == 2 ? 1u : 2u)); }
+template <int VAR>
+__global__ void __launch_bounds__(ps_threads(VAR), ps_build_min_blocks(VAR)) k_pug_build(KArgs a, GeArgs g) {
+  AFQ_DYN_SMEM(smem_raw);
+  u32* A = VAR < PS_SMEM_VARIANTS ? reinterpret_cast<u32*>(smem_raw) : g.ps_garena + (u64)blockIdx.x * g.ps_garena_words;
+  const u32 AWmax = VAR < PS_SMEM_VARIANTS ? ps_arena_words(VAR) : g.ps_garena_words;
+  __shared__ GeShared sh;
+  __shared__ PsExtra ex;
+  const u32 count = a.ctl->bin_count[PS_LIST0 + VAR];
+  const u32* list = a.bin_list + (u64)(PS_LIST0 + VAR) * a.n_cells;
+  if (threadIdx.x == 0) sh.job = atomicAdd(&a.ctl->bin_cursor[PS_LIST0 + VAR], 1u);
+  __syncthreads();
+  u32 job = sh.job;
+  __syncthreads();
+  while (job < count) {
+    if (threadIdx.x == 0) sh.job = atomicAdd(&a.ctl->bin_cursor[PS_LIST0 + VAR], 1u);
+    __syncthreads();
+    const u32 next = sh.job;
+    __syncthreads();
+    if (next < count) ps_prefetch_cell(a, list[next]);
+    const u32 cell = list[job];
+    const u32 AW = (g.ps_limit_words && g.ps_limit_words < AWmax) ? g.ps_limit_words : AWmax;
+    const bool ok = ps_cell<(VAR >= PS_SMEM_VARIANTS), true>(a, g, cell, A, AW, &sh, &ex, nullptr);
+    if (!ok && threadIdx.x == 0) {
+      g.ps_nwin[cell] = NONE32;        // k_pug_count skips the cell: k_gene_eqc redoes it
       const u32 idx = atomicAdd(&a.ctl->bin_count[GE_LIST_NORMAL], 1u);
       a.bin_list[(u64)GE_LIST_NORMAL * a.n_cells + idx] = cell;
     }

@@ -18,7 +18,8 @@ class _Opts(C.Structure):
                 ("init_uniform", C.c_int32), ("summary_stat", C.c_int32), ("dump_eq", C.c_int32),
                 ("resolution", C.c_char_p), ("pug_exact_umi", C.c_int32), ("sa_model", C.c_char_p),
                 ("small_thresh", C.c_uint64), ("large_graph_thresh", C.c_uint64), ("filter_list", C.c_char_p),
-                ("cmdline", C.c_char_p), ("version", C.c_char_p), ("device", C.c_int32), ("batch_records", C.c_uint64)]
+                ("cmdline", C.c_char_p), ("version", C.c_char_p), ("device", C.c_int32), ("batch_records", C.c_uint64),
+                ("devices", C.c_char_p)]
 
 
 class RadInfo(C.Structure):
@@ -58,14 +59,14 @@ def lib():
 
 def quantify(input_dir, tg_map, output_dir, resolution, num_threads=2, small_thresh=100, large_graph_thresh=None,
              pug_exact_umi=False, init_uniform=False, filter_list=None, device=0, batch_records=0, cmdline="python",
-             version="0.18.0-afq-b200", num_bootstraps=0, dump_eq=False, sa_model="winner-take-all"):
+             version="0.18.0-afq-b200", num_bootstraps=0, dump_eq=False, sa_model="winner-take-all", devices=None):
     """alevin_fry::quant::quantify(QuantOpts) (src/quant.rs:359). Raises RuntimeError on failure."""
     if large_graph_thresh is None:
         large_graph_thresh = 1000 if resolution.lower().startswith("parsimony") else 0
     o = _Opts(os.fsencode(input_dir), os.fsencode(tg_map), os.fsencode(output_dir), num_threads, num_bootstraps,
               int(init_uniform), 0, int(dump_eq), resolution.encode(), int(pug_exact_umi), sa_model.encode(),
               small_thresh, large_graph_thresh, os.fsencode(filter_list) if filter_list else None,
-              cmdline.encode(), version.encode(), device, batch_records)
+              cmdline.encode(), version.encode(), device, batch_records, devices.encode() if devices else None)
     err = C.create_string_buffer(2048)
     rc = lib().afqh_quantify(C.byref(o), err, 2048)
     if rc != 0:

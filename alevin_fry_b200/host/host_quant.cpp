@@ -579,13 +579,40 @@ int quantify_impl(const afqh_quant_opts& o) {
   cfg.barcode_len = (uint16_t)bc_len;
   cfg.umi_len = (uint16_t)umi_len;
   cfg.device = o.device;
-  afq_ctx* ctx = nullptr;
+  // one context per GPU of the device list (default: the single --device)
+  std::vector<int> devs;
+  if (o.devices && *o.devices) {
+    const std::string dl = lower(o.devices);
+    if (dl == "all") {
+      int n = afq_device_count();
+      for (int d = 0; d < n; ++d) devs.push_back(d);
+    } else {
+      size_t a = 0;
+      for (;;) {
+        const size_t b = dl.find(',', a);
+        const std::string tok = dl.substr(a, b == std::string::npos ? b : b - a);
+        if (tok.empty() || tok.find_first_not_of("0123456789") != std::string::npos) { fclose(f); throw Fail{"bad --devices list '" + dl + "' (expected e.g. 0,1,2,3 or all)"}; }
+        devs.push_back(atoi(tok.c_str()));
+        if (b == std::string::npos) break;
+        a = b + 1;
+      }
+    }
+    // (an ordinal may repeat: two contexts on one GPU are valid and let a single-GPU box exercise this path)
+  }
+  if (devs.empty()) devs.push_back(o.device);
+  const int D = (int)devs.size();
+  std::vector<afq_ctx*> ctxs((size_t)D, nullptr);
+  auto destroy_all = [&] { for (auto& c : ctxs) if (c) { afq_destroy(c); c = nullptr; } };
   cuda_warm.join();
   const auto t_create0 = std::chrono::steady_clock::now();
-  if (afq_create(&cfg, t2g.tid_to_gid.data(), t2g.tid_to_gid.size(), &ctx) != AFQ_OK) {
-    std::string m = afq_last_error(nullptr);
-    fclose(f);
-    throw Fail{"afq_create: " + m};
+  for (int d = 0; d < D; ++d) {
+    cfg.device = devs[d];
+    if (afq_create(&cfg, t2g.tid_to_gid.data(), t2g.tid_to_gid.size(), &ctxs[d]) != AFQ_OK) {
+      std::string m = afq_last_error(nullptr);
+      destroy_all();
+      fclose(f);
+      throw Fail{"afq_create: " + m};
+    }
   }
 
   mkdirs(out);
@@ -593,7 +620,7 @@ int quantify_impl(const afqh_quant_opts& o) {
   Outputs outs;
   outs.rows = fopen((out + "/alevin/quants_mat_rows.txt").c_str(), "wb");
   outs.feat = fopen((out + "/featureDump.txt").c_str(), "wb");
-  if (!outs.rows || !outs.feat) { afq_destroy(ctx); fclose(f); throw Fail{"could not create output files in " + out}; }
+  if (!outs.rows || !outs.feat) { destroy_all(); fclose(f); throw Fail{"could not create output files in " + out}; }
   fputs("CB\tCorrectedReads\tMappedReads\tDeduplicatedReads\tMappingRate\tDedupRate\tMeanByMax\tNumGenesExpressed\tNumGenesOverMean\n", outs.feat);
 
   using clk = std::chrono::steady_clock;
@@ -615,11 +642,11 @@ int quantify_impl(const afqh_quant_opts& o) {
   else {
     const int fd = open(rad_path.c_str(), O_RDONLY);
     struct stat st {};
-    if (fd < 0 || fstat(fd, &st) != 0) { if (fd >= 0) close(fd); afq_destroy(ctx); fclose(outs.rows); fclose(outs.feat); throw Fail{"couldn't open " + rad_path}; }
+    if (fd < 0 || fstat(fd, &st) != 0) { if (fd >= 0) close(fd); destroy_all(); fclose(outs.rows); fclose(outs.feat); throw Fail{"couldn't open " + rad_path}; }
     fsize = (uint64_t)st.st_size;
     fmap = fsize ? (const unsigned char*)mmap(nullptr, fsize, PROT_READ, MAP_PRIVATE, fd, 0) : nullptr;
     close(fd);
-    if (fsize && fmap == MAP_FAILED) { afq_destroy(ctx); fclose(outs.rows); fclose(outs.feat); throw Fail{"mmap failed for " + rad_path}; }
+    if (fsize && fmap == MAP_FAILED) { destroy_all(); fclose(outs.rows); fclose(outs.feat); throw Fail{"mmap failed for " + rad_path}; }
     madvise((void*)fmap, fsize, MADV_SEQUENTIAL);
   }
 
@@ -627,16 +654,21 @@ int quantify_impl(const afqh_quant_opts& o) {
   const unsigned n_threads = std::max(2u, std::min(o.num_threads < 2 ? 2u : o.num_threads, 128u));
   Pool pool(n_threads / 2), fmt_pool(n_threads - n_threads / 2);
   const uint64_t batch_records = o.batch_records ? o.batch_records : (16ull << 20);
-  constexpr int NB = 3;
-  HostBatch hb[NB];
+  // three host batches in flight per GPU (the context's slot count); batch k goes to context k mod D and the
+  // consumer collects in submission order, so the rows of the one output matrix stay in chunk order
+  const int NB = 3 * D;
+  std::vector<HostBatch> hb((size_t)NB);
+  std::vector<int> dev_of((size_t)NB, 0);
+  uint64_t batch_seq = 0;
   // 24-bit wire arrays whenever the chemistry allows: UMI <= 12 bases and fewer than 2^24 targets
   const bool pack24 = ul && umi_len <= 12 && lay.umi_size <= 4 && pre.ref_names.size() < (1u << 24) && !getenv("AFQ_NO_PACK24");
   for (auto& b : hb) b.pack24 = pack24;
-  uint64_t tickets[NB] = {0};
-  bool inflight[NB] = {false};
+  std::vector<uint64_t> tickets((size_t)NB, 0);
+  std::vector<char> inflight((size_t)NB, 0);
   auto finish = [&](int i) {
     afq_result r{};
     const auto ta = clk::now();
+    afq_ctx* ctx = ctxs[dev_of[i]];
     if (afq_wait(ctx, tickets[i], &r) != AFQ_OK) throw Fail{std::string("afq_wait: ") + afq_last_error(ctx)};
     const auto tb = clk::now();
     consume(hb[i], r, bc_len, unmapped, outs, fmt_pool);
@@ -661,7 +693,7 @@ int quantify_impl(const afqh_quant_opts& o) {
       std::string msg;
       try {
         if (consumer_failure.empty()) finish(i);
-        else { afq_result r{}; if (afq_wait(ctx, tickets[i], &r) == AFQ_OK) afq_result_release(ctx, &r); }
+        else { afq_result r{}; afq_ctx* ctx = ctxs[dev_of[i]]; if (afq_wait(ctx, tickets[i], &r) == AFQ_OK) afq_result_release(ctx, &r); }
       } catch (const Fail& e) { msg = e.msg; }
       { std::lock_guard<std::mutex> lk(qm); inflight[i] = false; if (!msg.empty() && consumer_failure.empty()) consumer_failure = msg; }
       qcv.notify_all();
@@ -691,6 +723,8 @@ int quantify_impl(const afqh_quant_opts& o) {
     if (!b.wide_na) { ab.rec_ref_offsets = nullptr; ab.rec_na8 = b.na8.p; }   // 1 byte instead of 4 per record over PCIe
     else { ab.rec_ref_offsets = b.ref_off.p; ab.rec_na8 = nullptr; }
     const auto ta = clk::now();
+    dev_of[i] = (int)(batch_seq++ % (uint64_t)D);
+    afq_ctx* ctx = ctxs[dev_of[i]];
     if (afq_submit(ctx, &ab, &tickets[i]) != AFQ_OK) throw Fail{std::string("afq_submit: ") + afq_last_error(ctx)};
     t_submit += secs(ta, clk::now());
     { std::lock_guard<std::mutex> lk(qm); inflight[i] = true; queue.push_back(i); }
@@ -743,13 +777,13 @@ int quantify_impl(const afqh_quant_opts& o) {
   consumer.join();
   if (failure.empty()) failure = consumer_failure;
   if (!failure.empty()) {
-    afq_destroy(ctx);
+    destroy_all();
     if (fmap && mapped) munmap((void*)fmap, fsize);
     fclose(outs.rows); fclose(outs.feat);
     throw Fail{failure};
   }
   const auto t_td0 = clk::now();
-  afq_destroy(ctx);
+  destroy_all();
   if (fmap && mapped) munmap((void*)fmap, fsize);
   fclose(outs.rows);
   fclose(outs.feat);

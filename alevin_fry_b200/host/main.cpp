@@ -30,7 +30,8 @@ static void usage() {
           "      --quant-subset <SFILE>      file containing list of barcodes to quantify\n"
           "  -r, --resolution <RESOLUTION>   trivial, cr-like, cr-like-em, parsimony, parsimony-em, parsimony-gene, parsimony-gene-em\n"
           "      --small-thresh <N>          cells with fewer records take the cr-like fast path [default: 100]\n"
-          "      --device <N>                CUDA device ordinal [default: 0]\n");
+          "      --device <N>                CUDA device ordinal [default: 0]\n"
+          "      --devices <LIST>            comma list of CUDA ordinals (or `all`): one reader feeds every listed GPU, one matrix is written\n");
 }
 
 int main(int argc, char** argv) {
@@ -42,7 +43,7 @@ int main(int argc, char** argv) {
   }
   std::string cmdline;
   for (int i = 0; i < argc; ++i) { if (i) cmdline += " "; cmdline += argv[i]; }
-  std::string input, tgmap, output, res, sa = "winner-take-all", subset;
+  std::string input, tgmap, output, res, sa = "winner-take-all", subset, devices;
   unsigned threads = std::max(2u, std::thread::hardware_concurrency());
   unsigned nboot = 0, device = 0;
   bool dump_eq = false, init_uniform = false, summary_stat = false;
@@ -72,6 +73,7 @@ int main(int argc, char** argv) {
     else if (a == "--small-thresh") small_thresh = strtoull(need(i), nullptr, 10);
     else if (a == "--multi-sample-output") need(i);
     else if (a == "--device") device = (unsigned)atoi(need(i));
+    else if (a == "--devices") devices = need(i);
     else if (a == "-h" || a == "--help") { usage(); return 0; }
     else { fprintf(stderr, "error: unexpected argument '%s' found\n", a.c_str()); usage(); return 2; }
   }
@@ -108,6 +110,7 @@ int main(int argc, char** argv) {
   o.small_thresh = small_thresh; o.large_graph_thresh = (uint64_t)large_thresh;
   o.filter_list = subset.empty() ? nullptr : subset.c_str();
   o.cmdline = cmdline.c_str(); o.version = VERSION; o.device = (int)device;
+  o.devices = devices.empty() ? nullptr : devices.c_str();
   char err[1024] = {0};
   if (afqh_quantify(&o, err, sizeof err) != 0) { fprintf(stderr, "Error: %s\n", err); return 1; }
   return 0;

@@ -324,14 +324,16 @@ def measure_config(args, name, cells, res, ctx):
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- roofline of the dominant kernel family (per-cell resolve) -----------------------------
-    fam = {k: v for k, v in prof.items() if k.startswith(("k_resolve", "k_gene_eqc", "k_pug_smem"))}
+    fam = {k: v for k, v in prof.items() if k.startswith(("k_resolve", "k_gene_eqc", "k_pug_smem", "k_pug_build", "k_pug_cover", "k_pug_count"))}
     fam_ms = sum(v[0] for v in fam.values()) / steps
     region = prof.get("resolve_region(wall)")
     pug_region = prof.get("pug_region(wall)")
     if region:  # arena kernels overlap on lanes: their device time is the wall time of the region(s)
         fam_ms = region[0] / steps
         if pug_region:   # the k_pug_smem variants overlap on lanes too; k_gene_eqc (handed-back cells) runs behind them
-            fam_ms += (pug_region[0] + sum(v[0] for k, v in fam.items() if k.startswith("k_gene_eqc"))) / steps
+            fam_ms += (pug_region[0] + sum(v[0] for k, v in fam.items() if k.startswith(("k_gene_eqc", "k_pug_count")))) / steps
+            if prof.get("cover_region(wall)"):   # split parsimony path: the flat cover kernels overlap on lanes as well
+                fam_ms += prof["cover_region(wall)"][0] / steps
         else:
             fam_ms += sum(v[0] for k, v in fam.items() if k.startswith(("k_gene_eqc", "k_pug_smem"))) / steps
     fam_launches = sum(v[1] for v in fam.values()) // max(steps, 1)
@@ -348,7 +350,7 @@ def measure_config(args, name, cells, res, ctx):
             traffic_note = "profiles/ncu_traffic.json was captured on another build of csrc/ (%s): not reported" % tj.get("build")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "per-cell resolve family (k_resolve_smem<*>/k_resolve_large/k_pug_smem<*>/k_gene_eqc), %d launches/step" % fam_launches,
+    roofline = {"bound": "hbm", "kernel": "per-cell resolve family (k_resolve_smem<*>/k_resolve_large/k_pug_smem<*>/k_pug_build<*>+k_pug_cover*+k_pug_count/k_gene_eqc), %d launches/step" % fam_launches,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note,
                 "algorithmic_bytes_per_step": abytes, "kernel_ms_per_step": fam_ms, "peak_source": peak_src, "nnz_per_gpu": nnz,
                 "per_kernel_ms": {k: v[0] / steps for k, v in prof.items()}}

@@ -155,7 +155,11 @@ void afq_result_release(afq_ctx* ctx, afq_result* res);
 int afq_quant_device(afq_ctx* ctx, const afq_batch* dev_batch, const afq_device_out* out,
                      void* cuda_stream);
 
-/* Pinned host memory for batches/results (cudaHostAlloc / cudaFreeHost).                */
+/* Number of CUDA devices visible to the process (0 when there is none or the driver fails). */
+int afq_device_count(void);
+
+/* Pinned host memory for batches/results (cudaHostAlloc, portable across the contexts of
+ * every GPU / cudaFreeHost).                                                            */
 int afq_host_alloc(void** ptr, size_t bytes);
 void afq_host_free(void* ptr);
 

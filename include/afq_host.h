@@ -29,8 +29,12 @@ typedef struct afqh_quant_opts {          /* mirrors QuantOpts (src/prog_opts.rs
   const char* filter_list;                /* --quant-subset or NULL                           */
   const char* cmdline;
   const char* version;
-  int32_t device;                         /* CUDA device ordinal                              */
-  uint64_t batch_records;                 /* records per device batch (0 = default 32M)       */
+  int32_t device;                         /* CUDA device ordinal (used when `devices` is NULL) */
+  uint64_t batch_records;                 /* records per device batch (0 = default 16M)       */
+  const char* devices;                    /* NULL, "all", or a comma list of CUDA ordinals ("0,1,2,3"): ONE reader feeds
+                                             the device batches round-robin to one context per GPU and ONE matrix is
+                                             written in chunk order — the reference's one-reader / N-workers / one-matrix
+                                             shape (src/quant.rs:1567-1575, 1678-1784, 1811-1847)                        */
 } afqh_quant_opts;
 
 /* Runs the whole quant stage. Returns 0 on success; on failure writes a message to err.    */

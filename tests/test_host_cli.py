@@ -317,3 +317,22 @@ def test_unmapped_counts_file_feeds_feature_dump(tmp_path):
         u = unm.get(int(bcs[c]), 0)
         assert int(fd[1 + c][1]) == nrec[c] + u and int(fd[1 + c][2]) == nrec[c]
         assert fd[1 + c][4] == fmt_f32(np.float32(nrec[c]) / np.float32(nrec[c] + u))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("res", ["cr-like", "parsimony-em"])
+def test_device_list_one_reader_many_contexts_one_matrix(tmp_path, res):
+    # src/quant.rs:1567-1575, 1811-1847: one reader feeds N workers and ONE matrix comes out. Batches go round-robin
+    # to one context per listed GPU; the files must be byte-identical to the single-context run whatever the device
+    # count (an ordinal may repeat, so a single-GPU box runs three contexts on GPU 0; `all` = every visible GPU)
+    spec = synth.SynthSpec(n_genes=300, reads_mean=220.0)
+    b, bcs, d, t2g_path = make_input(tmp_path, spec, 150)
+    host.quantify(d, t2g_path, str(tmp_path / "one"), res, batch_records=3000)
+    host.quantify(d, t2g_path, str(tmp_path / "three"), res, batch_records=3000, devices="0,0,0")
+    host.quantify(d, t2g_path, str(tmp_path / "all"), res, batch_records=3000, devices="all")
+    for fn in ("alevin/quants_mat.mtx", "alevin/quants_mat_rows.txt", "alevin/quants_mat_cols.txt", "featureDump.txt"):
+        ref = open(os.path.join(tmp_path / "one", fn), "rb").read()
+        assert open(os.path.join(tmp_path / "three", fn), "rb").read() == ref, fn
+        assert open(os.path.join(tmp_path / "all", fn), "rb").read() == ref, fn
+    with pytest.raises(RuntimeError):
+        host.quantify(d, t2g_path, str(tmp_path / "bad"), res, devices="0,x")
