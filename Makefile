@@ -23,7 +23,7 @@ HOST_SRCS := $(wildcard $(PKG)/host/*.cpp)
 HOST_HDRS := $(wildcard $(PKG)/host/*.h) include/afq.h include/afq_host.h
 
 $(PKG)/libafq_host.so: $(HOST_SRCS) $(HOST_HDRS) $(PKG)/libafq.so
-	$(CXX) $(CXXFLAGS) -shared -o $@ $(filter-out $(PKG)/host/main.cpp,$(HOST_SRCS)) -L$(PKG) -lafq -Wl,-rpath,'$$ORIGIN'
+	$(CXX) $(CXXFLAGS) -shared -o $@ $(filter-out $(PKG)/host/main.cpp,$(HOST_SRCS)) -L$(PKG) -lafq -lz -Wl,-rpath,'$$ORIGIN'
 
 bin/alevin-fry: $(PKG)/host/main.cpp $(PKG)/libafq_host.so
 	mkdir -p bin

@@ -29,7 +29,7 @@ FLAG_TINY, FLAG_ALT, FLAG_EMPTY = 1, 2, 4
 class AfqConfig(C.Structure):
     _fields_ = [
         ("resolution", C.c_int32), ("usa_mode", C.c_int32), ("em_init_uniform", C.c_int32),
-        ("pug_exact_umi", C.c_int32), ("sa_model", C.c_int32), ("reserved0", C.c_int32),
+        ("pug_exact_umi", C.c_int32), ("sa_model", C.c_int32), ("dump_eq", C.c_int32),
         ("num_gene_ids", C.c_uint32), ("num_rows", C.c_uint32),
         ("small_thresh", C.c_uint64), ("large_graph_thresh", C.c_uint64),
         ("barcode_len", C.c_uint16), ("umi_len", C.c_uint16), ("device", C.c_int32),
@@ -64,6 +64,15 @@ class AfqDeviceOut(C.Structure):
     ]
 
 
+class AfqEqcDump(C.Structure):
+    _fields_ = [("n_cells", C.c_uint64), ("n_classes", C.c_uint64), ("n_labels", C.c_uint64), ("cell_cls_ptr", C.c_void_p),
+                ("cls_lab_ptr", C.c_void_p), ("labels", C.c_void_p), ("counts", C.c_void_p)]
+
+
+class AfqEqcTable(C.Structure):
+    _fields_ = [("n_classes", C.c_uint64), ("label_offsets", C.c_void_p), ("labels", C.c_void_p)]
+
+
 # every symbol include/afq.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "afq_create": (C.c_int, [C.POINTER(AfqConfig), C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]),
@@ -77,6 +86,8 @@ SYMBOLS = {
     "afq_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "afq_host_free": (None, [C.c_void_p]),
     "afq_device_count": (C.c_int, []),
+    "afq_result_eqclasses": (C.c_int, [C.c_void_p, C.POINTER(AfqResult), C.POINTER(AfqEqcDump)]),
+    "afq_infer": (C.c_int, [C.c_void_p, C.POINTER(AfqEqcTable), C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(AfqResult)]),
     "afq_abi_version": (C.c_int, []),
     "afq_launch_count": (C.c_uint64, [C.c_void_p]),
     "afq_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),

@@ -11,12 +11,14 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <vector>
 
 #include "../../include/afq.h"
 #include "afq_pipeline.cuh"
+#include "afq_infer.cuh"
 
 using namespace afq;
 
@@ -109,6 +111,13 @@ struct Slot {  // one in-flight host batch
   HBuf<float> h_val, h_sum, h_max;
   HBuf<u8> h_flags;
   HBuf<Ctl> h_ctl;
+  // --dump-eqclasses
+  DBuf<u32> dump_ncls, dump_nlab, dump_cnt, dump_off, dump_lab, dq_counts, dq_labels;
+  DBuf<u64> dq_cls_ptr, dq_lab_base, dq_cls_lab_ptr;
+  HBuf<u64> h_cls_ptr, h_lab_base, h_cls_lab_ptr;
+  HBuf<u32> h_dq_counts, h_dq_labels;
+  u64 n_records = 0;
+  bool has_dump = false;
   cudaEvent_t ev_h2d = nullptr, ev_done = nullptr, ev_d2h = nullptr;
   u64 n_cells = 0, n_refs = 0, ticket = 0;
   bool busy = false;
@@ -118,6 +127,9 @@ struct Slot {  // one in-flight host batch
     num_expr.release(); num_over_mean.release(); flags.release();
     h_row_ptr.release(); h_col.release(); h_num_expr.release(); h_num_over_mean.release();
     h_val.release(); h_sum.release(); h_max.release(); h_flags.release(); h_ctl.release();
+    dump_ncls.release(); dump_nlab.release(); dump_cnt.release(); dump_off.release(); dump_lab.release(); dq_counts.release(); dq_labels.release();
+    dq_cls_ptr.release(); dq_lab_base.release(); dq_cls_lab_ptr.release();
+    h_cls_ptr.release(); h_lab_base.release(); h_cls_lab_ptr.release(); h_dq_counts.release(); h_dq_labels.release();
     if (ev_h2d) cudaEventDestroy(ev_h2d);
     if (ev_done) cudaEventDestroy(ev_done);
     if (ev_d2h) cudaEventDestroy(ev_d2h);
@@ -167,6 +179,12 @@ struct afq_ctx {
   double kid_ms[NUM_KID] = {0};
   u64 kid_launches[NUM_KID] = {0};
   Ctl* h_ctl_dev = nullptr;  // pinned, for afq_device_finish
+  // afq_infer: result arrays (valid until the next call)
+  std::vector<u64> inf_row_ptr;
+  std::vector<u32> inf_col, inf_num_expr, inf_num_over_mean;
+  std::vector<float> inf_val, inf_sum, inf_max;
+  std::vector<u8> inf_flags;
+  int grid_infer = 0;
 };
 
 namespace {
@@ -279,7 +297,7 @@ struct CudaLauncher {
 };
 
 // Enqueue the full device pipeline for one batch. All pointers are device pointers.
-int run_pipeline(afq_ctx* c, Work& w, const afq_batch& b, const afq_device_out& o, cudaStream_t st) {
+int run_pipeline(afq_ctx* c, Work& w, const afq_batch& b, const afq_device_out& o, cudaStream_t st, Slot* dump_slot = nullptr) {
   if (b.n_cells >= 0xFFFFFFF0ull || b.n_refs_total >= 0xFFFFFFF0ull || b.n_records >= 0xFFFFFFF0ull) {
     c->err = "batch too large: n_cells, n_records and n_refs_total must be < 2^32 (split the batch)";
     return AFQ_ERR_INVALID;
@@ -315,8 +333,31 @@ int run_pipeline(afq_ctx* c, Work& w, const afq_batch& b, const afq_device_out& 
   }
   PipeBufs pb{w.ctl.p, w.bin_list.p, w.stage_col.p, w.stage_val.p, w.tile_sums.p,
               c->large_keys, c->large_cnts, c->large_cap_log2, c->large_blocks};
+  Slot* ds = (dump_slot && b.n_cells) ? dump_slot : nullptr;
+  if (ds) {
+    CUDA_TRY(c, ds->dump_ncls.ensure(b.n_cells + 1)); CUDA_TRY(c, ds->dump_nlab.ensure(b.n_cells + 1));
+    CUDA_TRY(c, ds->dump_cnt.ensure(b.n_records + 1)); CUDA_TRY(c, ds->dump_off.ensure(b.n_records + 1)); CUDA_TRY(c, ds->dump_lab.ensure(b.n_refs_total + 1));
+    CUDA_TRY(c, ds->dq_cls_ptr.ensure(b.n_cells + 2)); CUDA_TRY(c, ds->dq_lab_base.ensure(b.n_cells + 2));
+    CUDA_TRY(c, ds->dq_cls_lab_ptr.ensure(b.n_records + 2)); CUDA_TRY(c, ds->dq_counts.ensure(b.n_records + 1)); CUDA_TRY(c, ds->dq_labels.ensure(b.n_refs_total + 1));
+    pb.dump_ncls = ds->dump_ncls.p; pb.dump_nlab = ds->dump_nlab.p; pb.dump_cnt = ds->dump_cnt.p; pb.dump_off = ds->dump_off.p; pb.dump_lab = ds->dump_lab.p;
+  }
   int rc = enqueue_batch(l, c->cfg, c->force_bin, pb, bb, o, c->err);
   if (rc != AFQ_OK) return rc;
+  if (ds) {   // compact the cells' classes: two exclusive scans (classes, label words) + one gather
+    const u32 n_tiles = (u32)((b.n_cells + SCAN_TILE - 1) / SCAN_TILE);
+    for (int k = 0; k < 2; ++k) {
+      const u32* src = k == 0 ? ds->dump_ncls.p : ds->dump_nlab.p;
+      u64* dst = k == 0 ? ds->dq_cls_ptr.p : ds->dq_lab_base.p;
+      l.launch(KID_SCAN_SUMS, k_scan_tile_sums, n_tiles, 1024u, (size_t)0, src, (u64)b.n_cells, w.tile_sums.p);
+      l.launch(KID_SCAN_TILES, k_scan_tiles, 1u, 1024u, (size_t)0, w.tile_sums.p, n_tiles, dst, (u64)b.n_cells);
+      l.launch(KID_SCAN_ROWS, k_scan_rows, n_tiles, 1024u, (size_t)0, src, (u64)b.n_cells, (const u64*)w.tile_sums.p, dst);
+    }
+    KArgs ka{};
+    ka.n_cells = b.n_cells; ka.cell_rec_off = bb.cell_rec_offsets; ka.ref_off = bb.rec_ref_offsets;
+    l.launch(KID_GATHER, k_dump_gather, (unsigned)((b.n_cells * 32 + 255) / 256), 256u, (size_t)0, ka, (const u32*)ds->dump_ncls.p,
+             (const u32*)ds->dump_nlab.p, (const u32*)ds->dump_cnt.p, (const u32*)ds->dump_off.p, (const u32*)ds->dump_lab.p,
+             (const u64*)ds->dq_cls_ptr.p, (const u64*)ds->dq_lab_base.p, ds->dq_cls_lab_ptr.p, ds->dq_labels.p, ds->dq_counts.p);
+  }
   CUDA_TRY(c, cudaGetLastError());
   return AFQ_OK;
 }
@@ -331,6 +372,11 @@ void learn_from(afq_ctx* c, const Ctl& h) {
 
 int check_device_error(afq_ctx* c, const Ctl& h) {
   learn_from(c, h);
+  if (getenv("AFQ_DEBUG_CTL")) {     // work-list sizes of the batch (diagnostics)
+    fprintf(stderr, "[afq ctl] lists:");
+    for (int i = 0; i < NUM_LISTS; ++i) fprintf(stderr, " %u", h.bin_count[i]);
+    fprintf(stderr, " | descs: %u %u %u %u | error %u\n", h.desc_count[0], h.desc_count[1], h.desc_count[2], h.desc_count[3], h.error);
+  }
   if (!h.error) return AFQ_OK;
   std::string buf;
   c->err = device_error_string(h, buf);
@@ -553,8 +599,16 @@ int afq_submit(afq_ctx* c, const afq_batch* hb, uint64_t* ticket) {
   o.col = s.col.p; o.val = s.val.p; o.cap_nnz = nf + 1;
   o.sum_umi = s.sum_umi.p; o.max_umi = s.max_umi.p;
   o.num_expr = s.num_expr.p; o.num_over_mean = s.num_over_mean.p; o.flags = s.flags.p;
-  int rc = run_pipeline(c, c->work_host, db, o, c->s_compute);
+  const bool dump = c->cfg.dump_eq != 0 && c->cfg.resolution != AFQ_RES_TRIVIAL;
+  int rc = run_pipeline(c, c->work_host, db, o, c->s_compute, dump ? &s : nullptr);
   if (rc != AFQ_OK) return rc;
+  s.has_dump = dump && nc > 0;
+  s.n_records = nr;
+  if (s.has_dump) {
+    CUDA_TRY(c, s.h_cls_ptr.ensure(nc + 2)); CUDA_TRY(c, s.h_lab_base.ensure(nc + 2));
+    CUDA_TRY(c, cudaMemcpyAsync(s.h_cls_ptr.p, s.dq_cls_ptr.p, (nc + 1) * sizeof(u64), cudaMemcpyDeviceToHost, c->s_compute));
+    CUDA_TRY(c, cudaMemcpyAsync(s.h_lab_base.p, s.dq_lab_base.p, (nc + 1) * sizeof(u64), cudaMemcpyDeviceToHost, c->s_compute));
+  }
   // small per-cell results come back on the compute stream right behind the kernels
   CUDA_TRY(c, cudaMemcpyAsync(s.h_row_ptr.p, s.row_ptr.p, (nc + 1) * sizeof(u64), cudaMemcpyDeviceToHost, c->s_compute));
   if (nc) {
@@ -592,9 +646,19 @@ int afq_wait(afq_ctx* c, uint64_t ticket, afq_result* out) {
   const u64 nnz = s.h_row_ptr.p[s.n_cells];
   CUDA_TRY(c, s.h_col.ensure(nnz + 1));
   CUDA_TRY(c, s.h_val.ensure(nnz + 1));
-  if (nnz) {
-    CUDA_TRY(c, cudaMemcpyAsync(s.h_col.p, s.col.p, nnz * sizeof(u32), cudaMemcpyDeviceToHost, c->s_d2h));
-    CUDA_TRY(c, cudaMemcpyAsync(s.h_val.p, s.val.p, nnz * sizeof(float), cudaMemcpyDeviceToHost, c->s_d2h));
+  const u64 dq_ncls = s.has_dump ? s.h_cls_ptr.p[s.n_cells] : 0, dq_nlab = s.has_dump ? s.h_lab_base.p[s.n_cells] : 0;
+  if (s.has_dump) {
+    CUDA_TRY(c, s.h_cls_lab_ptr.ensure(dq_ncls + 2)); CUDA_TRY(c, s.h_dq_counts.ensure(dq_ncls + 1)); CUDA_TRY(c, s.h_dq_labels.ensure(dq_nlab + 1));
+    s.h_cls_lab_ptr.p[dq_ncls] = dq_nlab;
+    if (dq_ncls) {
+      CUDA_TRY(c, cudaMemcpyAsync(s.h_cls_lab_ptr.p, s.dq_cls_lab_ptr.p, dq_ncls * sizeof(u64), cudaMemcpyDeviceToHost, c->s_d2h));
+      CUDA_TRY(c, cudaMemcpyAsync(s.h_dq_counts.p, s.dq_counts.p, dq_ncls * sizeof(u32), cudaMemcpyDeviceToHost, c->s_d2h));
+    }
+    if (dq_nlab) CUDA_TRY(c, cudaMemcpyAsync(s.h_dq_labels.p, s.dq_labels.p, dq_nlab * sizeof(u32), cudaMemcpyDeviceToHost, c->s_d2h));
+  }
+  if (nnz || dq_ncls) {
+    if (nnz) CUDA_TRY(c, cudaMemcpyAsync(s.h_col.p, s.col.p, nnz * sizeof(u32), cudaMemcpyDeviceToHost, c->s_d2h));
+    if (nnz) CUDA_TRY(c, cudaMemcpyAsync(s.h_val.p, s.val.p, nnz * sizeof(float), cudaMemcpyDeviceToHost, c->s_d2h));
     CUDA_TRY(c, cudaEventRecord(s.ev_d2h, c->s_d2h));
     lk.unlock();
     e = cudaEventSynchronize(s.ev_d2h);
@@ -614,12 +678,149 @@ int afq_wait(afq_ctx* c, uint64_t ticket, afq_result* out) {
   return AFQ_OK;
 }
 
+int afq_result_eqclasses(afq_ctx* c, const afq_result* res, afq_eqc_dump* out) {
+  if (!c || !res || !out) return AFQ_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  for (auto& s : c->slots)
+    if (s.busy && s.h_row_ptr.p == res->row_ptr) {
+      if (!c->cfg.dump_eq) { c->err = "afq_result_eqclasses: the context was created without dump_eq"; return AFQ_ERR_INVALID; }
+      memset(out, 0, sizeof(*out));
+      out->n_cells = s.n_cells;
+      static const uint64_t zero2[2] = {0, 0};
+      if (!s.has_dump) {       // `trivial` / an empty batch: no classes
+        out->cell_cls_ptr = s.n_cells ? nullptr : zero2; out->cls_lab_ptr = zero2;
+        if (s.n_cells) { c->err = "afq_result_eqclasses: no eq-classes for this resolution"; return AFQ_ERR_UNSUPPORTED; }
+        return AFQ_OK;
+      }
+      out->n_classes = s.h_cls_ptr.p[s.n_cells]; out->n_labels = s.h_lab_base.p[s.n_cells];
+      out->cell_cls_ptr = s.h_cls_ptr.p; out->cls_lab_ptr = s.h_cls_lab_ptr.p; out->labels = s.h_dq_labels.p; out->counts = s.h_dq_counts.p;
+      return AFQ_OK;
+    }
+  c->err = "afq_result_eqclasses: unknown or released result";
+  return AFQ_ERR_INVALID;
+}
+
 void afq_result_release(afq_ctx* c, afq_result* res) {
   if (!c || !res) return;
   std::lock_guard<std::mutex> lk(c->mu);
   for (auto& s : c->slots)
     if (s.busy && s.h_row_ptr.p == res->row_ptr) s.busy = false;
   memset(res, 0, sizeof(*res));
+}
+
+int afq_infer(afq_ctx* c, const afq_eqc_table* t, uint64_t n_cells, const uint64_t* cell_off, const uint32_t* cell_eq,
+              const uint32_t* cell_cnt, afq_result* out) {
+  if (!c || !t || !out || (n_cells && (!cell_off || !cell_eq || !cell_cnt)) || (t->n_classes && (!t->label_offsets || !t->labels))) return AFQ_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  const u32 num_alphas = c->cfg.num_rows;
+  const bool usa = c->cfg.usa_mode != 0;
+  if (num_alphas == 0 || (usa && num_alphas % 3 != 0)) { c->err = "afq_infer: bad num_rows"; return AFQ_ERR_INVALID; }
+  if (inf_smem_bytes(num_alphas) > 220 * 1024) { c->err = "afq_infer: the gene axis does not fit the shared-memory bitmap"; return AFQ_ERR_UNSUPPORTED; }
+  const u64 n_classes = t->n_classes, L = n_classes ? t->label_offsets[n_classes] : 0, nnz_in = n_cells ? cell_off[n_cells] : 0;
+  if (n_cells >= 0xFFFFFFF0ull || L >= 0xFFFFFFF0ull || n_classes >= 0xFFFFFFF0ull) { c->err = "afq_infer: table too large"; return AFQ_ERR_INVALID; }
+  for (u64 i = 0; i < n_classes; ++i) if (t->label_offsets[i + 1] < t->label_offsets[i]) { c->err = "afq_infer: label_offsets must ascend"; return AFQ_ERR_INVALID; }
+  for (u64 i = 0; i < L; ++i) if (t->labels[i] >= num_alphas) { c->err = "afq_infer: a class label is >= num_rows"; return AFQ_ERR_INVALID; }
+  // staging bounds and arena needs, from the class lengths
+  std::vector<u64> stage_off(n_cells + 1, 0);
+  u64 garena_words = 0;
+  for (u64 cc = 0; cc < n_cells; ++cc) {
+    if (cell_off[cc + 1] < cell_off[cc]) { c->err = "afq_infer: cell_offsets must ascend"; return AFQ_ERR_INVALID; }
+    u64 E = 0;
+    for (u64 k = cell_off[cc]; k < cell_off[cc + 1]; ++k) {
+      if (cell_eq[k] >= n_classes) { c->err = "afq_infer: eq-class id out of range"; return AFQ_ERR_INVALID; }
+      E += t->label_offsets[cell_eq[k] + 1] - t->label_offsets[cell_eq[k]];
+    }
+    u64 Sb = E * (usa ? 3 : 1);
+    if (Sb > num_alphas) Sb = num_alphas;
+    stage_off[cc + 1] = stage_off[cc] + Sb;
+    const u64 need = inf_need_words(cell_off[cc + 1] - cell_off[cc], E, Sb, usa);
+    if (need > INF_ARENA_WORDS && need > garena_words) garena_words = need;
+    if (need >= 0xFFFFFFF0ull) { c->err = "afq_infer: a cell is too large"; return AFQ_ERR_UNSUPPORTED; }
+  }
+  const u64 n_stage = stage_off[n_cells];
+  if (c->grid_infer == 0) {
+    const size_t sm = inf_smem_bytes(num_alphas);
+    CUDA_TRY(c, cudaFuncSetAttribute(k_em_subset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    int occ = 0;
+    CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_em_subset, (int)INF_THREADS, sm));
+    if (occ < 1) { c->err = "k_em_subset does not fit an SM"; return AFQ_ERR_CUDA; }
+    c->grid_infer = occ * c->num_sms;
+  }
+  unsigned grid = (unsigned)c->grid_infer;
+  if (grid > n_cells) grid = (unsigned)(n_cells ? n_cells : 1);
+  DBuf<u64> d_cell_off, d_stage_off, d_row_ptr, d_tiles;
+  DBuf<u32> d_eq, d_cnt, d_lab_off, d_labels, d_stage_col, d_num_expr, d_over, d_cursor, d_garena, d_col;
+  DBuf<float> d_stage_val, d_sum, d_max, d_val;
+  DBuf<u8> d_flags;
+  struct Rel { std::vector<std::function<void()>> f; ~Rel() { for (auto& g : f) g(); } } rel;
+#define INF_BUF(b, n) do { CUDA_TRY(c, (b).ensure(n)); rel.f.push_back([&] { (b).release(); }); } while (0)
+  INF_BUF(d_cell_off, n_cells + 2); INF_BUF(d_stage_off, n_cells + 2); INF_BUF(d_row_ptr, n_cells + 2); INF_BUF(d_tiles, n_cells / SCAN_TILE + 4);
+  INF_BUF(d_eq, nnz_in + 8); INF_BUF(d_cnt, nnz_in + 8); INF_BUF(d_lab_off, n_classes + 2); INF_BUF(d_labels, L + 8);
+  INF_BUF(d_stage_col, n_stage + 8); INF_BUF(d_stage_val, n_stage + 8); INF_BUF(d_num_expr, n_cells + 2); INF_BUF(d_over, n_cells + 2);
+  INF_BUF(d_cursor, 4); INF_BUF(d_sum, n_cells + 2); INF_BUF(d_max, n_cells + 2); INF_BUF(d_flags, n_cells + 2);
+  INF_BUF(d_garena, garena_words ? garena_words * grid + 16 : 4);
+#undef INF_BUF
+  cudaStream_t st = c->s_compute;
+  CUDA_TRY(c, cudaMemsetAsync(d_eq.p, 0, (nnz_in + 8) * 4, st));        // (the bulk copies read up to 3 words past a row)
+  CUDA_TRY(c, cudaMemsetAsync(d_cnt.p, 0, (nnz_in + 8) * 4, st));
+  CUDA_TRY(c, cudaMemsetAsync(d_cursor.p, 0, 16, st));
+  if (n_cells) {
+    CUDA_TRY(c, cudaMemcpyAsync(d_cell_off.p, cell_off, (n_cells + 1) * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(c, cudaMemcpyAsync(d_stage_off.p, stage_off.data(), (n_cells + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (nnz_in) {
+      CUDA_TRY(c, cudaMemcpyAsync(d_eq.p, cell_eq, nnz_in * 4, cudaMemcpyHostToDevice, st));
+      CUDA_TRY(c, cudaMemcpyAsync(d_cnt.p, cell_cnt, nnz_in * 4, cudaMemcpyHostToDevice, st));
+    }
+  }
+  if (n_classes) {
+    CUDA_TRY(c, cudaMemcpyAsync(d_lab_off.p, t->label_offsets, (n_classes + 1) * 4, cudaMemcpyHostToDevice, st));
+    if (L) CUDA_TRY(c, cudaMemcpyAsync(d_labels.p, t->labels, L * 4, cudaMemcpyHostToDevice, st));
+  }
+  u64 nnz = 0;
+  if (n_cells) {
+    InferArgs p{};
+    p.n_cells = n_cells; p.cell_off = d_cell_off.p; p.cell_eq = d_eq.p; p.cell_cnt = d_cnt.p; p.lab_off = d_lab_off.p; p.labels = d_labels.p;
+    p.num_alphas = num_alphas; p.usa = usa ? 1u : 0u; p.uo = usa ? num_alphas / 3 : 0; p.ao = 2 * p.uo;
+    p.init_uniform = c->cfg.em_init_uniform ? 1u : 0u; p.only_unique = 0;
+    p.stage_off = d_stage_off.p; p.stage_col = d_stage_col.p; p.stage_val = d_stage_val.p;
+    p.sum_umi = d_sum.p; p.max_umi = d_max.p; p.num_expr = d_num_expr.p; p.num_over_mean = d_over.p; p.flags = d_flags.p;
+    p.cursor = d_cursor.p; p.garena = d_garena.p; p.garena_words = garena_words;
+    c->launches += 5;
+    k_em_subset<<<grid, INF_THREADS, inf_smem_bytes(num_alphas), st>>>(p);
+    const u32 n_tiles = (u32)((n_cells + SCAN_TILE - 1) / SCAN_TILE);
+    k_scan_tile_sums<<<n_tiles, 1024, 0, st>>>(d_num_expr.p, n_cells, d_tiles.p);
+    k_scan_tiles<<<1, 1024, 0, st>>>(d_tiles.p, n_tiles, d_row_ptr.p, n_cells);
+    k_scan_rows<<<n_tiles, 1024, 0, st>>>(d_num_expr.p, n_cells, d_tiles.p, d_row_ptr.p);
+    CUDA_TRY(c, cudaGetLastError());
+    CUDA_TRY(c, cudaMemcpyAsync(&nnz, d_row_ptr.p + n_cells, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    CUDA_TRY(c, d_col.ensure(nnz + 4)); rel.f.push_back([&] { d_col.release(); });
+    CUDA_TRY(c, d_val.ensure(nnz + 4)); rel.f.push_back([&] { d_val.release(); });
+    k_gather_rows_at<<<(unsigned)((n_cells * 32 + 255) / 256), 256, 0, st>>>(n_cells, d_stage_off.p, d_num_expr.p, d_stage_col.p, d_stage_val.p,
+                                                                               d_row_ptr.p, d_col.p, d_val.p);
+    CUDA_TRY(c, cudaGetLastError());
+  }
+  c->inf_row_ptr.assign(n_cells + 1, 0); c->inf_col.resize(nnz); c->inf_val.resize(nnz);
+  c->inf_sum.resize(n_cells); c->inf_max.resize(n_cells); c->inf_num_expr.resize(n_cells); c->inf_num_over_mean.resize(n_cells); c->inf_flags.resize(n_cells);
+  if (n_cells) {
+    CUDA_TRY(c, cudaMemcpyAsync(c->inf_row_ptr.data(), d_row_ptr.p, (n_cells + 1) * 8, cudaMemcpyDeviceToHost, st));
+    if (nnz) {
+      CUDA_TRY(c, cudaMemcpyAsync(c->inf_col.data(), d_col.p, nnz * 4, cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(c, cudaMemcpyAsync(c->inf_val.data(), d_val.p, nnz * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(c, cudaMemcpyAsync(c->inf_sum.data(), d_sum.p, n_cells * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaMemcpyAsync(c->inf_max.data(), d_max.p, n_cells * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaMemcpyAsync(c->inf_num_expr.data(), d_num_expr.p, n_cells * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaMemcpyAsync(c->inf_num_over_mean.data(), d_over.p, n_cells * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaMemcpyAsync(c->inf_flags.data(), d_flags.p, n_cells, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+  }
+  out->n_cells = n_cells; out->nnz = nnz;
+  out->row_ptr = c->inf_row_ptr.data(); out->col = c->inf_col.data(); out->val = c->inf_val.data();
+  out->sum_umi = c->inf_sum.data(); out->max_umi = c->inf_max.data(); out->num_expr = c->inf_num_expr.data();
+  out->num_over_mean = c->inf_num_over_mean.data(); out->flags = c->inf_flags.data();
+  return AFQ_OK;
 }
 
 int afq_host_alloc(void** ptr, size_t bytes) {

@@ -859,6 +859,21 @@ __global__ void __launch_bounds__(256) k_unpack24(const u8* src, u64 n, u32* dst
   }
 }
 
+// --dump-eqclasses: one warp per cell compacts its classes (counts, label offsets, labels) from the per-cell regions
+// of the dump arrays into the batch-wide CSR-of-CSR (afq_eqc_dump)
+__global__ void __launch_bounds__(256) k_dump_gather(KArgs a, const u32* ncls, const u32* nlab, const u32* dcnt, const u32* doff, const u32* dlab,
+                                                     const u64* cls_ptr, const u64* lab_base, u64* cls_lab_ptr, u32* labels, u32* counts) {
+  const u64 w = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= a.n_cells) return;
+  const u32 lane = threadIdx.x & 31;
+  const u64 r0 = a.cell_rec_off[w];
+  const u64 f0 = a.ref_off[r0];
+  const u64 k0 = cls_ptr[w], l0 = lab_base[w];
+  for (u32 j = lane; j < ncls[w]; j += 32) { counts[k0 + j] = dcnt[r0 + j]; cls_lab_ptr[k0 + j] = l0 + doff[r0 + j]; }
+  for (u32 q = lane; q < nlab[w]; q += 32) labels[l0 + q] = dlab[f0 + q];
+  if (w + 1 == a.n_cells && lane == 0) cls_lab_ptr[cls_ptr[w + 1]] = lab_base[w + 1];
+}
+
 // one warp per cell copies its staging row to its CSR row
 __global__ void __launch_bounds__(256) k_gather_rows(KArgs a, const u64* row_ptr, u32* col, float* val) {
   const u64 w = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;

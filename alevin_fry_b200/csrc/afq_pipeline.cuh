@@ -56,6 +56,8 @@ struct PipeBufs {  // device scratch owned by the caller (one set per stream-ord
   u64* large_keys;     // giant-cell arenas for k_resolve_large
   u32* large_cnts;
   u32 large_cap_log2, large_blocks;
+  // --dump-eqclasses (nullptr: off): per-cell regions, see GeArgs
+  u32* dump_ncls = nullptr; u32* dump_nlab = nullptr; u32* dump_cnt = nullptr; u32* dump_off = nullptr; u32* dump_lab = nullptr;
 };
 
 struct PsSplitBufs { u32* win; u32* nwin; u32* mem; u32* desc; u32* glab; };
@@ -147,7 +149,9 @@ int enqueue_batch(L& l, const afq_config& cfg, int force_bin, const PipeBufs& pb
   if (l.memset_zero(pb.ctl, sizeof(Ctl))) { err = "memset(ctl) failed"; return AFQ_ERR_CUDA; }
   const int res = cfg.resolution;
   const unsigned bin_grid = (unsigned)((b.n_cells + 255) / 256);
-  if (res == AFQ_RES_CR_LIKE || res == AFQ_RES_TRIVIAL) {
+  const bool dump = pb.dump_ncls != nullptr;      // the cells' gene eq-classes are wanted: every non-tiny cell builds them (ge_back)
+  if (dump && (l.memset_zero(pb.dump_ncls, 4 * b.n_cells) || l.memset_zero(pb.dump_nlab, 4 * b.n_cells))) { err = "memset(dump) failed"; return AFQ_ERR_CUDA; }
+  if ((res == AFQ_RES_CR_LIKE && !dump) || res == AFQ_RES_TRIVIAL) {
     l.launch(KID_BIN, k_bin_cells, bin_grid, 256u, (size_t)0, a, force_bin, l.need_shift());
     launch_crlike_bins(l, a, pb);
   } else {
@@ -162,6 +166,7 @@ int enqueue_batch(L& l, const afq_config& cfg, int force_bin, const PipeBufs& pb
                                 : GE_MODE_CRLIKE;
     g.only_unique = res_is_em(res) ? 0u : 1u;
     g.ps_limit_words = l.ps_limit_words();
+    g.dump_ncls = pb.dump_ncls; g.dump_nlab = pb.dump_nlab; g.dump_cnt = pb.dump_cnt; g.dump_off = pb.dump_off; g.dump_lab = pb.dump_lab;
     // cells expected to fit a shared-memory arena take k_pug_smem (parsimony family, cr-like-em); it hands cells
     // it cannot finish (arena too small after all, a component of more than 32 vertices) back to
     // the k_gene_eqc list, which is drained afterwards
@@ -169,7 +174,7 @@ int enqueue_batch(L& l, const afq_config& cfg, int force_bin, const PipeBufs& pb
     // 224 KB / global arenas for ordinary cells, where one CTA per SM iterates slower than k_gene_eqc's
     // four — measured r1x: C4 76.4 ms with k_pug_smem vs 64.2 ms without)
     const bool ps_on = l.ps_grid(0) > 0 && (g.ge_mode == GE_MODE_CRLIKE ? (!cfg.usa_mode && !a.prefer_ambig) : cfg.large_graph_thresh >= 2);
-    const u32 ps_mode = ps_on ? (1u | (g.ge_mode == GE_MODE_PUG_GENE ? 2u : 0u) | (g.only_unique ? 0u : 4u) | (l.ps_grid(3) > 0 ? 8u : 0u)) : 0u;
+    const u32 ps_mode = ps_on ? (1u | (g.ge_mode == GE_MODE_PUG_GENE ? 2u : 0u) | ((g.only_unique && !dump) ? 0u : 4u) | (l.ps_grid(3) > 0 ? 8u : 0u)) : 0u;
     l.launch(KID_BIN_GE, k_bin_cells_ge, bin_grid, 256u, (size_t)0, a, force_bin, GE_BIG_RECORDS, l.need_shift(), ps_mode);
     launch_crlike_bins(l, a, pb);
     Ctl h{};
@@ -189,7 +194,7 @@ int enqueue_batch(L& l, const afq_config& cfg, int force_bin, const PipeBufs& pb
     u32 ps_cells = 0;
     // unique-only parsimony resolutions take the SPLIT form (afq_pugc.cuh): build per cell, cover flat over the batch, count per cell
     PsSplitBufs sb{};
-    const bool split = ps_on && g.only_unique && g.ge_mode != GE_MODE_CRLIKE && b.n_cells < (1ull << 24) &&
+    const bool split = ps_on && g.only_unique && !dump && g.ge_mode != GE_MODE_CRLIKE && b.n_cells < (1ull << 24) &&
                        pc_count_smem_bytes(cfg.num_rows) <= 200 * 1024 &&
                        l.ps_split(b.n_records, b.n_refs_total, b.n_cells, g.ge_mode == GE_MODE_PUG_GENE, &sb);
     if (split) {

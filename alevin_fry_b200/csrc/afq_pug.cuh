@@ -66,6 +66,13 @@ struct GeArgs {
   u32* ps_desc;         // [2 * ...]     component descriptors: first member, size << 24 | cell; four size-class lists
   u32* ps_glab;         // [n_refs_total] gene-level labels (parsimony-gene); transcript-level labels are read from the input refs
   u32 ps_desc_base[4];  // first descriptor slot of the lists of sizes 2 | 3-4 | 5-8 | 9-32
+  // --dump-eqclasses (src/quant.rs:1282-1307): every cell's gene eq-classes in canonical order. Cell c (records
+  // [r0, r0+n), alignments [f0, f0+P)) writes class j's count / label offset at r0 + j and its labels from f0 on.
+  u32* dump_ncls;       // [n_cells]  classes of the cell (zeroed per batch: tiny cells never build gene_eqc)
+  u32* dump_nlab;       // [n_cells]  label words of the cell
+  u32* dump_cnt;        // [n_records]
+  u32* dump_off;        // [n_records] label offset of class j inside the cell
+  u32* dump_lab;        // [n_refs_total]
 };
 
 __host__ __device__ inline u64 align8(u64 x) { return (x + 7) & ~7ull; }
@@ -1126,6 +1133,25 @@ __device__ inline void ge_back(const KArgs& a, const GeArgs& g, u32 cell, GeCell
   __syncthreads();
   auto cls_label = [&](u32 j) { return p.mlab + p.mol_off[p.gcls_m[j]]; };
   auto cls_len = [&](u32 j) { return p.mol_len[p.gcls_m[j]]; };
+  if (g.dump_ncls) {
+    // --dump-eqclasses: the cell's gene_eqc (label -> molecule count), classes in canonical (lexicographic) order.
+    // A class stands for >= 1 molecule = >= 1 record whose label is at least as long, so G <= n and the labels fit P.
+    u32 base = 0;
+    for (u32 c0 = 0; c0 < G; c0 += T) {
+      const u32 j = c0 + tid;
+      const u32 ln = j < G ? cls_len(j) : 0u;
+      u32 tot;
+      const u32 ex = block_exscan(ln, sh->scan, &tot);
+      if (j < G) {
+        g.dump_off[c.r0 + j] = base + ex;
+        g.dump_cnt[c.r0 + j] = p.gcls_cnt[j];
+        const u32* lab = cls_label(j);
+        for (u32 q = 0; q < ln; ++q) g.dump_lab[(u64)c.f0 + base + ex + q] = lab[q];
+      }
+      base += tot;
+    }
+    if (tid == 0) { g.dump_ncls[cell] = G; g.dump_nlab[cell] = base; }
+  }
 
   // =================== stage C: counts =========================================================
   const u64 out_base = c.f0;

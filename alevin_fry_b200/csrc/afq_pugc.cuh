@@ -411,18 +411,21 @@ __global__ void __launch_bounds__(PC_THREADS) k_pug_count(KArgs a, GeArgs g) {
       if (i < Wg) gpre[i] = nnz + ex;
       nnz += tot;
     }
-    for (u32 i = tid; i < nnz; i += T) gcnt[i] = 0;
+    // the per-slot counters: shared memory, or for a giant cell (more molecules than PC_MAX_WINNERS) the cell's region of
+    // the member pool, which is dead once the cover kernels are done (4 words per record >= nnz)
+    u32* cnt = m <= PC_MAX_WINNERS ? gcnt : g.ps_mem + 4ull * r0;
+    for (u32 i = tid; i < nnz; i += T) cnt[i] = 0;
     __syncthreads();
     for (u32 i = tid; i < m; i += T) {
       const u32 s = win[i];
       const u32 rank = gpre[s >> 5] + (u32)__popc(gbm[s >> 5] & ((1u << (s & 31)) - 1u));
-      if (atomicAdd(&gcnt[rank], 1u) == 0) a.stage_col[out_base + rank] = s;
+      if (atomicAdd(&cnt[rank], 1u) == 0) a.stage_col[out_base + rank] = s;
     }
     __syncthreads();
     const float mean = __fdiv_rn((float)m, (float)nnz);     // NumGenesOverMean (src/quant.rs:1190-1194)
     u32 lmax = 0, lover = 0;
     for (u32 j = tid; j < nnz; j += T) {
-      const u32 cn = gcnt[j];
+      const u32 cn = cnt[j];
       a.stage_val[out_base + j] = (float)cn;
       lmax = cn > lmax ? cn : lmax;
       if ((float)cn > mean) ++lover;

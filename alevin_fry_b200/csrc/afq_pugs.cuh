@@ -65,7 +65,7 @@ __host__ __device__ constexpr u32 ps_min_blocks(int v) { return v == 0 ? (u32)AF
 constexpr u32 PS_WSCR_WORDS = 64 + 256; // per-warp scratch of the warp-cooperative cover (members, masks, 16 x 16 label masks)
 constexpr u32 PS_COVER_WARPS = 4;       // warps of a 256-thread CTA that run the warp form (bounds its shared scratch: 5 KB);
                                         // 8 in the larger CTAs
-constexpr u32 PC_MAX_WINNERS = 16384;    // split path: most molecules a cell may have (k_pug_count's shared-memory counters)
+constexpr u32 PC_MAX_WINNERS = 16384;    // split path: molecules whose per-slot counters fit k_pug_count's shared memory (beyond: global scratch)
 constexpr u32 PS_EMPTY = 0xFFFFFFFFu;
 constexpr u32 PS_MULTI_GENE = 0xFFFFFFFEu;
 constexpr u32 PS_MAX_RECORDS = 65535;   // record indices and read counts share a 32-bit table entry (16 bits each)
@@ -639,7 +639,7 @@ __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A
   const u32 P = a.ref_off[r1] - f0;
   const bool gene = g.ge_mode == GE_MODE_PUG_GENE;
   const bool usa = a.usa_mode != 0;
-  const bool em = g.only_unique == 0;
+  const bool em = g.only_unique == 0 || (!SPLIT && g.dump_ncls != nullptr);   // (--dump-eqclasses: the molecules go through ge_back too)
 
   // ---- arena layout, phase A --------------------------------------------------------------------
   u32 off = 0;
@@ -790,7 +790,6 @@ __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A
   u32* wscr = SPLIT ? A : alloc(ncw * PS_WSCR_WORDS);
   u32* olist = SPLIT ? A : alloc(V / 2 + 2);          // components re-routed from the group cover to the warp cover
   if (!fits) return false;                            // uniform (V is block-wide)
-  if (SPLIT && V > PC_MAX_WINNERS) return false;      // (the count kernel's counters are sized for this many molecules)
   const u32 Wg = (a.num_rows + 31) >> 5;
   u32* gbm = nullptr;                                 // unique-only: presence bitmap + prefix over the output slots
   if (!em && !SPLIT) { gbm = alloc(2 * Wg); if (!fits) gbm = nullptr; }

@@ -22,6 +22,11 @@ class _Opts(C.Structure):
                 ("devices", C.c_char_p)]
 
 
+class _InferOpts(C.Structure):
+    _fields_ = [("count_mat", C.c_char_p), ("eq_labels", C.c_char_p), ("output_dir", C.c_char_p), ("usa_mode", C.c_int32),
+                ("filter_list", C.c_char_p), ("num_threads", C.c_uint32), ("device", C.c_int32)]
+
+
 class RadInfo(C.Structure):
     _fields_ = [("n_refs", C.c_uint64), ("num_chunks", C.c_uint64), ("n_records", C.c_uint64), ("n_alignments", C.c_uint64),
                 ("sum_bc", C.c_uint64), ("sum_umi", C.c_uint64), ("sum_refs", C.c_uint64),
@@ -45,6 +50,8 @@ def lib():
         l.afqh_snappy_framed_decompress.restype = C.c_int
         l.afqh_snappy_framed_decompress.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_uint32,
                                                     C.c_char_p, C.c_size_t]
+        l.afqh_infer.restype = C.c_int
+        l.afqh_infer.argtypes = [C.POINTER(_InferOpts), C.c_char_p, C.c_size_t]
         l.afqh_rad_summary.restype = C.c_int
         l.afqh_rad_summary.argtypes = [C.c_char_p, C.POINTER(RadInfo), C.c_char_p, C.c_size_t]
         l.afqh_free.restype = None
@@ -70,6 +77,15 @@ def quantify(input_dir, tg_map, output_dir, resolution, num_threads=2, small_thr
     err = C.create_string_buffer(2048)
     rc = lib().afqh_quantify(C.byref(o), err, 2048)
     if rc != 0:
+        raise RuntimeError(err.value.decode(errors="replace"))
+
+
+def infer(count_mat, eq_labels, output_dir, usa_mode=False, filter_list=None, num_threads=2, device=0):
+    """alevin_fry::infer::infer (src/infer.rs:31). Raises RuntimeError on failure."""
+    o = _InferOpts(os.fsencode(count_mat), os.fsencode(eq_labels), os.fsencode(output_dir), int(usa_mode),
+                   os.fsencode(filter_list) if filter_list else None, num_threads, device)
+    err = C.create_string_buffer(2048)
+    if lib().afqh_infer(C.byref(o), err, 2048) != 0:
         raise RuntimeError(err.value.decode(errors="replace"))
 
 

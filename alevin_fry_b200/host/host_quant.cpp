@@ -17,6 +17,7 @@
 #include <sys/mman.h>
 #include <thread>
 #include <unistd.h>
+#include <zlib.h>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -314,12 +315,30 @@ UnmappedCounts load_unmapped(const std::string& path) {
   return u;
 }
 
+// --dump-eqclasses: the GLOBAL gene-level eq-class table (EqcMap, src/quant.rs:218-229). Ids are handed out in first-seen
+// order — cells in row order, a cell's classes in canonical label order (the reference: hash order under one mutex,
+// src/quant.rs:1282-1307; the id NUMBERING is arbitrary there too, infer only needs it to be consistent).
+struct LabelVecHash {
+  size_t operator()(const std::vector<uint32_t>& v) const {
+    uint64_t h = 0x9E3779B97F4A7C15ull ^ (v.size() * 0xD6E8FEB86659FD93ull);
+    for (uint32_t x : v) { h ^= x + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); h *= 0xFF51AFD7ED558CCDull; h ^= h >> 32; }
+    return (size_t)h;
+  }
+};
+struct EqcMap {
+  std::unordered_map<std::vector<uint32_t>, uint64_t, LabelVecHash> global_eqc;
+  std::vector<const std::vector<uint32_t>*> by_id;          // id -> label (stable: unordered_map nodes do not move)
+  std::vector<std::pair<uint64_t, uint32_t>> cell_level_count;
+  std::vector<std::pair<uint64_t, uint64_t>> cell_offset;   // (row index, classes of the cell)
+};
+
 struct Outputs {
   FILE* rows = nullptr;
   FILE* feat = nullptr;
   std::vector<std::string> mtx_chunks;
   uint64_t nnz = 0, row_index = 0;
   std::vector<uint64_t> alt, empty, tiny;
+  EqcMap eqc;
 };
 
 // parse the chunks of a batch in parallel (ingest must not be the bottleneck)
@@ -473,8 +492,8 @@ int quantify_impl(const afqh_quant_opts& o) {
   REQUIRE(resolution_code(res) >= 0, "invalid value '" + std::string(o.resolution) + "' for '--resolution <RESOLUTION>'");
   const std::string sa = o.sa_model ? lower(o.sa_model) : "winner-take-all";
   REQUIRE(sa == "winner-take-all" || sa == "prefer-ambig", "invalid value for '--sa-model'");
+  REQUIRE(!(o.dump_eq && res == "trivial"), "Gene equivalence classes are not meaningful in case of Trivial resolution.");   // src/main.rs:705-711
   REQUIRE(o.num_bootstraps == 0, "bootstrapping (-b) is not implemented on the CUDA path (the reference's RNG is unseeded; see SURVEY.md §8(f) N4)");
-  REQUIRE(!o.dump_eq, "--dump-eqclasses is not implemented on the CUDA path yet (SURVEY.md §8(f) N3)");
   // src/main.rs:733-734, 759, 812-820
   REQUIRE(file_exists(in + "/generate_permit_list.json"), "The input directory " + in + " did not contain a generate_permit_list.json file; please run generate-permit-list and collate first.");
   bool velo = false;
@@ -579,6 +598,7 @@ int quantify_impl(const afqh_quant_opts& o) {
   cfg.barcode_len = (uint16_t)bc_len;
   cfg.umi_len = (uint16_t)umi_len;
   cfg.device = o.device;
+  cfg.dump_eq = o.dump_eq ? 1 : 0;
   // one context per GPU of the device list (default: the single --device)
   std::vector<int> devs;
   if (o.devices && *o.devices) {
@@ -671,6 +691,24 @@ int quantify_impl(const afqh_quant_opts& o) {
     afq_ctx* ctx = ctxs[dev_of[i]];
     if (afq_wait(ctx, tickets[i], &r) != AFQ_OK) throw Fail{std::string("afq_wait: ") + afq_last_error(ctx)};
     const auto tb = clk::now();
+    if (o.dump_eq) {   // record the cells' gene eq-classes before the rows are numbered by consume()
+      afq_eqc_dump d{};
+      if (afq_result_eqclasses(ctx, &r, &d) != AFQ_OK) throw Fail{std::string("afq_result_eqclasses: ") + afq_last_error(ctx)};
+      std::vector<uint32_t> key;
+      for (uint64_t c = 0; c < d.n_cells; ++c) {
+        const uint64_t k0 = d.cell_cls_ptr[c], k1 = d.cell_cls_ptr[c + 1];
+        for (uint64_t k = k0; k < k1; ++k) {
+          key.assign(d.labels + d.cls_lab_ptr[k], d.labels + d.cls_lab_ptr[k + 1]);
+          auto it = outs.eqc.global_eqc.find(key);
+          if (it == outs.eqc.global_eqc.end()) {
+            it = outs.eqc.global_eqc.emplace(key, (uint64_t)outs.eqc.by_id.size()).first;
+            outs.eqc.by_id.push_back(&it->first);
+          }
+          outs.eqc.cell_level_count.push_back({it->second, d.counts[k]});
+        }
+        outs.eqc.cell_offset.push_back({outs.row_index + c, k1 - k0});
+      }
+    }
     consume(hb[i], r, bc_len, unmapped, outs, fmt_pool);
     t_wait += secs(ta, tb); t_format += secs(tb, clk::now());
     afq_result_release(ctx, &r);
@@ -838,6 +876,53 @@ int quantify_impl(const afqh_quant_opts& o) {
     fclose(fm);
     REQUIRE(wr_ok && !wr_bad, "writing quants_mat.mtx failed");
   }
+  // --dump-eqclasses: geqc_counts.mtx (cells x classes) + gene_eqclass.txt.gz (write_eqc_counts, src/quant.rs:231-355)
+  if (o.dump_eq) {
+    const EqcMap& em = outs.eqc;
+    std::string body = "%%MatrixMarket matrix coordinate real general\n% written by sprs\n";
+    append_u64(body, em.cell_offset.size()); body.push_back(' ');
+    append_u64(body, em.by_id.size()); body.push_back(' ');
+    append_u64(body, em.cell_level_count.size()); body.push_back('\n');
+    uint64_t goff = 0;
+    for (auto& co : em.cell_offset) {
+      for (uint64_t k = goff; k < goff + co.second; ++k) {
+        append_u64(body, co.first + 1); body.push_back(' ');
+        append_u64(body, em.cell_level_count[k].first + 1); body.push_back(' ');
+        append_u64(body, em.cell_level_count[k].second); body.push_back('\n');
+      }
+      goff += co.second;
+    }
+    FILE* fm = fopen((out + "/alevin/geqc_counts.mtx").c_str(), "wb");
+    REQUIRE(fm, "could not write geqc_counts.mtx");
+    fwrite(body.data(), 1, body.size(), fm);
+    fclose(fm);
+    std::string txt;
+    append_u64(txt, t2g.num_rows); txt.push_back('\n');
+    append_u64(txt, em.by_id.size()); txt.push_back('\n');
+    const uint32_t uo = t2g.num_rows / 3, ao = 2 * uo;
+    for (uint64_t id = 0; id < em.by_id.size(); ++id) {
+      const std::vector<uint32_t>& gl = *em.by_id[id];
+      if (t2g.usa) {   // S -> k, U -> G + k, adjacent S,U of one gene -> 2G + k (src/quant.rs:288-335)
+        for (size_t i = 0; i < gl.size(); ++i) {
+          const uint32_t cg = gl[i];
+          if (i + 1 < gl.size() && ((cg | 1u) == (gl[i + 1] | 1u))) { append_u64(txt, (cg >> 1) + ao); txt.push_back('\t'); ++i; continue; }
+          append_u64(txt, (cg & 1u) == 0 ? (cg >> 1) : (cg >> 1) + uo); txt.push_back('\t');
+        }
+      } else {
+        for (uint32_t g : gl) { append_u64(txt, g); txt.push_back('\t'); }
+      }
+      append_u64(txt, id); txt.push_back('\n');
+    }
+    gzFile gz = gzopen((out + "/alevin/gene_eqclass.txt.gz").c_str(), "wb");
+    REQUIRE(gz, "could not write to gene_eqclass.txt.gz");
+    size_t done = 0;
+    while (done < txt.size()) {
+      const int w = gzwrite(gz, txt.data() + done, (unsigned)std::min<size_t>(txt.size() - done, 1u << 30));
+      if (w <= 0) { gzclose(gz); throw Fail{"could not write to gene_eqclass.txt.gz"}; }
+      done += (size_t)w;
+    }
+    gzclose(gz);
+  }
   // quant.json (src/quant.rs:1913-1933); keys in sorted order (serde_json Map without preserve_order)
   {
     std::string js = "{\n";
@@ -885,6 +970,162 @@ int quantify_impl(const afqh_quant_opts& o) {
   return 0;
 }
 
+// ---- infer (src/infer.rs) ---------------------------------------------------------------------------------------
+std::string dirname_of(const std::string& p) {
+  const size_t k = p.find_last_of('/');
+  return k == std::string::npos ? std::string(".") : (k == 0 ? std::string("/") : p.substr(0, k));
+}
+
+int infer_impl(const afqh_infer_opts& o) {
+  REQUIRE(o.count_mat && o.eq_labels && o.output_dir, "count_mat, eq_labels and output_dir are required");
+  // ---- the count matrix: MatrixMarket coordinate, `real` (what quant writes) or `integer` (src/infer.rs:55-85) ----
+  const std::string mtx = slurp(o.count_mat);
+  REQUIRE(!mtx.empty(), std::string("error reading mtx format matrix : cannot read ") + o.count_mat);
+  size_t pos = 0;
+  auto next_line = [&](std::string& line) { if (pos >= mtx.size()) return false; size_t e = mtx.find('\n', pos); if (e == std::string::npos) e = mtx.size(); line.assign(mtx, pos, e - pos); pos = e + 1; if (!line.empty() && line.back() == '\r') line.pop_back(); return true; };
+  std::string line;
+  REQUIRE(next_line(line) && line.rfind("%%MatrixMarket", 0) == 0, "error reading mtx format matrix : missing MatrixMarket banner");
+  {
+    const std::string l = lower(line);
+    REQUIRE(l.find("coordinate") != std::string::npos && (l.find(" real") != std::string::npos || l.find(" integer") != std::string::npos) &&
+            l.find("general") != std::string::npos, "error reading mtx format matrix : expected `matrix coordinate real|integer general`");
+  }
+  while (next_line(line) && (line.empty() || line[0] == '%')) {}
+  uint64_t n_rows = 0, n_cols = 0, nnz = 0;
+  REQUIRE(sscanf(line.c_str(), "%lu %lu %lu", &n_rows, &n_cols, &nnz) == 3, "error reading mtx format matrix : bad size line");
+  struct Trip { uint64_t r; uint32_t c, v; };
+  std::vector<Trip> trips;
+  trips.reserve(nnz);
+  {
+    const char* p = mtx.data() + pos;
+    const char* end = mtx.data() + mtx.size();
+    for (uint64_t k = 0; k < nnz; ++k) {
+      while (p < end && (*p == '\n' || *p == '\r' || *p == ' ')) ++p;
+      REQUIRE(p < end, "error reading mtx format matrix : fewer entries than the size line says");
+      char* q;
+      const uint64_t r = strtoull(p, &q, 10); p = q;
+      const uint64_t c = strtoull(p, &q, 10); p = q;
+      const double v = strtod(p, &q);
+      REQUIRE(q != p && r >= 1 && r <= n_rows && c >= 1 && c <= n_cols, "error reading mtx format matrix : bad entry");
+      p = q;
+      // whole UMI counts held in a float: round, do not truncate (src/infer.rs:367-376)
+      trips.push_back({r - 1, (uint32_t)(c - 1), (uint32_t)std::llround(v < 0 ? 0.0 : v)});
+    }
+  }
+  std::stable_sort(trips.begin(), trips.end(), [](const Trip& a, const Trip& b) { return a.r != b.r ? a.r < b.r : a.c < b.c; });   // to_csr
+  // ---- the global eq-class table (IndexedEqList::init_from_eqc_file, src/eq_class.rs:249-298) ----------------------
+  uint64_t num_genes = 0, num_eqc = 0;
+  std::vector<std::vector<uint32_t>> eqid_map;
+  {
+    gzFile gz = gzopen(o.eq_labels, "rb");
+    REQUIRE(gz, std::string("cannot open ") + o.eq_labels);
+    std::string text;
+    char buf[1 << 16];
+    int got;
+    while ((got = gzread(gz, buf, sizeof buf)) > 0) text.append(buf, (size_t)got);
+    gzclose(gz);
+    size_t tp = 0;
+    auto tline = [&](std::string& l) { if (tp >= text.size()) return false; size_t e = text.find('\n', tp); if (e == std::string::npos) e = text.size(); l.assign(text, tp, e - tp); tp = e + 1; return true; };
+    std::string l;
+    REQUIRE(tline(l), "gene_eqclass file is empty"); num_genes = strtoull(l.c_str(), nullptr, 10);
+    REQUIRE(tline(l), "gene_eqclass file is truncated"); num_eqc = strtoull(l.c_str(), nullptr, 10);
+    REQUIRE(num_genes > 0 && num_genes < (1ull << 32), "bad gene count in the gene_eqclass file");
+    eqid_map.assign(num_eqc, {});
+    while (tline(l)) {
+      std::vector<uint32_t> v;
+      const char* p = l.c_str();
+      for (;;) { while (*p == ' ' || *p == '\t') ++p; if (!*p) break; char* q; v.push_back((uint32_t)strtoull(p, &q, 10)); if (q == p) break; p = q; }
+      if (v.empty()) continue;
+      const uint32_t id = v.back(); v.pop_back();
+      REQUIRE(id < num_eqc, "eq-class id out of range in the gene_eqclass file");
+      eqid_map[id] = v;
+    }
+  }
+  REQUIRE(n_cols <= num_eqc, "the count matrix has more columns than the gene_eqclass file has classes");
+  std::vector<uint32_t> lab_off(num_eqc + 1, 0), labels;
+  for (uint64_t i = 0; i < num_eqc; ++i) { labels.insert(labels.end(), eqid_map[i].begin(), eqid_map[i].end()); lab_off[i + 1] = (uint32_t)labels.size(); }
+  // ---- barcodes (rows) + optional filter (src/infer.rs:108-150, 340-352) -------------------------------------------------
+  const std::string parent = dirname_of(o.count_mat);
+  std::vector<std::string> bcs;
+  {
+    std::ifstream bf(parent + "/quants_mat_rows.txt");
+    REQUIRE(bf.good(), "Unable to read first barcode from " + parent + "/quants_mat_rows.txt");
+    std::string l;
+    while (std::getline(bf, l)) { if (!l.empty() && l.back() == '\r') l.pop_back(); if (!l.empty()) bcs.push_back(l); }
+  }
+  REQUIRE(bcs.size() >= n_rows, "quants_mat_rows.txt has fewer barcodes than the count matrix has rows");
+  std::unordered_set<std::string> keep;
+  bool filtering = false;
+  if (o.filter_list && *o.filter_list) {
+    std::ifstream fl(o.filter_list);
+    REQUIRE(fl.good(), std::string("couldn't open file ") + o.filter_list);
+    std::string l;
+    while (std::getline(fl, l)) { if (!l.empty() && l.back() == '\r') l.pop_back(); if (!l.empty()) keep.insert(l); }
+    filtering = true;
+  }
+  std::vector<uint64_t> cell_off(1, 0);
+  std::vector<uint32_t> cell_eq, cell_cnt;
+  std::vector<uint64_t> kept_rows;
+  {
+    size_t t = 0;
+    for (uint64_t r = 0; r < n_rows; ++r) {
+      const size_t t0 = t;
+      while (t < trips.size() && trips[t].r == r) ++t;
+      if (filtering && !keep.count(bcs[r])) continue;
+      for (size_t k = t0; k < t; ++k) { cell_eq.push_back(trips[k].c); cell_cnt.push_back(trips[k].v); }
+      cell_off.push_back(cell_eq.size());
+      kept_rows.push_back(r);
+    }
+  }
+  // ---- the EM on the GPU ---------------------------------------------------------------------------------------------------
+  afq_config cfg{};
+  cfg.resolution = AFQ_RES_CR_LIKE_EM;
+  cfg.usa_mode = o.usa_mode ? 1 : 0;
+  cfg.em_init_uniform = 0;                       // infer always runs EmInitType::Informative (src/infer.rs:208)
+  cfg.num_rows = (uint32_t)num_genes;
+  cfg.num_gene_ids = o.usa_mode ? (uint32_t)(2 * (num_genes / 3)) : (uint32_t)num_genes;
+  cfg.small_thresh = 0; cfg.large_graph_thresh = 0; cfg.barcode_len = 16; cfg.umi_len = 12; cfg.device = o.device;
+  REQUIRE(!o.usa_mode || num_genes % 3 == 0, "--usa needs a gene count that is a multiple of 3");
+  const uint32_t dummy_t2g = 0;
+  afq_ctx* ctx = nullptr;
+  if (afq_create(&cfg, &dummy_t2g, 1, &ctx) != AFQ_OK) throw Fail{std::string("afq_create: ") + afq_last_error(nullptr)};
+  afq_eqc_table tab{num_eqc, lab_off.data(), labels.data()};
+  afq_result res{};
+  if (afq_infer(ctx, &tab, kept_rows.size(), cell_off.data(), cell_eq.data(), cell_cnt.data(), &res) != AFQ_OK) {
+    const std::string m = afq_last_error(ctx);
+    afq_destroy(ctx);
+    throw Fail{"afq_infer: " + m};
+  }
+  // ---- outputs ---------------------------------------------------------------------------------------------------------------
+  const std::string out = o.output_dir;
+  mkdirs(out);
+  {
+    const std::string cols = slurp(parent + "/quants_mat_cols.txt");
+    FILE* fc = fopen((out + "/quants_mat_cols.txt").c_str(), "wb");
+    if (!fc) { afq_destroy(ctx); throw Fail{"could not copy column (gene) names to output"}; }
+    fwrite(cols.data(), 1, cols.size(), fc);
+    fclose(fc);
+    std::string rows;
+    for (uint64_t r : kept_rows) { rows += bcs[r]; rows.push_back('\n'); }
+    FILE* fr = fopen((out + "/quants_mat_rows.txt").c_str(), "wb");
+    if (!fr) { afq_destroy(ctx); throw Fail{"couldn't create output barcode file"}; }
+    fwrite(rows.data(), 1, rows.size(), fr);
+    fclose(fr);
+    std::string body = "%%MatrixMarket matrix coordinate real general\n% written by sprs\n";
+    append_u64(body, res.n_cells); body.push_back(' '); append_u64(body, num_genes); body.push_back(' '); append_u64(body, res.nnz); body.push_back('\n');
+    for (uint64_t c = 0; c < res.n_cells; ++c)
+      for (uint64_t k = res.row_ptr[c]; k < res.row_ptr[c + 1]; ++k) {
+        append_u64(body, c + 1); body.push_back(' '); append_u64(body, (uint64_t)res.col[k] + 1); body.push_back(' '); append_f32(body, res.val[k]); body.push_back('\n');
+      }
+    FILE* fm = fopen((out + "/quants_mat.mtx").c_str(), "wb");
+    if (!fm) { afq_destroy(ctx); throw Fail{"couldn't create quants_mat.mtx"}; }
+    fwrite(body.data(), 1, body.size(), fm);
+    fclose(fm);
+  }
+  afq_destroy(ctx);
+  return 0;
+}
+
 template <class T> void put(FILE* f, T v) { fwrite(&v, sizeof(T), 1, f); }
 void put_str16(FILE* f, const std::string& s) { put<uint16_t>(f, (uint16_t)s.size()); fwrite(s.data(), 1, s.size(), f); }
 void put_tag(FILE* f, const std::string& name, uint8_t type) { put_str16(f, name); put<uint8_t>(f, type); }
@@ -897,6 +1138,19 @@ int afqh_quantify(const afqh_quant_opts* opts, char* err, size_t errlen) {
   if (!opts) return 1;
   try {
     return quantify_impl(*opts);
+  } catch (const Fail& e) {
+    if (err && errlen) { strncpy(err, e.msg.c_str(), errlen - 1); err[errlen - 1] = 0; }
+    return 1;
+  } catch (const std::exception& e) {
+    if (err && errlen) { strncpy(err, e.what(), errlen - 1); err[errlen - 1] = 0; }
+    return 1;
+  }
+}
+
+int afqh_infer(const afqh_infer_opts* opts, char* err, size_t errlen) {
+  if (!opts) return 1;
+  try {
+    return infer_impl(*opts);
   } catch (const Fail& e) {
     if (err && errlen) { strncpy(err, e.msg.c_str(), errlen - 1); err[errlen - 1] = 0; }
     return 1;

@@ -1,5 +1,5 @@
 // main.cpp — `alevin-fry quant` command-line clone (reference src/main.rs:294-348 for the
-// flags, 633-821 for validation and dispatch). Only the `quant` sub-command exists here:
+// flags, 633-821 for validation and dispatch). The `quant` and `infer` sub-commands exist here:
 // generate-permit-list and collate stay upstream (out of scope).
 #include <algorithm>
 #include <cstdio>
@@ -34,10 +34,52 @@ static void usage() {
           "      --devices <LIST>            comma list of CUDA ordinals (or `all`): one reader feeds every listed GPU, one matrix is written\n");
 }
 
+// `alevin-fry infer` (src/main.rs:350-365, 823-848)
+static int infer_main(int argc, char** argv) {
+  std::string count_mat, eq_labels, output, subset;
+  unsigned threads = std::max(2u, std::thread::hardware_concurrency()), device = 0;
+  bool usa = false;
+  auto need = [&](int& i) -> const char* {
+    if (i + 1 >= argc) { fprintf(stderr, "error: a value is required for '%s'\n", argv[i]); exit(2); }
+    return argv[++i];
+  };
+  for (int i = 2; i < argc; ++i) {
+    std::string a = argv[i];
+    if (a == "-c" || a == "--count-mat") count_mat = need(i);
+    else if (a == "-e" || a == "--eq-labels") eq_labels = need(i);
+    else if (a == "-o" || a == "--output-dir") output = need(i);
+    else if (a == "-t" || a == "--threads") threads = (unsigned)atoi(need(i));
+    else if (a == "--usa") usa = true;
+    else if (a == "--quant-subset") subset = need(i);
+    else if (a == "--use-mtx") {}
+    else if (a == "--use-eds") { fprintf(stderr, "Error: --use-eds is no longer supported. EDS output has been removed as of v0.12.\n"); return 1; }
+    else if (a == "--device") device = (unsigned)atoi(need(i));
+    else if (a == "-h" || a == "--help") {
+      fprintf(stderr, "Perform inference on equivalence class count data\n\nUsage: alevin-fry infer [OPTIONS] --count-mat <EQCMAT> --eq-labels <EQLABELS> --output-dir <OUTPUTDIR>\n\n"
+                      "Options:\n  -c, --count-mat <EQCMAT>      matrix of cells by equivalence class counts\n  -e, --eq-labels <EQLABELS>    file containing the gene labels of the equivalence classes\n"
+                      "  -o, --output-dir <OUTPUTDIR>  output directory where quantification results will be written\n  -t, --threads <THREADS>       number of threads to use for processing\n"
+                      "      --usa                     flag specifying that input equivalence classes were computed in USA mode\n      --quant-subset <SFILE>    file containing list of barcodes to quantify\n"
+                      "      --device <N>              CUDA device ordinal [default: 0]\n");
+      return 0;
+    } else { fprintf(stderr, "error: unexpected argument '%s' found\n", a.c_str()); return 2; }
+  }
+  if (count_mat.empty() || eq_labels.empty() || output.empty()) {
+    fprintf(stderr, "error: the following required arguments were not provided: --count-mat --eq-labels --output-dir\n");
+    return 2;
+  }
+  afqh_infer_opts o{};
+  o.count_mat = count_mat.c_str(); o.eq_labels = eq_labels.c_str(); o.output_dir = output.c_str();
+  o.usa_mode = usa; o.filter_list = subset.empty() ? nullptr : subset.c_str(); o.num_threads = threads < 2 ? 2 : threads; o.device = (int)device;
+  char err[1024] = {0};
+  if (afqh_infer(&o, err, sizeof err) != 0) { fprintf(stderr, "Error: %s\n", err); return 1; }
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc >= 2 && strcmp(argv[1], "infer") == 0) return infer_main(argc, argv);
   if (argc < 2 || strcmp(argv[1], "quant") != 0) {
     if (argc >= 2 && (strcmp(argv[1], "--version") == 0 || strcmp(argv[1], "-V") == 0)) { printf("alevin-fry %s\n", VERSION); return 0; }
-    fprintf(stderr, "only the `quant` sub-command is implemented in this build\n");
+    fprintf(stderr, "only the `quant` and `infer` sub-commands are implemented in this build\n");
     usage();
     return 2;
   }

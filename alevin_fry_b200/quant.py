@@ -28,6 +28,7 @@ class QuantOpts:
     barcode_len: int = 16
     umi_len: int = 12
     device: int = 0
+    dump_eq: bool = False                # -d/--dump-eqclasses: results carry every cell's gene eq-classes
 
     def to_c(self) -> AfqConfig:
         res = self.resolution.lower()
@@ -48,6 +49,7 @@ class QuantOpts:
         c.barcode_len = self.barcode_len
         c.umi_len = self.umi_len
         c.device = self.device
+        c.dump_eq = int(self.dump_eq)
         return c
 
 
@@ -151,6 +153,31 @@ class CellBatch:
 
 
 @dataclass
+class EqcDump:
+    """Per-cell gene eq-classes (afq_eqc_dump): cell c owns classes [cell_cls_ptr[c], cell_cls_ptr[c+1])."""
+    cell_cls_ptr: np.ndarray
+    cls_lab_ptr: np.ndarray
+    labels: np.ndarray
+    counts: np.ndarray
+
+    def cell(self, c):
+        """[(label tuple, count)] of cell c, in canonical (lexicographic) order"""
+        a, b = int(self.cell_cls_ptr[c]), int(self.cell_cls_ptr[c + 1])
+        return [(tuple(int(x) for x in self.labels[int(self.cls_lab_ptr[k]):int(self.cls_lab_ptr[k + 1])]), int(self.counts[k])) for k in range(a, b)]
+
+    @staticmethod
+    def from_c(d) -> "EqcDump":
+        def arr(p, n, dt):
+            if n == 0 or not p:
+                return np.zeros(0, dtype=dt)
+            buf = (C.c_char * (n * np.dtype(dt).itemsize)).from_address(p)
+            return np.frombuffer(buf, dtype=dt, count=n).copy()
+        nc, ncl, nl = int(d.n_cells), int(d.n_classes), int(d.n_labels)
+        return EqcDump(arr(d.cell_cls_ptr, nc + 1, np.uint64), arr(d.cls_lab_ptr, ncl + 1, np.uint64), arr(d.labels, nl, np.uint32),
+                       arr(d.counts, ncl, np.uint32))
+
+
+@dataclass
 class QuantResult:
     """Per-cell sparse counts in input cell order (CSR, ascending columns) + featureDump stats."""
     row_ptr: np.ndarray
@@ -239,6 +266,19 @@ class Quantifier:
     def quantify_batch(self, batch: CellBatch, use_na8: bool = False, use_pack24: bool = False) -> QuantResult:
         return self.wait(self.submit(batch, use_na8, use_pack24))
 
+    def quantify_batch_with_classes(self, batch: CellBatch, use_na8: bool = False, use_pack24: bool = False):
+        """(QuantResult, EqcDump) — needs QuantOpts.dump_eq (afq_result_eqclasses)."""
+        t = self.submit(batch, use_na8, use_pack24)
+        r = AfqResult()
+        self._check(self._lib.afq_wait(self._ctx, t, C.byref(r)))
+        self._keep.pop(t, None)
+        try:
+            d = _abi.AfqEqcDump()
+            self._check(self._lib.afq_result_eqclasses(self._ctx, C.byref(r), C.byref(d)))
+            return QuantResult.from_c(r), EqcDump.from_c(d)
+        finally:
+            self._lib.afq_result_release(self._ctx, C.byref(r))
+
     # ---- device API (torch tensors on this ctx's GPU) ----------------------------
     def quant_device(self, dev_batch: dict, dev_out: dict, stream_ptr: int = 0):
         """dev_batch: dict of torch cuda tensors cell_rec_offsets(int64), rec_umi32(int32),
@@ -270,6 +310,18 @@ class Quantifier:
         else:
             self._check(self._lib.afq_device_finish(self._ctx, C.c_void_p(stream_ptr), None, None, 0))
         return nnz.value
+
+    # ---- infer: EM over a global gene-eq-class table (src/infer.rs) ------------------
+    def infer(self, label_offsets, labels, cell_offsets, cell_eq, cell_cnt) -> QuantResult:
+        """afq_infer: per-cell EM (em_optimize_subset, src/em.rs:251-456) from the (class id, count) rows of a
+        geqc_counts matrix and the global class table of gene_eqclass.txt.gz. Host arrays in, QuantResult out."""
+        lo = np.ascontiguousarray(label_offsets, dtype=np.uint32); lb = np.ascontiguousarray(labels, dtype=np.uint32)
+        co = np.ascontiguousarray(cell_offsets, dtype=np.uint64); ce = np.ascontiguousarray(cell_eq, dtype=np.uint32)
+        cc = np.ascontiguousarray(cell_cnt, dtype=np.uint32)
+        t = _abi.AfqEqcTable(len(lo) - 1, _ptr(lo), _ptr(lb))
+        r = AfqResult()
+        self._check(self._lib.afq_infer(self._ctx, C.byref(t), len(co) - 1, _ptr(co), _ptr(ce), _ptr(cc), C.byref(r)))
+        return QuantResult.from_c(r)
 
     # ---- introspection ----------------------------------------------------------
     @property

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define AFQ_ABI_VERSION 2
+#define AFQ_ABI_VERSION 3
 
 /* status codes */
 enum {
@@ -64,7 +64,7 @@ typedef struct afq_config {
   int32_t sa_model;           /* AFQ_SA_* (prefer-ambig: src/pugutils.rs:505-641; applied as
                                  given — the host ignores it outside USA mode like
                                  src/quant.rs:1457-1467; switches the tiny-cell path off)   */
-  int32_t reserved0;
+  int32_t dump_eq;            /* -d/--dump-eqclasses: keep every cell's gene eq-classes (afq_result_eqclasses)      */
   uint32_t num_gene_ids;      /* size of the tid_to_gid value space: G (gene mode) or 2G */
   uint32_t num_rows;          /* output columns: G (gene mode) or 3G (USA)               */
   uint64_t small_thresh;      /* --small-thresh (default 100); 0 disables the tiny path  */
@@ -168,6 +168,36 @@ void afq_host_free(void* ptr);
  * `dev_row_ptr` are non-NULL, read back nnz = dev_row_ptr[n_cells].                     */
 int afq_device_finish(afq_ctx* ctx, void* cuda_stream, uint64_t* nnz,
                       const uint64_t* dev_row_ptr, uint64_t n_cells);
+
+/* --dump-eqclasses (src/quant.rs:1282-1307): with afq_config.dump_eq set, a host result also carries the gene-level
+ * eq-classes (sorted gene-id label -> molecule count; the reference's per-cell `gene_eqc` map) of every cell that did
+ * not take the tiny-cell fast path (those never build the map: src/quant.rs:1310-1321), classes in lexicographic label
+ * order. Cell c owns classes [cell_cls_ptr[c], cell_cls_ptr[c+1]); class k has labels[cls_lab_ptr[k] .. cls_lab_ptr[k+1])
+ * and counts[k]. Labels are gene ids as in tid_to_gid (USA: 2k / 2k+1). Valid until afq_result_release(res).      */
+typedef struct afq_eqc_dump {
+  uint64_t n_cells, n_classes, n_labels;
+  const uint64_t* cell_cls_ptr;    /* [n_cells+1]   */
+  const uint64_t* cls_lab_ptr;     /* [n_classes+1] */
+  const uint32_t* labels;          /* [n_labels]    */
+  const uint32_t* counts;          /* [n_classes]   */
+} afq_eqc_dump;
+int afq_result_eqclasses(afq_ctx* ctx, const afq_result* res, afq_eqc_dump* out);
+
+/* `alevin-fry infer` (src/infer.rs:31-241): EM over a GLOBAL gene-eq-class table — the result of `quant
+ * --dump-eqclasses` (gene_eqclass.txt.gz + geqc_counts.mtx). Replaces the worker loop around
+ * em_optimize_subset_with_scratch (src/infer.rs:196-241, src/em.rs:251-456). All pointers are HOST pointers; the call
+ * is synchronous. Rows of the count matrix are cells (CSR): cell c holds the classes cell_eq[cell_offsets[c] ..
+ * cell_offsets[c+1]) with counts cell_cnt[..], in row order (the order the reference iterates them in). Labels are
+ * column indices < num_rows (USA: the S | U | A column space written by --dump-eqclasses, src/quant.rs:273-353).
+ * Uses the context's usa_mode / num_rows / em_init_uniform (infer itself always runs Informative init). The result
+ * arrays are owned by the context and stay valid until the next afq_infer call or afq_destroy.            */
+typedef struct afq_eqc_table {
+  uint64_t n_classes;
+  const uint32_t* label_offsets;   /* [n_classes+1] */
+  const uint32_t* labels;          /* [label_offsets[n_classes]] */
+} afq_eqc_table;
+int afq_infer(afq_ctx* ctx, const afq_eqc_table* classes, uint64_t n_cells, const uint64_t* cell_offsets,
+              const uint32_t* cell_eq, const uint32_t* cell_cnt, afq_result* out);
 
 /* Introspection: ABI version; number of kernels this ctx has launched (bench.py's
  * gpu_launches); optional per-kernel device timing with CUDA events on the launching

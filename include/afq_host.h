@@ -40,6 +40,21 @@ typedef struct afqh_quant_opts {          /* mirrors QuantOpts (src/prog_opts.rs
 /* Runs the whole quant stage. Returns 0 on success; on failure writes a message to err.    */
 int afqh_quantify(const afqh_quant_opts* opts, char* err, size_t errlen);
 
+/* `alevin-fry infer` (src/infer.rs:31-424, CLI src/main.rs:350-365, 823-848): EM from the files `quant --dump-eqclasses`
+ * writes. Reads <count_mat> (geqc_counts.mtx: cells x eq-classes, `real` or `integer` MatrixMarket), <eq_labels>
+ * (gene_eqclass.txt.gz), quants_mat_rows.txt / quants_mat_cols.txt beside the count matrix; writes
+ * <output_dir>/{quants_mat.mtx, quants_mat_rows.txt, quants_mat_cols.txt}. The per-cell EM runs in afq_infer.     */
+typedef struct afqh_infer_opts {
+  const char* count_mat;      /* -c/--count-mat   */
+  const char* eq_labels;      /* -e/--eq-labels   */
+  const char* output_dir;     /* -o/--output-dir  */
+  int32_t usa_mode;           /* --usa            */
+  const char* filter_list;    /* --quant-subset or NULL */
+  uint32_t num_threads;       /* -t (host threads; floor 2) */
+  int32_t device;
+} afqh_infer_opts;
+int afqh_infer(const afqh_infer_opts* opts, char* err, size_t errlen);
+
 /* Test/bench helper: write a collated RAD directory (map.collated.rad, collate.json,
  * generate_permit_list.json) in the wire format of SURVEY.md §8(b) from SoA arrays:
  * one chunk per cell, read tags b:u32|u64 (by bc_len), u:u32|u64 (by umi_len), alignment tag

@@ -842,8 +842,11 @@ struct CellOut {
   uint8_t flags = 0;
 };
 
-void quant_cell(const CellView& c, const u32* t2g, const Cfg& cfg, CellOut& o) {
+// `classes` (optional): the cell's gene_eqc (src/quant.rs:719-720) in canonical label order — what --dump-eqclasses
+// records per cell (src/quant.rs:1282-1307); tiny and `trivial` cells never build the map.
+void quant_cell(const CellView& c, const u32* t2g, const Cfg& cfg, CellOut& o, std::vector<std::pair<Label, u32>>* classes = nullptr) {
   o = CellOut();
+  if (classes) classes->clear();
   const bool tiny_eligible = cfg.sa_model == AFQ_SA_WINNER_TAKE_ALL;
   if (tiny_eligible && c.nrec < cfg.small_thresh) {
     o.flags |= AFQ_FLAG_TINY;
@@ -884,6 +887,8 @@ void quant_cell(const CellView& c, const u32* t2g, const Cfg& cfg, CellOut& o) {
         alt = get_num_molecules(g, m, t2g, gene_eqc, cfg.large_graph_thresh);
         only_unique = (res == AFQ_RES_PARSIMONY || res == AFQ_RES_PARSIMONY_GENE);
       }
+      if (classes)
+        for (auto& cl : canonical_classes(gene_eqc)) classes->push_back({*cl.first, cl.second});
       if (cfg.usa_mode) {
         if (only_unique) {
           extract_counts(gene_eqc, cfg.num_rows, counts);
@@ -1111,6 +1116,8 @@ void tie_census_cell(const CellView& c, const u32* t2g, const Cfg& cfg, u64* tc)
 }
 
 struct OracleResult {
+  std::vector<u64> cls_ptr, cls_lab_ptr;      // --dump-eqclasses
+  std::vector<u32> cls_labels, cls_counts;
   std::vector<u64> row_ptr;
   std::vector<u32> col;
   std::vector<float> val, sum_umi, max_umi;
@@ -1127,8 +1134,16 @@ extern "C" {
 // Quantify a host batch on `n_threads` CPU threads (cells are independent work items,
 // the reference's only parallelism — src/quant.rs:1389, 733-735). Result arrays are
 // owned by the returned handle; free with afq_oracle_release.
+int afq_oracle_quant_dump(const afq_config* cfg_in, const uint32_t* tid_to_gid, uint64_t n_refs,
+                          const afq_batch* b, int n_threads, afq_result* out, void** handle, afq_eqc_dump* dump);
 int afq_oracle_quant(const afq_config* cfg_in, const uint32_t* tid_to_gid, uint64_t n_refs,
                      const afq_batch* b, int n_threads, afq_result* out, void** handle) {
+  return afq_oracle_quant_dump(cfg_in, tid_to_gid, n_refs, b, n_threads, out, handle, nullptr);
+}
+
+// ... and with `dump`: every cell's gene eq-classes (the reference's gene_eqc map, canonical order) as afq_eqc_dump
+int afq_oracle_quant_dump(const afq_config* cfg_in, const uint32_t* tid_to_gid, uint64_t n_refs,
+                          const afq_batch* b, int n_threads, afq_result* out, void** handle, afq_eqc_dump* dump) {
   (void)n_refs;
   if (!cfg_in || !b || !out || !handle) return AFQ_ERR_INVALID;
   Cfg cfg{cfg_in->resolution, cfg_in->usa_mode, cfg_in->em_init_uniform, cfg_in->pug_exact_umi,
@@ -1136,6 +1151,7 @@ int afq_oracle_quant(const afq_config* cfg_in, const uint32_t* tid_to_gid, uint6
           cfg_in->large_graph_thresh};
   const u64 nc = b->n_cells;
   std::vector<CellOut> outs(nc);
+  std::vector<std::vector<std::pair<Label, u32>>> cls(dump ? nc : 0);
   if (n_threads < 1) n_threads = 1;
   std::atomic<u64> next{0};
   auto work = [&]() {
@@ -1146,7 +1162,7 @@ int afq_oracle_quant(const afq_config* cfg_in, const uint32_t* tid_to_gid, uint6
       for (u64 c = c0; c < c1; ++c) {
         u64 r0 = b->cell_rec_offsets[c], r1 = b->cell_rec_offsets[c + 1];
         CellView cv{r1 - r0, b->rec_umi32 + r0, b->rec_ref_offsets + r0, b->refs};
-        quant_cell(cv, tid_to_gid, cfg, outs[c]);
+        quant_cell(cv, tid_to_gid, cfg, outs[c], dump ? &cls[c] : nullptr);
       }
     }
   };
@@ -1168,6 +1184,21 @@ int afq_oracle_quant(const afq_config* cfg_in, const uint32_t* tid_to_gid, uint6
     r->sum_umi[c] = outs[c].sum_umi; r->max_umi[c] = outs[c].max_umi;
     r->num_expr[c] = outs[c].num_expr; r->num_over_mean[c] = outs[c].num_over_mean;
     r->flags[c] = outs[c].flags;
+  }
+  if (dump) {
+    r->cls_ptr.assign(nc + 1, 0);
+    r->cls_lab_ptr.assign(1, 0);
+    for (u64 c = 0; c < nc; ++c) {
+      r->cls_ptr[c + 1] = r->cls_ptr[c] + cls[c].size();
+      for (auto& cl : cls[c]) {
+        r->cls_labels.insert(r->cls_labels.end(), cl.first.begin(), cl.first.end());
+        r->cls_lab_ptr.push_back(r->cls_labels.size());
+        r->cls_counts.push_back(cl.second);
+      }
+    }
+    dump->n_cells = nc; dump->n_classes = r->cls_counts.size(); dump->n_labels = r->cls_labels.size();
+    dump->cell_cls_ptr = r->cls_ptr.data(); dump->cls_lab_ptr = r->cls_lab_ptr.data();
+    dump->labels = r->cls_labels.data(); dump->counts = r->cls_counts.data();
   }
   out->n_cells = nc; out->nnz = r->row_ptr[nc];
   out->row_ptr = r->row_ptr.data(); out->col = r->col.data(); out->val = r->val.data();

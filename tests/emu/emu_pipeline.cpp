@@ -13,6 +13,7 @@ emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
 namespace cuda_emu { State g; }
 
 #include "../../alevin_fry_b200/csrc/afq_pipeline.cuh"
+#include "../../alevin_fry_b200/csrc/afq_infer.cuh"
 
 using namespace afq;
 
@@ -68,6 +69,8 @@ struct EmuLauncher {
 };
 
 struct EmuResult {
+  std::vector<u64> cls_ptr, cls_lab_ptr;     // --dump-eqclasses
+  std::vector<u32> cls_labels, cls_counts;
   std::vector<u64> row_ptr;
   std::vector<u32> col, num_expr, num_over_mean;
   std::vector<float> val, sum_umi, max_umi;
@@ -83,8 +86,14 @@ extern "C" {
 void afq_emu_last_counts(uint32_t* out, int n) { for (int i = 0; i < n && i <= NUM_LISTS; ++i) out[i] = g_last_ctl.bin_count[i]; }
 
 // k_scan_* and k_bin_* use grids of many CTAs: honoured as is (sequential CTAs).
+int afq_emu_quant_dump(const afq_config* cfg, const uint32_t* tid_to_gid, uint64_t n_refs, const afq_batch* b,
+                       afq_result* out, void** handle, char* errbuf, size_t errlen, uint32_t* dev_error, afq_eqc_dump* dump);
 int afq_emu_quant(const afq_config* cfg, const uint32_t* tid_to_gid, uint64_t n_refs, const afq_batch* b,
                   afq_result* out, void** handle, char* errbuf, size_t errlen, uint32_t* dev_error) {
+  return afq_emu_quant_dump(cfg, tid_to_gid, n_refs, b, out, handle, errbuf, errlen, dev_error, nullptr);
+}
+int afq_emu_quant_dump(const afq_config* cfg, const uint32_t* tid_to_gid, uint64_t n_refs, const afq_batch* b,
+                       afq_result* out, void** handle, char* errbuf, size_t errlen, uint32_t* dev_error, afq_eqc_dump* dump) {
   (void)n_refs;
   EmuLauncher l;
   l.t2g_ = tid_to_gid;
@@ -130,7 +139,30 @@ int afq_emu_quant(const afq_config* cfg, const uint32_t* tid_to_gid, uint64_t n_
     enqueue_na8_offsets(l, bb.rec_na8, bb.n_records, na_off.data(), na_tiles.data() + 1, na_tiles.data());
     bb.rec_ref_offsets = na_off.data();
   }
+  std::vector<u32> d_ncls, d_nlab, d_cnt, d_off, d_lab;
+  if (dump && cfg->resolution != AFQ_RES_TRIVIAL && nc) {
+    d_ncls.assign(nc + 1, 0xCDCDCDCDu); d_nlab.assign(nc + 1, 0xCDCDCDCDu);
+    d_cnt.assign(bb.n_records + 1, 0xCDCDCDCDu); d_off.assign(bb.n_records + 1, 0xCDCDCDCDu); d_lab.assign(nf + 1, 0xCDCDCDCDu);
+    pb.dump_ncls = d_ncls.data(); pb.dump_nlab = d_nlab.data(); pb.dump_cnt = d_cnt.data(); pb.dump_off = d_off.data(); pb.dump_lab = d_lab.data();
+  }
   int rc = enqueue_batch(l, *cfg, force_bin, pb, bb, o, err);
+  if (rc == AFQ_OK && dump) {
+    r->cls_ptr.assign(nc + 1, 0);
+    r->cls_lab_ptr.assign(1, 0);
+    for (u64 c = 0; c < nc && pb.dump_ncls; ++c) {
+      const u64 r0 = bb.cell_rec_offsets[c], f0 = bb.rec_ref_offsets[r0];
+      r->cls_ptr[c + 1] = r->cls_ptr[c] + d_ncls[c];
+      for (u32 j = 0; j < d_ncls[c]; ++j) {
+        const u32 lo = d_off[r0 + j], hi = j + 1 < d_ncls[c] ? d_off[r0 + j + 1] : d_nlab[c];
+        r->cls_labels.insert(r->cls_labels.end(), d_lab.begin() + f0 + lo, d_lab.begin() + f0 + hi);
+        r->cls_lab_ptr.push_back(r->cls_labels.size());
+        r->cls_counts.push_back(d_cnt[r0 + j]);
+      }
+    }
+    dump->n_cells = nc; dump->n_classes = r->cls_counts.size(); dump->n_labels = r->cls_labels.size();
+    dump->cell_cls_ptr = r->cls_ptr.data(); dump->cls_lab_ptr = r->cls_lab_ptr.data();
+    dump->labels = r->cls_labels.data(); dump->counts = r->cls_counts.data();
+  }
   g_last_ctl = ctl[0];
   if (dev_error) *dev_error = ctl[0].error;
   if (rc == AFQ_OK && ctl[0].error) {
@@ -150,5 +182,50 @@ int afq_emu_quant(const afq_config* cfg, const uint32_t* tid_to_gid, uint64_t n_
 }
 
 void afq_emu_release(void* h) { delete static_cast<EmuResult*>(h); }
+
+// k_em_subset (afq_infer.cuh) under emulation: same argument preparation as afq_infer in afq_cuda.cu
+int afq_emu_infer(uint32_t num_alphas, int usa, int init_uniform, uint64_t n_classes, const uint32_t* lab_off, const uint32_t* labels,
+                  uint64_t n_cells, const uint64_t* cell_off, const uint32_t* cell_eq, const uint32_t* cell_cnt, afq_result* out, void** handle,
+                  uint32_t force_global) {
+  (void)n_classes;
+  auto* r = new EmuResult();
+  std::vector<u64> stage_off(n_cells + 1, 0);
+  u64 garena_words = 0;
+  for (u64 cc = 0; cc < n_cells; ++cc) {
+    u64 E = 0;
+    for (u64 k = cell_off[cc]; k < cell_off[cc + 1]; ++k) E += lab_off[cell_eq[k] + 1] - lab_off[cell_eq[k]];
+    u64 Sb = E * (usa ? 3 : 1);
+    if (Sb > num_alphas) Sb = num_alphas;
+    stage_off[cc + 1] = stage_off[cc] + Sb;
+    const u64 need = inf_need_words(cell_off[cc + 1] - cell_off[cc], E, Sb, usa != 0);
+    if ((need > INF_ARENA_WORDS || force_global) && need > garena_words) garena_words = need;
+  }
+  const u64 nnz_in = n_cells ? cell_off[n_cells] : 0;
+  std::vector<u32> eq(cell_eq, cell_eq + nnz_in), cnt(cell_cnt, cell_cnt + nnz_in);
+  eq.resize(nnz_in + 8, 0); cnt.resize(nnz_in + 8, 0);
+  std::vector<u32> stage_col(stage_off[n_cells] + 8), cursor(4, 0), garena(garena_words + 16, 0xCDCDCDCDu);
+  std::vector<float> stage_val(stage_off[n_cells] + 8);
+  r->row_ptr.assign(n_cells + 1, 0);
+  r->sum_umi.assign(n_cells + 1, 0); r->max_umi.assign(n_cells + 1, 0); r->num_expr.assign(n_cells + 1, 0);
+  r->num_over_mean.assign(n_cells + 1, 0); r->flags.assign(n_cells + 1, 0);
+  InferArgs p{};
+  p.n_cells = n_cells; p.cell_off = cell_off; p.cell_eq = eq.data(); p.cell_cnt = cnt.data(); p.lab_off = lab_off; p.labels = labels;
+  p.num_alphas = num_alphas; p.usa = usa ? 1u : 0u; p.uo = usa ? num_alphas / 3 : 0; p.ao = 2 * p.uo; p.init_uniform = init_uniform ? 1u : 0u;
+  p.stage_off = stage_off.data(); p.stage_col = stage_col.data(); p.stage_val = stage_val.data();
+  p.sum_umi = r->sum_umi.data(); p.max_umi = r->max_umi.data(); p.num_expr = r->num_expr.data(); p.num_over_mean = r->num_over_mean.data();
+  p.flags = r->flags.data(); p.cursor = cursor.data(); p.garena = garena.data(); p.garena_words = garena_words;
+  if (force_global) p.garena_words = garena_words;
+  if (n_cells) cuda_emu::launch(k_em_subset, 1u, INF_THREADS, inf_smem_bytes(num_alphas), p);
+  for (u64 cc = 0; cc < n_cells; ++cc) r->row_ptr[cc + 1] = r->row_ptr[cc] + r->num_expr[cc];
+  r->col.assign(r->row_ptr[n_cells] + 1, 0); r->val.assign(r->row_ptr[n_cells] + 1, 0);
+  for (u64 cc = 0; cc < n_cells; ++cc)
+    for (u32 i = 0; i < r->num_expr[cc]; ++i) { r->col[r->row_ptr[cc] + i] = stage_col[stage_off[cc] + i]; r->val[r->row_ptr[cc] + i] = stage_val[stage_off[cc] + i]; }
+  out->n_cells = n_cells; out->nnz = r->row_ptr[n_cells];
+  out->row_ptr = r->row_ptr.data(); out->col = r->col.data(); out->val = r->val.data();
+  out->sum_umi = r->sum_umi.data(); out->max_umi = r->max_umi.data(); out->num_expr = r->num_expr.data();
+  out->num_over_mean = r->num_over_mean.data(); out->flags = r->flags.data();
+  *handle = r;
+  return AFQ_OK;
+}
 
 }  // extern "C"

@@ -25,7 +25,7 @@ def test_header_symbols_all_exported_and_bound():
     for n in names:
         assert hasattr(l, n), f"libafq.so does not export {n}"
         assert n in _abi.SYMBOLS, f"{n} missing from the ctypes binding table"
-    assert l.afq_abi_version() == 2
+    assert l.afq_abi_version() == 3
 
 
 def test_struct_sizes_match_header_layout():

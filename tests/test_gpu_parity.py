@@ -279,12 +279,19 @@ def test_pug_smem_runs_and_matches_the_global_arena_kernel(res, monkeypatch):
     t2g = synth.tid_to_gid(spec)
     o = opts_for(spec, res)
     got, launches = gpu_quant_profiled(o, t2g, b)
-    assert sum(n for k, n in launches.items() if k.startswith("k_pug_smem")) > 0, launches
+    split = res in ("parsimony", "parsimony-gene")   # unique-only: k_pug_build -> k_pug_cover* -> k_pug_count
+    assert sum(n for k, n in launches.items() if k.startswith("k_pug_build" if split else "k_pug_smem")) > 0, launches
+    assert (launches.get("k_pug_count", 0) > 0) == split, launches
     want = oracle_lib.oracle_quant(o, t2g, b)
     assert_same(got, want, exact=not res.endswith("-em"), ctx=res)
+    if split:                                        # the single-kernel form of the same path
+        monkeypatch.setenv("AFQ_NO_PS_SPLIT", "1")
+        one, launches = gpu_quant_profiled(o, t2g, b)
+        assert sum(n for k, n in launches.items() if k.startswith("k_pug_smem")) > 0 and "k_pug_count" not in launches, launches
+        assert_same(one, want, exact=True, ctx=res + "/no-split")
     monkeypatch.setenv("AFQ_NO_PS", "1")            # the global-arena kernel alone
     old, launches = gpu_quant_profiled(o, t2g, b)
-    assert sum(n for k, n in launches.items() if k.startswith("k_pug_smem")) == 0, launches
+    assert sum(n for k, n in launches.items() if k.startswith(("k_pug_smem", "k_pug_build"))) == 0, launches
     assert_same(old, want, exact=not res.endswith("-em"), ctx=res + "/no-ps")
     if not res.endswith("-em"):
         assert np.array_equal(old.val, got.val)
@@ -313,8 +320,22 @@ def test_pug_global_arena_variant_big_cells(res):
     t2g = synth.tid_to_gid(spec)
     o = opts_for(spec, res)
     got, launches = gpu_quant_profiled(o, t2g, b)
-    assert launches.get("k_pug_smem<3>(global arena)", 0) > 0, launches
+    assert launches.get("k_pug_smem<3>(global arena)", 0) + launches.get("k_pug_build<3>(global arena)", 0) > 0, launches
     assert_same(got, oracle_lib.oracle_quant(o, t2g, b), exact=not res.endswith("-em"), ctx=res)
+
+
+def test_pug_split_path_giant_cell_counts_in_global_scratch():
+    # a cell with more molecules than k_pug_count's shared-memory counters hold (PC_MAX_WINNERS = 16384): its per-slot
+    # counters live in the cell's (dead) member-pool region; must still take the split path and match the oracle
+    spec = synth.SynthSpec(fixed_reads=45000, n_genes=30000, reads_per_umi=1.2)
+    b = synth.generate(spec, 0, 3)
+    t2g = synth.tid_to_gid(spec)
+    for res in ("parsimony", "parsimony-gene"):
+        o = opts_for(spec, res)
+        got, launches = gpu_quant_profiled(o, t2g, b)
+        assert launches.get("k_pug_build<3>(global arena)", 0) > 0 and launches.get("k_gene_eqc", 0) <= 1, launches
+        assert got.sum_umi.min() > 16384
+        assert_same(got, oracle_lib.oracle_quant(o, t2g, b), ctx=res)
 
 
 @pytest.mark.parametrize("res", ["parsimony", "parsimony-em", "parsimony-gene"])

@@ -336,3 +336,95 @@ def test_device_list_one_reader_many_contexts_one_matrix(tmp_path, res):
         assert open(os.path.join(tmp_path / "all", fn), "rb").read() == ref, fn
     with pytest.raises(RuntimeError):
         host.quantify(d, t2g_path, str(tmp_path / "bad"), res, devices="0,x")
+
+
+# ---- --dump-eqclasses + `infer` (src/quant.rs:218-355, 1282-1307; src/infer.rs) -----------------------
+def _read_dump(out):
+    import gzip
+    lines = gzip.open(os.path.join(out, "alevin", "gene_eqclass.txt.gz"), "rt").read().split("\n")[:-1]
+    num_genes, num_eqc = int(lines[0]), int(lines[1])
+    classes = {}
+    for l in lines[2:]:
+        v = [int(x) for x in l.split()]
+        classes[v[-1]] = tuple(v[:-1])
+    m = open(os.path.join(out, "alevin", "geqc_counts.mtx")).read().split("\n")
+    assert m[0] == "%%MatrixMarket matrix coordinate real general"       # tests/infer_matrix_market.rs:52-63
+    body = [l for l in m if l and not l.startswith("%")]
+    dims = tuple(int(x) for x in body[0].split())
+    trips = [(int(a) - 1, int(b) - 1, int(c)) for a, b, c in (l.split() for l in body[1:])]
+    return num_genes, num_eqc, classes, dims, trips
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("res,usa", [("cr-like", False), ("parsimony-em", False), ("cr-like-em", True), ("parsimony", True)])
+def test_cli_dump_eqclasses_and_infer(tmp_path, res, usa):
+    spec = synth.SynthSpec(n_genes=400, reads_mean=260.0, usa_mode=usa)
+    b, bcs, d, t2g_path = make_input(tmp_path, spec, 80)
+    out = str(tmp_path / "out")
+    r = subprocess.run([host.CLI_PATH, "quant", "-i", d, "-m", t2g_path, "-o", out, "-r", res, "-t", "4", "-d"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    t2g = synth.tid_to_gid(spec)
+    o = QuantOpts(resolution=res, usa_mode=usa, num_gene_ids=spec.num_gene_ids, num_rows=spec.num_rows, dump_eq=True,
+                  large_graph_thresh=1000 if res.startswith("parsimony") else 0)
+    want, wd = oracle_lib.oracle_quant_with_classes(o, t2g, b)
+    num_genes, num_eqc, classes, dims, trips = _read_dump(out)
+    assert num_genes == spec.num_rows and len(classes) == num_eqc and dims == (80, num_eqc, len(trips))
+    assert host.load_quant_dir(out)["meta"]["dump_eq"] is True
+    # every cell's classes: the file's (label -> count) multiset equals the oracle's gene_eqc, after the USA id remap
+    G = spec.n_genes
+
+    def remap(lab):   # S -> k, U -> G + k, adjacent S, U of one gene -> 2G + k (src/quant.rs:288-335)
+        if not usa:
+            return tuple(lab)
+        res_, i = [], 0
+        while i < len(lab):
+            if i + 1 < len(lab) and (lab[i] | 1) == (lab[i + 1] | 1):
+                res_.append((lab[i] >> 1) + 2 * G); i += 2
+            else:
+                res_.append((lab[i] >> 1) if lab[i] % 2 == 0 else (lab[i] >> 1) + G); i += 1
+        return tuple(res_)
+    per_cell = {}
+    for r_, c_, v_ in trips:
+        per_cell.setdefault(r_, []).append((classes[c_], v_))
+    for c in range(80):
+        exp = sorted((remap(lab), cnt) for lab, cnt in wd.cell(c))
+        assert sorted(per_cell.get(c, [])) == exp, c
+    # `infer` on the dump: the same EM the oracle runs on those rows (informative init), written as a matrix
+    out2 = str(tmp_path / "inferred")
+    r = subprocess.run([host.CLI_PATH, "infer", "-c", os.path.join(out, "alevin", "geqc_counts.mtx"),
+                        "-e", os.path.join(out, "alevin", "gene_eqclass.txt.gz"), "-o", out2] + (["--usa"] if usa else []), capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(os.path.join(out2, "quants_mat_rows.txt")).read() == open(os.path.join(out, "alevin", "quants_mat_rows.txt")).read()
+    assert open(os.path.join(out2, "quants_mat_cols.txt")).read() == open(os.path.join(out, "alevin", "quants_mat_cols.txt")).read()
+    lo, lb = [0], []
+    for k in range(num_eqc):
+        lb.extend(classes[k]); lo.append(len(lb))
+    co, ce, cc = [0], [], []
+    for c in range(80):
+        row = sorted((c_, v_) for r_, c_, v_ in trips if r_ == c)
+        ce.extend(x[0] for x in row); cc.extend(x[1] for x in row); co.append(len(ce))
+    exp = oracle_lib.infer_cells(spec.num_rows, usa, False, np.array(lo, dtype=np.uint32), np.array(lb, dtype=np.uint32),
+                                 np.array(co, dtype=np.uint64), np.array(ce, dtype=np.uint32), np.array(cc, dtype=np.uint32))
+    m = open(os.path.join(out2, "quants_mat.mtx")).read().split("\n")
+    body = [l for l in m if l and not l.startswith("%")]
+    assert tuple(int(x) for x in body[0].split()) == (80, spec.num_rows, exp.nnz)
+    got_cols = np.array([int(l.split()[1]) - 1 for l in body[1:]], dtype=np.uint32)
+    got_vals = np.array([float(l.split()[2]) for l in body[1:]], dtype=np.float32)
+    assert np.array_equal(got_cols, exp.col)
+    np.testing.assert_allclose(got_vals, exp.val, rtol=1e-5)
+    # --quant-subset keeps the listed barcodes only, in matrix order
+    keep = [3, 17, 42]
+    open(tmp_path / "subset.txt", "w").write("".join(host.decode_barcode(bcs[i], 16) + "\n" for i in keep))
+    out3 = str(tmp_path / "inferred_subset")
+    host.infer(os.path.join(out, "alevin", "geqc_counts.mtx"), os.path.join(out, "alevin", "gene_eqclass.txt.gz"), out3, usa_mode=usa,
+               filter_list=str(tmp_path / "subset.txt"))
+    assert open(os.path.join(out3, "quants_mat_rows.txt")).read().split("\n")[:-1] == [host.decode_barcode(bcs[i], 16) for i in keep]
+
+
+def test_infer_cli_argument_validation(tmp_path):
+    r = subprocess.run([host.CLI_PATH, "infer", "-c", "x"], capture_output=True, text=True)
+    assert r.returncode == 2 and "required arguments" in r.stderr
+    r = subprocess.run([host.CLI_PATH, "infer", "-c", "x", "-e", "y", "-o", "z", "--use-eds"], capture_output=True, text=True)
+    assert r.returncode == 1 and "--use-eds is no longer supported" in r.stderr
+    with pytest.raises(RuntimeError):
+        host.infer(str(tmp_path / "missing.mtx"), str(tmp_path / "missing.gz"), str(tmp_path / "o"))
