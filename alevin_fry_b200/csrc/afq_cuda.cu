@@ -117,7 +117,9 @@ struct Slot {  // one in-flight host batch
   HBuf<u64> h_cls_ptr, h_lab_base, h_cls_lab_ptr;
   HBuf<u32> h_dq_counts, h_dq_labels;
   u64 n_records = 0;
-  bool has_dump = false;
+  bool has_dump = false, retried = false;
+  afq_batch db{};             // the batch with DEVICE pointers (giant-cell retry)
+  afq_device_out dout{};
   cudaEvent_t ev_h2d = nullptr, ev_done = nullptr, ev_d2h = nullptr;
   u64 n_cells = 0, n_refs = 0, ticket = 0;
   bool busy = false;
@@ -383,6 +385,56 @@ int check_device_error(afq_ctx* c, const Ctl& h) {
   return (h.error & (DEV_ERR_CELL_TOO_LARGE | DEV_ERR_ARENA | DEV_ERR_ADJ_POOL)) ? AFQ_ERR_UNSUPPORTED : AFQ_ERR_INTERNAL;
 }
 
+// the device pipeline of one host batch + the D2H of its small per-cell results, on the compute stream
+int enqueue_slot(afq_ctx* c, Slot& s) {
+  const u64 nc = s.n_cells;
+  const bool dump = c->cfg.dump_eq != 0 && c->cfg.resolution != AFQ_RES_TRIVIAL;
+  int rc = run_pipeline(c, c->work_host, s.db, s.dout, c->s_compute, dump ? &s : nullptr);
+  if (rc != AFQ_OK) return rc;
+  s.has_dump = dump && nc > 0;
+  if (s.has_dump) {
+    CUDA_TRY(c, s.h_cls_ptr.ensure(nc + 2)); CUDA_TRY(c, s.h_lab_base.ensure(nc + 2));
+    CUDA_TRY(c, cudaMemcpyAsync(s.h_cls_ptr.p, s.dq_cls_ptr.p, (nc + 1) * sizeof(u64), cudaMemcpyDeviceToHost, c->s_compute));
+    CUDA_TRY(c, cudaMemcpyAsync(s.h_lab_base.p, s.dq_lab_base.p, (nc + 1) * sizeof(u64), cudaMemcpyDeviceToHost, c->s_compute));
+  }
+  // small per-cell results come back on the compute stream right behind the kernels
+  CUDA_TRY(c, cudaMemcpyAsync(s.h_row_ptr.p, s.row_ptr.p, (nc + 1) * sizeof(u64), cudaMemcpyDeviceToHost, c->s_compute));
+  if (nc) {
+    CUDA_TRY(c, cudaMemcpyAsync(s.h_sum.p, s.sum_umi.p, nc * sizeof(float), cudaMemcpyDeviceToHost, c->s_compute));
+    CUDA_TRY(c, cudaMemcpyAsync(s.h_max.p, s.max_umi.p, nc * sizeof(float), cudaMemcpyDeviceToHost, c->s_compute));
+    CUDA_TRY(c, cudaMemcpyAsync(s.h_num_expr.p, s.num_expr.p, nc * sizeof(u32), cudaMemcpyDeviceToHost, c->s_compute));
+    CUDA_TRY(c, cudaMemcpyAsync(s.h_num_over_mean.p, s.num_over_mean.p, nc * sizeof(u32), cudaMemcpyDeviceToHost, c->s_compute));
+    CUDA_TRY(c, cudaMemcpyAsync(s.h_flags.p, s.flags.p, nc * sizeof(u8), cudaMemcpyDeviceToHost, c->s_compute));
+    CUDA_TRY(c, cudaMemcpyAsync(s.h_ctl.p, c->work_host.ctl.p, sizeof(Ctl), cudaMemcpyDeviceToHost, c->s_compute));
+  } else {
+    memset(s.h_ctl.p, 0, sizeof(Ctl));
+  }
+  return AFQ_OK;
+}
+
+// A cell had more alignments than the giant-cell arenas hold (DEV_ERR_CELL_TOO_LARGE): grow the arenas to fit it — fewer,
+// larger ones within the same memory budget — and run the batch again. Its inputs are still in the slot's device buffers.
+int grow_large_arena_and_rerun(afq_ctx* c, Slot& s, u32 max_cell_refs) {
+  u32 log2cap = c->large_cap_log2;
+  while (log2cap < 31 && (1ull << log2cap) < 2ull * max_cell_refs) ++log2cap;
+  if ((1ull << log2cap) < 2ull * max_cell_refs) { c->err = "a cell has more than 2^30 alignments"; return AFQ_ERR_UNSUPPORTED; }
+  CUDA_TRY(c, cudaStreamSynchronize(c->s_compute));           // no batch may be using the arenas
+  const size_t budget = (size_t)c->large_blocks << c->large_cap_log2;     // entries held today
+  u32 blocks = (u32)std::max<size_t>(1, std::min<size_t>(c->large_blocks, budget >> log2cap));
+  const size_t entries = (size_t)blocks << log2cap;
+  if (c->large_keys) cudaFree(c->large_keys);
+  if (c->large_cnts) cudaFree(c->large_cnts);
+  c->large_keys = nullptr; c->large_cnts = nullptr;
+  CUDA_TRY(c, cudaMalloc((void**)&c->large_keys, entries * sizeof(u64)));
+  CUDA_TRY(c, cudaMalloc((void**)&c->large_cnts, entries * sizeof(u32)));
+  c->large_cap_log2 = log2cap; c->large_blocks = blocks;
+  s.retried = true;
+  int rc = enqueue_slot(c, s);
+  if (rc != AFQ_OK) return rc;
+  CUDA_TRY(c, cudaStreamSynchronize(c->s_compute));
+  return AFQ_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -599,28 +651,9 @@ int afq_submit(afq_ctx* c, const afq_batch* hb, uint64_t* ticket) {
   o.col = s.col.p; o.val = s.val.p; o.cap_nnz = nf + 1;
   o.sum_umi = s.sum_umi.p; o.max_umi = s.max_umi.p;
   o.num_expr = s.num_expr.p; o.num_over_mean = s.num_over_mean.p; o.flags = s.flags.p;
-  const bool dump = c->cfg.dump_eq != 0 && c->cfg.resolution != AFQ_RES_TRIVIAL;
-  int rc = run_pipeline(c, c->work_host, db, o, c->s_compute, dump ? &s : nullptr);
+  s.db = db; s.dout = o; s.n_cells = nc; s.n_refs = nf; s.n_records = nr; s.retried = false;
+  int rc = enqueue_slot(c, s);
   if (rc != AFQ_OK) return rc;
-  s.has_dump = dump && nc > 0;
-  s.n_records = nr;
-  if (s.has_dump) {
-    CUDA_TRY(c, s.h_cls_ptr.ensure(nc + 2)); CUDA_TRY(c, s.h_lab_base.ensure(nc + 2));
-    CUDA_TRY(c, cudaMemcpyAsync(s.h_cls_ptr.p, s.dq_cls_ptr.p, (nc + 1) * sizeof(u64), cudaMemcpyDeviceToHost, c->s_compute));
-    CUDA_TRY(c, cudaMemcpyAsync(s.h_lab_base.p, s.dq_lab_base.p, (nc + 1) * sizeof(u64), cudaMemcpyDeviceToHost, c->s_compute));
-  }
-  // small per-cell results come back on the compute stream right behind the kernels
-  CUDA_TRY(c, cudaMemcpyAsync(s.h_row_ptr.p, s.row_ptr.p, (nc + 1) * sizeof(u64), cudaMemcpyDeviceToHost, c->s_compute));
-  if (nc) {
-    CUDA_TRY(c, cudaMemcpyAsync(s.h_sum.p, s.sum_umi.p, nc * sizeof(float), cudaMemcpyDeviceToHost, c->s_compute));
-    CUDA_TRY(c, cudaMemcpyAsync(s.h_max.p, s.max_umi.p, nc * sizeof(float), cudaMemcpyDeviceToHost, c->s_compute));
-    CUDA_TRY(c, cudaMemcpyAsync(s.h_num_expr.p, s.num_expr.p, nc * sizeof(u32), cudaMemcpyDeviceToHost, c->s_compute));
-    CUDA_TRY(c, cudaMemcpyAsync(s.h_num_over_mean.p, s.num_over_mean.p, nc * sizeof(u32), cudaMemcpyDeviceToHost, c->s_compute));
-    CUDA_TRY(c, cudaMemcpyAsync(s.h_flags.p, s.flags.p, nc * sizeof(u8), cudaMemcpyDeviceToHost, c->s_compute));
-    CUDA_TRY(c, cudaMemcpyAsync(s.h_ctl.p, c->work_host.ctl.p, sizeof(Ctl), cudaMemcpyDeviceToHost, c->s_compute));
-  } else {
-    memset(s.h_ctl.p, 0, sizeof(Ctl));
-  }
   CUDA_TRY(c, cudaEventRecord(s.ev_done, c->s_compute));
   s.n_cells = nc; s.n_refs = nf; s.ticket = t; s.busy = true;
   c->next_ticket++;
@@ -641,6 +674,10 @@ int afq_wait(afq_ctx* c, uint64_t ticket, afq_result* out) {
   cudaError_t e = cudaEventSynchronize(s.ev_done);
   lk.lock();
   if (e != cudaSuccess) { c->err = std::string("cudaEventSynchronize(ev_done): ") + cudaGetErrorString(e); s.busy = false; return AFQ_ERR_CUDA; }
+  if ((s.h_ctl.p->error & DEV_ERR_CELL_TOO_LARGE) && !s.retried) {
+    const int rr = grow_large_arena_and_rerun(c, s, s.h_ctl.p->max_cell_refs);
+    if (rr != AFQ_OK) { s.busy = false; return rr; }
+  }
   int rc = check_device_error(c, *s.h_ctl.p);
   if (rc != AFQ_OK) { s.busy = false; return rc; }
   const u64 nnz = s.h_row_ptr.p[s.n_cells];

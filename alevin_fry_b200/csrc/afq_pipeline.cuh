@@ -276,7 +276,7 @@ int enqueue_batch(L& l, const afq_config& cfg, int force_bin, const PipeBufs& pb
 }
 
 inline const char* device_error_string(const Ctl& h, std::string& buf) {
-  if (h.error & DEV_ERR_CELL_TOO_LARGE) buf = "a cell has " + std::to_string(h.max_cell_refs) + " alignments, more than the giant-cell arena holds (raise AFQ_LARGE_CAP_LOG2)";
+  if (h.error & DEV_ERR_CELL_TOO_LARGE) buf = "a cell has " + std::to_string(h.max_cell_refs) + " alignments, more than the giant-cell arena holds (the host API grows the arena and retries; with afq_quant_device raise AFQ_LARGE_CAP_LOG2)";
   else if (h.error & DEV_ERR_ADJ_POOL) buf = "PUG adjacency pool exhausted";
   else if (h.error & DEV_ERR_ARENA) buf = "a cell does not fit the gene-eq-class arena";
   else if (h.error & DEV_ERR_HASH) buf = "eq-class label hash collision not resolved after reseeding";

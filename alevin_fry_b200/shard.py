@@ -1,9 +1,11 @@
 """Multi-GPU plumbing for the cell-sharded quant path.
 
 Cells are independent work items (reference src/quant.rs:1389, 735), so ranks take contiguous
-cell ranges and never exchange data during compute. The only collective is an all-gather of
-per-cell row lengths, from which every rank derives the global CSR row pointer / its own row
-offset in the global matrix. Works with NCCL (CUDA tensors) and gloo (CPU tensors)."""
+cell ranges and never exchange data during compute. The collectives belong to the ASSEMBLY of the one
+output matrix (reference: every worker's triplets end up in one TriMat, src/quant.rs:1811-1847): an
+all-gather of per-cell row lengths, from which every rank derives the global CSR row pointer, and a
+variable-length all-gather of the (col, val) payload. Works with NCCL (CUDA tensors, NVLink / NVSwitch)
+and gloo (CPU tensors)."""
 from typing import Tuple
 
 import torch
@@ -38,3 +40,43 @@ def global_row_ptr(lengths: torch.Tensor, n_cells: int, world: int) -> torch.Ten
     rp = torch.zeros(n_cells + 1, dtype=torch.int64, device=lengths.device)
     torch.cumsum(allc, 0, out=rp[1:])
     return rp
+
+
+def assemble_csr(num_expr: torch.Tensor, col: torch.Tensor, val: torch.Tensor, n_cells: int, group=None, scratch=None, compact=True):
+    """The one sparse matrix of the job on every rank: (row_ptr int64 [n_cells+1], col int32 [nnz], val float32 [nnz]).
+
+    Rank r holds the rows of its cell range (shard_range) as CSR pieces `num_expr` (row lengths) and `col` / `val`
+    (only the first sum(num_expr) entries are used). Two collectives: row lengths (padded to the largest range), then
+    the payload padded to the largest per-rank nnz — one all_gather_into_tensor each for col and val, so that NCCL
+    moves two large messages per rank over NVLink instead of many small ones. `scratch` (a dict) keeps the padded
+    buffers between calls. compact=False skips the final concatenation and returns the gathered, padded payload
+    (rank r's entries start at r * stride): (row_ptr, col_padded, val_padded, stride, nnz_per_rank)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    dev = num_expr.device
+    _, mine = shard_range(n_cells, rank, world)
+    max_cells = max(shard_range(n_cells, r, world)[1] for r in range(world))
+    lens = gather_row_lengths(num_expr[:mine], max_cells, group)
+    nnz_r = lens.to(torch.int64).sum(dim=1)                      # [world] (padding rows are zero)
+    max_nnz = int(nnz_r.max().item())
+    my_nnz = int(nnz_r[rank].item())
+    scratch = scratch if scratch is not None else {}
+    key = (max_nnz, world, str(dev))
+    if scratch.get("key") != key:
+        scratch["key"] = key
+        scratch["pc"] = torch.zeros(max(max_nnz, 1), dtype=torch.int32, device=dev)
+        scratch["pv"] = torch.zeros(max(max_nnz, 1), dtype=torch.float32, device=dev)
+        scratch["ac"] = torch.empty(world * max(max_nnz, 1), dtype=torch.int32, device=dev)
+        scratch["av"] = torch.empty(world * max(max_nnz, 1), dtype=torch.float32, device=dev)
+    pc, pv, ac, av = scratch["pc"], scratch["pv"], scratch["ac"], scratch["av"]
+    pc[:my_nnz] = col[:my_nnz].to(torch.int32)
+    pv[:my_nnz] = val[:my_nnz]
+    dist.all_gather_into_tensor(ac, pc, group=group)
+    dist.all_gather_into_tensor(av, pv, group=group)
+    rp = global_row_ptr(lens, n_cells, world)
+    m = max(max_nnz, 1)
+    if not compact:
+        return rp, ac, av, m, nnz_r
+    cols = torch.cat([ac[r * m: r * m + int(nnz_r[r].item())] for r in range(world)])
+    vals = torch.cat([av[r * m: r * m + int(nnz_r[r].item())] for r in range(world)])
+    return rp, cols, vals

@@ -244,13 +244,16 @@ def measure_config(args, name, cells, res, ctx):
               sum_umi=torch.empty(nc, dtype=torch.float32, device=dev), max_umi=torch.empty(nc, dtype=torch.float32, device=dev),
               num_expr=torch.empty(nc, dtype=torch.int32, device=dev), num_over_mean=torch.empty(nc, dtype=torch.int32, device=dev),
               flags=torch.empty(nc, dtype=torch.uint8, device=dev))
-    counts_all = torch.empty(world * nc, dtype=torch.int32, device=dev) if world > 1 else None
+    asm_scratch = {}
     stream = torch.cuda.current_stream().cuda_stream
 
     def step_device():
         q.quant_device(db, do, stream)
-        if world > 1:  # global matrix index: every rank learns every rank's row lengths
-            dist.all_gather_into_tensor(counts_all, do["num_expr"])
+        if world > 1:
+            # assembly of the ONE sparse matrix of the job (north_star: "an NCCL all-gather only for the final sparse matrix
+            # assembly"): row lengths + the (col, val) payload of every rank, gathered over NVLink onto every rank
+            from alevin_fry_b200 import shard
+            shard.assemble_csr(do["num_expr"], do["col"], do["val"], nc * world, scratch=asm_scratch, compact=False)
 
     def barrier():
         if world > 1:
@@ -389,7 +392,7 @@ def measure_config(args, name, cells, res, ctx):
         "gpu_launches": int(launches) + 0, "clocks": clocks,
     }
     q.close()
-    del db, do, counts_all, parts
+    del db, do, asm_scratch, parts
     pool.close()
     torch.cuda.empty_cache()
     return out

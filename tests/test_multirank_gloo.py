@@ -34,8 +34,13 @@ def _worker(rank, world, port, n_cells, out):
     rp = shard.global_row_ptr(lens, n_cells, world)
     # every rank's own rows land at rp[first : first+cnt+1]
     assert torch.equal(rp[first:first + cnt + 1] - rp[first], torch.from_numpy(mine.row_ptr.astype(np.int64)))
+    # ... and the payload: one matrix on every rank (variable-length all-gather)
+    rp2, cols, vals = shard.assemble_csr(torch.from_numpy(mine.num_expr.astype(np.int32)), torch.from_numpy(mine.col.astype(np.int32)),
+                                         torch.from_numpy(mine.val), n_cells)
+    whole = oracle_lib.oracle_quant(opts, t2g, synth.generate(spec, 0, n_cells, n_threads=2), n_threads=2)
+    assert torch.equal(rp2, rp)
+    assert np.array_equal(cols.numpy().astype(np.uint32), whole.col) and np.array_equal(vals.numpy(), whole.val)
     if rank == 0:
-        whole = oracle_lib.oracle_quant(opts, t2g, synth.generate(spec, 0, n_cells, n_threads=2), n_threads=2)
         out.put((rp.numpy().tolist() == whole.row_ptr.astype(np.int64).tolist(), int(rp[-1]), int(whole.nnz)))
     dist.barrier()
     dist.destroy_process_group()
