@@ -76,7 +76,7 @@ struct Work {  // per-pipeline scratch (ordered on one stream)
   DBuf<u8> ge_arena[2];
   DBuf<u32> adj_pool;
   DBuf<u32> ps_garena;     // k_pug_smem<3> arenas
-  DBuf<u32> ps_win, ps_nwin, ps_mem, ps_desc, ps_glab;   // split parsimony path (afq_pugc.cuh)
+  DBuf<u32> ps_win, ps_nwin, ps_mem, ps_desc, ps_glab, ps_mlab, ps_nlab, ps_moff, ps_mlen, ps_back_list, ps_back_garena;   // split parsimony path (afq_pugc.cuh)
   DBuf<u64> na_tiles;      // rec_na8 -> offsets scan
   DBuf<u32> na_ref_off;    // device API: offsets derived from rec_na8
   DBuf<u32> umi_wide, refs_wide;   // rec_umi24 / refs24 widened to u32
@@ -93,6 +93,7 @@ struct Work {  // per-pipeline scratch (ordered on one stream)
     ctl.release(); bin_list.release(); stage_col.release(); stage_val.release();
     tile_sums.release(); ge_arena[0].release(); ge_arena[1].release(); adj_pool.release(); ps_garena.release();
     ps_win.release(); ps_nwin.release(); ps_mem.release(); ps_desc.release(); ps_glab.release();
+    ps_mlab.release(); ps_nlab.release(); ps_moff.release(); ps_mlen.release(); ps_back_list.release(); ps_back_garena.release();
     na_tiles.release(); na_ref_off.release(); umi_wide.release(); refs_wide.release();
   }
 };
@@ -166,6 +167,7 @@ struct afq_ctx {
   bool no_lanes = false;       // AFQ_NO_LANES=1: launch the arena kernels back to back on the caller's stream
   bool no_ps_split = false;    // AFQ_NO_PS_SPLIT=1: unique-only parsimony stays on the single-kernel k_pug_smem (A/B, tests)
   int grid_count = 0;          // k_pug_count's persistent grid (0: its shared memory does not fit => no split path)
+  int grid_back[4] = {0, 0, 0, 0};   // k_pug_back<tier>
   cudaStream_t lanes[NUM_BINS] = {nullptr};
   cudaEvent_t ev_fork = nullptr, ev_lane[NUM_BINS] = {nullptr};
   // pipelines
@@ -264,19 +266,26 @@ struct CudaLauncher {
   int ps_grid(int v) { return (c->no_ps || (v == 3 && c->no_ps_global)) ? 0 : c->grid_ps[v]; }
   u32* ps_garena(u64 words, u32 blocks) { return w->ps_garena.ensure((size_t)words * blocks + 16) == cudaSuccess ? w->ps_garena.p : nullptr; }
   u32 ps_limit_words() { return c->ps_limit_words; }
-  bool ps_split(u64 n_records, u64 n_refs, u64 n_cells, bool gene_labels, PsSplitBufs* o) {
-    if (c->no_ps_split || c->grid_count <= 0) return false;
+  bool ps_split(u64 n_records, u64 n_refs, u64 n_cells, bool gene_labels, bool molecules, PsSplitBufs* o) {
+    if (c->no_ps_split || (molecules ? c->grid_back[0] <= 0 : c->grid_count <= 0)) return false;
     const size_t desc_slots = (size_t)(n_records / 2 + n_records / 3 + n_records / 5 + n_records / 9 + 8);
-    if (w->ps_win.ensure(n_records + 4) != cudaSuccess || w->ps_nwin.ensure(n_cells + 4) != cudaSuccess ||
-        w->ps_mem.ensure(4 * (size_t)n_records + 16) != cudaSuccess || w->ps_desc.ensure(2 * desc_slots) != cudaSuccess ||
-        (gene_labels && w->ps_glab.ensure(n_refs + 4) != cudaSuccess)) {
+    bool ok = w->ps_nwin.ensure(n_cells + 4) == cudaSuccess && w->ps_mem.ensure(4 * (size_t)n_records + 16) == cudaSuccess &&
+              w->ps_desc.ensure(2 * desc_slots) == cudaSuccess && (!gene_labels || w->ps_glab.ensure(n_refs + 4) == cudaSuccess);
+    if (ok && !molecules) ok = w->ps_win.ensure(n_records + 4) == cudaSuccess;
+    if (ok && molecules)
+      ok = w->ps_mlab.ensure(n_refs + 4) == cudaSuccess && w->ps_nlab.ensure(n_cells + 4) == cudaSuccess &&
+           w->ps_moff.ensure(n_records + 4) == cudaSuccess && w->ps_mlen.ensure(n_records + 4) == cudaSuccess &&
+           w->ps_back_list.ensure(4 * (size_t)n_cells + 4) == cudaSuccess;
+    if (!ok) {
       cudaGetLastError();      // out of memory for the split buffers: the single-kernel path still works
       return false;
     }
     o->win = w->ps_win.p; o->nwin = w->ps_nwin.p; o->mem = w->ps_mem.p; o->desc = w->ps_desc.p; o->glab = gene_labels ? w->ps_glab.p : nullptr;
+    o->mlab = w->ps_mlab.p; o->nlab = w->ps_nlab.p; o->moff = w->ps_moff.p; o->mlen = w->ps_mlen.p; o->back_list = w->ps_back_list.p;
     return true;
   }
-  int pc_grid(int which, size_t) { return which == 0 ? c->num_sms * 8 : c->grid_count; }
+  int pc_grid(int which, size_t) { return which == 0 ? c->num_sms * 8 : (which == 1 ? c->grid_count : c->grid_back[which - 2]); }
+  u32* back_garena(u64 words, u32 blocks) { return w->ps_back_garena.ensure((size_t)words * blocks + 16) == cudaSuccess ? w->ps_back_garena.p : nullptr; }
   // fork / join: lanes are ctx-owned non-blocking streams ordered after / before the caller stream
   void fork(int n) {
     if (c->no_lanes) return;
@@ -525,6 +534,19 @@ int afq_create(const afq_config* cfg, const uint32_t* tid_to_gid, uint64_t n_ref
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pug_count, (int)PC_THREADS, csm) == cudaSuccess && occ >= 1)
       c->grid_count = occ * c->num_sms;
     else cudaGetLastError();
+  }
+  {   // k_pug_back<tier>: the back end's arrays in dynamic shared memory (48 / 100 / 224 KB) or per-CTA global arenas
+    int o0 = 0, o1 = 0, o2 = 0, o3 = 0;
+    if (cudaFuncSetAttribute(k_pug_back<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(pb_arena_words(0) * 4)) == cudaSuccess &&
+        cudaFuncSetAttribute(k_pug_back<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(pb_arena_words(1) * 4)) == cudaSuccess &&
+        cudaFuncSetAttribute(k_pug_back<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(pb_arena_words(2) * 4)) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o0, k_pug_back<0>, (int)PB_THREADS, pb_arena_words(0) * 4) == cudaSuccess && o0 >= 1 &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, k_pug_back<1>, (int)PB_THREADS, pb_arena_words(1) * 4) == cudaSuccess && o1 >= 1 &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, k_pug_back<2>, (int)PB_THREADS, pb_arena_words(2) * 4) == cudaSuccess && o2 >= 1 &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o3, k_pug_back<3>, (int)PB_THREADS, 0) == cudaSuccess && o3 >= 1) {
+      c->grid_back[0] = o0 * c->num_sms; c->grid_back[1] = o1 * c->num_sms; c->grid_back[2] = o2 * c->num_sms;
+      c->grid_back[3] = c->num_sms;     // (tier 3: one global arena per SM)
+    } else cudaGetLastError();
   }
   {
     int occ = 0;

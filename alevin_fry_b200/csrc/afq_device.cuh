@@ -32,6 +32,31 @@ __device__ __forceinline__ u32 hash_key(u64 k, u32 log2cap) {
 
 __device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31; }
 
+// ---- bulk copies global -> shared memory (cp.async.bulk, completion on an mbarrier; SASS: UBLKCP + SYNCS) ----------------
+// One thread arms the barrier with the byte count and issues the copies; the copy engine moves the data and every thread
+// waits on the barrier's phase. Source and destination must be 16-byte aligned, sizes multiples of 16 bytes.
+#ifndef AFQ_EMU
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64* bar, u32 count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64* bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, u32 bytes, u64* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
+  asm volatile("{\n.reg .pred P1;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}"
+               ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+#endif
+#ifndef AFQ_EMU
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#endif
+
 // ---- block-wide exclusive scan of one u32 per thread (blockDim.x <= 1024) -------------
 // s_warp must hold 33 u32. Returns the exclusive prefix; *total gets the block sum.
 __device__ __forceinline__ u32 block_exscan(u32 v, u32* s_warp, u32* total) {

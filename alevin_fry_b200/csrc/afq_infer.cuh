@@ -44,24 +44,6 @@ __host__ __device__ inline u64 inf_need_words(u64 C, u64 E, u64 S, bool usa) {
 }
 __host__ __device__ inline size_t inf_smem_bytes(u32 num_alphas) { return 4ull * (2ull * ((num_alphas + 31) / 32) + INF_ARENA_WORDS + 8); }
 
-#ifndef AFQ_EMU
-__device__ __forceinline__ u32 inf_smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void inf_mbar_init(u64* bar, u32 count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(inf_smem_u32(bar)), "r"(count));
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void inf_mbar_expect_tx(u64* bar, u32 bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(inf_smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void inf_bulk_g2s(void* dst, const void* src, u32 bytes, u64* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(inf_smem_u32(dst)), "l"(src), "r"(bytes), "r"(inf_smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void inf_mbar_wait(u64* bar, u32 parity) {
-  asm volatile("{\n.reg .pred P1;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}"
-               ::"r"(inf_smem_u32(bar)), "r"(parity) : "memory");
-}
-#endif
 
 __global__ void __launch_bounds__(INF_THREADS) k_em_subset(InferArgs p) {
   AFQ_DYN_SMEM(smem_raw);
@@ -76,7 +58,7 @@ __global__ void __launch_bounds__(INF_THREADS) k_em_subset(InferArgs p) {
   const u32 T = blockDim.x, tid = threadIdx.x;
   u32 phase = 0;
 #ifndef AFQ_EMU
-  if (tid == 0) inf_mbar_init(&s_bar, 1);
+  if (tid == 0) mbar_init(&s_bar, 1);
   __syncthreads();
 #endif
   for (;;) {
@@ -123,12 +105,12 @@ __global__ void __launch_bounds__(INF_THREADS) k_em_subset(InferArgs p) {
 #ifndef AFQ_EMU
     if (in_smem) {
       if (tid == 0) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic-proxy accesses of the arena are ordered first
-        inf_mbar_expect_tx(&s_bar, 2 * rowlen * 4);
-        inf_bulk_g2s(ceq_raw, p.cell_eq + (o0 - lead), rowlen * 4, &s_bar);
-        inf_bulk_g2s(ccnt_raw, p.cell_cnt + (o0 - lead), rowlen * 4, &s_bar);
+        fence_proxy_async();                             // earlier generic-proxy accesses of the arena are ordered first
+        mbar_expect_tx(&s_bar, 2 * rowlen * 4);
+        bulk_g2s(ceq_raw, p.cell_eq + (o0 - lead), rowlen * 4, &s_bar);
+        bulk_g2s(ccnt_raw, p.cell_cnt + (o0 - lead), rowlen * 4, &s_bar);
       }
-      inf_mbar_wait(&s_bar, phase);
+      mbar_wait(&s_bar, phase);
       phase ^= 1;
     } else
 #endif

@@ -43,12 +43,13 @@ struct Ctl {                       // per-batch device control block (zeroed per
   u32 ps3_max_n, ps3_max_p;        // largest cell on k_pug_smem<3>'s list (sizes its global arenas)
   u32 desc_count[4];               // split path: component descriptors on the lists of sizes 2 | 3-4 | 5-8 | 9-32
   u32 desc_cursor[4];              // ... and the cover kernels' work cursors
-  u32 count_cursor;                // k_pug_count's work cursor over the cells of the four k_pug_build lists
+  u32 count_cursor;                // k_pug_count's / k_pug_back's work cursor over the cells of the four k_pug_build lists
+  u32 back_count[4], back_cursor[4];     // k_pug_back's arena tiers: cells / work cursors
 };
 
 struct KArgs {
   // input batch (device)
-  u64 n_cells;
+  u64 n_cells, n_records, n_refs_total;
   const u64* cell_rec_off;
   const u32* umi;
   const u32* ref_off;

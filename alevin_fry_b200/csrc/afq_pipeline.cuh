@@ -19,9 +19,10 @@
 //   int  ps_grid(int variant);                                // persistent grid of k_pug_smem<variant>; 0 = disabled
 //   u32* ps_garena(u64 words_per_block, u32 blocks);          // grow-only global arenas of k_pug_smem<3>, nullptr on failure
 //   u32  ps_limit_words();                                    // 0, or a smaller arena for k_pug_smem (tests: forces fallbacks)
-//   bool ps_split(u64 n_records, u64 n_refs, u64 n_cells, bool gene_labels, PsSplitBufs* out);
+//   bool ps_split(u64 n_records, u64 n_refs, u64 n_cells, bool gene_labels, bool molecules, PsSplitBufs* out);
 //                                                              // grow-only global buffers of the split parsimony path; false = not available
-//   int  pc_grid(int which, size_t smem);                     // grid of the flat cover kernels (0) / of k_pug_count (1)
+//   int  pc_grid(int which, size_t smem);                     // grid of the flat cover kernels (0) / k_pug_count (1) / k_pug_back tiers 0..3 (2..5)
+//   u32* back_garena(u64 words_per_block, u32 blocks);        // grow-only global arenas of k_pug_back<3>, nullptr on failure
 #pragma once
 #include <string>
 
@@ -37,7 +38,7 @@ enum KernelId : int {
   KID_BIN = 0, KID_SMEM0 = 1, KID_LARGE = 7, KID_SCAN_SUMS = 8, KID_SCAN_TILES = 9, KID_SCAN_ROWS = 10,
   KID_GATHER = 11, KID_GENE_EQC = 12, KID_GENE_EQC_BIG = 13, KID_BIN_GE = 14, KID_REGION = 15, KID_NA_OFFSETS = 16, KID_UNPACK24 = 17,
   KID_PUG_SMEM0 = 18, KID_PUG_REGION = 22, KID_PUG_BUILD0 = 23, KID_PUG_COVER2 = 27, KID_PUG_COVER4 = 28,
-  KID_PUG_COVER8 = 29, KID_PUG_COVERW = 30, KID_PUG_COUNT = 31, KID_COVER_REGION = 32, NUM_KID = 33
+  KID_PUG_COVER8 = 29, KID_PUG_COVERW = 30, KID_PUG_COUNT = 31, KID_COVER_REGION = 32, KID_PUG_BACK = 33, KID_BACK_REGION = 38, NUM_KID = 39
 };
 static const char* const KID_NAMES[NUM_KID] = {
     "k_bin_cells", "k_resolve_smem<0>", "k_resolve_smem<1>", "k_resolve_smem<2>", "k_resolve_smem<3>",
@@ -45,7 +46,7 @@ static const char* const KID_NAMES[NUM_KID] = {
     "k_scan_rows", "k_gather_rows", "k_gene_eqc", "k_gene_eqc(big cells)", "k_bin_cells_ge", "resolve_region(wall)",
     "k_na_offsets(+tile sums)", "k_unpack24", "k_pug_smem<0>", "k_pug_smem<1>", "k_pug_smem<2>", "k_pug_smem<3>(global arena)", "pug_region(wall)",
     "k_pug_build<0>", "k_pug_build<1>", "k_pug_build<2>", "k_pug_build<3>(global arena)", "k_pug_cover2", "k_pug_cover_g<4>", "k_pug_cover_g<8>",
-    "k_pug_cover_w", "k_pug_count", "cover_region(wall)"};
+    "k_pug_cover_w", "k_pug_count", "cover_region(wall)", "k_pug_back<0>", "k_pug_back<1>", "k_pug_back<2>", "k_pug_back<3>(global arena)", "k_back_bin", "back_region(wall)"};
 
 struct PipeBufs {  // device scratch owned by the caller (one set per stream-ordered pipeline)
   Ctl* ctl;
@@ -60,7 +61,7 @@ struct PipeBufs {  // device scratch owned by the caller (one set per stream-ord
   u32* dump_ncls = nullptr; u32* dump_nlab = nullptr; u32* dump_cnt = nullptr; u32* dump_off = nullptr; u32* dump_lab = nullptr;
 };
 
-struct PsSplitBufs { u32* win; u32* nwin; u32* mem; u32* desc; u32* glab; };
+struct PsSplitBufs { u32* win; u32* nwin; u32* mem; u32* desc; u32* glab; u32* mlab; u32* nlab; u32* moff; u32* mlen; u32* back_list; };
 
 inline bool res_is_pug(int r) {
   return r == AFQ_RES_PARSIMONY || r == AFQ_RES_PARSIMONY_EM || r == AFQ_RES_PARSIMONY_GENE || r == AFQ_RES_PARSIMONY_GENE_EM;
@@ -118,7 +119,7 @@ int enqueue_batch(L& l, const afq_config& cfg, int force_bin, const PipeBufs& pb
                   const afq_device_out& o, std::string& err) {
   if (b.n_cells == 0) return l.memset_zero(o.row_ptr, sizeof(u64)) ? AFQ_ERR_CUDA : AFQ_OK;
   KArgs a{};
-  a.n_cells = b.n_cells;
+  a.n_cells = b.n_cells; a.n_records = b.n_records; a.n_refs_total = b.n_refs_total;
   a.cell_rec_off = b.cell_rec_offsets;
   a.umi = b.rec_umi32;
   a.ref_off = b.rec_ref_offsets;
@@ -173,8 +174,17 @@ int enqueue_batch(L& l, const afq_config& cfg, int force_bin, const PipeBufs& pb
     // (cr-like-em in USA mode stays on k_gene_eqc: its EM back end over 3 slots per gene needs the
     // 224 KB / global arenas for ordinary cells, where one CTA per SM iterates slower than k_gene_eqc's
     // four — measured r1x: C4 76.4 ms with k_pug_smem vs 64.2 ms without)
-    const bool ps_on = l.ps_grid(0) > 0 && (g.ge_mode == GE_MODE_CRLIKE ? (!cfg.usa_mode && !a.prefer_ambig) : cfg.large_graph_thresh >= 2);
-    const u32 ps_mode = ps_on ? (1u | (g.ge_mode == GE_MODE_PUG_GENE ? 2u : 0u) | ((g.only_unique && !dump) ? 0u : 4u) | (l.ps_grid(3) > 0 ? 8u : 0u)) : 0u;
+    // The SPLIT form (afq_pugc.cuh): k_pug_build per cell -> flat k_pug_cover* over the batch -> k_pug_count (unique-only)
+    // or k_pug_back (EM resolutions / --dump-eqclasses: the shared back end on the cells' molecules in a global pool).
+    const bool want_mol = !g.only_unique || dump;
+    PsSplitBufs sb{};
+    const bool split = l.ps_grid(0) > 0 && !a.prefer_ambig && b.n_cells < (1ull << 24) &&
+                       (g.ge_mode == GE_MODE_CRLIKE ? want_mol : cfg.large_graph_thresh >= 2) &&
+                       (want_mol || pc_count_smem_bytes(cfg.num_rows) <= 200 * 1024) &&
+                       l.ps_split(b.n_records, b.n_refs_total, b.n_cells, g.ge_mode == GE_MODE_PUG_GENE, want_mol, &sb);
+    const bool ps_on = split || (l.ps_grid(0) > 0 && (g.ge_mode == GE_MODE_CRLIKE ? (!cfg.usa_mode && !a.prefer_ambig) : cfg.large_graph_thresh >= 2));
+    // (bit 2: the in-kernel arena also holds the molecules and the EM back end — not on the split path)
+    const u32 ps_mode = ps_on ? (1u | (g.ge_mode == GE_MODE_PUG_GENE ? 2u : 0u) | ((want_mol && !split) ? 4u : 0u) | (l.ps_grid(3) > 0 ? 8u : 0u)) : 0u;
     l.launch(KID_BIN_GE, k_bin_cells_ge, bin_grid, 256u, (size_t)0, a, force_bin, GE_BIG_RECORDS, l.need_shift(), ps_mode);
     launch_crlike_bins(l, a, pb);
     Ctl h{};
@@ -193,12 +203,9 @@ int enqueue_batch(L& l, const afq_config& cfg, int force_bin, const PipeBufs& pb
     // overlaps the others instead of idling the chip (14.5 + 7.3 + 10.3 + 5.5 ms back to back)
     u32 ps_cells = 0;
     // unique-only parsimony resolutions take the SPLIT form (afq_pugc.cuh): build per cell, cover flat over the batch, count per cell
-    PsSplitBufs sb{};
-    const bool split = ps_on && g.only_unique && !dump && g.ge_mode != GE_MODE_CRLIKE && b.n_cells < (1ull << 24) &&
-                       pc_count_smem_bytes(cfg.num_rows) <= 200 * 1024 &&
-                       l.ps_split(b.n_records, b.n_refs_total, b.n_cells, g.ge_mode == GE_MODE_PUG_GENE, &sb);
     if (split) {
       g.ps_win = sb.win; g.ps_nwin = sb.nwin; g.ps_mem = sb.mem; g.ps_desc = sb.desc; g.ps_glab = sb.glab;
+      g.ps_mlab = sb.mlab; g.ps_nlab = sb.nlab; g.ps_moff = sb.moff; g.ps_mlen = sb.mlen; g.back_list = sb.back_list;
       const u64 nr = b.n_records;
       g.ps_desc_base[0] = 0;
       g.ps_desc_base[1] = (u32)(nr / 2 + 1);
@@ -237,20 +244,40 @@ int enqueue_batch(L& l, const afq_config& cfg, int force_bin, const PipeBufs& pb
     l.join();
     l.region_end(KID_PUG_REGION);
     if (split && ps_cells) {
-      // the four size classes are independent: forked onto lanes, rarest / most expensive first
-      const unsigned cg = (unsigned)l.pc_grid(0, 0);
-      l.region_begin();
-      l.fork(4);
-      l.lane(3); l.launch(KID_PUG_COVERW, k_pug_cover_w, cg, PC_THREADS, (size_t)0, a, g);
-      l.lane(2); l.launch(KID_PUG_COVER8, k_pug_cover_g<8, 2>, cg, PC_THREADS, (size_t)0, a, g);
-      l.lane(1); l.launch(KID_PUG_COVER4, k_pug_cover_g<4, 1>, cg, PC_THREADS, (size_t)0, a, g);
-      l.lane(0); l.launch(KID_PUG_COVER2, k_pug_cover2, cg, PC_THREADS, (size_t)0, a, g);
-      l.join();
-      l.region_end(KID_COVER_REGION);
-      const size_t csm = pc_count_smem_bytes(cfg.num_rows);
-      unsigned cb = (unsigned)l.pc_grid(1, csm);
-      if (cb > ps_cells) cb = ps_cells;
-      l.launch(KID_PUG_COUNT, k_pug_count, cb, PC_THREADS, csm, a, g);
+      if (g.ge_mode != GE_MODE_CRLIKE) {
+        // the four size classes are independent: forked onto lanes, rarest / most expensive first
+        const unsigned cg = (unsigned)l.pc_grid(0, 0);
+        l.region_begin();
+        l.fork(4);
+        l.lane(3); l.launch(KID_PUG_COVERW, k_pug_cover_w, cg, PC_THREADS, (size_t)0, a, g);
+        l.lane(2); l.launch(KID_PUG_COVER8, k_pug_cover_g<8, 2>, cg, PC_THREADS, (size_t)0, a, g);
+        l.lane(1); l.launch(KID_PUG_COVER4, k_pug_cover_g<4, 1>, cg, PC_THREADS, (size_t)0, a, g);
+        l.lane(0); l.launch(KID_PUG_COVER2, k_pug_cover2, cg, PC_THREADS, (size_t)0, a, g);
+        l.join();
+        l.region_end(KID_COVER_REGION);
+      }
+      if (!want_mol) {
+        const size_t csm = pc_count_smem_bytes(cfg.num_rows);
+        unsigned cb = (unsigned)l.pc_grid(1, csm);
+        if (cb > ps_cells) cb = ps_cells;
+        l.launch(KID_PUG_COUNT, k_pug_count, cb, PC_THREADS, csm, a, g);
+      } else {
+        // tier 3's per-CTA global arenas hold any cell of the batch (molecules <= records, label words <= alignments)
+        const u64 gw = (ps_back_words(h.ge_max_n[1], h.ge_max_p[1], cfg.usa_mode ? 3u : 1u) + 15) & ~3ull;
+        const unsigned g3 = (unsigned)l.pc_grid(5, 0);
+        g.back_garena = gw < 0xFFFFFFF0ull ? l.back_garena(gw, g3) : nullptr;
+        g.back_garena_words = (u32)gw;
+        if (!g.back_garena) { err = "k_pug_back global arena allocation failed"; return AFQ_ERR_CUDA; }
+        l.launch(KID_PUG_BACK + 4, k_back_bin, (unsigned)((ps_cells + 255) / 256), 256u, (size_t)0, a, g);
+        l.region_begin();
+        l.fork(PB_TIERS);
+        l.lane(3); l.launch(KID_PUG_BACK + 3, k_pug_back<3>, g3, PB_THREADS, (size_t)0, a, g);
+        l.lane(2); l.launch(KID_PUG_BACK + 2, k_pug_back<2>, (unsigned)l.pc_grid(4, 0), PB_THREADS, (size_t)pb_arena_words(2) * 4, a, g);
+        l.lane(1); l.launch(KID_PUG_BACK + 1, k_pug_back<1>, (unsigned)l.pc_grid(3, 0), PB_THREADS, (size_t)pb_arena_words(1) * 4, a, g);
+        l.lane(0); l.launch(KID_PUG_BACK + 0, k_pug_back<0>, (unsigned)l.pc_grid(2, 0), PB_THREADS, (size_t)pb_arena_words(0) * 4, a, g);
+        l.join();
+        l.region_end(KID_BACK_REGION);
+      }
     }
     for (int which = 0; which < 2; ++which) {
       const int list = which == 0 ? GE_LIST_BIG : GE_LIST_NORMAL;

@@ -66,6 +66,14 @@ struct GeArgs {
   u32* ps_desc;         // [2 * ...]     component descriptors: first member, size << 24 | cell; four size-class lists
   u32* ps_glab;         // [n_refs_total] gene-level labels (parsimony-gene); transcript-level labels are read from the input refs
   u32 ps_desc_base[4];  // first descriptor slot of the lists of sizes 2 | 3-4 | 5-8 | 9-32
+  // ... EM resolutions on the split path: the cells' molecules (sorted gene labels) for k_pug_back
+  u32* ps_mlab;         // [n_refs_total] labels of cell c from f0 on (a molecule's label is no longer than one of its records')
+  u32* ps_nlab;         // [n_cells]      label words used
+  u32* ps_moff;         // [n_records]    per molecule (cell region from r0 on): label offset inside the cell ...
+  u32* ps_mlen;         // [n_records]    ... and length; ps_nwin[c] = molecules of the cell
+  u32* back_list;       // [4 * n_cells]  the cells of k_pug_back's four arena tiers (k_back_bin)
+  u32* back_garena;     // per-CTA global arenas of tier 3
+  u32 back_garena_words;
   // --dump-eqclasses (src/quant.rs:1282-1307): every cell's gene eq-classes in canonical order. Cell c (records
   // [r0, r0+n), alignments [f0, f0+P)) writes class j's count / label offset at r0 + j and its labels from f0 on.
   u32* dump_ncls;       // [n_cells]  classes of the cell (zeroed per batch: tiny cells never build gene_eqc)

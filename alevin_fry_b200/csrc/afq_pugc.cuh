@@ -49,7 +49,9 @@ __device__ __forceinline__ PcCtx pc_ctx(const KArgs& a, const GeArgs& g) {
   x.exact = g.pug_exact_umi != 0;
   x.c.a = &a; x.c.refs = nullptr; x.c.roff = nullptr; x.c.roff32 = nullptr; x.c.rlen = nullptr;
   x.c.vumi = nullptr; x.c.vinfo = nullptr; x.c.vgene = nullptr; x.c.gene = gene;
-  x.sk.mode = a.usa_mode ? 1u : 0u; x.sk.uo = a.uo; x.sk.ao = a.ao;
+  const bool em = g.only_unique == 0 || g.dump_ncls != nullptr;     // molecules for k_pug_back instead of output slots
+  x.sk.mode = em ? 3u : (a.usa_mode ? 1u : 0u); x.sk.uo = a.uo; x.sk.ao = a.ao;
+  x.sk.g_lab = nullptr; x.sk.g_nlab = nullptr; x.sk.g_nmol = nullptr; x.sk.g_moff = nullptr; x.sk.g_mlen = nullptr;
   x.sk.A = nullptr; x.sk.lab_lo = x.sk.lab_hi = 0; x.sk.mol_off = x.sk.mol_len = nullptr; x.sk.sh = nullptr; x.sk.ex = nullptr;
   return x;
 }
@@ -58,10 +60,27 @@ __device__ __forceinline__ void pc_put(const PcCtx& x, u32 cell, u32 slot) {
   const u32 r0 = (u32)x.a->cell_rec_off[cell];
   x.g->ps_win[r0 + atomicAdd(&x.g->ps_nwin[cell], 1u)] = slot;
 }
-// the molecule whose label is the positions `inter` of label (li, ln); gv = the label's single gene if it has one
-__device__ __forceinline__ u32 pc_slot_masked(const PcCtx& x, const u32* li, u32 ln, u32 inter, u32 gv) {
-  if (gv < PS_MULTI_GENE && inter != 0) return ps_emit_genes(x.sk, &gv, 1u);
-  return ps_emit(x.c, x.sk, li, ln, [&](u32 q, u32) { return ((inter >> q) & 1u) != 0; });
+// the sink of one cell: output slots (unique-only) or the cell's regions of the global molecule pool (EM)
+__device__ __forceinline__ PsSink pc_sink(const PcCtx& x, u32 cell) {
+  PsSink sk = x.sk;
+  if (sk.mode == 3) {
+    const u64 r0 = x.a->cell_rec_off[cell];
+    const u32 f0 = x.a->ref_off[r0];
+    sk.g_lab = x.g->ps_mlab + f0; sk.g_nlab = x.g->ps_nlab + cell; sk.g_nmol = x.g->ps_nwin + cell;
+    sk.g_moff = x.g->ps_moff + r0; sk.g_mlen = x.g->ps_mlen + r0;
+  }
+  return sk;
+}
+// one molecule of cell `cell` whose transcript label is { li[k] : keep(k, li[k]) }; gv = its single gene if known
+template <class Keep>
+__device__ __forceinline__ void pc_emit(const PcCtx& x, u32 cell, const u32* li, u32 ln, u32 gv, bool gv_ok, Keep keep) {
+  const PsSink sk = pc_sink(x, cell);
+  const u32 slot = (gv < PS_MULTI_GENE && gv_ok) ? ps_emit_genes(sk, &gv, 1u) : ps_emit(x.c, sk, li, ln, keep);
+  if (sk.mode < 2) pc_put(x, cell, slot);
+}
+// ... given as the positions `inter` of label (li, ln)
+__device__ __forceinline__ void pc_emit_masked(const PcCtx& x, u32 cell, const u32* li, u32 ln, u32 inter, u32 gv) {
+  pc_emit(x, cell, li, ln, gv, inter != 0, [&](u32 q, u32) { return ((inter >> q) & 1u) != 0; });
 }
 
 // ---- sizes 2: one thread per component -----------------------------------------------------------------------------
@@ -72,15 +91,13 @@ __global__ void __launch_bounds__(PC_THREADS) k_pug_cover2(KArgs a, GeArgs g) {
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
     const u32 ms = dl[2ull * i], cell = dl[2ull * i + 1] & 0xFFFFFFu;
     const PcMember A = pc_load(g.ps_mem, ms), B = pc_load(g.ps_mem, ms + 1);
-    u32 slot;
-    if (A.gene == B.gene && A.gene < PS_MULTI_GENE) slot = ps_emit_genes(x.sk, &A.gene, 1u);
-    else if (A.cls == B.cls) slot = ps_emit(x.c, x.sk, x.lab + A.cls, A.len, [](u32, u32) { return true; });
+    if (A.gene == B.gene && A.gene < PS_MULTI_GENE) pc_emit(x, cell, x.lab + A.cls, A.len, A.gene, true, [](u32, u32) { return true; });
+    else if (A.cls == B.cls) pc_emit(x, cell, x.lab + A.cls, A.len, NONE32, false, [](u32, u32) { return true; });
     else {
       const u32* lb = x.lab + B.cls;
       const u32 nb = B.len;
-      slot = ps_emit(x.c, x.sk, x.lab + A.cls, A.len, [&](u32, u32 t) { return sorted_contains(lb, nb, t); });
+      pc_emit(x, cell, x.lab + A.cls, A.len, NONE32, false, [&](u32, u32 t) { return sorted_contains(lb, nb, t); });
     }
-    pc_put(x, cell, slot);
   }
 }
 
@@ -200,16 +217,15 @@ __device__ inline void pc_cover_warp(const PcCtx& x, u32 ms, u32 s, u32 cell, u3
       mask = __shfl_sync(0xFFFFFFFFu, my_mask, (int)winner);
     }
     if (lane == winner) {
-      u32 slot;
       if (masked) {
         u32 inter = 0xFFFFFFFFu;
         for (u32 mm = mask; mm; mm &= mm - 1) inter &= Mw[lane * 16 + (u32)__ffs((int)mm) - 1];
-        slot = pc_slot_masked(x, li, ln, inter, s_gen[lane]);
+        pc_emit_masked(x, cell, li, ln, inter, s_gen[lane]);
       } else {      // label = intersection of the MCC's class labels (src/pugutils.rs:1161-1188)
         const u32 first = (u32)__ffs((int)mask) - 1;
         const u32 cf = s_cls[first];
         const u32 rest = mask & (mask - 1);
-        slot = ps_emit(x.c, x.sk, x.lab + cf, s_len[first], [&](u32, u32 t) {
+        pc_emit(x, cell, x.lab + cf, s_len[first], NONE32, false, [&](u32, u32 t) {
           for (u32 r = rest; r; r &= r - 1) {
             const u32 j = (u32)__ffs((int)r) - 1;
             if (s_cls[j] != cf && !sorted_contains(x.lab + s_cls[j], s_len[j], t)) return false;
@@ -217,7 +233,6 @@ __device__ inline void pc_cover_warp(const PcCtx& x, u32 ms, u32 s, u32 cell, u3
           return true;
         });
       }
-      pc_put(x, cell, slot);
     }
     unc &= ~mask;
     __syncwarp();
@@ -351,7 +366,7 @@ __global__ void __launch_bounds__(PC_THREADS) k_pug_cover_g(KArgs a, GeArgs g) {
         u32 inter = full;
 #pragma unroll
         for (int j = 0; j < G; ++j) if ((mask >> j) & 1u) inter &= M[j];
-        pc_put(x, cell, pc_slot_masked(x, li, ln, inter, me.gene));
+        pc_emit_masked(x, cell, li, ln, inter, me.gene);
       }
       if (wm) unc &= ~mask;
       __syncwarp();
@@ -440,6 +455,81 @@ __global__ void __launch_bounds__(PC_THREADS) k_pug_count(KArgs a, GeArgs g) {
       a.num_over_mean[cell] = s_over;
       a.flags[cell] = nnz == 0 ? 4 : 0;
     }
+    __syncthreads();
+  }
+}
+
+// ---- EM resolutions: one CTA per cell runs the shared back end (ge_back, afq_pug.cuh: molecules -> gene eq-classes in
+// canonical order -> counts / EM -> staging row + statistics) on the cell's molecules in the global pool. The back end's
+// arrays are carved from an arena sized by what the cell holds: k_back_bin sorts the cells into four tiers by
+// ps_back_words(molecules, label words) — 48 KB x 4 CTAs per SM, 100 KB x 2, 224 KB x 1 of shared memory, and per-CTA
+// global arenas for the rest — and the four k_pug_back<tier> launches run side by side on lanes.
+constexpr u32 PB_THREADS = 256;
+constexpr int PB_TIERS = 4;
+__host__ __device__ constexpr u32 pb_arena_words(int tier) { return tier == 0 ? 12u * 1024u : (tier == 1 ? 25u * 1024u : 56u * 1024u); }
+
+__global__ void __launch_bounds__(256) k_back_bin(KArgs a, GeArgs g) {
+  u32 cum[PS_VARIANTS + 1];
+  cum[0] = 0;
+  for (int v = 0; v < PS_VARIANTS; ++v) cum[v + 1] = cum[v] + a.ctl->bin_count[PS_LIST0 + v];
+  const u32 per = a.usa_mode ? 3u : 1u;
+  for (u32 job = blockIdx.x * blockDim.x + threadIdx.x; job < cum[PS_VARIANTS]; job += gridDim.x * blockDim.x) {
+    int v = 0;
+    while (job >= cum[v + 1]) ++v;
+    const u32 cell = a.bin_list[(u64)(PS_LIST0 + v) * a.n_cells + (job - cum[v])];
+    const u32 M = g.ps_nwin[cell];
+    if (M == NONE32) continue;                     // handed back by k_pug_build
+    const u64 need = ps_back_words(M, g.ps_nlab[cell], per);
+    const int tier = need <= pb_arena_words(0) ? 0 : (need <= pb_arena_words(1) ? 1 : (need <= pb_arena_words(2) ? 2 : 3));
+    g.back_list[(u64)tier * a.n_cells + atomicAdd(&a.ctl->back_count[tier], 1u)] = cell;
+  }
+}
+
+template <int TIER>
+__global__ void __launch_bounds__(PB_THREADS) k_pug_back(KArgs a, GeArgs g) {
+  AFQ_DYN_SMEM(smem_raw);
+  u32* A = TIER < 3 ? reinterpret_cast<u32*>(smem_raw) : g.back_garena + (u64)blockIdx.x * g.back_garena_words;
+  const u32 AW = TIER < 3 ? pb_arena_words(TIER) : g.back_garena_words;
+  __shared__ GeShared sh;
+  __shared__ GePtrs s_ptrs;
+  __shared__ u32 s_job;
+  const u32 tid = threadIdx.x;
+  const u32 total = a.ctl->back_count[TIER];
+  const u32* list = g.back_list + (u64)TIER * a.n_cells;
+  for (;;) {
+    if (tid == 0) s_job = atomicAdd(&a.ctl->back_cursor[TIER], 1u);
+    __syncthreads();
+    const u32 job = s_job;
+    __syncthreads();
+    if (job >= total) break;
+    const u32 cell = list[job];
+    const u32 M = g.ps_nwin[cell], Lm = g.ps_nlab[cell];
+    const u64 r0 = a.cell_rec_off[cell];
+    const u32 f0 = a.ref_off[r0];
+    if (tid == 0) {
+      GePtrs pp{};
+      const bool ok = ps_back_carve(A, 0, AW, M, Lm, a.usa_mode ? 3u : 1u, &pp);
+      pp.mlab = g.ps_mlab + f0; pp.mol_off = g.ps_moff + r0; pp.mol_len = g.ps_mlen + r0;
+      s_ptrs = pp;
+      sh.flag = ok ? 0u : 1u;
+      sh.n_mol = M; sh.lab_bump = Lm; sh.alt = 0;
+      sh.cnt0 = sh.cnt1 = sh.cnt2 = sh.cnt3 = 0;
+    }
+    __syncthreads();
+    if (sh.flag) {      // (cannot happen: the tier was chosen with the same arithmetic; kept as a safety net) -> k_gene_eqc
+      if (tid == 0) {
+        g.ps_nwin[cell] = NONE32;
+        const u32 idx = atomicAdd(&a.ctl->bin_count[GE_LIST_NORMAL], 1u);
+        a.bin_list[(u64)GE_LIST_NORMAL * a.n_cells + idx] = cell;
+      }
+      __syncthreads();
+      continue;
+    }
+    GeCell gc(s_ptrs);
+    gc.a = &a; gc.g = &g; gc.scratch = nullptr; gc.scratch_budget = 0;
+    gc.vk_s = nullptr; gc.vc_s = nullptr; gc.cl_off_s = nullptr; gc.cl_len_s = nullptr;
+    gc.r0 = r0; gc.f0 = f0; gc.gene_labels = g.ge_mode == GE_MODE_PUG_GENE;
+    ge_back(a, g, cell, gc, &sh);
     __syncthreads();
   }
 }

@@ -80,7 +80,7 @@ __host__ __device__ inline u32 ps_need_words(u32 n, u32 P, bool gene, bool em, b
   const u32 vest = n / 2 + 16;
   u32 bw = pow2_ge(2 * vest, 64); if (bw > 4096) bw = 4096;
   const u32 post = pow2_ge(vest + vest / 2 + 2, 64) + bw + 2 * vest + (em ? 0 : pow2_ge(vest, 1)) + PS_COVER_WARPS * PS_WSCR_WORDS;
-  u32 w = P + (n + 2) / 2 + (gene ? (n + 1) / 2 : 0) + rec + 3 * vest + (post > rec ? post - rec : 0);
+  u32 w = P + (n + 2) / 2 + (gene ? (n + 1) / 2 : 0) + rec + 3 * vest + (post > rec ? post - rec : 0) + 24;   // (+ alignment slack of the bulk-copied arrays)
   if (em) {
     w += 2 * vest + P / 2 + 64;
     // the EM back end (ps_back_carve) on ~n/3 molecules with ~1.4 label entries each, + molecules at the top
@@ -118,6 +118,8 @@ struct PsExtra {
   u32 n_over;     // components of <= 8 vertices re-routed to the warp-cooperative cover (a label > 32 transcripts)
   u32 next_w, next_g;   // cover work queues: warp-form components / group passes handed out to the warps
   u32 dbase[4];         // SPLIT: this cell's first descriptor on each size-class list
+  u32 n_bulk;           // bulk-copy loads issued so far (the mbarrier's phase parity)
+  unsigned long long bar;   // mbarrier of the bulk-copy loads
 };
 
 // all lanes of a warp call: the warp claims the next item of a shared-memory work counter
@@ -169,7 +171,36 @@ struct PsSink {
   u32* mol_off; u32* mol_len;
   GeShared* sh;         // n_mol / lab_bump
   PsExtra* ex;
+  // mode 3 (split path, EM resolutions): molecules go to the cell's regions of the GLOBAL molecule pool
+  u32* g_lab;           // labels of the cell: pool + f0 (at most P words, see afq_pugc.cuh)
+  u32* g_nlab;          // label words used so far
+  u32* g_nmol;          // molecules emitted so far
+  u32* g_moff; u32* g_mlen;   // per molecule: label offset / length (cell region: + r0)
 };
+
+// store one molecule label of `want` reserved words; returns the destination (mode 2: arena, labels grow down; mode 3:
+// the cell's global pool region, labels grow up) or nullptr when the arena is exhausted
+__device__ __forceinline__ u32* ps_label_alloc(const PsSink& sk, u32 want, u32* off_out) {
+  if (sk.mode == 3) {
+    const u32 off = atomicAdd(sk.g_nlab, want);
+    *off_out = off;
+    return sk.g_lab + off;
+  }
+  const u32 used = atomicAdd(&sk.sh->lab_bump, want) + want;     // labels grow DOWN from lab_hi
+  if (used > sk.lab_hi - sk.lab_lo) { sk.ex->fail = 1; return nullptr; }
+  *off_out = sk.lab_hi - used;
+  return sk.A + *off_out;
+}
+__device__ __forceinline__ void ps_label_commit(const PsSink& sk, u32 off, u32 len) {
+  if (sk.mode == 3) {
+    const u32 id = atomicAdd(sk.g_nmol, 1u);
+    sk.g_moff[id] = off; sk.g_mlen[id] = len;
+    return;
+  }
+  const u32 id = atomicAdd(&sk.sh->n_mol, 1u);
+  sk.mol_off[id] = off;
+  sk.mol_len[id] = len;
+}
 
 // One molecule whose transcript label is { t = l0[k], k in [0, n0) : keep(k, t) } (ascending). Returns the
 // output slot for the unique-only modes (NONE32: contributes nothing); mode 2 stores the sorted
@@ -224,10 +255,9 @@ __device__ __forceinline__ u32 ps_emit(const PsCell& c, const PsSink& sk, const 
     ++nb;
   }
   const u32 want = big ? n0 : nb;
-  const u32 used = atomicAdd(&sk.sh->lab_bump, want) + want;     // labels grow DOWN from lab_hi
-  if (used > sk.lab_hi - sk.lab_lo) { sk.ex->fail = 1; return NONE32; }
-  const u32 off = sk.lab_hi - used;
-  u32* dst = sk.A + off;
+  u32 off;
+  u32* dst = ps_label_alloc(sk, want, &off);
+  if (!dst) return NONE32;
   u32 m = nb;
   if (!big) { for (u32 q = 0; q < nb; ++q) dst[q] = buf[q]; }
   else {      // more than 32 genes: project in place
@@ -238,9 +268,7 @@ __device__ __forceinline__ u32 ps_emit(const PsCell& c, const PsSink& sk, const 
     }
     if (!c.gene) m = sort_dedup_small(dst, m);
   }
-  const u32 id = atomicAdd(&sk.sh->n_mol, 1u);
-  sk.mol_off[id] = off;
-  sk.mol_len[id] = m;
+  ps_label_commit(sk, off, m);
   return NONE32;
 }
 
@@ -251,13 +279,11 @@ constexpr u32 PS_CRL_GENES = 24;     // cr-like-em: candidate genes of one UMI h
 __device__ __forceinline__ u32 ps_emit_genes(const PsSink& sk, const u32* genes, u32 nb) {
   if (sk.mode == 0) return nb == 1 ? genes[0] : NONE32;
   if (sk.mode == 1) return nb <= 10 ? usa_slot_for_label(genes, nb, sk.uo, sk.ao) : NONE32;
-  const u32 used = atomicAdd(&sk.sh->lab_bump, nb) + nb;
-  if (used > sk.lab_hi - sk.lab_lo) { sk.ex->fail = 1; return NONE32; }
-  const u32 off = sk.lab_hi - used;
-  for (u32 q = 0; q < nb; ++q) sk.A[off + q] = genes[q];
-  const u32 id = atomicAdd(&sk.sh->n_mol, 1u);
-  sk.mol_off[id] = off;
-  sk.mol_len[id] = nb;
+  u32 off;
+  u32* dst = ps_label_alloc(sk, nb, &off);
+  if (!dst) return NONE32;
+  for (u32 q = 0; q < nb; ++q) dst[q] = genes[q];
+  ps_label_commit(sk, off, nb);
   return NONE32;
 }
 
@@ -330,7 +356,7 @@ __device__ __forceinline__ void ps_emit_mcc(const PsCell& c, const PsSink& sk, u
     }
     return true;
   });
-  if (sk.mode != 2 && slot != NONE32) {
+  if (sk.mode < 2 && slot != NONE32) {
     winners[atomicAdd(&sk.ex->n_win, 1u)] = slot;
     if (gbm) atomicOr(&gbm[slot >> 5], 1u << (slot & 31));
   }
@@ -448,7 +474,7 @@ __device__ inline void ps_cover_group(const PsCell& c, const PsSink& sk, u32* wi
         const u32 gv = c.vgene[v];
         const u32 slot = (gv < PS_MULTI_GENE && inter != 0) ? ps_emit_genes(sk, &gv, 1u)
                                                             : ps_emit(c, sk, li, ln, [&](u32 q, u32) { return ((inter >> q) & 1u) != 0; });
-        if (sk.mode != 2 && slot != NONE32) {
+        if (sk.mode < 2 && slot != NONE32) {
           winners[atomicAdd(&sk.ex->n_win, 1u)] = slot;
           if (gbm) atomicOr(&gbm[slot >> 5], 1u << (slot & 31));
         }
@@ -569,7 +595,7 @@ __device__ inline void ps_cover_warp(const PsCell& c, const PsSink& sk, u32* win
         const u32 gv = c.vgene[wmem[lane]];
         const u32 slot = (gv < PS_MULTI_GENE && inter != 0) ? ps_emit_genes(sk, &gv, 1u)
                                                             : ps_emit(c, sk, li, ln, [&](u32 q, u32) { return ((inter >> q) & 1u) != 0; });
-        if (sk.mode != 2 && slot != NONE32) {
+        if (sk.mode < 2 && slot != NONE32) {
           winners[atomicAdd(&sk.ex->n_win, 1u)] = slot;
           if (gbm) atomicOr(&gbm[slot >> 5], 1u << (slot & 31));
         }
@@ -603,6 +629,15 @@ __device__ inline bool ps_back_carve(u32* A, u32 lo, u32 hi, u32 M, u32 Lm, u32 
   o->alpha_in = (float*)take(4ull * Sr); o->alpha_out = (float*)take(4ull * Sr); o->cls_inv = (float*)take(4ull * (M + 1));
   o->sib_a = (u32*)take(4ull * Sr); o->sib_b = (u32*)take(4ull * Sr);
   return align8(off) <= (u64)hi * 4;
+}
+
+// words of arena ps_back_carve needs for M molecules / Lm label words (same arithmetic)
+__host__ __device__ inline u64 ps_back_words(u64 M, u64 Lm, u32 per) {
+  auto p2 = [](u64 v) { u64 p = 1; while (p < v) p <<= 1; return p; };
+  const u64 Mp = p2(M ? M : 1), Lp = p2(Lm ? Lm : 1), TK = Mp > Lp ? Mp : Lp, Sp = p2(Lm * per ? Lm * per : 1), Sr = Lm * per + 2;
+  const u64 bytes = 8 * Mp + 4 * Mp + 4 * (M + 1) * 2 + 4 * (M + 2) + 8 * TK + 4 * (TK + 1) + 4 * (Lm + 1) + 4 * Sp + 4 * (Sr + 2) +
+                    4 * Sr * 2 + 4 * (M + 1) + 4 * Sr * 2 + 8 * 16;   // (+ the align8 padding of the 15 arrays)
+  return (bytes + 3) / 4;
 }
 
 // L2 prefetch of a cell's record arrays (one 128-byte line per thread and step)
@@ -639,19 +674,37 @@ __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A
   const u32 P = a.ref_off[r1] - f0;
   const bool gene = g.ge_mode == GE_MODE_PUG_GENE;
   const bool usa = a.usa_mode != 0;
-  const bool em = g.only_unique == 0 || (!SPLIT && g.dump_ncls != nullptr);   // (--dump-eqclasses: the molecules go through ge_back too)
+  // molecules (gene labels) instead of output slots: the EM resolutions, and --dump-eqclasses (the classes come out of ge_back).
+  // In-kernel back end (em) or, on the split path, the global molecule pool consumed by k_pug_back (sem).
+  const bool want_mol = g.only_unique == 0 || g.dump_ncls != nullptr;
+  const bool em = !SPLIT && want_mol, sem = SPLIT && want_mol;
 
   // ---- arena layout, phase A --------------------------------------------------------------------
+  // (shared-memory variants: refs / UMIs / record offsets arrive by bulk copy from 16-byte aligned addresses, so the
+  // arrays start `lead` words into their 16-byte aligned regions)
+#ifndef AFQ_EMU
+  const bool bulk = !WIDE && (u64)f0 + P + 4 <= a.n_refs_total && r1 + 5 <= a.n_records && P > 0;
+#else
+  const bool bulk = false;
+#endif
+  const u32 lead_f = bulk ? (f0 & 3u) : 0u, lead_r = bulk ? (u32)(r0 & 3u) : 0u;
+  const u32 refs_words = bulk ? ((lead_f + P + 3) & ~3u) : P;
+  const u32 umi_words = bulk ? ((lead_r + n + 3) & ~3u) : n;
+  const u32 roff_raw_words = (lead_r + n + 1 + 3) & ~3u;       // raw 32-bit offsets, staged in the (still unused) table area
   u32 off = 0;
-  u32* refs = A + off; off += P;
+  u32* refs_raw = A + off; off += refs_words;
+  u32* refs = refs_raw + lead_f;
   u16* roff = WIDE ? nullptr : reinterpret_cast<u16*>(A + off);
   u32* roff32 = WIDE ? A + off : nullptr;
   off += WIDE ? n + 1 : (n + 2) / 2;
   u16* rlen = nullptr;
   if (gene) { rlen = reinterpret_cast<u16*>(A + off); off += (n + 1) / 2; }
+  off = (off + 3) & ~3u;
   const u32 off_rec = off;                       // everything from here is re-carved after compaction
-  u32* umi = A + off; off += n;
+  u32* umi_raw = A + off; off += umi_words;
+  u32* umi = umi_raw + lead_r;
   u16* rcls = reinterpret_cast<u16*>(A + off); off += (n + 1) / 2;
+  off = (off + 3) & ~3u;
   const u32 TN = ps_table_size(n), tl2 = ilog2(TN), tmask = TN - 1;
   u32* tab = A + off; off += TN;
   const u32 off_dense = off;
@@ -659,12 +712,33 @@ __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A
                   sh->n_mol = 0; sh->lab_bump = 0; sh->alt = 0; sh->flag = 0; sh->cnt0 = sh->cnt1 = sh->cnt2 = sh->cnt3 = 0; }
   __syncthreads();
   if (ex->fail) { __syncthreads(); return false; }
-  // ---- load: the cell's records are read from HBM once, coalesced --------------------------------
-  for (u32 i = tid; i < P; i += T) refs[i] = a.refs[(u64)f0 + i];
-  for (u32 i = tid; i <= n; i += T) { if (WIDE) roff32[i] = a.ref_off[r0 + i] - f0; else roff[i] = (u16)(a.ref_off[r0 + i] - f0); }
-  for (u32 i = tid; i < n; i += T) umi[i] = a.umi[r0 + i];
-  for (u32 i = tid; i < TN; i += T) tab[i] = PS_EMPTY;
-  __syncthreads();
+  // ---- load: the cell's records are read from HBM once ----------------------------------------------
+#ifndef AFQ_EMU
+  if (bulk) {
+    // three bulk copies (cp.async.bulk global -> shared, one thread issues them, the copy engine moves the data); every
+    // thread waits on the mbarrier. ncu r2c: the three strided load loops held 10 % of k_pug_build's stall samples.
+    if (tid == 0) {
+      fence_proxy_async();                         // the previous cell's generic-proxy accesses of the arena come first
+      mbar_expect_tx((u64*)&ex->bar, 4u * (refs_words + umi_words + roff_raw_words));
+      bulk_g2s(refs_raw, a.refs + ((u64)f0 - lead_f), 4u * refs_words, (u64*)&ex->bar);
+      bulk_g2s(umi_raw, a.umi + (r0 - lead_r), 4u * umi_words, (u64*)&ex->bar);
+      bulk_g2s(tab, a.ref_off + (r0 - lead_r), 4u * roff_raw_words, (u64*)&ex->bar);
+    }
+    mbar_wait((u64*)&ex->bar, ex->n_bulk & 1u);
+    for (u32 i = tid; i <= n; i += T) roff[i] = (u16)(tab[lead_r + i] - f0);
+    __syncthreads();
+    if (tid == 0) ex->n_bulk++;
+    for (u32 i = tid; i < TN; i += T) tab[i] = PS_EMPTY;
+    __syncthreads();
+  } else
+#endif
+  {
+    for (u32 i = tid; i < P; i += T) refs[i] = a.refs[(u64)f0 + i];
+    for (u32 i = tid; i <= n; i += T) { if (WIDE) roff32[i] = a.ref_off[r0 + i] - f0; else roff[i] = (u16)(a.ref_off[r0 + i] - f0); }
+    for (u32 i = tid; i < n; i += T) umi[i] = a.umi[r0 + i];
+    for (u32 i = tid; i < TN; i += T) tab[i] = PS_EMPTY;
+    __syncthreads();
+  }
   PsCell c;
   c.a = &a; c.refs = refs; c.roff = roff; c.roff32 = roff32; c.rlen = rlen; c.gene = gene; c.vumi = nullptr; c.vinfo = nullptr; c.vgene = nullptr;
   if (gene) {   // sorted-dedup gene projection of every record, in place (src/eq_class.rs:742-744)
@@ -795,7 +869,12 @@ __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A
   if (!em && !SPLIT) { gbm = alloc(2 * Wg); if (!fits) gbm = nullptr; }
   // EM: molecule labels grow down from the molecule offsets / lengths at the top of the arena
   PsSink sk;
-  sk.mode = em ? 2u : (usa ? 1u : 0u);
+  sk.mode = sem ? 3u : (em ? 2u : (usa ? 1u : 0u));
+  if (sem) {
+    sk.g_lab = g.ps_mlab + f0; sk.g_nlab = g.ps_nlab + cell; sk.g_nmol = g.ps_nwin + cell;
+    sk.g_moff = g.ps_moff + r0; sk.g_mlen = g.ps_mlen + r0;
+    if (tid == 0) { g.ps_nwin[cell] = 0; g.ps_nlab[cell] = 0; }      // (a barrier follows before the first molecule)
+  }
   sk.uo = a.uo; sk.ao = a.ao; sk.A = A; sk.sh = sh; sk.ex = ex;
   sk.lab_lo = segB; sk.lab_hi = em ? topB : segB;
   sk.mol_off = A + (AW - V); sk.mol_len = A + (AW - 2 * V);
@@ -973,7 +1052,7 @@ __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A
   if (SPLIT) {
     // ---- export (nothing can fail from here on) ------------------------------------------------------
     const u32 r0w = (u32)r0;
-    const u32 nsingle = ex->n_win;
+    const u32 nsingle = sem ? 0u : ex->n_win;
     for (u32 i = tid; i < nsingle; i += T) g.ps_win[r0w + i] = swin[i];
     if (K) {
       GE_FOR(v, V) if (root[v] == v && csz[v] > 1) clist[atomicAdd(&ex->szc[csz[v]], 1u)] = v;
@@ -1015,7 +1094,7 @@ __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A
       }
     }
     __syncthreads();
-    if (tid == 0) g.ps_nwin[cell] = nsingle;
+    if (tid == 0 && !sem) g.ps_nwin[cell] = nsingle;      // (sem: the molecule counter has been running since the singletons)
     __syncthreads();
     return true;
   }
@@ -1061,6 +1140,7 @@ __device__ inline bool ps_cell(const KArgs& a, const GeArgs& g, u32 cell, u32* A
   }
   __syncthreads();
   if (ex->fail) { __syncthreads(); return false; }
+  if (SPLIT) return true;        // (cr-like-em on the split path: the per-UMI molecules are in the global pool)
 
   const u64 out_base = f0;
   if (em) {
@@ -1176,6 +1256,12 @@ __global__ void __launch_bounds__(ps_threads(VAR), ps_min_blocks(VAR)) k_pug_sme
   __shared__ GeShared sh;
   __shared__ PsExtra ex;
   __shared__ GePtrs s_ptrs;
+  if (threadIdx.x == 0) {
+    ex.n_bulk = 0;
+#ifndef AFQ_EMU
+    mbar_init((u64*)&ex.bar, 1);
+#endif
+  }
   const u32 count = a.ctl->bin_count[PS_LIST0 + VAR];
   const u32* list = a.bin_list + (u64)(PS_LIST0 + VAR) * a.n_cells;
   // jobs are claimed one ahead so that the NEXT cell's records can be prefetched into L2 while this
@@ -1212,6 +1298,12 @@ __global__ void __launch_bounds__(ps_threads(VAR), ps_build_min_blocks(VAR)) k_p
   const u32 AWmax = VAR < PS_SMEM_VARIANTS ? ps_arena_words(VAR) : g.ps_garena_words;
   __shared__ GeShared sh;
   __shared__ PsExtra ex;
+  if (threadIdx.x == 0) {
+    ex.n_bulk = 0;
+#ifndef AFQ_EMU
+    mbar_init((u64*)&ex.bar, 1);
+#endif
+  }
   const u32 count = a.ctl->bin_count[PS_LIST0 + VAR];
   const u32* list = a.bin_list + (u64)(PS_LIST0 + VAR) * a.n_cells;
   if (threadIdx.x == 0) sh.job = atomicAdd(&a.ctl->bin_cursor[PS_LIST0 + VAR], 1u);

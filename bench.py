@@ -327,16 +327,17 @@ def measure_config(args, name, cells, res, ctx):
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- roofline of the dominant kernel family (per-cell resolve) -----------------------------
-    fam = {k: v for k, v in prof.items() if k.startswith(("k_resolve", "k_gene_eqc", "k_pug_smem", "k_pug_build", "k_pug_cover", "k_pug_count"))}
+    fam = {k: v for k, v in prof.items() if k.startswith(("k_resolve", "k_gene_eqc", "k_pug_smem", "k_pug_build", "k_pug_cover", "k_pug_count", "k_pug_back", "k_back_bin"))}
     fam_ms = sum(v[0] for v in fam.values()) / steps
     region = prof.get("resolve_region(wall)")
     pug_region = prof.get("pug_region(wall)")
     if region:  # arena kernels overlap on lanes: their device time is the wall time of the region(s)
         fam_ms = region[0] / steps
         if pug_region:   # the k_pug_smem variants overlap on lanes too; k_gene_eqc (handed-back cells) runs behind them
-            fam_ms += (pug_region[0] + sum(v[0] for k, v in fam.items() if k.startswith(("k_gene_eqc", "k_pug_count")))) / steps
-            if prof.get("cover_region(wall)"):   # split parsimony path: the flat cover kernels overlap on lanes as well
-                fam_ms += prof["cover_region(wall)"][0] / steps
+            fam_ms += (pug_region[0] + sum(v[0] for k, v in fam.items() if k.startswith(("k_gene_eqc", "k_pug_count", "k_back_bin")))) / steps
+            for reg in ("cover_region(wall)", "back_region(wall)"):   # split path: the flat cover / back-end kernels overlap on lanes as well
+                if prof.get(reg):
+                    fam_ms += prof[reg][0] / steps
         else:
             fam_ms += sum(v[0] for k, v in fam.items() if k.startswith(("k_gene_eqc", "k_pug_smem"))) / steps
     fam_launches = sum(v[1] for v in fam.values()) // max(steps, 1)

@@ -21,7 +21,7 @@ namespace {
 struct EmuLauncher {
   const u32* t2g_ = nullptr;
   std::vector<u8> arena[2];
-  std::vector<u32> adj, garena, sp_win, sp_nwin, sp_mem, sp_desc, sp_glab;
+  std::vector<u32> adj, garena, sp_win, sp_nwin, sp_mem, sp_desc, sp_glab, sp_mlab, sp_nlab, sp_moff, sp_mlen, sp_big, sp_bga;
   u64 launches = 0;
   int ge_threads_override = 0;
   const u32* t2g() const { return t2g_; }
@@ -48,7 +48,7 @@ struct EmuLauncher {
   u32 need_shift() { const char* s = getenv("AFQ_NEED_SHIFT"); return s ? (u32)atoi(s) : 0; }
   u32* ps_garena(u64 words, u32 blocks) { garena.assign((size_t)words * blocks + 16, 0xCDCDCDCDu); return garena.data(); }
   u32 ps_limit_words() { const char* s = getenv("AFQ_PS_LIMIT_WORDS"); return s ? (u32)atoi(s) : 0; }
-  bool ps_split(u64 n_records, u64 n_refs, u64 n_cells, bool gene_labels, PsSplitBufs* o) {
+  bool ps_split(u64 n_records, u64 n_refs, u64 n_cells, bool gene_labels, bool molecules, PsSplitBufs* o) {
     const char* s = getenv("AFQ_NO_PS_SPLIT");
     if (s && atoi(s)) return false;
     sp_win.assign(n_records + 4, 0xCDCDCDCDu); sp_nwin.assign(n_cells + 4, 0xCDCDCDCDu);
@@ -56,10 +56,14 @@ struct EmuLauncher {
     sp_desc.assign(2 * (size_t)(n_records / 2 + n_records / 3 + n_records / 5 + n_records / 9 + 8), 0xCDCDCDCDu);
     sp_glab.assign(gene_labels ? n_refs + 4 : 4, 0xCDCDCDCDu);
     // (16-byte alignment of the member pool: std::vector<u32> storage from operator new is 16-byte aligned)
+    sp_mlab.assign(molecules ? n_refs + 4 : 4, 0xCDCDCDCDu); sp_nlab.assign(n_cells + 4, 0xCDCDCDCDu);
+    sp_moff.assign(molecules ? n_records + 4 : 4, 0xCDCDCDCDu); sp_mlen.assign(molecules ? n_records + 4 : 4, 0xCDCDCDCDu); sp_big.assign(4 * n_cells + 4, 0xCDCDCDCDu);
     o->win = sp_win.data(); o->nwin = sp_nwin.data(); o->mem = sp_mem.data(); o->desc = sp_desc.data(); o->glab = gene_labels ? sp_glab.data() : nullptr;
+    o->mlab = sp_mlab.data(); o->nlab = sp_nlab.data(); o->moff = sp_moff.data(); o->mlen = sp_mlen.data(); o->back_list = sp_big.data();
     return true;
   }
   int pc_grid(int, size_t) { return 1; }
+  u32* back_garena(u64 words, u32 blocks) { sp_bga.assign((size_t)words * blocks + 16, 0xCDCDCDCDu); return sp_bga.data(); }
   int ps_grid(int v) {
     const char* s = getenv("AFQ_NO_PS");
     if (s && atoi(s)) return 0;
