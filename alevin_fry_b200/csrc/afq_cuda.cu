@@ -76,7 +76,7 @@ struct Work {  // per-pipeline scratch (ordered on one stream)
   DBuf<u8> ge_arena[2];
   DBuf<u32> adj_pool;
   DBuf<u32> ps_garena;     // k_pug_smem<3> arenas
-  DBuf<u32> ps_win, ps_nwin, ps_mem, ps_desc, ps_glab, ps_mlab, ps_nlab, ps_moff, ps_mlen, ps_back_list, ps_back_garena;   // split parsimony path (afq_pugc.cuh)
+  DBuf<u32> ps_win, ps_nwin, ps_mem, ps_desc, ps_glab, ps_mlab, ps_nlab, ps_moff, ps_mlen, ps_back_list, ps_back_garena, cls_ncls, cls_nlab, cls_cnt, cls_off, cls_lab;   // split parsimony path (afq_pugc.cuh, afq_emc.cuh)
   DBuf<u64> na_tiles;      // rec_na8 -> offsets scan
   DBuf<u32> na_ref_off;    // device API: offsets derived from rec_na8
   DBuf<u32> umi_wide, refs_wide;   // rec_umi24 / refs24 widened to u32
@@ -94,6 +94,7 @@ struct Work {  // per-pipeline scratch (ordered on one stream)
     tile_sums.release(); ge_arena[0].release(); ge_arena[1].release(); adj_pool.release(); ps_garena.release();
     ps_win.release(); ps_nwin.release(); ps_mem.release(); ps_desc.release(); ps_glab.release();
     ps_mlab.release(); ps_nlab.release(); ps_moff.release(); ps_mlen.release(); ps_back_list.release(); ps_back_garena.release();
+    cls_ncls.release(); cls_nlab.release(); cls_cnt.release(); cls_off.release(); cls_lab.release();
     na_tiles.release(); na_ref_off.release(); umi_wide.release(); refs_wide.release();
   }
 };
@@ -168,6 +169,9 @@ struct afq_ctx {
   bool no_ps_split = false;    // AFQ_NO_PS_SPLIT=1: unique-only parsimony stays on the single-kernel k_pug_smem (A/B, tests)
   int grid_count = 0;          // k_pug_count's persistent grid (0: its shared memory does not fit => no split path)
   int grid_back[4] = {0, 0, 0, 0};   // k_pug_back<tier>
+  int grid_em[4] = {0, 0, 0, 0};     // k_em_cells<tier>
+  bool no_em_split = false;    // AFQ_NO_EM_SPLIT=1: k_pug_back runs ge_back's own stage C (A/B)
+  u32 back_max_tier = 0;       // AFQ_BACK_MAX_TIER: largest shared-memory arena tier of k_pug_back (r2j: 0 is fastest on C3-em / C4 / C5)
   cudaStream_t lanes[NUM_BINS] = {nullptr};
   cudaEvent_t ev_fork = nullptr, ev_lane[NUM_BINS] = {nullptr};
   // pipelines
@@ -284,7 +288,15 @@ struct CudaLauncher {
     o->mlab = w->ps_mlab.p; o->nlab = w->ps_nlab.p; o->moff = w->ps_moff.p; o->mlen = w->ps_mlen.p; o->back_list = w->ps_back_list.p;
     return true;
   }
-  int pc_grid(int which, size_t) { return which == 0 ? c->num_sms * 8 : (which == 1 ? c->grid_count : c->grid_back[which - 2]); }
+  int pc_grid(int which, size_t) { return which == 0 ? c->num_sms * 8 : (which == 1 ? c->grid_count : (which < 6 ? c->grid_back[which - 2] : c->grid_em[which - 6])); }
+  u32 back_max_tier() { return c->back_max_tier; }
+  bool em_split() { return !c->no_em_split && c->grid_em[0] > 0; }
+  bool cls_bufs(u64 n_records, u64 n_refs, u64 n_cells, ClsBufs* o) {
+    if (w->cls_ncls.ensure(n_cells + 4) != cudaSuccess || w->cls_nlab.ensure(n_cells + 4) != cudaSuccess || w->cls_cnt.ensure(n_records + 4) != cudaSuccess ||
+        w->cls_off.ensure(n_records + 4) != cudaSuccess || w->cls_lab.ensure(n_refs + 4) != cudaSuccess) return false;
+    o->ncls = w->cls_ncls.p; o->nlab = w->cls_nlab.p; o->cnt = w->cls_cnt.p; o->off = w->cls_off.p; o->lab = w->cls_lab.p;
+    return true;
+  }
   u32* back_garena(u64 words, u32 blocks) { return w->ps_back_garena.ensure((size_t)words * blocks + 16) == cudaSuccess ? w->ps_back_garena.p : nullptr; }
   // fork / join: lanes are ctx-owned non-blocking streams ordered after / before the caller stream
   void fork(int n) {
@@ -494,6 +506,8 @@ int afq_create(const afq_config* cfg, const uint32_t* tid_to_gid, uint64_t n_ref
   if (const char* s = getenv("AFQ_NO_PS")) c->no_ps = atoi(s) != 0;
   if (const char* s = getenv("AFQ_NO_PS_GLOBAL")) c->no_ps_global = atoi(s) != 0;
   if (const char* s = getenv("AFQ_NO_PS_SPLIT")) c->no_ps_split = atoi(s) != 0;
+  if (const char* s = getenv("AFQ_BACK_MAX_TIER")) c->back_max_tier = (u32)atoi(s);
+  if (const char* s = getenv("AFQ_NO_EM_SPLIT")) c->no_em_split = atoi(s) != 0;
   if (const char* s = getenv("AFQ_PS_LIMIT_WORDS")) c->ps_limit_words = (u32)atoi(s);
   if (c->large_cap_log2 < 10) c->large_cap_log2 = 10;
   if (c->large_cap_log2 > 30) c->large_cap_log2 = 30;
@@ -545,7 +559,24 @@ int afq_create(const afq_config* cfg, const uint32_t* tid_to_gid, uint64_t n_ref
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, k_pug_back<2>, (int)PB_THREADS, pb_arena_words(2) * 4) == cudaSuccess && o2 >= 1 &&
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o3, k_pug_back<3>, (int)PB_THREADS, 0) == cudaSuccess && o3 >= 1) {
       c->grid_back[0] = o0 * c->num_sms; c->grid_back[1] = o1 * c->num_sms; c->grid_back[2] = o2 * c->num_sms;
-      c->grid_back[3] = c->num_sms;     // (tier 3: one global arena per SM)
+      c->grid_back[3] = (o3 > 4 ? 4 : o3) * c->num_sms;     // (tier 3: up to four global arenas per SM)
+    } else cudaGetLastError();
+  }
+  {   // k_em_cells<tier>: slot bitmap + per-cell arrays in dynamic shared memory, or (tier 3) per-CTA global arenas
+    const u32 nr = cfg->num_rows;
+    const size_t s0 = ec_smem_bytes(0, nr), s1 = ec_smem_bytes(1, nr), s2 = ec_smem_bytes(2, nr), s3 = ec_smem_bytes(3, nr) - 4ull * ec_arena_words(2);
+    int o0 = 0, o1 = 0, o2 = 0, o3 = 0;
+    if (s2 <= 227 * 1024 &&
+        cudaFuncSetAttribute(k_em_cells<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s0) == cudaSuccess &&
+        cudaFuncSetAttribute(k_em_cells<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1) == cudaSuccess &&
+        cudaFuncSetAttribute(k_em_cells<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2) == cudaSuccess &&
+        cudaFuncSetAttribute(k_em_cells<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o0, k_em_cells<0>, (int)EC_THREADS, s0) == cudaSuccess && o0 >= 1 &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, k_em_cells<1>, (int)EC_THREADS, s1) == cudaSuccess && o1 >= 1 &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, k_em_cells<2>, (int)EC_THREADS, s2) == cudaSuccess && o2 >= 1 &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o3, k_em_cells<3>, (int)EC_THREADS, s3) == cudaSuccess && o3 >= 1) {
+      c->grid_em[0] = o0 * c->num_sms; c->grid_em[1] = o1 * c->num_sms; c->grid_em[2] = o2 * c->num_sms;
+      c->grid_em[3] = (o3 > 4 ? 4 : o3) * c->num_sms;
     } else cudaGetLastError();
   }
   {

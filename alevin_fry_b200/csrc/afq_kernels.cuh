@@ -45,6 +45,7 @@ struct Ctl {                       // per-batch device control block (zeroed per
   u32 desc_cursor[4];              // ... and the cover kernels' work cursors
   u32 count_cursor;                // k_pug_count's / k_pug_back's work cursor over the cells of the four k_pug_build lists
   u32 back_count[4], back_cursor[4];     // k_pug_back's arena tiers: cells / work cursors
+  u32 em_count[4], em_cursor[4];         // k_em_cells' arena tiers
 };
 
 struct KArgs {

@@ -21,8 +21,11 @@
 //   u32  ps_limit_words();                                    // 0, or a smaller arena for k_pug_smem (tests: forces fallbacks)
 //   bool ps_split(u64 n_records, u64 n_refs, u64 n_cells, bool gene_labels, bool molecules, PsSplitBufs* out);
 //                                                              // grow-only global buffers of the split parsimony path; false = not available
-//   int  pc_grid(int which, size_t smem);                     // grid of the flat cover kernels (0) / k_pug_count (1) / k_pug_back tiers 0..3 (2..5)
+//   int  pc_grid(int which, size_t smem);                     // grid of the flat cover kernels (0) / k_pug_count (1) / k_pug_back tiers 0..3 (2..5) / k_em_cells tiers 0..3 (6..9)
 //   u32* back_garena(u64 words_per_block, u32 blocks);        // grow-only global arenas of k_pug_back<3>, nullptr on failure
+//   u32  back_max_tier();                                     // largest shared-memory tier of k_pug_back (AFQ_BACK_MAX_TIER)
+//   bool em_split();                                          // stage C in k_em_cells (default) or inside k_pug_back (AFQ_NO_EM_SPLIT=1)
+//   bool cls_bufs(u64 n_records, u64 n_refs, u64 n_cells, ClsBufs* out);   // internal class regions (no --dump-eqclasses)
 #pragma once
 #include <string>
 
@@ -31,6 +34,7 @@
 #include "afq_pug.cuh"
 #include "afq_pugs.cuh"
 #include "afq_pugc.cuh"
+#include "afq_emc.cuh"
 
 namespace afq {
 
@@ -38,7 +42,7 @@ enum KernelId : int {
   KID_BIN = 0, KID_SMEM0 = 1, KID_LARGE = 7, KID_SCAN_SUMS = 8, KID_SCAN_TILES = 9, KID_SCAN_ROWS = 10,
   KID_GATHER = 11, KID_GENE_EQC = 12, KID_GENE_EQC_BIG = 13, KID_BIN_GE = 14, KID_REGION = 15, KID_NA_OFFSETS = 16, KID_UNPACK24 = 17,
   KID_PUG_SMEM0 = 18, KID_PUG_REGION = 22, KID_PUG_BUILD0 = 23, KID_PUG_COVER2 = 27, KID_PUG_COVER4 = 28,
-  KID_PUG_COVER8 = 29, KID_PUG_COVERW = 30, KID_PUG_COUNT = 31, KID_COVER_REGION = 32, KID_PUG_BACK = 33, KID_BACK_REGION = 38, NUM_KID = 39
+  KID_PUG_COVER8 = 29, KID_PUG_COVERW = 30, KID_PUG_COUNT = 31, KID_COVER_REGION = 32, KID_PUG_BACK = 33, KID_BACK_REGION = 38, KID_EM_CELLS = 39, KID_EM_REGION = 44, NUM_KID = 45
 };
 static const char* const KID_NAMES[NUM_KID] = {
     "k_bin_cells", "k_resolve_smem<0>", "k_resolve_smem<1>", "k_resolve_smem<2>", "k_resolve_smem<3>",
@@ -46,7 +50,8 @@ static const char* const KID_NAMES[NUM_KID] = {
     "k_scan_rows", "k_gather_rows", "k_gene_eqc", "k_gene_eqc(big cells)", "k_bin_cells_ge", "resolve_region(wall)",
     "k_na_offsets(+tile sums)", "k_unpack24", "k_pug_smem<0>", "k_pug_smem<1>", "k_pug_smem<2>", "k_pug_smem<3>(global arena)", "pug_region(wall)",
     "k_pug_build<0>", "k_pug_build<1>", "k_pug_build<2>", "k_pug_build<3>(global arena)", "k_pug_cover2", "k_pug_cover_g<4>", "k_pug_cover_g<8>",
-    "k_pug_cover_w", "k_pug_count", "cover_region(wall)", "k_pug_back<0>", "k_pug_back<1>", "k_pug_back<2>", "k_pug_back<3>(global arena)", "k_back_bin", "back_region(wall)"};
+    "k_pug_cover_w", "k_pug_count", "cover_region(wall)", "k_pug_back<0>", "k_pug_back<1>", "k_pug_back<2>", "k_pug_back<3>(global arena)", "k_back_bin", "back_region(wall)",
+    "k_em_cells<0>", "k_em_cells<1>", "k_em_cells<2>", "k_em_cells<3>(global arena)", "k_em_bin", "em_region(wall)"};
 
 struct PipeBufs {  // device scratch owned by the caller (one set per stream-ordered pipeline)
   Ctl* ctl;
@@ -61,6 +66,7 @@ struct PipeBufs {  // device scratch owned by the caller (one set per stream-ord
   u32* dump_ncls = nullptr; u32* dump_nlab = nullptr; u32* dump_cnt = nullptr; u32* dump_off = nullptr; u32* dump_lab = nullptr;
 };
 
+struct ClsBufs { u32* ncls; u32* nlab; u32* cnt; u32* off; u32* lab; };
 struct PsSplitBufs { u32* win; u32* nwin; u32* mem; u32* desc; u32* glab; u32* mlab; u32* nlab; u32* moff; u32* mlen; u32* back_list; };
 
 inline bool res_is_pug(int r) {
@@ -262,11 +268,28 @@ int enqueue_batch(L& l, const afq_config& cfg, int force_bin, const PipeBufs& pb
         if (cb > ps_cells) cb = ps_cells;
         l.launch(KID_PUG_COUNT, k_pug_count, cb, PC_THREADS, csm, a, g);
       } else {
+        // Stage B (molecules -> gene eq-classes, canonical order) in k_pug_back, stage C (counts / EM) in k_em_cells; the
+        // classes travel through the dump regions (the caller's when --dump-eqclasses is on, internal ones otherwise).
+        // AFQ_NO_EM_SPLIT=1: k_pug_back runs ge_back's own stage C instead (A/B).
+        const bool em_split = l.em_split();
+        if (em_split && !dump) {
+          ClsBufs cb{};
+          if (!l.cls_bufs(b.n_records, b.n_refs_total, b.n_cells, &cb)) { err = "class region allocation failed"; return AFQ_ERR_CUDA; }
+          g.dump_ncls = cb.ncls; g.dump_nlab = cb.nlab; g.dump_cnt = cb.cnt; g.dump_off = cb.off; g.dump_lab = cb.lab;
+        }
+        g.classes_only = em_split ? 1u : 0u;
         // tier 3's per-CTA global arenas hold any cell of the batch (molecules <= records, label words <= alignments)
-        const u64 gw = (ps_back_words(h.ge_max_n[1], h.ge_max_p[1], cfg.usa_mode ? 3u : 1u) + 15) & ~3ull;
+        const bool usa = cfg.usa_mode != 0;
+        u64 gw = em_split ? ps_back_words_b(h.ge_max_n[1]) : ps_back_words(h.ge_max_n[1], h.ge_max_p[1], usa ? 3u : 1u);
+        if (em_split) {
+          const u64 ew = ec_need_words(h.ge_max_n[1], h.ge_max_p[1], ec_support_bound(h.ge_max_p[1], cfg.num_rows, usa), usa);
+          if (ew > gw) gw = ew;
+        }
+        gw = (gw + 15) & ~3ull;
         const unsigned g3 = (unsigned)l.pc_grid(5, 0);
         g.back_garena = gw < 0xFFFFFFF0ull ? l.back_garena(gw, g3) : nullptr;
         g.back_garena_words = (u32)gw;
+        g.back_max_tier = l.back_max_tier();
         if (!g.back_garena) { err = "k_pug_back global arena allocation failed"; return AFQ_ERR_CUDA; }
         l.launch(KID_PUG_BACK + 4, k_back_bin, (unsigned)((ps_cells + 255) / 256), 256u, (size_t)0, a, g);
         l.region_begin();
@@ -277,6 +300,18 @@ int enqueue_batch(L& l, const afq_config& cfg, int force_bin, const PipeBufs& pb
         l.lane(0); l.launch(KID_PUG_BACK + 0, k_pug_back<0>, (unsigned)l.pc_grid(2, 0), PB_THREADS, (size_t)pb_arena_words(0) * 4, a, g);
         l.join();
         l.region_end(KID_BACK_REGION);
+        if (em_split) {
+          l.launch(KID_EM_CELLS + 4, k_em_bin, (unsigned)((ps_cells + 255) / 256), 256u, (size_t)0, a, g);
+          l.region_begin();
+          l.fork(EC_TIERS);
+          l.lane(3); l.launch(KID_EM_CELLS + 3, k_em_cells<3>, (unsigned)l.pc_grid(9, 0), EC_THREADS, ec_smem_bytes(3, cfg.num_rows) - 4ull * ec_arena_words(2), a, g);
+          l.lane(2); l.launch(KID_EM_CELLS + 2, k_em_cells<2>, (unsigned)l.pc_grid(8, 0), EC_THREADS, ec_smem_bytes(2, cfg.num_rows), a, g);
+          l.lane(1); l.launch(KID_EM_CELLS + 1, k_em_cells<1>, (unsigned)l.pc_grid(7, 0), EC_THREADS, ec_smem_bytes(1, cfg.num_rows), a, g);
+          l.lane(0); l.launch(KID_EM_CELLS + 0, k_em_cells<0>, (unsigned)l.pc_grid(6, 0), EC_THREADS, ec_smem_bytes(0, cfg.num_rows), a, g);
+          l.join();
+          l.region_end(KID_EM_REGION);
+          g.classes_only = 0;      // (k_gene_eqc behind runs the whole back end for the handed-back cells)
+        }
       }
     }
     for (int which = 0; which < 2; ++which) {

@@ -74,6 +74,8 @@ struct GeArgs {
   u32* back_list;       // [4 * n_cells]  the cells of k_pug_back's four arena tiers (k_back_bin)
   u32* back_garena;     // per-CTA global arenas of tier 3
   u32 back_garena_words;
+  u32 back_max_tier;    // largest shared-memory tier k_back_bin may choose (0..2)
+  u32 classes_only;     // ge_back stops behind stage B (classes written to the dump regions): k_em_cells does stage C
   // --dump-eqclasses (src/quant.rs:1282-1307): every cell's gene eq-classes in canonical order. Cell c (records
   // [r0, r0+n), alignments [f0, f0+P)) writes class j's count / label offset at r0 + j and its labels from f0 on.
   u32* dump_ncls;       // [n_cells]  classes of the cell (zeroed per batch: tiny cells never build gene_eqc)
@@ -1159,6 +1161,7 @@ __device__ inline void ge_back(const KArgs& a, const GeArgs& g, u32 cell, GeCell
       base += tot;
     }
     if (tid == 0) { g.dump_ncls[cell] = G; g.dump_nlab[cell] = base; }
+    if (g.classes_only) { __syncthreads(); return; }
   }
 
   // =================== stage C: counts =========================================================

@@ -479,8 +479,11 @@ __global__ void __launch_bounds__(256) k_back_bin(KArgs a, GeArgs g) {
     const u32 cell = a.bin_list[(u64)(PS_LIST0 + v) * a.n_cells + (job - cum[v])];
     const u32 M = g.ps_nwin[cell];
     if (M == NONE32) continue;                     // handed back by k_pug_build
-    const u64 need = ps_back_words(M, g.ps_nlab[cell], per);
-    const int tier = need <= pb_arena_words(0) ? 0 : (need <= pb_arena_words(1) ? 1 : (need <= pb_arena_words(2) ? 2 : 3));
+    const u64 need = g.classes_only ? ps_back_words_b(M) : ps_back_words(M, g.ps_nlab[cell], per);
+    // shared-memory tiers up to g.back_max_tier; beyond: per-CTA global arenas at full occupancy (a 100 / 224 KB arena
+    // means 2 / 1 CTAs per SM, which only pays when the cell's EM state would otherwise thrash L2)
+    const int mt = (int)g.back_max_tier;
+    const int tier = need <= pb_arena_words(0) ? 0 : ((mt >= 1 && need <= pb_arena_words(1)) ? 1 : ((mt >= 2 && need <= pb_arena_words(2)) ? 2 : 3));
     g.back_list[(u64)tier * a.n_cells + atomicAdd(&a.ctl->back_count[tier], 1u)] = cell;
   }
 }
@@ -508,7 +511,7 @@ __global__ void __launch_bounds__(PB_THREADS) k_pug_back(KArgs a, GeArgs g) {
     const u32 f0 = a.ref_off[r0];
     if (tid == 0) {
       GePtrs pp{};
-      const bool ok = ps_back_carve(A, 0, AW, M, Lm, a.usa_mode ? 3u : 1u, &pp);
+      const bool ok = g.classes_only ? ps_back_carve_b(A, 0, AW, M, &pp) : ps_back_carve(A, 0, AW, M, Lm, a.usa_mode ? 3u : 1u, &pp);
       pp.mlab = g.ps_mlab + f0; pp.mol_off = g.ps_moff + r0; pp.mol_len = g.ps_mlen + r0;
       s_ptrs = pp;
       sh.flag = ok ? 0u : 1u;

@@ -631,6 +631,20 @@ __device__ inline bool ps_back_carve(u32* A, u32 lo, u32 hi, u32 M, u32 Lm, u32 
   return align8(off) <= (u64)hi * 4;
 }
 
+// stage B only (k_pug_back with classes_only): molecule sort keys + class arrays
+__device__ inline bool ps_back_carve_b(u32* A, u32 lo, u32 hi, u32 M, GePtrs* o) {
+  u64 off = (u64)lo * 4;
+  auto take = [&](u64 bytes) { off = align8(off); u8* r = reinterpret_cast<u8*>(A) + off; off += bytes; return r; };
+  const u32 Mp = next_pow2(M ? M : 1);
+  o->mkey = (u64*)take(8ull * Mp); o->midx = (u32*)take(4ull * Mp);
+  o->gcls_m = (u32*)take(4ull * (M + 1)); o->gcls_cnt = (u32*)take(4ull * (M + 1)); o->gcls_eoff = (u32*)take(4ull * (M + 2));
+  return align8(off) <= (u64)hi * 4;
+}
+__host__ __device__ inline u64 ps_back_words_b(u64 M) {
+  u64 Mp = 1; while (Mp < (M ? M : 1)) Mp <<= 1;
+  return (12 * Mp + 12 * (M + 2) + 8 * 6 + 3) / 4;
+}
+
 // words of arena ps_back_carve needs for M molecules / Lm label words (same arithmetic)
 __host__ __device__ inline u64 ps_back_words(u64 M, u64 Lm, u32 per) {
   auto p2 = [](u64 v) { u64 p = 1; while (p < v) p <<= 1; return p; };

@@ -327,15 +327,15 @@ def measure_config(args, name, cells, res, ctx):
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- roofline of the dominant kernel family (per-cell resolve) -----------------------------
-    fam = {k: v for k, v in prof.items() if k.startswith(("k_resolve", "k_gene_eqc", "k_pug_smem", "k_pug_build", "k_pug_cover", "k_pug_count", "k_pug_back", "k_back_bin"))}
+    fam = {k: v for k, v in prof.items() if k.startswith(("k_resolve", "k_gene_eqc", "k_pug_smem", "k_pug_build", "k_pug_cover", "k_pug_count", "k_pug_back", "k_back_bin", "k_em_cells", "k_em_bin"))}
     fam_ms = sum(v[0] for v in fam.values()) / steps
     region = prof.get("resolve_region(wall)")
     pug_region = prof.get("pug_region(wall)")
     if region:  # arena kernels overlap on lanes: their device time is the wall time of the region(s)
         fam_ms = region[0] / steps
         if pug_region:   # the k_pug_smem variants overlap on lanes too; k_gene_eqc (handed-back cells) runs behind them
-            fam_ms += (pug_region[0] + sum(v[0] for k, v in fam.items() if k.startswith(("k_gene_eqc", "k_pug_count", "k_back_bin")))) / steps
-            for reg in ("cover_region(wall)", "back_region(wall)"):   # split path: the flat cover / back-end kernels overlap on lanes as well
+            fam_ms += (pug_region[0] + sum(v[0] for k, v in fam.items() if k.startswith(("k_gene_eqc", "k_pug_count", "k_back_bin", "k_em_bin")))) / steps
+            for reg in ("cover_region(wall)", "back_region(wall)", "em_region(wall)"):   # split path: the flat cover / back-end kernels overlap on lanes as well
                 if prof.get(reg):
                     fam_ms += prof[reg][0] / steps
         else:
@@ -381,6 +381,15 @@ def measure_config(args, name, cells, res, ctx):
                "sample": f"first {n_sample} cells ({sample.n_records} records) of the workload, {dt:.1f} s of wall time on {cores} threads",
                "note": "C++ restatement of the reference's Rust algorithm (reference not buildable here: no cargo/rustc)"}
 
+    # ---- tie census (parsimony family, rank 0, N=1): how much of the result could depend on the cover's visiting order,
+    # the one place where the reference follows hash-iteration order -------------------------------------
+    census = None
+    if cpu is not None and res.startswith("parsimony"):
+        import oracle_lib
+        cs = parts[0].slice_cells(0, min(parts[0].n_cells, 2000))
+        census = oracle_lib.tie_census(opts, t2g, cs, n_threads=os.cpu_count() or 1)
+        census["sample"] = f"first {cs.n_cells} cells of the workload"
+
     total_cells = nc * world
     cfg = workload_config(synth, name, spec, cells, res, world, rank)
     out = {
@@ -392,6 +401,8 @@ def measure_config(args, name, cells, res, ctx):
                                   ("refs24" if use_p24 else "refs (u32)")},
         "gpu_launches": int(launches) + 0, "clocks": clocks,
     }
+    if census is not None:
+        out["tie_census"] = census
     q.close()
     del db, do, asm_scratch, parts
     pool.close()

@@ -21,7 +21,7 @@ namespace {
 struct EmuLauncher {
   const u32* t2g_ = nullptr;
   std::vector<u8> arena[2];
-  std::vector<u32> adj, garena, sp_win, sp_nwin, sp_mem, sp_desc, sp_glab, sp_mlab, sp_nlab, sp_moff, sp_mlen, sp_big, sp_bga;
+  std::vector<u32> adj, garena, sp_win, sp_nwin, sp_mem, sp_desc, sp_glab, sp_mlab, sp_nlab, sp_moff, sp_mlen, sp_big, sp_bga, c_ncls, c_nlab, c_cnt, c_off, c_lab;
   u64 launches = 0;
   int ge_threads_override = 0;
   const u32* t2g() const { return t2g_; }
@@ -63,6 +63,14 @@ struct EmuLauncher {
     return true;
   }
   int pc_grid(int, size_t) { return 1; }
+  bool em_split() { const char* s = getenv("AFQ_NO_EM_SPLIT"); return !(s && atoi(s)); }
+  bool cls_bufs(u64 n_records, u64 n_refs, u64 n_cells, ClsBufs* o) {
+    c_ncls.assign(n_cells + 4, 0xCDCDCDCDu); c_nlab.assign(n_cells + 4, 0xCDCDCDCDu); c_cnt.assign(n_records + 4, 0xCDCDCDCDu);
+    c_off.assign(n_records + 4, 0xCDCDCDCDu); c_lab.assign(n_refs + 4, 0xCDCDCDCDu);
+    o->ncls = c_ncls.data(); o->nlab = c_nlab.data(); o->cnt = c_cnt.data(); o->off = c_off.data(); o->lab = c_lab.data();
+    return true;
+  }
+  u32 back_max_tier() { const char* s = getenv("AFQ_BACK_MAX_TIER"); return s ? (u32)atoi(s) : 0u; }
   u32* back_garena(u64 words, u32 blocks) { sp_bga.assign((size_t)words * blocks + 16, 0xCDCDCDCDu); return sp_bga.data(); }
   int ps_grid(int v) {
     const char* s = getenv("AFQ_NO_PS");

@@ -296,16 +296,22 @@ def test_pug_smem_runs_and_matches_the_global_arena_kernel(res, monkeypatch):
     t2g = synth.tid_to_gid(spec)
     o = opts_for(spec, res)
     got, launches = gpu_quant_profiled(o, t2g, b)
-    split = res in ("parsimony", "parsimony-gene")   # unique-only: k_pug_build -> k_pug_cover* -> k_pug_count
-    assert sum(n for k, n in launches.items() if k.startswith("k_pug_build" if split else "k_pug_smem")) > 0, launches
-    assert (launches.get("k_pug_count", 0) > 0) == split, launches
+    unique = res in ("parsimony", "parsimony-gene")   # split path: k_pug_build -> k_pug_cover* -> k_pug_count | k_pug_back
+    split = True
+    assert sum(n for k, n in launches.items() if k.startswith("k_pug_build")) > 0, launches
+    assert (launches.get("k_pug_count", 0) > 0) == unique and (launches.get("k_pug_back<0>", 0) > 0) == (not unique), launches
     want = oracle_lib.oracle_quant(o, t2g, b)
     assert_same(got, want, exact=not res.endswith("-em"), ctx=res)
     if split:                                        # the single-kernel form of the same path
         monkeypatch.setenv("AFQ_NO_PS_SPLIT", "1")
         one, launches = gpu_quant_profiled(o, t2g, b)
-        assert sum(n for k, n in launches.items() if k.startswith("k_pug_smem")) > 0 and "k_pug_count" not in launches, launches
-        assert_same(one, want, exact=True, ctx=res + "/no-split")
+        assert sum(n for k, n in launches.items() if k.startswith("k_pug_smem")) > 0 and "k_pug_count" not in launches and "k_pug_back<0>" not in launches, launches
+        monkeypatch.delenv("AFQ_NO_PS_SPLIT")
+        for tier in ("0", "2"):                      # the back end's arena tiers: shared memory only for small cells / for all that fit
+            monkeypatch.setenv("AFQ_BACK_MAX_TIER", tier)
+            assert_same(gpu_quant(o, t2g, b), want, exact=not res.endswith("-em"), ctx=res + "/tier" + tier)
+        monkeypatch.delenv("AFQ_BACK_MAX_TIER")
+        assert_same(one, want, exact=not res.endswith("-em"), ctx=res + "/no-split")
     monkeypatch.setenv("AFQ_NO_PS", "1")            # the global-arena kernel alone
     old, launches = gpu_quant_profiled(o, t2g, b)
     assert sum(n for k, n in launches.items() if k.startswith(("k_pug_smem", "k_pug_build"))) == 0, launches
