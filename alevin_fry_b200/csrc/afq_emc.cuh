@@ -22,10 +22,10 @@ namespace afq {
 
 constexpr u32 EC_THREADS = 256;
 constexpr int EC_TIERS = 4;
-__host__ __device__ constexpr u32 ec_arena_words(int tier) { return tier == 0 ? 6u * 1024u : (tier == 1 ? 13u * 1024u : 48u * 1024u); }
+__host__ __device__ constexpr u32 ec_arena_words(int tier) { return tier == 0 ? 6u * 1024u : (tier == 1 ? 13u * 1024u : 24u * 1024u); }
 __host__ __device__ inline size_t ec_smem_bytes(int tier, u32 num_rows) { return 4ull * (2ull * ((num_rows + 31) / 32) + ec_arena_words(tier) + 8); }
 // arena words of a cell with C classes, E label words, at most S support slots
-__host__ __device__ inline u64 ec_need_words(u64 C, u64 E, u64 S, bool usa) { return (C + 2) + 2 * C + 3 * E + (usa ? 7 : 5) * S + (S + 2) + 64; }
+__host__ __device__ inline u64 ec_need_words(u64 C, u64 E, u64 S, bool usa) { return (C + 2) + 2 * C + 3 * E + (usa ? 5 : 3) * S + (S + 2) + 64; }
 __host__ __device__ inline u64 ec_support_bound(u64 E, u32 num_rows, bool usa) { const u64 s = E * (usa ? 3 : 1); return s < num_rows ? s : num_rows; }
 
 // sort the cells of the k_pug_build lists into the arena tiers of k_em_cells
@@ -40,7 +40,12 @@ __global__ void __launch_bounds__(256) k_em_bin(KArgs a, GeArgs g) {
     const u32 cell = a.bin_list[(u64)(PS_LIST0 + v) * a.n_cells + (job - cum[v])];
     if (g.ps_nwin[cell] == NONE32) continue;       // handed back to k_gene_eqc
     const u64 C = g.dump_ncls[cell], E = g.dump_nlab[cell];
-    const u64 need = ec_need_words(C, E, ec_support_bound(E, a.num_rows, usa), usa);
+    // the support is at most 3 slots per label entry in USA mode and typically ~2.4: the tier is chosen with an estimate and a
+    // cell that turns out larger (exact size known once its bitmap is built) moves to the global-arena tier, which runs last
+    u64 Sest = usa ? (5 * E) / 2 + 8 : E;
+    const u64 Sb = ec_support_bound(E, a.num_rows, usa);
+    if (Sest > Sb) Sest = Sb;
+    const u64 need = ec_need_words(C, E, Sest, usa);
     const int tier = need <= ec_arena_words(0) ? 0 : (need <= ec_arena_words(1) ? 1 : (need <= ec_arena_words(2) ? 2 : 3));
     g.back_list[(u64)tier * a.n_cells + atomicAdd(&a.ctl->em_count[tier], 1u)] = cell;
   }
@@ -54,7 +59,7 @@ __global__ void __launch_bounds__(EC_THREADS) k_em_cells(KArgs a, GeArgs g) {
   u32* gpre = gbm + Wg;                                        // [Wg] support slots before word w
   u32* A = TIER < 3 ? gpre + Wg : g.back_garena + (u64)blockIdx.x * g.back_garena_words;
   __shared__ u32 s_scan[40];
-  __shared__ u32 s_job, s_flag, s_needs_em, s_over;
+  __shared__ u32 s_job, s_flag, s_needs_em, s_over, s_conv[2];
   __shared__ float s_sum, s_max;
   const u32 T = blockDim.x, tid = threadIdx.x;
   const bool usa = a.usa_mode != 0, only_unique = g.only_unique != 0;
@@ -75,7 +80,7 @@ __global__ void __launch_bounds__(EC_THREADS) k_em_cells(KArgs a, GeArgs g) {
     const u32* ccnt = g.dump_cnt + r0;
     const u32* roff = g.dump_off + r0;
     const u32* rlab = g.dump_lab + f0;
-    const u32 Sb = (u32)ec_support_bound(Eraw, a.num_rows, usa);
+    const u32 AW = TIER < 3 ? ec_arena_words(TIER) : g.back_garena_words;
     u32 off = 0;
     u32* coff = A + off; off += C + 2;                         // class -> first (re-mapped) label entry
     float* cinv = reinterpret_cast<float*>(A + off); off += C;
@@ -83,13 +88,11 @@ __global__ void __launch_bounds__(EC_THREADS) k_em_cells(KArgs a, GeArgs g) {
     u32* elab = A + off; off += Eraw;                          // label entries as OUTPUT SLOTS
     u32* eloc = A + off; off += Eraw;
     u32* tr = A + off; off += Eraw;
-    u32* gidx = A + off; off += Sb;
-    float* a_in = reinterpret_cast<float*>(A + off); off += Sb;
-    float* eff = reinterpret_cast<float*>(A + off); off += Sb;
-    u32* tr_off = A + off; off += Sb + 2;
-    u32* tr_cur = A + off; off += Sb;
-    u32* sibA = nullptr; u32* sibB = nullptr;
-    if (usa) { sibA = A + off; off += Sb; sibB = A + off; off += Sb; }
+    if (TIER < 3 && off > AW) {      // (cannot happen: k_em_bin counted these words) -> global-arena tier
+      if (tid == 0) g.back_list[3ull * a.n_cells + atomicAdd(&a.ctl->em_count[3], 1u)] = cell;
+      __syncthreads();
+      continue;
+    }
     // ---- labels as output slots --------------------------------------------------------------------------------------------
     // gene mode: the gene ids themselves. USA, EM: extract_usa_eqmap — S id 2k -> k, U id 2k+1 -> G + k, an adjacent
     // (S, U) pair of one gene -> 2G + k. USA, unique-only: the label's single slot by the tie rules, or nothing.
@@ -151,20 +154,36 @@ __global__ void __launch_bounds__(EC_THREADS) k_em_cells(KArgs a, GeArgs g) {
     }
     __syncthreads();
     u32 S = 0;
-    for (u32 c0 = 0; c0 < Wg; c0 += T) {
-      const u32 i = c0 + tid;
-      const u32 pc = i < Wg ? (u32)__popc(gbm[i]) : 0u;
-      u32 tot;
-      const u32 ex = block_exscan(pc, s_scan, &tot);
-      if (i < Wg) gpre[i] = S + ex;
-      S += tot;
+    {   // prefix popcount over the bitmap words: one chunk per thread (odd length: conflict-free), ONE block scan
+      const u32 Kw = ((Wg + T - 1) / T) | 1u;
+      u32 lo = tid * Kw; if (lo > Wg) lo = Wg;
+      u32 hi = lo + Kw; if (hi > Wg) hi = Wg;
+      u32 cnt = 0;
+      for (u32 i = lo; i < hi; ++i) cnt += (u32)__popc(gbm[i]);
+      u32 pos = block_exscan(cnt, s_scan, &S);
+      for (u32 i = lo; i < hi; ++i) { gpre[i] = pos; pos += (u32)__popc(gbm[i]); }
     }
+    // the support-sized arrays, carved with the exact size
+    if (TIER < 3 && ec_need_words(C, Eraw, S, usa) > AW) {      // larger than k_em_bin's estimate: the global-arena tier (runs last)
+      if (tid == 0) g.back_list[3ull * a.n_cells + atomicAdd(&a.ctl->em_count[3], 1u)] = cell;
+      __syncthreads();
+      continue;
+    }
+    u32* gidx = A + off; off += S;
+    float* a0 = reinterpret_cast<float*>(A + off); off += S;
+    float* a1 = reinterpret_cast<float*>(A + off); off += S;
+    u32* tr_off = A + off; off += S + 2;
+    u32* tr_cur = reinterpret_cast<u32*>(a1);                  // (fill cursors: only before the first iteration)
+    u32* sibA = nullptr; u32* sibB = nullptr;
+    if (usa) { sibA = A + off; off += S; sibB = A + off; off += S; }
+    float* a_in = a0;
+    __syncthreads();
     auto rank_of = [&](u32 s) { return gpre[s >> 5] + (u32)__popc(gbm[s >> 5] & ((1u << (s & 31)) - 1u)); };
     for (u32 i = tid; i < Wg; i += T) {
       u32 w = gbm[i], r = gpre[i];
       while (w) { const u32 b = (u32)__ffs((int)w) - 1; w &= w - 1; gidx[r++] = (i << 5) + b; }
     }
-    for (u32 s = tid; s < S; s += T) { a_in[s] = 0.0f; tr_off[s] = 0; tr_cur[s] = 0; }
+    for (u32 s = tid; s < S; s += T) { a0[s] = 0.0f; tr_off[s] = 0; tr_cur[s] = 0; }
     __syncthreads();
     // ---- local indices, unique tallies, transposed lists ---------------------------------------------------------------
     for (u32 j = tid; j < C; j += T) {
@@ -215,39 +234,42 @@ __global__ void __launch_bounds__(EC_THREADS) k_em_cells(KArgs a, GeArgs g) {
       __syncthreads();
       u32 it = 0;
       bool converged = true, last_round = false;
+      float* a_out = a1;
+      auto abund = [&](const float* av, u32 s) {       // get_abundance_for (src/em.rs:167-187)
+        if (!usa) return av[s];
+        if (gidx[s] >= ao) return __fadd_rn(__fadd_rn(av[sibA[s]], av[sibB[s]]), av[s]);
+        return __fadd_rn(av[sibA[s]], av[s]);
+      };
+      if (tid == 0) { s_conv[0] = 1; s_conv[1] = 1; }
+      __syncthreads();
       while (it < INF_MIN_ITER || (it < INF_MAX_ITER && !converged) || last_round) {
-        for (u32 s = tid; s < S; s += T) {       // get_abundance_for (src/em.rs:167-187)
-          float v;
-          if (!usa) v = a_in[s];
-          else if (gidx[s] >= ao) v = __fadd_rn(__fadd_rn(a_in[sibA[s]], a_in[sibB[s]]), a_in[s]);
-          else v = __fadd_rn(a_in[sibA[s]], a_in[s]);
-          eff[s] = v;
-        }
-        if (tid == 0) s_flag = 1;                // "converged"
-        __syncthreads();
+        // TWO barriers per iteration: the alphas ping-pong between two arrays and the "converged" flag alternates
+        // between two words (the other one is re-armed while this one is in use).
+        // E step: one thread per ambiguous class
         for (u32 j = tid; j < C; j += T) {
           const u32 e0 = coff[j], ln = coff[j + 1] - e0;
           if (ln > 1) {
             float denom = 0.0f;
-            for (u32 k = 0; k < ln; ++k) denom = __fadd_rn(denom, eff[eloc[e0 + k]]);
+            for (u32 k = 0; k < ln; ++k) denom = __fadd_rn(denom, abund(a_in, eloc[e0 + k]));
             cinv[j] = denom > 0.0f ? __fdiv_rn((float)ccnt[j], denom) : -1.0f;
           }
         }
         __syncthreads();
-        for (u32 s = tid; s < S; s += T) {
+        if (tid == 0) s_conv[(it + 1) & 1u] = 1;
+        for (u32 s = tid; s < S; s += T) {       // M step: every slot gathers its classes' contributions in class order
           float sum = 0.0f;
-          const float ef = eff[s];
+          const float ef = abund(a_in, s);
           for (u32 t = tr_off[s]; t < tr_off[s + 1]; ++t) {
             const u32 j = tr[t];
             if (coff[j + 1] - coff[j] == 1) sum = __fadd_rn(sum, (float)ccnt[j]);
             else if (cinv[j] >= 0.0f) sum = __fadd_rn(sum, __fmul_rn(ef, cinv[j]));
           }
-          if (sum > INF_ALPHA_CHECK_CUTOFF && fabsf(__fadd_rn(a_in[s], -sum)) > INF_REL_DIFF_TOLERANCE) s_flag = 0;
-          a_in[s] = sum;
+          if (sum > INF_ALPHA_CHECK_CUTOFF && fabsf(__fadd_rn(a_in[s], -sum)) > INF_REL_DIFF_TOLERANCE) s_conv[it & 1u] = 0;
+          a_out[s] = sum;
         }
         __syncthreads();
-        converged = s_flag != 0;
-        __syncthreads();
+        converged = s_conv[it & 1u] != 0;
+        { float* t = a_in; a_in = a_out; a_out = t; }
         ++it;
         if (usa) {     // M2: clamp, then one last round (src/em.rs:391-443)
           if (last_round) break;

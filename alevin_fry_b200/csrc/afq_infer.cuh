@@ -151,13 +151,14 @@ __global__ void __launch_bounds__(INF_THREADS) k_em_subset(InferArgs p) {
     }
     __syncthreads();
     u32 S = 0;
-    for (u32 c0 = 0; c0 < Wg; c0 += T) {
-      const u32 i = c0 + tid;
-      const u32 pc = i < Wg ? (u32)__popc(gbm[i]) : 0u;
-      u32 tot;
-      const u32 ex = block_exscan(pc, s_scan, &tot);
-      if (i < Wg) gpre[i] = S + ex;
-      S += tot;
+    {   // prefix popcount: one chunk of words per thread (odd length: conflict-free), ONE block scan
+      const u32 Kw = ((Wg + T - 1) / T) | 1u;
+      u32 lo = tid * Kw; if (lo > Wg) lo = Wg;
+      u32 hi = lo + Kw; if (hi > Wg) hi = Wg;
+      u32 pc = 0;
+      for (u32 i = lo; i < hi; ++i) pc += (u32)__popc(gbm[i]);
+      u32 pos = block_exscan(pc, s_scan, &S);
+      for (u32 i = lo; i < hi; ++i) { gpre[i] = pos; pos += (u32)__popc(gbm[i]); }
     }
     auto rank_of = [&](u32 g) { return gpre[g >> 5] + (u32)__popc(gbm[g >> 5] & ((1u << (g & 31)) - 1u)); };
     for (u32 i = tid; i < Wg; i += T) {

@@ -303,12 +303,13 @@ int enqueue_batch(L& l, const afq_config& cfg, int force_bin, const PipeBufs& pb
         if (em_split) {
           l.launch(KID_EM_CELLS + 4, k_em_bin, (unsigned)((ps_cells + 255) / 256), 256u, (size_t)0, a, g);
           l.region_begin();
-          l.fork(EC_TIERS);
-          l.lane(3); l.launch(KID_EM_CELLS + 3, k_em_cells<3>, (unsigned)l.pc_grid(9, 0), EC_THREADS, ec_smem_bytes(3, cfg.num_rows) - 4ull * ec_arena_words(2), a, g);
+          l.fork(3);
           l.lane(2); l.launch(KID_EM_CELLS + 2, k_em_cells<2>, (unsigned)l.pc_grid(8, 0), EC_THREADS, ec_smem_bytes(2, cfg.num_rows), a, g);
           l.lane(1); l.launch(KID_EM_CELLS + 1, k_em_cells<1>, (unsigned)l.pc_grid(7, 0), EC_THREADS, ec_smem_bytes(1, cfg.num_rows), a, g);
           l.lane(0); l.launch(KID_EM_CELLS + 0, k_em_cells<0>, (unsigned)l.pc_grid(6, 0), EC_THREADS, ec_smem_bytes(0, cfg.num_rows), a, g);
           l.join();
+          // the global-arena tier runs last: it also takes the cells whose exact support exceeded their tier's arena
+          l.launch(KID_EM_CELLS + 3, k_em_cells<3>, (unsigned)l.pc_grid(9, 0), EC_THREADS, ec_smem_bytes(3, cfg.num_rows) - 4ull * ec_arena_words(2), a, g);
           l.region_end(KID_EM_REGION);
           g.classes_only = 0;      // (k_gene_eqc behind runs the whole back end for the handed-back cells)
         }

@@ -418,13 +418,14 @@ __global__ void __launch_bounds__(PC_THREADS) k_pug_count(KArgs a, GeArgs g) {
     for (u32 i = tid; i < m; i += T) { const u32 s = win[i]; atomicOr(&gbm[s >> 5], 1u << (s & 31)); }
     __syncthreads();
     u32 nnz = 0;
-    for (u32 c0 = 0; c0 < Wg; c0 += T) {
-      const u32 i = c0 + tid;
-      const u32 pc = i < Wg ? (u32)__popc(gbm[i]) : 0u;
-      u32 tot;
-      const u32 ex = block_exscan(pc, s_scan, &tot);
-      if (i < Wg) gpre[i] = nnz + ex;
-      nnz += tot;
+    {   // prefix popcount: one chunk of words per thread (odd length: conflict-free), ONE block scan
+      const u32 Kw = ((Wg + T - 1) / T) | 1u;
+      u32 lo = tid * Kw; if (lo > Wg) lo = Wg;
+      u32 hi = lo + Kw; if (hi > Wg) hi = Wg;
+      u32 pc = 0;
+      for (u32 i = lo; i < hi; ++i) pc += (u32)__popc(gbm[i]);
+      u32 pos = block_exscan(pc, s_scan, &nnz);
+      for (u32 i = lo; i < hi; ++i) { gpre[i] = pos; pos += (u32)__popc(gbm[i]); }
     }
     // the per-slot counters: shared memory, or for a giant cell (more molecules than PC_MAX_WINNERS) the cell's region of
     // the member pool, which is dead once the cover kernels are done (4 words per record >= nnz)
