@@ -160,6 +160,7 @@ __global__ void __launch_bounds__(INF_THREADS) k_em_subset(InferArgs p) {
       u32 pos = block_exscan(pc, s_scan, &S);
       for (u32 i = lo; i < hi; ++i) { gpre[i] = pos; pos += (u32)__popc(gbm[i]); }
     }
+    __syncthreads();       // (the prefix words are read by other threads from here on)
     auto rank_of = [&](u32 g) { return gpre[g >> 5] + (u32)__popc(gbm[g >> 5] & ((1u << (g & 31)) - 1u)); };
     for (u32 i = tid; i < Wg; i += T) {
       u32 w = gbm[i], r = gpre[i];
