@@ -190,7 +190,7 @@ int enqueue_batch(L& l, const afq_config& cfg, int force_bin, const PipeBufs& pb
                        l.ps_split(b.n_records, b.n_refs_total, b.n_cells, g.ge_mode == GE_MODE_PUG_GENE, want_mol, &sb);
     const bool ps_on = split || (l.ps_grid(0) > 0 && (g.ge_mode == GE_MODE_CRLIKE ? (!cfg.usa_mode && !a.prefer_ambig) : cfg.large_graph_thresh >= 2));
     // (bit 2: the in-kernel arena also holds the molecules and the EM back end — not on the split path)
-    const u32 ps_mode = ps_on ? (1u | (g.ge_mode == GE_MODE_PUG_GENE ? 2u : 0u) | ((want_mol && !split) ? 4u : 0u) | (l.ps_grid(3) > 0 ? 8u : 0u)) : 0u;
+    const u32 ps_mode = ps_on ? (1u | (g.ge_mode == GE_MODE_PUG_GENE ? 2u : 0u) | ((want_mol && !split) ? 4u : 0u) | (l.ps_grid(3) > 0 ? 8u : 0u) | (split ? 16u : 0u)) : 0u;
     l.launch(KID_BIN_GE, k_bin_cells_ge, bin_grid, 256u, (size_t)0, a, force_bin, GE_BIG_RECORDS, l.need_shift(), ps_mode);
     launch_crlike_bins(l, a, pb);
     Ctl h{};

@@ -75,11 +75,12 @@ __host__ __device__ inline u32 ps_table_size(u32 n) { return pow2_ge(n + n / 4 +
 
 // Arena words a cell of n records / P alignments is EXPECTED to need (vertex count guessed at
 // n/2; the kernel re-checks with the real counts and falls back if they do not fit).
-__host__ __device__ inline u32 ps_need_words(u32 n, u32 P, bool gene, bool em, bool usa) {
+__host__ __device__ inline u32 ps_need_words(u32 n, u32 P, bool gene, bool em, bool usa, bool split = false) {
   const u32 rec = n + (n + 1) / 2 + ps_table_size(n);          // UMIs, classes, table: dead after compaction
   const u32 vest = n / 2 + 16;
   u32 bw = pow2_ge(2 * vest, 64); if (bw > 4096) bw = 4096;
-  const u32 post = pow2_ge(vest + vest / 2 + 2, 64) + bw + 2 * vest + (em ? 0 : pow2_ge(vest, 1)) + PS_COVER_WARPS * PS_WSCR_WORDS;
+  // (the split form keeps no winners / cover scratch in the arena, only the staged singleton slots)
+  const u32 post = pow2_ge(vest + vest / 2 + 2, 64) + bw + 2 * vest + (split ? vest : ((em ? 0 : pow2_ge(vest, 1)) + PS_COVER_WARPS * PS_WSCR_WORDS));
   u32 w = P + (n + 2) / 2 + (gene ? (n + 1) / 2 : 0) + rec + 3 * vest + (post > rec ? post - rec : 0) + 24;   // (+ alignment slack of the bulk-copied arrays)
   if (em) {
     w += 2 * vest + P / 2 + 64;
@@ -92,10 +93,10 @@ __host__ __device__ inline u32 ps_need_words(u32 n, u32 P, bool gene, bool em, b
   return w;
 }
 // smallest arena variant that is expected to hold the cell, or -1 (global_ok: variant 3 is available)
-__host__ __device__ inline int ps_variant_for(u64 n, u64 P, bool gene, bool em, bool usa, bool global_ok) {
+__host__ __device__ inline int ps_variant_for(u64 n, u64 P, bool gene, bool em, bool usa, bool global_ok, bool split = false) {
   if (n >= PS_MAX_RECORDS || P >= (1ull << 30) || n == 0) return -1;
   if (P < PS_MAX_REFS) {
-    const u32 need = ps_need_words((u32)n, (u32)P, gene, em, usa);
+    const u32 need = ps_need_words((u32)n, (u32)P, gene, em, usa, split);
     for (int v = 0; v < PS_SMEM_VARIANTS; ++v)
       if (need <= ps_arena_words(v)) return v;
   }
@@ -1345,7 +1346,7 @@ __global__ void __launch_bounds__(ps_threads(VAR), ps_build_min_blocks(VAR)) k_p
 
 // classify cells for the gene-eq-class resolutions: tiny cells go to the cr-like arenas
 // (src/quant.rs:794-846); cells expected to fit a shared-memory arena go to k_pug_smem's lists
-// (ps_mode bit 0: enabled, bit 1: gene-level labels, bit 2: EM, bit 3: global-arena variant available); the rest to the k_gene_eqc lists.
+// (ps_mode bit 0: enabled, bit 1: gene-level labels, bit 2: EM, bit 3: global-arena variant available, bit 4: split form); the rest to the k_gene_eqc lists.
 // ge_max_n / ge_max_p cover every non-tiny cell of their size class because k_pug_smem may hand
 // any of its cells back to the k_gene_eqc list.
 __global__ void k_bin_cells_ge(KArgs a, int force_bin, u32 big_records, u32 need_shift, u32 ps_mode) {
@@ -1369,7 +1370,7 @@ __global__ void k_bin_cells_ge(KArgs a, int force_bin, u32 big_records, u32 need
     atomicMax(&a.ctl->ge_max_n[w], (u32)n);
     atomicMax(&a.ctl->ge_max_p[w], p);
     if (w == 1 && (ps_mode & 1u)) {
-      const int v = ps_variant_for(n, p, (ps_mode & 2u) != 0, (ps_mode & 4u) != 0, a.usa_mode != 0, (ps_mode & 8u) != 0);
+      const int v = ps_variant_for(n, p, (ps_mode & 2u) != 0, (ps_mode & 4u) != 0, a.usa_mode != 0, (ps_mode & 8u) != 0, (ps_mode & 16u) != 0);
       if (v >= 0) b = PS_LIST0 + v;
       if (v == 3) { atomicMax(&a.ctl->ps3_max_n, (u32)n); atomicMax(&a.ctl->ps3_max_p, p); }
     }
