@@ -90,6 +90,7 @@ SYMBOLS = {
     "afq_infer": (C.c_int, [C.c_void_p, C.POINTER(AfqEqcTable), C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(AfqResult)]),
     "afq_abi_version": (C.c_int, []),
     "afq_launch_count": (C.c_uint64, [C.c_void_p]),
+    "afq_rerun_count": (C.c_uint64, [C.c_void_p]),
     "afq_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "afq_profile_collect": (C.c_int, [C.c_void_p]),
     "afq_profile_reset": (C.c_int, [C.c_void_p]),

@@ -80,6 +80,7 @@ struct Work {  // per-pipeline scratch (ordered on one stream)
   DBuf<u64> na_tiles;      // rec_na8 -> offsets scan
   DBuf<u32> na_ref_off;    // device API: offsets derived from rec_na8
   DBuf<u32> umi_wide, refs_wide;   // rec_umi24 / refs24 widened to u32
+  bool sync_sizing = true;         // read the control block back after the binning (device API) or plan the global arenas blind (afq_submit)
   cudaError_t ensure(u64 n_cells, u64 n_refs) {
     cudaError_t e;
     if ((e = ctl.ensure(1)) != cudaSuccess) return e;
@@ -119,7 +120,8 @@ struct Slot {  // one in-flight host batch
   HBuf<u64> h_cls_ptr, h_lab_base, h_cls_lab_ptr;
   HBuf<u32> h_dq_counts, h_dq_labels;
   u64 n_records = 0;
-  bool has_dump = false, retried = false;
+  bool has_dump = false;
+  u32 retried = 0;          // re-runs done for this batch (bit 0: giant-cell arenas grown, bit 1: arena pools grown)
   afq_batch db{};             // the batch with DEVICE pointers (giant-cell retry)
   afq_device_out dout{};
   cudaEvent_t ev_h2d = nullptr, ev_done = nullptr, ev_d2h = nullptr;
@@ -152,6 +154,7 @@ struct afq_ctx {
   u64 n_refs = 0;
   std::string err;
   u64 launches = 0;
+  u64 reruns = 0;
   // giant-cell scratch
   u64* large_keys = nullptr;
   u32* large_cnts = nullptr;
@@ -171,6 +174,11 @@ struct afq_ctx {
   int grid_back[4] = {0, 0, 0, 0};   // k_pug_back<tier>
   int grid_em[4] = {0, 0, 0, 0};     // k_em_cells<tier>
   bool no_em_split = false;    // AFQ_NO_EM_SPLIT=1: k_pug_back runs ge_back's own stage C (A/B)
+  // pools of the per-CTA global arenas on the afq_submit path (no read-back, see k_plan_arenas): sizes learnt from the batches seen
+  // so far — k_pug_build<3> words, k_pug_back<3> / k_em_cells<3> words, k_gene_eqc bytes (big / normal list)
+  u64 pool_hint[4] = {0, 0, 0, 0};
+  u64 pool_default_bytes = 256ull << 20;   // AFQ_POOL_MB: every pool's initial size
+  u64 pool_budget_bytes = 8ull << 30;      // no pool is grown beyond this for full occupancy (it always holds one arena)
   u32 back_max_tier = 0;       // AFQ_BACK_MAX_TIER: largest shared-memory arena tier of k_pug_back (r2j: 0 is fastest on C3-em / C4 / C5)
   cudaStream_t lanes[NUM_BINS] = {nullptr};
   cudaEvent_t ev_fork = nullptr, ev_lane[NUM_BINS] = {nullptr};
@@ -253,6 +261,18 @@ struct CudaLauncher {
     k<<<grid, block, smem, cur>>>(args...);
   }
   int memset_zero(void* p, size_t n) { return cudaMemsetAsync(p, 0, n, st) != cudaSuccess; }
+  bool sync_sizing() { return w->sync_sizing; }
+  template <class T>
+  T* pool(DBuf<T>& buf, int which, u64 min_elems, u64* cap) {
+    u64 want = min_elems;
+    if (!w->sync_sizing) {
+      const u64 learnt = c->pool_hint[which] > c->pool_default_bytes / sizeof(T) ? c->pool_hint[which] : c->pool_default_bytes / sizeof(T);
+      if (learnt > want) want = learnt;
+    }
+    if (buf.ensure((size_t)want + 64) != cudaSuccess) return nullptr;
+    *cap = buf.cap - 64;
+    return buf.p;
+  }
   int read_ctl(const Ctl* d, Ctl* h) {
     if (cudaMemcpyAsync(c->h_ctl_dev, d, sizeof(Ctl), cudaMemcpyDeviceToHost, st) != cudaSuccess) return 1;
     if (cudaStreamSynchronize(st) != cudaSuccess) return 1;
@@ -261,14 +281,11 @@ struct CudaLauncher {
   }
   int grid_for_bin(int b) { return c->grid_smem[b]; }
   int ge_blocks(int which) { return which == 0 ? 16 : c->ge_grid; }
-  u8* ge_arena(int which, u64 bytes, u32 blocks) {
-    if (w->ge_arena[which].ensure((size_t)bytes * blocks + 64) != cudaSuccess) return nullptr;
-    return w->ge_arena[which].p;
-  }
+  u8* ge_arena(int which, u64 min_bytes, u64* cap) { return pool(w->ge_arena[which], 2 + which, min_bytes, cap); }
   u32* adj_pool(u64 n) { return w->adj_pool.ensure((size_t)n) == cudaSuccess ? w->adj_pool.p : nullptr; }
   u32 need_shift() { return c->need_shift; }
   int ps_grid(int v) { return (c->no_ps || (v == 3 && c->no_ps_global)) ? 0 : c->grid_ps[v]; }
-  u32* ps_garena(u64 words, u32 blocks) { return w->ps_garena.ensure((size_t)words * blocks + 16) == cudaSuccess ? w->ps_garena.p : nullptr; }
+  u32* ps_garena(u64 min_words, u64* cap) { return pool(w->ps_garena, 0, min_words, cap); }
   u32 ps_limit_words() { return c->ps_limit_words; }
   bool ps_split(u64 n_records, u64 n_refs, u64 n_cells, bool gene_labels, bool molecules, PsSplitBufs* o) {
     if (c->no_ps_split || (molecules ? c->grid_back[0] <= 0 : c->grid_count <= 0)) return false;
@@ -297,7 +314,7 @@ struct CudaLauncher {
     o->ncls = w->cls_ncls.p; o->nlab = w->cls_nlab.p; o->cnt = w->cls_cnt.p; o->off = w->cls_off.p; o->lab = w->cls_lab.p;
     return true;
   }
-  u32* back_garena(u64 words, u32 blocks) { return w->ps_back_garena.ensure((size_t)words * blocks + 16) == cudaSuccess ? w->ps_back_garena.p : nullptr; }
+  u32* back_garena(u64 min_words, u64* cap) { return pool(w->ps_back_garena, 1, min_words, cap); }
   // fork / join: lanes are ctx-owned non-blocking streams ordered after / before the caller stream
   void fork(int n) {
     if (c->no_lanes) return;
@@ -391,6 +408,22 @@ void learn_from(afq_ctx* c, const Ctl& h) {
   u64 total = 0;
   for (int i = 0; i < NUM_LISTS; ++i) if (i != OVF_LIST) total += h.bin_count[i];
   if (total >= 64 && (u64)h.bin_count[OVF_LIST] * 50 > total && c->need_shift < 2) c->need_shift++;
+  // the arena pools of the afq_submit path: room for every CTA of the grid at this batch's strides (within the budget, and
+  // never less than one arena), so that later batches with cells like these run at full occupancy
+  if (c->cfg.resolution == AFQ_RES_CR_LIKE || c->cfg.resolution == AFQ_RES_TRIVIAL) return;
+  auto learn = [&](int which, u64 stride, u64 blocks, u64 elem_bytes) {
+    u64 wantv = stride * (blocks ? blocks : 1);
+    const u64 budget = c->pool_budget_bytes / elem_bytes;
+    if (wantv > budget) wantv = budget;
+    if (wantv < stride) wantv = stride;
+    wantv += 64;
+    if (wantv > c->pool_hint[which]) c->pool_hint[which] = wantv;
+  };
+  const bool starved = (h.error & DEV_ERR_POOL) != 0;      // (k_plan_arenas emptied the lists: learn every stride)
+  if (h.bin_count[PS_LIST0 + 3] || starved) learn(0, h.ps3_words, (u64)c->grid_ps[3], 4);
+  learn(1, h.back_words, (u64)std::max(c->grid_back[3], c->grid_em[3]), 4);
+  if (h.bin_count[GE_LIST_BIG] || starved) learn(2, h.ge_bytes[0], 16, 1);
+  learn(3, h.ge_bytes[1], std::min<u64>((u64)c->ge_grid, (u64)h.bin_count[GE_LIST_NORMAL] + 148), 1);
 }
 
 int check_device_error(afq_ctx* c, const Ctl& h) {
@@ -398,7 +431,8 @@ int check_device_error(afq_ctx* c, const Ctl& h) {
   if (getenv("AFQ_DEBUG_CTL")) {     // work-list sizes of the batch (diagnostics)
     fprintf(stderr, "[afq ctl] lists:");
     for (int i = 0; i < NUM_LISTS; ++i) fprintf(stderr, " %u", h.bin_count[i]);
-    fprintf(stderr, " | descs: %u %u %u %u | error %u\n", h.desc_count[0], h.desc_count[1], h.desc_count[2], h.desc_count[3], h.error);
+    fprintf(stderr, " | descs: %u %u %u %u | arenas: ps3 %u w x %u, back %u w x %u, ge %llu B x %u / %llu B x %u | error %u\n", h.desc_count[0], h.desc_count[1],
+            h.desc_count[2], h.desc_count[3], h.ps3_words, h.ps3_blocks, h.back_words, h.back_blocks, h.ge_bytes[0], h.ge_blocks[0], h.ge_bytes[1], h.ge_blocks[1], h.error);
   }
   if (!h.error) return AFQ_OK;
   std::string buf;
@@ -449,7 +483,19 @@ int grow_large_arena_and_rerun(afq_ctx* c, Slot& s, u32 max_cell_refs) {
   CUDA_TRY(c, cudaMalloc((void**)&c->large_keys, entries * sizeof(u64)));
   CUDA_TRY(c, cudaMalloc((void**)&c->large_cnts, entries * sizeof(u32)));
   c->large_cap_log2 = log2cap; c->large_blocks = blocks;
-  s.retried = true;
+  int rc = enqueue_slot(c, s);
+  if (rc != AFQ_OK) return rc;
+  CUDA_TRY(c, cudaStreamSynchronize(c->s_compute));
+  return AFQ_OK;
+}
+
+// A global-arena kernel found no arena in its pool for the batch's largest cell (DEV_ERR_POOL, afq_submit path): the pools were
+// sized from earlier batches. learn_from() has the strides of this one; run it again on pools that hold them.
+int grow_pools_and_rerun(afq_ctx* c, Slot& s) {
+  const Ctl& h = *s.h_ctl.p;
+  if (h.ps3_words >= 0xFFFFFFF0u || h.back_words >= 0xFFFFFFF0u) { c->err = "a cell needs a global arena of more than 2^32 words"; return AFQ_ERR_UNSUPPORTED; }
+  learn_from(c, h);
+  CUDA_TRY(c, cudaStreamSynchronize(c->s_compute));
   int rc = enqueue_slot(c, s);
   if (rc != AFQ_OK) return rc;
   CUDA_TRY(c, cudaStreamSynchronize(c->s_compute));
@@ -457,6 +503,12 @@ int grow_large_arena_and_rerun(afq_ctx* c, Slot& s, u32 max_cell_refs) {
 }
 
 }  // namespace
+
+// The pipeline keeps ~10 streams busy (copy, compute, read-back, up to 7 lanes). With the default of 8 hardware work queues
+// several of them share one, and a host that runs batches ahead gets its uploads queued behind the lane kernels of the batch
+// before (measured r2u: C4 e2e 83.6 ms at 8 queues, 70.9 ms at 32). The setting is read when the CUDA context is created, so it
+// is made here, when the library is loaded — unless the application has chosen a value itself.
+__attribute__((constructor)) static void afq_more_hardware_queues() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
 
 extern "C" {
 
@@ -507,6 +559,14 @@ int afq_create(const afq_config* cfg, const uint32_t* tid_to_gid, uint64_t n_ref
   if (const char* s = getenv("AFQ_NO_PS_GLOBAL")) c->no_ps_global = atoi(s) != 0;
   if (const char* s = getenv("AFQ_NO_PS_SPLIT")) c->no_ps_split = atoi(s) != 0;
   if (const char* s = getenv("AFQ_BACK_MAX_TIER")) c->back_max_tier = (u32)atoi(s);
+  if (const char* s = getenv("AFQ_POOL_MB")) c->pool_default_bytes = (u64)std::max(1, atoi(s)) << 20;
+  c->work_dev.sync_sizing = true;
+  c->work_host.sync_sizing = false;       // afq_submit never waits for the device
+  if (const char* s = getenv("AFQ_SYNC_SIZING")) c->work_host.sync_sizing = atoi(s) != 0;   // (A/B: the read-back of round 1)
+  {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b) c->pool_budget_bytes = std::max<u64>(1ull << 30, (u64)total_b / 16);
+  }
   if (const char* s = getenv("AFQ_NO_EM_SPLIT")) c->no_em_split = atoi(s) != 0;
   if (const char* s = getenv("AFQ_PS_LIMIT_WORDS")) c->ps_limit_words = (u32)atoi(s);
   if (c->large_cap_log2 < 10) c->large_cap_log2 = 10;
@@ -525,6 +585,7 @@ int afq_create(const afq_config* cfg, const uint32_t* tid_to_gid, uint64_t n_ref
   CREATE_TRY(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
   CREATE_TRY(cudaHostAlloc((void**)&c->h_ctl_dev, sizeof(Ctl), cudaHostAllocDefault));
   CREATE_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  // (stream priorities for the lanes of the larger arenas were tried, r2v: no effect on any configuration)
   for (int i = 0; i < NUM_BINS; ++i) {
     CREATE_TRY(cudaStreamCreateWithFlags(&c->lanes[i], cudaStreamNonBlocking));
     CREATE_TRY(cudaEventCreateWithFlags(&c->ev_lane[i], cudaEventDisableTiming));
@@ -704,7 +765,7 @@ int afq_submit(afq_ctx* c, const afq_batch* hb, uint64_t* ticket) {
   o.col = s.col.p; o.val = s.val.p; o.cap_nnz = nf + 1;
   o.sum_umi = s.sum_umi.p; o.max_umi = s.max_umi.p;
   o.num_expr = s.num_expr.p; o.num_over_mean = s.num_over_mean.p; o.flags = s.flags.p;
-  s.db = db; s.dout = o; s.n_cells = nc; s.n_refs = nf; s.n_records = nr; s.retried = false;
+  s.db = db; s.dout = o; s.n_cells = nc; s.n_refs = nf; s.n_records = nr; s.retried = 0;
   int rc = enqueue_slot(c, s);
   if (rc != AFQ_OK) return rc;
   CUDA_TRY(c, cudaEventRecord(s.ev_done, c->s_compute));
@@ -727,9 +788,14 @@ int afq_wait(afq_ctx* c, uint64_t ticket, afq_result* out) {
   cudaError_t e = cudaEventSynchronize(s.ev_done);
   lk.lock();
   if (e != cudaSuccess) { c->err = std::string("cudaEventSynchronize(ev_done): ") + cudaGetErrorString(e); s.busy = false; return AFQ_ERR_CUDA; }
-  if ((s.h_ctl.p->error & DEV_ERR_CELL_TOO_LARGE) && !s.retried) {
-    const int rr = grow_large_arena_and_rerun(c, s, s.h_ctl.p->max_cell_refs);
+  for (int attempt = 0; attempt < 2; ++attempt) {      // (each cause at most once)
+    const u32 flags = s.h_ctl.p->error;
+    int rr = AFQ_OK;
+    if ((flags & DEV_ERR_CELL_TOO_LARGE) && !(s.retried & 1)) { s.retried |= 1; rr = grow_large_arena_and_rerun(c, s, s.h_ctl.p->max_cell_refs); }
+    else if ((flags & DEV_ERR_POOL) && !(s.retried & 2)) { s.retried |= 2; rr = grow_pools_and_rerun(c, s); }
+    else break;
     if (rr != AFQ_OK) { s.busy = false; return rr; }
+    c->reruns++;
   }
   int rc = check_device_error(c, *s.h_ctl.p);
   if (rc != AFQ_OK) { s.busy = false; return rc; }
@@ -925,6 +991,7 @@ int afq_device_count(void) {
 void afq_host_free(void* ptr) { if (ptr) cudaFreeHost(ptr); }
 
 uint64_t afq_launch_count(const afq_ctx* c) { return c ? c->launches : 0; }
+uint64_t afq_rerun_count(const afq_ctx* c) { return c ? c->reruns : 0; }
 
 int afq_set_profiling(afq_ctx* c, int enable) {
   if (!c) return AFQ_ERR_INVALID;

@@ -57,7 +57,9 @@ __global__ void __launch_bounds__(EC_THREADS) k_em_cells(KArgs a, GeArgs g) {
   u32* gbm = reinterpret_cast<u32*>(smem_raw);                 // [Wg] presence bitmap over the output slots
   const u32 Wg = (a.num_rows + 31) >> 5;
   u32* gpre = gbm + Wg;                                        // [Wg] support slots before word w
-  u32* A = TIER < 3 ? gpre + Wg : g.back_garena + (u64)blockIdx.x * g.back_garena_words;
+  if (TIER == 3 && arena_cta_idle(a.ctl, a.ctl->back_blocks, a.ctl->em_count[3])) return;
+  const u32 gwords = TIER < 3 ? 0u : a.ctl->back_words;
+  u32* A = TIER < 3 ? gpre + Wg : g.back_garena + (u64)blockIdx.x * gwords;
   __shared__ u32 s_scan[40];
   __shared__ u32 s_job, s_flag, s_needs_em, s_over, s_conv[2];
   __shared__ float s_sum, s_max;
@@ -80,7 +82,7 @@ __global__ void __launch_bounds__(EC_THREADS) k_em_cells(KArgs a, GeArgs g) {
     const u32* ccnt = g.dump_cnt + r0;
     const u32* roff = g.dump_off + r0;
     const u32* rlab = g.dump_lab + f0;
-    const u32 AW = TIER < 3 ? ec_arena_words(TIER) : g.back_garena_words;
+    const u32 AW = TIER < 3 ? ec_arena_words(TIER) : gwords;
     u32 off = 0;
     u32* coff = A + off; off += C + 2;                         // class -> first (re-mapped) label entry
     float* cinv = reinterpret_cast<float*>(A + off); off += C;

@@ -28,7 +28,8 @@ __host__ __device__ constexpr u32 bin_threads(int b) {
 }
 
 enum : u32 { MODE_CRLIKE = 0, MODE_TRIVIAL = 1 };
-enum : u32 { DEV_ERR_CELL_TOO_LARGE = 1 };
+enum : u32 { DEV_ERR_CELL_TOO_LARGE = 1, DEV_ERR_POOL = 32 };   // (2..16: afq_pug.cuh)
+
 
 constexpr int NUM_LISTS = NUM_BINS + 7;          // + two k_gene_eqc lists (big / normal cells) + arena-overflow list + four k_pug_smem lists
 constexpr int OVF_LIST = NUM_BINS + 2;           // cells whose distinct pairs overflowed their shared-memory arena
@@ -46,7 +47,21 @@ struct Ctl {                       // per-batch device control block (zeroed per
   u32 count_cursor;                // k_pug_count's / k_pug_back's work cursor over the cells of the four k_pug_build lists
   u32 back_count[4], back_cursor[4];     // k_pug_back's arena tiers: cells / work cursors
   u32 em_count[4], em_cursor[4];         // k_em_cells' arena tiers
+  // per-CTA global arenas, planned ON THE DEVICE from the batch's maxima above (k_plan_arenas, afq_pipeline.cuh) so that the
+  // host never reads this block back between the binning and the kernels: words / bytes per CTA and the CTAs that have one
+  u32 ps3_words, ps3_blocks;             // k_pug_build<3> / k_pug_smem<3>
+  u32 back_words, back_blocks;           // k_pug_back<3> / k_em_cells<3>
+  u32 ge_blocks[2];                      // k_gene_eqc (big / normal list)
+  unsigned long long ge_bytes[2];
 };
+
+// a CTA of a global-arena kernel beyond the CTAs its pool holds arenas for leaves; if the pool holds none at all and there is
+// work, the batch is flagged (the host API grows the pool and runs the batch again)
+__device__ __forceinline__ bool arena_cta_idle(Ctl* ctl, u32 blocks, u32 work) {
+  if (blockIdx.x < blocks) return false;
+  if (blocks == 0 && blockIdx.x == 0 && threadIdx.x == 0 && work) atomicOr(&ctl->error, (u32)DEV_ERR_POOL);
+  return true;
+}
 
 struct KArgs {
   // input batch (device)

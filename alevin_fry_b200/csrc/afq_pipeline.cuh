@@ -7,22 +7,23 @@
 //   template <class... P, class... A>
 //   void launch(int kid, void (*kernel)(P...), unsigned grid, unsigned block, size_t smem, A... args);
 //   int  memset_zero(void* dev, size_t bytes);                // 0 on success
-//   int  read_ctl(const Ctl* dev, Ctl* host);                 // synchronising read-back
+//   bool sync_sizing();                                       // read the control block back after the binning and size the global arenas exactly
+//   int  read_ctl(const Ctl* dev, Ctl* host);                 // synchronising read-back (sync_sizing() only)
 //   int  grid_for_bin(int bin);                               // persistent grid size
 //   int  ge_blocks(int which);                                // 0 big-cell grid, 1 normal grid
-//   u8*  ge_arena(int which, u64 bytes_per_block, u32 blocks);// grow-only, nullptr on failure
+//   u8*  ge_arena(int which, u64 min_bytes, u64* cap_bytes);  // grow-only pool of k_gene_eqc's arenas (min 0: the learnt size), nullptr on failure
 //   u32* adj_pool(u64 entries);                               // grow-only, nullptr on failure
 //   void region_begin(); void region_end(int kid);            // wall time of a forked region (profiling)
 //   void fork(int lanes); void lane(int i); void join();      // independent launches may overlap:
 //       between fork and join, launches go to lane i's stream (CUDA) / run in order (emulator)
 //   u32  need_shift();                                        // arena-size bias learnt from overflows
 //   int  ps_grid(int variant);                                // persistent grid of k_pug_smem<variant>; 0 = disabled
-//   u32* ps_garena(u64 words_per_block, u32 blocks);          // grow-only global arenas of k_pug_smem<3>, nullptr on failure
+//   u32* ps_garena(u64 min_words, u64* cap_words);            // grow-only pool of the global arenas of k_pug_smem<3> / k_pug_build<3>, nullptr on failure
 //   u32  ps_limit_words();                                    // 0, or a smaller arena for k_pug_smem (tests: forces fallbacks)
 //   bool ps_split(u64 n_records, u64 n_refs, u64 n_cells, bool gene_labels, bool molecules, PsSplitBufs* out);
 //                                                              // grow-only global buffers of the split parsimony path; false = not available
 //   int  pc_grid(int which, size_t smem);                     // grid of the flat cover kernels (0) / k_pug_count (1) / k_pug_back tiers 0..3 (2..5) / k_em_cells tiers 0..3 (6..9)
-//   u32* back_garena(u64 words_per_block, u32 blocks);        // grow-only global arenas of k_pug_back<3>, nullptr on failure
+//   u32* back_garena(u64 min_words, u64* cap_words);          // grow-only pool of the global arenas of k_pug_back<3> / k_em_cells<3>, nullptr on failure
 //   u32  back_max_tier();                                     // largest shared-memory tier of k_pug_back (AFQ_BACK_MAX_TIER)
 //   bool em_split();                                          // stage C in k_em_cells (default) or inside k_pug_back (AFQ_NO_EM_SPLIT=1)
 //   bool cls_bufs(u64 n_records, u64 n_refs, u64 n_cells, ClsBufs* out);   // internal class regions (no --dump-eqclasses)
@@ -42,7 +43,7 @@ enum KernelId : int {
   KID_BIN = 0, KID_SMEM0 = 1, KID_LARGE = 7, KID_SCAN_SUMS = 8, KID_SCAN_TILES = 9, KID_SCAN_ROWS = 10,
   KID_GATHER = 11, KID_GENE_EQC = 12, KID_GENE_EQC_BIG = 13, KID_BIN_GE = 14, KID_REGION = 15, KID_NA_OFFSETS = 16, KID_UNPACK24 = 17,
   KID_PUG_SMEM0 = 18, KID_PUG_REGION = 22, KID_PUG_BUILD0 = 23, KID_PUG_COVER2 = 27, KID_PUG_COVER4 = 28,
-  KID_PUG_COVER8 = 29, KID_PUG_COVERW = 30, KID_PUG_COUNT = 31, KID_COVER_REGION = 32, KID_PUG_BACK = 33, KID_BACK_REGION = 38, KID_EM_CELLS = 39, KID_EM_REGION = 44, NUM_KID = 45
+  KID_PUG_COVER8 = 29, KID_PUG_COVERW = 30, KID_PUG_COUNT = 31, KID_COVER_REGION = 32, KID_PUG_BACK = 33, KID_BACK_REGION = 38, KID_EM_CELLS = 39, KID_EM_REGION = 44, KID_PLAN = 45, NUM_KID = 46
 };
 static const char* const KID_NAMES[NUM_KID] = {
     "k_bin_cells", "k_resolve_smem<0>", "k_resolve_smem<1>", "k_resolve_smem<2>", "k_resolve_smem<3>",
@@ -51,7 +52,7 @@ static const char* const KID_NAMES[NUM_KID] = {
     "k_na_offsets(+tile sums)", "k_unpack24", "k_pug_smem<0>", "k_pug_smem<1>", "k_pug_smem<2>", "k_pug_smem<3>(global arena)", "pug_region(wall)",
     "k_pug_build<0>", "k_pug_build<1>", "k_pug_build<2>", "k_pug_build<3>(global arena)", "k_pug_cover2", "k_pug_cover_g<4>", "k_pug_cover_g<8>",
     "k_pug_cover_w", "k_pug_count", "cover_region(wall)", "k_pug_back<0>", "k_pug_back<1>", "k_pug_back<2>", "k_pug_back<3>(global arena)", "k_back_bin", "back_region(wall)",
-    "k_em_cells<0>", "k_em_cells<1>", "k_em_cells<2>", "k_em_cells<3>(global arena)", "k_em_bin", "em_region(wall)"};
+    "k_em_cells<0>", "k_em_cells<1>", "k_em_cells<2>", "k_em_cells<3>(global arena)", "k_em_bin", "em_region(wall)", "k_plan_arenas"};
 
 struct PipeBufs {  // device scratch owned by the caller (one set per stream-ordered pipeline)
   Ctl* ctl;
@@ -119,6 +120,68 @@ inline void enqueue_na8_offsets(L& l, const u8* na8, u64 n_records, u32* ref_off
   l.launch(KID_NA_OFFSETS, k_na_offsets, n_tiles, 1024u, (size_t)0, na8, n_records, (const u64*)na_tiles, ref_off);
 }
 
+// ---- per-CTA global arenas, planned on the device ----------------------------------------------------------------------------
+// The global-arena kernels (k_pug_build<3> / k_pug_smem<3>, k_pug_back<3> / k_em_cells<3>, k_gene_eqc) give every CTA an arena that
+// holds the largest cell of the batch on their list. Those maxima exist only on the device (k_bin_cells_ge): k_plan_arenas turns
+// them into a stride and the number of CTAs the pool has arenas for, in the control block, and the kernels read both there. With
+// l.sync_sizing() the host reads the block back first and sizes the pools exactly (device API, emulator); without, nothing is read
+// back — afq_submit returns while the previous batch is still computing — the pools keep the size learnt from earlier batches, a
+// pool that holds fewer arenas than the grid runs fewer CTAs, and one that holds none flags DEV_ERR_POOL (the host grows it and
+// runs the batch again).
+struct ArenaPlan { u64 ps3_words, back_words, ge_bytes[2]; };
+struct PlanArgs {
+  u32 em_split, ps_on;
+  u32 grid_ps3, grid_back, grid_ge[2];
+  u64 pool_ps3, pool_back;      // words
+  u64 pool_ge[2];               // bytes
+};
+__host__ __device__ inline ArenaPlan plan_arenas(const Ctl& h, u32 num_rows, bool usa, u32 lgt, bool em_split) {
+  ArenaPlan p;
+  p.ps3_words = ps_global_words(h.ps3_max_n, h.ps3_max_p, num_rows);
+  // tier 3 of the back end / of k_em_cells holds any cell of the batch (molecules <= records, label words <= alignments)
+  u64 gw = em_split ? ps_back_words_b(h.ge_max_n[1]) : ps_back_words(h.ge_max_n[1], h.ge_max_p[1], usa ? 3u : 1u);
+  if (em_split) {
+    const u64 ew = ec_need_words(h.ge_max_n[1], h.ge_max_p[1], ec_support_bound(h.ge_max_p[1], num_rows, usa), usa);
+    if (ew > gw) gw = ew;
+  }
+  p.back_words = (gw + 15) & ~3ull;
+  for (int w = 0; w < 2; ++w) p.ge_bytes[w] = align8(ge_carve(nullptr, h.ge_max_n[w], h.ge_max_p[w], lgt, nullptr)) + 64;
+  return p;
+}
+__host__ __device__ inline u32 plan_ge_grid(const Ctl& h, int which, u32 grid, bool ps_on) {
+  if (which == 1 && ps_on && grid > h.bin_count[GE_LIST_NORMAL] + 148u) grid = h.bin_count[GE_LIST_NORMAL] + 148u;   // hand-backs are rare
+  return grid;
+}
+__global__ void k_plan_arenas(KArgs a, GeArgs g, PlanArgs pa) {
+  if (blockIdx.x || threadIdx.x) return;
+  Ctl& h = *a.ctl;
+  const ArenaPlan p = plan_arenas(h, a.num_rows, a.usa_mode != 0, g.large_graph_thresh, pa.em_split != 0);
+  auto fit = [](u64 pool, u64 stride, u32 grid, u64 limit) -> u32 {
+    if (stride >= limit) return 0u;
+    const u64 n = pool / (stride ? stride : 1);
+    return (u32)(n < grid ? n : grid);
+  };
+  h.ps3_words = (u32)(p.ps3_words < 0xFFFFFFF0ull ? p.ps3_words : 0xFFFFFFF0ull);
+  h.ps3_blocks = fit(pa.pool_ps3, p.ps3_words, pa.grid_ps3, 0xFFFFFFF0ull);
+  h.back_words = (u32)(p.back_words < 0xFFFFFFF0ull ? p.back_words : 0xFFFFFFF0ull);
+  h.back_blocks = fit(pa.pool_back, p.back_words, pa.grid_back, 0xFFFFFFF0ull);
+  for (int w = 0; w < 2; ++w) {
+    h.ge_bytes[w] = p.ge_bytes[w];
+    h.ge_blocks[w] = fit(pa.pool_ge[w], p.ge_bytes[w], plan_ge_grid(h, w, pa.grid_ge[w], pa.ps_on != 0), ~0ull);
+  }
+  // A pool without a single arena for a kernel that may get work: flag the batch now and empty the work lists, so that no later
+  // kernel runs on half-built state (the tiny cells' cr-like rows are done; every other row stays empty: num_expr was zeroed).
+  u32 ps_total = 0;
+  for (int v = 0; v < PS_VARIANTS; ++v) ps_total += h.bin_count[PS_LIST0 + v];
+  const bool starved = (pa.grid_ps3 && h.bin_count[PS_LIST0 + 3] && !h.ps3_blocks) || (pa.grid_back && ps_total && !h.back_blocks) ||
+                       (h.bin_count[GE_LIST_BIG] && !h.ge_blocks[0]) || ((h.bin_count[GE_LIST_NORMAL] || (pa.ps_on && ps_total)) && !h.ge_blocks[1]);
+  if (starved) {
+    h.error |= (u32)DEV_ERR_POOL;
+    for (int v = 0; v < PS_VARIANTS; ++v) h.bin_count[PS_LIST0 + v] = 0;
+    h.bin_count[GE_LIST_BIG] = 0; h.bin_count[GE_LIST_NORMAL] = 0;
+  }
+}
+
 // Enqueue the whole pipeline for one batch. All batch/out pointers are device pointers.
 template <class L>
 int enqueue_batch(L& l, const afq_config& cfg, int force_bin, const PipeBufs& pb, const afq_batch& b,
@@ -168,6 +231,7 @@ int enqueue_batch(L& l, const afq_config& cfg, int force_bin, const PipeBufs& pb
       err = "--large-graph-thresh above 4096 is not supported on the CUDA path";
       return AFQ_ERR_UNSUPPORTED;
     }
+    if (l.memset_zero(o.num_expr, 4 * b.n_cells)) { err = "memset(num_expr) failed"; return AFQ_ERR_CUDA; }   // (see k_plan_arenas)
     GeArgs g{};
     g.ge_mode = res_is_pug(res) ? ((res == AFQ_RES_PARSIMONY_GENE || res == AFQ_RES_PARSIMONY_GENE_EM) ? GE_MODE_PUG_GENE : GE_MODE_PUG_TXP)
                                 : GE_MODE_CRLIKE;
@@ -193,8 +257,6 @@ int enqueue_batch(L& l, const afq_config& cfg, int force_bin, const PipeBufs& pb
     const u32 ps_mode = ps_on ? (1u | (g.ge_mode == GE_MODE_PUG_GENE ? 2u : 0u) | ((want_mol && !split) ? 4u : 0u) | (l.ps_grid(3) > 0 ? 8u : 0u) | (split ? 16u : 0u)) : 0u;
     l.launch(KID_BIN_GE, k_bin_cells_ge, bin_grid, 256u, (size_t)0, a, force_bin, GE_BIG_RECORDS, l.need_shift(), ps_mode);
     launch_crlike_bins(l, a, pb);
-    Ctl h{};
-    if (l.read_ctl(pb.ctl, &h)) { err = "reading the control block failed"; return AFQ_ERR_CUDA; }
     g.em_init_uniform = cfg.em_init_uniform ? 1u : 0u;
     g.pug_exact_umi = cfg.pug_exact_umi ? 1u : 0u;
     g.umi_len = cfg.umi_len;
@@ -204,6 +266,42 @@ int enqueue_batch(L& l, const afq_config& cfg, int force_bin, const PipeBufs& pb
     g.adj_pool = l.adj_pool(g.adj_cap);
     g.adj_used = (u64*)&pb.ctl->adj_used;
     if (!g.adj_pool) { err = "adjacency pool allocation failed"; return AFQ_ERR_CUDA; }
+    // ---- the global arenas (see k_plan_arenas) ----
+    const bool sync = l.sync_sizing();
+    const bool usa = cfg.usa_mode != 0;
+    const bool em_split = split && want_mol && l.em_split();
+    const u32 all_cells = (u32)b.n_cells;
+    Ctl h{};
+    PlanArgs pa{};
+    pa.em_split = em_split ? 1u : 0u; pa.ps_on = ps_on ? 1u : 0u;
+    pa.grid_ps3 = ps_on ? (u32)l.ps_grid(3) : 0u;
+    pa.grid_back = (split && want_mol) ? (u32)(l.pc_grid(5, 0) > l.pc_grid(9, 0) ? l.pc_grid(5, 0) : l.pc_grid(9, 0)) : 0u;
+    pa.grid_ge[0] = (u32)l.ge_blocks(0); pa.grid_ge[1] = (u32)l.ge_blocks(1);
+    u64 want_ps3 = 0, want_back = 0, want_ge[2] = {0, 0};     // (0: whatever the launcher has learnt)
+    if (sync) {
+      if (l.read_ctl(pb.ctl, &h)) { err = "reading the control block failed"; return AFQ_ERR_CUDA; }
+      const ArenaPlan p = plan_arenas(h, cfg.num_rows, usa, g.large_graph_thresh, em_split);
+      if (p.ps3_words >= 0xFFFFFFF0ull || p.back_words >= 0xFFFFFFF0ull) { err = "a cell needs a global arena of more than 2^32 words"; return AFQ_ERR_UNSUPPORTED; }
+      const u32 c3 = h.bin_count[PS_LIST0 + 3];
+      want_ps3 = p.ps3_words * (c3 < pa.grid_ps3 ? c3 : pa.grid_ps3) + 16;
+      want_back = p.back_words * pa.grid_back + 16;
+      for (int w = 0; w < 2; ++w) {
+        const u32 cells = h.bin_count[w == 0 ? GE_LIST_BIG : GE_LIST_NORMAL] + (w == 1 && ps_on ? all_cells : 0u);   // every k_pug_smem cell may come back
+        u32 blocks = plan_ge_grid(h, w, pa.grid_ge[w], ps_on);
+        if (blocks > cells) blocks = cells;
+        want_ge[w] = p.ge_bytes[w] * blocks + 64;
+      }
+    }
+    if (pa.grid_ps3) { g.ps_garena = l.ps_garena(want_ps3, &pa.pool_ps3); if (!g.ps_garena) { err = "k_pug_smem global arena allocation failed"; return AFQ_ERR_CUDA; } }
+    if (pa.grid_back) { g.back_garena = l.back_garena(want_back, &pa.pool_back); if (!g.back_garena) { err = "k_pug_back global arena allocation failed"; return AFQ_ERR_CUDA; } }
+    u8* ge_pool[2];
+    for (int w = 0; w < 2; ++w) {
+      ge_pool[w] = l.ge_arena(w, want_ge[w], &pa.pool_ge[w]);
+      if (!ge_pool[w]) { err = "gene-eq-class arena allocation failed (" + std::to_string(want_ge[w]) + " B)"; return AFQ_ERR_CUDA; }
+    }
+    l.launch(KID_PLAN, k_plan_arenas, 1u, 32u, (size_t)0, a, g, pa);
+    // without the read-back the list sizes are unknown here: every kernel gets its full grid and finds its list on the device
+    auto list_cells = [&](int list) { return sync ? h.bin_count[list] : all_cells; };
     // the arena variants of k_pug_smem are independent of each other (cells they cannot finish go to k_gene_eqc's
     // list, drained afterwards): forked onto lanes like the cr-like arenas so that every persistent kernel's tail
     // overlaps the others instead of idling the chip (14.5 + 7.3 + 10.3 + 5.5 ms back to back)
@@ -220,18 +318,14 @@ int enqueue_batch(L& l, const afq_config& cfg, int force_bin, const PipeBufs& pb
     }
     l.region_begin();
     l.fork(PS_VARIANTS);
-    for (int v = PS_VARIANTS - 1; v >= 0; --v) {   // biggest cells first
-      const u32 cnt = h.bin_count[PS_LIST0 + v];
-      if (!cnt) continue;
-      ps_cells += cnt;
+    for (int v = PS_VARIANTS - 1; ps_on && v >= 0; --v) {   // biggest cells first
+      const u32 cnt = list_cells(PS_LIST0 + v);
       u32 blocks = (u32)l.ps_grid(v);
+      if (!cnt || !blocks) continue;
+      ps_cells = sync ? ps_cells + cnt : all_cells;
       if (blocks > cnt) blocks = cnt;
       l.lane(v);
       if (v == 3) {
-        const u64 words = ps_global_words(h.ps3_max_n, h.ps3_max_p, cfg.num_rows);   // (< 2^32: P < 2^30 on this list)
-        g.ps_garena = l.ps_garena(words, blocks);
-        g.ps_garena_words = (u32)words;
-        if (!g.ps_garena) { l.join(); err = "k_pug_smem global arena allocation failed"; return AFQ_ERR_CUDA; }
         if (split) l.launch(KID_PUG_BUILD0 + 3, k_pug_build<3>, blocks, ps_threads(3), (size_t)0, a, g);
         else l.launch(KID_PUG_SMEM0 + 3, k_pug_smem<3>, blocks, ps_threads(3), (size_t)0, a, g);
         continue;
@@ -271,26 +365,14 @@ int enqueue_batch(L& l, const afq_config& cfg, int force_bin, const PipeBufs& pb
         // Stage B (molecules -> gene eq-classes, canonical order) in k_pug_back, stage C (counts / EM) in k_em_cells; the
         // classes travel through the dump regions (the caller's when --dump-eqclasses is on, internal ones otherwise).
         // AFQ_NO_EM_SPLIT=1: k_pug_back runs ge_back's own stage C instead (A/B).
-        const bool em_split = l.em_split();
         if (em_split && !dump) {
           ClsBufs cb{};
           if (!l.cls_bufs(b.n_records, b.n_refs_total, b.n_cells, &cb)) { err = "class region allocation failed"; return AFQ_ERR_CUDA; }
           g.dump_ncls = cb.ncls; g.dump_nlab = cb.nlab; g.dump_cnt = cb.cnt; g.dump_off = cb.off; g.dump_lab = cb.lab;
         }
         g.classes_only = em_split ? 1u : 0u;
-        // tier 3's per-CTA global arenas hold any cell of the batch (molecules <= records, label words <= alignments)
-        const bool usa = cfg.usa_mode != 0;
-        u64 gw = em_split ? ps_back_words_b(h.ge_max_n[1]) : ps_back_words(h.ge_max_n[1], h.ge_max_p[1], usa ? 3u : 1u);
-        if (em_split) {
-          const u64 ew = ec_need_words(h.ge_max_n[1], h.ge_max_p[1], ec_support_bound(h.ge_max_p[1], cfg.num_rows, usa), usa);
-          if (ew > gw) gw = ew;
-        }
-        gw = (gw + 15) & ~3ull;
         const unsigned g3 = (unsigned)l.pc_grid(5, 0);
-        g.back_garena = gw < 0xFFFFFFF0ull ? l.back_garena(gw, g3) : nullptr;
-        g.back_garena_words = (u32)gw;
         g.back_max_tier = l.back_max_tier();
-        if (!g.back_garena) { err = "k_pug_back global arena allocation failed"; return AFQ_ERR_CUDA; }
         l.launch(KID_PUG_BACK + 4, k_back_bin, (unsigned)((ps_cells + 255) / 256), 256u, (size_t)0, a, g);
         l.region_begin();
         l.fork(PB_TIERS);
@@ -317,16 +399,13 @@ int enqueue_batch(L& l, const afq_config& cfg, int force_bin, const PipeBufs& pb
     }
     for (int which = 0; which < 2; ++which) {
       const int list = which == 0 ? GE_LIST_BIG : GE_LIST_NORMAL;
-      const u32 cells = h.bin_count[list] + (which == 1 ? ps_cells : 0u);   // upper bound: every k_pug_smem cell may come back
+      const u32 cells = sync ? h.bin_count[list] + (which == 1 ? ps_cells : 0u) : all_cells;   // upper bound: every k_pug_smem cell may come back
       if (cells == 0) continue;
-      const u64 bytes = align8(ge_carve(nullptr, h.ge_max_n[which], h.ge_max_p[which], g.large_graph_thresh, nullptr)) + 64;
-      u32 blocks = (u32)l.ge_blocks(which);
+      u32 blocks = plan_ge_grid(h, which, pa.grid_ge[which], sync && ps_on);
       if (blocks > cells) blocks = cells;
-      if (which == 1 && ps_cells && blocks > h.bin_count[list] + 148u) blocks = h.bin_count[list] + 148u;   // hand-backs are rare
-      g.arena = l.ge_arena(which, bytes, blocks);
-      if (!g.arena) { err = "gene-eq-class arena allocation failed (" + std::to_string(bytes) + " B x " + std::to_string(blocks) + ")"; return AFQ_ERR_CUDA; }
-      g.arena_bytes = bytes;
+      g.arena = ge_pool[which];
       g.list_id = (u32)list;
+      g.list_which = (u32)which;
       l.launch(which == 0 ? KID_GENE_EQC_BIG : KID_GENE_EQC, k_gene_eqc, blocks, GE_THREADS, (size_t)0, a, g);
     }
   }
@@ -340,6 +419,7 @@ int enqueue_batch(L& l, const afq_config& cfg, int force_bin, const PipeBufs& pb
 
 inline const char* device_error_string(const Ctl& h, std::string& buf) {
   if (h.error & DEV_ERR_CELL_TOO_LARGE) buf = "a cell has " + std::to_string(h.max_cell_refs) + " alignments, more than the giant-cell arena holds (the host API grows the arena and retries; with afq_quant_device raise AFQ_LARGE_CAP_LOG2)";
+  else if (h.error & DEV_ERR_POOL) buf = "the pool of a global-arena kernel holds no arena for this batch's largest cell (the host API grows the pool and retries)";
   else if (h.error & DEV_ERR_ADJ_POOL) buf = "PUG adjacency pool exhausted";
   else if (h.error & DEV_ERR_ARENA) buf = "a cell does not fit the gene-eq-class arena";
   else if (h.error & DEV_ERR_HASH) buf = "eq-class label hash collision not resolved after reseeding";

@@ -49,15 +49,14 @@ struct GeArgs {
   u32 num_alphas;       // G (gene mode) or 3G (USA)
   // per-CTA arenas
   u8* arena;
-  u64 arena_bytes;      // per CTA
   // adjacency pool (bump-allocated per cell, reset per batch)
   u32* adj_pool;
   u64 adj_cap;
   u64* adj_used;        // in Ctl-adjacent memory
   // which work list this launch consumes
   u32 list_id;
-  u32* ps_garena;       // k_pug_smem<3>: per-CTA global-memory arenas of ps_garena_words words
-  u32 ps_garena_words;
+  u32 list_which;       // 0: big list, 1: normal list (index of the arena plan in Ctl)
+  u32* ps_garena;       // k_pug_smem<3> / k_pug_build<3>: pool of per-CTA global-memory arenas (Ctl::ps3_words words each)
   u32 ps_limit_words;   // k_pug_smem: use at most this many arena words (0 = the variant's size; tests force fallbacks with it)
   // split path (k_pug_build -> k_pug_cover* -> k_pug_count, afq_pugc.cuh): per-batch global buffers
   u32* ps_win;          // [n_records]   winners (output slots) of cell c at [r0, r0 + ps_nwin[c])
@@ -72,8 +71,7 @@ struct GeArgs {
   u32* ps_moff;         // [n_records]    per molecule (cell region from r0 on): label offset inside the cell ...
   u32* ps_mlen;         // [n_records]    ... and length; ps_nwin[c] = molecules of the cell
   u32* back_list;       // [4 * n_cells]  the cells of k_pug_back's four arena tiers (k_back_bin)
-  u32* back_garena;     // per-CTA global arenas of tier 3
-  u32 back_garena_words;
+  u32* back_garena;     // pool of the per-CTA global arenas of tier 3 (Ctl::back_words words each)
   u32 back_max_tier;    // largest shared-memory tier k_back_bin may choose (0..2)
   u32 classes_only;     // ge_back stops behind stage B (classes written to the dump regions): k_em_cells does stage C
   // --dump-eqclasses (src/quant.rs:1282-1307): every cell's gene eq-classes in canonical order. Cell c (records
@@ -820,7 +818,7 @@ __device__ inline void gene_eqc_cell(const KArgs& a, const GeArgs& g, u32 cell, 
   if (threadIdx.x == 0) {
     sh->need_lo = 0;
     const u64 need = ge_carve(arena, n, P, g.large_graph_thresh, s_ptrs);
-    sh->need_lo = need > g.arena_bytes ? 1u : 0u;
+    sh->need_lo = need > a.ctl->ge_bytes[g.list_which] ? 1u : 0u;
     sh->n_mol = 0; sh->lab_bump = 0; sh->alt = 0; sh->flag = 0;
     sh->cnt0 = sh->cnt1 = sh->cnt2 = sh->cnt3 = 0;
   }
@@ -1489,8 +1487,9 @@ __global__ void __launch_bounds__(GE_THREADS, AFQ_GE_MIN_BLOCKS) k_gene_eqc(KArg
   __shared__ __align__(16) u8 s_scratch[GE_SCRATCH_BYTES];
   __shared__ GePtrs s_ptrs;
   __shared__ u32 s_cls[2 * GE_CLS_CACHE];
-  u8* arena = g.arena + (u64)blockIdx.x * g.arena_bytes;
   const u32 count = a.ctl->bin_count[g.list_id];
+  if (arena_cta_idle(a.ctl, a.ctl->ge_blocks[g.list_which], count)) return;
+  u8* arena = g.arena + (u64)blockIdx.x * a.ctl->ge_bytes[g.list_which];
   const u32* list = a.bin_list + (u64)g.list_id * a.n_cells;
   for (;;) {
     if (threadIdx.x == 0) sh.job = atomicAdd(&a.ctl->bin_cursor[g.list_id], 1u);

@@ -492,8 +492,10 @@ __global__ void __launch_bounds__(256) k_back_bin(KArgs a, GeArgs g) {
 template <int TIER>
 __global__ void __launch_bounds__(PB_THREADS) k_pug_back(KArgs a, GeArgs g) {
   AFQ_DYN_SMEM(smem_raw);
-  u32* A = TIER < 3 ? reinterpret_cast<u32*>(smem_raw) : g.back_garena + (u64)blockIdx.x * g.back_garena_words;
-  const u32 AW = TIER < 3 ? pb_arena_words(TIER) : g.back_garena_words;
+  if (TIER == 3 && arena_cta_idle(a.ctl, a.ctl->back_blocks, a.ctl->back_count[3])) return;
+  const u32 gwords = TIER < 3 ? 0u : a.ctl->back_words;
+  u32* A = TIER < 3 ? reinterpret_cast<u32*>(smem_raw) : g.back_garena + (u64)blockIdx.x * gwords;
+  const u32 AW = TIER < 3 ? pb_arena_words(TIER) : gwords;
   __shared__ GeShared sh;
   __shared__ GePtrs s_ptrs;
   __shared__ u32 s_job;

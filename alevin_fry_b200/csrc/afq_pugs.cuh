@@ -1266,8 +1266,10 @@ constexpr int PS_LIST0 = NUM_BINS + 3;      // bin_list rows of the three arena 
 template <int VAR>
 __global__ void __launch_bounds__(ps_threads(VAR), ps_min_blocks(VAR)) k_pug_smem(KArgs a, GeArgs g) {
   AFQ_DYN_SMEM(smem_raw);
-  u32* A = VAR < PS_SMEM_VARIANTS ? reinterpret_cast<u32*>(smem_raw) : g.ps_garena + (u64)blockIdx.x * g.ps_garena_words;
-  const u32 AWmax = VAR < PS_SMEM_VARIANTS ? ps_arena_words(VAR) : g.ps_garena_words;
+  if (VAR >= PS_SMEM_VARIANTS && arena_cta_idle(a.ctl, a.ctl->ps3_blocks, a.ctl->bin_count[PS_LIST0 + VAR])) return;
+  const u32 gwords = VAR < PS_SMEM_VARIANTS ? 0u : a.ctl->ps3_words;
+  u32* A = VAR < PS_SMEM_VARIANTS ? reinterpret_cast<u32*>(smem_raw) : g.ps_garena + (u64)blockIdx.x * gwords;
+  const u32 AWmax = VAR < PS_SMEM_VARIANTS ? ps_arena_words(VAR) : gwords;
   __shared__ GeShared sh;
   __shared__ PsExtra ex;
   __shared__ GePtrs s_ptrs;
@@ -1309,8 +1311,10 @@ __host__ __device__ constexpr u32 ps_build_min_blocks(int v) { return v == 0 ? (
 template <int VAR>
 __global__ void __launch_bounds__(ps_threads(VAR), ps_build_min_blocks(VAR)) k_pug_build(KArgs a, GeArgs g) {
   AFQ_DYN_SMEM(smem_raw);
-  u32* A = VAR < PS_SMEM_VARIANTS ? reinterpret_cast<u32*>(smem_raw) : g.ps_garena + (u64)blockIdx.x * g.ps_garena_words;
-  const u32 AWmax = VAR < PS_SMEM_VARIANTS ? ps_arena_words(VAR) : g.ps_garena_words;
+  if (VAR >= PS_SMEM_VARIANTS && arena_cta_idle(a.ctl, a.ctl->ps3_blocks, a.ctl->bin_count[PS_LIST0 + VAR])) return;
+  const u32 gwords = VAR < PS_SMEM_VARIANTS ? 0u : a.ctl->ps3_words;
+  u32* A = VAR < PS_SMEM_VARIANTS ? reinterpret_cast<u32*>(smem_raw) : g.ps_garena + (u64)blockIdx.x * gwords;
+  const u32 AWmax = VAR < PS_SMEM_VARIANTS ? ps_arena_words(VAR) : gwords;
   __shared__ GeShared sh;
   __shared__ PsExtra ex;
   if (threadIdx.x == 0) {

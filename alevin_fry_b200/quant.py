@@ -328,6 +328,11 @@ class Quantifier:
     def launch_count(self) -> int:
         return int(self._lib.afq_launch_count(self._ctx))
 
+    @property
+    def rerun_count(self) -> int:
+        """batches that afq_wait ran again after growing a device arena"""
+        return int(self._lib.afq_rerun_count(self._ctx))
+
     def set_profiling(self, on: bool):
         self._check(self._lib.afq_set_profiling(self._ctx, int(on)))
 

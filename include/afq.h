@@ -204,6 +204,9 @@ int afq_infer(afq_ctx* ctx, const afq_eqc_table* classes, uint64_t n_cells, cons
  * stream (afq_set_profiling(1) -> run -> afq_profile_collect -> afq_profile_get(i)).    */
 int afq_abi_version(void);
 uint64_t afq_launch_count(const afq_ctx* ctx);
+/* batches afq_wait ran a second time after growing a device arena (a giant cell, or the arena pools of the parsimony / EM
+ * kernels, which afq_submit sizes from the batches seen so far instead of reading the device back) */
+uint64_t afq_rerun_count(const afq_ctx* ctx);
 int afq_set_profiling(afq_ctx* ctx, int enable);
 int afq_profile_collect(afq_ctx* ctx);
 int afq_profile_reset(afq_ctx* ctx);

@@ -32,11 +32,20 @@ struct EmuLauncher {
     cuda_emu::launch(k, grid, block, smem, args...);
   }
   int memset_zero(void* p, size_t n) { memset(p, 0, n); return 0; }
+  // AFQ_EMU_ASYNC=1: the afq_submit form of the pipeline — no read-back, fixed pools of AFQ_EMU_POOL_WORDS words
+  bool sync_sizing() { const char* s = getenv("AFQ_EMU_ASYNC"); return !(s && atoi(s)); }
+  u64 pool_words(u64 min_words) {
+    if (sync_sizing()) return min_words;
+    const char* s = getenv("AFQ_EMU_POOL_WORDS");
+    const u64 fixed = s ? (u64)atoll(s) : (4ull << 20);
+    return fixed > min_words ? fixed : min_words;
+  }
   int read_ctl(const Ctl* d, Ctl* h) { *h = *d; return 0; }
   int grid_for_bin(int) { return 1; }
   int ge_blocks(int) { return 2; }
-  u8* ge_arena(int which, u64 bytes, u32 blocks) {
-    arena[which].assign((size_t)bytes * blocks + 64, 0xCD);
+  u8* ge_arena(int which, u64 min_bytes, u64* cap) {
+    *cap = 4 * pool_words((min_bytes + 3) / 4);
+    arena[which].assign((size_t)*cap + 64, 0xCD);
     return arena[which].data();
   }
   u32* adj_pool(u64 n) { adj.assign((size_t)n, 0xCDCDCDCDu); return adj.data(); }
@@ -46,7 +55,7 @@ struct EmuLauncher {
   void region_begin() {}
   void region_end(int) {}
   u32 need_shift() { const char* s = getenv("AFQ_NEED_SHIFT"); return s ? (u32)atoi(s) : 0; }
-  u32* ps_garena(u64 words, u32 blocks) { garena.assign((size_t)words * blocks + 16, 0xCDCDCDCDu); return garena.data(); }
+  u32* ps_garena(u64 min_words, u64* cap) { *cap = pool_words(min_words); garena.assign((size_t)*cap + 16, 0xCDCDCDCDu); return garena.data(); }
   u32 ps_limit_words() { const char* s = getenv("AFQ_PS_LIMIT_WORDS"); return s ? (u32)atoi(s) : 0; }
   bool ps_split(u64 n_records, u64 n_refs, u64 n_cells, bool gene_labels, bool molecules, PsSplitBufs* o) {
     const char* s = getenv("AFQ_NO_PS_SPLIT");
@@ -71,7 +80,7 @@ struct EmuLauncher {
     return true;
   }
   u32 back_max_tier() { const char* s = getenv("AFQ_BACK_MAX_TIER"); return s ? (u32)atoi(s) : 0u; }
-  u32* back_garena(u64 words, u32 blocks) { sp_bga.assign((size_t)words * blocks + 16, 0xCDCDCDCDu); return sp_bga.data(); }
+  u32* back_garena(u64 min_words, u64* cap) { *cap = pool_words(min_words); sp_bga.assign((size_t)*cap + 16, 0xCDCDCDCDu); return sp_bga.data(); }
   int ps_grid(int v) {
     const char* s = getenv("AFQ_NO_PS");
     if (s && atoi(s)) return 0;

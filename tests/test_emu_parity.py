@@ -302,6 +302,23 @@ def test_emu_pug_global_arena_variant(res, monkeypatch):
     assert cnt[emu_lib.LIST_GE_NORMAL] == 0, cnt
 
 
+@pytest.mark.parametrize("res", ["parsimony", "parsimony-em", "cr-like-em"])
+def test_emu_arena_pools_planned_on_the_device(res, monkeypatch):
+    # the afq_submit form of the pipeline: the control block is not read back after the binning, the global-arena kernels
+    # take their stride and the CTAs that have an arena from k_plan_arenas' plan in the control block, on fixed pools
+    spec = synth.SynthSpec(fixed_reads=10000, n_genes=3000)
+    b = synth.generate(spec, 0, 2)
+    monkeypatch.setenv("AFQ_EMU_ASYNC", "1")
+    check(opts_for(spec, res), synth.tid_to_gid(spec), b, res)            # roomy pools: both CTAs of a grid have an arena
+    monkeypatch.setenv("AFQ_PS_LIMIT_WORDS", "3000")                        # ... and with cells handed back to k_gene_eqc
+    check(opts_for(spec, res), synth.tid_to_gid(spec), b.slice_cells(0, 1), res)
+    monkeypatch.delenv("AFQ_PS_LIMIT_WORDS")
+    # a pool that holds no arena for the largest cell: the batch is flagged, never silently wrong (the host API re-runs it)
+    monkeypatch.setenv("AFQ_EMU_POOL_WORDS", "2000")
+    with pytest.raises(RuntimeError, match="pool of a global-arena kernel"):
+        emu_lib.emu_quant(opts_for(spec, res), synth.tid_to_gid(spec), b)
+
+
 @pytest.mark.parametrize("res", ["parsimony", "parsimony-em"])
 def test_emu_pug_smem_long_labels_take_the_warp_cover(res):
     # labels of more than 32 transcripts do not fit the group cover's position masks: such components

@@ -347,6 +347,34 @@ def test_pug_global_arena_variant_big_cells(res):
     assert_same(got, oracle_lib.oracle_quant(o, t2g, b), exact=not res.endswith("-em"), ctx=res)
 
 
+@pytest.mark.parametrize("res", ["parsimony", "parsimony-em", "cr-like-em"])
+def test_arena_pools_are_planned_on_the_device_and_grow_on_demand(res, monkeypatch):
+    # afq_submit does not read the control block back after the binning (it would wait for the previous batch's kernels): the
+    # global-arena kernels take stride and CTA count from k_plan_arenas' plan, on pools sized from the batches seen so far.
+    # 1 MB pools hold no arena for 30k-read cells: the batch is flagged, afq_wait grows the pools and runs it again.
+    monkeypatch.setenv("AFQ_POOL_MB", "1")
+    spec = synth.SynthSpec(fixed_reads=30000, n_genes=3000)
+    b = synth.generate(spec, 0, 6)
+    t2g = synth.tid_to_gid(spec)
+    o = opts_for(spec, res)
+    want = oracle_lib.oracle_quant(o, t2g, b)
+    with Quantifier(o, t2g) as q:
+        t1, t2 = q.submit(b), q.submit(b.slice_cells(0, 3))     # both in flight on the small pools
+        r1, r2 = q.wait(t1), q.wait(t2)
+        n_rerun = q.rerun_count
+        r3 = q.quantify_batch(b)                                 # the grown pools stay
+        assert n_rerun >= 1 and q.rerun_count == n_rerun, (n_rerun, q.rerun_count)
+    exact = not res.endswith("-em")
+    assert_same(r1, want, exact=exact, ctx=res + "/rerun")
+    assert_same(r3, want, exact=exact, ctx=res + "/learnt")
+    assert np.array_equal(r2.col, want.col[:int(want.row_ptr[3])])
+    # the round-1 form (read-back + exact sizing, what afq_quant_device still does) gives the same
+    monkeypatch.setenv("AFQ_SYNC_SIZING", "1")
+    with Quantifier(o, t2g) as q:
+        assert_same(q.quantify_batch(b), want, exact=exact, ctx=res + "/sync")
+        assert q.rerun_count == 0
+
+
 def test_pug_split_path_giant_cell_counts_in_global_scratch():
     # a cell with more molecules than k_pug_count's shared-memory counters hold (PC_MAX_WINNERS = 16384): its per-slot
     # counters live in the cell's (dead) member-pool region; must still take the split path and match the oracle
