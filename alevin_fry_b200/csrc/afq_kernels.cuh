@@ -142,6 +142,9 @@ __global__ void k_bin_cells(KArgs a, int force_bin, u32 need_shift) {
 //    reconverge every iteration (ncu r1c: 7.5 active lanes/instruction without it). Fully
 //    lock-stepped (vote-driven) probe loops were measured and are slower (r1e: +70 % warp
 //    instructions from the votes and predication), so the probe loops stay plainly divergent.
+//  * A lane-per-RECORD phase 1 (scan the record's refs, one insert for the ~85 % single-gene records, the refs of the
+//    multi-gene ones queued for a flat second pass) was measured in round 2 and is slower than the flat form: C2 8.91 vs
+//    8.18 ms (scripts/gpu_round2x.sh) — the per-record ref loads are uncoalesced and the scan loop diverges.
 // ------------------------------------------------------------------------------------
 __host__ __device__ constexpr u32 bin_buckets_log2(int b) { return b == 0 ? 7 : (b == 1 ? 8 : (b == 2 ? 9 : 10)); }
 __host__ __device__ constexpr bool bin_has_list(int b) { return b <= 3; }

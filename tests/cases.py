@@ -77,3 +77,39 @@ def random_pug_cells(rng, n_cells, n_tx, umi_bits, n_labels, max_label, recs_lo,
         rng.shuffle(recs)
         cells.append(recs[:n])
     return cells
+
+
+def record_shape_cells(rng):
+    """cr-like phase 1 (afq_kernels.cuh), the record shapes its two forms must agree on: cells dense in multi-gene records, a
+    record of 300 alignments, records that repeat a gene out of order (unsorted refs), alignment-free records.
+    3 transcripts per gene; returns (n_genes, tid_to_gid, cells)."""
+    import numpy as np
+    n_genes = 400
+    t2g = np.repeat(np.arange(n_genes, dtype=np.uint32), 3)
+    cells = []
+    # 200 records of three different genes each
+    c = []
+    for i in range(200):
+        gs = rng.choice(n_genes, 3, replace=False)
+        c.append((int(rng.integers(0, 60)), sorted(int(3 * g + rng.integers(0, 3)) for g in gs)))
+    cells.append(c)
+    # one very long multi-gene record among single-alignment ones
+    c = [(int(rng.integers(0, 50)), [int(rng.integers(0, 3 * n_genes))]) for _ in range(220)]
+    c.insert(17, (7, sorted(int(x) for x in rng.choice(3 * n_genes, 300, replace=False))))
+    cells.append(c)
+    # genes repeated out of order inside a record (unsorted refs), duplicates of whole records, records without alignments
+    c = []
+    for i in range(300):
+        g1, g2 = (int(x) for x in rng.choice(n_genes, 2, replace=False))
+        kind = i % 4
+        refs = [3 * g1, 3 * g2, 3 * g1 + 1] if kind == 0 else ([3 * g2 + 2, 3 * g1] if kind == 1 else ([] if kind == 2 else [3 * g1 + 2, 3 * g1]))
+        c.append((int(rng.integers(0, 40)), refs))
+    cells.append(c)
+    # a mid-size cell (a larger arena): every fourth record multi-gene
+    c = []
+    for i in range(3000):
+        g1 = int(rng.integers(0, n_genes))
+        refs = [3 * g1] if i % 4 else sorted([3 * g1, 3 * ((g1 + 1 + int(rng.integers(0, 5))) % n_genes) + 1])
+        c.append((int(rng.integers(0, 700)), refs))
+    cells.append(c)
+    return n_genes, t2g, cells

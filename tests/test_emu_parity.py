@@ -302,6 +302,13 @@ def test_emu_pug_global_arena_variant(res, monkeypatch):
     assert cnt[emu_lib.LIST_GE_NORMAL] == 0, cnt
 
 
+@pytest.mark.parametrize("res", ["cr-like", "trivial"])
+def test_emu_crlike_record_shapes(res):
+    n_genes, t2g, cells = cases.record_shape_cells(np.random.default_rng(5))
+    b = CellBatch.from_cells(cells)
+    check(QuantOpts(resolution=res, num_gene_ids=n_genes, num_rows=n_genes, umi_len=12), t2g, b, res)
+
+
 @pytest.mark.parametrize("res", ["parsimony", "parsimony-em", "cr-like-em"])
 def test_emu_arena_pools_planned_on_the_device(res, monkeypatch):
     # the afq_submit form of the pipeline: the control block is not read back after the binning, the global-arena kernels

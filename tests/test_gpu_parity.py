@@ -140,6 +140,15 @@ def test_forced_large_arena_matches(monkeypatch, force_bin):
         assert_same(gpu_quant(o, t2g, b), oracle_lib.oracle_quant(o, t2g, b), ctx=f"{res}/bin{force_bin}")
 
 
+@pytest.mark.parametrize("res", ["cr-like", "trivial"])
+def test_crlike_record_shapes(res):
+    # phase 1 of the cr-like kernels: multi-gene-dense cells, a record of 300 alignments, unsorted refs, empty records
+    n_genes, t2g, cells = cases.record_shape_cells(np.random.default_rng(5))
+    b = CellBatch.from_cells(cells)
+    o = QuantOpts(resolution=res, num_gene_ids=n_genes, num_rows=n_genes, umi_len=12)
+    assert_same(gpu_quant(o, t2g, b), oracle_lib.oracle_quant(o, t2g, b), ctx=res)
+
+
 def test_giant_cell_arena_grows_on_demand(monkeypatch):
     # VERDICT r1 missing #6: a cell beyond the giant-cell arena used to fail with AFQ_ERR_UNSUPPORTED unless an env var was
     # raised. Tiny arenas (2^12 entries) + every cell forced onto them: afq_wait grows the arenas and re-runs the batch.
