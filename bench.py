@@ -244,22 +244,57 @@ def measure_config(args, name, cells, res, ctx):
     class batch:  # whole-workload sizes
         n_cells, n_records, n_refs_total = cells, rbase, fbase
     nc = batch.n_cells
-    do = dict(row_ptr=torch.empty(nc + 1, dtype=torch.int64, device=dev),
-              col=torch.empty(batch.n_refs_total, dtype=torch.int32, device=dev),
-              val=torch.empty(batch.n_refs_total, dtype=torch.float32, device=dev),
-              sum_umi=torch.empty(nc, dtype=torch.float32, device=dev), max_umi=torch.empty(nc, dtype=torch.float32, device=dev),
-              num_expr=torch.empty(nc, dtype=torch.int32, device=dev), num_over_mean=torch.empty(nc, dtype=torch.int32, device=dev),
-              flags=torch.empty(nc, dtype=torch.uint8, device=dev))
-    asm_scratch = {}
-    stream = torch.cuda.current_stream().cuda_stream
+
+    def out_set():
+        return dict(row_ptr=torch.empty(nc + 1, dtype=torch.int64, device=dev),
+                    col=torch.empty(batch.n_refs_total, dtype=torch.int32, device=dev),
+                    val=torch.empty(batch.n_refs_total, dtype=torch.float32, device=dev),
+                    sum_umi=torch.empty(nc, dtype=torch.float32, device=dev), max_umi=torch.empty(nc, dtype=torch.float32, device=dev),
+                    num_expr=torch.empty(nc, dtype=torch.int32, device=dev), num_over_mean=torch.empty(nc, dtype=torch.int32, device=dev),
+                    flags=torch.empty(nc, dtype=torch.uint8, device=dev))
+    # N > 1: two output sets, so that the NCCL assembly of step i's matrix (on its own stream) overlaps step i+1's kernels
+    outs = [out_set() for _ in range(2 if world > 1 else 1)]
+    do = outs[0]
+    asm_scratch = [{} for _ in outs]
+    main = torch.cuda.current_stream()
+    stream = main.cuda_stream
+    comm = torch.cuda.Stream() if world > 1 else None
+    ev_done = [torch.cuda.Event() for _ in outs]       # step's kernels finished (main stream)
+    ev_asm = [None for _ in outs]                      # step's matrix assembled (comm stream)
+    pending = []                                       # output sets whose assembly has not been issued yet
+
+    def assemble(j):
+        # assembly of the ONE sparse matrix of the job (north_star: "an NCCL all-gather only for the final sparse matrix
+        # assembly"): row lengths + the (col, val) payload of every rank, gathered over NVLink onto every rank
+        from alevin_fry_b200 import shard
+        with torch.cuda.stream(comm):
+            comm.wait_event(ev_done[j])
+            shard.assemble_csr(outs[j]["num_expr"], outs[j]["col"], outs[j]["val"], nc * world, scratch=asm_scratch[j], compact=False)
+            ev_asm[j] = torch.cuda.Event()
+            ev_asm[j].record(comm)
+
+    step_no = [0]
 
     def step_device():
-        q.quant_device(db, do, stream)
+        j = step_no[0] % len(outs)
+        step_no[0] += 1
+        if ev_asm[j] is not None:
+            main.wait_event(ev_asm[j])                 # the set is free once its previous matrix has been gathered
+        q.quant_device(db, outs[j], stream)
         if world > 1:
-            # assembly of the ONE sparse matrix of the job (north_star: "an NCCL all-gather only for the final sparse matrix
-            # assembly"): row lengths + the (col, val) payload of every rank, gathered over NVLink onto every rank
-            from alevin_fry_b200 import shard
-            shard.assemble_csr(do["num_expr"], do["col"], do["val"], nc * world, scratch=asm_scratch, compact=False)
+            ev_done[j].record(main)
+            # the previous step's assembly is issued AFTER this step's kernels are queued: its host-side waits (row lengths,
+            # nnz) then overlap this step's compute, and so do its all-gathers
+            while pending:
+                assemble(pending.pop(0))
+            pending.append(j)
+
+    def drain_device():
+        while pending:
+            assemble(pending.pop(0))
+        for e in ev_asm:
+            if e is not None:
+                main.wait_event(e)
 
     def barrier():
         if world > 1:
@@ -269,7 +304,8 @@ def measure_config(args, name, cells, res, ctx):
     # ---- device-resident timing --------------------------------------------------------------
     for _ in range(warmup):
         step_device()
-    nnz = q.device_finish(stream, do["row_ptr"])
+    drain_device()
+    nnz = q.device_finish(stream, outs[(step_no[0] - 1) % len(outs)]["row_ptr"])
     q.set_profiling(True)
     q.profile_reset()
     launches0 = q.launch_count
@@ -281,6 +317,7 @@ def measure_config(args, name, cells, res, ctx):
     e0.record()
     for _ in range(steps):
         step_device()
+    drain_device()          # every step's matrix is assembled inside the timed region
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1) / steps
@@ -362,12 +399,13 @@ def measure_config(args, name, cells, res, ctx):
     abytes = algorithmic_bytes(batch, nnz)
     peak, peak_src = peak_hbm()
     achieved = abytes / (fam_ms * 1e-3) / 1e9 if fam_ms > 0 else 0.0
-    traffic, traffic_note = None, "no capture for this configuration"
+    traffic, traffic_note, warp_inst = None, "no capture for this configuration", None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         if tj.get("build") == build_hash():
             traffic = tj.get(name)
             traffic_note = tj.get("source")
+            warp_inst = (tj.get("warp_instructions") or {}).get(name)
         else:
             traffic_note = "profiles/ncu_traffic.json was captured on another build of csrc/ (%s): not reported" % tj.get("build")
     except Exception:
@@ -376,6 +414,14 @@ def measure_config(args, name, cells, res, ctx):
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note,
                 "algorithmic_bytes_per_step": abytes, "kernel_ms_per_step": fam_ms, "peak_source": peak_src, "nnz_per_gpu": nnz,
                 "per_kernel_ms": {k: v[0] / steps for k, v in prof.items()}}
+    # the family is instruction-issue / latency bound, not HBM bound: issue-slot utilisation beside the HBM fraction.
+    # warp instructions per step from the same ncu pass as `traffic` (same build), peak = SMs x 4 schedulers x SM clock
+    if warp_inst and traffic and fam_ms > 0:
+        scale = cells / float(tj.get("cells_per_step", {}).get(name, cells))      # (the capture's step may be a smaller cell count)
+        sm_hz = ((clocks or {}).get("sm_mhz") or 1965) * 1e6
+        n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+        roofline["issue"] = {"warp_instructions_per_step": warp_inst * scale, "achieved_ginst_s": warp_inst * scale / (fam_ms * 1e-3) / 1e9,
+                             "peak_ginst_s": n_sm * 4 * sm_hz / 1e9, "frac": warp_inst * scale / (fam_ms * 1e-3) / (n_sm * 4 * sm_hz)}
 
     # ---- CPU baseline (rank 0, N=1 only): oracle port on a bounded sample of the same workload --
     cpu = None
@@ -421,8 +467,11 @@ def measure_config(args, name, cells, res, ctx):
     }
     if census is not None:
         out["tie_census"] = census
+    if world > 1:
+        out["assembly"] = ("NCCL all-gather of row lengths + (col, val) onto every rank, inside the timed step; issued on a second stream so that "
+                           "step i's gathers overlap step i+1's kernels (two output sets), all drained before the closing event")
     q.close()
-    del db, do, asm_scratch, parts
+    del db, do, outs, asm_scratch, parts
     pool.close()
     torch.cuda.empty_cache()
     return out
@@ -479,6 +528,8 @@ def main():
                 "warmup": max(args.warmup, 3), "ms_per_step": hl["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": hl["config"], "roofline": hl["roofline"],
                 "cpu_baseline": hl["cpu_baseline"], "e2e": hl["e2e"], "gpu_launches": hl["gpu_launches"], "clocks": hl["clocks"]}
+        if hl.get("assembly"):
+            line["assembly"] = hl["assembly"]
         if len(names) > 1:
             line["other_configs"] = {n: legs[n] for n in names[1:]}
         emit(line)

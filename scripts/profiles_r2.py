@@ -69,7 +69,13 @@ for cfg, key in (("c2", "C2"), ("c3", "C3")):
         if m == "dram__bytes_read.sum": cur["dram_read_bytes"] = v
         elif m == "dram__bytes_write.sum": cur["dram_write_bytes"] = v
         elif m == "gpu__time_duration.sum": cur["us(cold, serialised)"] = v / 1000.0
+        elif m == "smsp__inst_executed.sum": cur["warp_instructions"] = v
     traffic[key] = sum(d["dram_read_bytes"] + d["dram_write_bytes"] for d in order)
+    traffic.setdefault("warp_instructions", {})[key] = sum(d.get("warp_instructions", 0.0) for d in order)
+    traffic.setdefault("cells_per_step", {})[key] = {"C2": 100000, "C3": 125000}[key]
     traffic["per_launch"][key] = order
+for key, order in traffic["per_launch"].items():
+    names = [d["kernel"] for d in order]
+    print(key, len(names), "launches;", "DUPLICATES (window is not one step)" if len(set(names)) != len(names) and key == "C2" else "", sorted(collections.Counter(names).items()))
 json.dump(traffic, open(os.path.join(P, "ncu_traffic.json"), "w"), indent=1)
 print({k: v for k, v in traffic.items() if k in ("build", "C2", "C3")})
