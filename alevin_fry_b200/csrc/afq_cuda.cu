@@ -81,6 +81,36 @@ struct Work {  // per-pipeline scratch (ordered on one stream)
   DBuf<u32> na_ref_off;    // device API: offsets derived from rec_na8
   DBuf<u32> umi_wide, refs_wide;   // rec_umi24 / refs24 widened to u32
   bool sync_sizing = true;         // read the control block back after the binning (device API) or plan the global arenas blind (afq_submit)
+  // every pipeline has its own stream, lanes and giant-cell arenas, so that two of them can run side by side on the device
+  cudaStream_t st = nullptr;       // host pipelines only (the device API runs on the caller's stream)
+  cudaStream_t lanes[NUM_BINS] = {nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_lane[NUM_BINS] = {nullptr};
+  u64* large_keys = nullptr;       // giant-cell scratch of k_resolve_large
+  u32* large_cnts = nullptr;
+  u32 large_cap_log2 = 0, large_blocks = 0;     // what the two arrays above were allocated for
+  cudaError_t create_streams(bool own_stream) {
+    cudaError_t e;
+    if (own_stream && (e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    if ((e = cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming)) != cudaSuccess) return e;
+    for (int i = 0; i < NUM_BINS; ++i) {     // (stream priorities for the lanes of the larger arenas were tried, r2v: no effect)
+      if ((e = cudaStreamCreateWithFlags(&lanes[i], cudaStreamNonBlocking)) != cudaSuccess) return e;
+      if ((e = cudaEventCreateWithFlags(&ev_lane[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+  }
+  // (re)allocate the giant-cell arenas for `blocks` CTAs of 2^cap_log2 entries; cudaFree waits for the device, so no batch is using them
+  cudaError_t ensure_large(u32 cap_log2, u32 blocks) {
+    if (large_keys && cap_log2 == large_cap_log2 && blocks == large_blocks) return cudaSuccess;
+    if (large_keys) cudaFree(large_keys);
+    if (large_cnts) cudaFree(large_cnts);
+    large_keys = nullptr; large_cnts = nullptr;
+    const size_t entries = (size_t)blocks << cap_log2;
+    cudaError_t e;
+    if ((e = cudaMalloc((void**)&large_keys, entries * sizeof(u64))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void**)&large_cnts, entries * sizeof(u32))) != cudaSuccess) return e;
+    large_cap_log2 = cap_log2; large_blocks = blocks;
+    return cudaSuccess;
+  }
   cudaError_t ensure(u64 n_cells, u64 n_refs) {
     cudaError_t e;
     if ((e = ctl.ensure(1)) != cudaSuccess) return e;
@@ -97,6 +127,13 @@ struct Work {  // per-pipeline scratch (ordered on one stream)
     ps_mlab.release(); ps_nlab.release(); ps_moff.release(); ps_mlen.release(); ps_back_list.release(); ps_back_garena.release();
     cls_ncls.release(); cls_nlab.release(); cls_cnt.release(); cls_off.release(); cls_lab.release();
     na_tiles.release(); na_ref_off.release(); umi_wide.release(); refs_wide.release();
+    if (large_keys) cudaFree(large_keys);
+    if (large_cnts) cudaFree(large_cnts);
+    large_keys = nullptr; large_cnts = nullptr;
+    for (int i = 0; i < NUM_BINS; ++i) { if (lanes[i]) cudaStreamDestroy(lanes[i]); if (ev_lane[i]) cudaEventDestroy(ev_lane[i]); lanes[i] = nullptr; ev_lane[i] = nullptr; }
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (st) cudaStreamDestroy(st);
+    ev_fork = nullptr; st = nullptr;
   }
 };
 
@@ -126,6 +163,7 @@ struct Slot {  // one in-flight host batch
   afq_device_out dout{};
   cudaEvent_t ev_h2d = nullptr, ev_done = nullptr, ev_d2h = nullptr;
   u64 n_cells = 0, n_refs = 0, ticket = 0;
+  int pipe = 0;               // which host pipeline (Work + stream) runs this batch
   bool busy = false;
   void release() {
     cell_rec_off.release(); umi.release(); ref_off.release(); refs.release(); na8.release(); umi24.release(); refs24.release();
@@ -155,9 +193,7 @@ struct afq_ctx {
   std::string err;
   u64 launches = 0;
   u64 reruns = 0;
-  // giant-cell scratch
-  u64* large_keys = nullptr;
-  u32* large_cnts = nullptr;
+  // giant-cell scratch (every pipeline holds arenas of this shape, Work::ensure_large)
   u32 large_cap_log2 = 21;
   u32 large_blocks = 0;   // 0 = one per SM
   int force_bin = -1;
@@ -180,13 +216,15 @@ struct afq_ctx {
   u64 pool_default_bytes = 256ull << 20;   // AFQ_POOL_MB: every pool's initial size
   u64 pool_budget_bytes = 8ull << 30;      // no pool is grown beyond this for full occupancy (it always holds one arena)
   u32 back_max_tier = 0;       // AFQ_BACK_MAX_TIER: largest shared-memory arena tier of k_pug_back (r2j: 0 is fastest on C3-em / C4 / C5)
-  cudaStream_t lanes[NUM_BINS] = {nullptr};
-  cudaEvent_t ev_fork = nullptr, ev_lane[NUM_BINS] = {nullptr};
-  // pipelines
-  Work work_dev, work_host;
+  // pipelines: the device API's, and two for afq_submit — consecutive host batches alternate between them, so that the
+  // next batch's kernels fill the SMs that the tail of this batch's persistent kernels leaves idle (a batch of 15 k cells
+  // runs 25 % below the rate of one of 125 k on C4, r2r). AFQ_HOST_PIPES=1: one pipeline, batches back to back.
+  static constexpr int NPIPE = 2;
+  Work work_dev, work_host[NPIPE];
+  int host_pipes = NPIPE;
   static constexpr int NSLOT = 3;
   Slot slots[NSLOT];
-  cudaStream_t s_copy = nullptr, s_compute = nullptr, s_d2h = nullptr;
+  cudaStream_t s_copy = nullptr, s_d2h = nullptr;
   u64 next_ticket = 1;
   std::mutex mu;
   // profiling
@@ -315,16 +353,16 @@ struct CudaLauncher {
     return true;
   }
   u32* back_garena(u64 min_words, u64* cap) { return pool(w->ps_back_garena, 1, min_words, cap); }
-  // fork / join: lanes are ctx-owned non-blocking streams ordered after / before the caller stream
+  // fork / join: lanes are the pipeline's own non-blocking streams ordered after / before the caller stream
   void fork(int n) {
     if (c->no_lanes) return;
     nlanes = n;
-    cudaEventRecord(c->ev_fork, st);
-    for (int i = 0; i < n; ++i) cudaStreamWaitEvent(c->lanes[i], c->ev_fork, 0);
+    cudaEventRecord(w->ev_fork, st);
+    for (int i = 0; i < n; ++i) cudaStreamWaitEvent(w->lanes[i], w->ev_fork, 0);
   }
-  void lane(int i) { cur = c->no_lanes ? st : c->lanes[i]; }
+  void lane(int i) { cur = c->no_lanes ? st : w->lanes[i]; }
   void join() {
-    for (int i = 0; i < nlanes; ++i) { cudaEventRecord(c->ev_lane[i], c->lanes[i]); cudaStreamWaitEvent(st, c->ev_lane[i], 0); }
+    for (int i = 0; i < nlanes; ++i) { cudaEventRecord(w->ev_lane[i], w->lanes[i]); cudaStreamWaitEvent(st, w->ev_lane[i], 0); }
     cur = st;
     nlanes = 0;
   }
@@ -347,6 +385,7 @@ int run_pipeline(afq_ctx* c, Work& w, const afq_batch& b, const afq_device_out& 
     return AFQ_ERR_INVALID;
   }
   if (b.n_cells) CUDA_TRY(c, w.ensure(b.n_cells, b.n_refs_total));
+  CUDA_TRY(c, w.ensure_large(c->large_cap_log2, c->large_blocks));
   afq_batch bb = b;
   CudaLauncher l{c, &w, st, st};
   if (!bb.rec_umi32 && bb.n_records) {
@@ -372,7 +411,7 @@ int run_pipeline(afq_ctx* c, Work& w, const afq_batch& b, const afq_device_out& 
     bb.rec_ref_offsets = w.na_ref_off.p;
   }
   PipeBufs pb{w.ctl.p, w.bin_list.p, w.stage_col.p, w.stage_val.p, w.tile_sums.p,
-              c->large_keys, c->large_cnts, c->large_cap_log2, c->large_blocks};
+              w.large_keys, w.large_cnts, w.large_cap_log2, w.large_blocks};
   Slot* ds = (dump_slot && b.n_cells) ? dump_slot : nullptr;
   if (ds) {
     CUDA_TRY(c, ds->dump_ncls.ensure(b.n_cells + 1)); CUDA_TRY(c, ds->dump_nlab.ensure(b.n_cells + 1));
@@ -444,23 +483,25 @@ int check_device_error(afq_ctx* c, const Ctl& h) {
 int enqueue_slot(afq_ctx* c, Slot& s) {
   const u64 nc = s.n_cells;
   const bool dump = c->cfg.dump_eq != 0 && c->cfg.resolution != AFQ_RES_TRIVIAL;
-  int rc = run_pipeline(c, c->work_host, s.db, s.dout, c->s_compute, dump ? &s : nullptr);
+  Work& w = c->work_host[s.pipe];
+  cudaStream_t st = w.st;
+  int rc = run_pipeline(c, w, s.db, s.dout, st, dump ? &s : nullptr);
   if (rc != AFQ_OK) return rc;
   s.has_dump = dump && nc > 0;
   if (s.has_dump) {
     CUDA_TRY(c, s.h_cls_ptr.ensure(nc + 2)); CUDA_TRY(c, s.h_lab_base.ensure(nc + 2));
-    CUDA_TRY(c, cudaMemcpyAsync(s.h_cls_ptr.p, s.dq_cls_ptr.p, (nc + 1) * sizeof(u64), cudaMemcpyDeviceToHost, c->s_compute));
-    CUDA_TRY(c, cudaMemcpyAsync(s.h_lab_base.p, s.dq_lab_base.p, (nc + 1) * sizeof(u64), cudaMemcpyDeviceToHost, c->s_compute));
+    CUDA_TRY(c, cudaMemcpyAsync(s.h_cls_ptr.p, s.dq_cls_ptr.p, (nc + 1) * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaMemcpyAsync(s.h_lab_base.p, s.dq_lab_base.p, (nc + 1) * sizeof(u64), cudaMemcpyDeviceToHost, st));
   }
   // small per-cell results come back on the compute stream right behind the kernels
-  CUDA_TRY(c, cudaMemcpyAsync(s.h_row_ptr.p, s.row_ptr.p, (nc + 1) * sizeof(u64), cudaMemcpyDeviceToHost, c->s_compute));
+  CUDA_TRY(c, cudaMemcpyAsync(s.h_row_ptr.p, s.row_ptr.p, (nc + 1) * sizeof(u64), cudaMemcpyDeviceToHost, st));
   if (nc) {
-    CUDA_TRY(c, cudaMemcpyAsync(s.h_sum.p, s.sum_umi.p, nc * sizeof(float), cudaMemcpyDeviceToHost, c->s_compute));
-    CUDA_TRY(c, cudaMemcpyAsync(s.h_max.p, s.max_umi.p, nc * sizeof(float), cudaMemcpyDeviceToHost, c->s_compute));
-    CUDA_TRY(c, cudaMemcpyAsync(s.h_num_expr.p, s.num_expr.p, nc * sizeof(u32), cudaMemcpyDeviceToHost, c->s_compute));
-    CUDA_TRY(c, cudaMemcpyAsync(s.h_num_over_mean.p, s.num_over_mean.p, nc * sizeof(u32), cudaMemcpyDeviceToHost, c->s_compute));
-    CUDA_TRY(c, cudaMemcpyAsync(s.h_flags.p, s.flags.p, nc * sizeof(u8), cudaMemcpyDeviceToHost, c->s_compute));
-    CUDA_TRY(c, cudaMemcpyAsync(s.h_ctl.p, c->work_host.ctl.p, sizeof(Ctl), cudaMemcpyDeviceToHost, c->s_compute));
+    CUDA_TRY(c, cudaMemcpyAsync(s.h_sum.p, s.sum_umi.p, nc * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaMemcpyAsync(s.h_max.p, s.max_umi.p, nc * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaMemcpyAsync(s.h_num_expr.p, s.num_expr.p, nc * sizeof(u32), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaMemcpyAsync(s.h_num_over_mean.p, s.num_over_mean.p, nc * sizeof(u32), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaMemcpyAsync(s.h_flags.p, s.flags.p, nc * sizeof(u8), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaMemcpyAsync(s.h_ctl.p, w.ctl.p, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
   } else {
     memset(s.h_ctl.p, 0, sizeof(Ctl));
   }
@@ -473,19 +514,12 @@ int grow_large_arena_and_rerun(afq_ctx* c, Slot& s, u32 max_cell_refs) {
   u32 log2cap = c->large_cap_log2;
   while (log2cap < 31 && (1ull << log2cap) < 2ull * max_cell_refs) ++log2cap;
   if ((1ull << log2cap) < 2ull * max_cell_refs) { c->err = "a cell has more than 2^30 alignments"; return AFQ_ERR_UNSUPPORTED; }
-  CUDA_TRY(c, cudaStreamSynchronize(c->s_compute));           // no batch may be using the arenas
   const size_t budget = (size_t)c->large_blocks << c->large_cap_log2;     // entries held today
-  u32 blocks = (u32)std::max<size_t>(1, std::min<size_t>(c->large_blocks, budget >> log2cap));
-  const size_t entries = (size_t)blocks << log2cap;
-  if (c->large_keys) cudaFree(c->large_keys);
-  if (c->large_cnts) cudaFree(c->large_cnts);
-  c->large_keys = nullptr; c->large_cnts = nullptr;
-  CUDA_TRY(c, cudaMalloc((void**)&c->large_keys, entries * sizeof(u64)));
-  CUDA_TRY(c, cudaMalloc((void**)&c->large_cnts, entries * sizeof(u32)));
-  c->large_cap_log2 = log2cap; c->large_blocks = blocks;
+  const u32 blocks = (u32)std::max<size_t>(1, std::min<size_t>(c->large_blocks, budget >> log2cap));
+  c->large_cap_log2 = log2cap; c->large_blocks = blocks;                  // (every pipeline re-allocates at its next batch)
   int rc = enqueue_slot(c, s);
   if (rc != AFQ_OK) return rc;
-  CUDA_TRY(c, cudaStreamSynchronize(c->s_compute));
+  CUDA_TRY(c, cudaStreamSynchronize(c->work_host[s.pipe].st));
   return AFQ_OK;
 }
 
@@ -495,10 +529,9 @@ int grow_pools_and_rerun(afq_ctx* c, Slot& s) {
   const Ctl& h = *s.h_ctl.p;
   if (h.ps3_words >= 0xFFFFFFF0u || h.back_words >= 0xFFFFFFF0u) { c->err = "a cell needs a global arena of more than 2^32 words"; return AFQ_ERR_UNSUPPORTED; }
   learn_from(c, h);
-  CUDA_TRY(c, cudaStreamSynchronize(c->s_compute));
-  int rc = enqueue_slot(c, s);
+  int rc = enqueue_slot(c, s);          // (a pool that grows is re-allocated behind a cudaFree, which waits for the device)
   if (rc != AFQ_OK) return rc;
-  CUDA_TRY(c, cudaStreamSynchronize(c->s_compute));
+  CUDA_TRY(c, cudaStreamSynchronize(c->work_host[s.pipe].st));
   return AFQ_OK;
 }
 
@@ -561,8 +594,11 @@ int afq_create(const afq_config* cfg, const uint32_t* tid_to_gid, uint64_t n_ref
   if (const char* s = getenv("AFQ_BACK_MAX_TIER")) c->back_max_tier = (u32)atoi(s);
   if (const char* s = getenv("AFQ_POOL_MB")) c->pool_default_bytes = (u64)std::max(1, atoi(s)) << 20;
   c->work_dev.sync_sizing = true;
-  c->work_host.sync_sizing = false;       // afq_submit never waits for the device
-  if (const char* s = getenv("AFQ_SYNC_SIZING")) c->work_host.sync_sizing = atoi(s) != 0;   // (A/B: the read-back of round 1)
+  for (auto& w : c->work_host) {
+    w.sync_sizing = false;                // afq_submit never waits for the device
+    if (const char* s = getenv("AFQ_SYNC_SIZING")) w.sync_sizing = atoi(s) != 0;   // (A/B: the read-back of round 1)
+  }
+  if (const char* s = getenv("AFQ_HOST_PIPES")) c->host_pipes = std::max(1, std::min((int)afq_ctx::NPIPE, atoi(s)));
   {
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b) c->pool_budget_bytes = std::max<u64>(1ull << 30, (u64)total_b / 16);
@@ -577,19 +613,12 @@ int afq_create(const afq_config* cfg, const uint32_t* tid_to_gid, uint64_t n_ref
   CREATE_TRY(cudaSetDevice(c->device));
   CREATE_TRY(cudaMalloc((void**)&c->d_t2g, n_refs * sizeof(u32)));
   CREATE_TRY(cudaMemcpy(c->d_t2g, tid_to_gid, n_refs * sizeof(u32), cudaMemcpyHostToDevice));
-  const size_t large_entries = (size_t)c->large_blocks << c->large_cap_log2;
-  CREATE_TRY(cudaMalloc((void**)&c->large_keys, large_entries * sizeof(u64)));
-  CREATE_TRY(cudaMalloc((void**)&c->large_cnts, large_entries * sizeof(u32)));
   CREATE_TRY(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
-  CREATE_TRY(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
   CREATE_TRY(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
   CREATE_TRY(cudaHostAlloc((void**)&c->h_ctl_dev, sizeof(Ctl), cudaHostAllocDefault));
-  CREATE_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-  // (stream priorities for the lanes of the larger arenas were tried, r2v: no effect on any configuration)
-  for (int i = 0; i < NUM_BINS; ++i) {
-    CREATE_TRY(cudaStreamCreateWithFlags(&c->lanes[i], cudaStreamNonBlocking));
-    CREATE_TRY(cudaEventCreateWithFlags(&c->ev_lane[i], cudaEventDisableTiming));
-  }
+  CREATE_TRY(c->work_dev.create_streams(false));
+  for (auto& w : c->work_host) CREATE_TRY(w.create_streams(true));
+  // (the giant-cell arenas are allocated by a pipeline's first batch: Work::ensure_large)
   for (auto& s : c->slots) {
     CREATE_TRY(cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
     CREATE_TRY(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
@@ -658,16 +687,11 @@ void afq_destroy(afq_ctx* c) {
   cudaDeviceSynchronize();
   for (auto& p : c->prof) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   c->work_dev.release();
-  c->work_host.release();
+  for (auto& w : c->work_host) w.release();
   for (auto& s : c->slots) s.release();
   if (c->d_t2g) cudaFree(c->d_t2g);
-  if (c->large_keys) cudaFree(c->large_keys);
-  if (c->large_cnts) cudaFree(c->large_cnts);
   if (c->h_ctl_dev) cudaFreeHost(c->h_ctl_dev);
-  for (int i = 0; i < NUM_BINS; ++i) { if (c->lanes[i]) cudaStreamDestroy(c->lanes[i]); if (c->ev_lane[i]) cudaEventDestroy(c->ev_lane[i]); }
-  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->s_copy) cudaStreamDestroy(c->s_copy);
-  if (c->s_compute) cudaStreamDestroy(c->s_compute);
   if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
   delete c;
 }
@@ -751,7 +775,8 @@ int afq_submit(afq_ctx* c, const afq_batch* hb, uint64_t* ticket) {
     else CUDA_TRY(c, cudaMemcpyAsync(s.refs.p, hb->refs, nf * sizeof(u32), cudaMemcpyHostToDevice, c->s_copy));
   }
   CUDA_TRY(c, cudaEventRecord(s.ev_h2d, c->s_copy));
-  CUDA_TRY(c, cudaStreamWaitEvent(c->s_compute, s.ev_h2d, 0));
+  s.pipe = (int)(t % (u64)c->host_pipes);
+  CUDA_TRY(c, cudaStreamWaitEvent(c->work_host[s.pipe].st, s.ev_h2d, 0));
   afq_batch db = *hb;
   db.cell_rec_offsets = s.cell_rec_off.p;
   db.rec_umi32 = use_umi24 ? nullptr : s.umi.p;
@@ -768,7 +793,7 @@ int afq_submit(afq_ctx* c, const afq_batch* hb, uint64_t* ticket) {
   s.db = db; s.dout = o; s.n_cells = nc; s.n_refs = nf; s.n_records = nr; s.retried = 0;
   int rc = enqueue_slot(c, s);
   if (rc != AFQ_OK) return rc;
-  CUDA_TRY(c, cudaEventRecord(s.ev_done, c->s_compute));
+  CUDA_TRY(c, cudaEventRecord(s.ev_done, c->work_host[s.pipe].st));
   s.n_cells = nc; s.n_refs = nf; s.ticket = t; s.busy = true;
   c->next_ticket++;
   *ticket = t;
@@ -917,7 +942,7 @@ int afq_infer(afq_ctx* c, const afq_eqc_table* t, uint64_t n_cells, const uint64
   INF_BUF(d_cursor, 4); INF_BUF(d_sum, n_cells + 2); INF_BUF(d_max, n_cells + 2); INF_BUF(d_flags, n_cells + 2);
   INF_BUF(d_garena, garena_words ? garena_words * grid + 16 : 4);
 #undef INF_BUF
-  cudaStream_t st = c->s_compute;
+  cudaStream_t st = c->work_host[0].st;
   CUDA_TRY(c, cudaMemsetAsync(d_eq.p, 0, (nnz_in + 8) * 4, st));        // (the bulk copies read up to 3 words past a row)
   CUDA_TRY(c, cudaMemsetAsync(d_cnt.p, 0, (nnz_in + 8) * 4, st));
   CUDA_TRY(c, cudaMemsetAsync(d_cursor.p, 0, 16, st));

@@ -202,6 +202,25 @@ def test_pipelined_submits_and_full_size_properties():
         assert_same(gpu_quant(oo, t2g, shuf), gpu_quant(oo, t2g, b.slice_cells(0, 200)), ctx="shuffle/" + res)
 
 
+@pytest.mark.parametrize("cfg,res", [("C4", "cr-like-em"), ("C3", "parsimony"), ("C5", "parsimony-em"), ("C2", "cr-like")])
+def test_batches_in_flight_on_two_pipelines(cfg, res):
+    # consecutive host batches alternate between two device pipelines (own stream, lanes, scratch) and overlap on the GPU;
+    # three in flight, every result against the oracle
+    spec = synth.config_spec(cfg)
+    t2g = synth.tid_to_gid(spec)
+    o = opts_for(spec, res)
+    parts = [synth.generate(spec, 1000 * i, 300 + 40 * i) for i in range(7)]
+    with Quantifier(o, t2g) as q:
+        tickets, rs = [], []
+        for p in parts:
+            tickets.append(q.submit(p, use_na8=True, use_pack24=True))
+            if len(tickets) == 3:
+                rs.append(q.wait(tickets.pop(0)))
+        rs += [q.wait(t) for t in tickets]
+    for i, (p, r) in enumerate(zip(parts, rs)):
+        assert_same(r, oracle_lib.oracle_quant(o, t2g, p), exact=not res.endswith("-em"), ctx=f"{cfg}/{res}/batch{i}")
+
+
 def test_na8_compact_offsets_match():
     # afq_batch.rec_na8 (1 B/record over PCIe instead of 4 B offsets) must give identical results
     spec = synth.config_spec("C2")
