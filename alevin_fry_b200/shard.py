@@ -62,19 +62,33 @@ def assemble_csr(num_expr: torch.Tensor, col: torch.Tensor, val: torch.Tensor, n
     my_nnz = int(nnz_r[rank].item())
     scratch = scratch if scratch is not None else {}
     key = (max_nnz, world, str(dev))
+    m = max(max_nnz, 1)
     if scratch.get("key") != key:
         scratch["key"] = key
-        scratch["pc"] = torch.zeros(max(max_nnz, 1), dtype=torch.int32, device=dev)
-        scratch["pv"] = torch.zeros(max(max_nnz, 1), dtype=torch.float32, device=dev)
-        scratch["ac"] = torch.empty(world * max(max_nnz, 1), dtype=torch.int32, device=dev)
-        scratch["av"] = torch.empty(world * max(max_nnz, 1), dtype=torch.float32, device=dev)
-    pc, pv, ac, av = scratch["pc"], scratch["pv"], scratch["ac"], scratch["av"]
-    pc[:my_nnz] = col[:my_nnz].to(torch.int32)
-    pv[:my_nnz] = val[:my_nnz]
+        scratch["pc"] = scratch["pv"] = None
+        scratch["ac"] = torch.empty(world * m, dtype=torch.int32, device=dev)
+        scratch["av"] = torch.empty(world * m, dtype=torch.float32, device=dev)
+    ac, av = scratch["ac"], scratch["av"]
+    # every rank sends `m` entries. The staging arrays of the device API hold one slot per alignment (>= any rank's nnz in
+    # practice), so the send buffer is normally a VIEW of col / val — what lies behind a rank's own nnz is never read by
+    # anyone; only arrays shorter than m are copied into a padded buffer first.
+    if col.dtype == torch.int32 and col.is_contiguous() and col.numel() >= m:
+        pc = col[:m]
+    else:
+        if scratch["pc"] is None:
+            scratch["pc"] = torch.zeros(m, dtype=torch.int32, device=dev)
+        pc = scratch["pc"]
+        pc[:my_nnz] = col[:my_nnz].to(torch.int32)
+    if val.dtype == torch.float32 and val.is_contiguous() and val.numel() >= m:
+        pv = val[:m]
+    else:
+        if scratch["pv"] is None:
+            scratch["pv"] = torch.zeros(m, dtype=torch.float32, device=dev)
+        pv = scratch["pv"]
+        pv[:my_nnz] = val[:my_nnz]
     dist.all_gather_into_tensor(ac, pc, group=group)
     dist.all_gather_into_tensor(av, pv, group=group)
     rp = global_row_ptr(lens, n_cells, world)
-    m = max(max_nnz, 1)
     if not compact:
         return rp, ac, av, m, nnz_r
     cols = torch.cat([ac[r * m: r * m + int(nnz_r[r].item())] for r in range(world)])
