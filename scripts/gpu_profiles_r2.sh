@@ -11,9 +11,9 @@ timeout 900 $NCU --set full --import-source on -k regex:k_resolve_smem --launch-
 timeout 900 $NCU --set full --import-source on -k regex:'k_pug_build|k_pug_cover|k_pug_count' --launch-skip 27 -c 9 -f -o gpurun_out/${TAG}_full_pug python bench.py --config C3 --steps 1 --warmup 1 --cells 10000 --no-cpu-baseline --no-others > gpurun_out/${TAG}_full_pug.log 2>&1
 timeout 900 $NCU --set full --import-source on -k regex:'k_pug_back|k_em_cells' --launch-skip 24 -c 8 -f -o gpurun_out/${TAG}_full_em_c4 python bench.py --config C4 --steps 1 --warmup 1 --cells 8000 --no-cpu-baseline --no-others > gpurun_out/${TAG}_full_em_c4.log 2>&1
 timeout 900 $NCU --set full --import-source on -k regex:'k_pug_back|k_em_cells' --launch-skip 24 -c 8 -f -o gpurun_out/${TAG}_full_em_c5 python bench.py --config C5 --steps 1 --warmup 1 --cells 10000 --no-cpu-baseline --no-others > gpurun_out/${TAG}_full_em_c5.log 2>&1
-# DRAM traffic of the resolve family, one full-size step (the first timed step after 3 warm-ups + 1)
-timeout 1500 $NCU --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,smsp__inst_executed.sum -k regex:'k_resolve' -s 32 -c 8 --csv --log-file gpurun_out/${TAG}_traffic_c2.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-others > gpurun_out/${TAG}_traffic_c2.log 2>&1
-timeout 1500 $NCU --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,smsp__inst_executed.sum -k regex:'k_pug|k_gene_eqc|k_resolve' -s 76 -c 19 --csv --log-file gpurun_out/${TAG}_traffic_c3.csv python bench.py --config C3 --steps 1 --warmup 1 --no-cpu-baseline --no-others > gpurun_out/${TAG}_traffic_c3.log 2>&1
+# DRAM traffic + warp instructions of the resolve family: every launch of the first steps is captured, profiles_r2.py keeps the 4th step (the timed one)
+timeout 1500 $NCU --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,smsp__inst_executed.sum -k regex:'k_resolve' -c 64 --csv --log-file gpurun_out/${TAG}_traffic_c2.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-others > gpurun_out/${TAG}_traffic_c2.log 2>&1
+timeout 1500 $NCU --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,smsp__inst_executed.sum -k regex:'k_pug_build|k_pug_cover|k_pug_count|k_gene_eqc|k_resolve' -c 110 --csv --log-file gpurun_out/${TAG}_traffic_c3.csv python bench.py --config C3 --steps 1 --warmup 1 --no-cpu-baseline --no-others > gpurun_out/${TAG}_traffic_c3.log 2>&1
 # summarise on the box (the reports together exceed what gpurun copies back); keep the parsimony report only
 BUILD=$(python -c "import bench; print(bench.build_hash())")
 PROFILES_OUT=gpurun_out/${TAG}_profiles python scripts/profiles_r2.py ${TAG} ${BUILD} 2>&1 | tail -8

@@ -52,12 +52,11 @@ for name, ksub, cmd, reading in FULL:
                         "ncu --set full --clock-control none --import-source on, " + cmd + " (scripts/gpu_profiles_r2.sh), csrc build " + build, reading, ksub], check=False)
 
 traffic = {"build": build, "source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none over the per-cell "
-           "resolve family of ONE full-size step (scripts/gpu_profiles_r2.sh); bytes per step = sum over the launches", "per_launch": {}}
+           "resolve family of ONE full-size device-resident step (the 4th of the run; scripts/gpu_profiles_r2.sh); bytes per step = sum over the launches", "per_launch": {}}
 for cfg, key in (("c2", "C2"), ("c3", "C3")):
     fn = os.path.join(G, f"{tag}_traffic_{cfg}.csv")
     if not os.path.exists(fn):
         continue
-    per = collections.OrderedDict()
     order = []
     cur = None
     for k, m, v in launches(fn):
@@ -70,6 +69,15 @@ for cfg, key in (("c2", "C2"), ("c3", "C3")):
         elif m == "dram__bytes_write.sum": cur["dram_write_bytes"] = v
         elif m == "gpu__time_duration.sum": cur["us(cold, serialised)"] = v / 1000.0
         elif m == "smsp__inst_executed.sum": cur["warp_instructions"] = v
+    # the capture holds every launch of the run: split it into steps (every step's first launch of the family is
+    # k_resolve_smem<5>) and keep the 4th — the timed device-resident full-size step behind the 3 warm-ups
+    steps_ = []
+    for d in order:
+        if d["kernel"].endswith("k_resolve_smem<5>") or not steps_:
+            steps_.append([])
+        steps_[-1].append(d)
+    print(key, "steps in the capture:", [len(x) for x in steps_][:12])
+    order = steps_[3] if len(steps_) > 3 else []
     traffic[key] = sum(d["dram_read_bytes"] + d["dram_write_bytes"] for d in order)
     traffic.setdefault("warp_instructions", {})[key] = sum(d.get("warp_instructions", 0.0) for d in order)
     traffic.setdefault("cells_per_step", {})[key] = {"C2": 100000, "C3": 125000}[key]
