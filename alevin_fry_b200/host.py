@@ -36,6 +36,12 @@ class RadInfo(C.Structure):
                 ("n_file_tags", C.c_uint32), ("n_read_tags", C.c_uint32), ("n_aln_tags", C.c_uint32)]
 
 
+class StageInfo(C.Structure):
+    _fields_ = [("n_cells", C.c_uint64), ("n_records", C.c_uint64), ("n_alignments", C.c_uint64), ("nnz", C.c_uint64),
+                ("mtx_bytes", C.c_uint64), ("mtx_sum", C.c_uint64), ("sum_umi", C.c_uint64), ("sum_refs", C.c_uint64), ("sum_na", C.c_uint64),
+                ("walk_s", C.c_double), ("parse_s", C.c_double), ("format_s", C.c_double), ("parse_warm_s", C.c_double), ("threads", C.c_uint32), ("pack24", C.c_uint32)]
+
+
 _lib = None
 
 
@@ -54,6 +60,8 @@ def lib():
         l.afqh_infer.argtypes = [C.POINTER(_InferOpts), C.c_char_p, C.c_size_t]
         l.afqh_rad_summary.restype = C.c_int
         l.afqh_rad_summary.argtypes = [C.c_char_p, C.POINTER(RadInfo), C.c_char_p, C.c_size_t]
+        l.afqh_host_stage_bench.restype = C.c_int
+        l.afqh_host_stage_bench.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.POINTER(StageInfo), C.c_char_p, C.c_size_t]
         l.afqh_free.restype = None
         l.afqh_free.argtypes = [C.c_void_p]
         l.afqh_write_collated_rad.restype = C.c_int
@@ -87,6 +95,16 @@ def infer(count_mat, eq_labels, output_dir, usa_mode=False, filter_list=None, nu
     err = C.create_string_buffer(2048)
     if lib().afqh_infer(C.byref(o), err, 2048) != 0:
         raise RuntimeError(err.value.decode(errors="replace"))
+
+
+def host_stage_bench(path, n_threads=0, frac_every=0) -> StageInfo:
+    """The two host stages of `quant` without a GPU: chunk index + the product's parallel parser, and the parallel text
+    formatting on a synthetic result (wall seconds per stage + checksums of the parsed arrays)."""
+    info = StageInfo()
+    err = C.create_string_buffer(1024)
+    if lib().afqh_host_stage_bench(os.fsencode(path), n_threads or (os.cpu_count() or 2), frac_every, C.byref(info), err, 1024) != 0:
+        raise RuntimeError(err.value.decode(errors="replace"))
+    return info
 
 
 def rad_summary(path) -> RadInfo:

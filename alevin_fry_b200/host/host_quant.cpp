@@ -94,6 +94,74 @@ void append_f32(std::string& out, float v) {
   auto r = std::to_chars(buf, buf + sizeof buf, v, std::chars_format::fixed);
   out.append(buf, r.ptr);
 }
+// ---- the matrix body is ~13 bytes x nnz of text: formatted with a two-digit table into uninitialised, geometrically grown
+// buffers (std::string appends + std::to_chars cost ~200 ns per entry and a memset per reserve; this is ~15 ns) ----------------
+static const char DIG2[] =
+    "0001020304050607080910111213141516171819202122232425262728293031323334353637383940414243444546474849"
+    "5051525354555657585960616263646566676869707172737475767778798081828384858687888990919293949596979899";
+inline unsigned dec_len_u32(uint32_t v) {
+  return v < 10u ? 1u : v < 100u ? 2u : v < 1000u ? 3u : v < 10000u ? 4u : v < 100000u ? 5u : v < 1000000u ? 6u : v < 10000000u ? 7u
+       : v < 100000000u ? 8u : v < 1000000000u ? 9u : 10u;
+}
+inline char* put_u32(char* d, uint32_t v) {        // decimal digits of v at d; returns the end
+  const unsigned n = dec_len_u32(v);
+  char* e = d + n;
+  char* q = e;
+  while (v >= 100u) { const uint32_t r = v % 100u; v /= 100u; q -= 2; memcpy(q, DIG2 + 2 * r, 2); }
+  if (v >= 10u) memcpy(q - 2, DIG2 + 2 * v, 2); else q[-1] = (char)('0' + v);
+  return e;
+}
+inline char* put_u64(char* d, uint64_t v) {
+  if (v <= 0xFFFFFFFFull) return put_u32(d, (uint32_t)v);
+  char tmp[24];
+  auto r = std::to_chars(tmp, tmp + sizeof tmp, v);
+  memcpy(d, tmp, (size_t)(r.ptr - tmp));
+  return d + (r.ptr - tmp);
+}
+struct TextBuf {   // a growable char buffer that never zero-fills
+  char* p = nullptr; size_t n = 0, cap = 0;
+  TextBuf() = default;
+  TextBuf(TextBuf&& o) noexcept : p(o.p), n(o.n), cap(o.cap) { o.p = nullptr; o.n = o.cap = 0; }
+  TextBuf& operator=(TextBuf&& o) noexcept { if (this != &o) { free(p); p = o.p; n = o.n; cap = o.cap; o.p = nullptr; o.n = o.cap = 0; } return *this; }
+  TextBuf(const TextBuf&) = delete;
+  TextBuf& operator=(const TextBuf&) = delete;
+  ~TextBuf() { free(p); }
+  void room(size_t extra) {             // at least `extra` writable bytes behind n
+    if (n + extra <= cap) return;
+    size_t nc = cap ? cap + cap / 2 : 4096;
+    if (nc < n + extra) nc = n + extra;
+    char* q = (char*)realloc(p, nc);
+    if (!q) throw Fail{"out of memory while formatting the matrix"};
+    p = q; cap = nc;
+  }
+  const char* data() const { return p; }
+  size_t size() const { return n; }
+  char operator[](size_t i) const { return p[i]; }
+};
+// one matrix entry "row col val\n" (row text preformatted); whole numbers below 2^24 take the integer path (Rust prints 3, not 3.0)
+inline void put_entry(TextBuf& b, const char* row_txt, unsigned row_len, uint32_t col1, float v) {
+  b.room(row_len + 1 + 10 + 1 + 64 + 1);
+  char* d = b.p + b.n;
+  memcpy(d, row_txt, row_len); d += row_len;
+  *d++ = ' ';
+  d = put_u32(d, col1);
+  *d++ = ' ';
+  if (v >= 0.0f && v < 16777216.0f && v == (float)(uint32_t)v) d = put_u32(d, (uint32_t)v);
+  else if (std::isnan(v)) { memcpy(d, "NaN", 3); d += 3; }
+  else if (std::isinf(v)) { const char* t = v < 0 ? "-inf" : "inf"; const size_t l = strlen(t); memcpy(d, t, l); d += l; }
+  else {
+    char tmp[128];
+    auto r = std::to_chars(tmp, tmp + sizeof tmp, v, std::chars_format::fixed);
+    const size_t l = (size_t)(r.ptr - tmp);
+    b.n = (size_t)(d - b.p);
+    b.room(l + 2);
+    d = b.p + b.n;
+    memcpy(d, tmp, l); d += l;
+  }
+  *d++ = '\n';
+  b.n = (size_t)(d - b.p);
+}
+
 void append_u64(std::string& out, uint64_t v) {
   char buf[24];
   auto r = std::to_chars(buf, buf + sizeof buf, v);
@@ -198,18 +266,27 @@ int resolution_code(const std::string& r) {
   return -1;
 }
 
+// afqh_host_stage_bench (no GPU: the host stages alone) keeps the batches in ordinary memory
+static bool g_plain_host_memory = false;
+
 template <class T>
 struct Pinned {  // growable pinned array (afq_host_alloc)
   T* p = nullptr; size_t n = 0, cap = 0;
-  ~Pinned() { if (p) afq_host_free(p); }
+  bool plain = false;
+  ~Pinned() { release(p); }
+  void release(T* q) { if (q) { if (plain) free(q); else afq_host_free(q); } }
   void reserve(size_t want) {
     if (want <= cap) return;
     size_t nc = cap ? cap : 1024;
     while (nc < want) nc = nc + nc / 2 + 1024;
     void* q = nullptr;
-    if (afq_host_alloc(&q, nc * sizeof(T)) != AFQ_OK) throw Fail{"pinned host allocation failed"};
+    const bool was_plain = plain;
+    if (g_plain_host_memory) { q = malloc(nc * sizeof(T)); if (!q) throw Fail{"host allocation failed"}; }
+    else if (afq_host_alloc(&q, nc * sizeof(T)) != AFQ_OK) throw Fail{"pinned host allocation failed"};
     if (n) memcpy(q, p, n * sizeof(T));
-    if (p) afq_host_free(p);
+    T* old = p;
+    plain = was_plain; release(old);
+    plain = g_plain_host_memory;
     p = (T*)q; cap = nc;
   }
   void push(T v) { if (n == cap) reserve(n + 1); p[n++] = v; }
@@ -335,7 +412,7 @@ struct EqcMap {
 struct Outputs {
   FILE* rows = nullptr;
   FILE* feat = nullptr;
-  std::vector<std::string> mtx_chunks;
+  std::vector<TextBuf> mtx_chunks;
   uint64_t nnz = 0, row_index = 0;
   std::vector<uint64_t> alt, empty, tiny;
   EqcMap eqc;
@@ -365,6 +442,55 @@ void parse_batch(HostBatch& b, const RecordLayout& lay, Pool& pool, std::string&
         uint64_t rec = ci.rec_off, ref = ci.ref_off;
         const uint64_t ref_end = ci.ref_off + ci.n_aln;
         bool ok = true;
+        // the usual layout (a 4-byte alignment = the compressed reference id, a UMI of at most 4 bytes) with 24-bit wire arrays:
+        // fixed strides the compiler can see, and 4-byte stores for the 3-byte values — the 4th byte lands on the next value's
+        // first byte, which is written afterwards; only a chunk's LAST value is stored byte by byte (the next one belongs to
+        // another thread)
+        if (b.pack24 && lay.aln_bytes == 4 && lay.refid_off == 0 && lay.umi_size <= 4) {
+          const size_t rb = lay.read_bytes, uo = lay.umi_off, us = lay.umi_size;
+          const uint64_t rec_last = ci.rec_off + ci.nrec - 1;
+          uint8_t* const u24 = b.umi24.p;
+          uint8_t* const r24 = b.refs24.p;
+          uint8_t* const na8 = b.na8.p;
+          bool wide = false;
+          for (uint32_t r = 0; r < ci.nrec; ++r) {
+            if (p + 4 + rb > end) { ok = false; break; }
+            uint32_t na; memcpy(&na, p, 4);
+            uint32_t rumi = 0; memcpy(&rumi, p + 4 + uo, us);
+            p += 4 + rb;
+            if (na == 0 || (uint64_t)na > ref_end - ref || p + (size_t)na * 4 > end) { ok = false; break; }
+            if (rec != rec_last) memcpy(u24 + 3 * rec, &rumi, 4);
+            else { uint8_t* d = u24 + 3 * rec; d[0] = (uint8_t)rumi; d[1] = (uint8_t)(rumi >> 8); d[2] = (uint8_t)(rumi >> 16); }
+            na8[rec] = (uint8_t)na;
+            wide |= na > 255;
+            uint32_t a = 0;
+            if (na <= 4 && ref + 5 <= ref_end && p + 16 <= end) {
+              // short record well inside its chunk: four unconditional copies instead of a loop whose trip count the branch
+              // predictor cannot guess (mean 1.9 alignments); what is written past `na` is overwritten by the next records
+              for (int q = 0; q < 4; ++q) {
+                uint32_t id; memcpy(&id, p + 4 * q, 4);
+                id &= 0x7FFFFFFFu;
+                memcpy(r24 + 3 * (ref + q), &id, 4);
+              }
+              a = na;
+            }
+            const uint32_t na_fast = (ref + na == ref_end) ? na - 1 : na;     // (all but the chunk's last alignment)
+            for (; a < na_fast; ++a) {
+              uint32_t id; memcpy(&id, p + 4 * (size_t)a, 4);
+              id &= 0x7FFFFFFFu;   // bit 31 = orientation (src/convert.rs:442-445)
+              memcpy(r24 + 3 * (ref + a), &id, 4);
+            }
+            for (; a < na; ++a) {
+              uint32_t id; memcpy(&id, p + 4 * (size_t)a, 4);
+              id &= 0x7FFFFFFFu;
+              uint8_t* d = r24 + 3 * (ref + a); d[0] = (uint8_t)id; d[1] = (uint8_t)(id >> 8); d[2] = (uint8_t)(id >> 16);
+            }
+            p += (size_t)na * 4;
+            ref += na;
+            ++rec;
+          }
+          if (wide) b.wide_na.store(true, std::memory_order_relaxed);
+        } else
         for (uint32_t r = 0; r < ci.nrec && ok; ++r) {
           if (p + 4 + lay.read_bytes > end) { ok = false; break; }
           uint32_t na; memcpy(&na, p, 4); p += 4;
@@ -423,16 +549,17 @@ void parse_batch(HostBatch& b, const RecordLayout& lay, Pool& pool, std::string&
 void consume(const HostBatch& hb, const afq_result& r, unsigned bc_len, const UnmappedCounts& unmapped, Outputs& o, Pool& pool) {
   constexpr uint64_t BLK = 256;
   const uint64_t nblk = (r.n_cells + BLK - 1) / BLK;
-  std::vector<std::string> rows(nblk), feat(nblk), mtx(nblk);
+  std::vector<std::string> rows(nblk), feat(nblk);
+  std::vector<TextBuf> mtx(nblk);
   std::atomic<uint64_t> next{0};
   const uint64_t row0 = o.row_index;
   pool.run([&](unsigned) {
     for (;;) {
       const uint64_t k = next.fetch_add(1);
       if (k >= nblk) return;
-      std::string& rs = rows[k]; std::string& fs = feat[k]; std::string& ms = mtx[k];
+      std::string& rs = rows[k]; std::string& fs = feat[k]; TextBuf& ms = mtx[k];
       const uint64_t c0 = k * BLK, c1 = c0 + BLK < r.n_cells ? c0 + BLK : r.n_cells;
-      ms.reserve((r.row_ptr[c1] - r.row_ptr[c0]) * 16 + 16);
+      ms.room((r.row_ptr[c1] - r.row_ptr[c0]) * 14 + 128);
       for (uint64_t c = c0; c < c1; ++c) {
         const std::string bc = decode_barcode(hb.chunks[c].bc, bc_len);
         rs += bc; rs.push_back('\n');
@@ -452,11 +579,9 @@ void consume(const HostBatch& hb, const afq_result& r, unsigned bc_len, const Un
         append_f32(fs, mean_by_max); fs.push_back('\t');
         append_u64(fs, r.num_expr[c]); fs.push_back('\t');
         append_u64(fs, r.num_over_mean[c]); fs.push_back('\n');
-        for (uint64_t k2 = r.row_ptr[c]; k2 < r.row_ptr[c + 1]; ++k2) {
-          append_u64(ms, row0 + c + 1); ms.push_back(' ');
-          append_u64(ms, (uint64_t)r.col[k2] + 1); ms.push_back(' ');
-          append_f32(ms, r.val[k2]); ms.push_back('\n');
-        }
+        char row_txt[24];
+        const unsigned row_len = (unsigned)(put_u64(row_txt, row0 + c + 1) - row_txt);
+        for (uint64_t k2 = r.row_ptr[c]; k2 < r.row_ptr[c + 1]; ++k2) put_entry(ms, row_txt, row_len, r.col[k2] + 1u, r.val[k2]);
       }
     }
   });
@@ -821,11 +946,16 @@ int quantify_impl(const afqh_quant_opts& o) {
     throw Fail{failure};
   }
   const auto t_td0 = clk::now();
-  destroy_all();
-  if (fmap && mapped) munmap((void*)fmap, fsize);
+  // the GPU contexts, the pinned batches and the input mapping go away on a helper thread while the output files are written
+  // (0.13-0.34 s of cudaFree / cudaFreeHost that nothing below depends on)
+  std::thread teardown([&] {
+    destroy_all();
+    hb.clear();
+    if (fmap && mapped) munmap((void*)fmap, fsize);
+  });
+  struct TeardownJoin { std::thread& t; ~TeardownJoin() { if (t.joinable()) t.join(); } } teardown_join{teardown};
   fclose(outs.rows);
   fclose(outs.feat);
-  const auto t_loop_end = clk::now();
 
   // quants_mat_cols.txt (src/quant.rs:1786-1809)
   {
@@ -863,7 +993,7 @@ int quantify_impl(const afqh_quant_opts& o) {
         if (i >= outs.mtx_chunks.size()) return;
         const size_t e = std::min(i + 16, outs.mtx_chunks.size());
         for (size_t j = i; j < e; ++j) {
-          const std::string& c = outs.mtx_chunks[j];
+          const TextBuf& c = outs.mtx_chunks[j];
           size_t done = 0;
           while (done < c.size()) {
             const ssize_t w = pwrite(mfd, c.data() + done, c.size() - done, (off_t)(offs[j] + done));
@@ -961,11 +1091,12 @@ int quantify_impl(const afqh_quant_opts& o) {
     fwrite(js.data(), 1, js.size(), fj);
     fclose(fj);
   }
+  const auto t_written = clk::now();
+  teardown.join();
   if (getenv("AFQ_TIMING")) {
-    const double tail = secs(t_loop_end, clk::now());
-    fprintf(stderr, "[afq timing] cells %llu records %llu threads %u | setup %.3f s (t2g %.3f, afq_create %.3f) | pipeline %.3f s (chunk index %.3f, parse %.3f, afq_submit %.3f, afq_wait %.3f, text formatting %.3f) | teardown %.3f s | final writes %.3f s\n",
+    fprintf(stderr, "[afq timing] cells %llu records %llu threads %u | setup %.3f s (t2g %.3f, afq_create %.3f) | pipeline %.3f s (chunk index %.3f, parse %.3f, afq_submit %.3f, afq_wait %.3f, text formatting %.3f) | final writes %.3f s | teardown (in the background of the writes) %.3f s beyond them\n",
             (unsigned long long)cells_seen, (unsigned long long)total_records, n_threads, secs(t_entry, t_begin), secs(t_t2g0, t_t2g1), secs(t_create0, t_begin),
-            secs(t_begin, t_td0), t_walk, t_parse, t_submit, t_wait, t_format, secs(t_td0, t_loop_end), tail);
+            secs(t_begin, t_td0), t_walk, t_parse, t_submit, t_wait, t_format, secs(t_td0, t_written), secs(t_written, clk::now()));
   }
   return 0;
 }
@@ -1205,6 +1336,149 @@ int afqh_write_collated_rad(const char* dir, uint64_t n_cells, const uint64_t* c
   j = fopen((d + "/generate_permit_list.json").c_str(), "wb");
   if (!j) return fail("cannot create generate_permit_list.json");
   fputs("{\n  \"velo_mode\": false,\n  \"max-ambig-record\": 8\n}\n", j); fclose(j);
+  return 0;
+}
+
+// The two host stages of `quant` WITHOUT a GPU (tests / scripts/host_stage_bench.py): the chunk index walk + parse_batch
+// (the product's parser, into ordinary memory) over every batch of the file, and consume() — the text formatting of the
+// rows / featureDump / matrix body — on a synthetic result of the same shape (per cell ~1/8 of its records as non-zeros,
+// ascending columns, counts 1..7; every `frac_every`-th value a non-integer). Reports wall seconds of both stages and
+// FNV checksums of the parsed arrays in file order (the same sums afqh_rad_summary computes with its own loop).
+int afqh_host_stage_bench(const char* rad_path, uint32_t n_threads, uint32_t frac_every, afqh_stage_info* out, char* err, size_t errlen) {
+  auto fail = [&](const std::string& m) { if (err && errlen) { strncpy(err, m.c_str(), errlen - 1); err[errlen - 1] = 0; } return 1; };
+  if (!rad_path || !out) return fail("null argument");
+  memset(out, 0, sizeof(*out));
+  g_plain_host_memory = true;
+  struct Restore { ~Restore() { g_plain_host_memory = false; } } restore;
+  try {
+    FILE* f = fopen(rad_path, "rb");
+    if (!f) return fail(std::string("cannot open ") + rad_path);
+    Reader rd(f);
+    RadPrelude pre;
+    std::string perr;
+    if (!parse_prelude(rd, pre, perr)) { fclose(f); return fail("RAD prelude: " + perr); }
+    RecordLayout lay;
+    if (!make_layout(pre, lay, perr)) { fclose(f); return fail(perr); }
+    const uint64_t body_start = rd.pos();
+    fclose(f);
+    const TagValue* cbl = pre.file_tag("cblen");
+    const TagValue* ul = pre.file_tag("ulen");
+    const unsigned bc_len = cbl ? (unsigned)cbl->u : 16;
+    const unsigned umi_len = ul ? (unsigned)ul->u : (unsigned)(4 * lay.umi_size);
+    const int fd = open(rad_path, O_RDONLY);
+    struct stat st {};
+    if (fd < 0 || fstat(fd, &st) != 0) { if (fd >= 0) close(fd); return fail("cannot open the file"); }
+    const uint64_t fsize = (uint64_t)st.st_size;
+    const unsigned char* fmap = fsize ? (const unsigned char*)mmap(nullptr, fsize, PROT_READ, MAP_PRIVATE, fd, 0) : nullptr;
+    close(fd);
+    if (fsize && fmap == MAP_FAILED) return fail("mmap failed");
+    struct Unmap { const unsigned char* p; uint64_t n; ~Unmap() { if (p) munmap((void*)p, n); } } unmap{fmap, fsize};
+    const unsigned nt = std::max(2u, std::min(n_threads < 2 ? 2u : n_threads, 128u));
+    Pool pool(nt / 2), fmt_pool(nt - nt / 2);
+    using clk = std::chrono::steady_clock;
+    auto secs = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+    HostBatch b;
+    b.pack24 = ul && umi_len <= 12 && lay.umi_size <= 4 && pre.ref_names.size() < (1u << 24) && !getenv("AFQ_NO_PACK24");
+    out->pack24 = b.pack24 ? 1 : 0;
+    Outputs outs;
+    outs.rows = fopen("/dev/null", "wb"); outs.feat = fopen("/dev/null", "wb");
+    UnmappedCounts unmapped;
+    uint64_t hu = 0xCBF29CE484222325ull, hr = hu, hn = hu;
+    auto mix = [](uint64_t& h, uint64_t v) { h = (h ^ v) * 0x100000001B3ull; };
+    const uint32_t n_cols = (uint32_t)std::max<size_t>(1, pre.ref_names.size());
+    std::vector<uint64_t> row_ptr;
+    std::vector<uint32_t> col, num_expr, num_over;
+    std::vector<float> val, sum_umi, max_umi;
+    std::vector<uint8_t> flags;
+    auto flush = [&]() {
+      if (b.n_cells() == 0) return;
+      std::string pf;
+      auto t0 = clk::now();
+      parse_batch(b, lay, pool, pf);
+      out->parse_s += secs(t0, clk::now());
+      if (!pf.empty()) throw Fail{pf};
+      // (the product parses into pinned buffers it re-uses and a file it has walked: a second pass over the same batch, with
+      // input and output pages mapped, is the steady-state cost of the loop itself)
+      t0 = clk::now();
+      parse_batch(b, lay, pool, pf);
+      out->parse_warm_s += secs(t0, clk::now());
+      for (uint64_t r = 0; r < b.n_rec; ++r) {
+        uint32_t u;
+        if (b.pack24) { const uint8_t* d = b.umi24.p + 3 * r; u = d[0] | (d[1] << 8) | (d[2] << 16); } else u = b.umi.p[r];
+        mix(hu, u);
+        mix(hn, b.wide_na ? b.ref_off.p[r + 1] - b.ref_off.p[r] : b.na8.p[r]);
+      }
+      for (uint64_t a = 0; a < b.n_ref; ++a) {
+        uint32_t id;
+        if (b.pack24) { const uint8_t* d = b.refs24.p + 3 * a; id = d[0] | (d[1] << 8) | (d[2] << 16); } else id = b.refs.p[a];
+        mix(hr, id);
+      }
+      out->n_records += b.n_rec; out->n_alignments += b.n_ref; out->n_cells += b.n_cells();
+      // the synthetic result of this batch
+      const uint64_t nc = b.n_cells();
+      row_ptr.assign(nc + 1, 0); num_expr.assign(nc, 0); num_over.assign(nc, 0); sum_umi.assign(nc, 0); max_umi.assign(nc, 0); flags.assign(nc, 0);
+      for (uint64_t c = 0; c < nc; ++c) {
+        const uint32_t k = std::min<uint32_t>(b.chunks[c].nrec / 8 + 1, n_cols);
+        num_expr[c] = k; row_ptr[c + 1] = row_ptr[c] + k;
+      }
+      col.resize(row_ptr[nc]); val.resize(row_ptr[nc]);
+      for (uint64_t c = 0; c < nc; ++c) {
+        const uint32_t k = num_expr[c];
+        const uint32_t stride = std::max(1u, n_cols / k);
+        float s = 0, m = 0;
+        for (uint32_t j = 0; j < k; ++j) {
+          const uint64_t e = row_ptr[c] + j;
+          col[e] = j * stride;
+          float v = (float)(1 + (e * 2654435761ull >> 7) % 7);
+          if (frac_every && e % frac_every == 0) v += 1.0f / (float)(2 + e % 5);
+          val[e] = v; s += v; m = v > m ? v : m;
+        }
+        sum_umi[c] = s; max_umi[c] = m;
+      }
+      afq_result r{};
+      r.n_cells = nc; r.nnz = row_ptr[nc]; r.row_ptr = row_ptr.data(); r.col = col.data(); r.val = val.data();
+      r.sum_umi = sum_umi.data(); r.max_umi = max_umi.data(); r.num_expr = num_expr.data(); r.num_over_mean = num_over.data(); r.flags = flags.data();
+      t0 = clk::now();
+      consume(b, r, bc_len, unmapped, outs, fmt_pool);
+      out->format_s += secs(t0, clk::now());
+      for (auto& c : outs.mtx_chunks) {     // FNV-1a over the whole matrix body (outside the timed stages)
+        out->mtx_bytes += c.size();
+        uint64_t h = out->mtx_sum ? out->mtx_sum : 0xCBF29CE484222325ull;
+        for (size_t i = 0; i < c.size(); ++i) h = (h ^ (unsigned char)c[i]) * 0x100000001B3ull;
+        out->mtx_sum = h;
+      }
+      outs.mtx_chunks.clear();
+      out->nnz += r.nnz;
+    };
+    const unsigned char* p = fmap + body_start;
+    const unsigned char* fend = fmap + fsize;
+    const size_t rec_fixed = 4 + lay.read_bytes;
+    const uint64_t batch_records = 16ull << 20;
+    for (uint64_t ch = 0; ch < pre.num_chunks; ++ch) {
+      const auto tw = clk::now();
+      if (p + 8 > fend) throw Fail{"truncated chunk header"};
+      uint32_t nbytes, nrec;
+      memcpy(&nbytes, p, 4); memcpy(&nrec, p + 4, 4);
+      if (nbytes < 8 || p + nbytes > fend || nrec == 0) throw Fail{"corrupt chunk header"};
+      const uint64_t payload = (uint64_t)nbytes - 8;
+      if (payload < (uint64_t)nrec * rec_fixed || lay.aln_bytes == 0 || (payload - (uint64_t)nrec * rec_fixed) % lay.aln_bytes != 0) throw Fail{"record overruns its chunk"};
+      ChunkInfo ci;
+      ci.body = p + 8; ci.body_bytes = (uint32_t)payload; ci.nrec = nrec;
+      ci.n_aln = (uint32_t)((payload - (uint64_t)nrec * rec_fixed) / lay.aln_bytes);
+      ci.bc = 0;
+      memcpy(&ci.bc, ci.body + 4 + lay.bc_off, lay.bc_size);
+      p += nbytes;
+      out->walk_s += secs(tw, clk::now());
+      ci.rec_off = b.n_rec; ci.ref_off = b.n_ref;
+      b.n_rec += nrec; b.n_ref += ci.n_aln;
+      b.chunks.push_back(ci);
+      if (b.n_rec >= batch_records || b.n_ref >= (3ull << 30)) { flush(); b.chunks.clear(); b.first_cell = out->n_cells; b.n_rec = b.n_ref = 0; }
+    }
+    flush();
+    fclose(outs.rows); fclose(outs.feat);
+    out->sum_umi = hu; out->sum_refs = hr; out->sum_na = hn;
+    out->threads = nt;
+  } catch (const Fail& e) { return fail(e.msg); }
   return 0;
 }
 

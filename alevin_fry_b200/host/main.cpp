@@ -8,6 +8,7 @@
 #include <string>
 #include <thread>
 #include <vector>
+#include <unistd.h>
 
 #include "../../include/afq_host.h"
 
@@ -155,5 +156,8 @@ int main(int argc, char** argv) {
   o.devices = devices.empty() ? nullptr : devices.c_str();
   char err[1024] = {0};
   if (afqh_quantify(&o, err, sizeof err) != 0) { fprintf(stderr, "Error: %s\n", err); return 1; }
-  return 0;
+  // every output file is closed: leave without running the static destructors (the CUDA runtime's process teardown costs
+  // 0.2-0.3 s that a command-line tool has no use for)
+  fflush(stdout); fflush(stderr);
+  _exit(0);
 }

@@ -80,6 +80,17 @@ typedef struct afqh_rad_info {
 } afqh_rad_info;
 int afqh_rad_summary(const char* rad_path, afqh_rad_info* info, char* err, size_t errlen);
 
+/* CPU-only run of the two host stages of `quant` (chunk index + the product's parallel parser; the parallel text formatting on
+ * a synthetic result of the same shape): wall seconds per stage, and FNV checksums (as afqh_rad_summary) of the PARSED arrays —
+ * UMI and alignment count of every record, reference id of every alignment, in file order.       */
+typedef struct afqh_stage_info {
+  uint64_t n_cells, n_records, n_alignments, nnz, mtx_bytes, mtx_sum;
+  uint64_t sum_umi, sum_refs, sum_na;
+  double walk_s, parse_s, format_s, parse_warm_s;
+  uint32_t threads, pack24;
+} afqh_stage_info;
+int afqh_host_stage_bench(const char* rad_path, uint32_t n_threads, uint32_t frac_every, afqh_stage_info* out, char* err, size_t errlen);
+
 /* Snappy FRAMING format (map.collated.rad.sz of `collate --compress`; the reference reads it with
  * snap::read::FrameDecoder, src/quant.rs:373-395) -> plain bytes. *out is malloc'ed (free with
  * afqh_free). Returns 0 on success.                                                          */

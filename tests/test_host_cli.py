@@ -217,6 +217,72 @@ def test_rad_reader_on_reference_layout_fixture(tmp_path, bc_len, umi_len):
     assert (info.sum_bc, info.sum_umi, info.sum_refs) == (hb, hu, hr)
 
 
+@pytest.mark.parametrize("layout", ["plain-pack24", "plain-u32", "extra-tags", "wide-umi"])
+def test_product_parser_against_the_reference_walk(tmp_path, layout, monkeypatch):
+    # the quantifier's own parallel parser (parse_batch: the 24-bit fast path with 4-byte stores and unconditional short-record
+    # copies, and the general path) run without a GPU by afqh_host_stage_bench, against the independent record walk of
+    # afqh_rad_summary and the values the fixture was written from: records of 1..4, of 5..9 and of 300 alignments (beyond the
+    # 1-byte alignment counts), chunks that end in short and in long records
+    import rad_fixture
+    rng = np.random.default_rng(17)
+    n_refs = 5000
+    names = [f"t{i}" for i in range(n_refs)]
+    umi_len = 16 if layout == "wide-umi" else 12
+    cells = _fixture_cells(rng, 40, n_refs, 16, umi_len, min_recs=1, max_recs=60)
+    for c in (3, 11, 39):       # long records, one of them the last of its chunk, one in the last chunk of the file
+        bc, recs = cells[c]
+        for na in (7, 300, 9):
+            refs = sorted(set(int(x) for x in rng.integers(0, n_refs, size=na)))
+            recs.insert(len(recs) if na == 9 else 1, (int(rng.integers(0, 1 << 20)), refs, [True] * len(refs)))
+    p = str(tmp_path / "map.collated.rad")
+    kw = {}
+    if layout == "extra-tags":
+        kw = dict(extra_read_tags=[(("frag_q", "u8"), 7)], extra_aln_tags=[(("pos", "u32"), 5)], extra_first=True)
+    rad_fixture.write_collated_rad(p, names, cells, 16, umi_len, **kw)
+    if layout == "plain-u32":
+        monkeypatch.setenv("AFQ_NO_PACK24", "1")
+    hb, hu, hr, nrec, naln = _expect(cells)
+    ref = host.rad_summary(p)
+    got = host.host_stage_bench(p, 4, 3)
+    assert got.pack24 == (1 if layout in ("plain-pack24", "extra-tags") else 0)
+    assert (got.n_cells, got.n_records, got.n_alignments) == (40, nrec, naln) == (ref.num_chunks, ref.n_records, ref.n_alignments)
+    assert (got.sum_umi, got.sum_refs) == (hu, hr) == (ref.sum_umi, ref.sum_refs)
+    assert got.sum_na == rad_fixture.fnv([len(r[1]) for _, recs in cells for r in recs])
+    assert got.nnz > 0 and got.mtx_bytes > 0
+
+
+def test_matrix_text_formatter_matches_printf(tmp_path):
+    # the fast "row col val" formatter of the matrix body (two-digit table, integer path for whole numbers, shortest
+    # round-trip digits otherwise) against Python's own formatting of the same synthetic result
+    spec = synth.SynthSpec(n_genes=50, fixed_reads=40)
+    b, bcs, d, _ = make_input(tmp_path, spec, 30)
+    a = host.host_stage_bench(os.path.join(d, "map.collated.rad"), 2, 0)
+    c = host.host_stage_bench(os.path.join(d, "map.collated.rad"), 4, 0)
+    assert (a.nnz, a.mtx_bytes, a.mtx_sum) == (c.nnz, c.mtx_bytes, c.mtx_sum)      # independent of the thread count
+    # re-create the synthetic result of afqh_host_stage_bench and format it here (every 3rd value a non-integer: Rust's `{}`
+    # prints the shortest digits that round-trip the f32, which is what numpy's repr of a float32 gives)
+    n_cols = spec.num_refs
+    for frac_every in (0, 3):
+        got = host.host_stage_bench(os.path.join(d, "map.collated.rad"), 2, frac_every)
+        lines, e = [], 0
+        for cell in range(30):
+            nrec = int(b.cell_rec_offsets[cell + 1] - b.cell_rec_offsets[cell])
+            k = min(nrec // 8 + 1, n_cols)
+            stride = max(1, n_cols // k)
+            for j in range(k):
+                v = np.float32(1 + (((e * 2654435761) & 0xFFFFFFFFFFFFFFFF) >> 7) % 7)
+                if frac_every and e % frac_every == 0:
+                    v = np.float32(v + np.float32(1.0) / np.float32(2 + e % 5))
+                text = str(int(v)) if float(v) == int(v) else np.format_float_positional(v, unique=True, trim="-")
+                lines.append(f"{cell + 1} {j * stride + 1} {text}\n")
+                e += 1
+        txt = "".join(lines).encode()
+        h = 0xCBF29CE484222325
+        for ch in txt:
+            h = ((h ^ ch) * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
+        assert (got.nnz, got.mtx_bytes, got.mtx_sum) == (len(lines), len(txt), h), frac_every
+
+
 def test_rad_reader_skips_extra_tags_of_every_type(tmp_path):
     # tags a mapper may add around the standard ones: string / array / float file tags (e.g. `known_rad_type`,
     # tests/multi_barcode_integration.rs:72-75), extra read-level and alignment-level tags before or after b / u / refid
