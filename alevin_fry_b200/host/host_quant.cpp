@@ -266,6 +266,29 @@ int resolution_code(const std::string& r) {
   return -1;
 }
 
+// Page tables of the mapped input, filled ahead of the chunk walk by a helper thread (MADV_POPULATE_READ, Linux >= 5.14) instead
+// of one minor fault per chunk header on the walking thread (1.5 us per chunk: 0.16 s of the 0.58 s pipeline on 100 k cells).
+// Best effort: where the call is not supported the walk faults the pages in as before.
+struct Prefault {
+  std::thread th;
+  std::atomic<bool> stop{false};
+  void start(const unsigned char* base, uint64_t size) {
+#ifdef MADV_POPULATE_READ
+    if (!base || !size || getenv("AFQ_NO_PREFAULT")) return;
+    th = std::thread([this, base, size] {
+      const uint64_t step = 32ull << 20;
+      const uintptr_t a0 = (uintptr_t)base & ~(uintptr_t)4095;
+      const uintptr_t a1 = (uintptr_t)base + size;
+      for (uintptr_t a = a0; a < a1 && !stop.load(std::memory_order_relaxed); a += step)
+        if (madvise((void*)a, (size_t)std::min<uint64_t>(step, a1 - a), MADV_POPULATE_READ) != 0) return;
+    });
+#else
+    (void)base; (void)size;
+#endif
+  }
+  ~Prefault() { stop = true; if (th.joinable()) th.join(); }
+};
+
 // afqh_host_stage_bench (no GPU: the host stages alone) keeps the batches in ordinary memory
 static bool g_plain_host_memory = false;
 
@@ -794,6 +817,8 @@ int quantify_impl(const afqh_quant_opts& o) {
     if (fsize && fmap == MAP_FAILED) { destroy_all(); fclose(outs.rows); fclose(outs.feat); throw Fail{"mmap failed for " + rad_path}; }
     madvise((void*)fmap, fsize, MADV_SEQUENTIAL);
   }
+  Prefault prefault;
+  if (mapped) prefault.start(fmap + body_start, fsize - body_start);
 
   // half of the threads parse the next batch while the other half format the previous result
   const unsigned n_threads = std::max(2u, std::min(o.num_threads < 2 ? 2u : o.num_threads, 128u));
@@ -1373,6 +1398,8 @@ int afqh_host_stage_bench(const char* rad_path, uint32_t n_threads, uint32_t fra
     close(fd);
     if (fsize && fmap == MAP_FAILED) return fail("mmap failed");
     struct Unmap { const unsigned char* p; uint64_t n; ~Unmap() { if (p) munmap((void*)p, n); } } unmap{fmap, fsize};
+    Prefault prefault;
+    if (fmap) prefault.start(fmap + body_start, fsize - body_start);
     const unsigned nt = std::max(2u, std::min(n_threads < 2 ? 2u : n_threads, 128u));
     Pool pool(nt / 2), fmt_pool(nt - nt / 2);
     using clk = std::chrono::steady_clock;
