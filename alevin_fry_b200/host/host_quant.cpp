@@ -677,6 +677,14 @@ int quantify_impl(const afqh_quant_opts& o) {
   }
   Reader rd(f);
   RadPrelude pre;
+  // Hardware work queues: libafq asks for 32 when it is loaded (a host that runs batches ahead of the GPU needs them, afq_cuda.cu),
+  // but a context with 32 queues takes 1-2 s longer to create (r2af: 0.58 s -> 1.65 s of set-up on one box) and this tool is
+  // bound by its own parse / format stages, not by the GPU: it keeps CUDA's default of 8 unless AFQ_HW_QUEUES says otherwise.
+  // (Must happen before the first CUDA call, i.e. before the warm-up thread below.)
+  {
+    const char* q = getenv("AFQ_HW_QUEUES");
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", (q && atoi(q) > 0) ? q : "8", 1);
+  }
   // the CUDA context comes up (~0.3-0.5 s) in the background while the prelude and the t2g map are parsed
   std::thread cuda_warm([] { void* w = nullptr; if (afq_host_alloc(&w, 4096) == AFQ_OK) afq_host_free(w); });
   struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } warm_join{cuda_warm};
