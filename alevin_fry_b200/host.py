@@ -19,7 +19,7 @@ class _Opts(C.Structure):
                 ("resolution", C.c_char_p), ("pug_exact_umi", C.c_int32), ("sa_model", C.c_char_p),
                 ("small_thresh", C.c_uint64), ("large_graph_thresh", C.c_uint64), ("filter_list", C.c_char_p),
                 ("cmdline", C.c_char_p), ("version", C.c_char_p), ("device", C.c_int32), ("batch_records", C.c_uint64),
-                ("devices", C.c_char_p)]
+                ("devices", C.c_char_p), ("process_exits", C.c_int32)]
 
 
 class _InferOpts(C.Structure):

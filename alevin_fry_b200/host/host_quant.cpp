@@ -13,6 +13,7 @@
 #include <deque>
 #include <fcntl.h>
 #include <functional>
+#include <memory>
 #include <mutex>
 #include <sys/mman.h>
 #include <thread>
@@ -835,7 +836,8 @@ int quantify_impl(const afqh_quant_opts& o) {
   // three host batches in flight per GPU (the context's slot count); batch k goes to context k mod D and the
   // consumer collects in submission order, so the rows of the one output matrix stay in chunk order
   const int NB = 3 * D;
-  std::vector<HostBatch> hb((size_t)NB);
+  auto hb_holder = std::make_unique<std::vector<HostBatch>>((size_t)NB);   // (on the heap: left behind when the process exits anyway)
+  std::vector<HostBatch>& hb = *hb_holder;
   std::vector<int> dev_of((size_t)NB, 0);
   uint64_t batch_seq = 0;
   // 24-bit wire arrays whenever the chemistry allows: UMI <= 12 bases and fewer than 2^24 targets
@@ -982,6 +984,7 @@ int quantify_impl(const afqh_quant_opts& o) {
   // the GPU contexts, the pinned batches and the input mapping go away on a helper thread while the output files are written
   // (0.13-0.34 s of cudaFree / cudaFreeHost that nothing below depends on)
   std::thread teardown([&] {
+    if (o.process_exits) { (void)hb_holder.release(); return; }      // the operating system reclaims everything in a moment
     destroy_all();
     hb.clear();
     if (fmap && mapped) munmap((void*)fmap, fsize);

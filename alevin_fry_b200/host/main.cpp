@@ -155,6 +155,7 @@ int main(int argc, char** argv) {
   o.cmdline = cmdline.c_str(); o.version = VERSION; o.device = (int)device;
   o.devices = devices.empty() ? nullptr : devices.c_str();
   char err[1024] = {0};
+  o.process_exits = 1;
   if (afqh_quantify(&o, err, sizeof err) != 0) { fprintf(stderr, "Error: %s\n", err); return 1; }
   // every output file is closed: leave without running the static destructors (the CUDA runtime's process teardown costs
   // 0.2-0.3 s that a command-line tool has no use for)

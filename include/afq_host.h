@@ -35,6 +35,9 @@ typedef struct afqh_quant_opts {          /* mirrors QuantOpts (src/prog_opts.rs
                                              the device batches round-robin to one context per GPU and ONE matrix is
                                              written in chunk order — the reference's one-reader / N-workers / one-matrix
                                              shape (src/quant.rs:1567-1575, 1678-1784, 1811-1847)                        */
+  int32_t process_exits;                  /* the caller's process ends right after this call (the CLI): the GPU contexts and
+                                             the pinned buffers are left to the operating system instead of being torn down
+                                             (0.4-0.5 s of cudaFree / cudaFreeHost on a 100 k-cell run)                 */
 } afqh_quant_opts;
 
 /* Runs the whole quant stage. Returns 0 on success; on failure writes a message to err.    */
