@@ -301,7 +301,9 @@ struct Pinned {  // growable pinned array (afq_host_alloc)
   void release(T* q) { if (q) { if (plain) free(q); else afq_host_free(q); } }
   void reserve(size_t want) {
     if (want <= cap) return;
-    size_t nc = cap ? cap : 1024;
+    // batches close one cell past the record budget, so their sizes differ by a few per cent: the first allocation carries
+    // 1/8 of head-room and a second one (pinning 100+ MB costs ~50 ms) is normally never needed
+    size_t nc = cap ? cap : want + want / 8 + 1024;
     while (nc < want) nc = nc + nc / 2 + 1024;
     void* q = nullptr;
     const bool was_plain = plain;
