@@ -321,7 +321,8 @@ def measure_config(args, name, cells, res, ctx):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1) / steps
-    launches = (q.launch_count - launches0) // max(steps, 1)
+    launches_total = q.launch_count - launches0                 # kernels of libafq launched inside the timed region
+    launches = launches_total // max(steps, 1)
     prof = q.profile()
     q.set_profiling(False)
     q.device_finish(stream)
@@ -463,7 +464,7 @@ def measure_config(args, name, cells, res, ctx):
                 "ms_per_step": e2e_s * 1e3, "host_batches_per_step": nb, "pipeline": "drained every step" if args.e2e_drain else "3 batches in flight, carried across steps, drained before the closing barrier",
                 "input_encoding": ("rec_umi24 + " if use_p24 else "rec_umi32 + ") + ("rec_na8 + " if use_na8 else "rec_ref_offsets + ") +
                                   ("refs24" if use_p24 else "refs (u32)")},
-        "gpu_launches": int(launches) + 0, "clocks": clocks,
+        "gpu_launches": int(launches_total), "gpu_launches_per_step": int(launches), "clocks": clocks,
     }
     if census is not None:
         out["tie_census"] = census
@@ -535,7 +536,8 @@ def main():
         line = {"metric": METRIC, "value": hl["value"], "unit": "cells/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": hl["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": hl["config"], "roofline": hl["roofline"],
-                "cpu_baseline": hl["cpu_baseline"], "e2e": hl["e2e"], "gpu_launches": hl["gpu_launches"], "clocks": hl["clocks"]}
+                "cpu_baseline": hl["cpu_baseline"], "e2e": hl["e2e"], "gpu_launches": hl["gpu_launches"], "gpu_launches_per_step": hl["gpu_launches_per_step"],
+                "clocks": hl["clocks"]}
         if hl.get("assembly"):
             line["assembly"] = hl["assembly"]
         if len(names) > 1:
