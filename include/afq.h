@@ -79,7 +79,12 @@ typedef struct afq_config {
  * All pointers are host pointers for afq_submit and device pointers for
  * afq_quant_device. Records of cell c are [cell_rec_offsets[c], cell_rec_offsets[c+1]).
  * `refs` hold transcript ids with the orientation bit already cleared, in the order the
- * mapper emitted them (ascending — src/eq_class.rs:859 relies on it).                   */
+ * mapper emitted them (ascending — src/eq_class.rs:859 relies on it).
+ * Every record is expected to carry at least one alignment: the reference's RAD writer asserts it
+ * (src/convert.rs:134) and its graph / EM resolvers index label[0], i.e. panic otherwise. cr-like and
+ * trivial skip an alignment-free record here (as the reference's tiny-cell path does, src/quant.rs:505);
+ * for the other resolutions the result of such a batch is unspecified — the callers that read files
+ * (afqh_quantify) reject it as a corrupt collated RAD before it gets here.                          */
 typedef struct afq_batch {
   uint64_t first_cell_index;        /* chunk index of cell 0 (src/quant.rs:734)          */
   uint64_t n_cells;
