@@ -81,8 +81,8 @@ typedef struct afq_config {
  * `refs` hold transcript ids with the orientation bit already cleared, in the order the
  * mapper emitted them (ascending — src/eq_class.rs:859 relies on it).
  * Every record is expected to carry at least one alignment: the reference's RAD writer asserts it
- * (src/convert.rs:134) and its graph / EM resolvers index label[0], i.e. panic otherwise. cr-like and
- * trivial skip an alignment-free record here (as the reference's tiny-cell path does, src/quant.rs:505);
+ * (src/convert.rs:132) and its graph / EM resolvers index label[0], i.e. panic otherwise. cr-like and
+ * trivial skip an alignment-free record here (as the reference's tiny-cell path does, src/quant.rs:495);
  * for the other resolutions the result of such a batch is unspecified — the callers that read files
  * (afqh_quantify) reject it as a corrupt collated RAD before it gets here.                          */
 typedef struct afq_batch {
