@@ -40,6 +40,16 @@ def _worker(rank, world, port, n_cells, out):
     whole = oracle_lib.oracle_quant(opts, t2g, synth.generate(spec, 0, n_cells, n_threads=2), n_threads=2)
     assert torch.equal(rp2, rp)
     assert np.array_equal(cols.numpy().astype(np.uint32), whole.col) and np.array_equal(vals.numpy(), whole.val)
+    # the form bench.py times (compact=False): the gathered payload stays padded to the largest rank, rank r's entries at
+    # r * stride; staging arrays longer than the stride are sent as views (no padded copy), as the device API's are
+    cap = int(mine.nnz) + 1000 + 17 * rank
+    col_cap = torch.full((cap,), -7, dtype=torch.int32); col_cap[:mine.nnz] = torch.from_numpy(mine.col.astype(np.int32))
+    val_cap = torch.full((cap,), -7.0, dtype=torch.float32); val_cap[:mine.nnz] = torch.from_numpy(mine.val)
+    rp3, ac, av, stride, nnz_r = shard.assemble_csr(torch.from_numpy(mine.num_expr.astype(np.int32)), col_cap, val_cap, n_cells, compact=False)
+    assert torch.equal(rp3, rp) and int(nnz_r.sum()) == int(whole.nnz) and ac.numel() == world * stride
+    got_c = torch.cat([ac[r * stride: r * stride + int(nnz_r[r])] for r in range(world)])
+    got_v = torch.cat([av[r * stride: r * stride + int(nnz_r[r])] for r in range(world)])
+    assert np.array_equal(got_c.numpy().astype(np.uint32), whole.col) and np.array_equal(got_v.numpy(), whole.val)
     if rank == 0:
         out.put((rp.numpy().tolist() == whole.row_ptr.astype(np.int64).tolist(), int(rp[-1]), int(whole.nnz)))
     dist.barrier()
