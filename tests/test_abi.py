@@ -71,3 +71,24 @@ def test_product_never_references_the_oracle():
                 if re.search(r"oracle_lib|libafq_oracle|afq_oracle_|oracle/", txt):
                     bad.append(os.path.join(dp, f))
     assert not bad, f"product files reference the oracle: {bad}"
+
+
+def test_host_header_symbols_exported_and_struct_layouts_match(tmp_path):
+    # include/afq_host.h: every afqh_* function is exported by libafq_host.so, and the ctypes mirrors in alevin_fry_b200/host.py
+    # have the sizes the C compiler gives the header's structs
+    import subprocess
+    from alevin_fry_b200 import host
+    hdr = open(os.path.join(ROOT, "include", "afq_host.h")).read()
+    hdr_nc = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = sorted(set(re.findall(r"\b(afqh_[a-z_0-9]+)\s*\(", hdr_nc)))
+    assert "afqh_quantify" in names and "afqh_infer" in names and "afqh_host_stage_bench" in names
+    l = host.lib()
+    for n in names:
+        assert hasattr(l, n), f"libafq_host.so does not export {n}"
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "%s"\nint main(void) { printf("%%zu %%zu %%zu %%zu", sizeof(afqh_quant_opts), sizeof(afqh_infer_opts), '
+                   'sizeof(afqh_rad_info), sizeof(afqh_stage_info)); return 0; }\n' % os.path.join(ROOT, "include", "afq_host.h"))
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-o", str(exe), str(src)], check=True)
+    sizes = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert sizes == [C.sizeof(host._Opts), C.sizeof(host._InferOpts), C.sizeof(host.RadInfo), C.sizeof(host.StageInfo)]
