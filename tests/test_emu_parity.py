@@ -320,6 +320,11 @@ def test_emu_arena_pools_planned_on_the_device(res, monkeypatch):
     monkeypatch.setenv("AFQ_PS_LIMIT_WORDS", "3000")                        # ... and with cells handed back to k_gene_eqc
     check(opts_for(spec, res), synth.tid_to_gid(spec), b.slice_cells(0, 1), res)
     monkeypatch.delenv("AFQ_PS_LIMIT_WORDS")
+    if res != "parsimony":      # the back end's other shapes plan their arenas with the same arithmetic
+        for k, v in (("AFQ_NO_EM_SPLIT", "1"), ("AFQ_BACK_MAX_TIER", "2")):
+            monkeypatch.setenv(k, v)
+            check(opts_for(spec, res), synth.tid_to_gid(spec), b.slice_cells(0, 1), res + "/" + k)
+            monkeypatch.delenv(k)
     # a pool that holds no arena for the largest cell: the batch is flagged, never silently wrong (the host API re-runs it)
     monkeypatch.setenv("AFQ_EMU_POOL_WORDS", "2000")
     with pytest.raises(RuntimeError, match="pool of a global-arena kernel"):
