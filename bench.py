@@ -160,10 +160,14 @@ def reference_leg(args, name, cells, res, steps, warmup, step_seconds):
     dt = (time.perf_counter() - t0) / max(steps, 1)
     v = n_sample / dt
     desc = f"first {n_sample} cells ({sample.n_records} records) of the workload per step, {steps} steps after {warmup} warm-up"
+    # the CPU path at ONE worker as well (the reference's `-t 2` = 1 reader + 1 worker, BASELINE's "1 thread"): a ~2 s sample
+    one = sample.slice_cells(0, int(max(64, min(n_sample, rate / max(cores, 1) * 2.0))))
+    t0 = time.perf_counter(); oracle_lib.oracle_quant(opts, t2g, one, n_threads=1); dt1 = time.perf_counter() - t0
     return {
         "value": v, "unit": "cells/s", "ms_per_step": dt * 1e3,
         "config": workload_config(synth, name, spec, cells, res, args.gpus),
         "cpu_baseline": {"value": v, "unit": "cells/s", "cores": cores, "kind": "port", "sample": desc,
+                         "one_worker": {"value": one.n_cells / dt1, "unit": "cells/s", "cores": 1, "sample": f"first {one.n_cells} cells, one pass"},
                          "note": "C++ restatement of the reference's Rust algorithm (reference not buildable here: no cargo/rustc)"},
         "e2e": {"value": v, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }

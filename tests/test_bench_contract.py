@@ -34,6 +34,7 @@ def test_reference_arm_line_has_the_contract_keys():
     assert j["value"] > 0 and j["ms_per_step"] > 0
     cb = j["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == j["value"] and "sample" in cb
+    assert cb["one_worker"]["cores"] == 1 and cb["one_worker"]["value"] > 0        # 1 worker beside all cores
     e = j["e2e"]
     assert e["value"] == j["value"] and e["unit"] == j["unit"] and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
     # (with --cells the other configurations are not measured; the default run adds other_configs C3 / C4 / C5)
